@@ -1,0 +1,173 @@
+// Small-matrix device routines shared by the SPD Gram kernel, the batched manifold operations and the acquisition
+// optimiser.  Everything is templated on the matrix size d (<= 8) so that the state lives in registers.
+#pragma once
+#include "common.cuh"
+
+namespace gabo {
+
+__host__ __device__ constexpr int tri_size(int d) { return d * (d + 1) / 2; }
+// per-point record written by gabo_spd_factor: [L (tri) | A = L^-1 (tri) | pad to an even count]
+__host__ __device__ constexpr int factor_stride(int d) { return ((2 * tri_size(d) + 1) / 2) * 2; }
+__host__ __device__ constexpr int tri_idx(int r, int c) { return r * (r + 1) / 2 + c; }  // c <= r
+
+// Mandel position of entry (r, c), r <= c: diagonal-by-diagonal layout of spd_utils_torch.py:181-187.
+__host__ __device__ constexpr int mandel_pos(int d, int r, int c) {
+    // k = c - r is the diagonal; diagonals 0..k-1 hold d, d-1, ..., d-k+1 entries
+    return (c - r) * d - ((c - r) * ((c - r) - 1)) / 2 + r;
+}
+
+// Cholesky X = L L^T and A = L^-1, fp64, packed lower-triangular row-major.  Returns false when a pivot is not
+// positive (torch.cholesky raises there, spd_utils_torch.py:87).  X is read through the accessor x(r, c), r >= c.
+template <int d, typename Acc>
+__device__ __forceinline__ bool chol_inv(Acc x, double (&L)[tri_size(d)], double (&A)[tri_size(d)]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+        double s = x(j, j);
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[tri_idx(j, k)], L[tri_idx(j, k)], s);
+        ok = ok && (s > 0.0);
+        const double ljj = sqrt(s);
+        const double inv = 1.0 / ljj;
+        L[tri_idx(j, j)] = ljj;
+        A[tri_idx(j, j)] = inv;
+#pragma unroll
+        for (int i = j + 1; i < d; ++i) {
+            double t = x(i, j);
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[tri_idx(i, k)], L[tri_idx(j, k)], t);
+            L[tri_idx(i, j)] = t * inv;
+        }
+    }
+    // A = L^-1 by forward substitution, column by column
+#pragma unroll
+    for (int j = 0; j < d; ++j) {
+#pragma unroll
+        for (int i = j + 1; i < d; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = j; k < i; ++k) t = fma(L[tri_idx(i, k)], A[tri_idx(k, j)], t);
+            A[tri_idx(i, j)] = -t * A[tri_idx(i, i)];
+        }
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One-sided (Hestenes) Jacobi on the columns of G (d x d): G V = U Sigma.  Works on the Cholesky-factor product
+// G = L_x^-1 L_y instead of the whitened matrix W = G G^T, which keeps high RELATIVE accuracy of the small
+// eigenvalues (error ~ eps * cond(G) = eps * sqrt(cond(W))).  On return the columns of G are u_k sigma_k and
+// lam[k] = sigma_k^2 are the eigenvalues of W; log/exp maps are then sum_k f(lam_k)/lam_k g_k g_k^T.
+// Converged rotations are skipped, so the result of a pair does not depend on how many extra sweeps its warp runs.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct JacobiTraits;
+
+template <>
+struct JacobiTraits<float> {
+    static constexpr int kMaxSweeps = 10;
+    static __device__ __forceinline__ float tol2() { return 3.6e-15f; }  // (6e-8)^2
+    static __device__ __forceinline__ void rotation(float a, float b, float c, float& cs, float& sn, float& t) {
+        const float zeta = (b - a) * rcp_approx(2.0f * c);
+        t = copysignf(1.0f, zeta) * rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.0f)));
+        const float h = fmaf(t, t, 1.0f);
+        const float y = rsqrt_approx(h);
+        cs = y * fmaf(-0.5f * h * y, y, 1.5f);  // one Newton step: |cs^2 (1+t^2) - 1| ~ 1 ulp
+        sn = t * cs;
+    }
+};
+
+template <>
+struct JacobiTraits<double> {
+    static constexpr int kMaxSweeps = 12;
+    static __device__ __forceinline__ double tol2() { return 1e-26; }  // (1e-13)^2
+    static __device__ __forceinline__ void rotation(double a, double b, double c, double& cs, double& sn, double& t) {
+        // The angle only has to be approximately the Jacobi angle (it sets the convergence rate, not the accuracy), so
+        // it is computed on the fp32 MUFU path; cs is then normalised in fp64 so that the rotation is orthogonal to 1e-16.
+        const float zf = static_cast<float>(b - a) * rcp_approx(2.0f * static_cast<float>(c));
+        const float tf = copysignf(1.0f, zf) * rcp_approx(fabsf(zf) + sqrt_approx(fmaf(zf, zf, 1.0f)));
+        t = static_cast<double>(tf);
+        cs = rsqrt(fma(t, t, 1.0));
+        sn = t * cs;
+    }
+};
+
+template <int d, typename T>
+__device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
+    using Tr = JacobiTraits<T>;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        T s = T(0);
+#pragma unroll
+        for (int r = 0; r < d; ++r) s = fma(G[r][k], G[r][k], s);
+        lam[k] = s;
+    }
+    for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < d - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < d; ++q) {
+                T c = T(0);
+#pragma unroll
+                for (int r = 0; r < d; ++r) c = fma(G[r][p], G[r][q], c);
+                const T a = lam[p], b = lam[q];
+                if (c * c > Tr::tol2() * a * b) {
+                    rotated = true;
+                    T cs, sn, t;
+                    Tr::rotation(a, b, c, cs, sn, t);
+#pragma unroll
+                    for (int r = 0; r < d; ++r) {
+                        const T gp = G[r][p], gq = G[r][q];
+                        G[r][p] = fma(cs, gp, -sn * gq);
+                        G[r][q] = fma(sn, gp, cs * gq);
+                    }
+                    const T c2 = cs * cs, tc2 = T(2) * t * c;
+                    lam[p] = c2 * (fma(t * t, b, a) - tc2);
+                    lam[q] = c2 * (fma(t * t, a, b) + tc2);
+                }
+            }
+        }
+        if (!__any_sync(__activemask(), rotated)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        T s = T(0);
+#pragma unroll
+        for (int r = 0; r < d; ++r) s = fma(G[r][k], G[r][k], s);
+        lam[k] = s;
+    }
+}
+
+// G = A * L for packed lower-triangular A (rows) and L, accumulated in fp64, returned in T.
+template <int d, typename T, typename AccA, typename AccL>
+__device__ __forceinline__ void tri_product(AccA A, AccL L, T (&G)[d][d]) {
+#pragma unroll
+    for (int r = 0; r < d; ++r) {
+#pragma unroll
+        for (int c = 0; c < d; ++c) {
+            if (c <= r) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = c; k <= r; ++k) s = fma(A(tri_idx(r, k)), L(tri_idx(k, c)), s);
+                G[r][c] = static_cast<T>(s);
+            } else {
+                G[r][c] = T(0);
+            }
+        }
+    }
+}
+
+// Reference tail (spd_utils_torch.py:108-120): eigenvalues rounded to fp32, log / square / sum / sqrt(+1e-15) in fp32.
+template <int d, typename T>
+__device__ __forceinline__ float ai_distance_from_eigs(const T (&lam)[d]) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        const float l = logf(static_cast<float>(lam[k]));
+        s = fmaf(l, l, s);
+    }
+    return sqrtf(s + 1e-15f);
+}
+
+}  // namespace gabo

@@ -1,0 +1,316 @@
+// SPD affine-invariant Gram (G3 + G4 + G5 of SURVEY.md section 8).
+//
+// Replaces vector_to_symmetric_matrix_mandel_torch (Riemannian_utils/spd_utils_torch.py:159-194, a Python loop over
+// matrices), affine_invariant_distance_torch (:53-120, one torch.symeig call per PAIR inside a Python loop, :109-110)
+// and the d^2 / exp passes of SpdAffineInvariantGaussianKernel.forward (kernel_utils/kernels_spd.py:90-100).
+//
+//   gabo_spd_factor  : per point, fp64: Mandel unpack -> Cholesky L -> A = L^-1          (O(N d^3), negligible)
+//   gabo_spd_ai_gram : per pair: G = A_i L_j (lower-triangular product, fp64 FMAs), one-sided Jacobi on G in
+//                      registers (fp32 or fp64), lambda = |g_k|^2, then the reference's fp32 tail
+//                      d = sqrt(sum log(lambda)^2 + 1e-15) and K = exp(-beta d^2).
+// One THREAD per pair: N^2 pairs give far more parallelism than the chip has lanes, so a per-thread register-resident
+// Jacobi needs no shuffles and no shared-memory traffic (the warp-cooperative form is used by the optimiser, where
+// parallelism is scarce).  A thread owns one column j (L_j in registers for d <= 5) and walks down the rows of the
+// tile, whose A_i are staged in shared memory by TMA bulk copies and read as broadcasts; a warp stores 128 contiguous
+// bytes per row.  Roofline: FP32/FP64 pipe, not HBM (d=3: ~0.5 kFLOP per 4 output bytes).
+#include "spd_common.cuh"
+
+namespace gabo {
+
+namespace {
+
+constexpr int kThreads = 128;  // columns per tile
+
+// ------------------------------------------------------------------------------------------------------------
+// per-point factorisation
+// ------------------------------------------------------------------------------------------------------------
+template <int d>
+__global__ void spd_factor_kernel(const double* __restrict__ x, int64_t n, int is_mandel, double* __restrict__ fac,
+                                  int32_t* __restrict__ flags) {
+    constexpr int TRI = tri_size(d);
+    constexpr int FS = factor_stride(d);
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double L[TRI], A[TRI];
+    bool ok;
+    if (is_mandel) {
+        const double* v = x + i * TRI;
+        // spd_utils_torch.py:181-187: diagonal first, then the k-th super-diagonal divided by sqrt(2)
+        auto acc = [&](int r, int c) {  // r >= c
+            const double e = v[mandel_pos(d, c, r)];
+            return (r == c) ? e : e * 0.70710678118654752440;
+        };
+        ok = chol_inv<d>(acc, L, A);
+    } else {
+        const double* m = x + i * d * d;
+        auto acc = [&](int r, int c) { return m[r * d + c]; };
+        ok = chol_inv<d>(acc, L, A);
+    }
+    double* o = fac + i * FS;
+#pragma unroll
+    for (int e = 0; e < TRI; ++e) o[e] = L[e];
+#pragma unroll
+    for (int e = 0; e < TRI; ++e) o[TRI + e] = A[e];
+    if (FS > 2 * TRI) o[2 * TRI] = 0.0;
+    if (!ok && flags) atomicOr(flags, 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-pair kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ float finish(float dist, double param) {
+    if (KIND == GABO_KIND_DIST) return dist;
+    const double dd = static_cast<double>(dist);
+    if (KIND == GABO_KIND_GAUSS) return exp_neg_arg(-param * dd * dd);  // kernels_spd.py:96-98
+    return exp_neg_arg(-param * dd);                                     // kernels_spd.py:185
+}
+
+// Tile enumeration.  General: t = jb * tiles_i + ib (rows fastest, so a CTA keeps its column block).  Symmetric
+// (x1 is x2): only the tiles that touch the upper triangle are enumerated, so the contiguous per-CTA ranges stay
+// balanced: for column block jb the row super-blocks sb = 0..jb (128 rows each, R = 128 / tile_m tiles per super-block).
+struct TileMap {
+    int64_t tiles_i;
+    int tile_m;
+    int symmetric;
+    __host__ __device__ void decode(int64_t t, int64_t& jb, int64_t& i0) const {
+        if (!symmetric) {
+            jb = t / tiles_i;
+            i0 = (t % tiles_i) * tile_m;
+        } else {
+            const int64_t R = kThreads / tile_m;
+            const int64_t u = t / R;
+            const int64_t r = t % R;
+            int64_t q = static_cast<int64_t>((sqrt(8.0 * static_cast<double>(u) + 1.0) - 1.0) * 0.5);
+            while ((q + 1) * (q + 2) / 2 <= u) ++q;
+            while (q * (q + 1) / 2 > u) --q;
+            jb = q;
+            i0 = ((u - q * (q + 1) / 2) * R + r) * tile_m;
+        }
+    }
+};
+
+template <int d>
+struct PairCfg {
+    static constexpr int kMaxTileM = (d <= 5) ? 32 : 8;  // keeps static shared memory under 48 KB for d = 8
+};
+
+template <int d, typename T, typename OutT, int KIND>
+__global__ void __launch_bounds__(kThreads)
+    spd_ai_gram_kernel(const double* __restrict__ fac1, int64_t n1, const double* __restrict__ fac2, int64_t n2,
+                       double param, OutT* __restrict__ out, int64_t ld_out, TileMap map, int64_t tiles_total) {
+    constexpr int TRI = tri_size(d);
+    constexpr int FS = factor_stride(d);
+    constexpr bool kLInRegs = (d <= 5);
+    constexpr int kMaxTileM = PairCfg<d>::kMaxTileM;
+    __shared__ __align__(16) double fs[2][kMaxTileM * FS];              // staged x1 records (we read the A halves)
+    __shared__ double ls[kLInRegs ? 1 : TRI * kThreads];                // L_j, entry-major (conflict-free), d >= 6 only
+    __shared__ __align__(8) uint64_t bar[2];
+
+    const int64_t per = (tiles_total + gridDim.x - 1) / gridDim.x;
+    const int64_t t_begin = static_cast<int64_t>(blockIdx.x) * per;
+    const int64_t t_end = imin(t_begin + per, tiles_total);
+    if (t_begin >= t_end) return;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t phase_bits = 0u;
+    // returns the number of rows of tile t (0 = empty edge tile: nothing is staged and nothing is waited for)
+    auto issue = [&](int64_t t, int buf) {
+        int64_t jb, i0;
+        map.decode(t, jb, i0);
+        const int rows = static_cast<int>(imax(0, imin(map.tile_m, n1 - i0)));
+        if (rows > 0 && threadIdx.x == 0) {
+            const uint32_t bytes = static_cast<uint32_t>(rows) * FS * sizeof(double);  // FS even -> multiple of 16
+            mbar_expect_tx(&bar[buf], bytes);
+            tma_load_1d(&fs[buf][0], fac1 + i0 * FS, bytes, &bar[buf]);
+        }
+    };
+
+    issue(t_begin, 0);
+    int64_t jb_loaded = -1;
+    double Lreg[kLInRegs ? TRI : 1];
+    int64_t j = 0;
+    bool jvalid = false;
+
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        const int buf = static_cast<int>((t - t_begin) & 1);
+        int64_t jb, i0;
+        map.decode(t, jb, i0);
+        const int rows = static_cast<int>(imax(0, imin(map.tile_m, n1 - i0)));
+
+        __syncthreads();  // everyone is done with the buffer that is refilled next, and with ls
+        if (t + 1 < t_end) issue(t + 1, buf ^ 1);
+        if (rows <= 0) continue;
+
+        if (jb != jb_loaded) {
+            jb_loaded = jb;
+            j = jb * kThreads + threadIdx.x;
+            jvalid = j < n2;
+            const double* src = fac2 + imin(j, n2 - 1) * FS;
+            if (kLInRegs) {
+#pragma unroll
+                for (int e = 0; e < (kLInRegs ? TRI : 1); ++e) Lreg[e] = __ldg(src + e);
+            } else {
+#pragma unroll
+                for (int e = 0; e < TRI; ++e) ls[e * kThreads + threadIdx.x] = __ldg(src + e);
+            }
+        }
+
+        mbar_wait(&bar[buf], (phase_bits >> buf) & 1u);
+        phase_bits ^= (1u << buf);
+
+        for (int i = 0; i < rows; ++i) {
+            const double* Ai = &fs[buf][i * FS + TRI];
+            T G[d][d];
+            if (kLInRegs) {
+                tri_product<d, T>([&](int e) { return Ai[e]; }, [&](int e) { return Lreg[kLInRegs ? e : 0]; }, G);
+            } else {
+                tri_product<d, T>([&](int e) { return Ai[e]; },
+                                  [&](int e) { return ls[e * kThreads + threadIdx.x]; }, G);
+            }
+            T lam[d];
+            jacobi_onesided<d, T>(G, lam);
+            const float v = finish<KIND>(ai_distance_from_eigs<d, T>(lam), param);
+            if (jvalid) {
+                const int64_t gi = i0 + i;
+                if (!map.symmetric) {
+                    st_cs(out + gi * ld_out + j, static_cast<OutT>(v));
+                } else if (j >= gi) {
+                    out[gi * ld_out + j] = static_cast<OutT>(v);
+                    if (j > gi) out[j * ld_out + gi] = static_cast<OutT>(v);
+                }
+            }
+        }
+    }
+}
+
+template <int d, typename T, typename OutT, int KIND>
+int launch_pair(const double* fac1, int64_t n1, const double* fac2, int64_t n2, double param, void* out,
+                int64_t ld_out, int symmetric, cudaStream_t stream) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spd_ai_gram_kernel<d, T, OutT, KIND>, kThreads, 0);
+    if (occ < 1) occ = 1;
+    const int64_t slots = static_cast<int64_t>(sm_count()) * occ;
+    const int64_t tiles_j = (n2 + kThreads - 1) / kThreads;
+    auto count = [&](int tm) {
+        if (!symmetric) return ((n1 + tm - 1) / tm) * tiles_j;
+        return (kThreads / tm) * (tiles_j * (tiles_j + 1) / 2);
+    };
+    // rows per tile: as large as possible while every resident CTA still gets >= 4 tiles (load balance at small N)
+    int tile_m = PairCfg<d>::kMaxTileM;
+    while (tile_m > 2 && count(tile_m) < 4 * slots) tile_m >>= 1;
+    TileMap map;
+    map.tile_m = tile_m;
+    map.tiles_i = (n1 + tile_m - 1) / tile_m;
+    map.symmetric = symmetric ? 1 : 0;
+    const int64_t tiles = count(tile_m);
+    const int64_t grid = imin(tiles, slots);
+    spd_ai_gram_kernel<d, T, OutT, KIND><<<static_cast<unsigned>(grid), kThreads, 0, stream>>>(
+        fac1, n1, fac2, n2, param, static_cast<OutT*>(out), ld_out, map, tiles);
+    return check_launch("spd_ai_gram_kernel");
+}
+
+template <int d, typename T, typename OutT>
+int launch_kind(const double* fac1, int64_t n1, const double* fac2, int64_t n2, double param, int kind, void* out,
+                int64_t ld_out, int symmetric, cudaStream_t stream) {
+    switch (kind) {
+        case GABO_KIND_GAUSS:
+            return launch_pair<d, T, OutT, GABO_KIND_GAUSS>(fac1, n1, fac2, n2, param, out, ld_out, symmetric, stream);
+        case GABO_KIND_LAPLACE:
+            return launch_pair<d, T, OutT, GABO_KIND_LAPLACE>(fac1, n1, fac2, n2, param, out, ld_out, symmetric,
+                                                              stream);
+        default:
+            return launch_pair<d, T, OutT, GABO_KIND_DIST>(fac1, n1, fac2, n2, param, out, ld_out, symmetric, stream);
+    }
+}
+
+template <int d>
+int launch_types(const double* fac1, int64_t n1, const double* fac2, int64_t n2, double param, int kind, int compute,
+                 void* out, int out_dtype, int64_t ld_out, int symmetric, cudaStream_t stream) {
+    if (compute == GABO_F32) {
+        if (out_dtype == GABO_F32)
+            return launch_kind<d, float, float>(fac1, n1, fac2, n2, param, kind, out, ld_out, symmetric, stream);
+        return launch_kind<d, float, double>(fac1, n1, fac2, n2, param, kind, out, ld_out, symmetric, stream);
+    }
+    if (out_dtype == GABO_F32)
+        return launch_kind<d, double, float>(fac1, n1, fac2, n2, param, kind, out, ld_out, symmetric, stream);
+    return launch_kind<d, double, double>(fac1, n1, fac2, n2, param, kind, out, ld_out, symmetric, stream);
+}
+
+}  // namespace
+
+}  // namespace gabo
+
+extern "C" int64_t gabo_spd_factor_stride(int d) {
+    if (d < 1 || d > GABO_MAX_SPD_DIM) return -1;
+    return gabo::factor_stride(d);
+}
+
+extern "C" int gabo_spd_factor(const double* x, int64_t n, int d, int input_is_mandel, double* fac, int32_t* flags,
+                               void* stream) {
+    using namespace gabo;
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_spd_factor: negative size");
+    if (n == 0) return GABO_OK;
+    GABO_REQUIRE(x && fac, GABO_E_ARG, "gabo_spd_factor: null pointer");
+    GABO_REQUIRE(d >= 1 && d <= GABO_MAX_SPD_DIM, GABO_E_ARG, "gabo_spd_factor: d=%d outside [1, %d]", d,
+                 GABO_MAX_SPD_DIM);
+    GABO_REQUIRE(aligned16(fac), GABO_E_ALIGN, "gabo_spd_factor: fac must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>((n + 127) / 128);
+    switch (d) {
+#define GABO_CASE(DD)                                                                         \
+    case DD:                                                                                  \
+        spd_factor_kernel<DD><<<grid, 128, 0, s>>>(x, n, input_is_mandel, fac, flags);        \
+        break;
+        GABO_CASE(1)
+        GABO_CASE(2)
+        GABO_CASE(3)
+        GABO_CASE(4)
+        GABO_CASE(5)
+        GABO_CASE(6)
+        GABO_CASE(7)
+        GABO_CASE(8)
+#undef GABO_CASE
+    }
+    return check_launch("spd_factor_kernel");
+}
+
+extern "C" int gabo_spd_ai_gram(const double* fac1, int64_t n1, const double* fac2, int64_t n2, int d, double param,
+                                int kind, int compute, int symmetric, void* out, int out_dtype, int64_t ld_out,
+                                void* stream) {
+    using namespace gabo;
+    GABO_REQUIRE(n1 >= 0 && n2 >= 0, GABO_E_ARG, "gabo_spd_ai_gram: negative size");
+    if (n1 == 0 || n2 == 0) return GABO_OK;
+    GABO_REQUIRE(fac1 && fac2 && out, GABO_E_ARG, "gabo_spd_ai_gram: null pointer");
+    GABO_REQUIRE(d >= 1 && d <= GABO_MAX_SPD_DIM, GABO_E_ARG, "gabo_spd_ai_gram: d=%d outside [1, %d]", d,
+                 GABO_MAX_SPD_DIM);
+    GABO_REQUIRE(kind >= GABO_KIND_GAUSS && kind <= GABO_KIND_DIST, GABO_E_ARG, "gabo_spd_ai_gram: bad kind %d", kind);
+    GABO_REQUIRE(compute == GABO_F32 || compute == GABO_F64, GABO_E_ARG, "gabo_spd_ai_gram: bad compute dtype");
+    GABO_REQUIRE(out_dtype == GABO_F32 || out_dtype == GABO_F64, GABO_E_ARG, "gabo_spd_ai_gram: bad out_dtype");
+    GABO_REQUIRE(ld_out >= n2, GABO_E_ARG, "gabo_spd_ai_gram: ld_out < n2");
+    GABO_REQUIRE(aligned16(fac1) && aligned16(fac2), GABO_E_ALIGN, "gabo_spd_ai_gram: factors must be 16-byte aligned");
+    GABO_REQUIRE(!symmetric || (fac1 == fac2 && n1 == n2), GABO_E_ARG,
+                 "gabo_spd_ai_gram: symmetric needs fac1 == fac2 and n1 == n2");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (d) {
+#define GABO_CASE(DD) \
+    case DD:          \
+        return launch_types<DD>(fac1, n1, fac2, n2, param, kind, compute, out, out_dtype, ld_out, symmetric, s);
+        GABO_CASE(1)
+        GABO_CASE(2)
+        GABO_CASE(3)
+        GABO_CASE(4)
+        GABO_CASE(5)
+        GABO_CASE(6)
+        GABO_CASE(7)
+        GABO_CASE(8)
+#undef GABO_CASE
+    }
+    return GABO_E_ARG;
+}

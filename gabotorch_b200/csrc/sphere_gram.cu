@@ -1,0 +1,368 @@
+// Fused sphere Gram: out[i,j] = f(acos(clamp(<x1_i, x2_j>))) in one pass (G1 + G2 of SURVEY.md section 8).
+//
+// Replaces sphere_distance_torch (BoManifolds/Riemannian_utils/sphere_utils_torch.py:12-55: two materialised
+// (N1,N2,D) broadcasts + an N1*N2-batch bmm + clamp + acos) and the d^2 / exp passes of
+// SphereGaussianKernel.forward (kernel_utils/kernels_sphere.py:89-94).
+//
+// Roofline: HBM write, 4 B (fp32 out) per pair; inputs are O(N*D) and stay in L2.
+// Layout: persistent CTAs walk a contiguous range of (column-block, row-block) tiles; a thread owns 4 consecutive
+// columns (x2 points held in registers as fp64) and streams down the rows of the tile, whose x1 points are staged in
+// shared memory by the TMA bulk-copy engine (double-buffered, mbarrier completion) and read as broadcasts.
+// Each row a warp writes 512 contiguous bytes with streaming float4 stores.
+//
+// Numerics: the inner product is accumulated in fp64 (D DFMAs), so 1-|c| is exact and the reference's
+// clamp epsilon (1e-15) keeps its meaning; everything after that is fp32:
+//   w = (1-|c|)/2,  r^2 = 4 asin^2(sqrt w) = 4w(1 + w P(w))   (degree-8 minimax P on [0, 1/2], no sqrt / acos needed),
+//   d^2 = r^2 for c >= 0,  (pi - r)^2 for c < 0,   K = 2^(d^2 * (-beta log2 e)).
+// Relative error of d^2 is ~1.8e-7, of K about (beta d^2) * 2e-7 + 1e-6.
+#include "common.cuh"
+
+namespace gabo {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kVec = 4;                    // columns per thread
+constexpr int kTileN = kThreads * kVec;    // 512 columns per tile
+constexpr int kTileM = 32;                 // rows per tile
+
+// asin^2(sqrt(w)) = w * (1 + w * P(w)),  w in [0, 0.5]
+__device__ __forceinline__ float asin2_sqrt(float w) {
+    float p = 0.3292977809906006f;
+    p = fmaf(p, w, -0.3745849132537842f);
+    p = fmaf(p, w, 0.28826069831848145f);
+    p = fmaf(p, w, -0.03355207294225693f);
+    p = fmaf(p, w, 0.07700732350349426f);
+    p = fmaf(p, w, 0.07967597246170044f);
+    p = fmaf(p, w, 0.1143670305609703f);
+    p = fmaf(p, w, 0.17777620255947113f);
+    p = fmaf(p, w, 0.3333333432674408f);
+    return w * fmaf(w, p, 1.0f);
+}
+
+struct TailParams {
+    float k_hi, k_lo;  // -param * log2(e) split in two floats (Gauss / Laplace)
+};
+
+// d^2 (and optionally d) of the geodesic distance from the fp64 inner product.
+template <int KIND>
+__device__ __forceinline__ float tail(double c, const TailParams& tp) {
+    c = fmin(fmax(c, -1.0 + 1e-15), 1.0 - 1e-15);  // sphere_utils_torch.py:53
+    const float w = 0.5f * static_cast<float>(1.0 - fabs(c));
+    const float r2 = 4.0f * asin2_sqrt(w);           // squared distance to the nearer pole (+-x)
+    const bool neg = c < 0.0;
+    if (KIND == GABO_KIND_GAUSS) {
+        float d2 = r2;
+        if (neg) {
+            const float r = sqrt_approx(r2);
+            const float d = (3.14159274101257324f - r) + (-8.74227765734758577e-8f);
+            d2 = d * d;
+        }
+        const float t = fmaf(d2, tp.k_hi, d2 * tp.k_lo);
+        return ex2_approx(t);
+    } else {
+        const float r = sqrt_approx(r2);
+        const float d = neg ? (3.14159274101257324f - r) + (-8.74227765734758577e-8f) : r;
+        if (KIND == GABO_KIND_DIST) return d;
+        const float t = fmaf(d, tp.k_hi, d * tp.k_lo);
+        return ex2_approx(t);
+    }
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store4(OutT* p, const float (&v)[kVec], int valid, bool vec_ok);
+
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float (&v)[kVec], int valid, bool vec_ok) {
+    if (vec_ok && valid == kVec) {
+        st_cs4(p, v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < kVec; ++q)
+            if (q < valid) st_cs(p + q, v[q]);
+    }
+}
+template <>
+__device__ __forceinline__ void store4<double>(double* p, const float (&v)[kVec], int valid, bool vec_ok) {
+    if (vec_ok && valid == kVec) {
+        st_cs2(p, static_cast<double>(v[0]), static_cast<double>(v[1]));
+        st_cs2(p + 2, static_cast<double>(v[2]), static_cast<double>(v[3]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < kVec; ++q)
+            if (q < valid) st_cs(p + q, static_cast<double>(v[q]));
+    }
+}
+
+template <int D, typename OutT, int KIND>
+__global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __restrict__ x1, int64_t n1,
+                                                               const double* __restrict__ x2, int64_t n2,
+                                                               TailParams tp, OutT* __restrict__ out, int64_t ld_out,
+                                                               int64_t tiles_i, int64_t tiles_total, bool vec_ok) {
+    __shared__ __align__(16) double xs[2][kTileM * D];
+    __shared__ __align__(8) uint64_t bar[2];
+
+    // contiguous tile range for this CTA; tile id t = jb * tiles_i + ib (rows fastest: x2 registers are reused)
+    const int64_t per = (tiles_total + gridDim.x - 1) / gridDim.x;
+    const int64_t t_begin = static_cast<int64_t>(blockIdx.x) * per;
+    const int64_t t_end = min(t_begin + per, tiles_total);
+    if (t_begin >= t_end) return;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t phase[2] = {0u, 0u};
+    auto issue = [&](int64_t t, int buf) {
+        const int64_t ib = t % tiles_i;
+        const int64_t i0 = ib * kTileM;
+        const int rows = static_cast<int>(imin(kTileM, n1 - i0));
+        const uint32_t bytes = static_cast<uint32_t>(rows) * D * sizeof(double);
+        const double* src = x1 + i0 * D;
+        const bool bulk = ((bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar[buf], bytes);
+                tma_load_1d(&xs[buf][0], src, bytes, &bar[buf]);
+            }
+        } else {
+            for (int e = threadIdx.x; e < rows * D; e += kThreads) xs[buf][e] = src[e];
+        }
+        return bulk;
+    };
+
+    bool bulk_cur = issue(t_begin, 0);
+    int64_t jb_loaded = -1;
+    double b[kVec][D];
+    int valid = 0;
+    int64_t j_first = 0;
+
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        const int buf = static_cast<int>((t - t_begin) & 1);
+        const int64_t jb = t / tiles_i;
+        const int64_t ib = t % tiles_i;
+        const int64_t i0 = ib * kTileM;
+        const int rows = static_cast<int>(imin(kTileM, n1 - i0));
+
+        // the buffer we are about to refill was last read two tiles ago
+        __syncthreads();
+        bool bulk_next = false;
+        if (t + 1 < t_end) bulk_next = issue(t + 1, buf ^ 1);
+
+        if (jb != jb_loaded) {
+            jb_loaded = jb;
+            j_first = jb * kTileN + static_cast<int64_t>(threadIdx.x) * kVec;
+            valid = static_cast<int>(imax(0, imin(kVec, n2 - j_first)));
+#pragma unroll
+            for (int q = 0; q < kVec; ++q) {
+                const int64_t j = imin(j_first + q, n2 - 1);
+#pragma unroll
+                for (int k = 0; k < D; ++k) b[q][k] = __ldg(x2 + j * D + k);
+            }
+        }
+
+        if (bulk_cur) {
+            mbar_wait(&bar[buf], phase[buf]);
+            phase[buf] ^= 1u;
+        } else {
+            __syncthreads();
+        }
+
+        if (valid > 0) {
+            OutT* orow = out + i0 * ld_out + j_first;
+#pragma unroll 2
+            for (int i = 0; i < rows; ++i) {
+                double a[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) a[k] = xs[buf][i * D + k];
+                float v[kVec];
+#pragma unroll
+                for (int q = 0; q < kVec; ++q) {
+                    double c = a[0] * b[q][0];
+#pragma unroll
+                    for (int k = 1; k < D; ++k) c = fma(a[k], b[q][k], c);
+                    v[q] = tail<KIND>(c, tp);
+                }
+                store4<OutT>(orow + static_cast<int64_t>(i) * ld_out, v, valid, vec_ok);
+            }
+        }
+        bulk_cur = bulk_next;
+    }
+}
+
+// Generic ambient dimension (D > 16, up to GABO_MAX_SPHERE_DIM): one thread per 4 columns, x2 re-read through L1.
+template <typename OutT, int KIND>
+__global__ void __launch_bounds__(kThreads) sphere_gram_generic_kernel(const double* __restrict__ x1, int64_t n1,
+                                                                       const double* __restrict__ x2, int64_t n2,
+                                                                       int dim, TailParams tp, OutT* __restrict__ out,
+                                                                       int64_t ld_out, int64_t tiles_i,
+                                                                       int64_t tiles_total) {
+    extern __shared__ __align__(16) double xs_dyn[];  // kTileM * dim
+    for (int64_t t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+        const int64_t jb = t / tiles_i;
+        const int64_t ib = t % tiles_i;
+        const int64_t i0 = ib * kTileM;
+        const int rows = static_cast<int>(imin(kTileM, n1 - i0));
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * dim; e += kThreads) xs_dyn[e] = x1[i0 * dim + e];
+        __syncthreads();
+        const int64_t j_first = jb * kTileN + static_cast<int64_t>(threadIdx.x) * kVec;
+        const int valid = static_cast<int>(imax(0, imin(kVec, n2 - j_first)));
+        if (valid <= 0) continue;
+        for (int i = 0; i < rows; ++i) {
+            double c[kVec] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = 0; k < dim; ++k) {
+                const double a = xs_dyn[i * dim + k];
+#pragma unroll
+                for (int q = 0; q < kVec; ++q) {
+                    const int64_t j = imin(j_first + q, n2 - 1);
+                    c[q] = fma(a, __ldg(x2 + j * dim + k), c[q]);
+                }
+            }
+            float v[kVec];
+#pragma unroll
+            for (int q = 0; q < kVec; ++q) v[q] = tail<KIND>(c[q], tp);
+            store4<OutT>(out + (i0 + i) * ld_out + j_first, v, valid, false);
+        }
+    }
+}
+
+template <typename OutT, int KIND>
+__global__ void sphere_gram_diag_kernel(const double* __restrict__ x1, const double* __restrict__ x2, int64_t n,
+                                        int dim, TailParams tp, OutT* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double c = 0.0;
+    for (int k = 0; k < dim; ++k) c = fma(x1[i * dim + k], x2[i * dim + k], c);
+    out[i] = static_cast<OutT>(tail<KIND>(c, tp));
+}
+
+TailParams make_tail(double param, int kind) {
+    TailParams tp;
+    const double k = (kind == GABO_KIND_DIST) ? 0.0 : -param * 1.4426950408889634074;
+    tp.k_hi = static_cast<float>(k);
+    tp.k_lo = static_cast<float>(k - static_cast<double>(tp.k_hi));
+    return tp;
+}
+
+template <int D, typename OutT, int KIND>
+int launch_fixed(const double* x1, int64_t n1, const double* x2, int64_t n2, TailParams tp, void* out, int64_t ld_out,
+                 cudaStream_t stream) {
+    const int64_t tiles_i = (n1 + kTileM - 1) / kTileM;
+    const int64_t tiles_j = (n2 + kTileN - 1) / kTileN;
+    const int64_t tiles = tiles_i * tiles_j;
+    int occ = 8;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sphere_gram_kernel<D, OutT, KIND>, kThreads, 0);
+    if (occ < 1) occ = 1;
+    const int64_t grid = imin(tiles, static_cast<int64_t>(sm_count()) * occ);
+    const bool vec_ok = (ld_out % kVec == 0) && aligned16(out);
+    sphere_gram_kernel<D, OutT, KIND><<<static_cast<unsigned>(grid), kThreads, 0, stream>>>(
+        x1, n1, x2, n2, tp, static_cast<OutT*>(out), ld_out, tiles_i, tiles, vec_ok);
+    return check_launch("sphere_gram_kernel");
+}
+
+template <typename OutT, int KIND>
+int launch_dim(const double* x1, int64_t n1, const double* x2, int64_t n2, int dim, TailParams tp, void* out,
+               int64_t ld_out, cudaStream_t stream) {
+    switch (dim) {
+#define GABO_CASE(DD) \
+    case DD:          \
+        return launch_fixed<DD, OutT, KIND>(x1, n1, x2, n2, tp, out, ld_out, stream);
+        GABO_CASE(2)
+        GABO_CASE(3)
+        GABO_CASE(4)
+        GABO_CASE(5)
+        GABO_CASE(6)
+        GABO_CASE(7)
+        GABO_CASE(8)
+        GABO_CASE(9)
+        GABO_CASE(10)
+        GABO_CASE(11)
+        GABO_CASE(12)
+#undef GABO_CASE
+        default: {
+            const int64_t tiles_i = (n1 + kTileM - 1) / kTileM;
+            const int64_t tiles_j = (n2 + kTileN - 1) / kTileN;
+            const int64_t tiles = tiles_i * tiles_j;
+            const int64_t grid = imin(tiles, static_cast<int64_t>(sm_count()) * 8);
+            const size_t smem = sizeof(double) * kTileM * dim;
+            sphere_gram_generic_kernel<OutT, KIND><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(
+                x1, n1, x2, n2, dim, tp, static_cast<OutT*>(out), ld_out, tiles_i, tiles);
+            return check_launch("sphere_gram_generic_kernel");
+        }
+    }
+}
+
+template <typename OutT>
+int launch_kind(const double* x1, int64_t n1, const double* x2, int64_t n2, int dim, double param, int kind, void* out,
+                int64_t ld_out, cudaStream_t stream) {
+    const TailParams tp = make_tail(param, kind);
+    switch (kind) {
+        case GABO_KIND_GAUSS:
+            return launch_dim<OutT, GABO_KIND_GAUSS>(x1, n1, x2, n2, dim, tp, out, ld_out, stream);
+        case GABO_KIND_LAPLACE:
+            return launch_dim<OutT, GABO_KIND_LAPLACE>(x1, n1, x2, n2, dim, tp, out, ld_out, stream);
+        default:
+            return launch_dim<OutT, GABO_KIND_DIST>(x1, n1, x2, n2, dim, tp, out, ld_out, stream);
+    }
+}
+
+template <typename OutT>
+int launch_diag(const double* x1, const double* x2, int64_t n, int dim, double param, int kind, void* out,
+                cudaStream_t stream) {
+    const TailParams tp = make_tail(param, kind);
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    OutT* o = static_cast<OutT*>(out);
+    switch (kind) {
+        case GABO_KIND_GAUSS:
+            sphere_gram_diag_kernel<OutT, GABO_KIND_GAUSS><<<grid, 256, 0, stream>>>(x1, x2, n, dim, tp, o);
+            break;
+        case GABO_KIND_LAPLACE:
+            sphere_gram_diag_kernel<OutT, GABO_KIND_LAPLACE><<<grid, 256, 0, stream>>>(x1, x2, n, dim, tp, o);
+            break;
+        default:
+            sphere_gram_diag_kernel<OutT, GABO_KIND_DIST><<<grid, 256, 0, stream>>>(x1, x2, n, dim, tp, o);
+            break;
+    }
+    return check_launch("sphere_gram_diag_kernel");
+}
+
+}  // namespace
+
+}  // namespace gabo
+
+extern "C" int gabo_sphere_gram(const double* x1, int64_t n1, const double* x2, int64_t n2, int dim, double param,
+                                int kind, void* out, int out_dtype, int64_t ld_out, void* stream) {
+    using namespace gabo;
+    GABO_REQUIRE(n1 >= 0 && n2 >= 0, GABO_E_ARG, "gabo_sphere_gram: negative size");
+    if (n1 == 0 || n2 == 0) return GABO_OK;
+    GABO_REQUIRE(x1 && x2 && out, GABO_E_ARG, "gabo_sphere_gram: null pointer");
+    GABO_REQUIRE(dim >= 1 && dim <= GABO_MAX_SPHERE_DIM, GABO_E_ARG, "gabo_sphere_gram: dim %d outside [1, %d]", dim,
+                 GABO_MAX_SPHERE_DIM);
+    GABO_REQUIRE(kind >= GABO_KIND_GAUSS && kind <= GABO_KIND_DIST, GABO_E_ARG, "gabo_sphere_gram: bad kind %d", kind);
+    GABO_REQUIRE(out_dtype == GABO_F32 || out_dtype == GABO_F64, GABO_E_ARG, "gabo_sphere_gram: bad out_dtype");
+    GABO_REQUIRE(ld_out >= n2, GABO_E_ARG, "gabo_sphere_gram: ld_out < n2");
+    GABO_REQUIRE(aligned16(x1) && aligned16(x2), GABO_E_ALIGN, "gabo_sphere_gram: inputs must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dim == 1) dim = 1;  // handled by the generic kernel
+    if (out_dtype == GABO_F32) return launch_kind<float>(x1, n1, x2, n2, dim, param, kind, out, ld_out, s);
+    return launch_kind<double>(x1, n1, x2, n2, dim, param, kind, out, ld_out, s);
+}
+
+extern "C" int gabo_sphere_gram_diag(const double* x1, const double* x2, int64_t n, int dim, double param, int kind,
+                                     void* out, int out_dtype, void* stream) {
+    using namespace gabo;
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_sphere_gram_diag: negative size");
+    if (n == 0) return GABO_OK;
+    GABO_REQUIRE(x1 && x2 && out, GABO_E_ARG, "gabo_sphere_gram_diag: null pointer");
+    GABO_REQUIRE(dim >= 1 && dim <= GABO_MAX_SPHERE_DIM, GABO_E_ARG, "gabo_sphere_gram_diag: bad dim %d", dim);
+    GABO_REQUIRE(kind >= GABO_KIND_GAUSS && kind <= GABO_KIND_DIST, GABO_E_ARG, "gabo_sphere_gram_diag: bad kind");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (out_dtype == GABO_F32) return launch_diag<float>(x1, x2, n, dim, param, kind, out, s);
+    if (out_dtype == GABO_F64) return launch_diag<double>(x1, x2, n, dim, param, kind, out, s);
+    set_error("gabo_sphere_gram_diag: bad out_dtype");
+    return GABO_E_ARG;
+}

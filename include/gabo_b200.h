@@ -1,0 +1,195 @@
+/*
+ * gabo_b200.h -- C ABI of libgabo_b200.so: the B200 (sm_100a) implementation of GaBOtorch's data-parallel hot path.
+ *
+ * Drop-in boundary.  The reference (NoemieJaquier/GaBOtorch @ 884f64a) is pure Python and has
+ * no FFI; each entry point below replaces the arithmetic of the reference function cited next to it, and the Python
+ * package `gabotorch_b200` binds them with ctypes behind the reference's own class / function names
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - row-major, contiguous, base pointers 16-byte aligned;
+ *   - the caller owns every buffer (inputs, outputs, scratch); the library allocates nothing persistent;
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*), no device synchronisation;
+ *   - return value 0 = ok, < 0 = error (GABO_E_*); gabo_last_error() gives a thread-local message;
+ *   - points are fp64 (the reference's dtype).  O(N) per-point work runs in fp64; O(N^2) / O(R*T) per-pair and
+ *     per-step work runs in the type selected by `compute` (GABO_F32 default, GABO_F64 reference-grade).
+ */
+#ifndef GABO_B200_H
+#define GABO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GABO_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define GABO_OK 0
+#define GABO_E_ARG (-1)    /* null pointer, bad size, unsupported dimension */
+#define GABO_E_ALIGN (-2)  /* base pointer not 16-byte aligned */
+#define GABO_E_CUDA (-3)   /* CUDA runtime error at launch */
+#define GABO_E_UNSUPPORTED (-4)
+
+/* dtypes */
+#define GABO_F32 0
+#define GABO_F64 1
+
+/* kernel kinds: what is written for each pair, given the geodesic distance d and the scalar `param` */
+#define GABO_KIND_GAUSS 0    /* exp(-param * d^2)   kernels_sphere.py:93, kernels_spd.py:98   (param = beta)          */
+#define GABO_KIND_LAPLACE 1  /* exp(-param * d)     kernels_sphere.py:132 (param = 1/l^2), kernels_spd.py:185 (beta) */
+#define GABO_KIND_DIST 2     /* d itself            sphere_utils_torch.py:55, spd_utils_torch.py:120                 */
+
+/* manifolds */
+#define GABO_SPHERE 0
+#define GABO_SPD 1
+
+#define GABO_MAX_SPHERE_DIM 128 /* ambient dimension D of S^{D-1}                          */
+#define GABO_MAX_SPD_DIM 8      /* matrix size d of SPD(d): Jacobi state lives in registers */
+#define GABO_MAX_TRAIN 128      /* GP training points held in shared memory by the optimiser */
+
+int gabo_version(void);
+const char* gabo_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * G1 + G2: fused sphere Gram.  Replaces sphere_distance_torch (BoManifolds/Riemannian_utils/sphere_utils_torch.py:12-55)
+ * followed by SphereGaussianKernel.forward / SphereLaplaceKernel.forward (kernel_utils/kernels_sphere.py:89-94, 129-134):
+ *   out[i, j] = f(acos(clamp(<x1_i, x2_j>, -1+1e-15, 1-1e-15)))      x1: n1 x dim, x2: n2 x dim (fp64)
+ * out: n1 x n2 with row stride ld_out (elements), dtype out_dtype.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gabo_sphere_gram(const double* x1, int64_t n1, const double* x2, int64_t n2, int dim, double param, int kind,
+                     void* out, int out_dtype, int64_t ld_out, void* stream);
+
+/* diag=True branch (sphere_utils_torch.py:45-49): out[i] = f(d(x1_i, x2_i)), n values. */
+int gabo_sphere_gram_diag(const double* x1, const double* x2, int64_t n, int dim, double param, int kind, void* out,
+                          int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * G3: Mandel notation.  Replaces vector_to_symmetric_matrix_mandel_torch / symmetric_matrix_to_vector_mandel_torch
+ * (Riemannian_utils/spd_utils_torch.py:159-194 / :197-226).  vec: n x d(d+1)/2, mat: n x d x d (fp64).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gabo_mandel_unpack(const double* vec, int64_t n, int d, double* mat, void* stream);
+int gabo_mandel_pack(const double* mat, int64_t n, int d, double* vec, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * G4 + G5: SPD affine-invariant Gram.  Replaces affine_invariant_distance_torch (spd_utils_torch.py:53-120) and
+ * SpdAffineInvariantGaussianKernel.forward / ...LaplaceKernel.forward (kernel_utils/kernels_spd.py:90-100, 178-187).
+ *
+ * Step 1 (per point, fp64): Mandel unpack (or plain matrices), Cholesky X = L L^T, A = L^-1.  `fac` receives, per point,
+ *   gabo_spd_factor_stride(d) doubles: [ L packed lower-triangular row-major | A packed the same way | padding ].
+ *   `flags` (nullable, one int32): bit 0 is set when any point is not positive definite (torch.cholesky raises at
+ *   spd_utils_torch.py:87; the library reports instead, the Python layer raises).
+ * Step 2 (per pair): G = A_i L_j (fp64 FMAs), one-sided Jacobi on G in `compute` precision, eigenvalues
+ *   lambda_k = |g_k|^2 rounded to fp32, d = sqrt(sum log(lambda)^2 + 1e-15) in fp32 exactly as spd_utils_torch.py:108-120.
+ *   `symmetric` != 0 (only when fac1 == fac2): computes the upper triangle of tiles and mirrors it.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int64_t gabo_spd_factor_stride(int d);
+int gabo_spd_factor(const double* x, int64_t n, int d, int input_is_mandel, double* fac, int32_t* flags, void* stream);
+int gabo_spd_ai_gram(const double* fac1, int64_t n1, const double* fac2, int64_t n2, int d, double param, int kind,
+                     int compute, int symmetric, void* out, int out_dtype, int64_t ld_out, void* stream);
+
+/* Frobenius / log-Euclidean Gram (spd_utils_torch.py:124-156, kernels_spd.py:230-241, 283-313):
+ *   out[i,j] = f(|| M1_i - M2_j + 1e-15 ||_F), m: n x d x d fp64 (apply gabo_spd_logm first for log-Euclidean);
+ *   kind GAUSS uses exp(-param d^2) with param = 1/lengthscale^2. */
+int gabo_frobenius_gram(const double* m1, int64_t n1, const double* m2, int64_t n2, int d, double param, int kind,
+                        void* out, int out_dtype, int64_t ld_out, void* stream);
+/* logm_torch (spd_utils_torch.py:13-30) batched: out_i = V diag(log lambda) V^T. */
+int gabo_spd_logm(const double* mat, int64_t n, int d, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * M1: batched sphere manifold operations (pymanopt Sphere; reference formulas Riemannian_utils/sphere_utils.py:14-123).
+ * All arrays n x dim fp64.  op codes below; `y` is the second point / vector where the op takes one.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define GABO_OP_PROJ 0      /* out = u - <x,u> x                       (proj / egrad2rgrad; a = x, b = u)      */
+#define GABO_OP_RETR 1      /* out = (x+u)/|x+u|                       (a = x, b = u)                          */
+#define GABO_OP_EXP 2       /* out = x cos|u| + u sin|u|/|u|           (a = x, b = u)  sphere_utils.py:33-36   */
+#define GABO_OP_LOG 3       /* out = Log_x(y)                          (a = x, b = y)  sphere_utils.py:60-63   */
+#define GABO_OP_TRANSP 4    /* out = proj(y, u)                        (a = y, b = u)  pymanopt Sphere.transp  */
+#define GABO_OP_PTRANSP 5   /* true parallel transport x->y of u       (a = x, b = y, c = u) sphere_utils.py:93-123 / spd_utils.py:200-213 */
+#define GABO_OP_EGRAD2RGRAD 6 /* spd: X sym(G) X                       (a = X, b = G)                          */
+int gabo_sphere_op(int op, const double* a, const double* b, const double* c, int64_t n, int dim, double* out,
+                   void* stream);
+/* out[i] = acos(clip(<x_i,y_i>, -1, 1))  (pymanopt Sphere.dist; sphere_utils.py:68-90) */
+int gabo_sphere_dist(const double* x, const double* y, int64_t n, int dim, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * M2: batched SPD manifold operations under the affine-invariant metric (pymanopt PositiveDefinite; reference formulas
+ * Riemannian_utils/spd_utils.py:104-213).  Matrices n x d x d fp64, d <= GABO_MAX_SPD_DIM.
+ *   EXP/RETR: L expm(L^-1 U L^-T) L^T;  LOG: L logm(L^-1 Y L^-T) L^T;  EGRAD2RGRAD: X sym(G) X;
+ *   PTRANSP: E U E^T, E = (Y X^-1)^(1/2);  TRANSP: identity (pymanopt 0.2.x), provided for completeness.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gabo_spd_op(int op, const double* a, const double* b, const double* c, int64_t n, int d, double* out,
+                void* stream);
+/* what: 0 = dist(X_i, Y_i) (b = Y);  1 = norm_X(U) = |L^-1 U L^-T|_F (b = U);  2 = inner_X(U, V) (b = U, c = V) */
+int gabo_spd_scalar(int what, const double* x, const double* b, const double* c, int64_t n, int d, double* out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * A4: acquisition value.  Replaces botorch ExpectedImprovement(model, best_f, maximize=False) over a SingleTaskGP with
+ * ScaleKernel(SphereGaussianKernel | SpdAffineInvariantGaussianKernel) (call sites gabo_sphere.py:131-165,
+ * gabo_spd.py:165-197).  The GP is described by precomputed device arrays:
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct gabo_gp_desc {
+    int32_t manifold;       /* GABO_SPHERE | GABO_SPD                                                        */
+    int32_t dim;            /* sphere: ambient D; spd: matrix size d                                          */
+    int32_t n_train;        /* <= GABO_MAX_TRAIN                                                              */
+    int32_t compute;        /* GABO_F32 | GABO_F64: arithmetic type of the per-restart work                   */
+    const double* x_train;  /* sphere: n x D unit vectors; spd: n x gabo_spd_factor_stride(d) (gabo_spd_factor) */
+    const double* alpha;    /* n:     (s K + noise I)^-1 (y - mean)                                           */
+    const double* minv;     /* n x n: (s K + noise I)^-1                                                      */
+    double mean;            /* constant mean                                                                  */
+    double outputscale;     /* s                                                                              */
+    double beta;            /* kernel parameter                                                               */
+    double best_f;          /* incumbent (minimisation)                                                       */
+    double kxx;             /* base-kernel k(x,x) (1 up to the reference's 1e-15 guards)                       */
+} gabo_gp_desc;
+
+/* EI and (optionally) its Riemannian gradient at r points.  x: sphere r x D, spd r x d x d (fp64).
+ * ei: r (fp64).  grad (nullable): same shape as x.  Points that are not SPD get ei = NaN. */
+int gabo_ei_eval(const gabo_gp_desc* gp, const double* x, int64_t r, double* ei, double* grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * A1: batched multi-start Riemannian conjugate gradient on cost = -EI.  Replaces the serial restart loop of
+ * gen_candidates_manifold (manifold_optimization/manifold_optimize.py:207-221) with pymanopt ConjugateGradient
+ * (Hestenes-Stiefel) + LineSearchAdaptive per restart.  One warp per restart, every step inside one launch.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct gabo_rcg_opts {
+    int32_t maxiter;          /* pymanopt Solver maxiter (default 1000)            */
+    int32_t ls_maxiter;       /* LineSearchAdaptive maxiter (10)                   */
+    double mingradnorm;       /* 1e-6                                              */
+    double minstepsize;       /* 1e-10                                             */
+    double contraction;       /* 0.5                                               */
+    double suff_decr;         /* 0.5                                               */
+    double initial_stepsize;  /* 1.0                                               */
+} gabo_rcg_opts;
+
+/* x (in/out): r starting points -> r candidates.  value: r, EI at the candidate (fp64).  iters / reason: r (int32,
+ * nullable); reason 1 = maxiter, 2 = gradnorm, 3 = stepsize. */
+int gabo_acq_rcg(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* opts, double* value,
+                 int32_t* iters, int32_t* reason, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * A3: candidate selection.  Replaces botorch get_best_candidates (argmax of batch values, manifold_optimize.py:118-120).
+ * Lexicographic (value descending, global index ascending), NaN = -inf: identical on 1 or N GPUs.
+ * values: n fp64; gidx: n int64 global restart indices (nullable = 0..n-1); out_slot: one int64 = winning position in
+ * the arrays; out_value: one fp64.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gabo_argmax_records(const double* values, const int64_t* gidx, int64_t n, int64_t* out_slot, double* out_value,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * P1: nested SPD projection Y = W^T X W (nested_mappings/nested_spd_utils.py:13-48) in Mandel coordinates:
+ *   y_mandel[n x dvl] = x_mandel[n x dvh] * P^T, P = gabo_nested_projection_matrix(W) (dvl x dvh).
+ * fp32 I/O, 3xTF32 tensor-core GEMM (error ~1e-6 relative).  P must be the padded layout written by
+ * gabo_nested_projection_matrix: [dvl_pad = roundup(dvl,8)] x [dvh_pad = roundup(dvh,8)] fp32.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gabo_nested_projection_matrix(const double* w, int D, int d, float* p_padded, void* stream);
+int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, int d, const float* p_padded, float* y_mandel,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GABO_B200_H */

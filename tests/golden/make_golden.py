@@ -1,0 +1,162 @@
+"""Generate the golden fixtures in this directory FROM THE REFERENCE'S OWN CODE.
+
+Run in the build container only (needs ``/root/reference``):
+
+    python tests/golden/make_golden.py
+
+It imports the importable slices of the reference (``oracle/reference_loader.py``: torch/numpy-only modules,
+with a ``torch.symeig`` -> ``torch.linalg.eigh`` shim because torch 2.11 removed ``symeig``) and records
+inputs + outputs of
+
+* ``sphere_distance_torch`` (sphere_utils_torch.py:12-55) and ``exp(-beta d^2)`` as in kernels_sphere.py:89-94
+* ``vector_to_symmetric_matrix_mandel_torch`` / ``symmetric_matrix_to_vector_mandel_torch`` (spd_utils_torch.py:159-226)
+* ``affine_invariant_distance_torch`` (spd_utils_torch.py:53-120) and ``exp(-beta d^2)`` as in kernels_spd.py:96-98
+* ``frobenius_distance_torch`` (spd_utils_torch.py:124-156), ``logm_torch`` (:13-30)
+* ``projection_from_spd_to_nested_spd`` (nested_spd_utils.py:13-48)
+* the numpy manifold formulas ``sphere_utils.py:14-123`` and ``spd_utils.py:104-213`` (exp/log/dist/transport)
+
+The kernel classes themselves (``kernels_sphere.py`` / ``kernels_spd.py``) import gpytorch, which is not
+installed, so ``K`` is formed here by the one line the class adds on top of the distance
+(``torch.exp(-distance2.mul(beta.double()))``) with ``beta = beta_min + softplus(0) = beta_min + ln 2``.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import reference_loader  # noqa: E402
+
+SEED = 1234
+LN2 = math.log(2.0)
+
+
+def sphere_points(rng, n, dim):
+    x = rng.standard_normal((n, dim))
+    return x / np.linalg.norm(x, axis=-1, keepdims=True)
+
+
+def spd_points(rng, n, d, max_cond=100.0):
+    """Law of the reference's spd_sample (spd_utils.py:298-305) with the cond<=100 filter of
+    examples/kernels/spd/spd_gaussian_kernel_parameters.py:91-96."""
+    out = []
+    while len(out) < n:
+        lam = 0.001 + (5.0 - 0.001) * rng.random(d)
+        q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+        if lam.max() / lam.min() > max_cond:
+            continue
+        m = (q * lam) @ q.T
+        out.append(0.5 * (m + m.T))
+    return np.array(out)
+
+
+def main():
+    ref = reference_loader.load()
+    st = ref.sphere_utils_torch
+    pt = ref.spd_utils_torch
+    rng = np.random.default_rng(SEED)
+    out = {}
+
+    # ---- sphere -------------------------------------------------------------------------------
+    for name, n, dim, beta_min in (('s2_n256', 256, 3, 6.5), ('s5_n1024', 1024, 6, 1.0), ('s8_n96', 96, 9, 0.6)):
+        x = sphere_points(rng, n, dim)
+        xt = torch.from_numpy(x)
+        d = st.sphere_distance_torch(xt, xt)
+        beta = beta_min + LN2
+        k = torch.exp(-torch.mul(d, d).mul(torch.tensor(beta, dtype=torch.float64)))
+        stride = max(1, n // 128)
+        out[name + '_x'] = x
+        out[name + '_beta'] = np.float64(beta)
+        out[name + '_stride'] = np.int64(stride)
+        out[name + '_d'] = d.numpy()[::stride, ::stride].copy()
+        out[name + '_k'] = k.numpy()[::stride, ::stride].copy()
+        out[name + '_ksum'] = np.float64(k.sum().item())
+        out[name + '_ddiag'] = st.sphere_distance_torch(xt, xt, diag=True).numpy()
+    # rectangular + near-duplicate / antipodal edge cases
+    a = sphere_points(rng, 37, 4)
+    b = sphere_points(rng, 53, 4)
+    b[0] = a[0]
+    b[1] = -a[1]
+    tiny = 1e-4 * rng.standard_normal(4)
+    b[2] = (a[2] + tiny) / np.linalg.norm(a[2] + tiny)
+    out['s3_rect_a'] = a
+    out['s3_rect_b'] = b
+    out['s3_rect_d'] = st.sphere_distance_torch(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+
+    # ---- Mandel + SPD -------------------------------------------------------------------------
+    for name, n, d, beta_min in (('spd3_n128', 128, 3, 0.5), ('spd8_n64', 64, 8, 0.22), ('spd2_n40', 40, 2, 0.6),
+                                 ('spd5_n48', 48, 5, 0.25)):
+        m = spd_points(rng, n, d)
+        mt = torch.from_numpy(m)
+        v = pt.symmetric_matrix_to_vector_mandel_torch(mt)
+        back = pt.vector_to_symmetric_matrix_mandel_torch(v)
+        dist = pt.affine_invariant_distance_torch(back, back)
+        beta = beta_min + LN2
+        k = torch.exp(-torch.mul(dist, dist).mul(torch.tensor(beta, dtype=torch.float64)))
+        out[name + '_mat'] = m
+        out[name + '_vec'] = v.numpy()
+        out[name + '_unpacked'] = back.numpy()
+        out[name + '_beta'] = np.float64(beta)
+        out[name + '_d'] = dist.numpy()
+        out[name + '_k'] = k.numpy()
+        out[name + '_frob'] = pt.frobenius_distance_torch(back, back).numpy()
+        out[name + '_logm'] = torch.stack([pt.logm_torch(back[i]) for i in range(n)]).numpy()
+    # rectangular SPD(3)
+    a = spd_points(rng, 19, 3)
+    b = spd_points(rng, 27, 3)
+    out['spd3_rect_a'] = a
+    out['spd3_rect_b'] = b
+    out['spd3_rect_d'] = pt.affine_invariant_distance_torch(torch.from_numpy(a), torch.from_numpy(b)).numpy()
+
+    # ---- nested projection --------------------------------------------------------------------
+    for name, n, D, d in (('proj_20_5', 64, 20, 5), ('proj_5_2', 16, 5, 2)):
+        x = spd_points(rng, n, D, max_cond=1e9)
+        w, _ = np.linalg.qr(rng.standard_normal((D, d)))
+        y = ref.nested_spd_utils.projection_from_spd_to_nested_spd(torch.from_numpy(x), torch.from_numpy(w))
+        out[name + '_x'] = x
+        out[name + '_w'] = w
+        out[name + '_y'] = y.numpy()
+        out[name + '_xvec'] = pt.symmetric_matrix_to_vector_mandel_torch(torch.from_numpy(x)).numpy()
+        out[name + '_yvec'] = pt.symmetric_matrix_to_vector_mandel_torch(y).numpy()
+
+    # ---- numpy manifold formulas (sphere_utils.py / spd_utils.py) -------------------------------
+    su, sp = ref.sphere_utils, ref.spd_utils
+    n = 24
+    xs = sphere_points(rng, n, 6)
+    ys = sphere_points(rng, n, 6)
+    logs = np.array([su.logmap(ys[i], xs[i])[:, 0] for i in range(n)])
+    exps = np.array([su.expmap(0.7 * logs[i], xs[i])[:, 0] for i in range(n)])
+    vs = rng.standard_normal((n, 6))
+    vs = vs - np.sum(vs * xs, axis=-1, keepdims=True) * xs
+    pts = np.array([su.parallel_transport_operator(xs[i], ys[i]) @ vs[i] for i in range(n)])
+    out['man_sphere_x'], out['man_sphere_y'], out['man_sphere_v'] = xs, ys, vs
+    out['man_sphere_log'], out['man_sphere_exp07'], out['man_sphere_pt'] = logs, exps, pts
+    out['man_sphere_dist'] = np.array([su.sphere_distance(xs[i], ys[i]) for i in range(n)]).reshape(n)
+
+    for d in (3, 8):
+        xs = spd_points(rng, n, d)
+        ys = spd_points(rng, n, d)
+        logs = np.array([np.real(sp.logmap(ys[i], xs[i])) for i in range(n)])
+        exps = np.array([np.real(sp.expmap(0.5 * logs[i], xs[i])) for i in range(n)])
+        dist = np.array([np.real(sp.affine_invariant_distance(xs[i], ys[i])) for i in range(n)])
+        us = rng.standard_normal((n, d, d))
+        us = 0.5 * (us + np.swapaxes(us, -1, -2))
+        pts = []
+        for i in range(n):
+            e = np.real(sp.parallel_transport_operator(xs[i], ys[i]))
+            pts.append(e @ us[i] @ e.T)
+        tag = 'man_spd%d_' % d
+        out[tag + 'x'], out[tag + 'y'], out[tag + 'u'] = xs, ys, us
+        out[tag + 'log'], out[tag + 'exp05'], out[tag + 'dist'], out[tag + 'pt'] = logs, exps, dist, np.array(pts)
+
+    path = os.path.join(HERE, 'reference_vectors.npz')
+    np.savez_compressed(path, **out)
+    print('wrote %s: %d arrays, %.1f KiB' % (path, len(out), os.path.getsize(path) / 1024))
+
+
+if __name__ == '__main__':
+    main()
