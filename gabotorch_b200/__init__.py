@@ -3,6 +3,25 @@
 Geodesic-kernel Gram builds on S^d and SPD(d), the batched Riemannian acquisition optimiser and the nested SPD
 projection, behind the reference's own class / function names.  Host code is Python/PyTorch (device memory, streams,
 torch.distributed); the arithmetic runs in hand-written CUDA kernels reached through the C ABI of
-``include/gabo_b200.h`` (``gabotorch_b200/lib/libgabo_b200.so``).  There is no CPU fallback.
+``include/gabo_b200.h`` (``gabotorch_b200/lib/libgabo_b200.so``).  There is no CPU fallback: the first call that
+needs the library raises ``GaboError`` when it has not been built or no CUDA device is visible.
+
+Module map (reference module -> here):
+    BoManifolds/kernel_utils/kernels_{sphere,spd}.py          -> gabotorch_b200.kernel_utils
+    BoManifolds/Riemannian_utils/{sphere,spd}_utils_torch.py   -> gabotorch_b200.riemannian_utils
+    BoManifolds/manifold_optimization/manifold_optimize.py     -> gabotorch_b200.manifold_optimization
+    BoManifolds/nested_mappings/nested_spd_utils.py            -> gabotorch_b200.nested_mappings
+    pymanopt.manifolds.{Sphere,PositiveDefinite}               -> gabotorch_b200.manifolds
 """
 __version__ = '0.1.0'
+
+from ._lib import GaboError  # noqa: F401
+from .kernel_utils import (SphereGaussianKernel, SphereLaplaceKernel, SpdAffineInvariantGaussianKernel,  # noqa: F401
+                           SpdAffineInvariantLaplaceKernel, SpdFrobeniusGaussianKernel,
+                           SpdLogEuclideanGaussianKernel)
+from ._compat import ScaleKernel  # noqa: F401
+from .manifolds import Sphere, PositiveDefinite  # noqa: F401
+from .manifold_optimization import (ConjugateGradient, ExpectedImprovement, ManifoldGP,  # noqa: F401
+                                    gen_batch_initial_conditions_manifold, gen_candidates_manifold,
+                                    get_best_candidates, joint_optimize_manifold)
+from .nested_mappings import NestedSpdProjection, projection_from_spd_to_nested_spd  # noqa: F401

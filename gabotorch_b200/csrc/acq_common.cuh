@@ -1,0 +1,100 @@
+// Shared pieces of the acquisition kernels (A1 / A4 of SURVEY.md section 8): GP description on the device, the analytic
+// Expected Improvement, the per-warp conjugate-gradient bookkeeping.
+//
+// What the reference does per restart (manifold_optimization/manifold_optimize.py:207-221): a pymanopt solve whose every
+// cost / gradient call runs botorch's ExpectedImprovement through gpytorch's exact-GP posterior with torch autograd
+// (pymanopt_addons/tools/autodiff/_pytorch.py:83-101).  Here ONE WARP owns one restart for the whole solve:
+//   - lanes are spread over the GP training points (distance, kernel value, one row of the K^-1 mat-vec each),
+//   - the posterior mean / variance are warp reductions, EI and its derivative are closed-form scalars,
+//   - the Riemannian gradient is assembled from the same per-point quantities:
+//         grad_x EI = 2 beta sum_i w_i k_i Log_x(X_i),   w_i = -Phi(u) alpha_i - phi(u) (M k)_i / sigma,
+//   - the CG recurrences (Hestenes-Stiefel, pymanopt's adaptive backtracking line search) are warp-uniform scalars.
+#pragma once
+#include "common.cuh"
+
+namespace gabo {
+
+struct GpParams {
+    int n;        // training points
+    int dim;      // sphere: ambient D; spd: d
+    double mean, outputscale, beta, best_f, kxx;
+    const double* x_train;
+    const double* alpha;
+    const double* minv;
+};
+
+struct RcgParams {
+    int maxiter, ls_maxiter;
+    double mingradnorm, minstepsize, contraction, suff_decr, initial_stepsize;
+};
+
+template <typename T>
+struct M;
+template <>
+struct M<float> {
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float acos_(float x) { return acosf(x); }
+    static __device__ __forceinline__ float erfc_(float x) { return erfcf(x); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float nan() { return __int_as_float(0x7fc00000); }
+    static __device__ __forceinline__ float clamp_eps() { return 0.0f; }  // 1e-15 is below fp32 resolution at 1
+};
+template <>
+struct M<double> {
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double acos_(double x) { return acos(x); }
+    static __device__ __forceinline__ double erfc_(double x) { return erfc(x); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+    static __device__ __forceinline__ double clamp_eps() { return 1e-15; }  // sphere_utils_torch.py:53
+};
+
+// botorch analytic EI, maximize=False:  sigma = sqrt(clamp_min(var, 1e-9)),  u = (best_f - mu) / sigma,
+// EI = sigma (phi(u) + u Phi(u)).  Also returns the two factors of the gradient weights.
+template <typename T>
+struct EiScalars {
+    T ei;
+    T cdf;            // Phi(u)            : -dEI/dmu
+    T pdf_over_sigma; // phi(u) / sigma    : dEI/dsigma / sigma, zero when the variance floor is active
+};
+
+template <typename T>
+__device__ __forceinline__ EiScalars<T> ei_scalars(T k_alpha, T k_m_k, const GpParams& gp) {
+    EiScalars<T> r;
+    const T mu = static_cast<T>(gp.mean) + k_alpha;
+    const T var_raw = static_cast<T>(gp.outputscale * gp.kxx) - k_m_k;
+    const bool clamped = !(var_raw >= T(1e-9));
+    const T sigma = M<T>::sqrt_(clamped ? T(1e-9) : var_raw);
+    const T u = (static_cast<T>(gp.best_f) - mu) / sigma;
+    const T pdf = M<T>::exp_(T(-0.5) * u * u) * T(0.3989422804014326779);
+    const T cdf = T(0.5) * M<T>::erfc_(-u * T(0.7071067811865475244));
+    r.ei = sigma * (pdf + u * cdf);
+    r.cdf = cdf;
+    r.pdf_over_sigma = clamped ? T(0) : pdf / sigma;
+    return r;
+}
+
+// Dynamic shared-memory carving helper (all offsets 16-byte aligned).
+struct SmemCarver {
+    size_t off = 0;
+    __host__ __device__ size_t take(size_t bytes) {
+        const size_t o = off;
+        off = (off + bytes + 15) & ~static_cast<size_t>(15);
+        return o;
+    }
+};
+
+constexpr int kAcqWarps = 4;  // restarts per CTA
+
+int launch_acq_sphere(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* opts, double* value,
+                      double* grad, int32_t* iters, int32_t* reason, cudaStream_t stream);
+
+template <int d>
+int launch_acq_spd(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* opts, double* value,
+                   double* grad, int32_t* iters, int32_t* reason, cudaStream_t stream);
+
+}  // namespace gabo

@@ -1,0 +1,450 @@
+// Acquisition value / multi-start Riemannian CG on SPD(d) under the affine-invariant metric (A1 + A4 with M2
+// primitives).  One warp per restart; lanes own GP training points, each running the same
+// in-register one-sided Jacobi eigen-solve as the Gram kernel (spd_common.cuh).
+//
+// pymanopt's PositiveDefinite (reference call sites manifold_optimize.py:207-221, gabo_spd.py:98; numpy statements
+// Riemannian_utils/spd_utils.py:104-213) gives  inner_X(U,V) = tr(X^-1 U X^-1 V),  retr = exp_X(U) = X expm(X^-1 U),
+// transp = identity,  Log_X(Y) = X^1/2 logm(X^-1/2 Y X^-1/2) X^1/2.  The solver is run in WHITENED COORDINATES:
+// the iterate is carried as an inverse factor  Finv  with  X = Finv^-1 Finv^-T,  a tangent vector xi as the symmetric
+// matrix  Xi = Finv xi Finv^T.  Then (exactly, for any factor):
+//     inner_X(xi1, xi2) = <Xi1, Xi2>_F,
+//     exp_X(a eta): with the eigen-decomposition  H = V diag(lam) V^T  of the whitened direction, the new inverse
+//                   factor is  Finv' = diag(exp(-a lam / 2)) V^T Finv                     (no Cholesky, no expm)
+//     identity transport to the new point:  Xi' = E V^T Xi V E,  E = diag(exp(-a lam / 2));  for eta itself
+//                   H' = diag(lam exp(-a lam)),
+//     Log_X(X_i) whitened = logm(G_i G_i^T) with G_i = Finv L_i (L_i the Cholesky factor of the training point)
+//                   = sum_k log(l_k)/l_k g_k g_k^T  after the one-sided Jacobi (columns g_k, l_k = |g_k|^2).
+// One symmetric eigen-solve per CG iteration (the direction), one one-sided Jacobi per training point per trial.
+// The iterate X is materialised once, at the end.  Same iterates as pymanopt's operations in exact arithmetic.
+#pragma once
+#include "acq_common.cuh"
+#include "spd_common.cuh"
+
+namespace gabo {
+namespace {
+
+__host__ __device__ constexpr int ui(int d, int r, int c) { return r * d - (r * (r - 1)) / 2 + (c - r); }  // r <= c
+
+template <int d, typename T, int NCH>
+__global__ void __launch_bounds__(kAcqWarps * 32)
+    spd_acq_kernel(GpParams gp, RcgParams opt, int mode, double* __restrict__ x_io, int64_t r,
+                   double* __restrict__ value, double* __restrict__ grad_out, int32_t* __restrict__ iters,
+                   int32_t* __restrict__ reason, int32_t* __restrict__ flags) {
+    constexpr int TRI = tri_size(d);
+    constexpr int FS = factor_stride(d);
+    constexpr int DD = d * d;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = gp.n;
+    const int npad = (n + 3) & ~3;
+    SmemCarver cv;
+    T* Ls = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * n * TRI));
+    T* alpha = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * npad));
+    T* Minv = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * n * n));
+    double* dbase = reinterpret_cast<double*>(smem_raw + cv.take(sizeof(double) * kAcqWarps * 2 * DD));
+    constexpr int kPerWarpT = 3 * DD + 3 * TRI + 2 * d;
+    T* tbase = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * kAcqWarps * (kPerWarpT + npad)));
+
+    for (int e = threadIdx.x; e < n * TRI; e += blockDim.x)
+        Ls[e] = static_cast<T>(gp.x_train[static_cast<int64_t>(e / TRI) * FS + (e % TRI)]);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) alpha[e] = static_cast<T>(gp.alpha[e]);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) Minv[e] = static_cast<T>(gp.minv[e]);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t rid = static_cast<int64_t>(blockIdx.x) * kAcqWarps + warp;
+    if (rid >= r) return;
+
+    double* Finv = dbase + warp * 2 * DD;  // inverse factor of the iterate (fp64)
+    double* Q0 = Finv + DD;                // V^T Finv
+    T* wt = tbase + warp * (kPerWarpT + npad);
+    T* Qs = wt;                 // Q0 in T (what the lanes read)
+    T* Vs = Qs + DD;            // eigenvectors of the whitened direction
+    T* tmp = Vs + DD;           // scratch d x d
+    T* Om = tmp + DD;           // whitened cost gradient (upper triangle)
+    T* Hh = Om + TRI;           // whitened search direction
+    T* OmV = Hh + TRI;          // V^T Om V
+    T* lamH = OmV + TRI;        // eigenvalues of Hh
+    T* Es = lamH + d;           // exp(-a lam / 2) of the trial
+    T* ksh = Es + d;
+
+    const T s_out = static_cast<T>(gp.outputscale), beta = static_cast<T>(gp.beta);
+    T k_l[NCH], mk_l[NCH];
+    T W[NCH][TRI];
+    EiScalars<T> sc;
+
+    // ---- cost at the trial point with inverse factor diag(Es) * Qs ------------------------------------------
+    auto cost_trial = [&]() -> T {
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int i = lane + 32 * ch;
+            T kk = T(0);
+            if (i < n) {
+                const T* Li = Ls + i * TRI;
+                T G[d][d];
+#pragma unroll
+                for (int rr = 0; rr < d; ++rr) {
+                    const T er = Es[rr];
+#pragma unroll
+                    for (int c = 0; c < d; ++c) {
+                        T s = T(0);
+#pragma unroll
+                        for (int m = c; m < d; ++m) s = fma(Qs[rr * d + m], Li[tri_idx(m, c)], s);
+                        G[rr][c] = er * s;
+                    }
+                }
+                T lam[d];
+                jacobi_onesided<d, T>(G, lam);
+                T dsq = T(1e-15);  // spd_utils_torch.py:120
+                T f[d];
+#pragma unroll
+                for (int k = 0; k < d; ++k) {
+                    const T l = M<T>::log_(lam[k]);
+                    dsq = fma(l, l, dsq);
+                    f[k] = l / lam[k];
+                }
+                kk = s_out * M<T>::exp_(-beta * dsq);
+#pragma unroll
+                for (int rr = 0; rr < d; ++rr)
+#pragma unroll
+                    for (int c = rr; c < d; ++c) {
+                        T s = T(0);
+#pragma unroll
+                        for (int k = 0; k < d; ++k) s = fma(f[k] * G[rr][k], G[c][k], s);
+                        W[ch][ui(d, rr, c)] = s;
+                    }
+                ksh[i] = kk;
+            } else {
+#pragma unroll
+                for (int e = 0; e < TRI; ++e) W[ch][e] = T(0);
+            }
+            k_l[ch] = kk;
+        }
+        __syncwarp();
+        T ka = T(0), kmk = T(0);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int i = lane + 32 * ch;
+            T mk = T(0);
+            if (i < n) {
+                for (int j = 0; j < n; ++j) mk = fma(Minv[j * n + i], ksh[j], mk);
+                ka = fma(k_l[ch], alpha[i], ka);
+                kmk = fma(k_l[ch], mk, kmk);
+            }
+            mk_l[ch] = mk;
+        }
+        ka = warp_sum(ka);
+        kmk = warp_sum(kmk);
+        sc = ei_scalars<T>(ka, kmk, gp);
+        const T cst = -sc.ei;
+        return (cst == cst) ? cst : M<T>::inf();
+    };
+
+    // ---- whitened cost gradient at the last evaluated trial point -> dst (upper triangle, smem) --------------
+    auto assemble_grad = [&](T* dst) {
+        T p[TRI];
+#pragma unroll
+        for (int e = 0; e < TRI; ++e) p[e] = T(0);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int i = lane + 32 * ch;
+            if (i < n) {
+                const T w = -sc.cdf * alpha[i] - sc.pdf_over_sigma * mk_l[ch];
+                const T coef = T(2) * beta * w * k_l[ch];
+#pragma unroll
+                for (int e = 0; e < TRI; ++e) p[e] = fma(coef, W[ch][e], p[e]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < TRI; ++e) {
+            const T s = warp_sum(p[e]);
+            if (lane == (e & 31)) dst[e] = -s;  // cost = -EI
+        }
+        __syncwarp();
+    };
+
+    auto sym_inner = [&](const T* a, const T* b) -> T {  // <A, B>_F of two symmetric matrices (upper storage)
+        T s = T(0);
+        for (int e = lane; e < TRI; e += 32) {
+            // entry e is on the diagonal iff e == ui(r, r) for some r
+            bool diag = false;
+#pragma unroll
+            for (int rr = 0; rr < d; ++rr) diag = diag || (e == ui(d, rr, rr));
+            s = fma((diag ? T(1) : T(2)) * a[e], b[e], s);
+        }
+        return warp_sum(s);
+    };
+
+    // ---- initial point: Cholesky of X0, Finv = L^-1 -----------------------------------------------------------
+    const double* xin = x_io + rid * DD;
+    double L0[TRI], A0[TRI];
+    const bool ok0 = chol_inv<d>([&](int rr, int c) { return xin[rr * d + c]; }, L0, A0);
+    if (!ok0) {
+        if (flags && lane == 0) atomicOr(flags, 1);
+        if (lane == 0) {
+            value[rid] = M<double>::nan();
+            if (iters) iters[rid] = 0;
+            if (reason) reason[rid] = -1;
+        }
+        if (mode == 0 && grad_out)
+            for (int e = lane; e < DD; e += 32) grad_out[rid * DD + e] = M<double>::nan();
+        return;
+    }
+#pragma unroll
+    for (int rr = 0; rr < d; ++rr)
+#pragma unroll
+        for (int c = 0; c < d; ++c) {
+            const int e = rr * d + c;
+            if (lane == (e & 31)) {
+                const double v = (c <= rr) ? A0[tri_idx(rr, c)] : 0.0;
+                Finv[e] = v;
+                Qs[e] = static_cast<T>(v);
+                tmp[e] = static_cast<T>((c <= rr) ? L0[tri_idx(rr, c)] : 0.0);  // lower factor, for the ambient gradient
+            }
+        }
+    for (int k = lane; k < d; k += 32) Es[k] = T(1);
+    __syncwarp();
+
+    T cost = cost_trial();
+    if (mode == 0) {
+        if (lane == 0) value[rid] = static_cast<double>(-cost);
+        if (grad_out) {
+            assemble_grad(Om);
+            // ambient Riemannian gradient of EI: L (-Om) L^T
+            for (int e = lane; e < DD; e += 32) {
+                const int rr = e / d, c = e % d;
+                double s = 0.0;
+                for (int a = 0; a <= rr; ++a)
+                    for (int b = 0; b <= c; ++b) {
+                        const int lo = a < b ? a : b, hi = a < b ? b : a;
+                        s += static_cast<double>(tmp[rr * d + a]) * static_cast<double>(Om[ui(d, lo, hi)]) *
+                             static_cast<double>(tmp[c * d + b]);
+                    }
+                grad_out[rid * DD + e] = -s;
+            }
+        }
+        return;
+    }
+
+    assemble_grad(Om);
+    T gPg = sym_inner(Om, Om);
+    T gradnorm = M<T>::sqrt_(gPg);
+    for (int e = lane; e < TRI; e += 32) Hh[e] = -Om[e];
+    __syncwarp();
+    int it = 0, why = 0;
+    T stepsize = M<T>::nan();
+    T oldalpha = T(-1);
+    const T mingrad = static_cast<T>(opt.mingradnorm), minstep = static_cast<T>(opt.minstepsize);
+    const T contraction = static_cast<T>(opt.contraction), suff = static_cast<T>(opt.suff_decr);
+
+    auto set_trial = [&](T a) {
+        __syncwarp();
+        for (int k = lane; k < d; k += 32) Es[k] = M<T>::exp_(T(-0.5) * a * lamH[k]);
+        __syncwarp();
+    };
+
+    while (true) {
+        if (it + 1 >= opt.maxiter) { why = 1; break; }
+        if (gradnorm < mingrad) { why = 2; break; }
+        if (stepsize < minstep) { why = 3; break; }
+        T df0 = sym_inner(Om, Hh);
+        if (df0 >= T(0)) {
+            __syncwarp();
+            for (int e = lane; e < TRI; e += 32) Hh[e] = -Om[e];
+            __syncwarp();
+            df0 = -gPg;
+        }
+        const T norm_d = M<T>::sqrt_(sym_inner(Hh, Hh));
+
+        // eigen-decomposition of the whitened direction (every lane, redundantly; warp-uniform result)
+        {
+            T S[d][d], lam[d], V[d][d];
+#pragma unroll
+            for (int rr = 0; rr < d; ++rr)
+#pragma unroll
+                for (int c = 0; c < d; ++c) S[rr][c] = (c >= rr) ? Hh[ui(d, rr, c)] : T(0);
+            jacobi_symmetric<d, T, true>(S, lam, V);
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < d; ++rr)
+#pragma unroll
+                for (int c = 0; c < d; ++c) {
+                    const int e = rr * d + c;
+                    if (lane == (e & 31)) Vs[e] = V[rr][c];
+                }
+#pragma unroll
+            for (int k = 0; k < d; ++k)
+                if (lane == k) lamH[k] = lam[k];
+            __syncwarp();
+        }
+        // Q0 = V^T Finv (fp64), Qs = (T) Q0;  tmp = Om V;  OmV = V^T tmp
+        for (int e = lane; e < DD; e += 32) {
+            const int rr = e / d, c = e % d;
+            double s = 0.0;
+            T t = T(0);
+            for (int m = 0; m < d; ++m) {
+                s = fma(static_cast<double>(Vs[m * d + rr]), Finv[m * d + c], s);
+                const int lo = rr < m ? rr : m, hi = rr < m ? m : rr;
+                t = fma(Om[ui(d, lo, hi)], Vs[m * d + c], t);
+            }
+            Q0[e] = s;
+            Qs[e] = static_cast<T>(s);
+            tmp[e] = t;
+        }
+        __syncwarp();
+        for (int e = lane; e < DD; e += 32) {
+            const int rr = e / d, c = e % d;
+            if (c >= rr) {
+                T t = T(0);
+                for (int m = 0; m < d; ++m) t = fma(Vs[m * d + rr], tmp[m * d + c], t);
+                OmV[ui(d, rr, c)] = t;
+            }
+        }
+        __syncwarp();
+
+        T a = (oldalpha >= T(0)) ? oldalpha : static_cast<T>(opt.initial_stepsize) / norm_d;
+        set_trial(a);
+        T newf = cost_trial();
+        int evals = 1;
+        while (newf > cost + suff * a * df0 && evals <= opt.ls_maxiter) {
+            a *= contraction;
+            set_trial(a);
+            newf = cost_trial();
+            ++evals;
+        }
+        const bool stay = newf > cost;
+        if (stay) {
+            a = T(0);
+            set_trial(a);
+            newf = cost;
+        }
+        stepsize = a * norm_d;
+        oldalpha = (evals == 2) ? a : T(2) * a;
+
+        // new gradient (in the coordinates of the accepted point) into tmp[0..TRI)
+        if (stay) {
+            for (int e = lane; e < TRI; e += 32) tmp[e] = OmV[e];
+            __syncwarp();
+        } else {
+            assemble_grad(tmp);
+        }
+        // transported old gradient E OmV E and direction diag(lam exp(-a lam)); Hestenes-Stiefel
+        T ip = T(0), den = T(0), ngg = T(0);
+        for (int e = lane; e < TRI; e += 32) {
+            int rr = 0, c = 0;
+#pragma unroll
+            for (int q = 0; q < d; ++q)
+                if (e >= ui(d, q, q)) {
+                    rr = q;
+                    c = q + (e - ui(d, q, q));
+                }
+            const T og = Es[rr] * OmV[e] * Es[c];
+            const T oe = (rr == c) ? lamH[rr] * Es[rr] * Es[rr] : T(0);
+            const T gnew = tmp[e];
+            const T df = gnew - og;
+            const T wgt = (rr == c) ? T(1) : T(2);
+            ip = fma(wgt * gnew, df, ip);
+            den = fma(wgt * df, oe, den);
+            ngg = fma(wgt * gnew, gnew, ngg);
+            Hh[e] = oe;
+        }
+        ip = warp_sum(ip);
+        den = warp_sum(den);
+        ngg = warp_sum(ngg);
+        const T q = ip / den;
+        const T bcg = (q > T(0) && q < M<T>::inf()) ? q : T(0);  // max(0, q); NaN -> 0 like Python's max(0, nan)
+        __syncwarp();
+        for (int e = lane; e < TRI; e += 32) {
+            const T gnew = tmp[e];
+            Hh[e] = fma(bcg, Hh[e], -gnew);
+            Om[e] = gnew;
+        }
+        // accept: Finv <- E Q0
+        for (int e = lane; e < DD; e += 32)
+            Finv[e] = exp(-0.5 * static_cast<double>(a) * static_cast<double>(lamH[e / d])) * Q0[e];
+        __syncwarp();
+        cost = newf;
+        gPg = ngg;
+        gradnorm = M<T>::sqrt_(ngg);
+        ++it;
+    }
+
+    // materialise X = Finv^-1 Finv^-T = (Finv^T Finv)^-1: Y = Finv^T Finv, Y = Ly Ly^T, X = Ly^-T Ly^-1
+    {
+        double Ly[TRI], Ay[TRI];
+        chol_inv<d>(
+            [&](int rr, int c) {
+                double s = 0.0;
+#pragma unroll
+                for (int m = 0; m < d; ++m) s = fma(Finv[m * d + rr], Finv[m * d + c], s);
+                return s;
+            },
+            Ly, Ay);
+#pragma unroll
+        for (int rr = 0; rr < d; ++rr)
+#pragma unroll
+            for (int c = rr; c < d; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int m = c; m < d; ++m) s = fma(Ay[tri_idx(m, rr)], Ay[tri_idx(m, c)], s);
+                const int e = rr * d + c;
+                if (lane == (e & 31)) {
+                    x_io[rid * DD + rr * d + c] = s;
+                    x_io[rid * DD + c * d + rr] = s;
+                }
+            }
+    }
+    if (lane == 0) {
+        value[rid] = static_cast<double>(-cost);
+        if (iters) iters[rid] = it;
+        if (reason) reason[rid] = why;
+    }
+}
+
+template <int d, typename T, int NCH>
+int launch_spd_t(const GpParams& gp, const RcgParams& opt, int mode, double* x, int64_t r, double* value, double* grad,
+                 int32_t* iters, int32_t* reason, cudaStream_t stream) {
+    constexpr int TRI = tri_size(d);
+    constexpr int DD = d * d;
+    const int n = gp.n;
+    const int npad = (n + 3) & ~3;
+    SmemCarver cv;
+    cv.take(sizeof(T) * n * TRI);
+    cv.take(sizeof(T) * npad);
+    cv.take(sizeof(T) * n * n);
+    cv.take(sizeof(double) * kAcqWarps * 2 * DD);
+    cv.take(sizeof(T) * kAcqWarps * (3 * DD + 3 * TRI + 2 * d + npad));
+    const size_t smem = cv.off;
+    GABO_REQUIRE(smem <= 227 * 1024, GABO_E_UNSUPPORTED,
+                 "spd acquisition kernel: n_train=%d, d=%d need %zu bytes of shared memory (> 227 KB)", n, d, smem);
+    auto kern = spd_acq_kernel<d, T, NCH>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const unsigned grid = static_cast<unsigned>((r + kAcqWarps - 1) / kAcqWarps);
+    kern<<<grid, kAcqWarps * 32, smem, stream>>>(gp, opt, mode, x, r, value, grad, iters, reason, nullptr);
+    return check_launch("spd_acq_kernel");
+}
+
+}  // namespace
+
+template <int d>
+int launch_acq_spd(const gabo_gp_desc* g, double* x, int64_t r, const gabo_rcg_opts* o, double* value, double* grad,
+                   int32_t* iters, int32_t* reason, cudaStream_t stream) {
+    GpParams gp{g->n_train, g->dim, g->mean, g->outputscale, g->beta, g->best_f, g->kxx, g->x_train, g->alpha, g->minv};
+    RcgParams opt{};
+    int mode = 0;
+    if (o) {
+        mode = 1;
+        opt = RcgParams{o->maxiter, o->ls_maxiter, o->mingradnorm, o->minstepsize, o->contraction, o->suff_decr,
+                        o->initial_stepsize};
+    }
+    const bool f64 = g->compute == GABO_F64;
+    if (gp.n <= 32) {
+        return f64 ? launch_spd_t<d, double, 1>(gp, opt, mode, x, r, value, grad, iters, reason, stream)
+                   : launch_spd_t<d, float, 1>(gp, opt, mode, x, r, value, grad, iters, reason, stream);
+    }
+    return f64 ? launch_spd_t<d, double, 4>(gp, opt, mode, x, r, value, grad, iters, reason, stream)
+               : launch_spd_t<d, float, 4>(gp, opt, mode, x, r, value, grad, iters, reason, stream);
+}
+
+}  // namespace gabo

@@ -1,0 +1,7 @@
+// SPD(1) instantiation of the acquisition kernels (one translation unit per matrix size: parallel nvcc jobs).
+#include "acq_spd.cuh"
+
+namespace gabo {
+template int launch_acq_spd<1>(const gabo_gp_desc*, double*, int64_t, const gabo_rcg_opts*, double*, double*, int32_t*,
+                               int32_t*, cudaStream_t);
+}  // namespace gabo

@@ -1,0 +1,296 @@
+// Acquisition value / multi-start Riemannian CG on the sphere (A1 + A4 with M1 primitives).
+// One warp per restart, all CG steps inside one launch; see acq_common.cuh for the scheme.
+//
+// Manifold operations used by the solver are pymanopt's Sphere (reference call sites manifold_optimize.py:207-221,
+// numpy statements Riemannian_utils/sphere_utils.py:14-123): retr(x,u) = (x+u)/|x+u|, transp(x,y,u) = u - <y,u> y,
+// inner = Euclidean dot, Log_x(y) = (y - <x,y> x) * theta / |y - <x,y> x|.
+#include "acq_common.cuh"
+
+namespace gabo {
+namespace {
+
+template <typename T>
+struct WarpVecs {
+    int D;
+    int lane;
+    __device__ __forceinline__ T dot(const T* a, const T* b) const {
+        T s = T(0);
+        for (int k = lane; k < D; k += 32) s = fma(a[k], b[k], s);
+        return warp_sum(s);
+    }
+};
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(kAcqWarps * 32)
+    sphere_acq_kernel(GpParams gp, RcgParams opt, int mode, double* __restrict__ x_io, int64_t r,
+                      double* __restrict__ value, double* __restrict__ grad_out, int32_t* __restrict__ iters,
+                      int32_t* __restrict__ reason) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = gp.n, D = gp.dim;
+    const int Dp = D | 1;            // odd row stride: conflict-free lane-per-row reads
+    const int npad = (n + 3) & ~3;
+    const int Dv = (D + 3) & ~3;
+    SmemCarver cv;
+    T* Xs = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * n * Dp));
+    T* alpha = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * npad));
+    T* Minv = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * n * n));
+    T* wbase = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * kAcqWarps * (5 * Dv + 3 * npad)));
+
+    for (int e = threadIdx.x; e < n * D; e += blockDim.x) Xs[(e / D) * Dp + (e % D)] = static_cast<T>(gp.x_train[e]);
+    for (int e = threadIdx.x; e < n; e += blockDim.x) alpha[e] = static_cast<T>(gp.alpha[e]);
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) Minv[e] = static_cast<T>(gp.minv[e]);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t rid = static_cast<int64_t>(blockIdx.x) * kAcqWarps + warp;
+    if (rid >= r) return;
+
+    T* xv = wbase + warp * (5 * Dv + 3 * npad);
+    T* gv = xv + Dv;
+    T* eta = gv + Dv;
+    T* xn = eta + Dv;
+    T* gn = xn + Dv;
+    T* ksh = gn + Dv;
+    T* gsh = ksh + npad;
+    T* csh = gsh + npad;
+    WarpVecs<T> wv{D, lane};
+
+    const T s_out = static_cast<T>(gp.outputscale), beta = static_cast<T>(gp.beta);
+    T c_l[NCH], th_l[NCH], k_l[NCH], mk_l[NCH];
+    EiScalars<T> sc;
+
+    // cost(p) = -EI(p); leaves the per-point quantities in the lane registers for grad()
+    auto cost_at = [&](const T* p) -> T {
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int i = lane + 32 * ch;
+            T kk = T(0), cc = T(0), tt = T(0);
+            if (i < n) {
+                const T* xi = Xs + i * Dp;
+                for (int k = 0; k < D; ++k) cc = fma(xi[k], p[k], cc);
+                cc = fmin(fmax(cc, T(-1) + M<T>::clamp_eps()), T(1) - M<T>::clamp_eps());
+                tt = M<T>::acos_(cc);
+                kk = s_out * M<T>::exp_(-beta * tt * tt);
+                ksh[i] = kk;
+            }
+            c_l[ch] = cc;
+            th_l[ch] = tt;
+            k_l[ch] = kk;
+        }
+        __syncwarp();
+        T ka = T(0), kmk = T(0);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int i = lane + 32 * ch;
+            T mk = T(0);
+            if (i < n) {
+                for (int j = 0; j < n; ++j) mk = fma(Minv[j * n + i], ksh[j], mk);
+                ka = fma(k_l[ch], alpha[i], ka);
+                kmk = fma(k_l[ch], mk, kmk);
+            }
+            mk_l[ch] = mk;
+        }
+        ka = warp_sum(ka);
+        kmk = warp_sum(kmk);
+        sc = ei_scalars<T>(ka, kmk, gp);
+        const T cst = -sc.ei;
+        return (cst == cst) ? cst : M<T>::inf();
+    };
+
+    // Riemannian gradient of the cost at p (the point of the last cost_at call) into out[]
+    auto grad_at = [&](const T* p, T* out) {
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int i = lane + 32 * ch;
+            if (i < n) {
+                const T w = -sc.cdf * alpha[i] - sc.pdf_over_sigma * mk_l[ch];
+                const T coef = T(2) * beta * w * k_l[ch];
+                const T* xi = Xs + i * Dp;
+                T pn = T(0);
+                for (int k = 0; k < D; ++k) {
+                    const T pk = fma(-c_l[ch], p[k], xi[k]);
+                    pn = fma(pk, pk, pn);
+                }
+                pn = M<T>::sqrt_(pn);
+                const T scale = (th_l[ch] > T(1e-6)) ? th_l[ch] / (pn > T(0) ? pn : T(1)) : T(1);
+                gsh[i] = coef * scale;
+                csh[i] = c_l[ch];
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < D; k += 32) {
+            T acc = T(0), sgc = T(0);
+            for (int i = 0; i < n; ++i) {
+                acc = fma(gsh[i], Xs[i * Dp + k], acc);
+                sgc = fma(gsh[i], csh[i], sgc);
+            }
+            out[k] = -(acc - sgc * p[k]);  // cost = -EI
+        }
+        __syncwarp();
+    };
+
+    const double* xin = x_io + rid * D;
+    for (int k = lane; k < D; k += 32) xv[k] = static_cast<T>(xin[k]);
+    __syncwarp();
+
+    T cost = cost_at(xv);
+    if (mode == 0) {
+        if (lane == 0) value[rid] = static_cast<double>(-cost);
+        if (grad_out) {
+            grad_at(xv, gv);
+            for (int k = lane; k < D; k += 32) grad_out[rid * D + k] = static_cast<double>(-gv[k]);
+        }
+        return;
+    }
+
+    grad_at(xv, gv);
+    T gPg = wv.dot(gv, gv);
+    T gradnorm = M<T>::sqrt_(gPg);
+    for (int k = lane; k < D; k += 32) eta[k] = -gv[k];
+    __syncwarp();
+    int it = 0, why = 0;
+    T stepsize = M<T>::nan();
+    T oldalpha = T(-1);  // unset
+    const T mingrad = static_cast<T>(opt.mingradnorm), minstep = static_cast<T>(opt.minstepsize);
+    const T contraction = static_cast<T>(opt.contraction), suff = static_cast<T>(opt.suff_decr);
+
+    auto retract = [&](T a) {  // xn = (x + a eta) / |x + a eta|
+        T s = T(0);
+        for (int k = lane; k < D; k += 32) {
+            const T t = fma(a, eta[k], xv[k]);
+            xn[k] = t;
+            s = fma(t, t, s);
+        }
+        s = warp_sum(s);
+        const T inv = T(1) / M<T>::sqrt_(s);
+        for (int k = lane; k < D; k += 32) xn[k] *= inv;
+        __syncwarp();
+    };
+
+    while (true) {
+        if (it + 1 >= opt.maxiter) { why = 1; break; }
+        if (gradnorm < mingrad) { why = 2; break; }
+        if (stepsize < minstep) { why = 3; break; }
+        T df0 = wv.dot(gv, eta);
+        if (df0 >= T(0)) {  // not a descent direction: restart from steepest descent
+            __syncwarp();
+            for (int k = lane; k < D; k += 32) eta[k] = -gv[k];
+            __syncwarp();
+            df0 = -gPg;
+        }
+        const T norm_d = M<T>::sqrt_(wv.dot(eta, eta));
+        T a = (oldalpha >= T(0)) ? oldalpha : static_cast<T>(opt.initial_stepsize) / norm_d;
+        retract(a);
+        T newf = cost_at(xn);
+        int evals = 1;
+        while (newf > cost + suff * a * df0 && evals <= opt.ls_maxiter) {
+            a *= contraction;
+            retract(a);
+            newf = cost_at(xn);
+            ++evals;
+        }
+        if (newf > cost) {  // no decrease: stay
+            a = T(0);
+            for (int k = lane; k < D; k += 32) {
+                xn[k] = xv[k];
+                gn[k] = gv[k];
+            }
+            __syncwarp();
+            newf = cost;
+        } else {
+            grad_at(xn, gn);
+        }
+        stepsize = a * norm_d;
+        oldalpha = (evals == 2) ? a : T(2) * a;
+        // transport g and eta to xn (projection), Hestenes-Stiefel beta
+        const T xg = wv.dot(xn, gv), xe = wv.dot(xn, eta);
+        T ip = T(0), den = T(0), ngg = T(0);
+        for (int k = lane; k < D; k += 32) {
+            const T og = fma(-xg, xn[k], gv[k]);
+            const T oe = fma(-xe, xn[k], eta[k]);
+            const T df = gn[k] - og;
+            ip = fma(gn[k], df, ip);
+            den = fma(df, oe, den);
+            ngg = fma(gn[k], gn[k], ngg);
+            eta[k] = oe;
+        }
+        ip = warp_sum(ip);
+        den = warp_sum(den);
+        ngg = warp_sum(ngg);
+        T bcg;
+        if (den == T(0)) {
+            bcg = T(1);  // pymanopt: ZeroDivisionError branch for float inner products
+        } else {
+            const T q = ip / den;
+            bcg = (q > T(0)) ? q : T(0);
+        }
+        __syncwarp();
+        for (int k = lane; k < D; k += 32) {
+            eta[k] = fma(bcg, eta[k], -gn[k]);
+            xv[k] = xn[k];
+            gv[k] = gn[k];
+        }
+        __syncwarp();
+        cost = newf;
+        gPg = ngg;
+        gradnorm = M<T>::sqrt_(ngg);
+        ++it;
+    }
+
+    // write back: renormalised in fp64 so the candidate is on the sphere to fp64 accuracy
+    double s = 0.0;
+    for (int k = lane; k < D; k += 32) s = fma(static_cast<double>(xv[k]), static_cast<double>(xv[k]), s);
+    s = warp_sum(s);
+    const double inv = 1.0 / sqrt(s);
+    for (int k = lane; k < D; k += 32) x_io[rid * D + k] = static_cast<double>(xv[k]) * inv;
+    if (lane == 0) {
+        value[rid] = static_cast<double>(-cost);
+        if (iters) iters[rid] = it;
+        if (reason) reason[rid] = why;
+    }
+}
+
+template <typename T, int NCH>
+int launch_t(const GpParams& gp, const RcgParams& opt, int mode, double* x, int64_t r, double* value, double* grad,
+             int32_t* iters, int32_t* reason, cudaStream_t stream) {
+    const int n = gp.n, D = gp.dim;
+    const int Dp = D | 1, npad = (n + 3) & ~3, Dv = (D + 3) & ~3;
+    SmemCarver cv;
+    cv.take(sizeof(T) * n * Dp);
+    cv.take(sizeof(T) * npad);
+    cv.take(sizeof(T) * n * n);
+    cv.take(sizeof(T) * kAcqWarps * (5 * Dv + 3 * npad));
+    const size_t smem = cv.off;
+    GABO_REQUIRE(smem <= 227 * 1024, GABO_E_UNSUPPORTED,
+                 "sphere acquisition kernel: n_train=%d, dim=%d need %zu bytes of shared memory (> 227 KB)", n, D, smem);
+    auto kern = sphere_acq_kernel<T, NCH>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const unsigned grid = static_cast<unsigned>((r + kAcqWarps - 1) / kAcqWarps);
+    kern<<<grid, kAcqWarps * 32, smem, stream>>>(gp, opt, mode, x, r, value, grad, iters, reason);
+    return check_launch("sphere_acq_kernel");
+}
+
+}  // namespace
+
+int launch_acq_sphere(const gabo_gp_desc* g, double* x, int64_t r, const gabo_rcg_opts* o, double* value, double* grad,
+                      int32_t* iters, int32_t* reason, cudaStream_t stream) {
+    GpParams gp{g->n_train, g->dim, g->mean, g->outputscale, g->beta, g->best_f, g->kxx, g->x_train, g->alpha, g->minv};
+    RcgParams opt{};
+    int mode = 0;
+    if (o) {
+        mode = 1;
+        opt = RcgParams{o->maxiter, o->ls_maxiter, o->mingradnorm, o->minstepsize, o->contraction, o->suff_decr,
+                        o->initial_stepsize};
+    }
+    const bool f64 = g->compute == GABO_F64;
+    if (gp.n <= 32) {
+        return f64 ? launch_t<double, 1>(gp, opt, mode, x, r, value, grad, iters, reason, stream)
+                   : launch_t<float, 1>(gp, opt, mode, x, r, value, grad, iters, reason, stream);
+    }
+    return f64 ? launch_t<double, 4>(gp, opt, mode, x, r, value, grad, iters, reason, stream)
+               : launch_t<float, 4>(gp, opt, mode, x, r, value, grad, iters, reason, stream);
+}
+
+}  // namespace gabo

@@ -170,4 +170,142 @@ __device__ __forceinline__ float ai_distance_from_eigs(const T (&lam)[d]) {
     return sqrtf(s + 1e-15f);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-sided cyclic Jacobi for a symmetric (possibly indefinite) d x d matrix: S = V diag(lam) V^T.
+// Used for the exponential map (expm of a whitened tangent vector) where the matrix is not positive definite, so the
+// one-sided form above does not apply.  Only the upper triangle of S is referenced (S[r][c], r <= c).
+// Rotations stop when every off-diagonal entry is below tol * ||S||_F: eigenvalues then carry an ABSOLUTE error of
+// order eps * ||S||, which is what exp(lam) needs.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct SymJacobiTraits;
+template <>
+struct SymJacobiTraits<float> {
+    static constexpr int kMaxSweeps = 10;
+    static __device__ __forceinline__ float tol() { return 6e-8f; }
+    static __device__ __forceinline__ float rsqrt_(float x) {
+        const float y = rsqrt_approx(x);
+        return y * fmaf(-0.5f * x * y, y, 1.5f);
+    }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
+};
+template <>
+struct SymJacobiTraits<double> {
+    static constexpr int kMaxSweeps = 14;
+    static __device__ __forceinline__ double tol() { return 1e-15; }
+    static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+};
+
+#define GABO_SYM(S, r, c) S[((r) < (c)) ? (r) : (c)][((r) < (c)) ? (c) : (r)]
+
+template <int d, typename T, bool kWantV>
+__device__ __forceinline__ void jacobi_symmetric(T (&S)[d][d], T (&lam)[d], T (&V)[d][d]) {
+    using Tr = SymJacobiTraits<T>;
+    if (kWantV) {
+#pragma unroll
+        for (int r = 0; r < d; ++r)
+#pragma unroll
+            for (int c = 0; c < d; ++c) V[r][c] = (r == c) ? T(1) : T(0);
+    }
+    T fro = T(0);
+#pragma unroll
+    for (int r = 0; r < d; ++r)
+#pragma unroll
+        for (int c = r; c < d; ++c) fro = fma((r == c) ? T(1) : T(2), S[r][c] * S[r][c], fro);
+    const T thr = Tr::tol() * Tr::sqrt_(fro);
+    for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < d - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < d; ++q) {
+                const T apq = S[p][q];
+                if (fabs(apq) > thr) {
+                    rotated = true;
+                    const T tau = (S[q][q] - S[p][p]) * Tr::rcp_(T(2) * apq);
+                    const T t = copysign(T(1), tau) * Tr::rcp_(fabs(tau) + Tr::sqrt_(fma(tau, tau, T(1))));
+                    const T cs = Tr::rsqrt_(fma(t, t, T(1)));
+                    const T sn = t * cs;
+                    S[p][p] = fma(-t, apq, S[p][p]);
+                    S[q][q] = fma(t, apq, S[q][q]);
+                    S[p][q] = T(0);
+#pragma unroll
+                    for (int r = 0; r < d; ++r) {
+                        if (r != p && r != q) {
+                            const T srp = GABO_SYM(S, r, p), srq = GABO_SYM(S, r, q);
+                            GABO_SYM(S, r, p) = fma(cs, srp, -sn * srq);
+                            GABO_SYM(S, r, q) = fma(sn, srp, cs * srq);
+                        }
+                    }
+                    if (kWantV) {
+#pragma unroll
+                        for (int r = 0; r < d; ++r) {
+                            const T vp = V[r][p], vq = V[r][q];
+                            V[r][p] = fma(cs, vp, -sn * vq);
+                            V[r][q] = fma(sn, vp, cs * vq);
+                        }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(__activemask(), rotated)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k) lam[k] = S[k][k];
+}
+
+// Full d x d from a packed lower-triangular array (row-major): M[r][c] = tri[r(r+1)/2 + c] for c <= r, else 0.
+template <int d, typename T, typename Acc>
+__device__ __forceinline__ void tri_expand(Acc tri, T (&M)[d][d]) {
+#pragma unroll
+    for (int r = 0; r < d; ++r)
+#pragma unroll
+        for (int c = 0; c < d; ++c) M[r][c] = (c <= r) ? static_cast<T>(tri(tri_idx(r, c))) : T(0);
+}
+
+// C = A * B (full d x d)
+template <int d, typename T>
+__device__ __forceinline__ void matmul(const T (&A)[d][d], const T (&B)[d][d], T (&C)[d][d]) {
+#pragma unroll
+    for (int r = 0; r < d; ++r)
+#pragma unroll
+        for (int c = 0; c < d; ++c) {
+            T s = T(0);
+#pragma unroll
+            for (int k = 0; k < d; ++k) s = fma(A[r][k], B[k][c], s);
+            C[r][c] = s;
+        }
+}
+// C = A * B^T
+template <int d, typename T>
+__device__ __forceinline__ void matmul_nt(const T (&A)[d][d], const T (&B)[d][d], T (&C)[d][d]) {
+#pragma unroll
+    for (int r = 0; r < d; ++r)
+#pragma unroll
+        for (int c = 0; c < d; ++c) {
+            T s = T(0);
+#pragma unroll
+            for (int k = 0; k < d; ++k) s = fma(A[r][k], B[c][k], s);
+            C[r][c] = s;
+        }
+}
+// C = sum_k f[k] * g_k g_k^T for the columns g_k of G  (symmetric; both triangles written)
+template <int d, typename T>
+__device__ __forceinline__ void weighted_outer(const T (&G)[d][d], const T (&f)[d], T (&C)[d][d]) {
+#pragma unroll
+    for (int r = 0; r < d; ++r)
+#pragma unroll
+        for (int c = r; c < d; ++c) {
+            T s = T(0);
+#pragma unroll
+            for (int k = 0; k < d; ++k) s = fma(f[k] * G[r][k], G[c][k], s);
+            C[r][c] = s;
+            C[c][r] = s;
+        }
+}
+
 }  // namespace gabo

@@ -1,0 +1,180 @@
+"""Geodesic kernels with the reference's class names and signatures (BoManifolds/kernel_utils), computed on the B200.
+
+Mirrors ``BoManifolds/kernel_utils/kernels_sphere.py`` and ``kernels_spd.py`` of the reference: same constructor
+arguments, same ``beta`` / ``lengthscale`` parameterisation (``beta = beta_min + softplus(raw_beta)``,
+kernels_sphere.py:56-60), same ``forward`` signatures -- including the reference's inconsistency that the sphere
+kernels take ``diag=`` while the SPD kernels take ``diagonal_distance=`` (kernels_sphere.py:71 vs kernels_spd.py:72).
+``forward`` returns float64 like the reference (``self.beta.double()``, kernels_sphere.py:93) on the device of ``x1``.
+
+The arithmetic is one fused CUDA launch per Gram matrix (``gabo_sphere_gram`` / ``gabo_spd_factor`` +
+``gabo_spd_ai_gram``, include/gabo_b200.h); there is no CPU implementation behind these classes.  Gradients: the Gram
+path is differentiable with respect to the kernel parameter (``raw_beta`` / ``raw_lengthscale``), which is what GP
+hyper-parameter fitting needs; gradients with respect to the inputs are provided in closed form by the acquisition
+kernels (``manifold_optimization``), not through autograd.
+"""
+import torch
+
+from . import _lib, ops
+from ._compat import GreaterThan, Kernel
+
+
+def _needs_param_grad(param):
+    return torch.is_grad_enabled() and param.requires_grad
+
+
+def _reject_input_grad(*xs):
+    if torch.is_grad_enabled() and any(torch.is_tensor(x) and x.requires_grad for x in xs):
+        raise NotImplementedError(
+            'gabotorch_b200 kernels do not back-propagate to their inputs through autograd; the acquisition '
+            'optimiser (manifold_optimization.gen_candidates_manifold) evaluates the Riemannian gradient in closed form')
+
+
+def _finish(out, like):
+    """Result on the caller's device (the reference returns CPU float64 for CPU inputs)."""
+    return out if like.is_cuda else out.to(like.device)
+
+
+class _BetaKernel(Kernel):
+    """Shared by the kernels parameterised with ``beta >= beta_min`` (kernels_sphere.py:30-69, kernels_spd.py:33-70)."""
+
+    def __init__(self, beta_min, beta_prior=None, **kwargs):
+        super().__init__(has_lengthscale=False, **kwargs)
+        self.beta_min = beta_min
+        self.register_parameter(name='raw_beta', parameter=torch.nn.Parameter(torch.zeros(*self.batch_shape, 1, 1)))
+        if beta_prior is not None:
+            self.register_prior('beta_prior', beta_prior, lambda: self.beta, lambda v: self._set_beta(v))
+        self.register_constraint('raw_beta', GreaterThan(self.beta_min))
+
+    @property
+    def beta(self):
+        return self.raw_beta_constraint.transform(self.raw_beta)
+
+    @beta.setter
+    def beta(self, value):
+        self._set_beta(value)
+
+    def _set_beta(self, value):
+        if not torch.is_tensor(value):
+            value = torch.as_tensor(value).to(self.raw_beta)
+        self.initialize(raw_beta=self.raw_beta_constraint.inverse_transform(value))
+
+    def _beta_scalar(self):
+        b = self.beta
+        if b.numel() != 1:
+            raise NotImplementedError('batched beta (batch_shape != []) is not supported by the fused Gram kernels')
+        return b
+
+
+def _param_gram(dist_fn, param, power):
+    """exp(-param * d^power) with autograd to ``param``: distances from the fused kernel, the exp in torch on-device."""
+    d = dist_fn()
+    p = param.double().to(d.device).reshape(())
+    return torch.exp(-(d * d if power == 2 else d).mul(p))
+
+
+class SphereGaussianKernel(_BetaKernel):
+    """exp(-beta d(x1,x2)^2) on the sphere (kernels_sphere.py:15-94)."""
+
+    def forward(self, x1, x2, diag=False, **params):
+        _reject_input_grad(x1, x2)
+        beta = self._beta_scalar()
+        if _needs_param_grad(self.raw_beta):
+            out = _param_gram(lambda: ops.sphere_gram(x1, x2, kind=_lib.KIND_DIST, diag=diag), beta, 2)
+        else:
+            out = ops.sphere_gram(x1, x2, float(beta.detach()), _lib.KIND_GAUSS, diag=diag)
+        return _finish(out, x1)
+
+
+class SphereLaplaceKernel(Kernel):
+    """exp(-d(x1,x2) / lengthscale^2) on the sphere (kernels_sphere.py:97-134)."""
+    has_lengthscale = True
+
+    def __init__(self, **kwargs):
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+
+    def forward(self, x1, x2, diag=False, **params):
+        _reject_input_grad(x1, x2)
+        ls = self.lengthscale.reshape(()).double()
+        inv = 1.0 / (ls * ls)
+        if _needs_param_grad(self.raw_lengthscale):
+            out = _param_gram(lambda: ops.sphere_gram(x1, x2, kind=_lib.KIND_DIST, diag=diag), inv, 1)
+        else:
+            out = ops.sphere_gram(x1, x2, float(inv.detach()), _lib.KIND_LAPLACE, diag=diag)
+        return _finish(out, x1)
+
+
+def _spd_diag_ones(x2):
+    # diagonal_distance=True: the reference returns zero distances of shape (..., N, 1) (spd_utils_torch.py:72-75)
+    return torch.ones(tuple(x2.shape[:-1]) + (1,), dtype=torch.float64, device=x2.device)
+
+
+class SpdAffineInvariantGaussianKernel(_BetaKernel):
+    """exp(-beta d_AI(X1,X2)^2) on SPD(d), inputs in Mandel notation (kernels_spd.py:17-100).
+
+    ``compute`` selects the arithmetic of the per-pair Jacobi eigen-solve: ``'f32'`` (default) or ``'f64'``.
+    """
+
+    def __init__(self, beta_min, beta_prior=None, compute='f32', **kwargs):
+        super().__init__(beta_min, beta_prior=beta_prior, **kwargs)
+        self.compute = compute
+
+    def _compute(self):
+        return _lib.GABO_F64 if self.compute == 'f64' else _lib.GABO_F32
+
+    def forward(self, x1, x2, diagonal_distance=False, **params):
+        _reject_input_grad(x1, x2)
+        if diagonal_distance is True:
+            return _spd_diag_ones(x2)
+        beta = self._beta_scalar()
+        if _needs_param_grad(self.raw_beta):
+            out = _param_gram(lambda: ops.spd_ai_gram(x1, x2, kind=_lib.KIND_DIST, compute=self._compute()), beta, 2)
+        else:
+            out = ops.spd_ai_gram(x1, x2, float(beta.detach()), _lib.KIND_GAUSS, compute=self._compute())
+        return _finish(out, x1)
+
+
+class SpdAffineInvariantLaplaceKernel(SpdAffineInvariantGaussianKernel):
+    """exp(-beta d_AI(X1,X2)) (kernels_spd.py:103-187)."""
+
+    def forward(self, x1, x2, diagonal_distance=False, **params):
+        _reject_input_grad(x1, x2)
+        if diagonal_distance is True:
+            return _spd_diag_ones(x2)
+        beta = self._beta_scalar()
+        if _needs_param_grad(self.raw_beta):
+            out = _param_gram(lambda: ops.spd_ai_gram(x1, x2, kind=_lib.KIND_DIST, compute=self._compute()), beta, 1)
+        else:
+            out = ops.spd_ai_gram(x1, x2, float(beta.detach()), _lib.KIND_LAPLACE, compute=self._compute())
+        return _finish(out, x1)
+
+
+class SpdFrobeniusGaussianKernel(Kernel):
+    """exp(-||X1 - X2||_F^2 / lengthscale^2) on Mandel-vectorised symmetric matrices (kernels_spd.py:190-241)."""
+    has_lengthscale = True
+
+    def __init__(self, **kwargs):
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+
+    def _matrices(self, x):
+        return ops.mandel_unpack(x)
+
+    def forward(self, x1, x2, diagonal_distance=False, **params):
+        _reject_input_grad(x1, x2)
+        if diagonal_distance is True:
+            return _spd_diag_ones(x2)
+        ls = self.lengthscale.reshape(()).double()
+        inv = 1.0 / (ls * ls)
+        m1 = self._matrices(x1)
+        m2 = m1 if x2 is x1 else self._matrices(x2)
+        if _needs_param_grad(self.raw_lengthscale):
+            out = _param_gram(lambda: ops.frobenius_gram(m1, m2, kind=_lib.KIND_DIST), inv, 2)
+        else:
+            out = ops.frobenius_gram(m1, m2, float(inv.detach()), _lib.KIND_GAUSS)
+        return _finish(out, x1)
+
+
+class SpdLogEuclideanGaussianKernel(SpdFrobeniusGaussianKernel):
+    """exp(-||logm X1 - logm X2||_F^2 / lengthscale^2) (kernels_spd.py:244-313)."""
+
+    def _matrices(self, x):
+        return ops.spd_logm(ops.mandel_unpack(x))

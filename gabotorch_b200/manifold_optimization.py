@@ -1,0 +1,357 @@
+"""Multi-start Riemannian acquisition optimisation with the reference's function names and signatures
+(``BoManifolds/manifold_optimization/manifold_optimize.py``), batched on the B200.
+
+Reference flow (manifold_optimize.py:36-321): raw manifold samples -> acquisition values -> botorch's
+``initialize_q_batch[_nonneg]`` picks ``num_restarts`` starts -> ONE pymanopt solve PER restart in a Python loop
+(:207-221), each cost / gradient call going through torch autograd -> acquisition re-evaluated at the candidates (:227)
+-> ``get_best_candidates`` = argmax (:118-120).
+
+Here the restarts are solved together by ``gabo_acq_rcg`` (one warp per restart, every CG step inside one launch, the
+EI gradient in closed form), the raw samples are scored by ``gabo_ei_eval`` and the winner is picked by
+``gabo_argmax_records``.  With ``torch.distributed`` initialised and ``options={'distributed': True}`` the restarts are
+sharded across ranks and ONE all-gather of (value, global index, candidate) records ends the solve.
+
+The fast path needs a recognised triple (no CPU fallback):
+  manifold    : ``Sphere`` / ``PositiveDefinite`` (ours, or pymanopt's by class name),
+  solver      : conjugate gradient (``ConjugateGradient`` below, or pymanopt's by class name),
+  acquisition : ``ExpectedImprovement`` over a GP whose kernel is ``ScaleKernel(SphereGaussianKernel |
+                SpdAffineInvariantGaussianKernel)`` (our ``ManifoldGP`` or a botorch ``SingleTaskGP`` duck-typed).
+Anything else raises ``NotImplementedError``.
+"""
+import math
+import warnings
+
+import torch
+
+from . import _lib, ops
+from .kernel_utils import SphereGaussianKernel, SpdAffineInvariantGaussianKernel
+
+
+class BadInitialCandidatesWarning(RuntimeWarning):
+    pass
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# solver description
+# ----------------------------------------------------------------------------------------------------------------
+
+class ConjugateGradient:
+    """Options of the batched Riemannian CG (pymanopt ``ConjugateGradient`` constructor surface: Hestenes-Stiefel,
+    adaptive backtracking line search; defaults are pymanopt's ``Solver`` / ``LineSearchAdaptive`` defaults)."""
+
+    def __init__(self, beta_type='HestenesStiefel', orth_value=float('inf'), linesearch=None, maxtime=1000,
+                 maxiter=1000, mingradnorm=1e-6, minstepsize=1e-10, maxcostevals=5000, logverbosity=0,
+                 contraction_factor=0.5, suff_decr=0.5, ls_maxiter=10, initial_stepsize=1.0):
+        if beta_type not in ('HestenesStiefel', 2):
+            raise NotImplementedError('the batched solver implements the Hestenes-Stiefel rule (pymanopt default)')
+        self._maxtime = maxtime
+        self._maxiter = maxiter
+        self._mingradnorm = mingradnorm
+        self._minstepsize = minstepsize
+        self._maxcostevals = maxcostevals
+        self._logverbosity = logverbosity
+        self.contraction_factor = contraction_factor
+        self.suff_decr = suff_decr
+        self.ls_maxiter = ls_maxiter
+        self.initial_stepsize = initial_stepsize
+
+
+def _solver_options(solver):
+    name = type(solver).__name__
+    if name != 'ConjugateGradient':
+        raise NotImplementedError(
+            'solver %s: the B200 path batches conjugate gradient only (trust-region / ALM solvers are SURVEY 8f '
+            '"next"); there is no CPU fallback' % name)
+    ls = getattr(solver, '_linesearch', None) or getattr(solver, 'linesearch', None)
+    return dict(
+        maxiter=int(getattr(solver, '_maxiter', 1000)),
+        mingradnorm=float(getattr(solver, '_mingradnorm', 1e-6)),
+        minstepsize=float(getattr(solver, '_minstepsize', 1e-10)),
+        contraction=float(getattr(solver, 'contraction_factor', getattr(ls, 'contraction_factor', 0.5))),
+        suff_decr=float(getattr(solver, 'suff_decr', getattr(ls, 'suff_decr', 0.5))),
+        ls_maxiter=int(getattr(solver, 'ls_maxiter', getattr(ls, 'maxiter', 10))),
+        initial_stepsize=float(getattr(solver, 'initial_stepsize', getattr(ls, 'initial_stepsize', 1.0))),
+    )
+
+
+def _manifold_kind(manifold):
+    name = type(manifold).__name__
+    if name == 'Sphere':
+        return _lib.SPHERE
+    if name in ('PositiveDefinite', 'SymmetricPositiveDefinite'):
+        return _lib.SPD
+    raise NotImplementedError('manifold %s is not supported by the B200 acquisition optimiser' % name)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GP + acquisition
+# ----------------------------------------------------------------------------------------------------------------
+
+class ManifoldGP:
+    """Exact GP with constant mean over a geodesic kernel: the slice of botorch ``SingleTaskGP`` the acquisition needs
+    (reference call sites gabo_sphere.py:131-165).  Hyper-parameters are given, not fitted (GP fitting is SURVEY 8f)."""
+
+    def __init__(self, train_x, train_y, covar_module, noise=1e-2, mean=None):
+        self.train_inputs = (torch.as_tensor(train_x, dtype=torch.float64),)
+        self.train_targets = torch.as_tensor(train_y, dtype=torch.float64).reshape(-1)
+        self.covar_module = covar_module
+        self.noise = float(noise)
+        self.mean = float(self.train_targets.mean()) if mean is None else float(mean)
+
+
+def _unwrap_model(model):
+    """(x_train, y, base_kernel, outputscale, noise, mean) from ManifoldGP or a botorch / gpytorch exact GP."""
+    x = model.train_inputs[0]
+    y = model.train_targets
+    cov = model.covar_module
+    base = getattr(cov, 'base_kernel', None)
+    if base is None:
+        base, scale = cov, 1.0
+    else:
+        scale = float(cov.outputscale.detach())
+    if isinstance(model, ManifoldGP):
+        noise, mean = model.noise, model.mean
+    else:  # gpytorch ExactGP duck-typing
+        noise = float(model.likelihood.noise.reshape(-1)[0])
+        mean = float(model.mean_module.constant.reshape(-1)[0])
+    return x.reshape(-1, x.shape[-1]), y.reshape(-1), base, scale, noise, mean
+
+
+class ExpectedImprovement:
+    """Analytic EI, botorch semantics (``ExpectedImprovement(model, best_f, maximize=False)``): evaluated on the
+    device by ``gabo_ei_eval``.  ``__call__`` takes ``b x 1 x dvec`` (or ``b x dvec``) points in the GP's input
+    representation (unit vectors; Mandel vectors for SPD) and returns ``b`` values."""
+
+    def __init__(self, model, best_f, maximize=False, compute='f32'):
+        self.model = model
+        self.best_f = float(best_f)
+        self.maximize = bool(maximize)
+        self.compute = compute
+        self._gp = None
+
+    def device_gp(self):
+        if self._gp is None:
+            self._gp = build_device_gp(self.model, self.best_f, self.maximize, self.compute)
+        return self._gp
+
+    def __call__(self, X):
+        X = torch.as_tensor(X)
+        gp = self.device_gp()
+        pts = X.reshape(-1, X.shape[-1])
+        if gp.manifold == _lib.SPD:
+            pts = ops.mandel_unpack(pts)
+        out = ops.ei_eval(gp, pts)
+        out = out.reshape(X.shape[:-2]) if X.dim() >= 3 else out
+        return out if X.is_cuda else out.to(X.device)
+
+
+def build_device_gp(model, best_f, maximize=False, compute='f32'):
+    """Precompute alpha = (sK + noise I)^-1 (y - m) and (sK + noise I)^-1 on the device (n <= 128, fp64)."""
+    x, y, base, scale, noise, mean = _unwrap_model(model)
+    comp = _lib.GABO_F64 if compute == 'f64' else _lib.GABO_F32
+    beta = float(base.beta.detach())
+    x = ops.to_dev64(x)
+    y = ops.to_dev64(y)
+    sign = 1.0
+    if maximize:
+        # EI for maximisation of f == EI for minimisation of -f: flip targets, mean and incumbent
+        sign = -1.0
+    if isinstance(base, SphereGaussianKernel):
+        manifold, dim = _lib.SPHERE, x.shape[-1]
+        k = ops.sphere_gram(x, x, beta, _lib.KIND_GAUSS)
+        x_dev = x
+        kxx = math.exp(-beta * math.acos(1.0 - 1e-15) ** 2)
+    elif isinstance(base, SpdAffineInvariantGaussianKernel):
+        manifold, dim = _lib.SPD, ops.mandel_dim(x.shape[-1])
+        x_dev = ops.spd_factor(x, dim, True)
+        k = ops.spd_ai_gram_from_factors(x_dev, x_dev, dim, beta, _lib.KIND_GAUSS, compute=_lib.GABO_F64,
+                                         symmetric=True)
+        kxx = 1.0  # diagonal_distance=True returns zero distances (spd_utils_torch.py:72-75)
+    else:
+        raise NotImplementedError('acquisition kernels support SphereGaussianKernel and '
+                                  'SpdAffineInvariantGaussianKernel, got %s' % type(base).__name__)
+    n = k.shape[0]
+    kn = scale * k + noise * torch.eye(n, dtype=torch.float64, device=k.device)
+    kn = 0.5 * (kn + kn.T)
+    minv = torch.linalg.inv(kn)
+    minv = 0.5 * (minv + minv.T)
+    alpha = torch.linalg.solve(kn, sign * (y - mean))
+    return ops.DeviceGP(manifold, dim, x_dev, alpha, minv, sign * mean, scale, beta, sign * best_f, kxx, comp)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# initial conditions (botorch initialize_q_batch_nonneg semantics)
+# ----------------------------------------------------------------------------------------------------------------
+
+def initialize_q_batch_nonneg(X, Y, n, eta=1.0, alpha=1e-4, generator=None):
+    """botorch.optim.initializers.initialize_q_batch_nonneg: keep the best point, sample the others with weights
+    exp(eta (Y / max - 1)) among the points with Y >= alpha max."""
+    n_samples = X.shape[0]
+    if n > n_samples:
+        raise RuntimeError('n cannot be larger than the number of provided samples')
+    if n == n_samples:
+        return X
+    max_val, max_idx = torch.max(Y, dim=0)
+    if bool(max_val <= 0):
+        warnings.warn('All acquisition values for raw sampled points are nonpositive, so initial conditions are '
+                      'being selected randomly.', BadInitialCandidatesWarning)
+        return X[torch.randperm(n_samples, device=X.device, generator=generator)][:n]
+    alpha_pos = Y >= alpha * max_val
+    while int(alpha_pos.sum()) < n:
+        alpha = 0.1 * alpha
+        alpha_pos = Y >= alpha * max_val
+    idcs_all = torch.arange(len(Y), device=Y.device)[alpha_pos]
+    weights = torch.exp(eta * (Y[alpha_pos] / max_val - 1))
+    idcs = idcs_all[torch.multinomial(weights, n, generator=generator)]
+    if not bool((idcs == max_idx).any()):
+        idcs[-1] = max_idx
+    return X[idcs]
+
+
+def _rand_points(manifold, n, generator):
+    if hasattr(manifold, 'rand_batch'):
+        return manifold.rand_batch(n, generator=generator)
+    import numpy as np  # foreign (pymanopt) manifold object: its own sampler, one point per call as in the reference
+    return ops.to_dev64(np.stack([manifold.rand() for _ in range(n)]))
+
+
+def gen_batch_initial_conditions_manifold(acq_function, manifold, bounds, q, num_restarts, raw_samples,
+                                          sample_type=torch.float64, options=None, post_processing_manifold=None):
+    """``num_restarts x q x dvec`` starting points (manifold_optimize.py:232-321).  Only q = 1 (as the reference)."""
+    options = options or {}
+    if q is None:
+        q = 1
+    if q != 1:
+        raise NotImplementedError('q != 1 is not handled (neither by the reference, manifold_optimize.py:206)')
+    seed = options.get('seed')
+    gen = None
+    if seed is not None:
+        gen = torch.Generator(device=ops.device())
+        gen.manual_seed(int(seed))
+    init_kwargs = {}
+    if 'eta' in options:
+        init_kwargs['eta'] = options.get('eta')
+    if 'alpha' in options:
+        init_kwargs['alpha'] = options.get('alpha')
+    factor, max_factor = 1, 5
+    batch_initial_conditions = None
+    while factor < max_factor:
+        with warnings.catch_warnings(record=True) as ws:
+            warnings.simplefilter('always')
+            pts = _rand_points(manifold, raw_samples * factor * q, gen)          # (n, ...) on the device
+            X_rnd = pts[:, None].to(sample_type)
+            if post_processing_manifold is not None:
+                X_rnd = post_processing_manifold(X_rnd)
+            with torch.no_grad():
+                Y_rnd = ops.to_dev64(acq_function(X_rnd)).reshape(-1)
+            batch_initial_conditions = initialize_q_batch_nonneg(X_rnd, Y_rnd, num_restarts, generator=gen,
+                                                                 **init_kwargs)
+            if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):
+                return batch_initial_conditions
+            factor += 1
+    warnings.warn('Unable to find non-zero acquisition function values - initial conditions are being selected '
+                  'randomly.', BadInitialCandidatesWarning)
+    return batch_initial_conditions
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# candidates
+# ----------------------------------------------------------------------------------------------------------------
+
+def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, solver, pre_processing_manifold=None,
+                            post_processing_manifold=None, lower_bounds=None, upper_bounds=None,
+                            inequality_constraints=None, equality_constraints=None, approx_hessian=False,
+                            solver_init_conds=False, options=None, return_info=False):
+    """All restarts solved in one launch (manifold_optimize.py:124-228).  Returns ``(candidates, acquisition values)``
+    with the shapes of the reference: ``R x 1 x dvec`` and ``R``.  Bounds are accepted and ignored, as in the
+    reference (:131-132 are never used by its body)."""
+    if inequality_constraints is not None or equality_constraints is not None:
+        raise NotImplementedError('constrained solvers are SURVEY 8f "next"; there is no CPU fallback')
+    if solver_init_conds:
+        raise NotImplementedError('solver-side initialisation (population methods) is not supported')
+    kind = _manifold_kind(manifold)
+    sopts = _solver_options(solver)
+    if not isinstance(acquisition_function, ExpectedImprovement):
+        raise NotImplementedError('the B200 optimiser evaluates ExpectedImprovement in closed form; got %s'
+                                  % type(acquisition_function).__name__)
+    gp = acquisition_function.device_gp()
+    if gp.manifold != kind:
+        raise ValueError('the manifold and the GP kernel live on different manifolds')
+    x0 = torch.as_tensor(initial_conditions).detach()
+    like = x0
+    if pre_processing_manifold is not None:
+        x0 = pre_processing_manifold(x0)
+    x0 = ops.to_dev64(x0)
+    if x0.dim() < 3 or x0.shape[1] != 1:
+        raise NotImplementedError('initial_conditions must be R x 1 x ... (q = 1, manifold_optimize.py:206)')
+    pts = x0[:, 0]
+    cand, val, iters, reason = ops.acq_rcg(gp, pts, **sopts)
+    candidates = cand[:, None]
+    if post_processing_manifold is not None:
+        candidates = post_processing_manifold(candidates)
+    if not like.is_cuda:
+        candidates, val = candidates.to(like.device), val.to(like.device)
+    if return_info:
+        return candidates, val, dict(iters=iters, reason=reason)
+    return candidates, val
+
+
+def get_best_candidates(batch_candidates, batch_values):
+    """botorch.gen.get_best_candidates: the candidate with the highest value (first index on ties, NaN loses)."""
+    slot, _ = ops.argmax_records(batch_values)
+    return batch_candidates[int(slot.item())]
+
+
+def shard_range(num, rank, world):
+    """Contiguous block partition of ``num`` restarts: rank g owns [g*num/G, (g+1)*num/G)."""
+    return (rank * num) // world, ((rank + 1) * num) // world
+
+
+def allgather_records(value, gidx, candidate, group=None):
+    """ONE all-gather of fixed-size fp64 records ``[value, global index, candidate...]``.  Device-agnostic
+    plumbing (NCCL on GPUs, gloo in the CPU tests).  Returns ``(values (G,), gidx (G,), candidates (G, ...))``."""
+    import torch.distributed as dist
+    flat = candidate.reshape(-1).to(torch.float64)
+    rec = torch.cat([value.reshape(1).to(torch.float64), gidx.reshape(1).to(torch.float64), flat])
+    world = dist.get_world_size(group)
+    out = torch.empty(world, rec.numel(), dtype=torch.float64, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group) if rec.is_cuda else \
+        dist.all_gather(list(out.unbind(0)), rec, group=group)
+    return out[:, 0], out[:, 1].to(torch.int64), out[:, 2:].reshape((world,) + tuple(candidate.shape))
+
+
+def joint_optimize_manifold(acq_function, manifold, solver, q, num_restarts, raw_samples, bounds=None,
+                            sample_type=torch.float64, options=None, inequality_constraints=None,
+                            equality_constraints=None, pre_processing_manifold=None, post_processing_manifold=None,
+                            approx_hessian=False, solver_init_conds=False):
+    """``q x dvec`` best candidate of a multi-start optimisation (manifold_optimize.py:36-120)."""
+    options = options or {}
+    distributed = bool(options.get('distributed', False))
+    ics = gen_batch_initial_conditions_manifold(acq_function=acq_function, manifold=manifold, bounds=bounds, q=None,
+                                                num_restarts=num_restarts, raw_samples=raw_samples,
+                                                sample_type=sample_type, options=options,
+                                                post_processing_manifold=post_processing_manifold)
+    lo, hi = 0, num_restarts
+    if distributed:
+        import torch.distributed as dist
+        # every rank must hold the same starts: take rank 0's
+        dist.broadcast(ics, src=0)
+        lo, hi = shard_range(num_restarts, dist.get_rank(), dist.get_world_size())
+    sub = {k: v for k, v in options.items() if k not in ('batch_limit', 'nonnegative', 'distributed', 'seed')}
+    cands, vals = gen_candidates_manifold(initial_conditions=ics[lo:hi], acquisition_function=acq_function,
+                                          manifold=manifold, solver=solver,
+                                          pre_processing_manifold=pre_processing_manifold,
+                                          post_processing_manifold=post_processing_manifold,
+                                          lower_bounds=None if bounds is None else bounds[0],
+                                          upper_bounds=None if bounds is None else bounds[1], options=sub,
+                                          inequality_constraints=inequality_constraints,
+                                          equality_constraints=equality_constraints, approx_hessian=approx_hessian,
+                                          solver_init_conds=solver_init_conds)
+    if not distributed:
+        return get_best_candidates(cands, vals)
+    gidx = torch.arange(lo, hi, device=vals.device)
+    slot, best = ops.argmax_records(vals, gidx)
+    s = int(slot.item())
+    v, g, c = allgather_records(best.reshape(()), gidx[s], ops.to_dev64(cands[s]))
+    win, _ = ops.argmax_records(v, g)
+    return c[int(win.item())]

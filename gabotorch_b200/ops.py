@@ -1,0 +1,367 @@
+"""Tensor-level wrappers of the C ABI (``include/gabo_b200.h``): torch CUDA tensors in, torch CUDA tensors out.
+
+Every function here is a thin argument-marshalling layer: it checks shapes, makes the operands contiguous fp64 device
+tensors (the reference's dtype), allocates the output and enqueues the library call on the current torch stream.
+There is no arithmetic here and no CPU fallback: a CPU tensor is copied to the device, computed there, and the result
+is returned on the device (the reference-facing classes in ``kernels.py`` / ``manifold_optimize.py`` move results
+back to the caller's device).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.GABO_F32, torch.float64: _lib.GABO_F64}
+
+
+def device():
+    """The CUDA device the library computes on (the current one).  Raises when no GPU is visible."""
+    if not torch.cuda.is_available():
+        raise _lib.GaboError('gabotorch_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else None)
+
+
+def to_dev64(x):
+    """Contiguous fp64 tensor on the compute device (no copy when it already is one)."""
+    x = torch.as_tensor(x)
+    dev = x.device if x.is_cuda else device()
+    return x.detach().to(device=dev, dtype=torch.float64).contiguous()
+
+
+def _flat_batches(x, trailing):
+    """View (..., *trailing-dims) as (B, *trailing-dims)."""
+    lead = x.shape[:x.dim() - trailing]
+    nb = 1
+    for s in lead:
+        nb *= int(s)
+    return x.reshape((nb,) + tuple(x.shape[x.dim() - trailing:])), tuple(lead)
+
+
+def _broadcast_lead(a, b, trailing):
+    la, lb = a.shape[:a.dim() - trailing], b.shape[:b.dim() - trailing]
+    lead = torch.broadcast_shapes(la, lb)
+    if tuple(la) != tuple(lead):
+        a = a.expand(tuple(lead) + tuple(a.shape[a.dim() - trailing:])).contiguous()
+    if tuple(lb) != tuple(lead):
+        b = b.expand(tuple(lead) + tuple(b.shape[b.dim() - trailing:])).contiguous()
+    return a, b, tuple(lead)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# sphere Gram (G1 + G2)
+# ----------------------------------------------------------------------------------------------------------------
+
+def sphere_gram(x1, x2, param=0.0, kind=_lib.KIND_GAUSS, diag=False, out_dtype=torch.float64):
+    """f(d(x1_i, x2_j)) for points (..., N, D) on the sphere.  Returns (..., N1, N2), or (..., N, 1) when diag."""
+    lib = _lib.load()
+    x1, x2 = to_dev64(x1), to_dev64(x2)
+    if x1.dim() < 2 or x2.dim() < 2 or x1.shape[-1] != x2.shape[-1]:
+        raise ValueError('sphere_gram: expected (..., N, D) inputs with equal D, got %s and %s'
+                         % (tuple(x1.shape), tuple(x2.shape)))
+    x1, x2, lead = _broadcast_lead(x1, x2, 2)
+    dim = x1.shape[-1]
+    b1, _ = _flat_batches(x1, 2)
+    b2, _ = _flat_batches(x2, 2)
+    n1, n2 = b1.shape[1], b2.shape[1]
+    s = _lib.stream_ptr()
+    if diag:
+        if n1 != n2:
+            raise ValueError('sphere_gram(diag=True) needs the same number of points in x1 and x2')
+        out = torch.empty(b1.shape[0], n1, 1, dtype=out_dtype, device=x1.device)
+        for b in range(b1.shape[0]):
+            _lib.check(lib.gabo_sphere_gram_diag(_p(b1[b]), _p(b2[b]), n1, dim, float(param), kind, _p(out[b]),
+                                                 _DT[out_dtype], s), 'gabo_sphere_gram_diag')
+        return out.reshape(lead + (n1, 1))
+    out = torch.empty(b1.shape[0], n1, n2, dtype=out_dtype, device=x1.device)
+    for b in range(b1.shape[0]):
+        _lib.check(lib.gabo_sphere_gram(_p(b1[b]), n1, _p(b2[b]), n2, dim, float(param), kind, _p(out[b]),
+                                        _DT[out_dtype], n2, s), 'gabo_sphere_gram')
+    return out.reshape(lead + (n1, n2))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Mandel notation (G3)
+# ----------------------------------------------------------------------------------------------------------------
+
+def mandel_dim(d_vec):
+    """Matrix size d for a Mandel vector of length d(d+1)/2 (spd_utils_torch.py:175)."""
+    d = int((-1.0 + (1.0 + 8.0 * d_vec) ** 0.5) / 2.0)
+    if d * (d + 1) // 2 != d_vec:
+        raise ValueError('%d is not a Mandel vector length d(d+1)/2' % d_vec)
+    return d
+
+
+def mandel_unpack(vec):
+    """(..., d(d+1)/2) -> (..., d, d); vector_to_symmetric_matrix_mandel_torch (spd_utils_torch.py:159-194)."""
+    lib = _lib.load()
+    v = to_dev64(vec)
+    d = mandel_dim(v.shape[-1])
+    flat = v.reshape(-1, v.shape[-1])
+    out = torch.empty(flat.shape[0], d, d, dtype=torch.float64, device=v.device)
+    _lib.check(lib.gabo_mandel_unpack(_p(flat), flat.shape[0], d, _p(out), _lib.stream_ptr()), 'gabo_mandel_unpack')
+    return out.reshape(tuple(v.shape[:-1]) + (d, d))
+
+
+def mandel_pack(mat):
+    """(..., d, d) -> (..., d(d+1)/2); symmetric_matrix_to_vector_mandel_torch (spd_utils_torch.py:197-226)."""
+    lib = _lib.load()
+    m = to_dev64(mat)
+    d = m.shape[-1]
+    if m.dim() < 2 or m.shape[-2] != d:
+        raise ValueError('mandel_pack: expected (..., d, d), got %s' % (tuple(m.shape),))
+    flat = m.reshape(-1, d, d)
+    out = torch.empty(flat.shape[0], d * (d + 1) // 2, dtype=torch.float64, device=m.device)
+    _lib.check(lib.gabo_mandel_pack(_p(flat), flat.shape[0], d, _p(out), _lib.stream_ptr()), 'gabo_mandel_pack')
+    return out.reshape(tuple(m.shape[:-2]) + (d * (d + 1) // 2,))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SPD affine-invariant Gram (G4 + G5)
+# ----------------------------------------------------------------------------------------------------------------
+
+class NotPositiveDefiniteError(_lib.GaboError):
+    """An input matrix has no Cholesky factor (the reference raises inside torch.cholesky, spd_utils_torch.py:87)."""
+
+
+def spd_factor(x, d, is_mandel, check=True):
+    """Per-point factor records [L | L^-1] for n points given as (n, dv) Mandel vectors or (n, d, d) matrices."""
+    lib = _lib.load()
+    x = to_dev64(x)
+    n = x.shape[0]
+    fs = lib.gabo_spd_factor_stride(d)
+    if fs < 0:
+        raise ValueError('SPD(%d): matrix size outside [1, %d]' % (d, _lib.MAX_SPD_DIM))
+    fac = torch.empty(n, fs, dtype=torch.float64, device=x.device)
+    flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+    _lib.check(lib.gabo_spd_factor(_p(x), n, d, 1 if is_mandel else 0, _p(fac), _p(flags), _lib.stream_ptr()),
+               'gabo_spd_factor')
+    if check and int(flags.item()) != 0:
+        raise NotPositiveDefiniteError('input contains a matrix that is not positive definite')
+    return fac
+
+
+def spd_ai_gram_from_factors(fac1, fac2, d, param=0.0, kind=_lib.KIND_GAUSS, compute=_lib.GABO_F32, symmetric=False,
+                             out_dtype=torch.float64, out=None):
+    lib = _lib.load()
+    n1, n2 = fac1.shape[0], fac2.shape[0]
+    if out is None:
+        out = torch.empty(n1, n2, dtype=out_dtype, device=fac1.device)
+    _lib.check(lib.gabo_spd_ai_gram(_p(fac1), n1, _p(fac2), n2, d, float(param), kind, compute,
+                                    1 if symmetric else 0, _p(out), _DT[out.dtype], out.stride(0),
+                                    _lib.stream_ptr()), 'gabo_spd_ai_gram')
+    return out
+
+
+def spd_ai_gram(x1, x2, param=0.0, kind=_lib.KIND_GAUSS, is_mandel=True, compute=_lib.GABO_F32,
+                out_dtype=torch.float64, check=True):
+    """f(d_AI(X1_i, X2_j)).  x: (..., N, dv) Mandel vectors (is_mandel) or (..., N, d, d) matrices -> (..., N1, N2)."""
+    same = x1 is x2
+    trailing = 2 if is_mandel else 3
+    x1 = to_dev64(x1)
+    x2 = x1 if same else to_dev64(x2)
+    d = mandel_dim(x1.shape[-1]) if is_mandel else x1.shape[-1]
+    if x1.shape[-1] != x2.shape[-1]:
+        raise ValueError('spd_ai_gram: x1 and x2 live on different SPD manifolds')
+    if not same:
+        x1, x2, lead = _broadcast_lead(x1, x2, trailing)
+    else:
+        lead = tuple(x1.shape[:x1.dim() - trailing])
+    b1, _ = _flat_batches(x1, trailing)
+    b2 = b1 if same else _flat_batches(x2, trailing)[0]
+    n1, n2 = b1.shape[1], b2.shape[1]
+    out = torch.empty(b1.shape[0], n1, n2, dtype=out_dtype, device=x1.device)
+    for b in range(b1.shape[0]):
+        f1 = spd_factor(b1[b], d, is_mandel, check=check)
+        f2 = f1 if same else spd_factor(b2[b], d, is_mandel, check=check)
+        spd_ai_gram_from_factors(f1, f2, d, param, kind, compute, symmetric=same, out=out[b])
+    return out.reshape(lead + (n1, n2))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Frobenius / log-Euclidean
+# ----------------------------------------------------------------------------------------------------------------
+
+def spd_logm(mat):
+    """Batched logm_torch (spd_utils_torch.py:13-30): (..., d, d) -> (..., d, d)."""
+    lib = _lib.load()
+    m = to_dev64(mat)
+    d = m.shape[-1]
+    flat = m.reshape(-1, d, d)
+    out = torch.empty_like(flat)
+    _lib.check(lib.gabo_spd_logm(_p(flat), flat.shape[0], d, _p(out), _lib.stream_ptr()), 'gabo_spd_logm')
+    return out.reshape(m.shape)
+
+
+def frobenius_gram(m1, m2, param=0.0, kind=_lib.KIND_GAUSS, out_dtype=torch.float64):
+    """f(||M1_i - M2_j + 1e-15||_F) for (..., N, d, d) matrices (spd_utils_torch.py:124-156)."""
+    lib = _lib.load()
+    m1, m2 = to_dev64(m1), to_dev64(m2)
+    m1, m2, lead = _broadcast_lead(m1, m2, 3)
+    d = m1.shape[-1]
+    b1, _ = _flat_batches(m1, 3)
+    b2, _ = _flat_batches(m2, 3)
+    n1, n2 = b1.shape[1], b2.shape[1]
+    out = torch.empty(b1.shape[0], n1, n2, dtype=out_dtype, device=m1.device)
+    for b in range(b1.shape[0]):
+        _lib.check(lib.gabo_frobenius_gram(_p(b1[b]), n1, _p(b2[b]), n2, d, float(param), kind, _p(out[b]),
+                                           _DT[out_dtype], n2, _lib.stream_ptr()), 'gabo_frobenius_gram')
+    return out.reshape(lead + (n1, n2))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# batched manifold operations (M1, M2)
+# ----------------------------------------------------------------------------------------------------------------
+
+def sphere_op(op, a, b, c=None):
+    lib = _lib.load()
+    a, b = to_dev64(a), to_dev64(b)
+    c = to_dev64(c) if c is not None else None
+    dim = a.shape[-1]
+    fa, fb = a.reshape(-1, dim), b.reshape(-1, dim)
+    fc = c.reshape(-1, dim) if c is not None else None
+    out = torch.empty_like(fa)
+    _lib.check(lib.gabo_sphere_op(op, _p(fa), _p(fb), _p(fc), fa.shape[0], dim, _p(out), _lib.stream_ptr()),
+               'gabo_sphere_op')
+    return out.reshape(a.shape)
+
+
+def sphere_dist(x, y):
+    lib = _lib.load()
+    x, y = to_dev64(x), to_dev64(y)
+    dim = x.shape[-1]
+    fx, fy = x.reshape(-1, dim), y.reshape(-1, dim)
+    out = torch.empty(fx.shape[0], dtype=torch.float64, device=x.device)
+    _lib.check(lib.gabo_sphere_dist(_p(fx), _p(fy), fx.shape[0], dim, _p(out), _lib.stream_ptr()),
+               'gabo_sphere_dist')
+    return out.reshape(x.shape[:-1])
+
+
+def spd_op(op, a, b, c=None):
+    lib = _lib.load()
+    a, b = to_dev64(a), to_dev64(b)
+    c = to_dev64(c) if c is not None else None
+    d = a.shape[-1]
+    fa, fb = a.reshape(-1, d, d), b.reshape(-1, d, d)
+    fc = c.reshape(-1, d, d) if c is not None else None
+    out = torch.empty_like(fa)
+    _lib.check(lib.gabo_spd_op(op, _p(fa), _p(fb), _p(fc), fa.shape[0], d, _p(out), _lib.stream_ptr()),
+               'gabo_spd_op')
+    return out.reshape(a.shape)
+
+
+def spd_scalar(what, x, b, c=None):
+    lib = _lib.load()
+    x, b = to_dev64(x), to_dev64(b)
+    c = to_dev64(c) if c is not None else None
+    d = x.shape[-1]
+    fx, fb = x.reshape(-1, d, d), b.reshape(-1, d, d)
+    fc = c.reshape(-1, d, d) if c is not None else None
+    out = torch.empty(fx.shape[0], dtype=torch.float64, device=x.device)
+    _lib.check(lib.gabo_spd_scalar(what, _p(fx), _p(fb), _p(fc), fx.shape[0], d, _p(out), _lib.stream_ptr()),
+               'gabo_spd_scalar')
+    return out.reshape(x.shape[:-2])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# acquisition (A1, A3, A4)
+# ----------------------------------------------------------------------------------------------------------------
+
+class DeviceGP:
+    """Device-resident description of the GP behind the acquisition function (struct gabo_gp_desc)."""
+
+    def __init__(self, manifold, dim, x_train, alpha, minv, mean, outputscale, beta, best_f, kxx=1.0,
+                 compute=_lib.GABO_F32):
+        self.manifold = manifold
+        self.dim = int(dim)
+        self.x_train = x_train          # sphere: (n, D) fp64; spd: (n, factor_stride) fp64 factor records
+        self.alpha = to_dev64(alpha)
+        self.minv = to_dev64(minv)
+        self.n_train = int(self.alpha.shape[0])
+        if self.n_train > _lib.MAX_TRAIN:
+            raise ValueError('at most %d training points are supported by the optimiser kernels' % _lib.MAX_TRAIN)
+        self.desc = _lib.GpDesc(manifold, self.dim, self.n_train, compute, x_train.data_ptr(),
+                                self.alpha.data_ptr(), self.minv.data_ptr(), float(mean), float(outputscale),
+                                float(beta), float(best_f), float(kxx))
+
+    @property
+    def point_shape(self):
+        return (self.dim,) if self.manifold == _lib.SPHERE else (self.dim, self.dim)
+
+
+def ei_eval(gp, x, want_grad=False):
+    """EI (and its Riemannian gradient) at r points; x: (r, D) or (r, d, d)."""
+    lib = _lib.load()
+    x = to_dev64(x)
+    r = x.shape[0]
+    ei = torch.empty(r, dtype=torch.float64, device=x.device)
+    grad = torch.empty_like(x) if want_grad else None
+    _lib.check(lib.gabo_ei_eval(ctypes.byref(gp.desc), _p(x), r, _p(ei), _p(grad), _lib.stream_ptr()),
+               'gabo_ei_eval')
+    return (ei, grad) if want_grad else ei
+
+
+def acq_rcg(gp, x0, maxiter=1000, mingradnorm=1e-6, minstepsize=1e-10, ls_maxiter=10, contraction=0.5,
+            suff_decr=0.5, initial_stepsize=1.0):
+    """Multi-start Riemannian CG on -EI.  Returns (candidates, values, iters, reasons)."""
+    lib = _lib.load()
+    x = to_dev64(x0).clone()
+    r = x.shape[0]
+    val = torch.empty(r, dtype=torch.float64, device=x.device)
+    iters = torch.empty(r, dtype=torch.int32, device=x.device)
+    reason = torch.empty(r, dtype=torch.int32, device=x.device)
+    opts = _lib.RcgOpts(int(maxiter), int(ls_maxiter), float(mingradnorm), float(minstepsize), float(contraction),
+                        float(suff_decr), float(initial_stepsize))
+    _lib.check(lib.gabo_acq_rcg(ctypes.byref(gp.desc), _p(x), r, ctypes.byref(opts), _p(val), _p(iters), _p(reason),
+                                _lib.stream_ptr()), 'gabo_acq_rcg')
+    return x, val, iters, reason
+
+
+def argmax_records(values, gidx=None):
+    """(slot, value) of the best record: highest value, lowest global index on ties, NaN = -inf."""
+    lib = _lib.load()
+    v = to_dev64(values).reshape(-1)
+    g = None
+    if gidx is not None:
+        g = torch.as_tensor(gidx).to(device=v.device, dtype=torch.int64).contiguous()
+    slot = torch.empty(1, dtype=torch.int64, device=v.device)
+    best = torch.empty(1, dtype=torch.float64, device=v.device)
+    _lib.check(lib.gabo_argmax_records(_p(v), _p(g), v.shape[0], _p(slot), _p(best), _lib.stream_ptr()),
+               'gabo_argmax_records')
+    return slot, best
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# nested projection (P1)
+# ----------------------------------------------------------------------------------------------------------------
+
+def nested_projection_matrix(w):
+    """Packed tf32 hi/lo Mandel projection operator for a (D, d) projection W (nested_spd_utils.py:13-48 in Mandel form)."""
+    lib = _lib.load()
+    w = to_dev64(w)
+    D, d = w.shape
+    size = lib.gabo_nested_projection_pack_size(D, d)
+    if size < 0:
+        raise ValueError('nested projection SPD(%d) -> SPD(%d) is not supported (d <= %d)' % (D, d, _lib.MAX_SPD_DIM))
+    p = torch.empty(size, dtype=torch.float32, device=w.device)
+    _lib.check(lib.gabo_nested_projection_matrix(_p(w), D, d, _p(p), _lib.stream_ptr()),
+               'gabo_nested_projection_matrix')
+    return p
+
+
+def nested_spd_project(x_mandel, D, d, p_padded):
+    """y_mandel (n, dvl) = x_mandel (n, dvh) P^T on the tensor cores; fp32 in / out."""
+    lib = _lib.load()
+    x = torch.as_tensor(x_mandel)
+    if not x.is_cuda:
+        x = x.to(device())
+    x = x.to(torch.float32).contiguous()
+    n = x.shape[0]
+    y = torch.empty(n, d * (d + 1) // 2, dtype=torch.float32, device=x.device)
+    _lib.check(lib.gabo_nested_spd_project(_p(x), n, D, d, _p(p_padded), _p(y), _lib.stream_ptr()),
+               'gabo_nested_spd_project')
+    return y

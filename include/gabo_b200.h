@@ -181,12 +181,14 @@ int gabo_argmax_records(const double* values, const int64_t* gidx, int64_t n, in
 
 /* ------------------------------------------------------------------------------------------------------------------
  * P1: nested SPD projection Y = W^T X W (nested_mappings/nested_spd_utils.py:13-48) in Mandel coordinates:
- *   y_mandel[n x dvl] = x_mandel[n x dvh] * P^T, P = gabo_nested_projection_matrix(W) (dvl x dvh).
- * fp32 I/O, 3xTF32 tensor-core GEMM (error ~1e-6 relative).  P must be the padded layout written by
- * gabo_nested_projection_matrix: [dvl_pad = roundup(dvl,8)] x [dvh_pad = roundup(dvh,8)] fp32.
+ *   y_mandel[n x dvl] = x_mandel[n x dvh] * P^T,  dvh = D(D+1)/2, dvl = d(d+1)/2, P built from W (D x d, fp64).
+ * fp32 I/O, 3xTF32 tensor-core contraction with fp32 accumulation (error ~1e-6 relative).
+ * gabo_nested_projection_matrix writes P, split into tf32 hi/lo parts and arranged per MMA lane, into `p_pack`
+ * (gabo_nested_projection_pack_size(D, d) floats, 16-byte aligned, caller-owned); gabo_nested_spd_project consumes it.
  * ------------------------------------------------------------------------------------------------------------------ */
-int gabo_nested_projection_matrix(const double* w, int D, int d, float* p_padded, void* stream);
-int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, int d, const float* p_padded, float* y_mandel,
+int64_t gabo_nested_projection_pack_size(int D, int d);
+int gabo_nested_projection_matrix(const double* w, int D, int d, float* p_pack, void* stream);
+int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, int d, const float* p_pack, float* y_mandel,
                             void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,87 @@
+"""The C-ABI library loads and exports every symbol include/gabo_b200.h declares; argument validation returns error
+codes without touching the GPU.  CPU only (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from gabotorch_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'gabo_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(gabo_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(build.lib_path()), 'run python -m gabotorch_b200.build'
+    assert os.path.dirname(build.lib_path()).startswith(ROOT)
+
+
+def test_every_header_symbol_is_exported_and_bound(lib):
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), 'libgabo_b200.so does not export %s' % s
+        assert s in _lib.SIGNATURES, 'no ctypes signature for %s' % s
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_version_and_struct_layout(lib):
+    assert lib.gabo_version() == 100
+    assert ctypes.sizeof(_lib.GpDesc) == 16 + 3 * 8 + 5 * 8
+    assert ctypes.sizeof(_lib.RcgOpts) == 8 + 5 * 8
+    assert lib.gabo_spd_factor_stride(3) == 12 and lib.gabo_spd_factor_stride(8) == 72
+    assert lib.gabo_spd_factor_stride(9) == -1
+    assert lib.gabo_nested_projection_pack_size(20, 5) == 27 * 32 * 2 * 4
+    assert lib.gabo_nested_projection_pack_size(5, 9) == -1
+
+
+def test_argument_errors_are_codes_not_crashes(lib):
+    null = ctypes.c_void_p(None)
+    fake = ctypes.c_void_p(4096)  # aligned, never dereferenced: validation fails first
+    assert lib.gabo_sphere_gram(null, 4, null, 4, 3, 1.0, 0, null, 0, 4, null) == -1
+    assert b'null' in lib.gabo_last_error()
+    assert lib.gabo_sphere_gram(fake, -1, fake, 4, 3, 1.0, 0, fake, 0, 4, null) == -1
+    assert lib.gabo_sphere_gram(fake, 4, fake, 4, 3, 1.0, 7, fake, 0, 4, null) == -1       # bad kind
+    assert lib.gabo_sphere_gram(fake, 4, fake, 4, 3, 1.0, 0, fake, 0, 2, null) == -1       # ld_out < n2
+    assert lib.gabo_sphere_gram(ctypes.c_void_p(4100), 4, fake, 4, 3, 1.0, 0, fake, 0, 4, null) == -2  # alignment
+    assert lib.gabo_sphere_gram(fake, 0, fake, 4, 3, 1.0, 0, fake, 0, 4, null) == 0        # empty input: nothing to do
+    assert lib.gabo_spd_ai_gram(fake, 4, fake, 4, 9, 1.0, 0, 0, 0, fake, 0, 4, null) == -1  # d > 8
+    assert b'outside' in lib.gabo_last_error()
+    assert lib.gabo_spd_ai_gram(fake, 4, fake, 5, 3, 1.0, 0, 0, 1, fake, 0, 5, null) == -1  # symmetric needs same set
+    assert lib.gabo_mandel_unpack(null, 3, 3, null, null) == -1
+    assert lib.gabo_spd_logm(fake, 3, 12, fake, null) == -1
+    assert lib.gabo_argmax_records(null, null, 4, null, null, null) == -1
+    desc = _lib.GpDesc(0, 3, 0, 0, 4096, 4096, 4096, 0.0, 1.0, 1.0, 0.0, 1.0)
+    assert lib.gabo_ei_eval(ctypes.byref(desc), fake, 4, fake, null, null) == -1           # n_train = 0
+    desc.n_train = 4
+    desc.manifold = 5
+    assert lib.gabo_ei_eval(ctypes.byref(desc), fake, 4, fake, null, null) == -1
+    assert lib.gabo_nested_spd_project(fake, 8, 4, 5, fake, fake, null) == -1              # d > D
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import gabotorch_b200 as g
+    k = g.SphereGaussianKernel(beta_min=6.5)
+    x = torch.nn.functional.normalize(torch.randn(5, 3, dtype=torch.float64), dim=-1)
+    with torch.no_grad(), pytest.raises(g.GaboError):
+        k.forward(x, x)
+    with pytest.raises(g.GaboError):
+        g.Sphere(3).exp(x[0].numpy(), 0.1 * x[1].numpy())
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'gabotorch_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text, f

@@ -1,0 +1,166 @@
+"""Acquisition path (A1-A4) through the C ABI against the oracle: EI values and closed-form Riemannian gradients,
+multi-start conjugate gradient trajectories (fp64 arithmetic follows the oracle step for step), fp32 solves reach the
+same optima, candidate selection is bit-exact.  The third-party parts of the oracle (pymanopt CG, botorch EI) are
+restated from the published algorithms: parity unpinned, see oracle/__init__.py."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from gabotorch_b200 import _lib, ops
+from oracle import gp as ogp
+from oracle import rcg as orcg
+from oracle import spd as ospd
+from oracle import sphere as osph
+
+pytestmark = pytest.mark.gpu
+
+
+def sphere_problem(D, n, beta, noise, seed):
+    rng = np.random.default_rng(seed)
+    xt = osph.rand(rng, n, D)
+    gp = ogp.make_gp('sphere', xt, osph.ackley(xt), beta=beta, noise=noise)
+    return rng, gp
+
+
+def spd_problem(d, n, beta, noise, seed):
+    rng = np.random.default_rng(seed)
+    xt = ospd.spd_sample(rng, n, d, max_cond=100.0)
+    y = ospd.ackley(ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(xt)))
+    gp = ogp.make_gp('spd', xt, y, beta=beta, noise=noise)
+    return rng, gp
+
+
+def device_gp(gp, compute):
+    if gp.manifold == 'sphere':
+        xdev = ops.to_dev64(gp.x_train)
+        return ops.DeviceGP(_lib.SPHERE, gp.x_train.shape[-1], xdev, gp.alpha, gp.minv, gp.mean, gp.outputscale,
+                            gp.beta, gp.best_f, gp.kxx, compute)
+    d = gp.x_train.shape[-1]
+    fac = ops.spd_factor(gp.x_train, d, False)
+    return ops.DeviceGP(_lib.SPD, d, fac, gp.alpha, gp.minv, gp.mean, gp.outputscale, gp.beta, gp.best_f, gp.kxx,
+                        compute)
+
+
+@pytest.mark.parametrize('D,n', [(3, 5), (6, 32), (4, 33), (9, 100), (16, 128)])
+def test_sphere_ei_and_gradient(D, n):
+    rng, gp = sphere_problem(D, n, beta=1.0 + math.log(2.0), noise=1e-2, seed=D)
+    x = osph.rand(rng, 64, D)
+    x[0] = gp.x_train[0]                                      # on a training point (distance clamp path)
+    ref = [ogp.ei_and_grad(gp, xi) for xi in x]
+    ei_ref = np.array([r[0] for r in ref])
+    g_ref = np.array([r[1] for r in ref])
+    ei64, g64 = ops.ei_eval(device_gp(gp, _lib.GABO_F64), x, want_grad=True)
+    np.testing.assert_allclose(ei64.cpu().numpy(), ei_ref, rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(g64.cpu().numpy(), g_ref, rtol=1e-7, atol=1e-10 * max(1.0, np.abs(g_ref).max()))
+    ei32, g32 = ops.ei_eval(device_gp(gp, _lib.GABO_F32), x, want_grad=True)
+    np.testing.assert_allclose(ei32.cpu().numpy(), ei_ref, rtol=2e-4, atol=1e-6 * ei_ref.max())
+    np.testing.assert_allclose(g32.cpu().numpy(), g_ref, rtol=0, atol=5e-4 * np.abs(g_ref).max())
+
+
+@pytest.mark.parametrize('d,n', [(2, 7), (3, 32), (5, 20), (8, 32), (3, 70)])
+def test_spd_ei_and_gradient(d, n):
+    rng, gp = spd_problem(d, n, beta=0.3 + math.log(2.0), noise=1e-2, seed=10 + d)
+    x = ospd.spd_sample(rng, 40, d, max_cond=100.0)
+    x[0] = gp.x_train[0]
+    ref = [ogp.ei_and_grad(gp, xi) for xi in x]
+    ei_ref = np.array([r[0] for r in ref])
+    g_ref = np.array([r[1] for r in ref])
+    ei64, g64 = ops.ei_eval(device_gp(gp, _lib.GABO_F64), x, want_grad=True)
+    np.testing.assert_allclose(ei64.cpu().numpy(), ei_ref, rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(g64.cpu().numpy(), g_ref, rtol=1e-6, atol=1e-9 * max(1.0, np.abs(g_ref).max()))
+    ei32, g32 = ops.ei_eval(device_gp(gp, _lib.GABO_F32), x, want_grad=True)
+    np.testing.assert_allclose(ei32.cpu().numpy(), ei_ref, rtol=1e-3, atol=1e-5 * ei_ref.max())
+    np.testing.assert_allclose(g32.cpu().numpy(), g_ref, rtol=0, atol=2e-3 * np.abs(g_ref).max())
+    bad = x.copy()
+    bad[5] = -bad[5]
+    ei_bad = ops.ei_eval(device_gp(gp, _lib.GABO_F64), bad).cpu().numpy()
+    assert np.isnan(ei_bad[5]) and not np.isnan(np.delete(ei_bad, 5)).any()
+
+
+@pytest.mark.parametrize('manifold,dim,n', [('sphere', 6, 32), ('sphere', 3, 12), ('spd', 3, 16), ('spd', 8, 32),
+                                            ('spd', 2, 40)])
+def test_rcg_f64_follows_the_oracle_step_for_step(manifold, dim, n):
+    steps = 25
+    if manifold == 'sphere':
+        rng, gp = sphere_problem(dim, n, beta=1.0 + math.log(2.0), noise=1e-2, seed=77 + dim)
+        x0 = osph.rand(rng, 12, dim)
+    else:
+        rng, gp = spd_problem(dim, n, beta=0.3 + math.log(2.0), noise=1e-2, seed=88 + dim)
+        x0 = ospd.spd_sample(rng, 12, dim, min_eig=0.5, max_eig=3.0)
+    opts = orcg.CGOptions(maxiter=steps)
+    ref = [orcg.solve_cg(gp, xi, opts) for xi in x0]
+    cand, val, iters, reason = ops.acq_rcg(device_gp(gp, _lib.GABO_F64), x0, maxiter=steps)
+    cand, val, iters, reason = cand.cpu().numpy(), val.cpu().numpy(), iters.cpu().numpy(), reason.cpu().numpy()
+    agree = 0
+    for i, (x, cost, it, why) in enumerate(ref):
+        same_path = (it == iters[i]) and (why == reason[i])
+        if same_path and np.allclose(cand[i], x, rtol=1e-6, atol=1e-8):
+            agree += 1
+            assert abs(val[i] + cost) <= 1e-7 * max(abs(cost), 1e-12) + 1e-13
+        # in every case the solve must not end below the oracle's optimum by more than rounding noise
+        assert val[i] >= -cost * (1 - 1e-3) - 1e-12 or val[i] >= ogp.ei_and_grad(gp, x0[i], False)[0]
+    assert agree >= len(ref) - 2, 'only %d of %d restarts follow the oracle trajectory' % (agree, len(ref))
+
+
+@pytest.mark.parametrize('manifold,dim,n,R', [('sphere', 6, 32, 256), ('spd', 3, 24, 128), ('spd', 8, 32, 64)])
+def test_rcg_f32_improves_ei_and_stays_on_the_manifold(manifold, dim, n, R):
+    if manifold == 'sphere':
+        rng, gp = sphere_problem(dim, n, beta=1.0 + math.log(2.0), noise=1e-2, seed=5)
+        x0 = osph.rand(rng, R, dim)
+    else:
+        rng, gp = spd_problem(dim, n, beta=0.3 + math.log(2.0), noise=1e-2, seed=6)
+        x0 = ospd.spd_sample(rng, R, dim, min_eig=0.5, max_eig=3.0)
+    dgp = device_gp(gp, _lib.GABO_F32)
+    ei0 = ops.ei_eval(dgp, x0).cpu().numpy()
+    cand, val, iters, reason = ops.acq_rcg(dgp, x0, maxiter=60)
+    cand, val = cand.cpu().numpy(), val.cpu().numpy()
+    assert np.all(val >= ei0 * (1 - 1e-5) - 1e-12)                 # line search never accepts an increase of the cost
+    assert np.all(np.isin(reason.cpu().numpy(), [1, 2, 3]))
+    # the reported value is the acquisition at the returned candidate (manifold_optimize.py:227), checked by the oracle
+    ref_val = np.array([ogp.ei_and_grad(gp, c, want_grad=False)[0] for c in cand[:32]])
+    np.testing.assert_allclose(val[:32], ref_val, rtol=2e-3, atol=1e-5 * ref_val.max())
+    if manifold == 'sphere':
+        np.testing.assert_allclose(np.linalg.norm(cand, axis=-1), 1.0, atol=1e-12)
+    else:
+        assert np.abs(cand - np.swapaxes(cand, -1, -2)).max() == 0.0
+        assert np.linalg.eigvalsh(cand).min() > 0
+    # the fp32 solves find the same best acquisition value as the fp64 solves (same algorithm, different rounding)
+    _, val64, _, _ = ops.acq_rcg(device_gp(gp, _lib.GABO_F64), x0, maxiter=60)
+    assert abs(val.max() - float(val64.max())) <= 2e-2 * float(val64.max())
+
+
+def test_rcg_stopping_criteria():
+    rng, gp = sphere_problem(4, 10, beta=2.0, noise=1e-2, seed=1)
+    x0 = osph.rand(rng, 8, 4)
+    dgp = device_gp(gp, _lib.GABO_F64)
+    _, _, it1, why1 = ops.acq_rcg(dgp, x0, maxiter=1)
+    assert torch.all(it1 == 0) and torch.all(why1 == 1)            # pymanopt: stops when iter + 1 >= maxiter
+    _, _, it2, why2 = ops.acq_rcg(dgp, x0, maxiter=1000, mingradnorm=1e30)
+    assert torch.all(it2 == 0) and torch.all(why2 == 2)
+    _, _, it3, why3 = ops.acq_rcg(dgp, x0, maxiter=1000)
+    assert torch.all(why3 >= 2) and int(it3.max()) < 999           # converges long before maxiter
+
+
+def test_argmax_records_is_exact_and_sharding_invariant():
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(5000).astype(np.float32).astype(np.float64)
+    v[[17, 901, 4000]] = v.max() + 1.0                            # three-way tie
+    v[5] = np.nan
+    slot, best = ops.argmax_records(v)
+    assert int(slot) == orcg.best_candidate(v) == 17 and float(best) == v[17]
+    # shards of any size, gathered in any order, select the same global index
+    for world in (2, 4, 8):
+        recs_v, recs_g = [], []
+        for r in range(world):
+            lo, hi = (r * 5000) // world, ((r + 1) * 5000) // world
+            gidx = torch.arange(lo, hi)
+            s, b = ops.argmax_records(v[lo:hi], gidx)
+            recs_v.append(float(b))
+            recs_g.append(int(gidx[int(s)]))
+        order = rng.permutation(world)
+        w, _ = ops.argmax_records(np.array(recs_v)[order], torch.tensor(np.array(recs_g)[order]))
+        assert np.array(recs_g)[order][int(w)] == 17
+    allnan = np.full(7, np.nan)
+    assert int(ops.argmax_records(allnan)[0]) == 0

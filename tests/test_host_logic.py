@@ -1,0 +1,133 @@
+"""Host-side logic that needs no GPU: parameter transforms of the kernel classes, solver / manifold recognition,
+restart sharding and the one-all-gather record exchange (gloo, world_size 2)."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import gabotorch_b200 as g
+from gabotorch_b200 import manifold_optimization as mo
+from oracle import rcg as orcg
+
+
+def test_beta_parameterisation_matches_gpytorch_greater_than():
+    k = g.SphereGaussianKernel(beta_min=6.5)
+    assert abs(float(k.beta.detach()) - (6.5 + math.log(2.0))) < 1e-6      # raw_beta = 0 -> beta_min + softplus(0)
+    k.beta = 9.25
+    assert abs(float(k.beta.detach()) - 9.25) < 1e-5
+    assert tuple(k.raw_beta.shape) == (1, 1)
+    s = g.SpdAffineInvariantGaussianKernel(beta_min=0.5)
+    s.beta = 0.75
+    assert abs(float(s.beta.detach()) - 0.75) < 1e-6
+    sk = g.ScaleKernel(k)
+    sk.outputscale = 2.5
+    assert abs(float(sk.outputscale.detach()) - 2.5) < 1e-6
+    lap = g.SphereLaplaceKernel()
+    lap.lengthscale = 0.3
+    assert abs(float(lap.lengthscale.detach()) - 0.3) < 1e-6
+
+
+def test_spd_kernel_diagonal_shortcut_needs_no_gpu():
+    k = g.SpdAffineInvariantGaussianKernel(beta_min=0.5)
+    x = torch.randn(7, 6, dtype=torch.float64)
+    out = k.forward(x, x, diagonal_distance=True)
+    assert tuple(out.shape) == (7, 1) and float((out - 1).abs().max()) == 0.0
+    # gpytorch passes diag=True; the SPD kernels' keyword is diagonal_distance, so diag lands in **params
+    # (kernels_spd.py:72) and the full path is taken -> needs the device
+    if not torch.cuda.is_available():
+        with torch.no_grad(), pytest.raises(g.GaboError):
+            k.forward(x, x, diag=True)
+
+
+def test_unsupported_triples_raise():
+    class TrustRegions:
+        pass
+
+    class Grassmann:
+        pass
+    with pytest.raises(NotImplementedError):
+        mo._solver_options(TrustRegions())
+    with pytest.raises(NotImplementedError):
+        mo._manifold_kind(Grassmann())
+    assert mo._manifold_kind(g.Sphere(4)) == 0 and mo._manifold_kind(g.PositiveDefinite(3)) == 1
+    o = mo._solver_options(g.ConjugateGradient(maxiter=200, mingradnorm=1e-5))
+    assert o['maxiter'] == 200 and o['mingradnorm'] == 1e-5 and o['ls_maxiter'] == 10 and o['contraction'] == 0.5
+    with pytest.raises(NotImplementedError):
+        g.PositiveDefinite(9)
+
+
+def test_manifold_attributes():
+    s = g.Sphere(6)
+    assert s.dim == 5 and s._shape == (6,) and s.typicaldist == math.pi
+    x = s.rand()
+    assert x.shape == (6,) and abs(np.linalg.norm(x) - 1) < 1e-12
+    p = g.PositiveDefinite(3)
+    assert p.dim == 6 and p._n == 3 and abs(p.typicaldist - math.sqrt(6)) < 1e-12
+    m = p.rand()
+    assert np.all(np.linalg.eigvalsh(m) > 0.99)
+
+
+def test_initialize_q_batch_nonneg_keeps_the_best_point():
+    torch.manual_seed(0)
+    X = torch.arange(50, dtype=torch.float64).reshape(50, 1, 1)
+    Y = torch.rand(50, dtype=torch.float64)
+    Y[17] = 5.0
+    out = mo.initialize_q_batch_nonneg(X, Y, 8)
+    assert out.shape == (8, 1, 1) and 17.0 in out.reshape(-1).tolist()
+    with pytest.warns(mo.BadInitialCandidatesWarning):
+        mo.initialize_q_batch_nonneg(X, torch.zeros(50, dtype=torch.float64), 8)
+
+
+def test_shard_range_partitions_restarts():
+    for num in (1, 5, 1024, 4097):
+        for world in (1, 2, 3, 8):
+            spans = [mo.shard_range(num, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == num
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        # every rank "optimised" its shard of 10 restarts; values are a fixed array so the answer is known
+        values = torch.tensor([0.3, 0.9, 0.1, 0.9, 0.2, float('nan'), 0.9, 0.0, 0.5, 0.4], dtype=torch.float64)
+        cands = torch.arange(10, dtype=torch.float64).reshape(10, 1).repeat(1, 3) + 0.25
+        lo, hi = mo.shard_range(10, rank, world)
+        gidx = torch.arange(lo, hi)
+        local = orcg.lexi_argmax_records(values[lo:hi].numpy(), gidx.numpy())   # selection rule (oracle = checker)
+        v, gi, c = mo.allgather_records(values[lo:hi][local], gidx[local], cands[lo:hi][local])
+        win = orcg.lexi_argmax_records(v.numpy(), gi.numpy())
+        ret[rank] = (int(gi[win]), float(v[win]), c[win].tolist(), v.tolist(), gi.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_records_world_size_2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    a, b = ret[0], ret[1]
+    assert a == b                                           # every rank reaches the same decision
+    gi, v, c, allv, allg = a
+    # single-process answer on the same value array: highest value, lowest global index on ties, NaN loses
+    assert gi == 1 and v == 0.9 and c == [1.25, 1.25, 1.25]
+    assert allg == [1, 6] and allv == [0.9, 0.9]
