@@ -30,8 +30,16 @@ def _reject_input_grad(*xs):
 
 
 def _finish(out, like):
-    """Result on the caller's device (the reference returns CPU float64 for CPU inputs)."""
-    return out if like.is_cuda else out.to(like.device)
+    """Result on the caller's device (the reference returns CPU float64 for CPU inputs).  Host results land in pinned
+    memory (torch's caching host allocator recycles the block), so the read-back runs at PCIe speed, not pageable speed."""
+    if like.is_cuda or not out.is_cuda:
+        return out
+    if out.requires_grad:
+        return out.to(like.device)
+    host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream(out.device).synchronize()
+    return host
 
 
 class _BetaKernel(Kernel):

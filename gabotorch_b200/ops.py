@@ -128,8 +128,10 @@ class NotPositiveDefiniteError(_lib.GaboError):
     """An input matrix has no Cholesky factor (the reference raises inside torch.cholesky, spd_utils_torch.py:87)."""
 
 
-def spd_factor(x, d, is_mandel, check=True):
-    """Per-point factor records [L | L^-1] for n points given as (n, dv) Mandel vectors or (n, d, d) matrices."""
+def spd_factor(x, d, is_mandel, check=True, flags=None):
+    """Per-point factor records [L | L^-1] for n points given as (n, dv) Mandel vectors or (n, d, d) matrices.
+    ``flags`` (one int32 on the device) lets a caller accumulate the not-positive-definite bit over several calls and
+    test it once (``check_spd_flags``) instead of synchronising per call."""
     lib = _lib.load()
     x = to_dev64(x)
     n = x.shape[0]
@@ -137,12 +139,19 @@ def spd_factor(x, d, is_mandel, check=True):
     if fs < 0:
         raise ValueError('SPD(%d): matrix size outside [1, %d]' % (d, _lib.MAX_SPD_DIM))
     fac = torch.empty(n, fs, dtype=torch.float64, device=x.device)
-    flags = torch.zeros(1, dtype=torch.int32, device=x.device)
+    own = flags is None
+    if own:
+        flags = torch.zeros(1, dtype=torch.int32, device=x.device)
     _lib.check(lib.gabo_spd_factor(_p(x), n, d, 1 if is_mandel else 0, _p(fac), _p(flags), _lib.stream_ptr()),
                'gabo_spd_factor')
-    if check and int(flags.item()) != 0:
-        raise NotPositiveDefiniteError('input contains a matrix that is not positive definite')
+    if check and own:
+        check_spd_flags(flags)
     return fac
+
+
+def check_spd_flags(flags):
+    if int(flags.item()) != 0:
+        raise NotPositiveDefiniteError('input contains a matrix that is not positive definite')
 
 
 def spd_ai_gram_from_factors(fac1, fac2, d, param=0.0, kind=_lib.KIND_GAUSS, compute=_lib.GABO_F32, symmetric=False,
@@ -158,8 +167,10 @@ def spd_ai_gram_from_factors(fac1, fac2, d, param=0.0, kind=_lib.KIND_GAUSS, com
 
 
 def spd_ai_gram(x1, x2, param=0.0, kind=_lib.KIND_GAUSS, is_mandel=True, compute=_lib.GABO_F32,
-                out_dtype=torch.float64, check=True):
-    """f(d_AI(X1_i, X2_j)).  x: (..., N, dv) Mandel vectors (is_mandel) or (..., N, d, d) matrices -> (..., N1, N2)."""
+                out_dtype=torch.float64, check=True, host_out=False):
+    """f(d_AI(X1_i, X2_j)).  x: (..., N, dv) Mandel vectors (is_mandel) or (..., N, d, d) matrices -> (..., N1, N2).
+    ``host_out``: the per-pair kernel stores straight into a pinned (device-mapped) HOST tensor, so the PCIe transfer
+    of the result overlaps the arithmetic instead of following it; the returned tensor is then a CPU tensor."""
     same = x1 is x2
     trailing = 2 if is_mandel else 3
     x1 = to_dev64(x1)
@@ -174,11 +185,18 @@ def spd_ai_gram(x1, x2, param=0.0, kind=_lib.KIND_GAUSS, is_mandel=True, compute
     b1, _ = _flat_batches(x1, trailing)
     b2 = b1 if same else _flat_batches(x2, trailing)[0]
     n1, n2 = b1.shape[1], b2.shape[1]
-    out = torch.empty(b1.shape[0], n1, n2, dtype=out_dtype, device=x1.device)
+    if host_out:
+        out = torch.empty(b1.shape[0], n1, n2, dtype=out_dtype, pin_memory=True)
+    else:
+        out = torch.empty(b1.shape[0], n1, n2, dtype=out_dtype, device=x1.device)
+    flags = torch.zeros(1, dtype=torch.int32, device=x1.device)
     for b in range(b1.shape[0]):
-        f1 = spd_factor(b1[b], d, is_mandel, check=check)
-        f2 = f1 if same else spd_factor(b2[b], d, is_mandel, check=check)
-        spd_ai_gram_from_factors(f1, f2, d, param, kind, compute, symmetric=same, out=out[b])
+        f1 = spd_factor(b1[b], d, is_mandel, flags=flags)
+        f2 = f1 if same else spd_factor(b2[b], d, is_mandel, flags=flags)
+        # the mirrored (symmetric) form writes columns: fine in HBM, wrong over PCIe
+        spd_ai_gram_from_factors(f1, f2, d, param, kind, compute, symmetric=same and not host_out, out=out[b])
+    if check:
+        check_spd_flags(flags)      # one synchronisation, after everything has been enqueued
     return out.reshape(lead + (n1, n2))
 
 
