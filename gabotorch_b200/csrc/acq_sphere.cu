@@ -85,7 +85,17 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
             const int i = lane + 32 * ch;
             T mk = T(0);
             if (i < n) {
-                for (int j = 0; j < n; ++j) mk = fma(Minv[j * n + i], ksh[j], mk);
+                // four independent accumulators: the n-long dependent FMA chain was the longest latency of a cost call
+                T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0);
+                int j = 0;
+                for (; j + 3 < n; j += 4) {
+                    m0 = fma(Minv[j * n + i], ksh[j], m0);
+                    m1 = fma(Minv[(j + 1) * n + i], ksh[j + 1], m1);
+                    m2 = fma(Minv[(j + 2) * n + i], ksh[j + 2], m2);
+                    m3 = fma(Minv[(j + 3) * n + i], ksh[j + 3], m3);
+                }
+                for (; j < n; ++j) m0 = fma(Minv[j * n + i], ksh[j], m0);
+                mk = (m0 + m1) + (m2 + m3);
                 ka = fma(k_l[ch], alpha[i], ka);
                 kmk = fma(k_l[ch], mk, kmk);
             }

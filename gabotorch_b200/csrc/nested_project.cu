@@ -124,11 +124,18 @@ __global__ void __launch_bounds__(kThreadsP, 1)
             __syncthreads();
         }
 
-        float acc[NT][4];
+        // Three accumulators per output tile (hi*hi, lo*hi, hi*lo): with a single one every k-step appended three
+        // DEPENDENT mma.sync to the same registers (81 in a row for dvh = 210), and with one warp per scheduler that
+        // chain, not HBM, set the tile time.  The small terms are summed first at the end.
+        float acc[NT][4], acc_lh[NT][4], acc_hl[NT][4];
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[j][q] = 0.0f;
+            for (int q = 0; q < 4; ++q) {
+                acc[j][q] = 0.0f;
+                acc_lh[j][q] = 0.0f;
+                acc_hl[j][q] = 0.0f;
+            }
         const float* r0 = A + (warp * 16 + g) * dvh;
         const float* r1 = r0 + 8 * dvh;
         const float4* bp = reinterpret_cast<const float4*>(Bp) + lane * NT;
@@ -154,11 +161,15 @@ __global__ void __launch_bounds__(kThreadsP, 1)
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const float4 b = bp[s * 32 * NT + j];  // {hi b0, hi b1, lo b0, lo b1}
-                mma_tf32(acc[j], al, b.x, b.y);
-                mma_tf32(acc[j], ah, b.z, b.w);
+                mma_tf32(acc_lh[j], al, b.x, b.y);
+                mma_tf32(acc_hl[j], ah, b.z, b.w);
                 mma_tf32(acc[j], ah, b.x, b.y);
             }
         }
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[j][q] += acc_lh[j][q] + acc_hl[j][q];
         __syncthreads();  // every warp is done with this stage (and with the previous tile's output staging)
         if (threadIdx.x == 0) {
             fence_proxy_async();

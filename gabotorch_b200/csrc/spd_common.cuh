@@ -63,38 +63,68 @@ __device__ __forceinline__ bool chol_inv(Acc x, double (&L)[tri_size(d)], double
 template <typename T>
 struct JacobiTraits;
 
+// XOR the sign bit of `s` into `v` (one LOP3).
+__device__ __forceinline__ float xor_sign(float v, float s) {
+    return __int_as_float(__float_as_int(v) ^ (__float_as_int(s) & 0x80000000));
+}
+
 template <>
 struct JacobiTraits<float> {
     static constexpr int kMaxSweeps = 10;
     static __device__ __forceinline__ float tol2() { return 3.6e-15f; }  // (6e-8)^2
-    static __device__ __forceinline__ void rotation(float a, float b, float c, float& cs, float& sn, float& t) {
-        const float zeta = (b - a) * rcp_approx(2.0f * c);
-        t = copysignf(1.0f, zeta) * rcp_approx(fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.0f)));
-        const float h = fmaf(t, t, 1.0f);
-        const float y = rsqrt_approx(h);
-        cs = y * fmaf(-0.5f * h * y, y, 1.5f);  // one Newton step: |cs^2 (1+t^2) - 1| ~ 1 ulp
-        sn = t * cs;
+    // Jacobi rotation for the 2x2 Gram block [[a, c], [c, b]] with TWO MUFU ops (no division):
+    //   h = b - a, r = sqrt(h^2 + 4c^2):  cos(2 theta) = |h| / r,  2 cos^2(theta) = (|h| + r) / r =: q2,
+    //   cs = sqrt(q2 / 2),  sn = sign(h) c / (r cs)   (|theta| <= pi/4, the inner rotation),
+    // both from rsqrt.approx of (h^2 + 4c^2) and of q2.  The MUFU results carry ~2 ulp, so (cs, sn) is renormalised
+    // with one Newton step on cs^2 + sn^2 = 1: the rotation is orthogonal to ~1e-14 and does not rescale the columns.
+    // tc = tan(theta) * c is the amount the squared column norms move: a' = a - tc, b' = b + tc.
+    static __device__ __forceinline__ void rotation(float a, float b, float c, float& cs, float& sn, float& tc) {
+        const float h = b - a;
+        const float c2 = c + c;
+        const float m = fmaf(h, h, c2 * c2);
+        const float ri = rsqrt_approx(m);
+        const float q2 = fmaf(m, ri, fabsf(h)) * ri;               // in [1, 2]
+        const float iq = rsqrt_approx(q2);                          // 1 / (sqrt2 cs)
+        const float cs0 = (q2 * iq) * 0.70710678118654752f;
+        const float sn0 = xor_sign((c2 * ri) * (iq * 0.70710678118654752f), h);
+        const float f = fmaf(-0.5f, fmaf(cs0, cs0, sn0 * sn0), 1.5f);
+        cs = cs0 * f;
+        sn = sn0 * f;
+        tc = (sn0 * (iq * 1.41421356237309505f)) * c;
     }
+    static __device__ __forceinline__ float log_(float x) { return __logf(x); }          // lg2.approx: |err| <= 1.7e-7
+    static __device__ __forceinline__ float dist_(float s) { return sqrt_approx(s + 1e-15f); }
 };
 
 template <>
 struct JacobiTraits<double> {
     static constexpr int kMaxSweeps = 12;
     static __device__ __forceinline__ double tol2() { return 1e-26; }  // (1e-13)^2
-    static __device__ __forceinline__ void rotation(double a, double b, double c, double& cs, double& sn, double& t) {
+    static __device__ __forceinline__ void rotation(double a, double b, double c, double& cs, double& sn, double& tc) {
         // The angle only has to be approximately the Jacobi angle (it sets the convergence rate, not the accuracy), so
         // it is computed on the fp32 MUFU path; cs is then normalised in fp64 so that the rotation is orthogonal to 1e-16.
         const float zf = static_cast<float>(b - a) * rcp_approx(2.0f * static_cast<float>(c));
         const float tf = copysignf(1.0f, zf) * rcp_approx(fabsf(zf) + sqrt_approx(fmaf(zf, zf, 1.0f)));
-        t = static_cast<double>(tf);
+        const double t = static_cast<double>(tf);
         cs = rsqrt(fma(t, t, 1.0));
         sn = t * cs;
+        // exact norm update for an inexact angle: a' = cs^2 (a + t^2 b - 2 t c); expressed as a - tc_p below would
+        // need two values, so the caller recomputes the norms from the columns in fp64 (see jacobi_onesided).
+        tc = t * c;
     }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float dist_(float s) { return sqrtf(s + 1e-15f); }
 };
 
+// Stopping rule: a rotation is applied while c^2 > tol2 * a * b; the sweeps end when no lane of the warp rotated.
+// (Stopping a sweep earlier on the strength of quadratic convergence is NOT safe here: for nearly identical matrices
+// W = I + E the iteration converges relative to |E|, not to the diagonal, and d^2 ~ |E|_F^2 needs the off-diagonal part
+// resolved to ~1e-7 of the DIAGONAL to keep |d - d_ref| <= 1e-6.)
+// Converged rotations are skipped per lane, so the result of a pair does not depend on the other pairs of its warp.
 template <int d, typename T>
 __device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
     using Tr = JacobiTraits<T>;
+    constexpr bool kF32 = sizeof(T) == 4;
 #pragma unroll
     for (int k = 0; k < d; ++k) {
         T s = T(0);
@@ -112,19 +142,24 @@ __device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
 #pragma unroll
                 for (int r = 0; r < d; ++r) c = fma(G[r][p], G[r][q], c);
                 const T a = lam[p], b = lam[q];
-                if (c * c > Tr::tol2() * a * b) {
+                if (c * c > Tr::tol2() * (a * b)) {
                     rotated = true;
-                    T cs, sn, t;
-                    Tr::rotation(a, b, c, cs, sn, t);
+                    T cs, sn, tc;
+                    Tr::rotation(a, b, c, cs, sn, tc);
 #pragma unroll
                     for (int r = 0; r < d; ++r) {
                         const T gp = G[r][p], gq = G[r][q];
                         G[r][p] = fma(cs, gp, -sn * gq);
                         G[r][q] = fma(sn, gp, cs * gq);
                     }
-                    const T c2 = cs * cs, tc2 = T(2) * t * c;
-                    lam[p] = c2 * (fma(t * t, b, a) - tc2);
-                    lam[q] = c2 * (fma(t * t, a, b) + tc2);
+                    if (kF32) {
+                        lam[p] = a - tc;
+                        lam[q] = b + tc;
+                    } else {  // the fp64 angle is approximate: use the exact expression for the rotated norms
+                        const T c2 = cs * cs, s2 = sn * sn, x = T(2) * cs * sn * c;
+                        lam[p] = fma(c2, a, fma(s2, b, -x));
+                        lam[q] = fma(s2, a, fma(c2, b, x));
+                    }
                 }
             }
         }
@@ -159,15 +194,18 @@ __device__ __forceinline__ void tri_product(AccA A, AccL L, T (&G)[d][d]) {
 }
 
 // Reference tail (spd_utils_torch.py:108-120): eigenvalues rounded to fp32, log / square / sum / sqrt(+1e-15) in fp32.
+// The fp32 compute path takes the logs and the root on the MUFU (abs. error of d <= 3e-7, inside the 1e-6 floor the
+// reference's own float32 eigenvalues leave); the fp64 ("reference-grade") path uses the IEEE-accurate logf / sqrtf.
 template <int d, typename T>
 __device__ __forceinline__ float ai_distance_from_eigs(const T (&lam)[d]) {
+    using Tr = JacobiTraits<T>;
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < d; ++k) {
-        const float l = logf(static_cast<float>(lam[k]));
+        const float l = Tr::log_(static_cast<float>(lam[k]));
         s = fmaf(l, l, s);
     }
-    return sqrtf(s + 1e-15f);
+    return Tr::dist_(s);
 }
 
 

@@ -58,12 +58,24 @@ __global__ void spd_factor_kernel(const double* __restrict__ x, int64_t n, int i
 // ------------------------------------------------------------------------------------------------------------
 // per-pair kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int KIND>
-__device__ __forceinline__ float finish(float dist, double param) {
+// K = exp(-param d^2) / exp(-param d) / d.  `kp` = -param log2(e) split into two floats by the launcher.
+// fp32 compute path: d^2 and the product with (k_hi + k_lo) in fp32 (relative error of the exponent 6e-8, i.e. of K at
+// most 6e-8 * param d^2), 2^t on the MUFU.  fp64 ("reference-grade") path: the exponent is reduced in fp64.
+struct ExpParams {
+    float k_hi, k_lo;
+    double param;
+};
+
+template <int KIND, typename T>
+__device__ __forceinline__ float finish(float dist, const ExpParams& kp) {
     if (KIND == GABO_KIND_DIST) return dist;
+    if (sizeof(T) == 4) {
+        const float v = (KIND == GABO_KIND_GAUSS) ? dist * dist : dist;   // kernels_spd.py:96-98 / :185
+        return ex2_approx(fmaf(v, kp.k_hi, v * kp.k_lo));
+    }
     const double dd = static_cast<double>(dist);
-    if (KIND == GABO_KIND_GAUSS) return exp_neg_arg(-param * dd * dd);  // kernels_spd.py:96-98
-    return exp_neg_arg(-param * dd);                                     // kernels_spd.py:185
+    if (KIND == GABO_KIND_GAUSS) return exp_neg_arg(-kp.param * dd * dd);
+    return exp_neg_arg(-kp.param * dd);
 }
 
 // Tile enumeration.  General: t = jb * tiles_i + ib (rows fastest, so a CTA keeps its column block).  Symmetric
@@ -90,6 +102,26 @@ struct TileMap {
     }
 };
 
+// A CTA walks a contiguous range of tile ids: the (column block, first row) of the first one is decoded once (64-bit
+// divisions, a square root in the symmetric case), every following tile is an increment -- the decode used to cost
+// ~100 integer instructions per tile, comparable to a whole pair at tile_m = 4.
+struct TileCursor {
+    int64_t jb, i0, i_end;   // column block, first row of the tile, first row past this column block's tiles
+    __device__ void start(const TileMap& map, int64_t t, int64_t n1) {
+        map.decode(t, jb, i0);
+        i_end = map.symmetric ? (jb + 1) * kThreads : map.tiles_i * map.tile_m;
+        (void)n1;
+    }
+    __device__ void advance(const TileMap& map) {
+        i0 += map.tile_m;
+        if (i0 >= i_end) {
+            i0 = 0;
+            ++jb;
+            if (map.symmetric) i_end += kThreads;
+        }
+    }
+};
+
 template <int d>
 struct PairCfg {
     static constexpr int kMaxTileM = (d <= 5) ? 32 : 8;  // keeps static shared memory under 48 KB for d = 8
@@ -98,7 +130,7 @@ struct PairCfg {
 template <int d, typename T, typename OutT, int KIND>
 __global__ void __launch_bounds__(kThreads)
     spd_ai_gram_kernel(const double* __restrict__ fac1, int64_t n1, const double* __restrict__ fac2, int64_t n2,
-                       double param, OutT* __restrict__ out, int64_t ld_out, TileMap map, int64_t tiles_total) {
+                       ExpParams kp, OutT* __restrict__ out, int64_t ld_out, TileMap map, int64_t tiles_total) {
     constexpr int TRI = tri_size(d);
     constexpr int FS = factor_stride(d);
     constexpr bool kLInRegs = (d <= 5);
@@ -120,19 +152,20 @@ __global__ void __launch_bounds__(kThreads)
     __syncthreads();
 
     uint32_t phase_bits = 0u;
-    // returns the number of rows of tile t (0 = empty edge tile: nothing is staged and nothing is waited for)
-    auto issue = [&](int64_t t, int buf) {
-        int64_t jb, i0;
-        map.decode(t, jb, i0);
-        const int rows = static_cast<int>(imax(0, imin(map.tile_m, n1 - i0)));
+    // stage the rows of the tile under cursor `c` (an empty edge tile stages nothing and nothing is waited for)
+    auto issue = [&](const TileCursor& c, int buf) {
+        const int rows = static_cast<int>(imax(0, imin(map.tile_m, n1 - c.i0)));
         if (rows > 0 && threadIdx.x == 0) {
             const uint32_t bytes = static_cast<uint32_t>(rows) * FS * sizeof(double);  // FS even -> multiple of 16
             mbar_expect_tx(&bar[buf], bytes);
-            tma_load_1d(&fs[buf][0], fac1 + i0 * FS, bytes, &bar[buf]);
+            tma_load_1d(&fs[buf][0], fac1 + c.i0 * FS, bytes, &bar[buf]);
         }
     };
 
-    issue(t_begin, 0);
+    TileCursor cur, nxt;
+    cur.start(map, t_begin, n1);
+    nxt = cur;
+    issue(cur, 0);
     int64_t jb_loaded = -1;
     double Lreg[kLInRegs ? TRI : 1];
     int64_t j = 0;
@@ -140,12 +173,13 @@ __global__ void __launch_bounds__(kThreads)
 
     for (int64_t t = t_begin; t < t_end; ++t) {
         const int buf = static_cast<int>((t - t_begin) & 1);
-        int64_t jb, i0;
-        map.decode(t, jb, i0);
+        cur = nxt;
+        const int64_t jb = cur.jb, i0 = cur.i0;
         const int rows = static_cast<int>(imax(0, imin(map.tile_m, n1 - i0)));
 
         __syncthreads();  // everyone is done with the buffer that is refilled next, and with ls
-        if (t + 1 < t_end) issue(t + 1, buf ^ 1);
+        nxt.advance(map);
+        if (t + 1 < t_end) issue(nxt, buf ^ 1);
         if (rows <= 0) continue;
 
         if (jb != jb_loaded) {
@@ -176,7 +210,7 @@ __global__ void __launch_bounds__(kThreads)
             }
             T lam[d];
             jacobi_onesided<d, T>(G, lam);
-            const float v = finish<KIND>(ai_distance_from_eigs<d, T>(lam), param);
+            const float v = finish<KIND, T>(ai_distance_from_eigs<d, T>(lam), kp);
             if (jvalid) {
                 const int64_t gi = i0 + i;
                 if (!map.symmetric) {
@@ -211,8 +245,13 @@ int launch_pair(const double* fac1, int64_t n1, const double* fac2, int64_t n2, 
     map.symmetric = symmetric ? 1 : 0;
     const int64_t tiles = count(tile_m);
     const int64_t grid = imin(tiles, slots);
+    ExpParams kp;
+    const double k2 = -param * 1.4426950408889634074;
+    kp.k_hi = static_cast<float>(k2);
+    kp.k_lo = static_cast<float>(k2 - static_cast<double>(kp.k_hi));
+    kp.param = param;
     spd_ai_gram_kernel<d, T, OutT, KIND><<<static_cast<unsigned>(grid), kThreads, 0, stream>>>(
-        fac1, n1, fac2, n2, param, static_cast<OutT*>(out), ld_out, map, tiles);
+        fac1, n1, fac2, n2, kp, static_cast<OutT*>(out), ld_out, map, tiles);
     return check_launch("spd_ai_gram_kernel");
 }
 
