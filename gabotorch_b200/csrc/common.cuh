@@ -147,6 +147,33 @@ __device__ __forceinline__ float exp_neg_arg(double a) {
     return r * __int_as_float((n1 + 127) << 23) * __int_as_float((n2 + 127) << 23);
 }
 
+// Packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2): one issue slot for two fp32 lanes of work.  The FMA pipe
+// spends two cycles on it, so peak FLOP/s is unchanged -- the gain is for ISSUE-bound kernels (measured on B200:
+// 3.8 FFMA or 2.0 FFMA2 warp-instructions per clock per SM, scripts/micro/ffma2_bench.cu).
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 f2_from(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(d);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -174,6 +174,90 @@ __device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same one-sided Jacobi for TWO independent problems per thread on the packed fp32x2 pipe (.x = problem 0,
+// .y = problem 1).  The Gram kernel is issue-bound and ~60 % of its instructions are fp32 FMA/MUL/ADD; packing two
+// pairs halves those issue slots (FFMA2 / FMUL2 / FADD2).  A rotation is executed when EITHER problem needs it; the
+// other one gets the exact identity (cs = 1, sn = 0, tc = 0), so each problem sees exactly the rotations it would see
+// alone and its result does not depend on its partner.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 abs2(float2 v) { return make_float2(fabsf(v.x), fabsf(v.y)); }
+__device__ __forceinline__ float2 rsqrt2(float2 v) { return make_float2(rsqrt_approx(v.x), rsqrt_approx(v.y)); }
+
+template <int d>
+__device__ __forceinline__ void jacobi_onesided_x2(float2 (&G)[d][d], float2 (&lam)[d]) {
+    using Tr = JacobiTraits<float>;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        float2 s = mul2(G[0][k], G[0][k]);
+#pragma unroll
+        for (int r = 1; r < d; ++r) s = fma2(G[r][k], G[r][k], s);
+        lam[k] = s;
+    }
+    for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < d - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < d; ++q) {
+                float2 c = mul2(G[0][p], G[0][q]);
+#pragma unroll
+                for (int r = 1; r < d; ++r) c = fma2(G[r][p], G[r][q], c);
+                const float2 a = lam[p], b = lam[q];
+                const float2 cc = mul2(c, c), thr = mul2(mul2(a, b), splat2(Tr::tol2()));
+                const bool n0 = cc.x > thr.x, n1 = cc.y > thr.y;
+                if (n0 || n1) {
+                    rotated = true;
+                    // JacobiTraits<float>::rotation, two at a time
+                    const float2 h = sub2(b, a), c2 = add2(c, c);
+                    const float2 m = fma2(h, h, mul2(c2, c2));
+                    const float2 ri = rsqrt2(m);
+                    const float2 q2 = mul2(fma2(m, ri, abs2(h)), ri);
+                    const float2 iqs = mul2(rsqrt2(q2), splat2(0.70710678118654752f));
+                    const float2 cs0 = mul2(q2, iqs);
+                    float2 sn0 = mul2(mul2(c2, ri), iqs);
+                    sn0.x = xor_sign(sn0.x, h.x);
+                    sn0.y = xor_sign(sn0.y, h.y);
+                    const float2 f = fma2(splat2(-0.5f), fma2(cs0, cs0, mul2(sn0, sn0)), splat2(1.5f));
+                    float2 cs = mul2(cs0, f), sn = mul2(sn0, f);
+                    float2 tc = mul2(mul2(sn0, add2(iqs, iqs)), c);
+                    if (!n0) { cs.x = 1.0f; sn.x = 0.0f; tc.x = 0.0f; }
+                    if (!n1) { cs.y = 1.0f; sn.y = 0.0f; tc.y = 0.0f; }
+                    const float2 nsn = make_float2(-sn.x, -sn.y);
+#pragma unroll
+                    for (int r = 0; r < d; ++r) {
+                        const float2 gp = G[r][p], gq = G[r][q];
+                        G[r][p] = fma2(cs, gp, mul2(nsn, gq));
+                        G[r][q] = fma2(sn, gp, mul2(cs, gq));
+                    }
+                    lam[p] = sub2(a, tc);
+                    lam[q] = add2(b, tc);
+                }
+            }
+        }
+        if (!__any_sync(__activemask(), rotated)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        float2 s = mul2(G[0][k], G[0][k]);
+#pragma unroll
+        for (int r = 1; r < d; ++r) s = fma2(G[r][k], G[r][k], s);
+        lam[k] = s;
+    }
+}
+
+// sum_k log2(lambda_k)^2 for both problems (the natural-log scale ln2^2 is applied by the caller).
+template <int d>
+__device__ __forceinline__ float2 sum_log2_sq_x2(const float2 (&lam)[d]) {
+    float2 s = splat2(0.0f);
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        const float2 l = make_float2(__log2f(lam[k].x), __log2f(lam[k].y));
+        s = fma2(l, l, s);
+    }
+    return s;
+}
+
 // G = A * L for packed lower-triangular A (rows) and L, accumulated in fp64, returned in T.
 template <int d, typename T, typename AccA, typename AccL>
 __device__ __forceinline__ void tri_product(AccA A, AccL L, T (&G)[d][d]) {

@@ -125,6 +125,7 @@ struct TileCursor {
 template <int d>
 struct PairCfg {
     static constexpr int kMaxTileM = (d <= 5) ? 32 : 8;  // keeps static shared memory under 48 KB for d = 8
+    static constexpr bool kPacked = (d <= 5);            // G for two problems fits the register file
 };
 
 template <int d, typename T, typename OutT, int KIND>
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int TRI = tri_size(d);
     constexpr int FS = factor_stride(d);
     constexpr bool kLInRegs = (d <= 5);
+    constexpr bool kX2 = PairCfg<d>::kPacked && sizeof(T) == 4;   // two pairs per thread on the fp32x2 pipe
     constexpr int kMaxTileM = PairCfg<d>::kMaxTileM;
     __shared__ __align__(16) double fs[2][kMaxTileM * FS];              // staged x1 records (we read the A halves)
     __shared__ double ls[kLInRegs ? 1 : TRI * kThreads];                // L_j, entry-major (conflict-free), d >= 6 only
@@ -199,26 +201,68 @@ __global__ void __launch_bounds__(kThreads)
         mbar_wait(&bar[buf], (phase_bits >> buf) & 1u);
         phase_bits ^= (1u << buf);
 
-        for (int i = 0; i < rows; ++i) {
-            const double* Ai = &fs[buf][i * FS + TRI];
-            T G[d][d];
-            if (kLInRegs) {
-                tri_product<d, T>([&](int e) { return Ai[e]; }, [&](int e) { return Lreg[kLInRegs ? e : 0]; }, G);
-            } else {
-                tri_product<d, T>([&](int e) { return Ai[e]; },
-                                  [&](int e) { return ls[e * kThreads + threadIdx.x]; }, G);
+        auto store = [&](int64_t gi, float v) {
+            if (!jvalid) return;
+            if (!map.symmetric) {
+                st_cs(out + gi * ld_out + j, static_cast<OutT>(v));
+            } else if (j >= gi) {
+                out[gi * ld_out + j] = static_cast<OutT>(v);
+                if (j > gi) out[j * ld_out + gi] = static_cast<OutT>(v);
             }
-            T lam[d];
-            jacobi_onesided<d, T>(G, lam);
-            const float v = finish<KIND, T>(ai_distance_from_eigs<d, T>(lam), kp);
-            if (jvalid) {
-                const int64_t gi = i0 + i;
-                if (!map.symmetric) {
-                    st_cs(out + gi * ld_out + j, static_cast<OutT>(v));
-                } else if (j >= gi) {
-                    out[gi * ld_out + j] = static_cast<OutT>(v);
-                    if (j > gi) out[j * ld_out + gi] = static_cast<OutT>(v);
+        };
+        auto Lj = [&](int e) { return kLInRegs ? Lreg[kLInRegs ? e : 0] : ls[e * kThreads + threadIdx.x]; };
+
+        if (kX2) {
+            // two rows of the tile per step, same column: (A_i, A_i+1) x L_j on the packed fp32x2 pipe
+            for (int i = 0; i < rows; i += 2) {
+                const int i1 = min(i + 1, rows - 1);            // odd tail: the partner repeats row i (not stored)
+                const double* A0 = &fs[buf][i * FS + TRI];
+                const double* A1 = &fs[buf][i1 * FS + TRI];
+                float2 G[d][d];
+#pragma unroll
+                for (int r = 0; r < d; ++r) {
+#pragma unroll
+                    for (int c = 0; c < d; ++c) {
+                        if (c <= r) {
+                            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                            for (int k = c; k <= r; ++k) {
+                                const double l = Lj(tri_idx(k, c));
+                                s0 = fma(A0[tri_idx(r, k)], l, s0);
+                                s1 = fma(A1[tri_idx(r, k)], l, s1);
+                            }
+                            G[r][c] = make_float2(static_cast<float>(s0), static_cast<float>(s1));
+                        } else {
+                            G[r][c] = make_float2(0.0f, 0.0f);
+                        }
+                    }
                 }
+                float2 lam[d];
+                jacobi_onesided_x2<d>(G, lam);
+                // spd_utils_torch.py:117-120 in fp32: d^2 = sum log(lambda)^2 + 1e-15, log = ln2 * log2 (MUFU)
+                const float2 d2 = fma2(sum_log2_sq_x2<d>(lam), splat2(0.48045301391820142f), splat2(1e-15f));
+                float2 v;
+                if (KIND == GABO_KIND_GAUSS) {
+                    const float2 t = fma2(d2, splat2(kp.k_hi), mul2(d2, splat2(kp.k_lo)));   // kernels_spd.py:96-98
+                    v = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                } else {
+                    v = make_float2(sqrt_approx(d2.x), sqrt_approx(d2.y));
+                    if (KIND == GABO_KIND_LAPLACE) {
+                        const float2 t = fma2(v, splat2(kp.k_hi), mul2(v, splat2(kp.k_lo)));  // kernels_spd.py:185
+                        v = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    }
+                }
+                store(i0 + i, v.x);
+                if (i1 != i) store(i0 + i1, v.y);
+            }
+        } else {
+            for (int i = 0; i < rows; ++i) {
+                const double* Ai = &fs[buf][i * FS + TRI];
+                T G[d][d];
+                tri_product<d, T>([&](int e) { return Ai[e]; }, Lj, G);
+                T lam[d];
+                jacobi_onesided<d, T>(G, lam);
+                store(i0 + i, finish<KIND, T>(ai_distance_from_eigs<d, T>(lam), kp));
             }
         }
     }
