@@ -495,6 +495,12 @@ class Bench:
 
     def run(self):
         args = self.args
+        if args.only == 'acq':      # developer switch: just the acquisition extra
+            e = self.extra_acq_sphere(R=args.acq_restarts, T=200)
+            self.clocks.stop()
+            if self.rank == 0:
+                print(json.dumps(e), flush=True)
+            return 0
         head = self.headline()
         extras = []
         if not args.no_extras:
@@ -541,6 +547,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-extras', action='store_true')
+    ap.add_argument('--only', default='', help='developer switch: run a single extra (acq)')
+    ap.add_argument('--acq-restarts', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-rows', type=int, default=256, help='rows of the N=2048 Gram in the cpu_baseline sample')
     ap.add_argument('--ref-rows', type=int, default=16, help='rows per step of the reference arm')

@@ -4,6 +4,9 @@
 // Manifold operations used by the solver are pymanopt's Sphere (reference call sites manifold_optimize.py:207-221,
 // numpy statements Riemannian_utils/sphere_utils.py:14-123): retr(x,u) = (x+u)/|x+u|, transp(x,y,u) = u - <y,u> y,
 // inner = Euclidean dot, Log_x(y) = (y - <x,y> x) * theta / |y - <x,y> x|.
+#include <cstdlib>
+#include <type_traits>
+
 #include "acq_common.cuh"
 
 namespace gabo {
@@ -272,88 +275,130 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
 // alpha also live in registers.  Warp shuffles remain only where the math sums over training points: the posterior
 // mean / variance (2 sums per cost call) and the gradient (D + 1 sums).  Same formulas as the kernel above.
 // ---------------------------------------------------------------------------------------------------------------
+// Four consecutive shared-memory values with one (fp32) or two (fp64) vector loads.
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// Per-warp evaluator: lanes own the training points (coordinates and alpha in registers), the query point is replicated.
+// For n <= 32 (NCH == 1, the regime of the reference's BO loops: 5..35 points) the lane's row of K^-1 lives in
+// registers too, so the K^-1 k product is 8 broadcast vector loads of k + 32 FMAs with no address arithmetic.
 template <typename T, int DP, int NCH>
-__global__ void __launch_bounds__(kAcqWarps * 32)
-    sphere_acq_reg_kernel(GpParams gp, RcgParams opt, int mode, double* __restrict__ x_io, int64_t r,
-                          double* __restrict__ value, double* __restrict__ grad_out, int32_t* __restrict__ iters,
-                          int32_t* __restrict__ reason) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = gp.n, D = gp.dim;
-    const int npad = (n + 3) & ~3;
-    SmemCarver cv;
-    T* Minv = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * npad * n));       // rows n..npad-1 are zero
-    T* kbase = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * kAcqWarps * npad));
-    for (int e = threadIdx.x; e < npad * n; e += blockDim.x) Minv[e] = (e < n * n) ? static_cast<T>(gp.minv[e]) : T(0);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t rid = static_cast<int64_t>(blockIdx.x) * kAcqWarps + warp;
-    if (rid >= r) return;
-    T* ksh = kbase + warp * npad;
-
-    // training points owned by this lane
+struct SphereEval {
+    static constexpr bool kRowInRegs = (NCH == 1);
+    static constexpr int kKsh = kRowInRegs ? 32 : 0;       // minimum size of the per-warp k buffer
     T Xi[NCH][DP], al[NCH];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-        const int i = lane + 32 * ch;
-        al[ch] = (i < n) ? static_cast<T>(gp.alpha[i]) : T(0);
-#pragma unroll
-        for (int k = 0; k < DP; ++k) Xi[ch][k] = (i < n && k < D) ? static_cast<T>(gp.x_train[i * D + k]) : T(0);
-    }
-    const T s_out = static_cast<T>(gp.outputscale), beta = static_cast<T>(gp.beta);
-    T c_l[NCH], th_l[NCH], k_l[NCH], mk_l[NCH];
+    T Mrow[kRowInRegs ? 32 : 1];
+    T c_l[NCH], th2_l[NCH], k_l[NCH], mk_l[NCH];   // per-point quantities of the last cost() call, kept for grad()
     EiScalars<T> sc;
+    T s_out, beta;
+    int n, npad, lane;
+    const T* Minv;   // shared: npad x n, rows n..npad-1 zero
+    T* ksh;          // shared: max(npad, kKsh) values, private to the warp
 
-    auto dot = [](const T (&a)[DP], const T (&b)[DP]) {
+    static __host__ __device__ int ksh_size(int n_train) {
+        const int np = (n_train + 3) & ~3;
+        return np > kKsh ? np : kKsh;
+    }
+
+    static __device__ __forceinline__ T dot(const T (&a)[DP], const T (&b)[DP]) {
         T s = a[0] * b[0];
 #pragma unroll
         for (int k = 1; k < DP; ++k) s = fma(a[k], b[k], s);
         return s;
-    };
+    }
 
-    auto cost_at = [&](const T (&p)[DP]) -> T {
+    __device__ __forceinline__ void load(const GpParams& gp, int lane_, const T* minv_s, T* ksh_w) {
+        n = gp.n;
+        npad = (n + 3) & ~3;
+        lane = lane_;
+        Minv = minv_s;
+        ksh = ksh_w;
+        s_out = static_cast<T>(gp.outputscale);
+        beta = static_cast<T>(gp.beta);
+        const int D = gp.dim;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int i = lane + 32 * ch;
+            al[ch] = (i < n) ? static_cast<T>(gp.alpha[i]) : T(0);
+#pragma unroll
+            for (int k = 0; k < DP; ++k) Xi[ch][k] = (i < n && k < D) ? static_cast<T>(gp.x_train[i * D + k]) : T(0);
+        }
+        if (kRowInRegs) {
+#pragma unroll
+            for (int j = 0; j < (kRowInRegs ? 32 : 1); ++j) Mrow[j] = (lane < n && j < n) ? minv_s[j * n + lane] : T(0);
+        }
+    }
+
+    // cost(p) = -EI(p); all lanes return the same value
+    __device__ __forceinline__ T cost(const T (&p)[DP], const GpParams& gp) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
             const int i = lane + 32 * ch;
             T cc = dot(Xi[ch], p);
             cc = fmin(fmax(cc, T(-1) + M<T>::clamp_eps()), T(1) - M<T>::clamp_eps());
-            const T tt = M<T>::acos_(cc);
-            const T kk = (i < n) ? s_out * M<T>::exp_(-beta * tt * tt) : T(0);
-            if (i < npad) ksh[i] = kk;
+            const T t2 = M<T>::theta2_(cc);
+            const T kk = (i < n) ? s_out * M<T>::exp_neg_(-beta * t2) : T(0);
+            if (kRowInRegs || i < npad) ksh[i] = kk;
             c_l[ch] = cc;
-            th_l[ch] = tt;
+            th2_l[ch] = t2;
             k_l[ch] = kk;
         }
         __syncwarp();
         T ka = T(0), kmk = T(0);
+        if (kRowInRegs) {
+            T m[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-            const int i = lane + 32 * ch;
-            T mk = T(0);
-            if (i < n) {
-                T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0);
-                for (int j = 0; j < npad; j += 4) {     // K^-1 is symmetric: row i read as column i, conflict-free
-                    m0 = fma(Minv[j * n + i], ksh[j], m0);
-                    m1 = fma(Minv[(j + 1) * n + i], ksh[j + 1], m1);
-                    m2 = fma(Minv[(j + 2) * n + i], ksh[j + 2], m2);
-                    m3 = fma(Minv[(j + 3) * n + i], ksh[j + 3], m3);
-                }
-                mk = (m0 + m1) + (m2 + m3);
+            for (int j = 0; j < 32; j += 4) {
+                T kv[4];
+                ld4(ksh + j, kv);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) m[q] = fma(Mrow[kRowInRegs ? j + q : 0], kv[q], m[q]);
             }
-            mk_l[ch] = mk;
-            ka = fma(k_l[ch], al[ch], ka);
-            kmk = fma(k_l[ch], mk, kmk);
+            const T mk = (m[0] + m[1]) + (m[2] + m[3]);
+            mk_l[0] = mk;
+            ka = k_l[0] * al[0];
+            kmk = k_l[0] * mk;
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int i = lane + 32 * ch;
+                T mk = T(0);
+                if (i < n) {
+                    T m0 = T(0), m1 = T(0), m2 = T(0), m3 = T(0);
+                    for (int j = 0; j < npad; j += 4) {     // K^-1 is symmetric: row i read as column i, conflict-free
+                        T kv[4];
+                        ld4(ksh + j, kv);
+                        m0 = fma(Minv[j * n + i], kv[0], m0);
+                        m1 = fma(Minv[(j + 1) * n + i], kv[1], m1);
+                        m2 = fma(Minv[(j + 2) * n + i], kv[2], m2);
+                        m3 = fma(Minv[(j + 3) * n + i], kv[3], m3);
+                    }
+                    mk = (m0 + m1) + (m2 + m3);
+                }
+                mk_l[ch] = mk;
+                ka = fma(k_l[ch], al[ch], ka);
+                kmk = fma(k_l[ch], mk, kmk);
+            }
         }
         __syncwarp();   // ksh is rewritten by the next call
-        ka = warp_sum(ka);
-        kmk = warp_sum(kmk);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ka += __shfl_xor_sync(0xffffffffu, ka, o);
+            kmk += __shfl_xor_sync(0xffffffffu, kmk, o);
+        }
         sc = ei_scalars<T>(ka, kmk, gp);
         const T cst = -sc.ei;
         return (cst == cst) ? cst : M<T>::inf();
-    };
+    }
 
-    // Riemannian gradient of the cost at p (the point of the last cost_at call)
-    auto grad_at = [&](const T (&p)[DP], T (&out)[DP]) {
+    // Riemannian gradient of the cost at p (the point of the last cost() call); all lanes get the whole vector
+    __device__ __forceinline__ void grad(const T (&p)[DP], T (&out)[DP]) {
         T acc[DP], sgc = T(0);
 #pragma unroll
         for (int k = 0; k < DP; ++k) acc[k] = T(0);
@@ -361,159 +406,297 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
         for (int ch = 0; ch < NCH; ++ch) {
             const T w = -sc.cdf * al[ch] - sc.pdf_over_sigma * mk_l[ch];
             const T coef = T(2) * beta * w * k_l[ch];          // k_l = 0 for lanes without a training point
-            T pn = T(0);
+            T pn2 = T(0);
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
                 const T pk = fma(-c_l[ch], p[k], Xi[ch][k]);
-                pn = fma(pk, pk, pn);
+                pn2 = fma(pk, pk, pn2);
             }
-            pn = M<T>::sqrt_(pn);
-            const T scale = (th_l[ch] > T(1e-6)) ? th_l[ch] / (pn > T(0) ? pn : T(1)) : T(1);
+            // Log_p(X_i) = (X_i - c p) * theta / |X_i - c p|;  unscaled when theta <= 1e-6 (pymanopt Sphere.log)
+            const T th = M<T>::theta_(th2_l[ch]);
+            const T scale = (th > T(1e-6) && pn2 > T(0)) ? th * M<T>::rsqrt_(pn2) : T(1);
             const T g = coef * scale;
 #pragma unroll
             for (int k = 0; k < DP; ++k) acc[k] = fma(g, Xi[ch][k], acc[k]);
             sgc = fma(g, c_l[ch], sgc);
         }
 #pragma unroll
-        for (int k = 0; k < DP; ++k) acc[k] = warp_sum(acc[k]);
-        sgc = warp_sum(sgc);
+        for (int o = 16; o > 0; o >>= 1) {   // D + 1 interleaved butterflies
+#pragma unroll
+            for (int k = 0; k < DP; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            sgc += __shfl_xor_sync(0xffffffffu, sgc, o);
+        }
 #pragma unroll
         for (int k = 0; k < DP; ++k) out[k] = -(acc[k] - sgc * p[k]);  // cost = -EI
-    };
-
-    T xv[DP], gv[DP], eta[DP], xn[DP], gn[DP];
-#pragma unroll
-    for (int k = 0; k < DP; ++k) xv[k] = (k < D) ? static_cast<T>(x_io[rid * D + k]) : T(0);
-
-    T cost = cost_at(xv);
-    if (mode == 0) {
-        if (lane == 0) value[rid] = static_cast<double>(-cost);
-        if (grad_out) {
-            grad_at(xv, gv);
-#pragma unroll
-            for (int k = 0; k < DP; ++k)
-                if (k < D && lane == 0) grad_out[rid * D + k] = static_cast<double>(-gv[k]);
-        }
-        return;
     }
+};
 
-    grad_at(xv, gv);
-    T gPg = dot(gv, gv);
-    T gradnorm = M<T>::sqrt_(gPg);
+// A4: EI (and its Riemannian gradient) at r points, one warp per point.
+template <typename T, int DP, int NCH>
+__global__ void __launch_bounds__(kAcqWarps * 32)
+    sphere_ei_reg_kernel(GpParams gp, const double* __restrict__ x_in, int64_t r, double* __restrict__ value,
+                         double* __restrict__ grad_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = gp.n, D = gp.dim;
+    const int npad = (n + 3) & ~3;
+    SmemCarver cv;
+    T* Minv = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * npad * n));
+    const int ksz = SphereEval<T, DP, NCH>::ksh_size(n);
+    T* kbase = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * kAcqWarps * ksz));
+    for (int e = threadIdx.x; e < npad * n; e += blockDim.x) Minv[e] = (e < n * n) ? static_cast<T>(gp.minv[e]) : T(0);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t rid = static_cast<int64_t>(blockIdx.x) * kAcqWarps + warp;
+    if (rid >= r) return;
+    SphereEval<T, DP, NCH> ev;
+    ev.load(gp, lane, Minv, kbase + warp * ksz);
+    T xv[DP], gv[DP];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) eta[k] = -gv[k];
-    int it = 0, why = 0;
-    T stepsize = M<T>::nan();
-    T oldalpha = T(-1);  // unset
+    for (int k = 0; k < DP; ++k) xv[k] = (k < D) ? static_cast<T>(x_in[rid * D + k]) : T(0);
+    const T cost = ev.cost(xv, gp);
+    if (lane == 0) value[rid] = static_cast<double>(-cost);
+    if (grad_out) {
+        ev.grad(xv, gv);
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+            if (k < D && lane == 0) grad_out[rid * D + k] = static_cast<double>(-gv[k]);
+    }
+}
+
+// A1: multi-start conjugate gradient, ONE CTA PER RESTART with speculative backtracking across its warps.
+// pymanopt's LineSearchAdaptive tries alpha, alpha c, alpha c^2, ... one cost call at a time and takes the FIRST step
+// that passes the Armijo test.  The cost calls of different trial steps are independent, so warp w of the CTA evaluates
+// trial (base + w) and the first acceptable one wins: the accepted step, the number of cost evaluations it accounts
+// for and hence every later iterate are exactly those of the sequential search, at the latency of one cost call per
+// kSpec trials.  (ncu on the warp-per-restart version: latency-bound at 1-2 warps per scheduler, and the launch time
+// was set by the restarts whose line search backtracks to the limit, 11 sequential cost calls per iteration.)
+// Every warp carries the whole CG state in registers and executes the same scalar recurrences on the same data, so
+// control flow is identical across the CTA; only the trial costs and the new point + gradient go through shared memory.
+// kSpec = warps per restart = trial steps evaluated concurrently (1 = plain sequential search, one warp per restart)
+template <typename T, int DP, int NCH, int kSpec>
+__global__ void __launch_bounds__(kSpec * 32)
+    sphere_rcg_cta_kernel(GpParams gp, RcgParams opt, double* __restrict__ x_io, int64_t r, double* __restrict__ value,
+                          int32_t* __restrict__ iters, int32_t* __restrict__ reason) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = gp.n, D = gp.dim;
+    const int npad = (n + 3) & ~3;
+    SmemCarver cv;
+    T* Minv = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * npad * n));
+    const int ksz = SphereEval<T, DP, NCH>::ksh_size(n);
+    T* kbase = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * kSpec * ksz));
+    T* f_sh = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * 2 * kSpec));      // trial costs, double-buffered
+    T* xg_sh = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * 2 * 2 * DP));    // new point | gradient, double-buffered
+    for (int e = threadIdx.x; e < npad * n; e += blockDim.x) Minv[e] = (e < n * n) ? static_cast<T>(gp.minv[e]) : T(0);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    SphereEval<T, DP, NCH> ev;
+    ev.load(gp, lane, Minv, kbase + warp * ksz);
+    using E = SphereEval<T, DP, NCH>;
     const T mingrad = static_cast<T>(opt.mingradnorm), minstep = static_cast<T>(opt.minstepsize);
     const T contraction = static_cast<T>(opt.contraction), suff = static_cast<T>(opt.suff_decr);
 
-    auto retract = [&](T a) {  // xn = (x + a eta) / |x + a eta|
-        T s = T(0);
+    for (int64_t rid = blockIdx.x; rid < r; rid += gridDim.x) {
+        T xv[DP], gv[DP], eta[DP], xn[DP], gn[DP], xt[DP];
 #pragma unroll
-        for (int k = 0; k < DP; ++k) {
-            xn[k] = fma(a, eta[k], xv[k]);
-            s = fma(xn[k], xn[k], s);
-        }
-        const T inv = T(1) / M<T>::sqrt_(s);
+        for (int k = 0; k < DP; ++k) xv[k] = (k < D) ? static_cast<T>(x_io[rid * D + k]) : T(0);
+        T cost = ev.cost(xv, gp);   // every warp computes the start redundantly: same data, same result
+        ev.grad(xv, gv);
+        T gPg = E::dot(gv, gv);
+        T gradnorm = M<T>::sqrt_(gPg);
 #pragma unroll
-        for (int k = 0; k < DP; ++k) xn[k] *= inv;
-    };
+        for (int k = 0; k < DP; ++k) eta[k] = -gv[k];
+        int it = 0, why = 0;
+        unsigned fbuf = 0, gbuf = 0;
+        T stepsize = M<T>::nan();
+        T oldalpha = T(-1);  // unset
 
-    while (true) {
-        if (it + 1 >= opt.maxiter) { why = 1; break; }
-        if (gradnorm < mingrad) { why = 2; break; }
-        if (stepsize < minstep) { why = 3; break; }
-        T df0 = dot(gv, eta);
-        if (df0 >= T(0)) {  // not a descent direction: restart from steepest descent
+        while (true) {
+            if (it + 1 >= opt.maxiter) { why = 1; break; }
+            if (gradnorm < mingrad) { why = 2; break; }
+            if (stepsize < minstep) { why = 3; break; }
+            T df0 = E::dot(gv, eta);
+            if (df0 >= T(0)) {  // not a descent direction: restart from steepest descent
 #pragma unroll
-            for (int k = 0; k < DP; ++k) eta[k] = -gv[k];
-            df0 = -gPg;
-        }
-        const T norm_d = M<T>::sqrt_(dot(eta, eta));
-        T a = (oldalpha >= T(0)) ? oldalpha : static_cast<T>(opt.initial_stepsize) / norm_d;
-        retract(a);
-        T newf = cost_at(xn);
-        int evals = 1;
-        while (newf > cost + suff * a * df0 && evals <= opt.ls_maxiter) {
-            a *= contraction;
-            retract(a);
-            newf = cost_at(xn);
-            ++evals;
-        }
-        if (newf > cost) {  // no decrease: stay
-            a = T(0);
+                for (int k = 0; k < DP; ++k) eta[k] = -gv[k];
+                df0 = -gPg;
+            }
+            const T norm_d = M<T>::sqrt_(E::dot(eta, eta));
+            // trial k (k = 0 .. ls_maxiter) uses alpha_k = alpha_0 c^k; the first one passing the Armijo test wins, the
+            // last one is kept when none passes (LineSearchAdaptive leaves its loop after ls_maxiter + 1 cost calls)
+            T a = (oldalpha >= T(0)) ? oldalpha : static_cast<T>(opt.initial_stepsize) / norm_d;
+            const int ktotal = opt.ls_maxiter + 1;
+            int evals = 0, sel = 0;
+            T newf = cost;
+            bool done = false;
+            for (int base = 0; base < ktotal && !done; base += kSpec) {
+                T ak[kSpec];
+#pragma unroll
+                for (int t = 0; t < kSpec; ++t) {
+                    ak[t] = a;
+                    a *= contraction;
+                }
+                T amine = ak[0];
+#pragma unroll
+                for (int t = 1; t < kSpec; ++t) amine = (warp == t) ? ak[t] : amine;
+                {   // my trial: retraction (x + a eta) / |x + a eta| and its cost
+                    T s = T(0);
+#pragma unroll
+                    for (int k = 0; k < DP; ++k) {
+                        xt[k] = fma(amine, eta[k], xv[k]);
+                        s = fma(xt[k], xt[k], s);
+                    }
+                    const T inv = T(1) / M<T>::sqrt_(s);
+#pragma unroll
+                    for (int k = 0; k < DP; ++k) xt[k] *= inv;
+                }
+                const T fmine = (base + warp < ktotal) ? ev.cost(xt, gp) : M<T>::inf();
+                T* fb = f_sh + fbuf * kSpec;
+                fbuf ^= 1u;
+                if (lane == 0) fb[warp] = fmine;
+                __syncthreads();
+#pragma unroll
+                for (int t = 0; t < kSpec; ++t) {
+                    if (!done && base + t < ktotal) {
+                        const T ft = fb[t];
+                        evals = base + t + 1;
+                        sel = t;
+                        newf = ft;
+                        a = ak[t];                   // on exit: the step of the accepted (or of the last) trial
+                        done = !(ft > cost + suff * ak[t] * df0);
+                    }
+                }
+                if (!done && base + kSpec < ktotal) a = ak[kSpec - 1] * contraction;
+            }
+            if (newf > cost) {  // no decrease: stay
+                a = T(0);
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    xn[k] = xv[k];
+                    gn[k] = gv[k];
+                }
+                newf = cost;
+            } else {            // the winning warp holds the per-point state of the accepted point: it takes the gradient
+                T* xb = xg_sh + gbuf * 2 * DP;
+                gbuf ^= 1u;
+                if (warp == sel) {
+                    ev.grad(xt, gn);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < DP; ++k) {
+                            xb[k] = xt[k];
+                            xb[DP + k] = gn[k];
+                        }
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    xn[k] = xb[k];
+                    gn[k] = xb[DP + k];
+                }
+            }
+            stepsize = a * norm_d;
+            oldalpha = (evals == 2) ? a : T(2) * a;
+            // transport g and eta to xn (projection), Hestenes-Stiefel beta
+            const T xg = E::dot(xn, gv), xe = E::dot(xn, eta);
+            T ip = T(0), den = T(0), ngg = T(0);
 #pragma unroll
             for (int k = 0; k < DP; ++k) {
-                xn[k] = xv[k];
-                gn[k] = gv[k];
+                const T og = fma(-xg, xn[k], gv[k]);
+                const T oe = fma(-xe, xn[k], eta[k]);
+                const T df = gn[k] - og;
+                ip = fma(gn[k], df, ip);
+                den = fma(df, oe, den);
+                ngg = fma(gn[k], gn[k], ngg);
+                eta[k] = oe;
             }
-            newf = cost;
-        } else {
-            grad_at(xn, gn);
-        }
-        stepsize = a * norm_d;
-        oldalpha = (evals == 2) ? a : T(2) * a;
-        // transport g and eta to xn (projection), Hestenes-Stiefel beta
-        const T xg = dot(xn, gv), xe = dot(xn, eta);
-        T ip = T(0), den = T(0), ngg = T(0);
+            T bcg;
+            if (den == T(0)) {
+                bcg = T(1);  // pymanopt: ZeroDivisionError branch for float inner products
+            } else {
+                const T q = ip / den;
+                bcg = (q > T(0)) ? q : T(0);
+            }
 #pragma unroll
-        for (int k = 0; k < DP; ++k) {
-            const T og = fma(-xg, xn[k], gv[k]);
-            const T oe = fma(-xe, xn[k], eta[k]);
-            const T df = gn[k] - og;
-            ip = fma(gn[k], df, ip);
-            den = fma(df, oe, den);
-            ngg = fma(gn[k], gn[k], ngg);
-            eta[k] = oe;
+            for (int k = 0; k < DP; ++k) {
+                eta[k] = fma(bcg, eta[k], -gn[k]);
+                xv[k] = xn[k];
+                gv[k] = gn[k];
+            }
+            cost = newf;
+            gPg = ngg;
+            gradnorm = M<T>::sqrt_(ngg);
+            ++it;
         }
-        T bcg;
-        if (den == T(0)) {
-            bcg = T(1);  // pymanopt: ZeroDivisionError branch for float inner products
-        } else {
-            const T q = ip / den;
-            bcg = (q > T(0)) ? q : T(0);
-        }
-#pragma unroll
-        for (int k = 0; k < DP; ++k) {
-            eta[k] = fma(bcg, eta[k], -gn[k]);
-            xv[k] = xn[k];
-            gv[k] = gn[k];
-        }
-        cost = newf;
-        gPg = ngg;
-        gradnorm = M<T>::sqrt_(ngg);
-        ++it;
-    }
 
-    // write back: renormalised in fp64 so the candidate is on the sphere to fp64 accuracy
-    double s = 0.0;
+        // write back: renormalised in fp64 so the candidate is on the sphere to fp64 accuracy
+        if (warp == 0 && lane == 0) {
+            double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < DP; ++k) s = fma(static_cast<double>(xv[k]), static_cast<double>(xv[k]), s);
-    const double inv = 1.0 / sqrt(s);
-    if (lane == 0) {
+            for (int k = 0; k < DP; ++k) s = fma(static_cast<double>(xv[k]), static_cast<double>(xv[k]), s);
+            const double inv = 1.0 / sqrt(s);
 #pragma unroll
-        for (int k = 0; k < DP; ++k)
-            if (k < D) x_io[rid * D + k] = static_cast<double>(xv[k]) * inv;
-        value[rid] = static_cast<double>(-cost);
-        if (iters) iters[rid] = it;
-        if (reason) reason[rid] = why;
+            for (int k = 0; k < DP; ++k)
+                if (k < D) x_io[rid * D + k] = static_cast<double>(xv[k]) * inv;
+            value[rid] = static_cast<double>(-cost);
+            if (iters) iters[rid] = it;
+            if (reason) reason[rid] = why;
+        }
     }
+}
+
+int spec_width() {   // GABO_ACQ_SPEC = 1 | 2 | 4 (developer switch for the speculation width)
+    static const int w = [] {
+        const char* e = getenv("GABO_ACQ_SPEC");
+        const int v = e ? atoi(e) : 0;
+        return (v == 1 || v == 2 || v == 4) ? v : 0;
+    }();
+    return w;
+}
+
+template <typename T, int DP, int NCH, int kSpec>
+int launch_rcg(const GpParams& gp, const RcgParams& opt, double* x, int64_t r, double* value, int32_t* iters,
+               int32_t* reason, cudaStream_t stream) {
+    const int n = gp.n, npad = (n + 3) & ~3;
+    SmemCarver cv;
+    cv.take(sizeof(T) * npad * n);
+    cv.take(sizeof(T) * kSpec * SphereEval<T, DP, NCH>::ksh_size(n));
+    cv.take(sizeof(T) * 2 * kSpec);
+    cv.take(sizeof(T) * 2 * 2 * DP);
+    const size_t smem = cv.off;
+    auto kern = sphere_rcg_cta_kernel<T, DP, NCH, kSpec>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSpec * 32, smem);
+    if (occ < 1) occ = 1;
+    const unsigned grid = static_cast<unsigned>(imin(r, static_cast<int64_t>(sm_count()) * occ));
+    kern<<<grid, kSpec * 32, smem, stream>>>(gp, opt, x, r, value, iters, reason);
+    return check_launch("sphere_rcg_cta_kernel");
 }
 
 template <typename T, int DP, int NCH>
 int launch_reg(const GpParams& gp, const RcgParams& opt, int mode, double* x, int64_t r, double* value, double* grad,
                int32_t* iters, int32_t* reason, cudaStream_t stream) {
     const int n = gp.n, npad = (n + 3) & ~3;
-    SmemCarver cv;
-    cv.take(sizeof(T) * npad * n);
-    cv.take(sizeof(T) * kAcqWarps * npad);
-    const size_t smem = cv.off;
-    auto kern = sphere_acq_reg_kernel<T, DP, NCH>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    const unsigned grid = static_cast<unsigned>((r + kAcqWarps - 1) / kAcqWarps);
-    kern<<<grid, kAcqWarps * 32, smem, stream>>>(gp, opt, mode, x, r, value, grad, iters, reason);
-    return check_launch("sphere_acq_reg_kernel");
+    if (mode == 0) {
+        SmemCarver cv;
+        cv.take(sizeof(T) * npad * n);
+        cv.take(sizeof(T) * kAcqWarps * SphereEval<T, DP, NCH>::ksh_size(n));
+        const size_t smem = cv.off;
+        auto kern = sphere_ei_reg_kernel<T, DP, NCH>;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        const unsigned grid = static_cast<unsigned>((r + kAcqWarps - 1) / kAcqWarps);
+        kern<<<grid, kAcqWarps * 32, smem, stream>>>(gp, x, r, value, grad);
+        return check_launch("sphere_ei_reg_kernel");
+    }
+    // Speculation width: the chip has 592 warp schedulers; with fewer restarts than that, idle schedulers are put to
+    // work on speculative trial steps, beyond it the speculative work would compete with useful work.
+    int spec = spec_width();
+    if (spec == 0) spec = (r * 4 <= 592) ? 4 : ((r <= 1216) ? 2 : 1);   // measured on B200: R=1024 -> 2, R=4096 -> 1
+    if (spec == 4) return launch_rcg<T, DP, NCH, 4>(gp, opt, x, r, value, iters, reason, stream);
+    if (spec == 2) return launch_rcg<T, DP, NCH, 2>(gp, opt, x, r, value, iters, reason, stream);
+    return launch_rcg<T, DP, NCH, 1>(gp, opt, x, r, value, iters, reason, stream);
 }
 
 template <typename T, int DP>

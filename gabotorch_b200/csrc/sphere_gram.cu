@@ -26,20 +26,6 @@ constexpr int kVec = 4;                    // columns per thread
 constexpr int kTileN = kThreads * kVec;    // 512 columns per tile
 constexpr int kTileM = 32;                 // rows per tile
 
-// asin^2(sqrt(w)) = w * (1 + w * P(w)),  w in [0, 0.5]
-__device__ __forceinline__ float asin2_sqrt(float w) {
-    float p = 0.3292977809906006f;
-    p = fmaf(p, w, -0.3745849132537842f);
-    p = fmaf(p, w, 0.28826069831848145f);
-    p = fmaf(p, w, -0.03355207294225693f);
-    p = fmaf(p, w, 0.07700732350349426f);
-    p = fmaf(p, w, 0.07967597246170044f);
-    p = fmaf(p, w, 0.1143670305609703f);
-    p = fmaf(p, w, 0.17777620255947113f);
-    p = fmaf(p, w, 0.3333333432674408f);
-    return w * fmaf(w, p, 1.0f);
-}
-
 struct TailParams {
     float k_hi, k_lo;  // -param * log2(e) split in two floats (Gauss / Laplace)
 };

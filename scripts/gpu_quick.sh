@@ -1,7 +1,7 @@
 #!/bin/bash
 # Parity tests + bench on one B200 (no profiler).  Run under gpurun.
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log
+( timeout 1500 python -m pytest tests -m gpu -x -q --durations=6 2>&1 | tail -25 ) > gpurun_out/pytest_gpu.log
 ( timeout 600 python bench.py "$@" 2> gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_n1.json
 tail -4 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/bench.err
 python - <<'PY'
