@@ -8,8 +8,9 @@
 // pipe alone cannot keep up with HBM at that intensity, so the products run on the tensor cores as 3xTF32
 // (a_hi b_hi + a_lo b_hi + a_hi b_lo, error ~ 2^-21) with fp32 accumulation -- the only GEMM-shaped op on the path.
 // Layout: persistent CTAs (one per SM), 64-row tiles of x streamed through a 3-stage shared-memory ring by the TMA
-// bulk-copy engine (rows are contiguous, a tile is one 1-D copy), four warps x m16 rows, P pre-split into hi/lo and
-// pre-arranged per lane so that a k-step needs one 16-byte shared load per 8 output columns.
+// bulk-copy engine (rows are contiguous, a tile is one 1-D copy), eight warps = 4 row groups (m16) x 2 halves of k,
+// P pre-split into hi/lo and pre-arranged per lane (one 16-byte value per 8 output columns and k-step), kept in
+// registers when it fits.
 #include "spd_common.cuh"
 
 namespace gabo {
@@ -17,7 +18,7 @@ namespace {
 
 constexpr int kTileRows = 64;
 constexpr int kStages = 3;
-constexpr int kThreadsP = 128;
+constexpr int kThreadsP = 256;
 
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
@@ -75,16 +76,25 @@ __global__ void projection_pack_kernel(const double* __restrict__ w, int D, int 
     }
 }
 
-template <int NT, bool EVEN>
+// Work split inside a CTA (one CTA per SM, 8 warps): warp w handles 16 rows (group w & 3) of the 64-row tile and HALF
+// of the k range (w >> 2); the two partial accumulators of a row group meet in shared memory.
+// 3xTF32 split of the streamed operand: a_hi = a with the low 13 mantissa bits cleared (exactly a tf32 number, one
+// LOP3), a_lo = a - a_hi (exact, one FADD; its own low bits are dropped by the tensor core: error 2^-21 |a|).
+// The projection operator P was split (round-to-nearest) when it was packed; when a warp's half of the k range is at
+// most KH steps its fragments of P live in REGISTERS for the whole kernel (KH > 0), otherwise they are read from
+// shared memory every tile (KH = 0).
+template <int NT, bool EVEN, int KH>
 __global__ void __launch_bounds__(kThreadsP, 1)
     nested_project_kernel(const float* __restrict__ x, int64_t n, int dvh, int dvl, int ksteps,
                           const float* __restrict__ pack, float* __restrict__ y) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int stage_floats = kTileRows * dvh;  // 64 * dvh * 4 bytes: a multiple of 256
+    const int os_floats = (kTileRows * dvl + 3) & ~3;
     float* As = reinterpret_cast<float*>(smem_raw);
     float* Bp = As + kStages * stage_floats;
     float* Os = Bp + ksteps * 32 * NT * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Os + ((kTileRows * dvl + 3) & ~3));
+    float* Os2 = Os + os_floats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Os2 + os_floats);
 
     const int64_t tiles = (n + kTileRows - 1) / kTileRows;
     if (threadIdx.x == 0) {
@@ -107,7 +117,29 @@ __global__ void __launch_bounds__(kThreadsP, 1)
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rowgrp = warp & 3, khalf = warp >> 2;
     const int g = lane >> 2, t = lane & 3;
+    // Fragment row -> tile row.  The rows are 4 dvh bytes apart (a whole tile is ONE bulk copy, so they cannot be
+    // padded) and with the natural mapping the 64-bit fragment loads of a half-warp (4 rows x 4 column pairs) collide
+    // two ways for dvh = 210 (ncu: 52 % of the shared-memory wavefronts were conflicts and the LSU pipe, at 70 %, was
+    // the limiter).  Rows are independent outputs, so fragment rows g / g+8 are mapped to tile rows
+    // 4 (g & 3) + (g >> 2) and that + 2: a half-warp then touches rows 4 apart, whose bank offsets are 8 words apart.
+    const int row_lo = 4 * (g & 3) + (g >> 2);
+    const int ksplit = (ksteps + 1) >> 1;
+    const int s_begin = khalf ? ksplit : 0;
+    const int s_end = khalf ? ksteps : ksplit;
+    // the last k-step reaches past the end of a row when dvh is not a multiple of 8: the half that owns it masks it
+    const bool has_ragged = (8 * ksteps != dvh) && s_begin < s_end && s_end == ksteps;
+    float4 breg[KH > 0 ? KH : 1][NT];
+    if (KH > 0) {
+#pragma unroll
+        for (int i = 0; i < (KH > 0 ? KH : 1); ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                breg[i][j] = (s_begin + i < s_end)
+                                 ? reinterpret_cast<const float4*>(Bp)[(s_begin + i) * 32 * NT + lane * NT + j]
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     uint32_t phase_bits = 0u;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
@@ -124,9 +156,7 @@ __global__ void __launch_bounds__(kThreadsP, 1)
             __syncthreads();
         }
 
-        // Three accumulators per output tile (hi*hi, lo*hi, hi*lo): with a single one every k-step appended three
-        // DEPENDENT mma.sync to the same registers (81 in a row for dvh = 210), and with one warp per scheduler that
-        // chain, not HBM, set the tile time.  The small terms are summed first at the end.
+        // Three accumulators per output tile (hi*hi, lo*hi, hi*lo): independent mma.sync chains; small terms summed first.
         float acc[NT][4], acc_lh[NT][4], acc_hl[NT][4];
 #pragma unroll
         for (int j = 0; j < NT; ++j)
@@ -136,52 +166,89 @@ __global__ void __launch_bounds__(kThreadsP, 1)
                 acc_lh[j][q] = 0.0f;
                 acc_hl[j][q] = 0.0f;
             }
-        const float* r0 = A + (warp * 16 + g) * dvh;
-        const float* r1 = r0 + 8 * dvh;
+        const float* r0 = A + (rowgrp * 16 + row_lo) * dvh;
+        const float* r1 = r0 + 2 * dvh;
         const float4* bp = reinterpret_cast<const float4*>(Bp) + lane * NT;
-#pragma unroll 3
-        for (int s = 0; s < ksteps; ++s) {
+        auto kstep = [&](const float (&a)[4], const float4 (&b)[NT]) {  // a0:(lo row, col) a1:(hi row, col) a2/a3: col+1
+            float ah[4], al[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ah[q] = __uint_as_float(__float_as_uint(a[q]) & 0xffffe000u);
+                al[q] = a[q] - ah[q];
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {   // b = {hi b0, hi b1, lo b0, lo b1}
+                mma_tf32(acc_lh[j], al, b[j].x, b[j].y);
+                mma_tf32(acc_hl[j], ah, b[j].z, b[j].w);
+                mma_tf32(acc[j], ah, b[j].x, b[j].y);
+            }
+        };
+        auto load_a = [&](int s, float (&a)[4], bool ragged) {
             const int col = 8 * s + 2 * t;
-            float a[4];  // a0:(g, k=col) a1:(g+8, col) a2:(g, col+1) a3:(g+8, col+1)
-            if (EVEN) {
+            if (ragged) {   // columns past the end of the row are zero, never read
+                a[0] = (col < dvh) ? r0[col] : 0.0f;
+                a[1] = (col < dvh) ? r1[col] : 0.0f;
+                a[2] = (col + 1 < dvh) ? r0[col + 1] : 0.0f;
+                a[3] = (col + 1 < dvh) ? r1[col + 1] : 0.0f;
+            } else if (EVEN) {
                 const float2 u = *reinterpret_cast<const float2*>(r0 + col);
                 const float2 v = *reinterpret_cast<const float2*>(r1 + col);
                 a[0] = u.x; a[2] = u.y; a[1] = v.x; a[3] = v.y;
             } else {
                 a[0] = r0[col]; a[2] = r0[col + 1]; a[1] = r1[col]; a[3] = r1[col + 1];
             }
-            if (col >= dvh) { a[0] = 0.0f; a[1] = 0.0f; }
-            if (col + 1 >= dvh) { a[2] = 0.0f; a[3] = 0.0f; }
-            float ah[4], al[4];
+        };
+        if (KH > 0) {   // operator fragments in registers: the k loop is fully unrolled
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ah[q] = to_tf32(a[q]);
-                al[q] = to_tf32(a[q] - ah[q]);
+            for (int i = 0; i < (KH > 0 ? KH : 1); ++i) {
+                const int s = s_begin + i;
+                if (s < s_end) {
+                    float a[4];
+                    load_a(s, a, has_ragged && s == s_end - 1);
+                    kstep(a, breg[KH > 0 ? i : 0]);
+                }
             }
+        } else {
+#pragma unroll 2
+            for (int s = s_begin; s < s_end; ++s) {
+                float a[4];
+                load_a(s, a, has_ragged && s == s_end - 1);
+                float4 b[NT];
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const float4 b = bp[s * 32 * NT + j];  // {hi b0, hi b1, lo b0, lo b1}
-                mma_tf32(acc_lh[j], al, b.x, b.y);
-                mma_tf32(acc_hl[j], ah, b.z, b.w);
-                mma_tf32(acc[j], ah, b.x, b.y);
+                for (int j = 0; j < NT; ++j) b[j] = bp[s * 32 * NT + j];
+                kstep(a, b);
             }
         }
 #pragma unroll
         for (int j = 0; j < NT; ++j)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[j][q] += acc_lh[j][q] + acc_hl[j][q];
+
         __syncthreads();  // every warp is done with this stage (and with the previous tile's output staging)
         if (threadIdx.x == 0) {
             fence_proxy_async();
             issue(tile + static_cast<int64_t>(kStages) * gridDim.x, stage);
         }
+        float* o0 = (khalf ? Os2 : Os) + (rowgrp * 16 + row_lo) * dvl;
+        float* o1 = o0 + 2 * dvl;
+        if (khalf) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const int c0 = 8 * j + 2 * t;
-            float* o0 = Os + (warp * 16 + g) * dvl;
-            float* o1 = o0 + 8 * dvl;
-            if (c0 < dvl) { o0[c0] = acc[j][0]; o1[c0] = acc[j][2]; }
-            if (c0 + 1 < dvl) { o0[c0 + 1] = acc[j][1]; o1[c0 + 1] = acc[j][3]; }
+            for (int j = 0; j < NT; ++j) {
+                const int c0 = 8 * j + 2 * t;
+                if (c0 < dvl) { o0[c0] = acc[j][0]; o1[c0] = acc[j][2]; }
+                if (c0 + 1 < dvl) { o0[c0 + 1] = acc[j][1]; o1[c0 + 1] = acc[j][3]; }
+            }
+        }
+        __syncthreads();
+        if (!khalf) {
+            const float* p0 = Os2 + (rowgrp * 16 + row_lo) * dvl;
+            const float* p1 = p0 + 2 * dvl;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int c0 = 8 * j + 2 * t;
+                if (c0 < dvl) { o0[c0] = acc[j][0] + p0[c0]; o1[c0] = acc[j][2] + p1[c0]; }
+                if (c0 + 1 < dvl) { o0[c0 + 1] = acc[j][1] + p0[c0 + 1]; o1[c0 + 1] = acc[j][3] + p1[c0 + 1]; }
+            }
         }
         __syncthreads();
         float* dst = y + tile * kTileRows * dvl;
@@ -196,20 +263,25 @@ template <int NT>
 int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, float* y, cudaStream_t s) {
     const int ksteps = ksteps_for(dvh);
     const size_t smem = sizeof(float) * (static_cast<size_t>(kStages) * kTileRows * dvh + static_cast<size_t>(ksteps) * 32 * NT * 4 +
-                                         ((kTileRows * dvl + 3) & ~3)) + 8 * kStages + 16;
+                                         2 * ((kTileRows * dvl + 3) & ~3)) + 8 * kStages + 16;
     GABO_REQUIRE(smem <= 227 * 1024, GABO_E_UNSUPPORTED,
                  "gabo_nested_spd_project: Mandel length %d needs %zu bytes of shared memory (> 227 KB)", dvh, smem);
     const int64_t tiles = (n + kTileRows - 1) / kTileRows;
     const unsigned grid = static_cast<unsigned>(imin(tiles, sm_count()));
     const bool even = (dvh % 2) == 0;
-    if (even) {
-        auto kern = nested_project_kernel<NT, true>;
+    // operator fragments in registers when a warp's half of the k range is at most 14 steps and NT <= 2
+    // (SPD(20) -> SPD(5): 27 steps, NT = 2 -> 112 registers); shared memory otherwise
+    auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         kern<<<grid, kThreadsP, smem, s>>>(x, n, dvh, dvl, ksteps, pack, y);
+    };
+    constexpr int kRegSteps = (NT <= 2) ? 14 : 0;
+    if (kRegSteps > 0 && (ksteps + 1) / 2 <= kRegSteps) {
+        if (even) go(nested_project_kernel<NT, true, kRegSteps>);
+        else go(nested_project_kernel<NT, false, kRegSteps>);
     } else {
-        auto kern = nested_project_kernel<NT, false>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, kThreadsP, smem, s>>>(x, n, dvh, dvl, ksteps, pack, y);
+        if (even) go(nested_project_kernel<NT, true, 0>);
+        else go(nested_project_kernel<NT, false, 0>);
     }
     return check_launch("nested_project_kernel");
 }
