@@ -8,7 +8,7 @@
 // pipe alone cannot keep up with HBM at that intensity, so the products run on the tensor cores as 3xTF32
 // (a_hi b_hi + a_lo b_hi + a_hi b_lo, error ~ 2^-21) with fp32 accumulation -- the only GEMM-shaped op on the path.
 // Layout: persistent CTAs (one per SM), 64-row tiles of x streamed through a 3-stage shared-memory ring by the TMA
-// bulk-copy engine (rows are contiguous, a tile is one 1-D copy), eight warps = 4 row groups (m16) x 2 halves of k,
+// bulk-copy engine (rows are contiguous, a tile is one 1-D copy), sixteen warps = 4 row groups (m16) x 4 parts of k,
 // P pre-split into hi/lo and pre-arranged per lane (one 16-byte value per 8 output columns and k-step), kept in
 // registers when it fits.
 #include "spd_common.cuh"
@@ -18,7 +18,8 @@ namespace {
 
 constexpr int kTileRows = 64;
 constexpr int kStages = 3;
-constexpr int kThreadsP = 256;
+constexpr int kSplitK = 4;                    // warps sharing a row group, each with a quarter of the k range
+constexpr int kThreadsP = 4 * kSplitK * 32;   // 16 warps
 
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
@@ -76,8 +77,10 @@ __global__ void projection_pack_kernel(const double* __restrict__ w, int D, int 
     }
 }
 
-// Work split inside a CTA (one CTA per SM, 8 warps): warp w handles 16 rows (group w & 3) of the 64-row tile and HALF
-// of the k range (w >> 2); the two partial accumulators of a row group meet in shared memory.
+// Work split inside a CTA (one CTA per SM, 16 warps): warp w handles 16 rows (group w & 3) of the 64-row tile and a
+// QUARTER of the k range (w >> 2); the partial accumulators of a row group are summed through shared memory.  ncu on
+// the 4- and 8-warp versions: no pipe above 35 %, every warp waiting on its own fixed-latency dependencies (~650
+// instructions per tile at ~6 cycles each) -- the cure is more warps per scheduler, each with a shorter stream.
 // 3xTF32 split of the streamed operand: a_hi = a with the low 13 mantissa bits cleared (exactly a tf32 number, one
 // LOP3), a_lo = a - a_hi (exact, one FADD; its own low bits are dropped by the tensor core: error 2^-21 |a|).
 // The projection operator P was split (round-to-nearest) when it was packed; when a warp's half of the k range is at
@@ -85,20 +88,19 @@ __global__ void projection_pack_kernel(const double* __restrict__ w, int D, int 
 // shared memory every tile (KH = 0).
 template <int NT, bool EVEN, int KH>
 __global__ void __launch_bounds__(kThreadsP, 1)
-    nested_project_kernel(const float* __restrict__ x, int64_t n, int dvh, int dvl, int ksteps,
+    nested_project_kernel(const float* __restrict__ x, int64_t n, int dvh, int dvl, int ksteps, int nstages,
                           const float* __restrict__ pack, float* __restrict__ y) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int stage_floats = kTileRows * dvh;  // 64 * dvh * 4 bytes: a multiple of 256
     const int os_floats = (kTileRows * dvl + 3) & ~3;
     float* As = reinterpret_cast<float*>(smem_raw);
-    float* Bp = As + kStages * stage_floats;
-    float* Os = Bp + ksteps * 32 * NT * 4;
-    float* Os2 = Os + os_floats;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Os2 + os_floats);
+    float* Bp = As + nstages * stage_floats;
+    float* Os = Bp + ksteps * 32 * NT * 4;          // kSplitK partial output tiles; part 0 becomes the total
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Os + kSplitK * os_floats);
 
     const int64_t tiles = (n + kTileRows - 1) / kTileRows;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < nstages; ++s) mbar_init(&bars[s], 1);
         fence_mbar_init();
     }
     for (int e = threadIdx.x; e < ksteps * 32 * NT; e += kThreadsP)
@@ -113,11 +115,11 @@ __global__ void __launch_bounds__(kThreadsP, 1)
         }
     };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) issue(static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x, s);
+        for (int s = 0; s < nstages; ++s) issue(static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x, s);
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rowgrp = warp & 3, khalf = warp >> 2;
+    const int rowgrp = warp & 3, khalf = warp >> 2;   // khalf: which part of the k range (0 .. kSplitK-1)
     const int g = lane >> 2, t = lane & 3;
     // Fragment row -> tile row.  The rows are 4 dvh bytes apart (a whole tile is ONE bulk copy, so they cannot be
     // padded) and with the natural mapping the 64-bit fragment loads of a half-warp (4 rows x 4 column pairs) collide
@@ -125,9 +127,9 @@ __global__ void __launch_bounds__(kThreadsP, 1)
     // the limiter).  Rows are independent outputs, so fragment rows g / g+8 are mapped to tile rows
     // 4 (g & 3) + (g >> 2) and that + 2: a half-warp then touches rows 4 apart, whose bank offsets are 8 words apart.
     const int row_lo = 4 * (g & 3) + (g >> 2);
-    const int ksplit = (ksteps + 1) >> 1;
-    const int s_begin = khalf ? ksplit : 0;
-    const int s_end = khalf ? ksteps : ksplit;
+    const int ksplit = (ksteps + kSplitK - 1) / kSplitK;
+    const int s_begin = static_cast<int>(imin(khalf * ksplit, ksteps));
+    const int s_end = static_cast<int>(imin(s_begin + ksplit, ksteps));
     // the last k-step reaches past the end of a row when dvh is not a multiple of 8: the half that owns it masks it
     const bool has_ragged = (8 * ksteps != dvh) && s_begin < s_end && s_end == ksteps;
     float4 breg[KH > 0 ? KH : 1][NT];
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(kThreadsP, 1)
     uint32_t phase_bits = 0u;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int stage = it % kStages;
+        const int stage = it % nstages;
         const int rows = static_cast<int>(imin(kTileRows, n - tile * kTileRows));
         float* A = As + stage * stage_floats;
         if (rows == kTileRows) {
@@ -227,32 +229,24 @@ __global__ void __launch_bounds__(kThreadsP, 1)
         __syncthreads();  // every warp is done with this stage (and with the previous tile's output staging)
         if (threadIdx.x == 0) {
             fence_proxy_async();
-            issue(tile + static_cast<int64_t>(kStages) * gridDim.x, stage);
+            issue(tile + static_cast<int64_t>(nstages) * gridDim.x, stage);
         }
-        float* o0 = (khalf ? Os2 : Os) + (rowgrp * 16 + row_lo) * dvl;
+        float* o0 = Os + khalf * os_floats + (rowgrp * 16 + row_lo) * dvl;
         float* o1 = o0 + 2 * dvl;
-        if (khalf) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int c0 = 8 * j + 2 * t;
-                if (c0 < dvl) { o0[c0] = acc[j][0]; o1[c0] = acc[j][2]; }
-                if (c0 + 1 < dvl) { o0[c0 + 1] = acc[j][1]; o1[c0 + 1] = acc[j][3]; }
-            }
-        }
-        __syncthreads();
-        if (!khalf) {
-            const float* p0 = Os2 + (rowgrp * 16 + row_lo) * dvl;
-            const float* p1 = p0 + 2 * dvl;
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int c0 = 8 * j + 2 * t;
-                if (c0 < dvl) { o0[c0] = acc[j][0] + p0[c0]; o1[c0] = acc[j][2] + p1[c0]; }
-                if (c0 + 1 < dvl) { o0[c0 + 1] = acc[j][1] + p0[c0 + 1]; o1[c0 + 1] = acc[j][3] + p1[c0 + 1]; }
-            }
+        for (int j = 0; j < NT; ++j) {
+            const int c0 = 8 * j + 2 * t;
+            if (c0 < dvl) { o0[c0] = acc[j][0]; o1[c0] = acc[j][2]; }
+            if (c0 + 1 < dvl) { o0[c0 + 1] = acc[j][1]; o1[c0 + 1] = acc[j][3]; }
         }
         __syncthreads();
         float* dst = y + tile * kTileRows * dvl;
-        for (int e = threadIdx.x; e < rows * dvl; e += kThreadsP) __stcs(dst + e, Os[e]);
+        for (int e = threadIdx.x; e < rows * dvl; e += kThreadsP) {   // sum of the k-range partials, coalesced store
+            float v = Os[e];
+#pragma unroll
+            for (int q = 1; q < kSplitK; ++q) v += Os[q * os_floats + e];
+            __stcs(dst + e, v);
+        }
     }
 }
 
@@ -262,21 +256,27 @@ int ntiles_for(int dvl) { return (dvl + 7) / 8; }
 template <int NT>
 int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, float* y, cudaStream_t s) {
     const int ksteps = ksteps_for(dvh);
-    const size_t smem = sizeof(float) * (static_cast<size_t>(kStages) * kTileRows * dvh + static_cast<size_t>(ksteps) * 32 * NT * 4 +
-                                         2 * ((kTileRows * dvl + 3) & ~3)) + 8 * kStages + 16;
+    // ring depth: kStages when it fits the 227 KB of shared memory, otherwise 2 (long Mandel vectors)
+    auto smem_for = [&](int stages) {
+        return sizeof(float) * (static_cast<size_t>(stages) * kTileRows * dvh + static_cast<size_t>(ksteps) * 32 * NT * 4 +
+                                kSplitK * ((kTileRows * dvl + 3) & ~3)) + 8 * kStages + 16;
+    };
+    int nstages = kStages;
+    while (nstages > 2 && smem_for(nstages) > 227 * 1024) --nstages;
+    const size_t smem = smem_for(nstages);
     GABO_REQUIRE(smem <= 227 * 1024, GABO_E_UNSUPPORTED,
                  "gabo_nested_spd_project: Mandel length %d needs %zu bytes of shared memory (> 227 KB)", dvh, smem);
     const int64_t tiles = (n + kTileRows - 1) / kTileRows;
     const unsigned grid = static_cast<unsigned>(imin(tiles, sm_count()));
     const bool even = (dvh % 2) == 0;
-    // operator fragments in registers when a warp's half of the k range is at most 14 steps and NT <= 2
-    // (SPD(20) -> SPD(5): 27 steps, NT = 2 -> 112 registers); shared memory otherwise
+    // operator fragments in registers when a warp's part of the k range is at most 7 steps and NT <= 2
+    // (SPD(20) -> SPD(5): 27 steps / 4 parts = 7, NT = 2 -> 56 registers); shared memory otherwise
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, kThreadsP, smem, s>>>(x, n, dvh, dvl, ksteps, pack, y);
+        kern<<<grid, kThreadsP, smem, s>>>(x, n, dvh, dvl, ksteps, nstages, pack, y);
     };
-    constexpr int kRegSteps = (NT <= 2) ? 14 : 0;
-    if (kRegSteps > 0 && (ksteps + 1) / 2 <= kRegSteps) {
+    constexpr int kRegSteps = (NT <= 2) ? 7 : 0;
+    if (kRegSteps > 0 && (ksteps + kSplitK - 1) / kSplitK <= kRegSteps) {
         if (even) go(nested_project_kernel<NT, true, kRegSteps>);
         else go(nested_project_kernel<NT, false, kRegSteps>);
     } else {
