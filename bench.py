@@ -454,6 +454,46 @@ class Bench:
                 'candidates_per_s': self.world * R * T / (ms * 1e-3), 'ms_per_step': ms, 'mean_iters': iters,
                 'collective': 'one all_gather of (value, gidx, candidate) per solve' if self.world > 1 else 'none (1 GPU)'}
 
+    def extra_acq_spd(self, R, T, d=8, n_train=32, noise=1e-2, steps=3):
+        """BASELINE configs[3] per-GPU shard: Ackley on SPD(8), R restarts x T CG steps per rank + the record all-gather."""
+        import gabotorch_b200 as g
+        from gabotorch_b200 import manifold_optimization as mo
+        torch, ops = self.torch, self.ops
+        rng = np.random.default_rng(2025)
+        xm = spd_sample_mandel(rng, n_train, d)                # GP inputs: Mandel vectors (replicated on every rank)
+        mats = ops.mandel_unpack(torch.from_numpy(xm)).cpu().numpy()
+        lam, q = np.linalg.eigh(mats / 2.0)                    # Ackley in the tangent space at 2 I (test_functions_spd.py:34-69)
+        logm = 2.0 * (q * np.log(lam)[:, None, :]) @ np.swapaxes(q, -1, -2)
+        iu = np.triu_indices(d)
+        v = logm[:, iu[0], iu[1]]
+        dv = v.shape[1]
+        y = (-20.0 * np.exp(-0.2 * np.sqrt((v ** 2).sum(1) / dv)) - np.exp(np.cos(2 * np.pi * v).sum(1) / dv) + 20.0 + np.e)
+        base = g.SpdAffineInvariantGaussianKernel(beta_min=0.22)   # d = 8: nearest tabulated beta_min (gabo_spd.py:151-162)
+        model = g.ManifoldGP(torch.from_numpy(xm), torch.from_numpy(y), g.ScaleKernel(base), noise=noise)
+        model.covar_module.outputscale = 1.0
+        acq = g.ExpectedImprovement(model, best_f=float(y.min()))
+        gp = acq.device_gp()
+        rs = np.random.default_rng(778)
+        x0_all = spd_sample_mandel(rs, R * self.world, d)      # starts keyed by GLOBAL restart index
+        lo = self.rank * R
+        x0 = ops.mandel_unpack(torch.from_numpy(x0_all[lo:lo + R]).to(self.dev))
+        gidx = torch.arange(lo, lo + R, device=self.dev)
+        res = {}
+
+        def step():
+            cand, val, iters, _ = ops.acq_rcg(gp, x0, maxiter=T + 1, mingradnorm=0.0, minstepsize=-1.0)
+            slot, best = ops.argmax_records(val, gidx)
+            if self.world > 1:
+                v_, gi, c = mo.allgather_records(best.reshape(()), gidx[slot].reshape(()), cand[slot].reshape(-1))
+                ops.argmax_records(v_, gi)
+            res['iters'] = iters
+        ms = self.time_steps(step, steps, 1, flush=False) / steps
+        return {'workload': 'acq RCG on EI, SPD(%d), %d restarts/GPU x %d CG steps, n_train=%d, noise=%g'
+                            % (d, R, T, n_train, noise),
+                'candidates_per_s': self.world * R * T / (ms * 1e-3), 'ms_per_step': ms,
+                'mean_iters': res['iters'].double().mean().item(),
+                'collective': 'one all_gather of (value, gidx, candidate) per solve' if self.world > 1 else 'none (1 GPU)'}
+
     def extra_projection(self, n, D=20, d=5, steps=10):
         torch, ops = self.torch, self.ops
         gen = torch.Generator(device=self.dev)
@@ -495,8 +535,9 @@ class Bench:
 
     def run(self):
         args = self.args
-        if args.only == 'acq':      # developer switch: just the acquisition extra
-            e = self.extra_acq_sphere(R=args.acq_restarts, T=200)
+        if args.only in ('acq', 'acq_spd'):      # developer switch: just one acquisition extra
+            e = (self.extra_acq_sphere(R=args.acq_restarts, T=200) if args.only == 'acq'
+                 else self.extra_acq_spd(R=args.acq_restarts, T=args.acq_steps, d=args.acq_dim))
             self.clocks.stop()
             if self.rank == 0:
                 print(json.dumps(e), flush=True)
@@ -506,6 +547,7 @@ class Bench:
         if not args.no_extras:
             torch = self.torch
             extras.append(self.extra_acq_sphere(R=1024, T=200))
+            extras.append(self.extra_acq_spd(R=512, T=200))
             if self.world == 1:
                 extras.append(self.extra_spd(N_POINTS, SPD_D, BETA_SPD3, symmetric=True))
                 extras.append(self.extra_spd(8192, 3, BETA_SPD3, symmetric=False, steps=5))
@@ -549,6 +591,8 @@ def main():
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--only', default='', help='developer switch: run a single extra (acq)')
     ap.add_argument('--acq-restarts', type=int, default=1024)
+    ap.add_argument('--acq-steps', type=int, default=200)
+    ap.add_argument('--acq-dim', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-rows', type=int, default=256, help='rows of the N=2048 Gram in the cpu_baseline sample')
     ap.add_argument('--ref-rows', type=int, default=16, help='rows per step of the reference arm')

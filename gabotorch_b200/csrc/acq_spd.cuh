@@ -44,8 +44,10 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
     constexpr int kPerWarpT = 3 * DD + 3 * TRI + 2 * d;
     T* tbase = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * kAcqWarps * (kPerWarpT + npad)));
 
+    // entry-major (Ls[e * n + i]): lanes = training points read consecutive words (point-major rows of TRI words
+    // collided 4 ways for TRI = 36)
     for (int e = threadIdx.x; e < n * TRI; e += blockDim.x)
-        Ls[e] = static_cast<T>(gp.x_train[static_cast<int64_t>(e / TRI) * FS + (e % TRI)]);
+        Ls[(e % TRI) * n + (e / TRI)] = static_cast<T>(gp.x_train[static_cast<int64_t>(e / TRI) * FS + (e % TRI)]);
     for (int e = threadIdx.x; e < n; e += blockDim.x) alpha[e] = static_cast<T>(gp.alpha[e]);
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) Minv[e] = static_cast<T>(gp.minv[e]);
     __syncthreads();
@@ -80,7 +82,6 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
             const int i = lane + 32 * ch;
             T kk = T(0);
             if (i < n) {
-                const T* Li = Ls + i * TRI;
                 T G[d][d];
 #pragma unroll
                 for (int rr = 0; rr < d; ++rr) {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
                     for (int c = 0; c < d; ++c) {
                         T s = T(0);
 #pragma unroll
-                        for (int m = c; m < d; ++m) s = fma(Qs[rr * d + m], Li[tri_idx(m, c)], s);
+                        for (int m = c; m < d; ++m) s = fma(Qs[rr * d + m], Ls[tri_idx(m, c) * n + i], s);
                         G[rr][c] = er * s;
                     }
                 }
@@ -215,32 +216,11 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
     for (int k = lane; k < d; k += 32) Es[k] = T(1);
     __syncwarp();
 
-    T cost = cost_trial();
-    if (mode == 0) {
-        if (lane == 0) value[rid] = static_cast<double>(-cost);
-        if (grad_out) {
-            assemble_grad(Om);
-            // ambient Riemannian gradient of EI: L (-Om) L^T
-            for (int e = lane; e < DD; e += 32) {
-                const int rr = e / d, c = e % d;
-                double s = 0.0;
-                for (int a = 0; a <= rr; ++a)
-                    for (int b = 0; b <= c; ++b) {
-                        const int lo = a < b ? a : b, hi = a < b ? b : a;
-                        s += static_cast<double>(tmp[rr * d + a]) * static_cast<double>(Om[ui(d, lo, hi)]) *
-                             static_cast<double>(tmp[c * d + b]);
-                    }
-                grad_out[rid * DD + e] = -s;
-            }
-        }
-        return;
-    }
-
-    assemble_grad(Om);
-    T gPg = sym_inner(Om, Om);
-    T gradnorm = M<T>::sqrt_(gPg);
-    for (int e = lane; e < TRI; e += 32) Hh[e] = -Om[e];
-    __syncwarp();
+    // The whole solve is ONE loop with ONE cost_trial() call site: the initial evaluation is its first pass.  cost_trial
+    // inlines a fully unrolled d x d Jacobi (thousands of instructions for d = 8); with three call sites the kernel was
+    // 27k instructions (440 KB) and ncu showed the warps starved on instruction fetch (stall no_instruction 5.7 per
+    // issue, 13 % issue-active).
+    T cost = T(0), gPg = T(0), gradnorm = T(0);
     int it = 0, why = 0;
     T stepsize = M<T>::nan();
     T oldalpha = T(-1);
@@ -253,75 +233,112 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
         __syncwarp();
     };
 
+    bool first = true;
     while (true) {
-        if (it + 1 >= opt.maxiter) { why = 1; break; }
-        if (gradnorm < mingrad) { why = 2; break; }
-        if (stepsize < minstep) { why = 3; break; }
-        T df0 = sym_inner(Om, Hh);
-        if (df0 >= T(0)) {
-            __syncwarp();
-            for (int e = lane; e < TRI; e += 32) Hh[e] = -Om[e];
-            __syncwarp();
-            df0 = -gPg;
-        }
-        const T norm_d = M<T>::sqrt_(sym_inner(Hh, Hh));
-
-        // eigen-decomposition of the whitened direction (every lane, redundantly; warp-uniform result)
-        {
-            T S[d][d], lam[d], V[d][d];
-#pragma unroll
-            for (int rr = 0; rr < d; ++rr)
-#pragma unroll
-                for (int c = 0; c < d; ++c) S[rr][c] = (c >= rr) ? Hh[ui(d, rr, c)] : T(0);
-            jacobi_symmetric<d, T, true>(S, lam, V);
-            __syncwarp();
-#pragma unroll
-            for (int rr = 0; rr < d; ++rr)
-#pragma unroll
-                for (int c = 0; c < d; ++c) {
-                    const int e = rr * d + c;
-                    if (lane == (e & 31)) Vs[e] = V[rr][c];
-                }
-#pragma unroll
-            for (int k = 0; k < d; ++k)
-                if (lane == k) lamH[k] = lam[k];
-            __syncwarp();
-        }
-        // Q0 = V^T Finv (fp64), Qs = (T) Q0;  tmp = Om V;  OmV = V^T tmp
-        for (int e = lane; e < DD; e += 32) {
-            const int rr = e / d, c = e % d;
-            double s = 0.0;
-            T t = T(0);
-            for (int m = 0; m < d; ++m) {
-                s = fma(static_cast<double>(Vs[m * d + rr]), Finv[m * d + c], s);
-                const int lo = rr < m ? rr : m, hi = rr < m ? m : rr;
-                t = fma(Om[ui(d, lo, hi)], Vs[m * d + c], t);
+        T df0 = T(0), norm_d = T(0), a = T(0);
+        if (!first) {
+            if (it + 1 >= opt.maxiter) { why = 1; break; }
+            if (gradnorm < mingrad) { why = 2; break; }
+            if (stepsize < minstep) { why = 3; break; }
+            df0 = sym_inner(Om, Hh);
+            if (df0 >= T(0)) {
+                __syncwarp();
+                for (int e = lane; e < TRI; e += 32) Hh[e] = -Om[e];
+                __syncwarp();
+                df0 = -gPg;
             }
-            Q0[e] = s;
-            Qs[e] = static_cast<T>(s);
-            tmp[e] = t;
-        }
-        __syncwarp();
-        for (int e = lane; e < DD; e += 32) {
-            const int rr = e / d, c = e % d;
-            if (c >= rr) {
+            norm_d = M<T>::sqrt_(sym_inner(Hh, Hh));
+
+            // eigen-decomposition of the whitened direction (every lane, redundantly; warp-uniform result)
+            {
+                T S[d][d], lam[d], V[d][d];
+#pragma unroll
+                for (int rr = 0; rr < d; ++rr)
+#pragma unroll
+                    for (int c = 0; c < d; ++c) S[rr][c] = (c >= rr) ? Hh[ui(d, rr, c)] : T(0);
+                jacobi_symmetric<d, T, true>(S, lam, V);
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < d; ++rr)
+#pragma unroll
+                    for (int c = 0; c < d; ++c) {
+                        const int e = rr * d + c;
+                        if (lane == (e & 31)) Vs[e] = V[rr][c];
+                    }
+#pragma unroll
+                for (int k = 0; k < d; ++k)
+                    if (lane == k) lamH[k] = lam[k];
+                __syncwarp();
+            }
+            // Q0 = V^T Finv (fp64), Qs = (T) Q0;  tmp = Om V;  OmV = V^T tmp
+            for (int e = lane; e < DD; e += 32) {
+                const int rr = e / d, c = e % d;
+                double s = 0.0;
                 T t = T(0);
-                for (int m = 0; m < d; ++m) t = fma(Vs[m * d + rr], tmp[m * d + c], t);
-                OmV[ui(d, rr, c)] = t;
+                for (int m = 0; m < d; ++m) {
+                    s = fma(static_cast<double>(Vs[m * d + rr]), Finv[m * d + c], s);
+                    const int lo = rr < m ? rr : m, hi = rr < m ? m : rr;
+                    t = fma(Om[ui(d, lo, hi)], Vs[m * d + c], t);
+                }
+                Q0[e] = s;
+                Qs[e] = static_cast<T>(s);
+                tmp[e] = t;
             }
-        }
-        __syncwarp();
+            __syncwarp();
+            for (int e = lane; e < DD; e += 32) {
+                const int rr = e / d, c = e % d;
+                if (c >= rr) {
+                    T t = T(0);
+                    for (int m = 0; m < d; ++m) t = fma(Vs[m * d + rr], tmp[m * d + c], t);
+                    OmV[ui(d, rr, c)] = t;
+                }
+            }
+            __syncwarp();
 
-        T a = (oldalpha >= T(0)) ? oldalpha : static_cast<T>(opt.initial_stepsize) / norm_d;
-        set_trial(a);
-        T newf = cost_trial();
-        int evals = 1;
-        while (newf > cost + suff * a * df0 && evals <= opt.ls_maxiter) {
-            a *= contraction;
-            set_trial(a);
+            a = (oldalpha >= T(0)) ? oldalpha : static_cast<T>(opt.initial_stepsize) / norm_d;
+        }
+        // LineSearchAdaptive: first trial unconditional, then backtrack while the Armijo test fails (<= ls_maxiter times)
+        T newf;
+        int evals = 0;
+        do {
+            if (!first) {
+                if (evals > 0) a *= contraction;
+                set_trial(a);
+            }
             newf = cost_trial();
             ++evals;
+        } while (!first && newf > cost + suff * a * df0 && evals <= opt.ls_maxiter);
+
+        if (first) {   // this pass was the evaluation at the starting point
+            first = false;
+            cost = newf;
+            if (mode == 0) {
+                if (lane == 0) value[rid] = static_cast<double>(-cost);
+                if (grad_out) {
+                    assemble_grad(Om);
+                    // ambient Riemannian gradient of EI: L (-Om) L^T
+                    for (int e = lane; e < DD; e += 32) {
+                        const int rr = e / d, c = e % d;
+                        double s = 0.0;
+                        for (int a = 0; a <= rr; ++a)
+                            for (int b = 0; b <= c; ++b) {
+                                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                                s += static_cast<double>(tmp[rr * d + a]) * static_cast<double>(Om[ui(d, lo, hi)]) *
+                                     static_cast<double>(tmp[c * d + b]);
+                            }
+                        grad_out[rid * DD + e] = -s;
+                    }
+                }
+                return;
+            }
+            assemble_grad(Om);
+            gPg = sym_inner(Om, Om);
+            gradnorm = M<T>::sqrt_(gPg);
+            for (int e = lane; e < TRI; e += 32) Hh[e] = -Om[e];
+            __syncwarp();
+            continue;
         }
+
         const bool stay = newf > cost;
         if (stay) {
             a = T(0);

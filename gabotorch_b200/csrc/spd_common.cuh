@@ -116,13 +116,112 @@ struct JacobiTraits<double> {
     static __device__ __forceinline__ float dist_(float s) { return sqrtf(s + 1e-15f); }
 };
 
+// Round-robin ("tournament") ordering of the index pairs of a sweep: m - 1 rounds of m / 2 DISJOINT pairs
+// (m = d rounded up to even; pairs that involve the dummy index d are skipped).  The rotations of one round touch
+// different columns, so a thread can overlap them -- the row-cyclic order (0,1),(0,2),... makes every rotation depend on
+// the previous one, and both the SPD(8) Gram kernel and the acquisition kernel are bound by that dependency chain.
+template <int d>
+struct RoundRobin {
+    static constexpr int m = (d % 2 == 0) ? d : d + 1;
+    static constexpr int kRounds = m - 1;
+    static constexpr int kPairs = m / 2;
+    static __host__ __device__ constexpr int player(int round, int i) {
+        return i == 0 ? 0 : 1 + ((i - 1 + round) % (m - 1));
+    }
+    static __host__ __device__ constexpr int lo(int round, int j) {
+        return player(round, j) < player(round, m - 1 - j) ? player(round, j) : player(round, m - 1 - j);
+    }
+    static __host__ __device__ constexpr int hi(int round, int j) {
+        return player(round, j) < player(round, m - 1 - j) ? player(round, m - 1 - j) : player(round, j);
+    }
+};
+
+// One-sided Jacobi with the round-robin ordering, branch-free inside a round: the m / 2 inner products, rotation
+// parameters and column updates of a round are independent instruction streams (rotations that are already converged
+// get the exact identity by selection, so a lane's result still does not depend on its warp neighbours).
+template <int d, typename T>
+__device__ __forceinline__ void jacobi_onesided_rr(T (&G)[d][d], T (&lam)[d]) {
+    using Tr = JacobiTraits<T>;
+    using RR = RoundRobin<d>;
+    constexpr bool kF32 = sizeof(T) == 4;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        T s = T(0);
+#pragma unroll
+        for (int r = 0; r < d; ++r) s = fma(G[r][k], G[r][k], s);
+        lam[k] = s;
+    }
+#pragma unroll 1
+    for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int round = 0; round < RR::kRounds; ++round) {
+            T c[RR::kPairs];
+            bool need[RR::kPairs];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < RR::kPairs; ++j) {
+                constexpr int dummy = d;  // index d does not exist when d is odd
+                const int p = RR::lo(round, j), q = RR::hi(round, j);
+                c[j] = T(0);
+                need[j] = false;
+                if (q < dummy) {
+                    T s = T(0);
+#pragma unroll
+                    for (int r = 0; r < d; ++r) s = fma(G[r][p], G[r][q], s);
+                    c[j] = s;
+                    need[j] = s * s > Tr::tol2() * (lam[p] * lam[q]);
+                    any = any || need[j];
+                }
+            }
+            if (any) {
+                rotated = true;
+#pragma unroll
+                for (int j = 0; j < RR::kPairs; ++j) {
+                    const int p = RR::lo(round, j), q = RR::hi(round, j);
+                    if (q < d) {
+                        const T a = lam[p], b = lam[q];
+                        T cs, sn, tc;
+                        Tr::rotation(a, b, c[j], cs, sn, tc);
+                        cs = need[j] ? cs : T(1);
+                        sn = need[j] ? sn : T(0);
+                        tc = need[j] ? tc : T(0);
+#pragma unroll
+                        for (int r = 0; r < d; ++r) {
+                            const T gp = G[r][p], gq = G[r][q];
+                            G[r][p] = fma(cs, gp, -sn * gq);
+                            G[r][q] = fma(sn, gp, cs * gq);
+                        }
+                        if (kF32) {
+                            lam[p] = a - tc;
+                            lam[q] = b + tc;
+                        } else {  // the fp64 angle is approximate: exact expression for the rotated norms
+                            const T c2 = cs * cs, s2 = sn * sn, x = T(2) * cs * sn * c[j];
+                            lam[p] = fma(c2, a, fma(s2, b, -x));
+                            lam[q] = fma(s2, a, fma(c2, b, x));
+                        }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(__activemask(), rotated)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        T s = T(0);
+#pragma unroll
+        for (int r = 0; r < d; ++r) s = fma(G[r][k], G[r][k], s);
+        lam[k] = s;
+    }
+}
+
 // Stopping rule: a rotation is applied while c^2 > tol2 * a * b; the sweeps end when no lane of the warp rotated.
 // (Stopping a sweep earlier on the strength of quadratic convergence is NOT safe here: for nearly identical matrices
 // W = I + E the iteration converges relative to |E|, not to the diagonal, and d^2 ~ |E|_F^2 needs the off-diagonal part
 // resolved to ~1e-7 of the DIAGONAL to keep |d - d_ref| <= 1e-6.)
 // Converged rotations are skipped per lane, so the result of a pair does not depend on the other pairs of its warp.
 template <int d, typename T>
-__device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
+__device__ __forceinline__ void jacobi_onesided_cyclic(T (&G)[d][d], T (&lam)[d]) {
     using Tr = JacobiTraits<T>;
     constexpr bool kF32 = sizeof(T) == 4;
 #pragma unroll
@@ -132,6 +231,7 @@ __device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
         for (int r = 0; r < d; ++r) s = fma(G[r][k], G[r][k], s);
         lam[k] = s;
     }
+#pragma unroll 1
     for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
         bool rotated = false;
 #pragma unroll
@@ -194,6 +294,7 @@ __device__ __forceinline__ void jacobi_onesided_x2(float2 (&G)[d][d], float2 (&l
         for (int r = 1; r < d; ++r) s = fma2(G[r][k], G[r][k], s);
         lam[k] = s;
     }
+#pragma unroll 1
     for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
         bool rotated = false;
 #pragma unroll
@@ -277,6 +378,16 @@ __device__ __forceinline__ void tri_product(AccA A, AccL L, T (&G)[d][d]) {
     }
 }
 
+// d <= 3 has at most one real pair per round: the row-cyclic form (with its per-rotation skip) is the cheaper one there.
+template <int d, typename T>
+__device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
+    if constexpr (d >= 4) {
+        jacobi_onesided_rr<d, T>(G, lam);
+    } else {
+        jacobi_onesided_cyclic<d, T>(G, lam);
+    }
+}
+
 // Reference tail (spd_utils_torch.py:108-120): eigenvalues rounded to fp32, log / square / sum / sqrt(+1e-15) in fp32.
 // The fp32 compute path takes the logs and the root on the MUFU (abs. error of d <= 3e-7, inside the 1e-6 floor the
 // reference's own float32 eigenvalues leave); the fp64 ("reference-grade") path uses the IEEE-accurate logf / sqrtf.
@@ -339,6 +450,7 @@ __device__ __forceinline__ void jacobi_symmetric(T (&S)[d][d], T (&lam)[d], T (&
 #pragma unroll
         for (int c = r; c < d; ++c) fro = fma((r == c) ? T(1) : T(2), S[r][c] * S[r][c], fro);
     const T thr = Tr::tol() * Tr::sqrt_(fro);
+#pragma unroll 1
     for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
         bool rotated = false;
 #pragma unroll

@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(kThreads)
                 T G[d][d];
                 tri_product<d, T>([&](int e) { return Ai[e]; }, Lj, G);
                 T lam[d];
-                jacobi_onesided<d, T>(G, lam);
+                // throughput-bound here: the row-cyclic order with its per-rotation skip does less work than the
+                // branch-free round-robin form (which wins where latency binds, in the acquisition kernel)
+                jacobi_onesided_cyclic<d, T>(G, lam);
                 store(i0 + i, finish<KIND, T>(ai_distance_from_eigs<d, T>(lam), kp));
             }
         }
