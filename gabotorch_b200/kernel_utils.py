@@ -29,6 +29,12 @@ def _reject_input_grad(*xs):
             'optimiser (manifold_optimization.gen_candidates_manifold) evaluates the Riemannian gradient in closed form')
 
 
+def _host_result(x1, x2):
+    """True when the caller works with host tensors and the result is wanted on the host (two distinct operands)."""
+    return (torch.is_tensor(x1) and torch.is_tensor(x2) and not x1.is_cuda and not x2.is_cuda and x1 is not x2
+            and x1.dim() == 2 and x2.dim() == 2)
+
+
 def _finish(out, like):
     """Result on the caller's device (the reference returns CPU float64 for CPU inputs).  Host results land in pinned
     memory (torch's caching host allocator recycles the block), so the read-back runs at PCIe speed, not pageable speed."""
@@ -137,7 +143,14 @@ class SpdAffineInvariantGaussianKernel(_BetaKernel):
         if _needs_param_grad(self.raw_beta):
             out = _param_gram(lambda: ops.spd_ai_gram(x1, x2, kind=_lib.KIND_DIST, compute=self._compute()), beta, 2)
         else:
-            out = ops.spd_ai_gram(x1, x2, float(beta.detach()), _lib.KIND_GAUSS, compute=self._compute())
+            # host inputs: the per-pair kernel stores straight into a pinned host tensor (the PCIe transfer of the
+            # Gram matrix overlaps its computation); the mirrored x1-is-x2 form stays on the device path
+            host = _host_result(x1, x2)
+            out = ops.spd_ai_gram(x1, x2, float(beta.detach()), _lib.KIND_GAUSS, compute=self._compute(),
+                                  host_out=host)
+            if host:
+                torch.cuda.current_stream().synchronize()
+                return out
         return _finish(out, x1)
 
 

@@ -143,6 +143,26 @@ def test_rcg_stopping_criteria():
     assert torch.all(why3 >= 2) and int(it3.max()) < 999           # converges long before maxiter
 
 
+@pytest.mark.parametrize('compute', [_lib.GABO_F32, _lib.GABO_F64])
+def test_sphere_rcg_speculative_line_search_is_exactly_the_sequential_one(compute):
+    # The launcher picks the speculation width from the number of restarts (4 warps per restart up to 148 restarts,
+    # 2 up to 1216, plain sequential search beyond).  Speculation evaluates several trial steps of pymanopt's
+    # backtracking at once and keeps the first acceptable one, so iterates, values and iteration counts must be
+    # BIT-IDENTICAL to the sequential search whatever the width.
+    rng, gp = sphere_problem(6, 32, beta=1.0 + math.log(2.0), noise=1e-2, seed=77)
+    x0 = osph.rand(rng, 1300, 6)
+    dgp = device_gp(gp, compute)
+    seq = ops.acq_rcg(dgp, x0, maxiter=40)               # width 1
+    two = ops.acq_rcg(dgp, x0[:600], maxiter=40)         # width 2
+    four = ops.acq_rcg(dgp, x0[:100], maxiter=40)        # width 4
+    for part, m in ((two, 600), (four, 100)):
+        assert torch.equal(part[0], seq[0][:m])          # candidates
+        assert torch.equal(part[1], seq[1][:m])          # EI values
+        assert torch.equal(part[2], seq[2][:m])          # iterations
+        assert torch.equal(part[3], seq[3][:m])          # stopping reasons
+    assert int(seq[2].max()) > 3
+
+
 def test_argmax_records_is_exact_and_sharding_invariant():
     rng = np.random.default_rng(0)
     v = rng.standard_normal(5000).astype(np.float32).astype(np.float64)
