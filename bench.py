@@ -258,6 +258,18 @@ class Bench:
         self.launches = 0
 
     # -- helpers ---------------------------------------------------------------------------------------------
+    def ncu_traffic(self, kernel):
+        """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of the same
+        command (profiles/rNN_traffic.json, written by scripts/make_profiles.py); None when there is no capture.
+        For the N = 2048 Gram it is far BELOW the algorithmic bytes: the 33.5 MB result stays in the 126 MB L2."""
+        try:
+            files = sorted(f for f in os.listdir(os.path.join(ROOT, 'profiles')) if f.endswith('_traffic.json'))
+            with open(os.path.join(ROOT, 'profiles', files[-1])) as f:
+                t = json.load(f)[kernel]
+            return t['dram_bytes_read'] + t['dram_bytes_write']
+        except Exception:
+            return None
+
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
@@ -350,7 +362,8 @@ class Bench:
         alg_bytes = pairs * 8 + 2 * N_POINTS * fs * 8
         achieved = alg_bytes / (roof_ms * 1e-3) / 1e9
         roofline = {'kernel': 'spd_ai_gram_kernel<3,float,double,GAUSS>', 'bound': 'hbm', 'achieved': achieved,
-                    'peak': self.hbm_peak, 'unit': 'GB/s', 'frac': achieved / self.hbm_peak, 'traffic': None,
+                    'peak': self.hbm_peak, 'unit': 'GB/s', 'frac': achieved / self.hbm_peak,
+                    'traffic': self.ncu_traffic('spd_ai_gram_kernel<3, float, double, 0>'),
                     'peak_source': self.peak_src, 'ms_per_launch': roof_ms, 'algorithmic_bytes_per_launch': alg_bytes,
                     'note': 'the per-pair Jacobi solve is FP32-pipe bound (about 0.6 kFLOP per 8 output bytes): '
                             'see compute_roofline; the HBM fraction is reported because the contract asks for it'}

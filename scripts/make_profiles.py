@@ -55,6 +55,23 @@ for rep in sorted(f for f in os.listdir(go) if f.endswith('.ncu-rep')):
         lines += ['', 'SASS mix (%d warp-instructions): ' % tot + ', '.join('%s %.1f%% (stall samples %.1f%%)' % (op, p, s) for op, n, p, s in ops), '']
 open(os.path.join(out_dir, '%s_ncu_summary.md' % tag), 'w').write('\n'.join(lines) + '\n')
 
+# per-kernel DRAM traffic of the captured launch (bench.py reports it as roofline.traffic)
+import json, re
+traffic = {}
+def _bytes(v, u):
+    v = float(v.replace(',', ''))
+    return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+for rep in sorted(f for f in os.listdir(go) if f.endswith('.ncu-rep')):
+    hdr, units, rows = raw(os.path.join(go, rep))
+    for r in rows:
+        d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
+        name = re.sub(r'^void |unnamed>::|<unnamed>::|gabo::', '', d.get('Kernel Name', '?')).split('(')[0]
+        traffic[name] = {'dram_bytes_read': _bytes(d['dram__bytes_read.sum'], u['dram__bytes_read.sum']),
+                         'dram_bytes_write': _bytes(d['dram__bytes_write.sum'], u['dram__bytes_write.sum']),
+                         'gpu_time_us_under_ncu': float(d['gpu__time_duration.sum'].replace(',', '')) * {'us': 1, 'ms': 1e3, 'ns': 1e-3}[u['gpu__time_duration.sum']],
+                         'report': rep}
+json.dump(traffic, open(os.path.join(out_dir, '%s_traffic.json' % tag), 'w'), indent=1)
+
 # launch list: aggregate per kernel + keep the raw csv (small)
 lc = os.path.join(go, 'launches.csv')
 if os.path.exists(lc):
