@@ -5,7 +5,7 @@
 
 Headline workload (BASELINE.json configs[1]): the SpdAffineInvariantGaussianKernel Gram matrix on SPD(3), N = 2048 points
 given as Mandel vectors, K = exp(-beta d_AI^2), fp64 output like the reference (kernels_spd.py:72-100).
-One "step" = one full Gram build = per-point factorisation of both operands (gabo_spd_factor x 2) + the per-pair kernel
+One "step" = one full Gram build = per-point factorisation of both operands (gabo_spd_factor2, one launch) + the per-pair kernel
 (gabo_spd_ai_gram, all N x N pairs -- the symmetric shortcut of the product API is NOT used for the headline value).
 
   value        pairs/s, inputs resident in HBM, CUDA-event time of the K steps (L2 flushed between steps), max over ranks
@@ -255,7 +255,6 @@ class Bench:
         self.peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in self.peaks else 'fallback (B200_PROFILING.md)'
         self.clocks = ClockSampler(self.local_rank)
         self.clocks.start()
-        self.launches = 0
 
     # -- helpers ---------------------------------------------------------------------------------------------
     def ncu_traffic(self, kernel):
@@ -328,14 +327,13 @@ class Bench:
     def spd_gram_step(self, st, beta, symmetric=False):
         lib, lb, p, s = self.lib, self._lib, self.p, self._lib.stream_ptr()
         n, d = st['n'], st['d']
-        lb.check(lib.gabo_spd_factor(p(st['x1']), n, d, 1, p(st['fac1']), p(st['flags']), s), 'gabo_spd_factor')
         if symmetric:
             f2 = st['fac1']
-            self.launches += 2
+            lb.check(lib.gabo_spd_factor(p(st['x1']), n, d, 1, p(st['fac1']), p(st['flags']), s), 'gabo_spd_factor')
         else:
             f2 = st['fac2']
-            lb.check(lib.gabo_spd_factor(p(st['x2']), n, d, 1, p(f2), p(st['flags']), s), 'gabo_spd_factor')
-            self.launches += 3
+            lb.check(lib.gabo_spd_factor2(p(st['x1']), n, p(st['x2']), n, d, 1, p(st['fac1']), p(f2), p(st['flags']), s),
+                     'gabo_spd_factor2')
         lb.check(lib.gabo_spd_ai_gram(p(st['fac1']), n, p(f2), n, d, beta, lb.KIND_GAUSS, lb.GABO_F32,
                                       1 if symmetric else 0, p(st['out']), lb.GABO_F64, n, s), 'gabo_spd_ai_gram')
 
@@ -350,7 +348,7 @@ class Bench:
         st = self.spd_gram_setup(N_POINTS, SPD_D, 1234)
         pairs = N_POINTS * N_POINTS
         total_ms = self.time_steps(lambda: self.spd_gram_step(st, BETA_SPD3), args.steps, args.warmup)
-        launches = 3 * args.steps                              # 2 x spd_factor_kernel + 1 x spd_ai_gram_kernel per step
+        launches = 2 * args.steps                              # spd_factor_kernel (both operands) + spd_ai_gram_kernel per step
         assert int(st['flags'].item()) == 0
         ms_per_step = total_ms / args.steps
         value = self.world * pairs / (ms_per_step * 1e-3)

@@ -42,6 +42,7 @@ SIGNATURES = {
     'gabo_mandel_pack': (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_spd_factor_stride': (c_i64, [c_i32]),
     'gabo_spd_factor': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    'gabo_spd_factor2': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'gabo_spd_ai_gram': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_f64, c_i32, c_i32, c_i32, c_ptr, c_i32, c_i64,
                                  c_ptr]),
     'gabo_frobenius_gram': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_f64, c_i32, c_ptr, c_i32, c_i64, c_ptr]),

@@ -15,6 +15,8 @@
 //   w = (1-|c|)/2,  r^2 = 4 asin^2(sqrt w) = 4w(1 + w P(w))   (degree-8 minimax P on [0, 1/2], no sqrt / acos needed),
 //   d^2 = r^2 for c >= 0,  (pi - r)^2 for c < 0,   K = 2^(d^2 * (-beta log2 e)).
 // Relative error of d^2 is ~1.8e-7, of K about (beta d^2) * 2e-7 + 1e-6.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace gabo {
@@ -27,7 +29,12 @@ constexpr int kTileN = kThreads * kVec;    // 512 columns per tile
 constexpr int kTileM = 32;                 // rows per tile
 
 struct TailParams {
-    float k_hi, k_lo;  // -param * log2(e) split in two floats (Gauss / Laplace)
+    float k_hi, k_lo;  // k = -param * log2(e) split in two floats (Gauss / Laplace)
+    // Gaussian kind, fused form: the exponent t = k d^2 of K = 2^t straight from w2 = 1 - |c|, with k folded into the
+    // polynomial on the host:  near side  t = w2 (2k + w2 sum_j (k a_j / 2^j) w2^j)  (= k * 4 asin^2(sqrt(w2 / 2))),
+    // far side (c < 0)  t = -(sqrt|k| pi - sqrt(-t_near))^2.  Saves the three scalings (x 1/2, x 4, x k) per pair.
+    float pc[10];      // pc[0..8] = k a_j / 2^j for j = 8 .. 0,  pc[9] = 2k
+    float skpi_hi, skpi_lo;  // sqrt|k| * pi in two floats
 };
 
 // d^2 (and optionally d) of the geodesic distance from the fp64 inner product.
@@ -87,6 +94,19 @@ __device__ __forceinline__ float2 tail2(double c0, double c1, const TailParams& 
     float w0 = static_cast<float>(1.0 - fabs(c0)), w1 = static_cast<float>(1.0 - fabs(c1));
     w0 = (w0 < kClampW) ? kClampW : w0;
     w1 = (w1 < kClampW) ? kClampW : w1;
+    if (KIND == GABO_KIND_GAUSS) {   // fused exponent (see TailParams): 10 packed FMAs + the far-side fix-up
+        const float2 w = make_float2(w0, w1);
+        float2 p = splat2(tp.pc[0]);
+#pragma unroll
+        for (int j = 1; j <= 9; ++j) p = fma2(p, w, splat2(tp.pc[j]));
+        const float2 tn = mul2(w, p);                                         // k d^2 on the near side (<= 0)
+        const float2 s = make_float2(sqrt_approx(-tn.x), sqrt_approx(-tn.y));
+        const float2 u = add2(sub2(splat2(tp.skpi_hi), s), splat2(tp.skpi_lo));  // sqrt|k| (pi - r)
+        const float2 tf = mul2(make_float2(-u.x, -u.y), u);
+        const float tx = (__double2hiint(c0) < 0) ? tf.x : tn.x;
+        const float ty = (__double2hiint(c1) < 0) ? tf.y : tn.y;
+        return make_float2(ex2_approx(tx), ex2_approx(ty));
+    }
     const float2 r2 = mul2(splat2(4.0f), asin2_sqrt2(mul2(splat2(0.5f), make_float2(w0, w1))));
     const bool n0 = __double2hiint(c0) < 0, n1 = __double2hiint(c1) < 0;
     float2 v;
@@ -280,6 +300,15 @@ TailParams make_tail(double param, int kind) {
     const double k = (kind == GABO_KIND_DIST) ? 0.0 : -param * 1.4426950408889634074;
     tp.k_hi = static_cast<float>(k);
     tp.k_lo = static_cast<float>(k - static_cast<double>(tp.k_hi));
+    // coefficients of asin2_sqrt (common.cuh), highest power first; a_j is the coefficient of w^j in P(w)
+    static const double a_hi_first[9] = {0.3292977809906006, -0.3745849132537842, 0.28826069831848145,
+                                         -0.03355207294225693, 0.07700732350349426, 0.07967597246170044,
+                                         0.1143670305609703, 0.17777620255947113, 0.3333333432674408};
+    for (int i = 0; i < 9; ++i) tp.pc[i] = static_cast<float>(k * a_hi_first[i] / static_cast<double>(1 << (8 - i)));
+    tp.pc[9] = static_cast<float>(2.0 * k);
+    const double skpi = sqrt(fabs(k)) * 3.14159265358979323846;
+    tp.skpi_hi = static_cast<float>(skpi);
+    tp.skpi_lo = static_cast<float>(skpi - static_cast<double>(tp.skpi_hi));
     return tp;
 }
 

@@ -149,6 +149,20 @@ def spd_factor(x, d, is_mandel, check=True, flags=None):
     return fac
 
 
+def spd_factor_pair(x1, x2, d, is_mandel, flags):
+    """Factor records of both operands of a Gram build with ONE launch (gabo_spd_factor2)."""
+    lib = _lib.load()
+    x1, x2 = to_dev64(x1), to_dev64(x2)
+    fs = lib.gabo_spd_factor_stride(d)
+    if fs < 0:
+        raise ValueError('SPD(%d): matrix size outside [1, %d]' % (d, _lib.MAX_SPD_DIM))
+    f1 = torch.empty(x1.shape[0], fs, dtype=torch.float64, device=x1.device)
+    f2 = torch.empty(x2.shape[0], fs, dtype=torch.float64, device=x1.device)
+    _lib.check(lib.gabo_spd_factor2(_p(x1), x1.shape[0], _p(x2), x2.shape[0], d, 1 if is_mandel else 0, _p(f1), _p(f2),
+                                    _p(flags), _lib.stream_ptr()), 'gabo_spd_factor2')
+    return f1, f2
+
+
 def check_spd_flags(flags):
     if int(flags.item()) != 0:
         raise NotPositiveDefiniteError('input contains a matrix that is not positive definite')
@@ -191,8 +205,10 @@ def spd_ai_gram(x1, x2, param=0.0, kind=_lib.KIND_GAUSS, is_mandel=True, compute
         out = torch.empty(b1.shape[0], n1, n2, dtype=out_dtype, device=x1.device)
     flags = torch.zeros(1, dtype=torch.int32, device=x1.device)
     for b in range(b1.shape[0]):
-        f1 = spd_factor(b1[b], d, is_mandel, flags=flags)
-        f2 = f1 if same else spd_factor(b2[b], d, is_mandel, flags=flags)
+        if same:
+            f1 = f2 = spd_factor(b1[b], d, is_mandel, flags=flags)
+        else:
+            f1, f2 = spd_factor_pair(b1[b], b2[b], d, is_mandel, flags)
         # the mirrored (symmetric) form writes columns: fine in HBM, wrong over PCIe
         spd_ai_gram_from_factors(f1, f2, d, param, kind, compute, symmetric=same and not host_out, out=out[b])
     if check:

@@ -87,6 +87,9 @@ int gabo_mandel_pack(const double* mat, int64_t n, int d, double* vec, void* str
  * ------------------------------------------------------------------------------------------------------------------ */
 int64_t gabo_spd_factor_stride(int d);
 int gabo_spd_factor(const double* x, int64_t n, int d, int input_is_mandel, double* fac, int32_t* flags, void* stream);
+/* Both operands of a Gram build in ONE launch (either set may be empty). */
+int gabo_spd_factor2(const double* x1, int64_t n1, const double* x2, int64_t n2, int d, int input_is_mandel, double* fac1,
+                     double* fac2, int32_t* flags, void* stream);
 int gabo_spd_ai_gram(const double* fac1, int64_t n1, const double* fac2, int64_t n2, int d, double param, int kind,
                      int compute, int symmetric, void* out, int out_dtype, int64_t ld_out, void* stream);
 
