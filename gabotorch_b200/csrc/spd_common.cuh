@@ -215,6 +215,101 @@ __device__ __forceinline__ void jacobi_onesided_rr(T (&G)[d][d], T (&lam)[d]) {
     }
 }
 
+// The same round-robin sweep as a LOOP over the rounds (Brent-Luk style): every round rotates the FIXED column pairs
+// (0,1), (2,3), ... and then moves the columns one step along the tournament cycle (position 0 stays), so after m - 1
+// rounds every pair has met once and the columns are back in place.  The loop body is ~350 instructions instead of the
+// ~2000 of the fully unrolled sweep: the acquisition kernels, whose code no longer fitted the instruction caches (ncu:
+// stall_no_instruction 4-6 warps per issue), run out of the L0/L1.5 instruction cache again; the price is the register
+// moves of the permutation (+25 % instructions).  Odd d gets a zero dummy column (its rotations are identities).
+template <int d, typename T>
+__device__ __forceinline__ void jacobi_onesided_loop(T (&G)[d][d], T (&lam)[d]) {
+    using Tr = JacobiTraits<T>;
+    constexpr bool kF32 = sizeof(T) == 4;
+    constexpr int m = d + (d & 1);
+    constexpr int h = m / 2;
+    T C[d][m], l[m];
+#pragma unroll
+    for (int k = 0; k < m; ++k) {
+        T s = T(0);
+#pragma unroll
+        for (int r = 0; r < d; ++r) {
+            C[r][k] = (k < d) ? G[r][k < d ? k : 0] : T(0);
+            s = fma(C[r][k], C[r][k], s);
+        }
+        l[k] = s;
+    }
+#pragma unroll 1
+    for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
+        bool rotated = false;
+#pragma unroll 1
+        for (int round = 0; round < m - 1; ++round) {
+            T c[h];
+            bool need[h];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < h; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int r = 0; r < d; ++r) s = fma(C[r][2 * j], C[r][2 * j + 1], s);
+                c[j] = s;
+                need[j] = s * s > Tr::tol2() * (l[2 * j] * l[2 * j + 1]);
+                any = any || need[j];
+            }
+            if (any) {
+                rotated = true;
+#pragma unroll
+                for (int j = 0; j < h; ++j) {
+                    const T a = l[2 * j], b = l[2 * j + 1];
+                    T cs, sn, tc;
+                    Tr::rotation(a, b, c[j], cs, sn, tc);
+                    cs = need[j] ? cs : T(1);
+                    sn = need[j] ? sn : T(0);
+                    tc = need[j] ? tc : T(0);
+#pragma unroll
+                    for (int r = 0; r < d; ++r) {
+                        const T gp = C[r][2 * j], gq = C[r][2 * j + 1];
+                        C[r][2 * j] = fma(cs, gp, -sn * gq);
+                        C[r][2 * j + 1] = fma(sn, gp, cs * gq);
+                    }
+                    if (kF32) {
+                        l[2 * j] = a - tc;
+                        l[2 * j + 1] = b + tc;
+                    } else {
+                        const T c2 = cs * cs, s2 = sn * sn, x = T(2) * cs * sn * c[j];
+                        l[2 * j] = fma(c2, a, fma(s2, b, -x));
+                        l[2 * j + 1] = fma(s2, a, fma(c2, b, x));
+                    }
+                }
+            }
+            // tournament step: 1 <- 3 <- 5 ... <- m-1 <- m-2 <- m-4 ... <- 2 <- 1   (one cycle through all but position 0)
+            if (m > 2) {
+#pragma unroll
+                for (int r = 0; r <= d; ++r) {   // r == d moves the norms
+                    auto at = [&](int k) -> T& { return r < d ? C[r < d ? r : 0][k] : l[k]; };
+                    const T t = at(1);
+#pragma unroll
+                    for (int k = 1; k + 2 <= m - 1; k += 2) at(k) = at(k + 2);          // odd positions move down
+                    at(m - 1) = at(m - 2);
+#pragma unroll
+                    for (int k = m - 2; k - 2 >= 2; k -= 2) at(k) = at(k - 2);          // even positions move up
+                    at(2) = t;
+                }
+            }
+        }
+        if (!__any_sync(__activemask(), rotated)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        T s = T(0);
+#pragma unroll
+        for (int r = 0; r < d; ++r) {
+            G[r][k] = C[r][k];
+            s = fma(C[r][k], C[r][k], s);
+        }
+        lam[k] = s;
+    }
+}
+
 // Stopping rule: a rotation is applied while c^2 > tol2 * a * b; the sweeps end when no lane of the warp rotated.
 // (Stopping a sweep earlier on the strength of quadratic convergence is NOT safe here: for nearly identical matrices
 // W = I + E the iteration converges relative to |E|, not to the diagonal, and d^2 ~ |E|_F^2 needs the off-diagonal part
@@ -383,6 +478,16 @@ template <int d, typename T>
 __device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {
     if constexpr (d >= 4) {
         jacobi_onesided_rr<d, T>(G, lam);
+    } else {
+        jacobi_onesided_cyclic<d, T>(G, lam);
+    }
+}
+
+// The form for kernels that inline the solve into a large body (acquisition): compact looped rounds for d >= 4.
+template <int d, typename T>
+__device__ __forceinline__ void jacobi_onesided_compact(T (&G)[d][d], T (&lam)[d]) {
+    if constexpr (d >= 4) {
+        jacobi_onesided_loop<d, T>(G, lam);
     } else {
         jacobi_onesided_cyclic<d, T>(G, lam);
     }
