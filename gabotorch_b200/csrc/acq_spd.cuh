@@ -654,8 +654,13 @@ __global__ void __launch_bounds__(kSpec * 32)
                 }
                 norm_d = M<T>::sqrt_(sym_inner(Hh, Hh));
 
-                // eigen-decomposition of the whitened direction (every lane, redundantly; uniform result)
-                {
+                // eigen-decomposition of the whitened direction.  d >= 5: warp 0, cooperatively in shared memory (tmp =
+                // scratch); small d: every lane redundantly in registers (cheaper than the round trips; measured at d = 3)
+                if constexpr (d >= 5) {
+                    __syncthreads();
+                    if (warp == 0) jacobi_symmetric_warp<d, T>(Hh, tmp, Vs, lamH, lane);
+                    __syncthreads();
+                } else {
                     T S[d][d], lam[d], V[d][d];
 #pragma unroll
                     for (int rr = 0; rr < d; ++rr)

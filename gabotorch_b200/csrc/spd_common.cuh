@@ -597,6 +597,82 @@ __device__ __forceinline__ void jacobi_symmetric(T (&S)[d][d], T (&lam)[d], T (&
     for (int k = 0; k < d; ++k) lam[k] = S[k][k];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-cooperative two-sided Jacobi for ONE symmetric (possibly indefinite) d x d matrix in shared memory, d <= 8:
+// lane = 8 j + r works on pair j of the current round-robin round and on row (then column) r.  The rotations of a
+// round act on disjoint index pairs, so all column updates (S <- S J, V <- V J) run in parallel, then all row updates
+// (S <- J^T S).  ~45 instructions per round instead of the ~3000-instruction unrolled sweep every lane used to run
+// redundantly for the same matrix (the whitened search direction of the acquisition solver).
+//   Hu : upper triangle, packed row-major (entry (r,c), r <= c, at r d - r (r-1)/2 + c - r);  S : d*d scratch;
+//   V  : d*d eigenvectors (row-major, column k = k-th eigenvector);  lam : d eigenvalues.  Call with a full warp.
+// ---------------------------------------------------------------------------------------------------------------
+template <int d, typename T>
+__device__ __forceinline__ void jacobi_symmetric_warp(const T* Hu, T* S, T* V, T* lam, int lane) {
+    using Tr = SymJacobiTraits<T>;
+    using RR = RoundRobin<d>;
+    static_assert(d <= 8, "one row per lane octet");
+    __syncwarp();
+    T fro = T(0);
+    for (int e = lane; e < d * d; e += 32) {
+        const int r = e / d, c = e % d;
+        const int lo = r < c ? r : c, hi = r < c ? c : r;
+        const T v = Hu[lo * d - (lo * (lo - 1)) / 2 + (hi - lo)];
+        S[e] = v;
+        V[e] = (r == c) ? T(1) : T(0);
+        fro = fma(v, v, fro);
+    }
+    fro = warp_sum(fro);
+    const T thr = Tr::tol() * Tr::sqrt_(fro);
+    __syncwarp();
+    const int j = lane >> 3, r = lane & 7;
+    const bool lane_ok = (j < RR::kPairs) && (r < d);
+#pragma unroll 1
+    for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
+        bool rotated = false;
+#pragma unroll 1
+        for (int round = 0; round < RR::kRounds; ++round) {
+            int p = 0, q = 1;
+            bool act = false;
+            T cs = T(1), sn = T(0);
+            if (j < RR::kPairs) {
+                const int a = RR::player(round, j), b = RR::player(round, RR::m - 1 - j);
+                p = a < b ? a : b;
+                q = a < b ? b : a;
+                if (q < d) {
+                    const T apq = S[p * d + q];
+                    if (fabs(apq) > thr) {
+                        act = true;
+                        const T tau = (S[q * d + q] - S[p * d + p]) * Tr::rcp_(T(2) * apq);
+                        const T t = copysign(T(1), tau) * Tr::rcp_(fabs(tau) + Tr::sqrt_(fma(tau, tau, T(1))));
+                        cs = Tr::rsqrt_(fma(t, t, T(1)));
+                        sn = t * cs;
+                    }
+                }
+            }
+            rotated = rotated || act;
+            __syncwarp();
+            if (act && lane_ok) {           // columns p, q of S and V, row r
+                const T sp = S[r * d + p], sq = S[r * d + q];
+                S[r * d + p] = fma(cs, sp, -sn * sq);
+                S[r * d + q] = fma(sn, sp, cs * sq);
+                const T vp = V[r * d + p], vq = V[r * d + q];
+                V[r * d + p] = fma(cs, vp, -sn * vq);
+                V[r * d + q] = fma(sn, vp, cs * vq);
+            }
+            __syncwarp();
+            if (act && lane_ok) {           // rows p, q of S, column r
+                const T sp = S[p * d + r], sq = S[q * d + r];
+                S[p * d + r] = fma(cs, sp, -sn * sq);
+                S[q * d + r] = fma(sn, sp, cs * sq);
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(0xffffffffu, rotated)) break;
+    }
+    for (int k = lane; k < d; k += 32) lam[k] = S[k * d + k];
+    __syncwarp();
+}
+
 // Full d x d from a packed lower-triangular array (row-major): M[r][c] = tri[r(r+1)/2 + c] for c <= r, else 0.
 template <int d, typename T, typename Acc>
 __device__ __forceinline__ void tri_expand(Acc tri, T (&M)[d][d]) {
