@@ -216,7 +216,7 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -551,7 +551,7 @@ class Bench:
                  else self.extra_acq_spd(R=args.acq_restarts, T=args.acq_steps, d=args.acq_dim))
             self.clocks.stop()
             if self.rank == 0:
-                print(json.dumps(e), flush=True)
+                emit(e)
             return 0
         head = self.headline()
         extras = []
@@ -586,14 +586,34 @@ class Bench:
                 'roofline': head['roofline'], 'compute_roofline': head['compute'], 'cpu_baseline': cpu,
                 'e2e': head['e2e'], 'gpu_launches': head['launches'], 'clocks': clocks, 'extra': extras,
             }
-            print(json.dumps(line), flush=True)
+            emit(line)
         if self.world > 1:
             self.dist.barrier()
             self.dist.destroy_process_group()
         return 0
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything libraries print on stdout while the bench runs (NCCL's version banner, torchrun notices) goes to
+    stderr; the ONE JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + '\n')
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
@@ -617,7 +637,7 @@ def main():
         import subprocess
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
                '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 1000)] + sys.argv
-        return subprocess.call(cmd)
+        return subprocess.call(cmd, stdout=_REAL_STDOUT)     # the children write their JSON line to the real stdout
     return Bench(args).run()
 
 
