@@ -80,7 +80,12 @@ def test_spd_ei_and_gradient(d, n):
 
 
 @pytest.mark.parametrize('manifold,dim,n', [('sphere', 6, 32), ('sphere', 3, 12), ('spd', 3, 16), ('spd', 8, 32),
-                                            ('spd', 2, 40)])
+                                            ('spd', 2, 40),
+                                            # kernel variants: padded dimension 16 with two / four points per lane, the
+                                            # shared-memory fallback (dim > 8 with n > 64), odd SPD sizes (dummy column
+                                            # of the looped Jacobi, warp-cooperative direction solve), n > 32 on SPD
+                                            ('sphere', 9, 40), ('sphere', 4, 70), ('sphere', 12, 100), ('spd', 5, 20),
+                                            ('spd', 7, 16), ('spd', 4, 40)])
 def test_rcg_f64_follows_the_oracle_step_for_step(manifold, dim, n):
     steps = 25
     if manifold == 'sphere':
