@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kAcqWarps * 32)
         if (first) {   // this pass was the evaluation at the starting point
             first = false;
             cost = newf;
-            if (mode == 0) {
+            {   // this kernel only serves gabo_ei_eval now (mode 0); the solver is spd_rcg_cta_kernel
                 if (lane == 0) value[rid] = static_cast<double>(-cost);
                 if (grad_out) {
                     assemble_grad(Om);
@@ -919,12 +919,9 @@ int launch_spd_t(const GpParams& gp, const RcgParams& opt, int mode, double* x, 
         // speculation width from the restart count: idle schedulers (592 on the chip) take speculative trial steps
         const char* e = getenv("GABO_ACQ_SPEC");   // developer switch: force a width
         const int forced = e ? atoi(e) : 0;
-        if (forced == 4) return launch_spd_rcg<d, T, NCH, 4>(gp, opt, x, r, value, iters, reason, stream, true);
         if (forced == 2) return launch_spd_rcg<d, T, NCH, 2>(gp, opt, x, r, value, iters, reason, stream, true);
         if (forced != 1) {
-            int rc = launch_spd_rcg<d, T, NCH, 4>(gp, opt, x, r, value, iters, reason, stream, false);
-            if (rc != 1) return rc;
-            rc = launch_spd_rcg<d, T, NCH, 2>(gp, opt, x, r, value, iters, reason, stream, false);
+            const int rc = launch_spd_rcg<d, T, NCH, 2>(gp, opt, x, r, value, iters, reason, stream, false);
             if (rc != 1) return rc;
         }
         return launch_spd_rcg<d, T, NCH, 1>(gp, opt, x, r, value, iters, reason, stream, true);
