@@ -9,9 +9,12 @@ kernels take ``diag=`` while the SPD kernels take ``diagonal_distance=`` (kernel
 The arithmetic is one fused CUDA launch per Gram matrix (``gabo_sphere_gram`` / ``gabo_spd_factor`` +
 ``gabo_spd_ai_gram``, include/gabo_b200.h); there is no CPU implementation behind these classes.  Gradients: the Gram
 path is differentiable with respect to the kernel parameter (``raw_beta`` / ``raw_lengthscale``), which is what GP
-hyper-parameter fitting needs; gradients with respect to the inputs are provided in closed form by the acquisition
-kernels (``manifold_optimization``), not through autograd.
+hyper-parameter fitting needs.  The sphere kernels also back-propagate to their inputs (``_SphereDistance``); for the
+SPD kernels the input gradient is provided in closed form by the acquisition kernels (``manifold_optimization``),
+not through autograd.
 """
+import math
+
 import torch
 
 from . import _lib, ops
@@ -79,6 +82,44 @@ class _BetaKernel(Kernel):
         return b
 
 
+class _SphereDistance(torch.autograd.Function):
+    """d_ij = acos(clamp(<x1_i, x2_j>)) from the fused kernel, differentiable with respect to the inputs the way the
+    reference's op sequence is (sphere_utils_torch.py:29-55 under autograd): dd/dc = -1 / sqrt(1 - c^2) = -1 / sin d,
+    zero where the clamp is active.  Forward is one launch of ``gabo_sphere_gram(KIND_DIST)``; the backward is two
+    device matrix products on the (N1, N2) weight matrix  -g_ij / sin d_ij."""
+
+    @staticmethod
+    def forward(ctx, x1, x2):
+        a, b = ops.to_dev64(x1), ops.to_dev64(x2)
+        d = ops.sphere_gram(a, b, kind=_lib.KIND_DIST)
+        ctx.save_for_backward(a, b, d)
+        ctx.devs = (x1.device, x2.device, x1.dtype, x2.dtype)
+        return d
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, d = ctx.saved_tensors
+        lo = math.acos(1.0 - 1e-15)                       # clamp active: d == acos(1 - 1e-15) or pi - that
+        live = (d > lo * (1 + 1e-9)) & (d < math.pi - lo * (1 + 1e-9))
+        w = torch.where(live, -g.to(d) / torch.sin(d), torch.zeros_like(d))
+        ga = torch.matmul(w, b) if ctx.needs_input_grad[0] else None
+        gb = torch.matmul(w.transpose(-1, -2), a) if ctx.needs_input_grad[1] else None
+        d1, d2, t1, t2 = ctx.devs
+        return (None if ga is None else ga.to(device=d1, dtype=t1)), (None if gb is None else gb.to(device=d2, dtype=t2))
+
+
+def _sphere_distance_with_grad(x1, x2, diag):
+    if diag:
+        raise NotImplementedError('input gradients of the diag=True branch are not provided')
+    if x1.dim() != 2 or x2.dim() != 2:
+        raise NotImplementedError('input gradients are provided for (N, D) inputs')
+    return _SphereDistance.apply(x1, x2)
+
+
+def _wants_input_grad(*xs):
+    return torch.is_grad_enabled() and any(torch.is_tensor(x) and x.requires_grad for x in xs)
+
+
 def _param_gram(dist_fn, param, power):
     """exp(-param * d^power) with autograd to ``param``: distances from the fused kernel, the exp in torch on-device."""
     d = dist_fn()
@@ -90,9 +131,10 @@ class SphereGaussianKernel(_BetaKernel):
     """exp(-beta d(x1,x2)^2) on the sphere (kernels_sphere.py:15-94)."""
 
     def forward(self, x1, x2, diag=False, **params):
-        _reject_input_grad(x1, x2)
         beta = self._beta_scalar()
-        if _needs_param_grad(self.raw_beta):
+        if _wants_input_grad(x1, x2):      # autograd callers (acquisition via torch.autograd as in the reference)
+            out = _param_gram(lambda: _sphere_distance_with_grad(x1, x2, diag), beta, 2)
+        elif _needs_param_grad(self.raw_beta):
             out = _param_gram(lambda: ops.sphere_gram(x1, x2, kind=_lib.KIND_DIST, diag=diag), beta, 2)
         else:
             out = ops.sphere_gram(x1, x2, float(beta.detach()), _lib.KIND_GAUSS, diag=diag)
@@ -107,10 +149,11 @@ class SphereLaplaceKernel(Kernel):
         super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
 
     def forward(self, x1, x2, diag=False, **params):
-        _reject_input_grad(x1, x2)
         ls = self.lengthscale.reshape(()).double()
         inv = 1.0 / (ls * ls)
-        if _needs_param_grad(self.raw_lengthscale):
+        if _wants_input_grad(x1, x2):
+            out = _param_gram(lambda: _sphere_distance_with_grad(x1, x2, diag), inv, 1)
+        elif _needs_param_grad(self.raw_lengthscale):
             out = _param_gram(lambda: ops.sphere_gram(x1, x2, kind=_lib.KIND_DIST, diag=diag), inv, 1)
         else:
             out = ops.sphere_gram(x1, x2, float(inv.detach()), _lib.KIND_LAPLACE, diag=diag)

@@ -154,3 +154,32 @@ def test_joint_optimize_manifold_spd_with_mandel_processing():
     assert ei_new == pytest.approx(float(acq(new_x[None])[0]), rel=2e-3)
     raw = man.rand_batch(128)
     assert ei_new >= float(acq(ru.symmetric_matrix_to_vector_mandel_torch(raw)[:, None]).max()) * 0.5
+
+
+@pytest.mark.parametrize('kernel', ['gauss', 'laplace'])
+def test_sphere_kernels_backpropagate_to_their_inputs(kernel):
+    # the reference differentiates acos(clamp(<x1, x2>)) with torch.autograd (sphere_utils_torch.py:29-55); the fused
+    # path must give the same input gradients, including zero gradient where the clamp is active (identical points)
+    rng = np.random.default_rng(11)
+    a, b = osph.rand(rng, 17, 5), osph.rand(rng, 23, 5)
+    b[0] = a[0]                                                  # clamp active for the pair (0, 0)
+    wts = torch.from_numpy(rng.standard_normal((17, 23)))
+    x1 = torch.from_numpy(a).clone().requires_grad_(True)
+    x2 = torch.from_numpy(b).clone().requires_grad_(True)
+    if kernel == 'gauss':
+        k = g.SphereGaussianKernel(beta_min=1.0)
+        ref_fn = lambda u, v: osph.sphere_gaussian_kernel(u, v, float(k.beta.detach()))
+    else:
+        k = g.SphereLaplaceKernel()
+        k.lengthscale = 0.8
+        ref_fn = lambda u, v: osph.sphere_laplace_kernel(u, v, 0.8)
+    out = k.forward(x1, x2)
+    (out * wts).sum().backward()
+    r1 = torch.from_numpy(a).clone().requires_grad_(True)
+    r2 = torch.from_numpy(b).clone().requires_grad_(True)
+    ref = ref_fn(r1, r2)
+    (ref * wts).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-7)
+    scale = float(r1.grad.abs().max())
+    np.testing.assert_allclose(x1.grad.numpy(), r1.grad.numpy(), rtol=0, atol=2e-5 * scale)
+    np.testing.assert_allclose(x2.grad.numpy(), r2.grad.numpy(), rtol=0, atol=2e-5 * scale)
