@@ -465,6 +465,25 @@ class Bench:
                 'candidates_per_s': self.world * R * T / (ms * 1e-3), 'ms_per_step': ms, 'mean_iters': iters,
                 'collective': 'one all_gather of (value, gidx, candidate) per solve' if self.world > 1 else 'none (1 GPU)'}
 
+    def extra_ei_screen(self, R=1 << 20, D=6, n_train=32, noise=1e-2, steps=5):
+        """A2 / A4: raw-sample screening -- EI at R random points of S^5 in one launch (manifold_optimize.py:297-309)."""
+        import gabotorch_b200 as g
+        torch, ops = self.torch, self.ops
+        rng = np.random.default_rng(2024)
+        xt = sphere_sample(rng, n_train, D)
+        y = ackley_sphere(xt)
+        base = g.SphereGaussianKernel(beta_min=1.0)
+        model = g.ManifoldGP(torch.from_numpy(xt), torch.from_numpy(y), g.ScaleKernel(base), noise=noise)
+        model.covar_module.outputscale = 1.0
+        gp = g.ExpectedImprovement(model, best_f=float(y.min())).device_gp()
+        gen = torch.Generator(device=self.dev)
+        gen.manual_seed(17 + self.rank)
+        x = torch.randn(R, D, dtype=torch.float64, device=self.dev, generator=gen)
+        x = x / x.norm(dim=-1, keepdim=True)
+        ms = self.time_steps(lambda: ops.ei_eval(gp, x), steps, 3, flush=False) / steps
+        return {'workload': 'EI screening of %d raw samples on S^%d, n_train=%d (one launch)' % (R, D - 1, n_train),
+                'ei_evals_per_s': self.world * R / (ms * 1e-3), 'ms_per_step': ms}
+
     def extra_acq_spd(self, R, T, d=8, n_train=32, noise=1e-2, steps=3):
         """BASELINE configs[3] per-GPU shard: Ackley on SPD(8), R restarts x T CG steps per rank + the record all-gather."""
         import gabotorch_b200 as g
@@ -559,13 +578,16 @@ class Bench:
             torch = self.torch
             extras.append(self.extra_acq_sphere(R=1024, T=200))
             extras.append(self.extra_acq_spd(R=512, T=200))
+            extras.append(self.extra_ei_screen())
             if self.world == 1:
                 extras.append(self.extra_spd(N_POINTS, SPD_D, BETA_SPD3, symmetric=True))
                 extras.append(self.extra_spd(8192, 3, BETA_SPD3, symmetric=False, steps=5))
                 extras.append(self.extra_spd(2048, 8, 0.22 + math.log(2.0), symmetric=False, steps=5))
                 extras.append(self.extra_sphere(256, 3, 6.5 + math.log(2.0), torch.float64, steps=20))
                 extras.append(self.extra_sphere(32768, 3, 6.5 + math.log(2.0), torch.float32, steps=5))
+                extras.append(self.extra_sphere(32768, 3, 6.5 + math.log(2.0), torch.float64, steps=5))   # the API's dtype
                 extras.append(self.extra_sphere(32768, 9, 0.6 + math.log(2.0), torch.float32, steps=5))
+                extras.append(self.extra_sphere(32768, 9, 0.6 + math.log(2.0), torch.float64, steps=5))
                 extras.append(self.extra_projection(1 << 20))
         cpu = None
         if self.rank == 0 and self.world == 1 and not args.no_cpu_baseline:

@@ -148,6 +148,32 @@ __device__ __forceinline__ void store4<double>(double* p, const float (&v)[kVec]
     }
 }
 
+// Two consecutive columns per store.  The fixed-dimension kernel gives a thread columns {2 lane, 2 lane + 1} of each
+// 64-column half of its warp's 128-column group, so that ONE warp store instruction covers a contiguous 256 B (fp32)
+// or 512 B (fp64) run.  (With 4 consecutive columns per thread the fp64 result needed two 16-byte stores per thread
+// that each touched only half of every 32-byte sector: the fp64-output Gram -- the dtype the reference API returns --
+// ran at 55 % of HBM where the fp32-output one reached 59 %.)
+template <typename OutT>
+__device__ __forceinline__ void store2(OutT* p, float v0, float v1, int valid, bool vec_ok);
+template <>
+__device__ __forceinline__ void store2<float>(float* p, float v0, float v1, int valid, bool vec_ok) {
+    if (vec_ok && valid == 2) {
+        __stcs(reinterpret_cast<float2*>(p), make_float2(v0, v1));
+    } else {
+        if (valid > 0) st_cs(p, v0);
+        if (valid > 1) st_cs(p + 1, v1);
+    }
+}
+template <>
+__device__ __forceinline__ void store2<double>(double* p, float v0, float v1, int valid, bool vec_ok) {
+    if (vec_ok && valid == 2) {
+        st_cs2(p, static_cast<double>(v0), static_cast<double>(v1));
+    } else {
+        if (valid > 0) st_cs(p, static_cast<double>(v0));
+        if (valid > 1) st_cs(p + 1, static_cast<double>(v1));
+    }
+}
+
 template <int D, typename OutT, int KIND>
 __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __restrict__ x1, int64_t n1,
                                                                const double* __restrict__ x2, int64_t n2,
@@ -191,7 +217,9 @@ __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __r
     bool bulk_cur = issue(t_begin, 0);
     int64_t jb_loaded = -1;
     double b[kVec][D];
-    int valid = 0;
+    // fp64 output (the dtype the reference API returns): two-column stores, see store2; fp32 output: one float4 store
+    constexpr bool kPairLayout = sizeof(OutT) == 8;
+    int valid = 0, valid_hi = 0;
     int64_t j_first = 0;
 
     for (int64_t t = t_begin; t < t_end; ++t) {
@@ -208,11 +236,17 @@ __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __r
 
         if (jb != jb_loaded) {
             jb_loaded = jb;
-            j_first = jb * kTileN + static_cast<int64_t>(threadIdx.x) * kVec;
-            valid = static_cast<int>(imax(0, imin(kVec, n2 - j_first)));
+            if (kPairLayout) {   // columns of this thread: j_first + {0, 1} and j_first + 64 + {0, 1}
+                j_first = jb * kTileN + static_cast<int64_t>(threadIdx.x >> 5) * 128 + 2 * (threadIdx.x & 31);
+                valid = static_cast<int>(imax(0, imin(2, n2 - j_first)));
+                valid_hi = static_cast<int>(imax(0, imin(2, n2 - (j_first + 64))));
+            } else {             // four consecutive columns: one 16-byte store per row
+                j_first = jb * kTileN + static_cast<int64_t>(threadIdx.x) * kVec;
+                valid = static_cast<int>(imax(0, imin(kVec, n2 - j_first)));
+            }
 #pragma unroll
             for (int q = 0; q < kVec; ++q) {
-                const int64_t j = imin(j_first + q, n2 - 1);
+                const int64_t j = imin(j_first + (kPairLayout ? (q >> 1) * 64 + (q & 1) : q), n2 - 1);
 #pragma unroll
                 for (int k = 0; k < D; ++k) b[q][k] = __ldg(x2 + j * D + k);
             }
@@ -240,8 +274,13 @@ __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __r
                     for (int k = 1; k < D; ++k) c[q] = fma(a[k], b[q][k], c[q]);
                 }
                 const float2 v01 = tail2<KIND>(c[0], c[1], tp), v23 = tail2<KIND>(c[2], c[3], tp);
-                const float v[kVec] = {v01.x, v01.y, v23.x, v23.y};
-                store4<OutT>(orow, v, valid, vec_ok);
+                if (kPairLayout) {
+                    store2<OutT>(orow, v01.x, v01.y, valid, vec_ok);
+                    store2<OutT>(orow + 64, v23.x, v23.y, valid_hi, vec_ok);
+                } else {
+                    const float v[kVec] = {v01.x, v01.y, v23.x, v23.y};
+                    store4<OutT>(orow, v, valid, vec_ok);
+                }
             }
         }
         bulk_cur = bulk_next;
