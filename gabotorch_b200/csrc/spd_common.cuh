@@ -1,6 +1,7 @@
 // Small-matrix device routines shared by the SPD Gram kernel, the batched manifold operations and the acquisition
 // optimiser.  Everything is templated on the matrix size d (<= 8) so that the state lives in registers.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace gabo {
@@ -215,18 +216,21 @@ __device__ __forceinline__ void jacobi_onesided_rr(T (&G)[d][d], T (&lam)[d]) {
     }
 }
 
-// The same round-robin sweep as a LOOP over the rounds (Brent-Luk style): every round rotates the FIXED column pairs
-// (0,1), (2,3), ... and then moves the columns one step along the tournament cycle (position 0 stays), so after m - 1
-// rounds every pair has met once and the columns are back in place.  The loop body is ~350 instructions instead of the
-// ~2000 of the fully unrolled sweep: the acquisition kernels, whose code no longer fitted the instruction caches (ncu:
-// stall_no_instruction 4-6 warps per issue), run out of the L0/L1.5 instruction cache again; the price is the register
-// moves of the permutation (+25 % instructions).  Odd d gets a zero dummy column (its rotations are identities).
+// Compact sweep for kernels that inline the solve into a large body (the acquisition kernels): ODD-EVEN TRANSPOSITION
+// ordering with rotate-and-interchange.  A sweep is m / 2 passes over the same two rounds,
+//     even round: (0,1) (2,3) ... (m-2,m-1)        odd round: (1,2) (3,4) ... (m-3,m-2),
+// and every rotation also EXCHANGES its two columns (free: the rotated columns are simply stored crosswise).  As in
+// odd-even transposition sort, after m rounds the column order is reversed and every pair of columns has met exactly
+// once.  The loop body is two rounds (~500 instructions, m - 1 rotations) and needs no register moves; the fully
+// unrolled round-robin sweep is ~2000 instructions and did not fit the instruction caches once inlined in the
+// acquisition kernel (ncu: stall_no_instruction 4-6 warps per issue), and a round-robin loop with an explicit column
+// permutation spent 29 % of its instructions on MOVs.  Branch-free inside a round (independent rotations overlap);
+// converged pairs get the exact identity (+ exchange).  Odd d gets a zero dummy column.
 template <int d, typename T>
 __device__ __forceinline__ void jacobi_onesided_loop(T (&G)[d][d], T (&lam)[d]) {
     using Tr = JacobiTraits<T>;
     constexpr bool kF32 = sizeof(T) == 4;
     constexpr int m = d + (d & 1);
-    constexpr int h = m / 2;
     T C[d][m], l[m];
 #pragma unroll
     for (int k = 0; k < m; ++k) {
@@ -238,75 +242,91 @@ __device__ __forceinline__ void jacobi_onesided_loop(T (&G)[d][d], T (&lam)[d]) 
         }
         l[k] = s;
     }
+    // one round over the pairs (first, first+1), (first+2, first+3), ...; returns whether this lane rotated
+    auto round = [&](auto first_tag) -> bool {
+        constexpr int first = decltype(first_tag)::value;
+        constexpr int np = (m - first) / 2;
+        T c[np > 0 ? np : 1];
+        bool need[np > 0 ? np : 1];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < np; ++j) {
+            const int p = first + 2 * j, q = p + 1;
+            T s = T(0);
+#pragma unroll
+            for (int r = 0; r < d; ++r) s = fma(C[r][p], C[r][q], s);
+            c[j] = s;
+            need[j] = s * s > Tr::tol2() * (l[p] * l[q]);
+            any = any || need[j];
+        }
+#pragma unroll
+        for (int j = 0; j < np; ++j) {
+            const int p = first + 2 * j, q = p + 1;
+            const T a = l[p], b = l[q];
+            T cs, sn, tc;
+            Tr::rotation(a, b, c[j], cs, sn, tc);
+            cs = need[j] ? cs : T(1);
+            sn = need[j] ? sn : T(0);
+            tc = need[j] ? tc : T(0);
+#pragma unroll
+            for (int r = 0; r < d; ++r) {
+                const T gp = C[r][p], gq = C[r][q];
+                C[r][q] = fma(cs, gp, -sn * gq);      // rotated column p, stored at q
+                C[r][p] = fma(sn, gp, cs * gq);       // rotated column q, stored at p
+            }
+            if (kF32) {
+                l[q] = a - tc;
+                l[p] = b + tc;
+            } else {  // the fp64 angle is approximate: exact expression for the rotated norms
+                const T c2 = cs * cs, s2 = sn * sn, x = T(2) * cs * sn * c[j];
+                l[q] = fma(c2, a, fma(s2, b, -x));
+                l[p] = fma(s2, a, fma(c2, b, x));
+            }
+        }
+        return any;
+    };
 #pragma unroll 1
     for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
         bool rotated = false;
 #pragma unroll 1
-        for (int round = 0; round < m - 1; ++round) {
-            T c[h];
-            bool need[h];
-            bool any = false;
-#pragma unroll
-            for (int j = 0; j < h; ++j) {
-                T s = T(0);
-#pragma unroll
-                for (int r = 0; r < d; ++r) s = fma(C[r][2 * j], C[r][2 * j + 1], s);
-                c[j] = s;
-                need[j] = s * s > Tr::tol2() * (l[2 * j] * l[2 * j + 1]);
-                any = any || need[j];
-            }
-            if (any) {
-                rotated = true;
-#pragma unroll
-                for (int j = 0; j < h; ++j) {
-                    const T a = l[2 * j], b = l[2 * j + 1];
-                    T cs, sn, tc;
-                    Tr::rotation(a, b, c[j], cs, sn, tc);
-                    cs = need[j] ? cs : T(1);
-                    sn = need[j] ? sn : T(0);
-                    tc = need[j] ? tc : T(0);
-#pragma unroll
-                    for (int r = 0; r < d; ++r) {
-                        const T gp = C[r][2 * j], gq = C[r][2 * j + 1];
-                        C[r][2 * j] = fma(cs, gp, -sn * gq);
-                        C[r][2 * j + 1] = fma(sn, gp, cs * gq);
-                    }
-                    if (kF32) {
-                        l[2 * j] = a - tc;
-                        l[2 * j + 1] = b + tc;
-                    } else {
-                        const T c2 = cs * cs, s2 = sn * sn, x = T(2) * cs * sn * c[j];
-                        l[2 * j] = fma(c2, a, fma(s2, b, -x));
-                        l[2 * j + 1] = fma(s2, a, fma(c2, b, x));
-                    }
-                }
-            }
-            // tournament step: 1 <- 3 <- 5 ... <- m-1 <- m-2 <- m-4 ... <- 2 <- 1   (one cycle through all but position 0)
-            if (m > 2) {
-#pragma unroll
-                for (int r = 0; r <= d; ++r) {   // r == d moves the norms
-                    auto at = [&](int k) -> T& { return r < d ? C[r < d ? r : 0][k] : l[k]; };
-                    const T t = at(1);
-#pragma unroll
-                    for (int k = 1; k + 2 <= m - 1; k += 2) at(k) = at(k + 2);          // odd positions move down
-                    at(m - 1) = at(m - 2);
-#pragma unroll
-                    for (int k = m - 2; k - 2 >= 2; k -= 2) at(k) = at(k - 2);          // even positions move up
-                    at(2) = t;
-                }
-            }
+        for (int pass = 0; pass < m / 2; ++pass) {
+            rotated = round(std::integral_constant<int, 0>{}) || rotated;
+            rotated = round(std::integral_constant<int, 1>{}) || rotated;
         }
         if (!__any_sync(__activemask(), rotated)) break;
     }
+    // the dummy column of an odd d is wherever the exchanges left it: it is the (only) zero column
 #pragma unroll
-    for (int k = 0; k < d; ++k) {
-        T s = T(0);
+    for (int k = 0; k < d; ++k) lam[k] = T(0);
+    if (d == m) {
 #pragma unroll
-        for (int r = 0; r < d; ++r) {
-            G[r][k] = C[r][k];
-            s = fma(C[r][k], C[r][k], s);
+        for (int k = 0; k < d; ++k) {
+            T s = T(0);
+#pragma unroll
+            for (int r = 0; r < d; ++r) {
+                G[r][k] = C[r][k];
+                s = fma(C[r][k], C[r][k], s);
+            }
+            lam[k] = s;
         }
-        lam[k] = s;
+    } else {
+        // after an even number of sweeps the order is the original one, after an odd number it is reversed: the dummy
+        // sits at position m-1 or 0; pick the d real columns accordingly (warp-uniform: every lane ran the same sweeps)
+        T s0 = T(0);
+#pragma unroll
+        for (int r = 0; r < d; ++r) s0 = fma(C[r][0], C[r][0], s0);
+        const bool dummy_first = (s0 == T(0));
+#pragma unroll
+        for (int k = 0; k < d; ++k) {
+            T s = T(0);
+#pragma unroll
+            for (int r = 0; r < d; ++r) {
+                const T v = dummy_first ? C[r][k + 1 < m ? k + 1 : 0] : C[r][k];
+                G[r][k] = v;
+                s = fma(v, v, s);
+            }
+            lam[k] = s;
+        }
     }
 }
 

@@ -176,12 +176,12 @@ def test_spd_rcg_speculative_line_search_is_exactly_the_sequential_one(d, monkey
     x0 = ospd.spd_sample(rng, 48, d, max_cond=100.0)
     dgp = device_gp(gp, _lib.GABO_F32)
     runs = {}
-    for width in ('1', '2'):
+    for width in ('1', '2', '4'):          # 4 exists for d <= 5 only; at d = 8 the request falls through to 2
         monkeypatch.setenv('GABO_ACQ_SPEC', width)
         runs[width] = ops.acq_rcg(dgp, x0, maxiter=15)
     monkeypatch.delenv('GABO_ACQ_SPEC')
     auto = ops.acq_rcg(dgp, x0, maxiter=15)
-    for other in (runs['2'], auto):
+    for other in (runs['2'], runs['4'], auto):
         for a, b in zip(runs['1'], other):
             assert torch.equal(a, b)
     assert int(runs['1'][2].max()) > 2
