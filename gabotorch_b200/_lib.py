@@ -55,6 +55,7 @@ SIGNATURES = {
     'gabo_acq_rcg': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, ctypes.POINTER(RcgOpts), c_ptr, c_ptr, c_ptr,
                              c_ptr]),
     'gabo_argmax_records': (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    'gabo_nested_spd_project_f64': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     'gabo_nested_projection_pack_size': (c_i64, [c_i32, c_i32]),
     'gabo_nested_projection_matrix': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     'gabo_nested_spd_project': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),

@@ -289,6 +289,52 @@ int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, fl
 }  // namespace
 }  // namespace gabo
 
+namespace gabo {
+namespace {
+// Reference-precision path of the projection for the nested kernels (kernels_nested_spd.py:122-127): fp64 in, fp64 out,
+// one thread per (matrix, output Mandel entry).  The tensor-core path above is fp32 (3xTF32, ~1e-6 relative), which is
+// right for streaming millions of raw samples but not for the affine-invariant distance of ill-conditioned projected
+// matrices (its error is amplified by their condition number); GP training sets are tens of points.
+__global__ void nested_project_f64_kernel(const double* __restrict__ x, int64_t n, int D, int d,
+                                          const double* __restrict__ w, double* __restrict__ y) {
+    const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n * dvl) return;
+    const int64_t i = e / dvl;
+    const int o = static_cast<int>(e % dvl);
+    int a, b;
+    mandel_rc_dev(d, o, a, b);
+    const double* xi = x + i * dvh;
+    // y_ab = sum_pq W_pa X_pq W_qb, X_pq read from the Mandel vector (off-diagonal entries carry a factor sqrt 2)
+    double acc = 0.0;
+    for (int p = 0; p < D; ++p) {
+        double t = 0.0;
+        for (int q = 0; q < D; ++q) {
+            const int lo = p < q ? p : q, hi = p < q ? q : p;
+            const double xv = xi[mandel_pos(D, lo, hi)];
+            t = fma((p == q) ? xv : xv * 0.70710678118654752440, w[q * d + b], t);
+        }
+        acc = fma(w[p * d + a], t, acc);
+    }
+    y[e] = (a == b) ? acc : acc * 1.41421356237309504880;
+}
+}  // namespace
+}  // namespace gabo
+
+extern "C" int gabo_nested_spd_project_f64(const double* x_mandel, int64_t n, int D, int d, const double* w,
+                                           double* y_mandel, void* stream) {
+    using namespace gabo;
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_nested_spd_project_f64: negative size");
+    if (n == 0) return GABO_OK;
+    GABO_REQUIRE(x_mandel && w && y_mandel, GABO_E_ARG, "gabo_nested_spd_project_f64: null pointer");
+    GABO_REQUIRE(D >= 1 && d >= 1 && d <= D, GABO_E_ARG, "gabo_nested_spd_project_f64: need 1 <= d <= D, got D=%d d=%d",
+                 D, d);
+    const int64_t total = n * (static_cast<int64_t>(d) * (d + 1) / 2);
+    nested_project_f64_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_mandel, n, D, d, w, y_mandel);
+    return check_launch("nested_project_f64_kernel");
+}
+
 extern "C" int64_t gabo_nested_projection_pack_size(int D, int d) {
     if (D < 1 || d < 1 || d > D || d > GABO_MAX_SPD_DIM) return -1;
     return static_cast<int64_t>(gabo::ksteps_for(D * (D + 1) / 2)) * 32 * gabo::ntiles_for(d * (d + 1) / 2) * 4;

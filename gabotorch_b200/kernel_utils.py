@@ -242,3 +242,101 @@ class SpdLogEuclideanGaussianKernel(SpdFrobeniusGaussianKernel):
 
     def _matrices(self, x):
         return ops.spd_logm(ops.mandel_unpack(x))
+
+
+def _grassmann_rand(D, d):
+    """pymanopt ``Grassmann(D, d).rand()``: the Q factor of a Gaussian matrix (kernels_nested_spd.py:75-78)."""
+    q, _ = torch.linalg.qr(torch.randn(D, d, dtype=torch.float64))
+    return q
+
+
+class _GrassmannStub:
+    """What the reference stores as ``raw_projection_matrix_manifold`` (pymanopt ``Grassmann``): ``rand`` and the sizes."""
+
+    def __init__(self, n, p):
+        self._n, self._p = n, p
+
+    def rand(self):
+        return _grassmann_rand(self._n, self._p).numpy()
+
+
+class _NestedSpdMixin:
+    """Projection parameter shared by the nested SPD kernels (kernels_nested_spd.py:74-100, :176-191).
+
+    Deviation: ``raw_projection_matrix`` is created with ``requires_grad=False`` -- in the reference it is fitted on the
+    Grassmann manifold by ``fit_gpytorch_manifold`` (GP fitting is outside this package's scope); asking for
+    its gradient raises instead of silently returning none."""
+
+    def _init_projection(self, dim, latent_dim):
+        self.dim = dim
+        self.latent_dim = latent_dim
+        self.raw_projection_matrix_manifold = _GrassmannStub(dim, latent_dim)
+        w = _grassmann_rand(dim, latent_dim).to(torch.float32).repeat(*self.batch_shape, 1, 1)
+        self.register_parameter(name='raw_projection_matrix', parameter=torch.nn.Parameter(w, requires_grad=False))
+
+    @property
+    def projection_matrix(self):
+        return self.raw_projection_matrix
+
+    @projection_matrix.setter
+    def projection_matrix(self, value):
+        self._set_projection_matrix(value)
+
+    def _set_projection_matrix(self, value):
+        self.initialize(raw_projection_matrix=value)
+
+    def _project(self, x):
+        """Mandel vectors of SPD(dim) -> Mandel vectors of SPD(latent_dim): G3 -> P1 -> G3 of SURVEY section 8."""
+        w = self.raw_projection_matrix
+        if torch.is_grad_enabled() and w.requires_grad:
+            raise NotImplementedError('gradients with respect to the projection matrix are not provided '
+                                      '(fit_gpytorch_manifold is outside the scope of gabotorch_b200)')
+        if w.dim() != 2:
+            raise NotImplementedError('batched projection matrices (batch_shape != []) are not supported')
+        return ops.nested_spd_project_f64(x, w.detach().double())
+
+
+class NestedSpdAffineInvariantGaussianKernel(_NestedSpdMixin, _BetaKernel):
+    """exp(-beta d_AI(W^T X1 W, W^T X2 W)^2) for Mandel-vectorised SPD(dim) inputs (kernels_nested_spd.py:19-136)."""
+
+    def __init__(self, dim, latent_dim, beta_min, beta_prior=None, compute='f32', **kwargs):
+        _BetaKernel.__init__(self, beta_min, beta_prior=beta_prior, **kwargs)
+        self.compute = compute
+        self._init_projection(dim, latent_dim)
+
+    def forward(self, x1, x2, diagonal_distance=False, **params):
+        _reject_input_grad(x1, x2)
+        if diagonal_distance is True:
+            return _spd_diag_ones(x2)
+        beta = self._beta_scalar()
+        comp = _lib.GABO_F64 if self.compute == 'f64' else _lib.GABO_F32
+        y1 = self._project(x1)
+        y2 = y1 if x2 is x1 else self._project(x2)
+        if _needs_param_grad(self.raw_beta):
+            out = _param_gram(lambda: ops.spd_ai_gram(y1, y2, kind=_lib.KIND_DIST, compute=comp), beta, 2)
+        else:
+            out = ops.spd_ai_gram(y1, y2, float(beta.detach()), _lib.KIND_GAUSS, compute=comp)
+        return _finish(out, x1)
+
+
+class NestedSpdLogEuclideanGaussianKernel(_NestedSpdMixin, Kernel):
+    """exp(-||logm(W^T X1 W) - logm(W^T X2 W)||_F^2 / lengthscale^2) (kernels_nested_spd.py:139-246)."""
+    has_lengthscale = True
+
+    def __init__(self, dim, latent_dim, **kwargs):
+        Kernel.__init__(self, has_lengthscale=True, ard_num_dims=None, **kwargs)
+        self._init_projection(dim, latent_dim)
+
+    def forward(self, x1, x2, diagonal_distance=False, **params):
+        _reject_input_grad(x1, x2)
+        if diagonal_distance is True:
+            return _spd_diag_ones(x2)
+        ls = self.lengthscale.reshape(()).double()
+        inv = 1.0 / (ls * ls)
+        m1 = ops.spd_logm(ops.mandel_unpack(self._project(x1)))
+        m2 = m1 if x2 is x1 else ops.spd_logm(ops.mandel_unpack(self._project(x2)))
+        if _needs_param_grad(self.raw_lengthscale):
+            out = _param_gram(lambda: ops.frobenius_gram(m1, m2, kind=_lib.KIND_DIST), inv, 2)
+        else:
+            out = ops.frobenius_gram(m1, m2, float(inv.detach()), _lib.KIND_GAUSS)
+        return _finish(out, x1)

@@ -387,6 +387,21 @@ def nested_projection_matrix(w):
     return p
 
 
+def nested_spd_project_f64(x_mandel, w):
+    """Mandel(W^T X W) in fp64 for (..., D(D+1)/2) Mandel vectors and a (D, d) projection matrix."""
+    lib = _lib.load()
+    x = to_dev64(x_mandel)
+    w = to_dev64(w).to(x.device)
+    D, d = int(w.shape[0]), int(w.shape[1])
+    if mandel_dim(x.shape[-1]) != D:
+        raise ValueError('Mandel length %d does not match a %d x %d matrix' % (x.shape[-1], D, D))
+    flat = x.reshape(-1, x.shape[-1])
+    y = torch.empty(flat.shape[0], d * (d + 1) // 2, dtype=torch.float64, device=x.device)
+    _lib.check(lib.gabo_nested_spd_project_f64(_p(flat), flat.shape[0], D, d, _p(w), _p(y), _lib.stream_ptr()),
+               'gabo_nested_spd_project_f64')
+    return y.reshape(tuple(x.shape[:-1]) + (y.shape[-1],))
+
+
 def nested_spd_project(x_mandel, D, d, p_padded):
     """y_mandel (n, dvl) = x_mandel (n, dvh) P^T on the tensor cores; fp32 in / out."""
     lib = _lib.load()

@@ -189,6 +189,10 @@ int gabo_argmax_records(const double* values, const int64_t* gidx, int64_t n, in
  * gabo_nested_projection_matrix writes P, split into tf32 hi/lo parts and arranged per MMA lane, into `p_pack`
  * (gabo_nested_projection_pack_size(D, d) floats, 16-byte aligned, caller-owned); gabo_nested_spd_project consumes it.
  * ------------------------------------------------------------------------------------------------------------------ */
+/* Reference-precision (fp64) form for the nested kernels (kernel_utils/kernels_nested_spd.py:122-127):
+ * y_mandel[n x d(d+1)/2] = Mandel(W^T X W), x_mandel: n x D(D+1)/2, w: D x d row-major, all fp64. */
+int gabo_nested_spd_project_f64(const double* x_mandel, int64_t n, int D, int d, const double* w, double* y_mandel,
+                                void* stream);
 int64_t gabo_nested_projection_pack_size(int D, int d);
 int gabo_nested_projection_matrix(const double* w, int D, int d, float* p_pack, void* stream);
 int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, int d, const float* p_pack, float* y_mandel,

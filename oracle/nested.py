@@ -52,6 +52,15 @@ def nested_spd_affine_invariant_gaussian_kernel(x1, x2, w, beta):
     return torch.exp(-torch.mul(d, d).mul(torch.as_tensor(beta, dtype=torch.float64)))
 
 
+def nested_spd_log_euclidean_gaussian_kernel(x1, x2, w, lengthscale):
+    """kernels_nested_spd.py:209-246: Mandel unpack, project, logm per matrix, Frobenius distance, exp(-d^2 / l^2)."""
+    m1 = _spd.logm(projection_from_spd_to_nested_spd(_spd.vector_to_symmetric_matrix_mandel(x1), w))
+    m2 = _spd.logm(projection_from_spd_to_nested_spd(_spd.vector_to_symmetric_matrix_mandel(x2), w))
+    d = _spd.frobenius_distance(m1, m2)
+    ls = torch.as_tensor(lengthscale, dtype=torch.float64)
+    return torch.exp(-torch.mul(d, d).div(ls * ls))
+
+
 def grassmann_rand(rng, D, d):
     """pymanopt Grassmann.rand: Q of QR(randn(D,d))."""
     q, _ = np.linalg.qr(rng.standard_normal((D, d)))

@@ -50,3 +50,56 @@ def test_projection_linearity_and_spd_preservation():
     assert np.linalg.eigvalsh(y.numpy()).min() > 0
     np.testing.assert_allclose(y.numpy(), onest.projection_from_spd_to_nested_spd(x, proj_matrix).numpy(), rtol=0,
                                atol=1e-5 * np.abs(x).max())
+
+
+@pytest.mark.parametrize('name', ['proj_20_5', 'proj_5_2'])
+def test_projection_f64_golden(golden, name):
+    # reference-precision path used by the nested kernels: golden vectors generated from the reference's own bmm code
+    ym = ops.nested_spd_project_f64(torch.from_numpy(golden[name + '_xvec']), torch.from_numpy(golden[name + '_w']))
+    np.testing.assert_allclose(ym.cpu().numpy(), golden[name + '_yvec'], rtol=1e-12,
+                               atol=1e-13 * np.abs(golden[name + '_yvec']).max())
+
+
+@pytest.mark.parametrize('D,d,n1,n2', [(5, 2, 35, 20), (20, 5, 40, 33), (8, 3, 17, 17)])
+def test_nested_spd_kernels_vs_oracle(D, d, n1, n2):
+    # P2 of SURVEY section 8: kernels_nested_spd.py:104-136 (affine-invariant) and :191-246 (log-Euclidean); the oracle
+    # composes the pieces pinned on the reference (Mandel unpack, W^T X W, AI distance / logm + Frobenius distance)
+    import gabotorch_b200 as g
+    from oracle import spd as ospd
+    rng = np.random.default_rng(D * 10 + d)
+    x1 = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(ospd.spd_sample(rng, n1, D, max_cond=100.0)))
+    x2 = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(ospd.spd_sample(rng, n2, D, max_cond=100.0)))
+    w = onest.grassmann_rand(rng, D, d)
+    k = g.NestedSpdAffineInvariantGaussianKernel(D, d, beta_min=0.25)
+    k.projection_matrix = torch.from_numpy(w)
+    assert k.raw_projection_matrix.dtype == torch.float32         # the reference's parameter dtype
+    w32 = k.raw_projection_matrix.detach().double().numpy()        # what both sides project with
+    beta = float(k.beta.detach())
+    with torch.no_grad():
+        got = k.forward(x1, x2)
+        sym = k.forward(x1, x1)
+    assert got.dtype == torch.float64 and not got.is_cuda and tuple(got.shape) == (n1, n2)
+    ref = onest.nested_spd_affine_invariant_gaussian_kernel(x1, x2, torch.from_numpy(w32), beta).numpy()
+    m = ref >= 1e-6
+    d_ref = np.sqrt(-np.log(np.maximum(ref, 1e-300)) / beta)
+    tol = 1e-5 * np.maximum(1.0, 2 * beta * d_ref ** 2)            # bound implied by the distance tolerance (fp32 Jacobi)
+    assert np.all(np.abs(got.numpy() - ref)[m] <= tol[m] * ref[m])
+    np.testing.assert_allclose(sym.numpy(), onest.nested_spd_affine_invariant_gaussian_kernel(
+        x1, x1, torch.from_numpy(w32), beta).numpy(), rtol=0, atol=2e-5)
+    assert torch.all(k.forward(x1, x1, diagonal_distance=True) == 1) and k.forward(x1, x1, diagonal_distance=True).shape == (n1, 1)
+
+    le = g.NestedSpdLogEuclideanGaussianKernel(D, d)
+    le.projection_matrix = torch.from_numpy(w)
+    le.lengthscale = 1.7
+    ls = float(le.lengthscale.detach())
+    with torch.no_grad():
+        got_le = le.forward(x1, x2)
+    ref_le = onest.nested_spd_log_euclidean_gaussian_kernel(x1, x2, torch.from_numpy(w32), ls).numpy()
+    np.testing.assert_allclose(got_le.numpy(), ref_le, rtol=1e-7, atol=1e-12)
+    # beta / lengthscale stay differentiable (GP hyper-parameter fitting), the projection matrix does not
+    out = k.forward(x1, x2)
+    out.sum().backward()
+    assert k.raw_beta.grad is not None and torch.isfinite(k.raw_beta.grad).all()
+    k.raw_projection_matrix.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        k.forward(x1, x2)
