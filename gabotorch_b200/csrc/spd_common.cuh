@@ -493,6 +493,65 @@ __device__ __forceinline__ void tri_product(AccA A, AccL L, T (&G)[d][d]) {
     }
 }
 
+// Row-cyclic one-sided Jacobi (fp32) with the ROWS of G packed two per register pair: inner products and column
+// updates run on the packed fp32x2 pipe (FFMA2 / FMUL2), halving their issue slots.  For the single-problem-per-thread
+// sizes (d >= 6, where two problems per thread would not fit the register file) the Gram kernel is issue-bound with
+// as many FMULs as FFMAs in the rotation updates (ncu: 63 % issue-active, FMA pipe 49 %).  An odd d gets a zero row.
+template <int d>
+__device__ __forceinline__ void jacobi_onesided_cyclic_rows2(float (&G)[d][d], float (&lam)[d]) {
+    using Tr = JacobiTraits<float>;
+    constexpr int R2 = (d + 1) / 2;
+    float2 H[R2][d];
+#pragma unroll
+    for (int r = 0; r < R2; ++r)
+#pragma unroll
+        for (int k = 0; k < d; ++k) H[r][k] = make_float2(G[2 * r][k], (2 * r + 1 < d) ? G[(2 * r + 1 < d) ? 2 * r + 1 : 0][k] : 0.0f);
+    auto dot2 = [&](int p, int q) {
+        float2 s = mul2(H[0][p], H[0][q]);
+#pragma unroll
+        for (int r = 1; r < R2; ++r) s = fma2(H[r][p], H[r][q], s);
+        return s.x + s.y;
+    };
+#pragma unroll
+    for (int k = 0; k < d; ++k) lam[k] = dot2(k, k);
+#pragma unroll 1
+    for (int sweep = 0; sweep < Tr::kMaxSweeps; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int p = 0; p < d - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < d; ++q) {
+                const float c = dot2(p, q);
+                const float a = lam[p], b = lam[q];
+                if (c * c > Tr::tol2() * (a * b)) {
+                    rotated = true;
+                    float cs, sn, tc;
+                    Tr::rotation(a, b, c, cs, sn, tc);
+                    const float2 cs2 = splat2(cs), sn2 = splat2(sn), nsn2 = splat2(-sn);
+#pragma unroll
+                    for (int r = 0; r < R2; ++r) {
+                        const float2 gp = H[r][p], gq = H[r][q];
+                        H[r][p] = fma2(cs2, gp, mul2(nsn2, gq));
+                        H[r][q] = fma2(sn2, gp, mul2(cs2, gq));
+                    }
+                    lam[p] = a - tc;
+                    lam[q] = b + tc;
+                }
+            }
+        }
+        if (!__any_sync(__activemask(), rotated)) break;
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k) lam[k] = dot2(k, k);
+#pragma unroll
+    for (int r = 0; r < R2; ++r)
+#pragma unroll
+        for (int k = 0; k < d; ++k) {
+            G[2 * r][k] = H[r][k].x;
+            if (2 * r + 1 < d) G[(2 * r + 1 < d) ? 2 * r + 1 : 0][k] = H[r][k].y;
+        }
+}
+
 // d <= 3 has at most one real pair per round: the row-cyclic form (with its per-rotation skip) is the cheaper one there.
 template <int d, typename T>
 __device__ __forceinline__ void jacobi_onesided(T (&G)[d][d], T (&lam)[d]) {

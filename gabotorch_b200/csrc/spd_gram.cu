@@ -273,7 +273,11 @@ __global__ void __launch_bounds__(kThreads)
                 T lam[d];
                 // throughput-bound here: the row-cyclic order with its per-rotation skip does less work than the
                 // branch-free round-robin form (which wins where latency binds, in the acquisition kernel)
-                jacobi_onesided_cyclic<d, T>(G, lam);
+                if constexpr (sizeof(T) == 4 && d >= 8) {
+                    jacobi_onesided_cyclic_rows2<d>(G, lam);     // fp32: rows packed on the fp32x2 pipe
+                } else {
+                    jacobi_onesided_cyclic<d, T>(G, lam);
+                }
                 store(i0 + i, finish<KIND, T>(ai_distance_from_eigs<d, T>(lam), kp));
             }
         }
