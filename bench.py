@@ -426,7 +426,7 @@ class Bench:
                 'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': self.hbm_peak, 'unit': 'GB/s',
                              'frac': gbs / self.hbm_peak, 'algorithmic_bytes_per_launch': nbytes}}
 
-    def extra_acq_sphere(self, R, T, D=6, n_train=32, noise=1e-2, steps=5):
+    def extra_acq_sphere(self, R, T, D=6, n_train=32, noise=1e-2, steps=5, forced=True):
         """BASELINE configs[2]: Ackley on S^5, R restarts x T CG steps per rank, then ONE all-gather of the best records."""
         import gabotorch_b200 as g
         from gabotorch_b200 import manifold_optimization as mo
@@ -447,8 +447,10 @@ class Bench:
         res = {}
 
         def step():
-            # maxiter = T + 1 with the stopping tolerances disabled: every restart runs exactly T CG iterations
-            cand, val, iters, _ = ops.acq_rcg(gp, x0, maxiter=T + 1, mingradnorm=0.0, minstepsize=-1.0)
+            if forced:   # maxiter = T + 1 with the stopping tolerances disabled: every restart runs exactly T iterations
+                cand, val, iters, _ = ops.acq_rcg(gp, x0, maxiter=T + 1, mingradnorm=0.0, minstepsize=-1.0)
+            else:        # pymanopt's defaults (mingradnorm 1e-6, minstepsize 1e-10): restarts stop when converged
+                cand, val, iters, _ = ops.acq_rcg(gp, x0, maxiter=T)
             slot, best = ops.argmax_records(val, gidx)
             if self.world > 1:
                 s = slot                                                   # device-side gather of the winner
@@ -460,6 +462,11 @@ class Bench:
             res['iters'] = iters
         ms = self.time_steps(step, steps, 3, flush=False) / steps
         iters = res['iters'].double().mean().item()
+        if not forced:
+            return {'workload': 'acq RCG on EI, S^%d, %d restarts/GPU, ConjugateGradient(maxiter=%d) with pymanopt default '
+                                'stopping rules, n_train=%d, noise=%g' % (D - 1, R, T, n_train, noise),
+                    'solves_per_s': self.world * R / (ms * 1e-3), 'executed_iterations_per_s': self.world * R * iters / (ms * 1e-3),
+                    'ms_per_step': ms, 'mean_iters': iters}
         return {'workload': 'acq RCG on EI, S^%d, %d restarts/GPU x %d CG steps, n_train=%d, noise=%g'
                             % (D - 1, R, T, n_train, noise),
                 'candidates_per_s': self.world * R * T / (ms * 1e-3), 'ms_per_step': ms, 'mean_iters': iters,
@@ -577,6 +584,7 @@ class Bench:
         if not args.no_extras:
             torch = self.torch
             extras.append(self.extra_acq_sphere(R=1024, T=200))
+            extras.append(self.extra_acq_sphere(R=1024, T=200, forced=False))
             extras.append(self.extra_acq_spd(R=512, T=200))
             extras.append(self.extra_ei_screen())
             if self.world == 1:
@@ -647,7 +655,7 @@ def main():
     ap.add_argument('--acq-steps', type=int, default=200)
     ap.add_argument('--acq-dim', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-rows', type=int, default=256, help='rows of the N=2048 Gram in the cpu_baseline sample')
+    ap.add_argument('--cpu-rows', type=int, default=640, help='rows of the N=2048 Gram in the cpu_baseline sample')
     ap.add_argument('--ref-rows', type=int, default=16, help='rows per step of the reference arm')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
