@@ -45,6 +45,7 @@ SIGNATURES = {
     'gabo_spd_factor2': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'gabo_spd_ai_gram': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_f64, c_i32, c_i32, c_i32, c_ptr, c_i32, c_i64,
                                  c_ptr]),
+    'gabo_spd_ai_gram_backward': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     'gabo_frobenius_gram': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_f64, c_i32, c_ptr, c_i32, c_i64, c_ptr]),
     'gabo_spd_logm': (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_sphere_op': (c_i32, [c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),

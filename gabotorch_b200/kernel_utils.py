@@ -9,9 +9,9 @@ kernels take ``diag=`` while the SPD kernels take ``diagonal_distance=`` (kernel
 The arithmetic is one fused CUDA launch per Gram matrix (``gabo_sphere_gram`` / ``gabo_spd_factor`` +
 ``gabo_spd_ai_gram``, include/gabo_b200.h); there is no CPU implementation behind these classes.  Gradients: the Gram
 path is differentiable with respect to the kernel parameter (``raw_beta`` / ``raw_lengthscale``), which is what GP
-hyper-parameter fitting needs.  The sphere kernels also back-propagate to their inputs (``_SphereDistance``); for the
-SPD kernels the input gradient is provided in closed form by the acquisition kernels (``manifold_optimization``),
-not through autograd.
+hyper-parameter fitting needs.  The sphere kernels (``_SphereDistance``) and the SPD
+affine-invariant Gaussian kernel (``_SpdAiDistance2``) also back-propagate to their inputs; the batched acquisition
+optimiser does not go through autograd (closed-form Riemannian gradient in its kernels).
 """
 import math
 
@@ -120,6 +120,37 @@ def _wants_input_grad(*xs):
     return torch.is_grad_enabled() and any(torch.is_tensor(x) and x.requires_grad for x in xs)
 
 
+class _SpdAiDistance2(torch.autograd.Function):
+    """d_AI(X1_i, X2_j)^2 for Mandel-vectorised inputs, differentiable with respect to both inputs.  Forward: the fused
+    Gram kernel; backward: ``gabo_spd_ai_gram_backward`` (weighted sums of whitened log maps, one warp per point) and a
+    Mandel pack.  The reference reaches the same gradient through torch.autograd over cholesky / inverse / bmm /
+    symeig(eigenvectors=True) (spd_utils_torch.py:87-120)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, compute):
+        a, b = ops.to_dev64(x1), ops.to_dev64(x2)
+        d = ops.mandel_dim(a.shape[-1])
+        flags = torch.zeros(1, dtype=torch.int32, device=a.device)
+        f1, f2 = ops.spd_factor_pair(a, b, d, True, flags)
+        dist = ops.spd_ai_gram_from_factors(f1, f2, d, kind=_lib.KIND_DIST, compute=compute)
+        ops.check_spd_flags(flags)
+        ctx.save_for_backward(f1, f2)
+        ctx.meta = (d, compute, x1.device, x2.device, x1.dtype, x2.dtype)
+        return dist * dist
+
+    @staticmethod
+    def backward(ctx, g):
+        f1, f2 = ctx.saved_tensors
+        d, compute, dev1, dev2, t1, t2 = ctx.meta
+        g = ops.to_dev64(g)
+        g1 = g2 = None
+        if ctx.needs_input_grad[0]:
+            g1 = ops.mandel_pack(ops.spd_ai_gram_backward(f1, f2, d, g, False, compute)).to(device=dev1, dtype=t1)
+        if ctx.needs_input_grad[1]:
+            g2 = ops.mandel_pack(ops.spd_ai_gram_backward(f2, f1, d, g, True, compute)).to(device=dev2, dtype=t2)
+        return g1, g2, None
+
+
 def _param_gram(dist_fn, param, power):
     """exp(-param * d^power) with autograd to ``param``: distances from the fused kernel, the exp in torch on-device."""
     d = dist_fn()
@@ -179,11 +210,15 @@ class SpdAffineInvariantGaussianKernel(_BetaKernel):
         return _lib.GABO_F64 if self.compute == 'f64' else _lib.GABO_F32
 
     def forward(self, x1, x2, diagonal_distance=False, **params):
-        _reject_input_grad(x1, x2)
         if diagonal_distance is True:
             return _spd_diag_ones(x2)
         beta = self._beta_scalar()
-        if _needs_param_grad(self.raw_beta):
+        if _wants_input_grad(x1, x2):      # autograd callers: exp(-beta d^2) on the differentiable squared distance
+            if x1.dim() != 2 or x2.dim() != 2:
+                raise NotImplementedError('input gradients are provided for (N, dv) Mandel inputs')
+            d2 = _SpdAiDistance2.apply(x1, x2, self._compute())
+            out = torch.exp(-d2 * beta.double().to(d2.device).reshape(()))
+        elif _needs_param_grad(self.raw_beta):
             out = _param_gram(lambda: ops.spd_ai_gram(x1, x2, kind=_lib.KIND_DIST, compute=self._compute()), beta, 2)
         else:
             # host inputs: the per-pair kernel stores straight into a pinned host tensor (the PCIe transfer of the

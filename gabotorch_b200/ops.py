@@ -216,6 +216,17 @@ def spd_ai_gram(x1, x2, param=0.0, kind=_lib.KIND_GAUSS, is_mandel=True, compute
     return out.reshape(lead + (n1, n2))
 
 
+def spd_ai_gram_backward(fac1, fac2, d, w, transpose_w=False, compute=_lib.GABO_F32):
+    """sum_j w_ij grad_{X1_i} d_AI^2(X1_i, X2_j) as (n1, d, d) fp64 matrices (gabo_spd_ai_gram_backward)."""
+    lib = _lib.load()
+    w = to_dev64(w)
+    n1, n2 = fac1.shape[0], fac2.shape[0]
+    out = torch.empty(n1, d, d, dtype=torch.float64, device=fac1.device)
+    _lib.check(lib.gabo_spd_ai_gram_backward(_p(fac1), n1, _p(fac2), n2, d, _p(w), w.stride(0), 1 if transpose_w else 0,
+                                             compute, _p(out), _lib.stream_ptr()), 'gabo_spd_ai_gram_backward')
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Frobenius / log-Euclidean
 # ----------------------------------------------------------------------------------------------------------------

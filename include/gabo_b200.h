@@ -93,6 +93,15 @@ int gabo_spd_factor2(const double* x1, int64_t n1, const double* x2, int64_t n2,
 int gabo_spd_ai_gram(const double* fac1, int64_t n1, const double* fac2, int64_t n2, int d, double param, int kind,
                      int compute, int symmetric, void* out, int out_dtype, int64_t ld_out, void* stream);
 
+/* Input gradient of the affine-invariant Gram (what the reference gets from torch.autograd through
+ * affine_invariant_distance_torch, spd_utils_torch.py:53-120).  w: upstream weights dLoss/d(d_ij^2), n1 x n2 with row
+ * stride ld_w (transpose_w != 0: w is stored n2 x n1 and read transposed).  out: n1 x d x d fp64,
+ *   out_i = sum_j w_ij grad_{X1_i} d^2(X1_i, X2_j) = -2 A_i^T (sum_j w_ij logm(A_i X2_j A_i^T)) A_i;
+ * its Mandel vector (gabo_mandel_pack) is the gradient with respect to the Mandel input.  The gradient with respect
+ * to the second operand is the same call with the operands swapped and transpose_w = 1. */
+int gabo_spd_ai_gram_backward(const double* fac1, int64_t n1, const double* fac2, int64_t n2, int d, const double* w,
+                              int64_t ld_w, int transpose_w, int compute, double* out, void* stream);
+
 /* Frobenius / log-Euclidean Gram (spd_utils_torch.py:124-156, kernels_spd.py:230-241, 283-313):
  *   out[i,j] = f(|| M1_i - M2_j + 1e-15 ||_F), m: n x d x d fp64 (apply gabo_spd_logm first for log-Euclidean);
  *   kind GAUSS uses exp(-param d^2) with param = 1/lengthscale^2. */

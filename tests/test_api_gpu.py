@@ -73,8 +73,8 @@ def test_spd_kernel_classes(golden):
         le.lengthscale = 1.3
         np.testing.assert_allclose(le.forward(v, v).numpy(),
                                    ospd.spd_log_euclidean_gaussian_kernel(v, v, ls).numpy(), rtol=1e-8, atol=1e-12)
-    with pytest.raises(NotImplementedError):
-        k.forward(v.clone().requires_grad_(True), v)
+    with pytest.raises(NotImplementedError):                       # no input gradients for the Laplace / Frobenius kernels
+        lap.forward(v.clone().requires_grad_(True), v)
 
 
 def test_riemannian_utils_functions(golden):
@@ -183,3 +183,31 @@ def test_sphere_kernels_backpropagate_to_their_inputs(kernel):
     scale = float(r1.grad.abs().max())
     np.testing.assert_allclose(x1.grad.numpy(), r1.grad.numpy(), rtol=0, atol=2e-5 * scale)
     np.testing.assert_allclose(x2.grad.numpy(), r2.grad.numpy(), rtol=0, atol=2e-5 * scale)
+
+
+# f64: limited by the forward distance, whose eigenvalues pass through float32 like the reference's (spd_utils_torch.py:108)
+@pytest.mark.parametrize('d,compute,tol', [(3, 'f64', 5e-6), (3, 'f32', 2e-4), (5, 'f64', 5e-6), (8, 'f32', 5e-4)])
+def test_spd_kernel_backpropagates_to_its_inputs(d, compute, tol):
+    # the reference differentiates cholesky / inverse / bmm / symeig with torch.autograd (spd_utils_torch.py:87-120);
+    # here: exact-fp64 restatement of the same function under autograd vs the fused forward + log-map backward kernel
+    rng = np.random.default_rng(40 + d)
+    n1, n2 = 19, 27
+    a = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(ospd.spd_sample(rng, n1, d, max_cond=50.0)))
+    b = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(ospd.spd_sample(rng, n2, d, max_cond=50.0)))
+    wts = torch.from_numpy(rng.standard_normal((n1, n2)))
+    k = g.SpdAffineInvariantGaussianKernel(beta_min=0.3, compute=compute)
+    beta = float(k.beta.detach())
+    x1 = a.clone().requires_grad_(True)
+    x2 = b.clone().requires_grad_(True)
+    out = k.forward(x1, x2)
+    (out * wts).sum().backward()
+    r1 = a.clone().requires_grad_(True)
+    r2 = b.clone().requires_grad_(True)
+    dist = ospd.affine_invariant_distance(ospd.vector_to_symmetric_matrix_mandel(r1),
+                                          ospd.vector_to_symmetric_matrix_mandel(r2), exact=True)
+    ref = torch.exp(-dist * dist * beta)
+    (ref * wts).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=max(tol, 1e-5), atol=1e-9)
+    for got, want in ((x1.grad, r1.grad), (x2.grad, r2.grad)):
+        scale = float(want.abs().max())
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=tol * scale)
