@@ -7,7 +7,7 @@ torch.distributed); the arithmetic runs in hand-written CUDA kernels reached thr
 needs the library raises ``GaboError`` when it has not been built or no CUDA device is visible.
 
 Module map (reference module -> here):
-    BoManifolds/kernel_utils/kernels_{sphere,spd,nested_spd}.py -> gabotorch_b200.kernel_utils
+    BoManifolds/kernel_utils/kernels_{sphere,spd,nested_spd,nested_sphere}.py -> gabotorch_b200.kernel_utils
     BoManifolds/Riemannian_utils/{sphere,spd}_utils_torch.py   -> gabotorch_b200.riemannian_utils
     BoManifolds/manifold_optimization/manifold_optimize.py     -> gabotorch_b200.manifold_optimization
     BoManifolds/nested_mappings/nested_spd_utils.py            -> gabotorch_b200.nested_mappings
@@ -19,7 +19,7 @@ from ._lib import GaboError  # noqa: F401
 from .kernel_utils import (SphereGaussianKernel, SphereLaplaceKernel, SpdAffineInvariantGaussianKernel,  # noqa: F401
                            SpdAffineInvariantLaplaceKernel, SpdFrobeniusGaussianKernel,
                            SpdLogEuclideanGaussianKernel, NestedSpdAffineInvariantGaussianKernel,
-                           NestedSpdLogEuclideanGaussianKernel)
+                           NestedSpdLogEuclideanGaussianKernel, NestedSphereGaussianKernel)
 from ._compat import ScaleKernel  # noqa: F401
 from .manifolds import Sphere, PositiveDefinite  # noqa: F401
 from .manifold_optimization import (ConjugateGradient, ExpectedImprovement, ManifoldGP,  # noqa: F401

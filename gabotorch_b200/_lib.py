@@ -50,6 +50,7 @@ SIGNATURES = {
     'gabo_spd_logm': (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_sphere_op': (c_i32, [c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_sphere_dist': (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
+    'gabo_nested_sphere_project': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'gabo_spd_op': (c_i32, [c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_spd_scalar': (c_i32, [c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_ei_eval': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),

@@ -365,3 +365,79 @@ extern "C" int gabo_spd_scalar(int what, const double* x, const double* b, const
     }
     return check_launch("spd_scalar_kernel");
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Nested-sphere projection chain of HD-GaBO on spheres: S^{D-1} -> S^{D-2} -> ... -> S^{dl-1}.
+// Replaces projection_from_sphere_to_subsphere (BoManifolds/nested_mappings/nested_spheres_utils.py:120-147: per level
+// a rotation matrix from rotation_from_sphere_points_torch, sphere_utils_torch.py:58-93, two dense matrix products,
+// a projection onto the nested sphere and the identification with the next subsphere, :13-118).
+// One thread per point, every level in registers/local memory.  The rotation R that moves the level's axis v to the
+// north pole e is never formed: with c = <v, e>, s = sqrt(1 - c^2) and u = (v - c e) / |v - c e|,
+//     R x = x + (s a + (c - 1) b) e + ((c - 1) a - s b) u,      a = <u, x>,  b = <e, x> = x_k,
+// which is O(k) per point instead of O(k^2).  R^T is only used by the reference to go back to the nested sphere and
+// forth again (R R^T = I), so the subsphere coordinates are the first k-1 rotated ones.
+// ---------------------------------------------------------------------------------------------------------------
+namespace gabo {
+namespace {
+
+constexpr int kMaxNestedDim = 64;
+
+__global__ void nested_sphere_project_kernel(const double* __restrict__ x, int64_t n, int D, int dl,
+                                             const double* __restrict__ axes, const double* __restrict__ dists,
+                                             double* __restrict__ y) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[kMaxNestedDim];
+    for (int k = 0; k < D; ++k) p[k] = x[i * D + k];
+    const double* v = axes;
+    for (int k = D, lvl = 0; k > dl; --k, ++lvl) {
+        // rotation parameters of this level (identical for every thread; O(k))
+        double c = fmin(fmax(v[k - 1], -1.0 + 1e-15), 1.0 - 1e-15);      // <v, e>, sphere_utils_torch.py:80-83
+        double un = 0.0;
+        for (int q = 0; q < k; ++q) {
+            const double t = v[q] - ((q == k - 1) ? c : 0.0);
+            un = fma(t, t, un);
+        }
+        const double uinv = 1.0 / sqrt(un);
+        const double s = sin(acos(c));
+        double a = 0.0;
+        for (int q = 0; q < k; ++q) a = fma((v[q] - ((q == k - 1) ? c : 0.0)) * uinv, p[q], a);
+        const double b = p[k - 1];
+        const double ce = s * a + (c - 1.0) * b, cu = (c - 1.0) * a - s * b;
+        for (int q = 0; q < k; ++q) p[q] = fma(cu, (v[q] - ((q == k - 1) ? c : 0.0)) * uinv, p[q]);
+        p[k - 1] += ce;                                                   // p = R x
+        // distance to the axis, projection onto the nested sphere (nested_spheres_utils.py:50-59)
+        const double r = dists[lvl];
+        const double da = acos(fmin(fmax(p[k - 1], -1.0 + 1e-15), 1.0 - 1e-15));
+        const double sr = sin(r), inv_sd = 1.0 / (sin(da) + 1e-6);
+        // identification with the subsphere (:104-112): first k-1 coordinates / (sin r + 1e-6), renormalised
+        const double inv_sr = 1.0 / (sr + 1e-6);
+        double nn = 0.0;
+        for (int q = 0; q < k - 1; ++q) {
+            p[q] = (sr * p[q]) * inv_sd * inv_sr;
+            nn = fma(p[q], p[q], nn);
+        }
+        const double inv_n = 1.0 / (sqrt(nn) + 1e-6);
+        for (int q = 0; q < k - 1; ++q) p[q] *= inv_n;
+        v += k;
+    }
+    for (int k = 0; k < dl; ++k) y[i * dl + k] = p[k];
+}
+
+}  // namespace
+}  // namespace gabo
+
+extern "C" int gabo_nested_sphere_project(const double* x, int64_t n, int D, int d_latent, const double* axes,
+                                          const double* dists, double* y, void* stream) {
+    using namespace gabo;
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_nested_sphere_project: negative size");
+    if (n == 0) return GABO_OK;
+    GABO_REQUIRE(x && y && (D == d_latent || (axes && dists)), GABO_E_ARG, "gabo_nested_sphere_project: null pointer");
+    GABO_REQUIRE(D >= 2 && D <= kMaxNestedDim && d_latent >= 1 && d_latent <= D, GABO_E_ARG,
+                 "gabo_nested_sphere_project: need 1 <= d_latent <= D <= %d, got D=%d d_latent=%d", kMaxNestedDim, D,
+                 d_latent);
+    nested_sphere_project_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, n, D, d_latent, axes, dists, y);
+    return check_launch("nested_sphere_project_kernel");
+}

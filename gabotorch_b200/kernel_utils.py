@@ -375,3 +375,53 @@ class NestedSpdLogEuclideanGaussianKernel(_NestedSpdMixin, Kernel):
         else:
             out = ops.frobenius_gram(m1, m2, float(inv.detach()), _lib.KIND_GAUSS)
         return _finish(out, x1)
+
+
+class NestedSphereGaussianKernel(_BetaKernel):
+    """exp(-beta d(p(x1), p(x2))^2) with p the nested-sphere projection S^{dim-1} -> S^{latent_dim-1}
+    (kernels_nested_sphere.py:19-152).  One axis parameter ``raw_axis_S<k>`` per level k = dim .. latent_dim+1 and the
+    distances to the axes fixed at pi/2, as in the reference; the axes are created with ``requires_grad=False`` (they
+    are fitted on sphere manifolds by ``fit_gpytorch_manifold`` in the reference, which is outside this package)."""
+
+    def __init__(self, dim, latent_dim, beta_min, beta_prior=None, **kwargs):
+        super().__init__(beta_min, beta_prior=beta_prior, **kwargs)
+        self.dim = dim
+        self.latent_dim = latent_dim
+        for k in range(dim, latent_dim, -1):
+            axis = torch.randn(1, k)
+            axis = (axis / torch.norm(axis)).repeat(*self.batch_shape, 1, 1)
+            self.register_parameter(name='raw_axis_S%d' % k, parameter=torch.nn.Parameter(axis, requires_grad=False))
+        self.distances_to_axis = [math.pi / 2 * torch.ones(1, 1) for _ in range(dim, latent_dim, -1)]
+
+    @property
+    def axes(self):
+        return [self._parameters['raw_axis_S%d' % k] for k in range(self.dim, self.latent_dim, -1)]
+
+    @axes.setter
+    def axes(self, values_list):
+        self._set_axes(values_list)
+
+    def _set_axes(self, values_list):
+        for k in range(self.dim, self.latent_dim, -1):
+            name = 'raw_axis_S%d' % k
+            value = values_list[self.dim - k]
+            if not torch.is_tensor(value):
+                value = torch.as_tensor(value)
+            self.initialize(**{name: value.to(self._parameters[name]).reshape(self._parameters[name].shape)})
+
+    def _project(self, x):
+        if torch.is_grad_enabled() and any(a.requires_grad for a in self.axes):
+            raise NotImplementedError('gradients with respect to the nested-sphere axes are not provided '
+                                      '(fit_gpytorch_manifold is outside the scope of gabotorch_b200)')
+        return ops.nested_sphere_project(x, [a.detach().double() for a in self.axes], self.distances_to_axis)
+
+    def forward(self, x1, x2, diag=False, **params):
+        _reject_input_grad(x1, x2)
+        beta = self._beta_scalar()
+        p1 = self._project(x1)
+        p2 = p1 if x2 is x1 else self._project(x2)
+        if _needs_param_grad(self.raw_beta):
+            out = _param_gram(lambda: ops.sphere_gram(p1, p2, kind=_lib.KIND_DIST, diag=diag), beta, 2)
+        else:
+            out = ops.sphere_gram(p1, p2, float(beta.detach()), _lib.KIND_GAUSS, diag=diag)
+        return _finish(out, x1)

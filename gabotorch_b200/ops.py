@@ -286,6 +286,28 @@ def sphere_dist(x, y):
     return out.reshape(x.shape[:-1])
 
 
+def nested_sphere_project(x, axes, dists):
+    """S^{D-1} -> S^{dl-1} through the nested-sphere chain: x (..., D); axes: list of (1, k) or (k,) unit vectors for
+    k = D, D-1, ..., dl+1; dists: one distance to the axis per level.  Returns (..., dl) fp64 on the device."""
+    lib = _lib.load()
+    x = to_dev64(x)
+    D = x.shape[-1]
+    dl = D - len(axes)
+    flat = x.reshape(-1, D)
+    y = torch.empty(flat.shape[0], dl, dtype=torch.float64, device=x.device)
+    if len(axes) > 0:
+        ax = torch.cat([to_dev64(a).reshape(-1) for a in axes]).to(x.device)
+        for k, a in zip(range(D, dl, -1), axes):
+            if torch.as_tensor(a).numel() != k:
+                raise ValueError('axis of level %d must have %d components' % (k, k))
+        ds = torch.cat([to_dev64(r).reshape(-1)[:1] for r in dists]).to(x.device)
+    else:
+        ax = ds = None
+    _lib.check(lib.gabo_nested_sphere_project(_p(flat), flat.shape[0], D, dl, _p(ax), _p(ds), _p(y), _lib.stream_ptr()),
+               'gabo_nested_sphere_project')
+    return y.reshape(tuple(x.shape[:-1]) + (dl,))
+
+
 def spd_op(op, a, b, c=None):
     lib = _lib.load()
     a, b = to_dev64(a), to_dev64(b)

@@ -126,6 +126,13 @@ int gabo_sphere_op(int op, const double* a, const double* b, const double* c, in
 /* out[i] = acos(clip(<x_i,y_i>, -1, 1))  (pymanopt Sphere.dist; sphere_utils.py:68-90) */
 int gabo_sphere_dist(const double* x, const double* y, int64_t n, int dim, double* out, void* stream);
 
+/* Nested-sphere projection chain of HD-GaBO on spheres (nested_mappings/nested_spheres_utils.py:120-147 with
+ * rotation_from_sphere_points_torch, sphere_utils_torch.py:58-93):  x: n x D unit vectors -> y: n x d_latent unit vectors.
+ * axes: the unit axes of the levels D, D-1, ..., d_latent+1 concatenated (D + (D-1) + ... values); dists: one distance
+ * to the axis per level (the kernel of kernels_nested_sphere.py fixes them to pi/2).  fp64, D <= 64. */
+int gabo_nested_sphere_project(const double* x, int64_t n, int D, int d_latent, const double* axes, const double* dists,
+                               double* y, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * M2: batched SPD manifold operations under the affine-invariant metric (pymanopt PositiveDefinite; reference formulas
  * Riemannian_utils/spd_utils.py:104-213).  Matrices n x d x d fp64, d <= GABO_MAX_SPD_DIM.

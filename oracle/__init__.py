@@ -13,7 +13,9 @@ It restates, in plain numpy / torch-CPU fp64, the arithmetic of the reference
   ``Riemannian_utils/sphere_utils.py:14-123``.
 * ``oracle.spd``     – ``Riemannian_utils/spd_utils_torch.py:13-226``,
   ``kernel_utils/kernels_spd.py:72-100,160-187,217-313`` and ``Riemannian_utils/spd_utils.py:57-306``.
-* ``oracle.nested``  – ``nested_mappings/nested_spd_utils.py:13-48``.
+* ``oracle.nested``  – ``nested_mappings/nested_spd_utils.py:13-48`` and ``kernel_utils/kernels_nested_spd.py``.
+* ``oracle.nested_sphere`` – ``nested_mappings/nested_spheres_utils.py:13-147``,
+  ``Riemannian_utils/sphere_utils_torch.py:58-93``, ``kernel_utils/kernels_nested_sphere.py:129-152``.
 * ``oracle.gp``      – the GP posterior / analytic Expected Improvement that the reference
   obtains from botorch/gpytorch (call sites ``examples/bo_sphere/benchmark_examples/gabo_sphere.py:131-165``).
 * ``oracle.rcg``     – the multi-start driver ``manifold_optimization/manifold_optimize.py:36-321``
@@ -24,7 +26,7 @@ Parity pinning
 PINNED (against the reference's own code imported from ``/root/reference`` with a
 ``torch.symeig`` shim, see ``tests/golden/make_golden.py`` and the committed fixtures):
 sphere distance / kernel, Mandel pack/unpack, SPD affine-invariant distance / kernel,
-Frobenius and log-Euclidean distance, nested SPD projection.
+Frobenius and log-Euclidean distance, nested SPD projection, nested-sphere projection chain.
 
 PARITY UNPINNED: everything whose arithmetic lives in pymanopt / botorch / gpytorch
 (third-party, unpinned versions, absent from ``/root/reference`` and from this image):

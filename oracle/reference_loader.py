@@ -42,4 +42,5 @@ def load():
     ns['sphere_utils'] = importlib.import_module('BoManifolds.Riemannian_utils.sphere_utils')
     ns['spd_utils'] = importlib.import_module('BoManifolds.Riemannian_utils.spd_utils')
     ns['nested_spd_utils'] = importlib.import_module('BoManifolds.nested_mappings.nested_spd_utils')
+    ns['nested_spheres_utils'] = importlib.import_module('BoManifolds.nested_mappings.nested_spheres_utils')
     return type('Reference', (), dict(ns))

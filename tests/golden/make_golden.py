@@ -13,6 +13,7 @@ inputs + outputs of
 * ``affine_invariant_distance_torch`` (spd_utils_torch.py:53-120) and ``exp(-beta d^2)`` as in kernels_spd.py:96-98
 * ``frobenius_distance_torch`` (spd_utils_torch.py:124-156), ``logm_torch`` (:13-30)
 * ``projection_from_spd_to_nested_spd`` (nested_spd_utils.py:13-48)
+* ``projection_from_sphere_to_subsphere`` (nested_spheres_utils.py:120-147)
 * the numpy manifold formulas ``sphere_utils.py:14-123`` and ``spd_utils.py:104-213`` (exp/log/dist/transport)
 
 The kernel classes themselves (``kernels_sphere.py`` / ``kernels_spd.py``) import gpytorch, which is not
@@ -152,6 +153,20 @@ def main():
         tag = 'man_spd%d_' % d
         out[tag + 'x'], out[tag + 'y'], out[tag + 'u'] = xs, ys, us
         out[tag + 'log'], out[tag + 'exp05'], out[tag + 'dist'], out[tag + 'pt'] = logs, exps, dist, np.array(pts)
+
+    # ---- nested spheres (appended last so that the arrays above keep their values) ----------------------------
+    nsu = ref.nested_spheres_utils
+    for name, n, D, dl, r in (('nsph_5_3', 40, 5, 3, math.pi / 2), ('nsph_6_2', 33, 6, 2, 1.1)):
+        x = sphere_points(rng, n, D)
+        axes = [torch.from_numpy(sphere_points(rng, 1, k)) for k in range(D, dl, -1)]
+        dists = [r * torch.ones(1, 1, dtype=torch.float64) for _ in axes]
+        levels = nsu.projection_from_sphere_to_subsphere(torch.from_numpy(x), axes, dists)
+        out[name + '_x'] = x
+        out[name + '_r'] = np.array(r)
+        for lvl, a in enumerate(axes):
+            out[name + '_axis%d' % lvl] = a.numpy()
+        for lvl, y in enumerate(levels[1:]):
+            out[name + '_y%d' % lvl] = y.numpy()
 
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)

@@ -103,3 +103,38 @@ def test_nested_spd_kernels_vs_oracle(D, d, n1, n2):
     k.raw_projection_matrix.requires_grad_(True)
     with pytest.raises(NotImplementedError):
         k.forward(x1, x2)
+
+
+@pytest.mark.parametrize('name,D,dl', [('nsph_5_3', 5, 3), ('nsph_6_2', 6, 2)])
+def test_nested_sphere_projection_golden(golden, name, D, dl):
+    axes = [torch.from_numpy(golden[name + '_axis%d' % lvl]) for lvl in range(D - dl)]
+    r = float(golden[name + '_r'])
+    y = ops.nested_sphere_project(torch.from_numpy(golden[name + '_x']), axes, [torch.tensor([[r]])] * len(axes))
+    np.testing.assert_allclose(y.cpu().numpy(), golden[name + '_y%d' % (D - dl - 1)], rtol=0, atol=1e-12)
+
+
+def test_nested_sphere_kernel_vs_oracle():
+    # kernels_nested_sphere.py:129-152 (hd_gabo_sphere.py:134 uses NestedSphereGaussianKernel(5 -> 3))
+    import gabotorch_b200 as g
+    from oracle import nested_sphere as ons
+    from oracle import sphere as osph
+    rng = np.random.default_rng(8)
+    x1, x2 = osph.rand(rng, 45, 5), osph.rand(rng, 31, 5)
+    k = g.NestedSphereGaussianKernel(5, 3, beta_min=2.0)
+    axes = [a.detach().double() for a in k.axes]
+    assert [tuple(a.shape) for a in axes] == [(1, 5), (1, 4)] and len(k.distances_to_axis) == 2
+    beta = float(k.beta.detach())
+    with torch.no_grad():
+        got = k.forward(torch.from_numpy(x1), torch.from_numpy(x2))
+        dg = k.forward(torch.from_numpy(x1), torch.from_numpy(x1), diag=True)
+    ref = ons.nested_sphere_gaussian_kernel(x1, x2, axes, k.distances_to_axis, beta).numpy()
+    m = ref >= 1e-6
+    assert np.all(np.abs(got.numpy() - ref)[m] <= 1e-5 * ref[m]) and tuple(dg.shape) == (45, 1)
+    new_axes = [osph.rand(rng, 1, 5), osph.rand(rng, 1, 4)]
+    k.axes = new_axes
+    ref2 = ons.nested_sphere_gaussian_kernel(x1, x2, [torch.from_numpy(a).float().double() for a in new_axes],
+                                             k.distances_to_axis, beta).numpy()
+    with torch.no_grad():
+        got2 = k.forward(torch.from_numpy(x1), torch.from_numpy(x2)).numpy()
+    m2 = ref2 >= 1e-6
+    assert np.all(np.abs(got2 - ref2)[m2] <= 1e-5 * ref2[m2])

@@ -162,3 +162,15 @@ def test_oracle_against_live_reference():
                                ref.spd_utils_torch.affine_invariant_distance_torch(m, m).numpy(), rtol=3e-7, atol=2e-7)
     v = ref.spd_utils_torch.symmetric_matrix_to_vector_mandel_torch(m)
     np.testing.assert_allclose(ospd.symmetric_matrix_to_vector_mandel(m).numpy(), v.numpy(), atol=1e-15)
+
+
+@pytest.mark.parametrize('name,D,dl', [('nsph_5_3', 5, 3), ('nsph_6_2', 6, 2)])
+def test_nested_sphere_projection_matches_reference(golden, name, D, dl):
+    # nested_spheres_utils.py:120-147 run from the reference's own code (tests/golden/make_golden.py)
+    from oracle import nested_sphere as ons
+    axes = [torch.from_numpy(golden[name + '_axis%d' % lvl]) for lvl in range(D - dl)]
+    r = float(golden[name + '_r'])
+    levels = ons.projection_from_sphere_to_subsphere(golden[name + '_x'], axes, [r] * len(axes))
+    for lvl in range(D - dl):
+        np.testing.assert_allclose(levels[lvl + 1].numpy(), golden[name + '_y%d' % lvl], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(np.linalg.norm(levels[-1].numpy(), axis=-1), 1.0, atol=2e-6)   # the 1e-6 of :112
