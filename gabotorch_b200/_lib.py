@@ -61,6 +61,13 @@ SIGNATURES = {
     'gabo_nested_projection_pack_size': (c_i64, [c_i32, c_i32]),
     'gabo_nested_projection_matrix': (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     'gabo_nested_spd_project': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    'gabo_nested_sphere_chain': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'gabo_nested_sphere_to_nested': (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_f64, c_ptr, c_ptr]),
+    'gabo_nested_sphere_reconstruct': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'gabo_spd_sqrtm': (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
+    'gabo_nested_spd_reconstruct_pack_size': (c_i64, [c_i32, c_i32]),
+    'gabo_nested_spd_reconstruct_setup': (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    'gabo_nested_spd_reconstruct': (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
 }
 
 

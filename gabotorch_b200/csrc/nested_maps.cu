@@ -1,0 +1,432 @@
+// Nested-manifold maps either side of the latent acquisition optimisation of HD-GaBO:
+//   gabo_nested_sphere_chain        : every level of projection_from_sphere_to_subsphere
+//                                     (BoManifolds/nested_mappings/nested_spheres_utils.py:120-147)
+//   gabo_nested_sphere_to_nested    : projection_from_sphere_to_nested_sphere (:13-67)
+//   gabo_nested_sphere_reconstruct  : every level of projection_from_subsphere_to_sphere (:149-213)
+//   gabo_spd_sqrtm                  : sqrtm_torch for a batch (Riemannian_utils/spd_utils_torch.py:33-50)
+//   gabo_nested_spd_reconstruct_*   : projection_from_nested_spd_to_spd (nested_mappings/nested_spd_utils.py:51-118)
+// All fp64 (the reference runs these in fp64 on a handful of points; here they are batched, one thread or one CTA
+// per point, with every rotation applied in O(k) without forming the k x k matrix).
+#include "common.cuh"
+#include "spd_common.cuh"
+
+namespace gabo {
+namespace {
+
+constexpr int kMaxNestedDim = 64;
+
+// The reference's rotation_from_sphere_points_torch(x, y) (sphere_utils_torch.py:58-93) moves x to y:
+//     R = I + sin(theta) (y (x) u - u (x) y) + (c - 1) (y (x) y + u (x) u),  c = clamp(<x, y>), theta = acos c,
+//     u = (x - c y) / |x - c y|.
+// Applied to p:  R p = p + (s a + (c-1) b) y + ((c-1) a - s b) u,   a = <u, p>, b = <y, p>;  R^T flips the sign of s.
+// Here one of x, y is always the north pole e = (0, ..., 0, 1), so c = clamp(v[k-1]) for the level's axis v.
+struct LevelRotation {
+    double c, s, uinv;
+};
+
+__device__ __forceinline__ LevelRotation level_rotation(const double* __restrict__ v, int k, bool to_north) {
+    LevelRotation r;
+    r.c = fmin(fmax(v[k - 1], -1.0 + 1e-15), 1.0 - 1e-15);            // sphere_utils_torch.py:80-83
+    double un = 0.0;
+    if (to_north) {                                                    // u ~ v - c e
+        for (int q = 0; q < k; ++q) {
+            const double t = v[q] - ((q == k - 1) ? r.c : 0.0);
+            un = fma(t, t, un);
+        }
+    } else {                                                           // u ~ e - c v
+        for (int q = 0; q < k; ++q) {
+            const double t = ((q == k - 1) ? 1.0 : 0.0) - r.c * v[q];
+            un = fma(t, t, un);
+        }
+    }
+    r.uinv = 1.0 / sqrt(un);
+    r.s = sin(acos(r.c));
+    return r;
+}
+
+// p <- R p (sign = +1) or R^T p (sign = -1) for the rotation axis -> north pole.
+__device__ __forceinline__ void rotate_to_north(double* p, const double* __restrict__ v, int k, const LevelRotation& r,
+                                                double sign) {
+    double a = 0.0;
+    for (int q = 0; q < k; ++q) a = fma((v[q] - ((q == k - 1) ? r.c : 0.0)) * r.uinv, p[q], a);
+    const double b = p[k - 1];
+    const double s = sign * r.s;
+    const double ce = s * a + (r.c - 1.0) * b, cu = (r.c - 1.0) * a - s * b;
+    for (int q = 0; q < k; ++q) p[q] = fma(cu, (v[q] - ((q == k - 1) ? r.c : 0.0)) * r.uinv, p[q]);
+    p[k - 1] += ce;
+}
+
+// p <- R p for the rotation north pole -> axis.
+__device__ __forceinline__ void rotate_from_north(double* p, const double* __restrict__ v, int k,
+                                                  const LevelRotation& r) {
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < k; ++q) {
+        a = fma((((q == k - 1) ? 1.0 : 0.0) - r.c * v[q]) * r.uinv, p[q], a);
+        b = fma(v[q], p[q], b);
+    }
+    const double cy = r.s * a + (r.c - 1.0) * b, cu = (r.c - 1.0) * a - r.s * b;
+    for (int q = 0; q < k; ++q) {
+        const double u = (((q == k - 1) ? 1.0 : 0.0) - r.c * v[q]) * r.uinv;
+        p[q] = fma(cy, v[q], fma(cu, u, p[q]));
+    }
+}
+
+// One level down, in place: p (k values on S^{k-1}) -> k-1 values on S^{k-2} (nested_spheres_utils.py:44-59, 97-112).
+__device__ __forceinline__ void level_down(double* p, const double* __restrict__ v, int k, double r) {
+    const LevelRotation rot = level_rotation(v, k, true);
+    rotate_to_north(p, v, k, rot, 1.0);
+    const double da = acos(fmin(fmax(p[k - 1], -1.0 + 1e-15), 1.0 - 1e-15));
+    const double sr = sin(r), inv_sd = 1.0 / (sin(da) + 1e-6), inv_sr = 1.0 / (sr + 1e-6);
+    double nn = 0.0;
+    for (int q = 0; q < k - 1; ++q) {
+        p[q] = (sr * p[q]) * inv_sd * inv_sr;
+        nn = fma(p[q], p[q], nn);
+    }
+    const double inv_n = 1.0 / (sqrt(nn) + 1e-6);
+    for (int q = 0; q < k - 1; ++q) p[q] *= inv_n;
+}
+
+__global__ void nested_sphere_chain_kernel(const double* __restrict__ x, int64_t n, int D, int dl,
+                                           const double* __restrict__ axes, const double* __restrict__ dists,
+                                           double* __restrict__ levels) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[kMaxNestedDim];
+    for (int k = 0; k < D; ++k) p[k] = x[i * D + k];
+    const double* v = axes;
+    double* out = levels;
+    for (int k = D, lvl = 0; k > dl; --k, ++lvl) {
+        level_down(p, v, k, dists[lvl]);
+        for (int q = 0; q < k - 1; ++q) out[i * (k - 1) + q] = p[q];
+        out += n * (k - 1);
+        v += k;
+    }
+}
+
+__global__ void nested_sphere_to_nested_kernel(const double* __restrict__ x, int64_t n, int k,
+                                               const double* __restrict__ v, double r, double* __restrict__ y) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[kMaxNestedDim];
+    for (int q = 0; q < k; ++q) p[q] = x[i * k + q];
+    const LevelRotation rot = level_rotation(v, k, true);
+    rotate_to_north(p, v, k, rot, 1.0);
+    const double da = acos(fmin(fmax(p[k - 1], -1.0 + 1e-15), 1.0 - 1e-15));
+    const double sr = sin(r), inv_sd = 1.0 / (sin(da) + 1e-6);
+    for (int q = 0; q < k - 1; ++q) p[q] = (sr * p[q]) * inv_sd;
+    p[k - 1] = fma(sr, p[k - 1], sin(da - r)) * inv_sd;
+    rotate_to_north(p, v, k, rot, -1.0);                               // back: R^T
+    for (int q = 0; q < k; ++q) y[i * k + q] = p[q];
+}
+
+// Up the chain: y (dl values) -> dl+1 -> ... -> D.  axes / dists are given in the order of the projection
+// (levels D, D-1, ..., dl+1); the reconstruction consumes them last to first (nested_spheres_utils.py:207-211).
+__global__ void nested_sphere_reconstruct_kernel(const double* __restrict__ y, int64_t n, int dl, int D,
+                                                 const double* __restrict__ axes, const double* __restrict__ dists,
+                                                 double* __restrict__ levels) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double p[kMaxNestedDim];
+    for (int q = 0; q < dl; ++q) p[q] = y[i * dl + q];
+    // offset of the axis of level k (k = D, D-1, ...): sum of the longer ones before it
+    double* out = levels;
+    for (int k = dl + 1; k <= D; ++k) {
+        const int lvl = D - k;
+        int off = 0;
+        for (int kk = D; kk > k; --kk) off += kk;
+        const double* v = axes + off;
+        const double r = dists[lvl];
+        const double sr = sin(r), cr = cos(r);
+        for (int q = 0; q < k - 1; ++q) p[q] *= sr;                    // nested_spheres_utils.py:176-177
+        p[k - 1] = cr;
+        const LevelRotation rot = level_rotation(v, k, false);
+        rotate_from_north(p, v, k, rot);
+        for (int q = 0; q < k; ++q) out[i * k + q] = p[q];
+        out += n * k;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sqrtm for a batch of small SPD matrices: same route as gabo_spd_logm (Cholesky X = L L^T, one-sided Jacobi on L:
+// L V = U Sigma, X = U Sigma^2 U^T, sqrtm X = sum_k g_k g_k^T / sigma_k with g_k = sigma_k u_k the columns of L V).
+// ---------------------------------------------------------------------------------------------------------------
+template <int d>
+__global__ void spd_sqrtm_kernel(const double* __restrict__ mat, int64_t n, double* __restrict__ out) {
+    constexpr int TRI = tri_size(d);
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* m = mat + i * d * d;
+    double L[TRI], A[TRI];
+    const bool ok = chol_inv<d>([&](int r, int c) { return m[c * d + r]; }, L, A);   // symeig(upper=True)
+    double G[d][d];
+    tri_expand<d, double>([&](int e) { return L[e]; }, G);
+    double lam[d];
+    jacobi_onesided<d, double>(G, lam);
+    double f[d];
+#pragma unroll
+    for (int k = 0; k < d; ++k) f[k] = 1.0 / sqrt(lam[k]);
+    double C[d][d];
+    weighted_outer<d, double>(G, f, C);
+    double* o = out + i * d * d;
+    const double nanv = ok ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+    for (int r = 0; r < d; ++r)
+#pragma unroll
+        for (int c = 0; c < d; ++c) o[r * d + c] = C[r][c] + nanv;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SPD reconstruction X = R [Y B; B^T C] R^T, R = [W V], B = Y^(1/2) K C^(1/2)  (nested_spd_utils.py:51-118), as
+//     X = W Y W^T + E + E^T + Z,   E = W Y^(1/2) N,   N = K C^(1/2) V^T (d x D),   Z = V C V^T (D x D).
+// N and Z do not depend on the point: the setup kernel computes them once (C^(1/2) by a warp-cooperative two-sided
+// Jacobi in shared memory, any size up to 32), the batch kernel streams the points.
+// pack = [W (D x d) | N (d x D) | Z (D x D)] doubles.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxReconDim = 32;
+
+__global__ void __launch_bounds__(32)
+nested_spd_reconstruct_setup_kernel(const double* __restrict__ w, const double* __restrict__ v,
+                                    const double* __restrict__ cmat, const double* __restrict__ kmat, int D, int d,
+                                    double* __restrict__ pack, int* __restrict__ flag) {
+    const int m = D - d;
+    const int lane = threadIdx.x;
+    __shared__ double S[kMaxReconDim * kMaxReconDim];   // working copy of C -> diagonal
+    __shared__ double Q[kMaxReconDim * kMaxReconDim];   // eigenvectors (columns), then C^(1/2)
+    __shared__ double M[8 * kMaxReconDim];              // K C^(1/2)  (d x m)
+    __shared__ double lam[kMaxReconDim];
+    double fro = 0.0;
+    for (int e = lane; e < m * m; e += 32) {
+        const int r = e / m, c = e % m;
+        const double val = (r <= c) ? cmat[r * m + c] : cmat[c * m + r];   // symeig(upper=True)
+        S[e] = val;
+        Q[e] = (r == c) ? 1.0 : 0.0;
+        fro = fma(val, val, fro);
+    }
+    fro = warp_sum(fro);
+    const double thr = 1e-15 * sqrt(fro);
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < m - 1; ++p) {
+            for (int q = p + 1; q < m; ++q) {
+                const double apq = S[p * m + q];
+                if (fabs(apq) <= thr) continue;                           // uniform across the warp
+                rotated = true;
+                const double tau = (S[q * m + q] - S[p * m + p]) / (2.0 * apq);
+                const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
+                const double cs = 1.0 / sqrt(fma(t, t, 1.0)), sn = t * cs;
+                __syncwarp();
+                if (lane < m) {                                            // columns p, q
+                    const double sp = S[lane * m + p], sq = S[lane * m + q];
+                    S[lane * m + p] = fma(cs, sp, -sn * sq);
+                    S[lane * m + q] = fma(sn, sp, cs * sq);
+                    const double vp = Q[lane * m + p], vq = Q[lane * m + q];
+                    Q[lane * m + p] = fma(cs, vp, -sn * vq);
+                    Q[lane * m + q] = fma(sn, vp, cs * vq);
+                }
+                __syncwarp();
+                if (lane < m) {                                            // rows p, q
+                    const double sp = S[p * m + lane], sq = S[q * m + lane];
+                    S[p * m + lane] = fma(cs, sp, -sn * sq);
+                    S[q * m + lane] = fma(sn, sp, cs * sq);
+                }
+                __syncwarp();
+            }
+        }
+        if (!rotated) break;
+    }
+    bool bad = false;
+    if (lane < m) {
+        const double l = S[lane * m + lane];
+        bad = !(l > 0.0);
+        lam[lane] = sqrt(l);
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) *flag = 1;              // bottom block not positive definite
+    __syncwarp();
+    // C^(1/2) = Q diag(sqrt lam) Q^T into S
+    for (int e = lane; e < m * m; e += 32) {
+        const int r = e / m, c = e % m;
+        double acc = 0.0;
+        for (int k = 0; k < m; ++k) acc = fma(Q[r * m + k] * lam[k], Q[c * m + k], acc);
+        S[e] = acc;
+    }
+    __syncwarp();
+    for (int e = lane; e < d * m; e += 32) {                               // M = K C^(1/2)
+        const int r = e / m, c = e % m;
+        double acc = 0.0;
+        for (int k = 0; k < m; ++k) acc = fma(kmat[r * m + k], S[k * m + c], acc);
+        M[e] = acc;
+    }
+    __syncwarp();
+    double* pw = pack;
+    double* pn = pack + D * d;
+    double* pz = pn + d * D;
+    for (int e = lane; e < D * d; e += 32) pw[e] = w[e];
+    for (int e = lane; e < d * D; e += 32) {                               // N = M V^T
+        const int r = e / D, c = e % D;
+        double acc = 0.0;
+        for (int k = 0; k < m; ++k) acc = fma(M[r * m + k], v[c * m + k], acc);
+        pn[e] = acc;
+    }
+    // Z = V C V^T: first T = V C into Q (D x m fits: D <= 32, m < 32), then Z
+    for (int e = lane; e < D * m; e += 32) {
+        const int r = e / m, c = e % m;
+        double acc = 0.0;
+        for (int k = 0; k < m; ++k) acc = fma(v[r * m + k], cmat[k * m + c], acc);
+        Q[e] = acc;
+    }
+    __syncwarp();
+    for (int e = lane; e < D * D; e += 32) {
+        const int r = e / D, c = e % D;
+        double acc = 0.0;
+        for (int k = 0; k < m; ++k) acc = fma(Q[r * m + k], v[c * m + k], acc);
+        pz[e] = acc;
+    }
+}
+
+// One CTA of 128 threads per point (grid-stride).  Output rows are written contiguously (coalesced).
+__global__ void __launch_bounds__(128)
+nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __restrict__ sq, int64_t n, int D, int d,
+                              const double* __restrict__ pack, double* __restrict__ x) {
+    extern __shared__ double sm[];
+    double* W = sm;                  // D x d
+    double* N = W + D * d;           // d x D
+    double* Z = N + d * D;           // D x D
+    double* T1 = Z + D * D;          // W Y      (D x d)
+    double* T2 = T1 + D * d;         // W Y^1/2  (D x d)
+    double* Yi = T2 + D * d;         // d x d
+    double* Si = Yi + d * d;         // d x d
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 2 * D * d + D * D; e += 128) sm[e] = pack[e];
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        __syncthreads();
+        for (int e = tid; e < d * d; e += 128) {
+            Yi[e] = y[i * d * d + e];
+            Si[e] = sq[i * d * d + e];
+        }
+        __syncthreads();
+        for (int e = tid; e < D * d; e += 128) {
+            const int r = e / d, c = e % d;
+            double a1 = 0.0, a2 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                a1 = fma(W[r * d + k], Yi[k * d + c], a1);
+                a2 = fma(W[r * d + k], Si[k * d + c], a2);
+            }
+            T1[e] = a1;
+            T2[e] = a2;
+        }
+        __syncthreads();
+        double* xo = x + i * D * D;
+        for (int e = tid; e < D * D; e += 128) {
+            const int r = e / D, c = e % D;
+            double acc = Z[e];
+            for (int k = 0; k < d; ++k) {
+                acc = fma(T1[r * d + k], W[c * d + k], acc);
+                acc = fma(T2[r * d + k], N[k * D + c], acc);
+                acc = fma(T2[c * d + k], N[k * D + r], acc);
+            }
+            xo[e] = acc;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace gabo
+
+using namespace gabo;
+
+static int check_nested_dims(const char* who, int D, int dl) {
+    GABO_REQUIRE(D >= 2 && D <= kMaxNestedDim && dl >= 1 && dl <= D, GABO_E_ARG,
+                 "%s: need 1 <= d_latent <= D <= %d, got D=%d d_latent=%d", who, kMaxNestedDim, D, dl);
+    return GABO_OK;
+}
+
+extern "C" int gabo_nested_sphere_chain(const double* x, int64_t n, int D, int d_latent, const double* axes,
+                                        const double* dists, double* levels, void* stream) {
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_nested_sphere_chain: negative size");
+    if (int rc = check_nested_dims("gabo_nested_sphere_chain", D, d_latent)) return rc;
+    if (n == 0 || D == d_latent) return GABO_OK;
+    GABO_REQUIRE(x && axes && dists && levels, GABO_E_ARG, "gabo_nested_sphere_chain: null pointer");
+    nested_sphere_chain_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, n, D, d_latent, axes, dists, levels);
+    return check_launch("nested_sphere_chain_kernel");
+}
+
+extern "C" int gabo_nested_sphere_to_nested(const double* x, int64_t n, int dim, const double* axis, double dist,
+                                            double* y, void* stream) {
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_nested_sphere_to_nested: negative size");
+    if (int rc = check_nested_dims("gabo_nested_sphere_to_nested", dim, dim)) return rc;
+    if (n == 0) return GABO_OK;
+    GABO_REQUIRE(x && axis && y, GABO_E_ARG, "gabo_nested_sphere_to_nested: null pointer");
+    nested_sphere_to_nested_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0,
+                                     static_cast<cudaStream_t>(stream)>>>(x, n, dim, axis, dist, y);
+    return check_launch("nested_sphere_to_nested_kernel");
+}
+
+extern "C" int gabo_nested_sphere_reconstruct(const double* y, int64_t n, int d_latent, int D, const double* axes,
+                                              const double* dists, double* levels, void* stream) {
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_nested_sphere_reconstruct: negative size");
+    if (int rc = check_nested_dims("gabo_nested_sphere_reconstruct", D, d_latent)) return rc;
+    if (n == 0 || D == d_latent) return GABO_OK;
+    GABO_REQUIRE(y && axes && dists && levels, GABO_E_ARG, "gabo_nested_sphere_reconstruct: null pointer");
+    nested_sphere_reconstruct_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0,
+                                       static_cast<cudaStream_t>(stream)>>>(y, n, d_latent, D, axes, dists, levels);
+    return check_launch("nested_sphere_reconstruct_kernel");
+}
+
+extern "C" int gabo_spd_sqrtm(const double* mat, int64_t n, int d, double* out, void* stream) {
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_spd_sqrtm: negative size");
+    if (n == 0) return GABO_OK;
+    GABO_REQUIRE(mat && out, GABO_E_ARG, "gabo_spd_sqrtm: null pointer");
+    GABO_REQUIRE(d >= 1 && d <= GABO_MAX_SPD_DIM, GABO_E_ARG, "gabo_spd_sqrtm: d=%d outside [1, %d]", d,
+                 GABO_MAX_SPD_DIM);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>((n + 63) / 64);
+    switch (d) {
+#define GABO_CASE(DD)                                           \
+    case DD:                                                    \
+        spd_sqrtm_kernel<DD><<<grid, 64, 0, s>>>(mat, n, out);  \
+        break;
+        GABO_CASE(1)
+        GABO_CASE(2)
+        GABO_CASE(3)
+        GABO_CASE(4)
+        GABO_CASE(5)
+        GABO_CASE(6)
+        GABO_CASE(7)
+        GABO_CASE(8)
+#undef GABO_CASE
+    }
+    return check_launch("spd_sqrtm_kernel");
+}
+
+static int check_recon_dims(const char* who, int D, int d) {
+    GABO_REQUIRE(d >= 1 && d <= GABO_MAX_SPD_DIM && D > d && D <= kMaxReconDim, GABO_E_ARG,
+                 "%s: need 1 <= d <= %d and d < D <= %d, got D=%d d=%d", who, GABO_MAX_SPD_DIM, kMaxReconDim, D, d);
+    return GABO_OK;
+}
+
+extern "C" int64_t gabo_nested_spd_reconstruct_pack_size(int D, int d) {
+    if (d < 1 || D <= d) return 0;
+    return static_cast<int64_t>(2) * D * d + static_cast<int64_t>(D) * D;
+}
+
+extern "C" int gabo_nested_spd_reconstruct_setup(const double* w, const double* v, const double* c, const double* k,
+                                                 int D, int d, double* pack, int* flag, void* stream) {
+    if (int rc = check_recon_dims("gabo_nested_spd_reconstruct_setup", D, d)) return rc;
+    GABO_REQUIRE(w && v && c && k && pack && flag, GABO_E_ARG, "gabo_nested_spd_reconstruct_setup: null pointer");
+    nested_spd_reconstruct_setup_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(w, v, c, k, D, d, pack, flag);
+    return check_launch("nested_spd_reconstruct_setup_kernel");
+}
+
+extern "C" int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt, int64_t n, int D, int d,
+                                           const double* pack, double* x, void* stream) {
+    GABO_REQUIRE(n >= 0, GABO_E_ARG, "gabo_nested_spd_reconstruct: negative size");
+    if (int rc = check_recon_dims("gabo_nested_spd_reconstruct", D, d)) return rc;
+    if (n == 0) return GABO_OK;
+    GABO_REQUIRE(y && y_sqrt && pack && x, GABO_E_ARG, "gabo_nested_spd_reconstruct: null pointer");
+    const size_t smem = sizeof(double) * (static_cast<size_t>(4) * D * d + static_cast<size_t>(D) * D + 2 * d * d);
+    const unsigned grid = static_cast<unsigned>(imin(n, static_cast<int64_t>(sm_count()) * 8));
+    nested_spd_reconstruct_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(y, y_sqrt, n, D, d, pack, x);
+    return check_launch("nested_spd_reconstruct_kernel");
+}

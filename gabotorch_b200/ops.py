@@ -242,6 +242,48 @@ def spd_logm(mat):
     return out.reshape(m.shape)
 
 
+def spd_sqrtm(mat):
+    """Batched sqrtm_torch (spd_utils_torch.py:33-50): (..., d, d) -> (..., d, d)."""
+    lib = _lib.load()
+    m = to_dev64(mat)
+    d = m.shape[-1]
+    flat = m.reshape(-1, d, d)
+    out = torch.empty_like(flat)
+    _lib.check(lib.gabo_spd_sqrtm(_p(flat), flat.shape[0], d, _p(out), _lib.stream_ptr()), 'gabo_spd_sqrtm')
+    return out.reshape(m.shape)
+
+
+def nested_spd_reconstruct_pack(w, v, c, k):
+    """Point-independent factors of projection_from_nested_spd_to_spd for fixed (W, V, C, K)."""
+    lib = _lib.load()
+    w, v, c, k = (to_dev64(t) for t in (w, v, c, k))
+    D, d = int(w.shape[0]), int(w.shape[1])
+    m = D - d
+    if tuple(v.shape) != (D, m) or tuple(c.shape) != (m, m) or tuple(k.shape) != (d, m):
+        raise ValueError('expected W (D, d), V (D, D-d), C (D-d, D-d), K (d, D-d)')
+    size = lib.gabo_nested_spd_reconstruct_pack_size(D, d)
+    pack = torch.empty(max(size, 1), dtype=torch.float64, device=w.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=w.device)
+    _lib.check(lib.gabo_nested_spd_reconstruct_setup(_p(w), _p(v), _p(c), _p(k), D, d, _p(pack), _p(flag),
+                                                     _lib.stream_ptr()), 'gabo_nested_spd_reconstruct_setup')
+    if int(flag.item()) != 0:
+        raise NotPositiveDefiniteError('bottom_spd_matrix is not positive definite')
+    return pack
+
+
+def nested_spd_reconstruct(y, D, pack):
+    """(n, d, d) latent SPD matrices -> (n, D, D)."""
+    lib = _lib.load()
+    y = to_dev64(y)
+    d = y.shape[-1]
+    flat = y.reshape(-1, d, d)
+    sq = spd_sqrtm(flat)
+    x = torch.empty(flat.shape[0], D, D, dtype=torch.float64, device=y.device)
+    _lib.check(lib.gabo_nested_spd_reconstruct(_p(flat), _p(sq), flat.shape[0], D, d, _p(pack), _p(x),
+                                               _lib.stream_ptr()), 'gabo_nested_spd_reconstruct')
+    return x.reshape(tuple(y.shape[:-2]) + (D, D))
+
+
 def frobenius_gram(m1, m2, param=0.0, kind=_lib.KIND_GAUSS, out_dtype=torch.float64):
     """f(||M1_i - M2_j + 1e-15||_F) for (..., N, d, d) matrices (spd_utils_torch.py:124-156)."""
     lib = _lib.load()
@@ -306,6 +348,79 @@ def nested_sphere_project(x, axes, dists):
     _lib.check(lib.gabo_nested_sphere_project(_p(flat), flat.shape[0], D, dl, _p(ax), _p(ds), _p(y), _lib.stream_ptr()),
                'gabo_nested_sphere_project')
     return y.reshape(tuple(x.shape[:-1]) + (dl,))
+
+
+def _nested_axes(axes, dists, D, device):
+    """Concatenated axes / distances of the levels D, D-1, ... (each axis (1, k) or (k,))."""
+    dl = D - len(axes)
+    if len(dists) != len(axes):
+        raise ValueError('need one distance to the axis per level')
+    for k, a in zip(range(D, dl, -1), axes):
+        if torch.as_tensor(a).numel() != k:
+            raise ValueError('axis of level %d must have %d components' % (k, k))
+    ax = torch.cat([to_dev64(a).reshape(-1) for a in axes]).to(device)
+    ds = torch.cat([to_dev64(r).reshape(-1)[:1] for r in dists]).to(device)
+    return ax, ds
+
+
+def _split_levels(buf, n, dims, lead):
+    out, off = [], 0
+    for k in dims:
+        out.append(buf[off:off + n * k].reshape(tuple(lead) + (k,)))
+        off += n * k
+    return out
+
+
+def nested_sphere_chain(x, axes, dists):
+    """Every level of the projection chain: x (..., D) -> [(..., D-1), ..., (..., dl)] fp64 on the device."""
+    lib = _lib.load()
+    x = to_dev64(x)
+    D = x.shape[-1]
+    if len(axes) == 0:
+        return []
+    ax, ds = _nested_axes(axes, dists, D, x.device)
+    dl = D - len(axes)
+    flat = x.reshape(-1, D)
+    n = flat.shape[0]
+    dims = list(range(D - 1, dl - 1, -1))
+    buf = torch.empty(n * sum(dims), dtype=torch.float64, device=x.device)
+    _lib.check(lib.gabo_nested_sphere_chain(_p(flat), n, D, dl, _p(ax), _p(ds), _p(buf), _lib.stream_ptr()),
+               'gabo_nested_sphere_chain')
+    return _split_levels(buf, n, dims, x.shape[:-1])
+
+
+def nested_sphere_to_nested(x, axis, dist):
+    """Closest points of the nested sphere {p: d(p, axis) = dist}: (..., k) -> (..., k)."""
+    lib = _lib.load()
+    x = to_dev64(x)
+    k = x.shape[-1]
+    ax = to_dev64(axis).reshape(-1).to(x.device)
+    if ax.numel() != k:
+        raise ValueError('axis must have %d components' % k)
+    flat = x.reshape(-1, k)
+    y = torch.empty_like(flat)
+    _lib.check(lib.gabo_nested_sphere_to_nested(_p(flat), flat.shape[0], k, _p(ax), float(torch.as_tensor(dist).reshape(-1)[0]),
+                                                _p(y), _lib.stream_ptr()), 'gabo_nested_sphere_to_nested')
+    return y.reshape(x.shape)
+
+
+def nested_sphere_reconstruct(y, axes, dists):
+    """Every level of the inverse chain: y (..., dl) -> [(..., dl+1), ..., (..., D)]; axes / dists ordered as for the
+    projection (levels D, D-1, ..., dl+1)."""
+    lib = _lib.load()
+    y = to_dev64(y)
+    dl = y.shape[-1]
+    if len(axes) == 0:
+        return []
+    D = dl + len(axes)
+    ax, ds = _nested_axes(axes, dists, D, y.device)
+    flat = y.reshape(-1, dl)
+    n = flat.shape[0]
+    dims = list(range(dl + 1, D + 1))
+    buf = torch.empty(n * sum(dims), dtype=torch.float64, device=y.device)
+    _lib.check(lib.gabo_nested_sphere_reconstruct(_p(flat), n, dl, D, _p(ax), _p(ds), _p(buf), _lib.stream_ptr()),
+               'gabo_nested_sphere_reconstruct')
+    return _split_levels(buf, n, dims, y.shape[:-1])
 
 
 def spd_op(op, a, b, c=None):

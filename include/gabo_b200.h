@@ -132,6 +132,18 @@ int gabo_sphere_dist(const double* x, const double* y, int64_t n, int dim, doubl
  * to the axis per level (the kernel of kernels_nested_sphere.py fixes them to pi/2).  fp64, D <= 64. */
 int gabo_nested_sphere_project(const double* x, int64_t n, int D, int d_latent, const double* axes, const double* dists,
                                double* y, void* stream);
+/* Every level of the same chain (projection_from_sphere_to_subsphere returns the list, nested_spheres_utils.py:139-147):
+ * levels = [n x (D-1) | n x (D-2) | ... | n x d_latent] blocks, level-major, each row-major. */
+int gabo_nested_sphere_chain(const double* x, int64_t n, int D, int d_latent, const double* axes, const double* dists,
+                             double* levels, void* stream);
+/* projection_from_sphere_to_nested_sphere (nested_spheres_utils.py:13-67): x: n x dim on S^{dim-1} -> y: n x dim, the
+ * closest points at geodesic distance `dist` from `axis` (still in the coordinates of S^{dim-1}). */
+int gabo_nested_sphere_to_nested(const double* x, int64_t n, int dim, const double* axis, double dist, double* y,
+                                 void* stream);
+/* Inverse chain, projection_from_subsphere_to_sphere (nested_spheres_utils.py:149-213): y: n x d_latent ->
+ * levels = [n x (d_latent+1) | ... | n x D]; axes / dists in the order of the projection (levels D, D-1, ...). */
+int gabo_nested_sphere_reconstruct(const double* y, int64_t n, int d_latent, int D, const double* axes,
+                                   const double* dists, double* levels, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * M2: batched SPD manifold operations under the affine-invariant metric (pymanopt PositiveDefinite; reference formulas
@@ -213,6 +225,23 @@ int64_t gabo_nested_projection_pack_size(int D, int d);
 int gabo_nested_projection_matrix(const double* w, int D, int d, float* p_pack, void* stream);
 int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, int d, const float* p_pack, float* y_mandel,
                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Approximate inverse of P1, projection_from_nested_spd_to_spd (nested_mappings/nested_spd_utils.py:51-118):
+ *   X = R [Y B; B^T C] R^T,  R = [W V],  B = Y^(1/2) K C^(1/2);   fp64, d <= GABO_MAX_SPD_DIM, d < D <= 32.
+ * gabo_spd_sqrtm is sqrtm_torch (Riemannian_utils/spd_utils_torch.py:33-50) for a batch of d x d matrices (NaN output
+ * for a matrix that is not positive definite).  gabo_nested_spd_reconstruct_setup folds the point-independent factors
+ * (W: D x d, V: D x (D-d), C: (D-d)^2, K: d x (D-d), row-major) into `pack`
+ * (gabo_nested_spd_reconstruct_pack_size(D, d) doubles, caller-owned); *flag (device int, zeroed by the caller) is set
+ * when C is not positive definite.  gabo_nested_spd_reconstruct maps y (n x d x d) with y_sqrt = sqrtm(y) to
+ * x (n x D x D).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gabo_spd_sqrtm(const double* mat, int64_t n, int d, double* out, void* stream);
+int64_t gabo_nested_spd_reconstruct_pack_size(int D, int d);
+int gabo_nested_spd_reconstruct_setup(const double* w, const double* v, const double* c, const double* k, int D, int d,
+                                      double* pack, int* flag, void* stream);
+int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt, int64_t n, int D, int d, const double* pack,
+                                double* x, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,9 @@
 """Oracle (CPU, fp64) for the nested SPD projection of HD-GaBO.  Test infrastructure only.
 
 Follows ``BoManifolds/nested_mappings/nested_spd_utils.py:13-48`` (``Y = W^T X W`` through two ``bmm``)
-and ``kernel_utils/kernels_nested_spd.py:104-136`` (nested affine-invariant Gaussian kernel).
+and ``kernel_utils/kernels_nested_spd.py:104-136`` (nested affine-invariant Gaussian kernel); the approximate inverse
+``projection_from_nested_spd_to_spd`` follows ``nested_spd_utils.py:51-118`` with ``sqrtm_torch``
+(``Riemannian_utils/spd_utils_torch.py:33-50``).
 """
 import numpy as np
 import torch
@@ -65,3 +67,21 @@ def grassmann_rand(rng, D, d):
     """pymanopt Grassmann.rand: Q of QR(randn(D,d))."""
     q, _ = np.linalg.qr(rng.standard_normal((D, d)))
     return q
+
+
+def projection_from_nested_spd_to_spd(y, w, v, c, k):
+    """nested_spd_utils.py:77-118: X = R [Y B; B^T C] R^T, R = [W V], B = sqrtm(Y) K sqrtm(C)."""
+    y = torch.as_tensor(y, dtype=torch.float64)
+    w, v, c, k = (torch.as_tensor(t, dtype=torch.float64) for t in (w, v, c, k))
+    single = y.dim() == 2
+    if single:
+        y = y[None]
+    rot = torch.cat((w, v), dim=1)
+    sqrt_c = _spd.sqrtm(c)
+    out = []
+    for n in range(y.shape[0]):
+        side = torch.mm(torch.mm(_spd.sqrtm(y[n]), k), sqrt_c)
+        xr = torch.cat((torch.cat((y[n], side), dim=1), torch.cat((side.T, c), dim=1)), dim=0)
+        out.append(torch.mm(rot, torch.mm(xr, rot.T)))
+    out = torch.stack(out)
+    return out[0] if single else out

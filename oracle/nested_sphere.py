@@ -2,7 +2,7 @@
 
 Follows ``BoManifolds/Riemannian_utils/sphere_utils_torch.py:58-93`` (``rotation_from_sphere_points_torch``),
 ``BoManifolds/nested_mappings/nested_spheres_utils.py:13-147`` (projection to a nested sphere, identification with
-the next subsphere, chain over several levels) and ``kernel_utils/kernels_nested_sphere.py:129-152`` (the kernel).
+the next subsphere, chain over several levels), ``:149-213`` (the inverse chain) and ``kernel_utils/kernels_nested_sphere.py:129-152`` (the kernel).
 Pinned on the reference's own code through ``tests/golden`` (``nsph_*`` arrays).
 """
 import math
@@ -26,6 +26,42 @@ def rotation_from_sphere_points(x, y):
     return (torch.eye(k, dtype=inner.dtype)
             + torch.sin(torch.acos(inner)) * (torch.mm(y.T, c_vec) - torch.mm(c_vec.T, y))
             + (inner - 1.) * (torch.mm(y.T, y) + torch.mm(c_vec.T, c_vec)))
+
+
+def projection_to_nested_sphere(x, axis, dist_to_axis):
+    """nested_spheres_utils.py:13-67: closest points at distance r from the axis, in the coordinates of S^{k-1}."""
+    x = torch.as_tensor(x, dtype=torch.float64)
+    axis = torch.as_tensor(axis, dtype=torch.float64).reshape(1, -1)
+    r = torch.as_tensor(dist_to_axis, dtype=torch.float64).reshape(1, 1)
+    k = x.shape[-1]
+    north = torch.zeros_like(axis)
+    north[:, -1] = 1.
+    rot = rotation_from_sphere_points(axis, north)
+    x_rot = torch.mm(rot, x.T).T
+    d_axis = _sph.sphere_distance(x_rot, north).repeat((1, k))
+    x_ns_rot = torch.sin(r) * x_rot + torch.sin(d_axis - r) * north
+    x_ns_rot = x_ns_rot / (torch.sin(d_axis) + DIV_EPS)
+    return torch.mm(rot.T, x_ns_rot.T).T
+
+
+def projection_from_subsphere_to_next_sphere(x_sub, axis, dist_to_axis):
+    """nested_spheres_utils.py:149-180: (N, k-1) on S^{k-2} -> (N, k) on the nested sphere of S^{k-1}."""
+    x_sub = torch.as_tensor(x_sub, dtype=torch.float64)
+    axis = torch.as_tensor(axis, dtype=torch.float64).reshape(1, -1)
+    r = torch.as_tensor(dist_to_axis, dtype=torch.float64).reshape(1, 1)
+    north = torch.zeros_like(axis)
+    north[:, -1] = 1.
+    rot = rotation_from_sphere_points(north, axis)
+    cos_vec = torch.cos(r) * torch.ones(x_sub.shape[0], 1, dtype=torch.float64)
+    return torch.mm(rot, torch.cat((torch.sin(r) * x_sub, cos_vec), 1).T).T
+
+
+def projection_from_subsphere_to_sphere(x_sub, axes, dists):
+    """nested_spheres_utils.py:182-213: axes in the order of the projection, consumed last to first."""
+    out = [torch.as_tensor(x_sub, dtype=torch.float64)]
+    for a, r in zip(reversed(list(axes)), reversed(list(dists))):
+        out.append(projection_from_subsphere_to_next_sphere(out[-1], a, r))
+    return out
 
 
 def projection_to_next_subsphere(x, axis, dist_to_axis):

@@ -13,7 +13,9 @@ inputs + outputs of
 * ``affine_invariant_distance_torch`` (spd_utils_torch.py:53-120) and ``exp(-beta d^2)`` as in kernels_spd.py:96-98
 * ``frobenius_distance_torch`` (spd_utils_torch.py:124-156), ``logm_torch`` (:13-30)
 * ``projection_from_spd_to_nested_spd`` (nested_spd_utils.py:13-48)
-* ``projection_from_sphere_to_subsphere`` (nested_spheres_utils.py:120-147)
+* ``projection_from_sphere_to_subsphere`` (nested_spheres_utils.py:120-147), ``projection_from_sphere_to_nested_sphere``
+  (:13-67), ``projection_from_subsphere_to_sphere`` (:149-213)
+* ``sqrtm_torch`` (spd_utils_torch.py:33-50), ``projection_from_nested_spd_to_spd`` (nested_spd_utils.py:51-118)
 * the numpy manifold formulas ``sphere_utils.py:14-123`` and ``spd_utils.py:104-213`` (exp/log/dist/transport)
 
 The kernel classes themselves (``kernels_sphere.py`` / ``kernels_spd.py``) import gpytorch, which is not
@@ -167,6 +169,37 @@ def main():
             out[name + '_axis%d' % lvl] = a.numpy()
         for lvl, y in enumerate(levels[1:]):
             out[name + '_y%d' % lvl] = y.numpy()
+
+    # ---- reconstruction maps (appended after everything above) ---------------------------------
+    # nested spheres: projection onto the nested sphere (:13-67) and the inverse chain (:149-213), same axes as above
+    for name, n, D, dl, r in (('nsph_5_3', 40, 5, 3, math.pi / 2), ('nsph_6_2', 33, 6, 2, 1.1)):
+        x = torch.from_numpy(out[name + '_x'])
+        axes = [torch.from_numpy(out[name + '_axis%d' % lvl]) for lvl in range(D - dl)]
+        dists = [r * torch.ones(1, 1, dtype=torch.float64) for _ in axes]
+        out[name + '_ns0'] = nsu.projection_from_sphere_to_nested_sphere(x, axes[0], dists[0]).numpy()
+        y_low = torch.from_numpy(out[name + '_y%d' % (D - dl - 1)])
+        ups = nsu.projection_from_subsphere_to_sphere(y_low, axes, dists)
+        for lvl, u in enumerate(ups[1:]):
+            out[name + '_up%d' % lvl] = u.numpy()
+
+    # sqrtm_torch (spd_utils_torch.py:33-50)
+    for d in (3, 5):
+        xs = spd_points(rng, 20, d)
+        out['sqrtm%d_x' % d] = xs
+        out['sqrtm%d_y' % d] = np.array([pt.sqrtm_torch(torch.from_numpy(m)).numpy() for m in xs])
+
+    # projection_from_nested_spd_to_spd (nested_spd_utils.py:51-118)
+    for name, n, D, d in (('recon_5_2', 12, 5, 2), ('recon_20_5', 16, 20, 5)):
+        q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        w, v = q[:, :d].copy(), q[:, d:].copy()
+        c = spd_points(rng, 1, D - d, max_cond=1e9)[0]
+        k = rng.standard_normal((d, D - d))
+        k = 0.7 * k / np.linalg.norm(k, 2)
+        y = spd_points(rng, n, d)
+        x = ref.nested_spd_utils.projection_from_nested_spd_to_spd(
+            torch.from_numpy(y), torch.from_numpy(w), torch.from_numpy(v), torch.from_numpy(c), torch.from_numpy(k))
+        out[name + '_w'], out[name + '_v'], out[name + '_c'], out[name + '_k'] = w, v, c, k
+        out[name + '_y'], out[name + '_x'] = y, x.numpy()
 
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)

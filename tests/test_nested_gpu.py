@@ -138,3 +138,107 @@ def test_nested_sphere_kernel_vs_oracle():
         got2 = k.forward(torch.from_numpy(x1), torch.from_numpy(x2)).numpy()
     m2 = ref2 >= 1e-6
     assert np.all(np.abs(got2 - ref2)[m2] <= 1e-5 * ref2[m2])
+
+
+# ---- reconstruction maps -------------------------------------------------------------------------
+
+@pytest.mark.parametrize('name,D,dl', [('nsph_5_3', 5, 3), ('nsph_6_2', 6, 2)])
+def test_nested_sphere_chain_and_reconstruction_golden(golden, name, D, dl):
+    # nested_spheres_utils.py:13-67, :117-147, :149-213 against the reference's own outputs
+    axes = [torch.from_numpy(golden[name + '_axis%d' % lvl]) for lvl in range(D - dl)]
+    r = float(golden[name + '_r'])
+    dists = [torch.tensor([[r]], dtype=torch.float64)] * len(axes)
+    x = torch.from_numpy(golden[name + '_x'])
+    down = nm.projection_from_sphere_to_subsphere(x, axes, dists)
+    assert len(down) == D - dl + 1 and down[0] is x
+    for lvl in range(D - dl):
+        assert down[lvl + 1].dtype == torch.float64 and not down[lvl + 1].is_cuda
+        np.testing.assert_allclose(down[lvl + 1].numpy(), golden[name + '_y%d' % lvl], rtol=0, atol=1e-12)
+    one = nm.projection_from_sphere_to_next_subsphere(x, axes[0], dists[0])
+    np.testing.assert_allclose(one.numpy(), golden[name + '_y0'], rtol=0, atol=1e-12)
+    ns = nm.projection_from_sphere_to_nested_sphere(x, axes[0], dists[0])
+    np.testing.assert_allclose(ns.numpy(), golden[name + '_ns0'], rtol=0, atol=1e-12)
+    y_low = torch.from_numpy(golden[name + '_y%d' % (D - dl - 1)])
+    ups = nm.projection_from_subsphere_to_sphere(y_low, axes, dists)
+    assert len(ups) == D - dl + 1
+    for lvl in range(D - dl):
+        np.testing.assert_allclose(ups[lvl + 1].numpy(), golden[name + '_up%d' % lvl], rtol=0, atol=1e-12)
+    nxt = nm.projection_from_subsphere_to_next_sphere(y_low, axes[-1], dists[-1])
+    np.testing.assert_allclose(nxt.numpy(), golden[name + '_up0'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('D,dl,n', [(3, 2, 1), (8, 3, 1000), (20, 5, 4097), (64, 60, 33)])
+def test_nested_sphere_round_trip_vs_oracle(D, dl, n):
+    # projecting the reconstruction returns the latent points (the projection is a left inverse up to the 1e-6
+    # regularisers of nested_spheres_utils.py:58,107,112); both directions against the oracle on ragged sizes
+    from oracle import nested_sphere as ons
+    from oracle import sphere as osph
+    rng = np.random.default_rng(D * 10 + dl)
+    axes = [torch.from_numpy(osph.rand(rng, 1, k)) for k in range(D, dl, -1)]
+    dists = [torch.tensor([[0.9 + 0.1 * i]], dtype=torch.float64) for i in range(len(axes))]
+    y = torch.from_numpy(osph.rand(rng, n, dl))
+    ups = ops.nested_sphere_reconstruct(y, axes, dists)
+    ref = ons.projection_from_subsphere_to_sphere(y, axes, [float(r) for r in dists])
+    for got, want in zip(ups, ref[1:]):
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(ups[-1].cpu().numpy(), axis=-1), 1.0, atol=1e-12)
+    back = ops.nested_sphere_chain(ups[-1], axes, dists)
+    ref_back = ons.projection_from_sphere_to_subsphere(ups[-1].cpu(), axes, [float(r) for r in dists])
+    for got, want in zip(back, ref_back[1:]):
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=0, atol=1e-11)
+    np.testing.assert_allclose(back[-1].cpu().numpy(), y.numpy(), rtol=0, atol=2e-5 * (D - dl))
+    np.testing.assert_array_equal(ops.nested_sphere_project(ups[-1], axes, dists).cpu().numpy(),
+                                  back[-1].cpu().numpy())
+
+
+@pytest.mark.parametrize('d', [3, 5])
+def test_sqrtm_golden(golden, d):
+    y = ops.spd_sqrtm(torch.from_numpy(golden['sqrtm%d_x' % d])).cpu().numpy()
+    np.testing.assert_allclose(y, golden['sqrtm%d_y' % d], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('d', [1, 2, 4, 6, 7, 8])
+def test_sqrtm_squares_back(d):
+    from oracle import spd as ospd
+    x = ospd.spd_sample(np.random.default_rng(d), 300, d)
+    y = ops.spd_sqrtm(torch.from_numpy(x)).cpu().numpy()
+    np.testing.assert_allclose(y @ y, x, rtol=0, atol=1e-12 * np.abs(x).max())
+    np.testing.assert_allclose(y, np.swapaxes(y, -1, -2), rtol=0, atol=1e-13)
+    bad = x.copy()
+    bad[7] = -bad[7]
+    out = ops.spd_sqrtm(torch.from_numpy(bad)).cpu().numpy()
+    assert np.isnan(out[7]).all() and not np.isnan(out[6]).any()
+
+
+@pytest.mark.parametrize('name', ['recon_5_2', 'recon_20_5'])
+def test_nested_spd_reconstruction_golden(golden, name):
+    # nested_spd_utils.py:51-118 against the reference's own outputs, batch and single-matrix forms
+    w, v, c, k = (torch.from_numpy(golden[name + s]) for s in ('_w', '_v', '_c', '_k'))
+    y = torch.from_numpy(golden[name + '_y'])
+    x = nm.projection_from_nested_spd_to_spd(y, w, v, c, k)
+    assert x.dtype == torch.float64 and not x.is_cuda and tuple(x.shape) == golden[name + '_x'].shape
+    scale = np.abs(golden[name + '_x']).max()
+    np.testing.assert_allclose(x.numpy(), golden[name + '_x'], rtol=0, atol=1e-11 * scale)
+    x0 = nm.projection_from_nested_spd_to_spd(y[0], w, v, c, k)
+    np.testing.assert_allclose(x0.numpy(), golden[name + '_x'][0], rtol=0, atol=1e-11 * scale)
+
+
+@pytest.mark.parametrize('D,d,n', [(20, 5, 3000), (9, 8, 257), (32, 3, 100), (2, 1, 5)])
+def test_nested_spd_reconstruction_right_inverse(D, d, n):
+    # W^T X W = Y (the reconstruction is a right inverse of P1), X positive definite for |K| < 1, oracle on a sample
+    from oracle import spd as ospd
+    rng = np.random.default_rng(D + d)
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    w, v = q[:, :d].copy(), q[:, d:].copy()
+    c = ospd.spd_sample(rng, 1, D - d)[0]
+    k = rng.standard_normal((d, D - d))
+    k = 0.9 * k / np.linalg.norm(k, 2)
+    y = ospd.spd_sample(rng, n, d)
+    rec = nm.NestedSpdReconstruction(torch.from_numpy(w), torch.from_numpy(v), torch.from_numpy(c), torch.from_numpy(k))
+    x = rec(torch.from_numpy(y)).cpu().numpy()
+    ref = onest.projection_from_nested_spd_to_spd(y[:40], w, v, c, k).numpy()
+    np.testing.assert_allclose(x[:40], ref, rtol=0, atol=1e-11 * np.abs(ref).max())
+    np.testing.assert_allclose(np.swapaxes(w, 0, 1) @ x @ w, y, rtol=0, atol=1e-11 * np.abs(y).max())
+    assert np.linalg.eigvalsh(0.5 * (x + np.swapaxes(x, -1, -2))).min() > 0
+    with pytest.raises(ops.NotPositiveDefiniteError):
+        nm.NestedSpdReconstruction(torch.from_numpy(w), torch.from_numpy(v), torch.from_numpy(-c), torch.from_numpy(k))

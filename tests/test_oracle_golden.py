@@ -174,3 +174,40 @@ def test_nested_sphere_projection_matches_reference(golden, name, D, dl):
     for lvl in range(D - dl):
         np.testing.assert_allclose(levels[lvl + 1].numpy(), golden[name + '_y%d' % lvl], rtol=0, atol=1e-14)
     np.testing.assert_allclose(np.linalg.norm(levels[-1].numpy(), axis=-1), 1.0, atol=2e-6)   # the 1e-6 of :112
+
+
+@pytest.mark.parametrize('name,D,dl', [('nsph_5_3', 5, 3), ('nsph_6_2', 6, 2)])
+def test_nested_sphere_reconstruction_matches_reference(golden, name, D, dl):
+    # nested_spheres_utils.py:13-67 and :149-213 run from the reference's own code
+    from oracle import nested_sphere as ons
+    axes = [torch.from_numpy(golden[name + '_axis%d' % lvl]) for lvl in range(D - dl)]
+    r = float(golden[name + '_r'])
+    ns = ons.projection_to_nested_sphere(golden[name + '_x'], axes[0], r)
+    np.testing.assert_allclose(ns.numpy(), golden[name + '_ns0'], rtol=0, atol=1e-14)
+    ups = ons.projection_from_subsphere_to_sphere(golden[name + '_y%d' % (D - dl - 1)], axes, [r] * len(axes))
+    for lvl in range(D - dl):
+        np.testing.assert_allclose(ups[lvl + 1].numpy(), golden[name + '_up%d' % lvl], rtol=0, atol=1e-14)
+    # the reconstruction lands on the nested sphere of every level: distance r to that level's axis
+    top = ups[-1].numpy()
+    np.testing.assert_allclose(np.arccos(np.clip(top @ axes[0].numpy().reshape(-1), -1, 1)), r, atol=1e-9)
+
+
+@pytest.mark.parametrize('d', [3, 5])
+def test_sqrtm_matches_reference(golden, d):
+    from oracle import spd as ospd_
+    y = ospd_.sqrtm(torch.from_numpy(golden['sqrtm%d_x' % d])).numpy()
+    np.testing.assert_allclose(y, golden['sqrtm%d_y' % d], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(y @ y, golden['sqrtm%d_x' % d], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['recon_5_2', 'recon_20_5'])
+def test_nested_spd_reconstruction_matches_reference(golden, name):
+    # nested_spd_utils.py:51-118 run from the reference's own code
+    from oracle import nested as onest
+    w, v, c, k = (golden[name + s] for s in ('_w', '_v', '_c', '_k'))
+    x = onest.projection_from_nested_spd_to_spd(golden[name + '_y'], w, v, c, k).numpy()
+    np.testing.assert_allclose(x, golden[name + '_x'], rtol=0, atol=1e-11)
+    # right inverse of the projection: W^T X W = Y; and X is positive definite (|K| < 1)
+    back = onest.projection_from_spd_to_nested_spd(x, w).numpy()
+    np.testing.assert_allclose(back, golden[name + '_y'], rtol=0, atol=1e-11)
+    assert np.linalg.eigvalsh(0.5 * (x + np.swapaxes(x, -1, -2))).min() > 0
