@@ -25,4 +25,7 @@ from .manifolds import Sphere, PositiveDefinite  # noqa: F401
 from .manifold_optimization import (ConjugateGradient, ExpectedImprovement, ManifoldGP,  # noqa: F401
                                     gen_batch_initial_conditions_manifold, gen_candidates_manifold,
                                     get_best_candidates, joint_optimize_manifold)
-from .nested_mappings import NestedSpdProjection, projection_from_spd_to_nested_spd  # noqa: F401
+from .nested_mappings import (NestedSpdProjection, NestedSpdReconstruction,  # noqa: F401
+                              projection_from_spd_to_nested_spd, projection_from_nested_spd_to_spd)
+from .gp_fit import fit_gpytorch_model, ExactMarginalLogLikelihood  # noqa: F401
+from ._compat import GammaPrior  # noqa: F401

@@ -145,3 +145,19 @@ except Exception:  # gpytorch absent: minimal equivalents
             k = self.base_kernel.forward(x1, x2, diag=diag, **params)
             s = self.outputscale
             return k * s.to(k).view(*s.shape, 1, 1) if s.dim() > 0 else k * s.to(k)
+
+
+class GammaPrior:
+    """Gamma(concentration, rate) prior with the two attributes and the ``log_prob`` the reference's model set-up uses
+    (``gpytorch.priors.torch_priors.GammaPrior(2.0, 0.15)``, gabo_sphere.py:131-137).  gpytorch's own class is accepted
+    wherever this one is (duck-typed on ``concentration`` / ``rate``)."""
+
+    def __init__(self, concentration, rate):
+        self.concentration = torch.as_tensor(float(concentration))
+        self.rate = torch.as_tensor(float(rate))
+
+    def log_prob(self, x):
+        x = torch.as_tensor(x, dtype=torch.float64)
+        c, r = self.concentration.double(), self.rate.double()
+        return c * torch.log(r) + (c - 1.0) * torch.log(x) - r * x - torch.lgamma(c)
+

@@ -68,6 +68,7 @@ SIGNATURES = {
     'gabo_nested_spd_reconstruct_pack_size': (c_i64, [c_i32, c_i32]),
     'gabo_nested_spd_reconstruct_setup': (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     'gabo_nested_spd_reconstruct': (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    'gabo_gp_mll': (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
 

@@ -1,0 +1,187 @@
+// GP marginal log-likelihood, its gradient and the posterior factors, one CTA per hyper-parameter set.
+//
+// Replaces, for the models of the reference (botorch SingleTaskGP = constant mean + ScaleKernel(geodesic kernel) +
+// GaussianLikelihood; examples/bo_sphere/benchmark_examples/gabo_sphere.py:131-165), the arithmetic that
+// gpytorch.mlls.ExactMarginalLogLikelihood + torch.autograd perform on every objective evaluation of
+// botorch.fit_gpytorch_model (gabo_sphere.py:162), and the (K + noise I)^-1 / alpha factors the acquisition needs:
+//     K_theta = s exp(-beta Dm) + noise I            Dm = d^2 (Gaussian kernels) or d (Laplace kernels), n x n
+//     ll      = -1/2 (r^T alpha + log det K_theta + n log 2 pi),    r = y - m,  alpha = K_theta^-1 r
+//     dll/dp  = 1/2 tr((alpha alpha^T - K_theta^-1) dK/dp),  p in {beta, s, noise};   dll/dm = 1^T alpha
+// The distance matrix is computed once per fit by the Gram kernels; every evaluation after that is this one launch.
+// fp64 throughout; K_theta, its Cholesky factor L (lower triangle) and L^-1 (stored transposed in the strict upper
+// triangle) share one n x (n+1) shared-memory tile, n <= 128.
+#include "common.cuh"
+
+namespace gabo {
+namespace {
+
+constexpr int kGpThreads = 256;
+constexpr int kMaxGpTrain = 128;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < kGpThreads / 32; ++i) t += red[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(kGpThreads)
+gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__ y, const double* __restrict__ theta,
+              double* __restrict__ out_ll, double* __restrict__ out_grad, double* __restrict__ out_alpha,
+              double* __restrict__ out_kinv, int* __restrict__ flags) {
+    extern __shared__ double sm[];
+    const int ld = n + 1;                                   // odd row stride in 8-byte words: conflict-free columns
+    double* A = sm;                                         // n x ld
+    double* vec = A + n * ld;                               // n : residual -> z -> alpha
+    double* dinv = vec + n;                                 // n : 1 / L_kk
+    double* red = dinv + n;                                 // kGpThreads / 32
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const double beta = theta[b * 4 + 0], s = theta[b * 4 + 1], noise = theta[b * 4 + 2], mean = theta[b * 4 + 3];
+    if (tid == 0) bad = 0;
+    for (int e = tid; e < n * n; e += kGpThreads) {
+        const int i = e / n, j = e % n;
+        if (j <= i) A[i * ld + j] = fma(s, exp(-beta * dmat[e]), (i == j) ? noise : 0.0);
+    }
+    for (int i = tid; i < n; i += kGpThreads) vec[i] = y[i] - mean;
+    __syncthreads();
+    // --- Cholesky, right-looking, in place (lower triangle) ---
+    double logdet = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const double piv = A[k * ld + k];
+        if (!(piv > 0.0)) {
+            if (tid == 0) bad = 1;
+            break;                                          // uniform: every thread reads the same pivot
+        }
+        const double lkk = sqrt(piv), inv = 1.0 / lkk;
+        logdet += log(piv);                                 // = 2 log L_kk
+        __syncthreads();
+        if (tid == 0) {
+            A[k * ld + k] = lkk;
+            dinv[k] = inv;
+        }
+        for (int i = k + 1 + tid; i < n; i += kGpThreads) A[i * ld + k] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: rows i > k, columns k < j <= i
+        const int m = n - k - 1;
+        for (int e = tid; e < m * m; e += kGpThreads) {
+            const int i = k + 1 + e / m, j = k + 1 + e % m;
+            if (j <= i) A[i * ld + j] = fma(-A[i * ld + k], A[j * ld + k], A[i * ld + j]);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (bad) {                                              // not positive definite: NaN outputs + flag
+        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+        if (tid == 0) {
+            out_ll[b] = nanv;
+            flags[b] = 1;
+        }
+        if (out_grad && tid < 4) out_grad[b * 4 + tid] = nanv;
+        if (out_alpha) for (int i = tid; i < n; i += kGpThreads) out_alpha[b * n + i] = nanv;
+        if (out_kinv) for (int e = tid; e < n * n; e += kGpThreads) out_kinv[b * n * n + e] = nanv;
+        return;
+    }
+    // --- L z = r (column-oriented forward substitution), quad = z^T z ---
+    for (int k = 0; k < n; ++k) {
+        const double zk = vec[k] * dinv[k];
+        __syncthreads();
+        if (tid == 0) vec[k] = zk;
+        for (int i = k + 1 + tid; i < n; i += kGpThreads) vec[i] = fma(-A[i * ld + k], zk, vec[i]);
+        __syncthreads();
+    }
+    double quad = 0.0;
+    for (int i = tid; i < n; i += kGpThreads) quad = fma(vec[i], vec[i], quad);
+    quad = block_sum(quad, red);
+    // --- L^T alpha = z (backward substitution) ---
+    for (int k = n - 1; k >= 0; --k) {
+        const double ak = vec[k] * dinv[k];
+        __syncthreads();
+        if (tid == 0) vec[k] = ak;
+        for (int i = tid; i < k; i += kGpThreads) vec[i] = fma(-A[k * ld + i], ak, vec[i]);
+        __syncthreads();
+    }
+    const double ll = -0.5 * (quad + logdet + n * 1.8378770664093453);   // log(2 pi)
+    if (tid == 0) {
+        out_ll[b] = ll;
+        flags[b] = 0;
+    }
+    if (out_alpha) for (int i = tid; i < n; i += kGpThreads) out_alpha[b * n + i] = vec[i];
+    if (!out_grad && !out_kinv) return;
+    // --- X = L^-1, one column per thread, stored transposed in the strict upper triangle: A[j][i] = X_ij, i > j ---
+    for (int j = tid; j < n; j += kGpThreads) {
+        for (int i = j + 1; i < n; ++i) {
+            double acc = A[i * ld + j] * dinv[j];           // L_ij X_jj
+            for (int k = j + 1; k < i; ++k) acc = fma(A[i * ld + k], A[j * ld + k], acc);
+            A[j * ld + i] = -acc * dinv[i];
+        }
+    }
+    __syncthreads();
+    // --- K^-1 = X^T X entry by entry; gradient sums over the lower triangle ---
+    double gb = 0.0, gs = 0.0, gn = 0.0, gm = 0.0;
+    const int tri = n * (n + 1) / 2;
+    for (int e = tid; e < tri; e += kGpThreads) {
+        // e -> (i, j), j <= i
+        int i = static_cast<int>((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        while (i * (i + 1) / 2 > e) --i;
+        const int j = e - i * (i + 1) / 2;
+        // sum_{k >= i} X_ki X_kj with X_ii = dinv[i]
+        double kin = dinv[i] * ((i == j) ? dinv[i] : A[j * ld + i]);
+        for (int k = i + 1; k < n; ++k) kin = fma(A[i * ld + k], A[j * ld + k], kin);
+        if (out_kinv) {
+            out_kinv[b * n * n + i * n + j] = kin;
+            out_kinv[b * n * n + j * n + i] = kin;
+        }
+        const double w = fma(vec[i], vec[j], -kin);
+        const double dm = dmat[i * n + j];
+        const double base = exp(-beta * dm);
+        const double mult = (i == j) ? 0.5 : 1.0;           // 1/2 tr(.) over both triangles
+        gs = fma(mult * w, base, gs);
+        gb = fma(mult * w, -s * dm * base, gb);
+        if (i == j) gn = fma(0.5, w, gn);
+    }
+    for (int i = tid; i < n; i += kGpThreads) gm += vec[i];
+    if (out_grad) {
+        gb = block_sum(gb, red);
+        gs = block_sum(gs, red);
+        gn = block_sum(gn, red);
+        gm = block_sum(gm, red);
+        if (tid == 0) {
+            out_grad[b * 4 + 0] = gb;
+            out_grad[b * 4 + 1] = gs;
+            out_grad[b * 4 + 2] = gn;
+            out_grad[b * 4 + 3] = gm;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace gabo
+
+using namespace gabo;
+
+extern "C" int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const double* theta, int64_t batch,
+                           double* out_ll, double* out_grad, double* out_alpha, double* out_kinv, int* flags,
+                           void* stream) {
+    GABO_REQUIRE(n >= 0 && batch >= 0, GABO_E_ARG, "gabo_gp_mll: negative size");
+    GABO_REQUIRE(n >= 1 && n <= kMaxGpTrain, GABO_E_ARG, "gabo_gp_mll: n=%lld outside [1, %d]",
+                 static_cast<long long>(n), kMaxGpTrain);
+    if (batch == 0) return GABO_OK;
+    GABO_REQUIRE(dmat && y && theta && out_ll && flags, GABO_E_ARG, "gabo_gp_mll: null pointer");
+    const size_t smem = sizeof(double) * (static_cast<size_t>(n) * (n + 1) + 2 * n + kGpThreads / 32);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(gp_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(double) * (kMaxGpTrain * (kMaxGpTrain + 1) + 2 * kMaxGpTrain + 8)));
+        configured = true;
+    }
+    gp_mll_kernel<<<static_cast<unsigned>(batch), kGpThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        dmat, static_cast<int>(n), y, theta, out_ll, out_grad, out_alpha, out_kinv, flags);
+    return check_launch("gp_mll_kernel");
+}

@@ -89,14 +89,21 @@ def _manifold_kind(manifold):
 
 class ManifoldGP:
     """Exact GP with constant mean over a geodesic kernel: the slice of botorch ``SingleTaskGP`` the acquisition needs
-    (reference call sites gabo_sphere.py:131-165).  Hyper-parameters are given, not fitted (GP fitting is SURVEY 8f)."""
+    (reference call sites gabo_sphere.py:131-165).  Hyper-parameters are given, or fitted in place by ``gp_fit.fit_gpytorch_model``."""
 
-    def __init__(self, train_x, train_y, covar_module, noise=1e-2, mean=None):
+    def __init__(self, train_x, train_y, covar_module, noise=1e-2, mean=None, noise_prior=None, noise_min=1e-8):
         self.train_inputs = (torch.as_tensor(train_x, dtype=torch.float64),)
         self.train_targets = torch.as_tensor(train_y, dtype=torch.float64).reshape(-1)
         self.covar_module = covar_module
         self.noise = float(noise)
         self.mean = float(self.train_targets.mean()) if mean is None else float(mean)
+        # used by gp_fit.fit_gpytorch_model only: (concentration, rate) of the Gamma prior on the noise and the lower
+        # bound of its constraint (GaussianLikelihood(noise_prior=..., noise_constraint=GreaterThan(1e-8)))
+        if noise_prior is not None and not isinstance(noise_prior, tuple):
+            noise_prior = (float(noise_prior.concentration), float(noise_prior.rate))
+        self.noise_prior = noise_prior
+        self.noise_min = float(noise_min)
+        self.likelihood = None
 
 
 def _unwrap_model(model):

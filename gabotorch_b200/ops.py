@@ -503,6 +503,27 @@ def acq_rcg(gp, x0, maxiter=1000, mingradnorm=1e-6, minstepsize=1e-10, ls_maxite
     return x, val, iters, reason
 
 
+def gp_mll(dmat, y, theta, want_grad=True, want_factors=False):
+    """log N(y | m, s exp(-beta dmat) + noise I) for a batch of theta = (beta, s, noise, m) rows (``gabo_gp_mll``).
+    Returns (ll (B,), grad (B, 4) or None, alpha (B, n) or None, kinv (B, n, n) or None, flags (B,) int32), on device."""
+    lib = _lib.load()
+    dmat = to_dev64(dmat)
+    y = to_dev64(y).reshape(-1)
+    theta = to_dev64(theta).reshape(-1, 4)
+    n, B = y.shape[0], theta.shape[0]
+    if tuple(dmat.shape) != (n, n):
+        raise ValueError('dmat must be (n, n) with n = len(y)')
+    dev = dmat.device
+    ll = torch.empty(B, dtype=torch.float64, device=dev)
+    grad = torch.empty(B, 4, dtype=torch.float64, device=dev) if want_grad else None
+    alpha = torch.empty(B, n, dtype=torch.float64, device=dev) if want_factors else None
+    kinv = torch.empty(B, n, n, dtype=torch.float64, device=dev) if want_factors else None
+    flags = torch.zeros(B, dtype=torch.int32, device=dev)
+    _lib.check(lib.gabo_gp_mll(_p(dmat), n, _p(y), _p(theta), B, _p(ll), _p(grad), _p(alpha), _p(kinv), _p(flags),
+                               _lib.stream_ptr()), 'gabo_gp_mll')
+    return ll, grad, alpha, kinv, flags
+
+
 def argmax_records(values, gidx=None):
     """(slot, value) of the best record: highest value, lowest global index on ties, NaN = -inf."""
     lib = _lib.load()

@@ -243,6 +243,20 @@ int gabo_nested_spd_reconstruct_setup(const double* w, const double* v, const do
 int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt, int64_t n, int D, int d, const double* pack,
                                 double* x, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * GP hyper-parameter fit: the objective botorch.fit_gpytorch_model evaluates at every L-BFGS step
+ * (examples/bo_sphere/benchmark_examples/gabo_sphere.py:131-165: SingleTaskGP = constant mean +
+ * ScaleKernel(geodesic kernel) + GaussianLikelihood under gpytorch.mlls.ExactMarginalLogLikelihood), for `batch`
+ * hyper-parameter sets at once, one CTA each:
+ *   K = s exp(-beta dmat) + noise I,  ll = log N(y | m 1, K),  theta[b] = {beta, s, noise, m}.
+ * dmat: n x n (squared geodesic distances for the Gaussian kernels, distances for the Laplace kernels), y: n.
+ * out_ll: batch (NOT divided by n, priors not included); out_grad: batch x 4 = d ll / d{beta, s, noise, m} (nullable);
+ * out_alpha: batch x n = K^-1 (y - m) and out_kinv: batch x n x n = K^-1 (nullable; what gabo_gp_desc consumes);
+ * flags: batch ints, 1 where K is not positive definite (outputs NaN).  fp64, n <= 128.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const double* theta, int64_t batch, double* out_ll,
+                double* out_grad, double* out_alpha, double* out_kinv, int* flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,3 +145,46 @@ def ei_torch(gp, x):
     u = (gp.best_f - mu) / sigma
     normal = torch.distributions.Normal(torch.zeros((), dtype=x.dtype), torch.ones((), dtype=x.dtype))
     return sigma * (torch.exp(normal.log_prob(u)) + u * normal.cdf(u))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Marginal likelihood (gpytorch ExactMarginalLogLikelihood; botorch fit_gpytorch_model).  PARITY UNPINNED (third-party);
+# restated from the published definitions:  ll = log N(y | m 1, s exp(-beta Dm) + noise I);  gpytorch divides the sum
+# of ll and the log-priors by n (ExactMarginalLogLikelihood.forward), priors are evaluated on the TRANSFORMED values.
+# ----------------------------------------------------------------------------------------------------------------
+
+def exact_log_likelihood(dmat, y, theta):
+    """ll and its gradient w.r.t. theta = (beta, s, noise, m) by torch.autograd on torch.distributions."""
+    dmat = torch.as_tensor(dmat, dtype=torch.float64)
+    y = torch.as_tensor(y, dtype=torch.float64)
+    th = torch.as_tensor(theta, dtype=torch.float64).clone().requires_grad_(True)
+    n = y.shape[0]
+    k = th[1] * torch.exp(-th[0] * dmat) + th[2] * torch.eye(n, dtype=torch.float64)
+    k = 0.5 * (k + k.T)
+    dist = torch.distributions.MultivariateNormal(th[3] * torch.ones(n, dtype=torch.float64), covariance_matrix=k)
+    ll = dist.log_prob(y)
+    grad, = torch.autograd.grad(ll, th)
+    return float(ll.detach()), grad.numpy()
+
+
+def gamma_log_prob(x, concentration, rate):
+    """torch.distributions.Gamma(concentration, rate).log_prob(x) (gpytorch GammaPrior)."""
+    return (concentration * math.log(rate) + (concentration - 1.0) * math.log(x) - rate * x
+            - math.lgamma(concentration))
+
+
+def softplus(r):
+    return math.log1p(math.exp(-abs(r))) + max(r, 0.0)
+
+
+def mll_objective(dmat, y, raw, beta_min, noise_min=1e-8, outputscale_prior=None, noise_prior=None, beta_prior=None):
+    """-(ll + sum of log-priors) / n at raw = (raw_beta, raw_outputscale, raw_noise, mean): what fit_gpytorch_model
+    hands to scipy (constraints GreaterThan(beta_min) / Positive / GreaterThan(noise_min) as softplus transforms)."""
+    beta = beta_min + softplus(raw[0])
+    s = softplus(raw[1])
+    noise = noise_min + softplus(raw[2])
+    ll, _ = exact_log_likelihood(dmat, y, (beta, s, noise, raw[3]))
+    for val, prior in ((s, outputscale_prior), (noise, noise_prior), (beta, beta_prior)):
+        if prior is not None:
+            ll += gamma_log_prob(val, *prior)
+    return -ll / len(y)

@@ -73,6 +73,9 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.gabo_nested_spd_reconstruct_pack_size(5, 5) == 0
     assert lib.gabo_nested_spd_reconstruct(fake, fake, 4, 40, 5, fake, fake, null) == -1      # D > 32
     assert lib.gabo_nested_spd_reconstruct_setup(fake, fake, fake, fake, 5, 5, fake, fake, null) == -1
+    assert lib.gabo_gp_mll(fake, 129, fake, fake, 1, fake, null, null, null, fake, null) == -1   # n > 128
+    assert lib.gabo_gp_mll(null, 8, null, null, 1, null, null, null, null, null, null) == -1
+    assert lib.gabo_gp_mll(fake, 8, fake, fake, 0, fake, null, null, null, fake, null) == 0      # empty batch
 
 
 def test_product_path_has_no_cpu_fallback():

@@ -131,3 +131,42 @@ def test_allgather_records_world_size_2_gloo():
     # single-process answer on the same value array: highest value, lowest global index on ties, NaN loses
     assert gi == 1 and v == 0.9 and c == [1.25, 1.25, 1.25]
     assert allg == [1, 6] and allv == [0.9, 0.9]
+
+
+def test_gp_fit_transforms_priors_and_oracle_likelihood():
+    # host side of gp_fit (no device call): gpytorch's softplus constraints round-trip, Gamma log-priors match
+    # torch.distributions, and the oracle's likelihood equals the closed form -1/2 (r^T K^-1 r + log det K + n log 2 pi)
+    import math
+    from gabotorch_b200 import gp_fit
+    from oracle import gp as ogp
+    obj = gp_fit.MarginalLogLikelihood.__new__(gp_fit.MarginalLogLikelihood)
+    obj.beta_min, obj.noise_min, obj.priors = 6.5, 1e-8, ((3.0, 2.0), (2.0, 0.15), (1.1, 0.05))
+    theta = (7.25, 0.4, 2.0, -0.3)
+    raw = obj.inverse_transform(theta)
+    np.testing.assert_allclose(obj.transform(raw), theta, rtol=1e-12)
+    assert abs(obj.transform([0.0, 0.0, 0.0, 1.0])[0] - (6.5 + math.log(2.0))) < 1e-15   # kernels_sphere.py:48-60
+    lp, dlp = obj._prior_terms(theta)
+    t64 = lambda v: torch.tensor(v, dtype=torch.float64)  # noqa: E731
+    ref = sum(float(torch.distributions.Gamma(t64(c), t64(r)).log_prob(t64(v)))
+              for (c, r), v in zip(obj.priors, theta[:3]))
+    assert abs(lp - ref) < 1e-12
+    assert abs(ogp.gamma_log_prob(0.4, 2.0, 0.15)
+               - float(torch.distributions.Gamma(t64(2.0), t64(0.15)).log_prob(t64(0.4)))) < 1e-12
+    for i, (c, r) in enumerate(obj.priors):
+        assert abs(dlp[i] - ((c - 1.0) / theta[i] - r)) < 1e-15
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((9, 4))
+    x /= np.linalg.norm(x, axis=-1, keepdims=True)
+    dm = np.arccos(np.clip(x @ x.T, -1, 1)) ** 2
+    y = rng.standard_normal(9)
+    th = (2.5, 0.8, 0.05, 0.1)
+    ll, grad = ogp.exact_log_likelihood(dm, y, th)
+    k = th[1] * np.exp(-th[0] * dm) + th[2] * np.eye(9)
+    r = y - th[3]
+    closed = -0.5 * (r @ np.linalg.solve(k, r) + np.linalg.slogdet(k)[1] + 9 * math.log(2 * math.pi))
+    assert abs(ll - closed) < 1e-10
+    alpha = np.linalg.solve(k, r)
+    w = np.outer(alpha, alpha) - np.linalg.inv(k)
+    base = np.exp(-th[0] * dm)
+    np.testing.assert_allclose(grad, [0.5 * np.sum(w * (-th[1] * dm * base)), 0.5 * np.sum(w * base),
+                                      0.5 * np.trace(w), alpha.sum()], rtol=1e-8, atol=1e-10)
