@@ -32,6 +32,12 @@ class RcgOpts(ctypes.Structure):
                 ('minstepsize', c_f64), ('contraction', c_f64), ('suff_decr', c_f64), ('initial_stepsize', c_f64)]
 
 
+class RtrOpts(ctypes.Structure):
+    _fields_ = [('maxiter', ctypes.c_int32), ('mininner', ctypes.c_int32), ('maxinner', ctypes.c_int32),
+                ('reserved', ctypes.c_int32), ('mingradnorm', c_f64), ('kappa', c_f64), ('theta', c_f64),
+                ('rho_prime', c_f64), ('rho_regularization', c_f64), ('delta_bar', c_f64), ('delta0', c_f64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/gabo_b200.h declares (tests/test_abi.py checks it)
 SIGNATURES = {
     'gabo_version': (c_i32, []),
@@ -55,6 +61,8 @@ SIGNATURES = {
     'gabo_spd_scalar': (c_i32, [c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_ei_eval': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     'gabo_acq_rcg': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, ctypes.POINTER(RcgOpts), c_ptr, c_ptr, c_ptr,
+                             c_ptr]),
+    'gabo_acq_rtr': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, ctypes.POINTER(RtrOpts), c_ptr, c_ptr, c_ptr,
                              c_ptr]),
     'gabo_argmax_records': (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     'gabo_nested_spd_project_f64': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),

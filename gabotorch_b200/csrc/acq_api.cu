@@ -1,4 +1,4 @@
-// C-ABI entry points of the acquisition path: gabo_ei_eval (A4), gabo_acq_rcg (A1), gabo_argmax_records (A3).
+// C-ABI entry points of the acquisition path: gabo_ei_eval (A4), gabo_acq_rcg / gabo_acq_rtr (A1), gabo_argmax_records (A3).
 #include "acq_common.cuh"
 
 namespace gabo {
@@ -129,6 +129,22 @@ extern "C" int gabo_acq_rcg(const gabo_gp_desc* gp, double* x, int64_t r, const 
     GABO_REQUIRE(opts->maxiter >= 1 && opts->ls_maxiter >= 0, GABO_E_ARG, "gabo_acq_rcg: bad iteration limits");
     GABO_REQUIRE(opts->contraction > 0.0 && opts->contraction < 1.0, GABO_E_ARG, "gabo_acq_rcg: bad contraction factor");
     return dispatch(gp, x, r, opts, value, nullptr, iters, reason, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gabo_acq_rtr(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rtr_opts* opts, double* value,
+                            int32_t* iters, int32_t* reason, void* stream) {
+    using namespace gabo;
+    const int rc = validate_gp(gp, "gabo_acq_rtr");
+    if (rc != GABO_OK) return rc;
+    GABO_REQUIRE(r >= 0, GABO_E_ARG, "gabo_acq_rtr: negative size");
+    if (r == 0) return GABO_OK;
+    GABO_REQUIRE(x && value && opts, GABO_E_ARG, "gabo_acq_rtr: null pointer");
+    GABO_REQUIRE(opts->maxiter >= 1 && opts->mininner >= 0, GABO_E_ARG, "gabo_acq_rtr: bad iteration limits");
+    GABO_REQUIRE(opts->kappa > 0.0 && opts->rho_prime >= 0.0 && opts->rho_prime < 0.25, GABO_E_ARG,
+                 "gabo_acq_rtr: need kappa > 0 and 0 <= rho_prime < 1/4");
+    GABO_REQUIRE(gp->manifold == GABO_SPHERE, GABO_E_UNSUPPORTED,
+                 "gabo_acq_rtr: the trust-region solver is implemented for the sphere (use gabo_acq_rcg on SPD)");
+    return launch_rtr_sphere(gp, x, r, opts, value, iters, reason, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gabo_argmax_records(const double* values, const int64_t* gidx, int64_t n, int64_t* out_slot,

@@ -28,6 +28,11 @@ struct RcgParams {
     double mingradnorm, minstepsize, contraction, suff_decr, initial_stepsize;
 };
 
+struct RtrParams {
+    int maxiter, mininner, maxinner;
+    double mingradnorm, kappa, theta, rho_prime, rho_regularization, delta_bar, delta0, fd_eps;
+};
+
 template <typename T>
 struct M;
 template <>
@@ -114,6 +119,9 @@ constexpr int kAcqWarps = 4;  // restarts per CTA
 
 int launch_acq_sphere(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* opts, double* value,
                       double* grad, int32_t* iters, int32_t* reason, cudaStream_t stream);
+
+int launch_rtr_sphere(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rtr_opts* opts, double* value,
+                      int32_t* iters, int32_t* reason, cudaStream_t stream);
 
 template <int d>
 int launch_acq_spd(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* opts, double* value,

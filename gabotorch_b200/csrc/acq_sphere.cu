@@ -645,6 +645,199 @@ __global__ void __launch_bounds__(kSpec * 32)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Trust-region acquisition solver, ONE WARP PER RESTART.  Restates the reference's own
+// TrustRegions.solve / _truncated_conjugate_gradient (BoManifolds/manifold_optimization/robust_trust_regions.py:116-352,
+// :410-520, use_rand=False, identity preconditioner, the d_Hd != 0 guard of :461-465) with the finite-difference
+// Hessian of approximate_hessian.py:11-62 (H[a] = (T_{x1->x} grad f(x1) - grad f(x)) / c, x1 = R_x(c a),
+// c = 2^-14 / |a|) -- the combination gen_candidates_manifold builds for approx_hessian=True
+// (manifold_optimize.py:199-200).  Sphere operations as in pymanopt: R_x(u) = (x + u) / |x + u|, T_{x1->x} = P_x.
+// Every vector of the solver (iterate, gradient, eta, H eta, residual, search direction, H delta) is replicated in
+// the registers of all 32 lanes, as in the CG kernel; lanes differ only in the training points they own inside
+// SphereEval, so the whole tCG recurrence is warp-uniform scalar code and one Hessian-vector product costs one
+// cost + gradient evaluation.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Eps;
+template <>
+struct Eps<float> {
+    static __device__ __forceinline__ float value() { return 1.1920929e-7f; }
+};
+template <>
+struct Eps<double> {
+    static __device__ __forceinline__ double value() { return 2.220446049250313e-16; }   // np.spacing(1)
+};
+
+template <typename T, int DP, int NCH>
+__global__ void __launch_bounds__(kAcqWarps * 32)
+    sphere_rtr_kernel(GpParams gp, RtrParams opt, double* __restrict__ x_io, int64_t r, double* __restrict__ value,
+                      int32_t* __restrict__ iters, int32_t* __restrict__ reason) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = gp.n, D = gp.dim;
+    const int npad = (n + 3) & ~3;
+    SmemCarver cv;
+    T* Minv = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * npad * n));
+    const int ksz = SphereEval<T, DP, NCH>::ksh_size(n);
+    T* kbase = reinterpret_cast<T*>(smem_raw + cv.take(sizeof(T) * kAcqWarps * ksz));
+    for (int e = threadIdx.x; e < npad * n; e += blockDim.x) Minv[e] = (e < n * n) ? static_cast<T>(gp.minv[e]) : T(0);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t rid = static_cast<int64_t>(blockIdx.x) * kAcqWarps + warp;
+    if (rid >= r) return;
+    using E = SphereEval<T, DP, NCH>;
+    E ev;
+    ev.load(gp, lane, Minv, kbase + warp * ksz);
+    const T mingrad = static_cast<T>(opt.mingradnorm), kappa = static_cast<T>(opt.kappa);
+    const T theta = static_cast<T>(opt.theta), rho_prime = static_cast<T>(opt.rho_prime);
+    const T delta_bar = static_cast<T>(opt.delta_bar), fd_eps = static_cast<T>(opt.fd_eps);
+    const T rho_scale = Eps<T>::value() * static_cast<T>(opt.rho_regularization);
+
+    T xv[DP], g[DP], eta[DP], heta[DP], rv[DP], dl[DP], hd[DP], xt[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) xv[k] = (k < D) ? static_cast<T>(x_io[rid * D + k]) : T(0);
+    T fx = ev.cost(xv, gp);
+    ev.grad(xv, g);
+    T norm_grad = M<T>::sqrt_(E::dot(g, g));
+    T radius = static_cast<T>(opt.delta0);
+    int it = 0, why = 0;
+
+    while (true) {
+        // ---- truncated CG on the model m(eta) = <g, eta> + 1/2 <eta, H eta> within |eta| <= radius ----
+        T r_r = E::dot(g, g);
+        const T norm_r0 = M<T>::sqrt_(r_r);
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            eta[k] = T(0);
+            heta[k] = T(0);
+            rv[k] = g[k];
+            dl[k] = -g[k];
+        }
+        T e_pe = T(0), z_r = r_r, d_pd = r_r, e_pd = T(0), model_value = T(0);
+        int stop = 4;   // MAX_INNER_ITER
+        const T radius2 = radius * radius;
+#pragma unroll 1
+        for (int j = 0; j < opt.maxinner; ++j) {
+            // H delta by finite differences of the gradient (approximate_hessian.py:30-62)
+            const T norm_a = M<T>::sqrt_(E::dot(dl, dl));
+            if (norm_a < T(1e-15)) {
+#pragma unroll
+                for (int k = 0; k < DP; ++k) hd[k] = T(0);
+            } else {
+                const T c = fd_eps / norm_a;
+                T s = T(0);
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    xt[k] = fma(c, dl[k], xv[k]);
+                    s = fma(xt[k], xt[k], s);
+                }
+                const T inv = T(1) / M<T>::sqrt_(s);
+#pragma unroll
+                for (int k = 0; k < DP; ++k) xt[k] *= inv;
+                ev.cost(xt, gp);
+                ev.grad(xt, hd);
+                const T t = E::dot(xv, hd);                       // transport x1 -> x: projection onto T_x
+#pragma unroll
+                for (int k = 0; k < DP; ++k) hd[k] = fma(-t, xv[k], hd[k]) / c - g[k] / c;
+            }
+            const T d_hd = E::dot(dl, hd);
+            T alpha = T(0), e_pe_new = e_pe;
+            if (d_hd != T(0)) {
+                alpha = z_r / d_hd;
+                e_pe_new = e_pe + T(2) * alpha * e_pd + alpha * alpha * d_pd;
+            }
+            if (d_hd <= T(0) || e_pe_new >= radius2) {
+                const T tau = (-e_pd + M<T>::sqrt_(e_pd * e_pd + d_pd * (radius2 - e_pe))) / d_pd;
+#pragma unroll
+                for (int k = 0; k < DP; ++k) {
+                    eta[k] = fma(tau, dl[k], eta[k]);
+                    heta[k] = fma(tau, hd[k], heta[k]);
+                }
+                stop = (d_hd <= T(0)) ? 0 : 1;                    // NEGATIVE_CURVATURE : EXCEEDED_TR
+                break;
+            }
+            e_pe = e_pe_new;
+            T m1 = T(0), m2 = T(0);
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                const T ne = fma(alpha, dl[k], eta[k]), nh = fma(alpha, hd[k], heta[k]);
+                m1 = fma(ne, g[k], m1);
+                m2 = fma(ne, nh, m2);
+            }
+            const T new_model_value = m1 + T(0.5) * m2;
+            if (new_model_value >= model_value) {
+                stop = 5;                                         // MODEL_INCREASED
+                break;
+            }
+            model_value = new_model_value;
+            r_r = T(0);
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+                eta[k] = fma(alpha, dl[k], eta[k]);
+                heta[k] = fma(alpha, hd[k], heta[k]);
+                rv[k] = fma(alpha, hd[k], rv[k]);
+                r_r = fma(rv[k], rv[k], r_r);
+            }
+            const T norm_r = M<T>::sqrt_(r_r);
+            const T pw = (theta == T(1)) ? norm_r0 : static_cast<T>(pow(static_cast<double>(norm_r0),
+                                                                        static_cast<double>(theta)));
+            if (j >= opt.mininner && norm_r <= norm_r0 * fmin(pw, kappa)) {
+                stop = (kappa < pw) ? 2 : 3;                      // REACHED_TARGET_LINEAR : SUPERLINEAR
+                break;
+            }
+            const T zold_rold = z_r;
+            z_r = r_r;
+            const T bcg = z_r / zold_rold;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) dl[k] = fma(bcg, dl[k], -rv[k]);
+            e_pd = bcg * (e_pd + alpha * d_pd);
+            d_pd = z_r + bcg * bcg * d_pd;
+        }
+        // ---- proposal, ratio of actual to predicted decrease, radius update (robust_trust_regions.py:225-300) ----
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+            xt[k] = xv[k] + eta[k];
+            s = fma(xt[k], xt[k], s);
+        }
+        const T inv = T(1) / M<T>::sqrt_(s);
+#pragma unroll
+        for (int k = 0; k < DP; ++k) xt[k] *= inv;
+        const T fx_prop = ev.cost(xt, gp);
+        const T rho_reg = fmax(T(1), fabs(fx)) * rho_scale;
+        const T rhonum = (fx - fx_prop) + rho_reg;
+        const T rhoden = (-E::dot(g, eta) - T(0.5) * E::dot(eta, heta)) + rho_reg;
+        const bool model_decreased = rhoden >= T(0);
+        const T rho = rhonum / rhoden;                            // NaN for 0/0, as np.nan in the reference
+        if (rho < T(0.25) || !model_decreased || rho != rho) {
+            radius = radius / T(4);
+        } else if (rho > T(0.75) && (stop == 0 || stop == 1)) {
+            radius = fmin(T(2) * radius, delta_bar);
+        }
+        if (model_decreased && rho > rho_prime) {
+#pragma unroll
+            for (int k = 0; k < DP; ++k) xv[k] = xt[k];
+            fx = fx_prop;
+            ev.grad(xv, g);                                       // the evaluator's state is that of cost(x_prop)
+            norm_grad = M<T>::sqrt_(E::dot(g, g));
+        }
+        ++it;
+        if (it >= opt.maxiter) { why = 1; break; }
+        if (norm_grad < mingrad) { why = 2; break; }
+    }
+    if (lane == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) s = fma(static_cast<double>(xv[k]), static_cast<double>(xv[k]), s);
+        const double inv = 1.0 / sqrt(s);
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+            if (k < D) x_io[rid * D + k] = static_cast<double>(xv[k]) * inv;
+        value[rid] = static_cast<double>(-fx);
+        if (iters) iters[rid] = it;
+        if (reason) reason[rid] = why;
+    }
+}
+
 int spec_width() {   // GABO_ACQ_SPEC = 1 | 2 | 4 (developer switch for the speculation width)
     static const int w = [] {
         const char* e = getenv("GABO_ACQ_SPEC");
@@ -728,6 +921,30 @@ int launch_t(const GpParams& gp, const RcgParams& opt, int mode, double* x, int6
     return check_launch("sphere_acq_kernel");
 }
 
+template <typename T, int DP, int NCH>
+int launch_rtr(const GpParams& gp, const RtrParams& opt, double* x, int64_t r, double* value, int32_t* iters,
+               int32_t* reason, cudaStream_t stream) {
+    const int n = gp.n, npad = (n + 3) & ~3;
+    SmemCarver cv;
+    cv.take(sizeof(T) * npad * n);
+    cv.take(sizeof(T) * kAcqWarps * SphereEval<T, DP, NCH>::ksh_size(n));
+    const size_t smem = cv.off;
+    auto kern = sphere_rtr_kernel<T, DP, NCH>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const unsigned grid = static_cast<unsigned>((r + kAcqWarps - 1) / kAcqWarps);
+    kern<<<grid, kAcqWarps * 32, smem, stream>>>(gp, opt, x, r, value, iters, reason);
+    return check_launch("sphere_rtr_kernel");
+}
+
+template <typename T, int DP>
+int launch_rtr_n(const GpParams& gp, const RtrParams& opt, double* x, int64_t r, double* value, int32_t* iters,
+                 int32_t* reason, cudaStream_t stream) {
+    if (gp.n <= 32) return launch_rtr<T, DP, 1>(gp, opt, x, r, value, iters, reason, stream);
+    if (gp.n <= 64) return launch_rtr<T, DP, 2>(gp, opt, x, r, value, iters, reason, stream);
+    if constexpr (DP <= 8) return launch_rtr<T, DP, 4>(gp, opt, x, r, value, iters, reason, stream);
+    return GABO_E_UNSUPPORTED;
+}
+
 }  // namespace
 
 int launch_acq_sphere(const gabo_gp_desc* g, double* x, int64_t r, const gabo_rcg_opts* o, double* value, double* grad,
@@ -757,6 +974,35 @@ int launch_acq_sphere(const gabo_gp_desc* g, double* x, int64_t r, const gabo_rc
     }
     return f64 ? launch_t<double, 4>(gp, opt, mode, x, r, value, grad, iters, reason, stream)
                : launch_t<float, 4>(gp, opt, mode, x, r, value, grad, iters, reason, stream);
+}
+
+int launch_rtr_sphere(const gabo_gp_desc* g, double* x, int64_t r, const gabo_rtr_opts* o, double* value, int32_t* iters,
+                      int32_t* reason, cudaStream_t stream) {
+    GpParams gp{g->n_train, g->dim, g->mean, g->outputscale, g->beta, g->best_f, g->kxx, g->x_train, g->alpha, g->minv};
+    RtrParams opt{};
+    opt.maxiter = o->maxiter;
+    opt.mininner = o->mininner;
+    opt.maxinner = o->maxinner > 0 ? o->maxinner : g->dim - 1;                  // pymanopt Sphere.dim
+    opt.mingradnorm = o->mingradnorm;
+    opt.kappa = o->kappa;
+    opt.theta = o->theta;
+    opt.rho_prime = o->rho_prime;
+    opt.rho_regularization = o->rho_regularization;
+    opt.delta_bar = o->delta_bar > 0.0 ? o->delta_bar : 3.14159265358979323846; // pymanopt Sphere.typicaldist
+    opt.delta0 = o->delta0 > 0.0 ? o->delta0 : opt.delta_bar / 8.0;
+    opt.fd_eps = 1.0 / 16384.0;                                                 // approximate_hessian.py:43
+    const bool f64 = g->compute == GABO_F64;
+    GABO_REQUIRE(gp.dim <= 8 || (gp.dim <= 16 && gp.n <= 64), GABO_E_UNSUPPORTED,
+                 "gabo_acq_rtr: the trust-region kernel keeps the iterate in registers: ambient dimension <= 8, or "
+                 "<= 16 with n_train <= 64 (got dim=%d, n_train=%d)", gp.dim, gp.n);
+    if (gp.dim <= 4)
+        return f64 ? launch_rtr_n<double, 4>(gp, opt, x, r, value, iters, reason, stream)
+                   : launch_rtr_n<float, 4>(gp, opt, x, r, value, iters, reason, stream);
+    if (gp.dim <= 8)
+        return f64 ? launch_rtr_n<double, 8>(gp, opt, x, r, value, iters, reason, stream)
+                   : launch_rtr_n<float, 8>(gp, opt, x, r, value, iters, reason, stream);
+    return f64 ? launch_rtr_n<double, 16>(gp, opt, x, r, value, iters, reason, stream)
+               : launch_rtr_n<float, 16>(gp, opt, x, r, value, iters, reason, stream);
 }
 
 }  // namespace gabo

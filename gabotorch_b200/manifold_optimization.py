@@ -56,12 +56,49 @@ class ConjugateGradient:
         self.initial_stepsize = initial_stepsize
 
 
+class TrustRegions:
+    """Options of the batched Riemannian trust-region solver: constructor surface of the reference's own
+    ``TrustRegions`` (manifold_optimization/robust_trust_regions.py:91-108; pymanopt ``Solver`` keywords behind it).
+    Hessian-vector products are the finite differences of ``approximate_hessian.py`` -- what the reference uses with
+    ``approx_hessian=True``; with ``approx_hessian=False`` the reference differentiates the gradient with autograd
+    instead, which this path does not do (the two differ by O(2^-14) relative)."""
+
+    def __init__(self, miniter=3, kappa=0.1, theta=1.0, rho_prime=0.1, use_rand=False, rho_regularization=1e3,
+                 maxtime=1000, maxiter=1000, mingradnorm=1e-6, minstepsize=1e-10, maxcostevals=5000, logverbosity=0,
+                 mininner=1, maxinner=None, Delta_bar=None, Delta0=None):
+        if use_rand:
+            raise NotImplementedError('use_rand=True (randomised tCG start + Cauchy point) is not supported')
+        self.miniter, self.kappa, self.theta, self.rho_prime = miniter, kappa, theta, rho_prime
+        self.use_rand, self.rho_regularization = use_rand, rho_regularization
+        self._maxtime, self._maxiter, self._mingradnorm = maxtime, maxiter, mingradnorm
+        self._minstepsize, self._maxcostevals, self._logverbosity = minstepsize, maxcostevals, logverbosity
+        # arguments of TrustRegions.solve in the reference (:110-111); the batched entry takes them here
+        self.mininner, self.maxinner, self.Delta_bar, self.Delta0 = mininner, maxinner, Delta_bar, Delta0
+
+
+def _trust_region_options(solver):
+    if getattr(solver, 'use_rand', False):
+        raise NotImplementedError('use_rand=True (randomised tCG start + Cauchy point) is not supported')
+    return dict(
+        maxiter=int(getattr(solver, '_maxiter', 1000)),
+        mingradnorm=float(getattr(solver, '_mingradnorm', 1e-6)),
+        kappa=float(getattr(solver, 'kappa', 0.1)),
+        theta=float(getattr(solver, 'theta', 1.0)),
+        rho_prime=float(getattr(solver, 'rho_prime', 0.1)),
+        rho_regularization=float(getattr(solver, 'rho_regularization', 1e3)),
+        mininner=int(getattr(solver, 'mininner', 1)),
+        maxinner=getattr(solver, 'maxinner', None),
+        delta_bar=getattr(solver, 'Delta_bar', None),
+        delta0=getattr(solver, 'Delta0', None),
+    )
+
+
 def _solver_options(solver):
     name = type(solver).__name__
     if name != 'ConjugateGradient':
         raise NotImplementedError(
-            'solver %s: the B200 path batches conjugate gradient only (trust-region / ALM solvers are SURVEY 8f '
-            '"next"); there is no CPU fallback' % name)
+            'solver %s: the B200 path batches ConjugateGradient and TrustRegions (constrained trust regions / ALM are '
+            'SURVEY 8f "next"); there is no CPU fallback' % name)
     ls = getattr(solver, '_linesearch', None) or getattr(solver, 'linesearch', None)
     return dict(
         maxiter=int(getattr(solver, '_maxiter', 1000)),
@@ -277,7 +314,10 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     if solver_init_conds:
         raise NotImplementedError('solver-side initialisation (population methods) is not supported')
     kind = _manifold_kind(manifold)
-    sopts = _solver_options(solver)
+    trust_region = type(solver).__name__ == 'TrustRegions'
+    if trust_region and kind != _lib.SPHERE:
+        raise NotImplementedError('the batched trust-region solver covers the sphere; use ConjugateGradient on SPD')
+    sopts = _trust_region_options(solver) if trust_region else _solver_options(solver)
     if not isinstance(acquisition_function, ExpectedImprovement):
         raise NotImplementedError('the B200 optimiser evaluates ExpectedImprovement in closed form; got %s'
                                   % type(acquisition_function).__name__)
@@ -292,7 +332,7 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     if x0.dim() < 3 or x0.shape[1] != 1:
         raise NotImplementedError('initial_conditions must be R x 1 x ... (q = 1, manifold_optimize.py:206)')
     pts = x0[:, 0]
-    cand, val, iters, reason = ops.acq_rcg(gp, pts, **sopts)
+    cand, val, iters, reason = (ops.acq_rtr if trust_region else ops.acq_rcg)(gp, pts, **sopts)
     candidates = cand[:, None]
     if post_processing_manifold is not None:
         candidates = post_processing_manifold(candidates)

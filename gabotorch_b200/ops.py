@@ -503,6 +503,24 @@ def acq_rcg(gp, x0, maxiter=1000, mingradnorm=1e-6, minstepsize=1e-10, ls_maxite
     return x, val, iters, reason
 
 
+def acq_rtr(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1, rho_regularization=1e3,
+            mininner=1, maxinner=None, delta_bar=None, delta0=None):
+    """Multi-start Riemannian trust regions (tCG, finite-difference Hessian) on -EI, sphere.  Returns (candidates,
+    values, iters, reasons)."""
+    lib = _lib.load()
+    x = to_dev64(x0).clone()
+    r = x.shape[0]
+    val = torch.empty(r, dtype=torch.float64, device=x.device)
+    iters = torch.empty(r, dtype=torch.int32, device=x.device)
+    reason = torch.empty(r, dtype=torch.int32, device=x.device)
+    opts = _lib.RtrOpts(int(maxiter), int(mininner), int(maxinner or 0), 0, float(mingradnorm), float(kappa),
+                        float(theta), float(rho_prime), float(rho_regularization), float(delta_bar or 0.0),
+                        float(delta0 or 0.0))
+    _lib.check(lib.gabo_acq_rtr(ctypes.byref(gp.desc), _p(x), r, ctypes.byref(opts), _p(val), _p(iters), _p(reason),
+                                _lib.stream_ptr()), 'gabo_acq_rtr')
+    return x, val, iters, reason
+
+
 def gp_mll(dmat, y, theta, want_grad=True, want_factors=False):
     """log N(y | m, s exp(-beta dmat) + noise I) for a batch of theta = (beta, s, noise, m) rows (``gabo_gp_mll``).
     Returns (ll (B,), grad (B, 4) or None, alpha (B, n) or None, kinv (B, n, n) or None, flags (B,) int32), on device."""

@@ -201,6 +201,26 @@ typedef struct gabo_rcg_opts {
 int gabo_acq_rcg(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* opts, double* value,
                  int32_t* iters, int32_t* reason, void* stream);
 
+/* Trust-region variant: the reference's own TrustRegions solver
+ * (manifold_optimization/robust_trust_regions.py:116-352 with _truncated_conjugate_gradient :410-520) over the
+ * finite-difference Hessian of manifold_optimization/approximate_hessian.py:11-62, one warp per restart, sphere only
+ * (ambient dimension <= 8, or <= 16 with n_train <= 64).  reason 1 = maxiter, 2 = gradnorm. */
+typedef struct gabo_rtr_opts {
+    int32_t maxiter;            /* pymanopt Solver maxiter (1000)                                   */
+    int32_t mininner;           /* TrustRegions.solve mininner (1)                                  */
+    int32_t maxinner;           /* <= 0: manifold.dim                                               */
+    int32_t reserved;
+    double mingradnorm;         /* 1e-6                                                             */
+    double kappa;               /* 0.1   (robust_trust_regions.py:95-96)                            */
+    double theta;               /* 1.0                                                              */
+    double rho_prime;           /* 0.1                                                              */
+    double rho_regularization;  /* 1e3                                                              */
+    double delta_bar;           /* <= 0: manifold.typicaldist (pi on the sphere)                    */
+    double delta0;              /* <= 0: delta_bar / 8                                              */
+} gabo_rtr_opts;
+int gabo_acq_rtr(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rtr_opts* opts, double* value,
+                 int32_t* iters, int32_t* reason, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * A3: candidate selection.  Replaces botorch get_best_candidates (argmax of batch values, manifold_optimize.py:118-120).
  * Lexicographic (value descending, global index ascending), NaN = -inf: identical on 1 or N GPUs.

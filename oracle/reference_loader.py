@@ -44,3 +44,59 @@ def load():
     ns['nested_spd_utils'] = importlib.import_module('BoManifolds.nested_mappings.nested_spd_utils')
     ns['nested_spheres_utils'] = importlib.import_module('BoManifolds.nested_mappings.nested_spheres_utils')
     return type('Reference', (), dict(ns))
+
+
+def load_trust_regions():
+    """The reference's own ``TrustRegions`` class and ``get_hessianfd`` (manifold_optimization/robust_trust_regions.py,
+    approximate_hessian.py).  The module imports the third-party base class ``pymanopt.solvers.solver.Solver``
+    (absent here); a stand-in with pymanopt 0.2.x's published constructor defaults and stopping rule
+    (``_check_stopping_criterion``: time, iter >= maxiter, gradnorm < mingradnorm, stepsize < minstepsize,
+    costevals >= maxcostevals, in that order) is registered under that name first."""
+    if not available():
+        raise RuntimeError('reference tree not present at %s' % REFERENCE_ROOT)
+    import importlib
+    import time
+    import types
+    if 'pymanopt.solvers.solver' not in sys.modules:
+        class Solver(object):
+            def __init__(self, maxtime=1000, maxiter=1000, mingradnorm=1e-6, minstepsize=1e-10, maxcostevals=5000,
+                         logverbosity=0):
+                self._maxtime, self._maxiter, self._mingradnorm = maxtime, maxiter, mingradnorm
+                self._minstepsize, self._maxcostevals, self._logverbosity = minstepsize, maxcostevals, logverbosity
+                self._optlog = None
+
+            def _check_stopping_criterion(self, time0, iter=-1, gradnorm=float('inf'), stepsize=float('inf'),
+                                          costevals=-1):
+                self._last_iter = iter               # kept so that the golden generator can record the iteration count
+                if time.time() >= time0 + self._maxtime:
+                    return 'max time'
+                if iter >= self._maxiter:
+                    return 'max iter'
+                if gradnorm < self._mingradnorm:
+                    return 'min grad norm'
+                if stepsize < self._minstepsize:
+                    return 'min stepsize'
+                if costevals >= self._maxcostevals:
+                    return 'max cost evals'
+                return None
+
+            def _start_optlog(self, *args, **kwargs):
+                pass
+
+            def _stop_optlog(self, *args, **kwargs):
+                pass
+
+        pkg = types.ModuleType('pymanopt')
+        solvers = types.ModuleType('pymanopt.solvers')
+        solver = types.ModuleType('pymanopt.solvers.solver')
+        solver.Solver = Solver
+        pkg.solvers = solvers
+        solvers.solver = solver
+        sys.modules.setdefault('pymanopt', pkg)
+        sys.modules.setdefault('pymanopt.solvers', solvers)
+        sys.modules['pymanopt.solvers.solver'] = solver
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    rtr = importlib.import_module('BoManifolds.manifold_optimization.robust_trust_regions')
+    fd = importlib.import_module('BoManifolds.manifold_optimization.approximate_hessian')
+    return rtr.TrustRegions, fd.get_hessianfd

@@ -201,6 +201,46 @@ def main():
         out[name + '_w'], out[name + '_v'], out[name + '_c'], out[name + '_k'] = w, v, c, k
         out[name + '_y'], out[name + '_x'] = y, x.numpy()
 
+    # ---- trust-region acquisition solver: the reference's own TrustRegions class (robust_trust_regions.py) with its
+    # finite-difference Hessian (approximate_hessian.py) on the oracle's EI problem; own generator so that the arrays
+    # above keep their values ----------------------------------------------------------------------------------------
+    import types
+    from oracle import gp as ogp, rtr as ortr, sphere as osph, spd as ospd
+    TrustRegions, get_hessianfd = reference_loader.load_trust_regions()
+    rng_tr = np.random.default_rng(SEED + 1)
+    for name, manifold, dim, n, beta, noise, nstart in (('rtr_s2', 'sphere', 3, 12, 6.5 + LN2, 1e-2, 12),
+                                                        ('rtr_s5', 'sphere', 6, 32, 1.0 + LN2, 1e-2, 12),
+                                                        ('rtr_s5_noisy', 'sphere', 6, 32, 1.0 + LN2, 2.0, 6)):
+        xt = osph.rand(rng_tr, n, dim)
+        y = osph.ackley(xt)
+        gp = ogp.make_gp(manifold, xt, y, beta=beta, noise=noise)
+        man = ortr._Man(manifold, xt[0])
+        cost, grad = ortr.ei_problem(gp)
+
+        class Problem(object):     # the attributes TrustRegions.solve reads from a pymanopt Problem
+            manifold = man
+            verbosity = 0
+
+            def precon(self, x, d):           # manifold_optimize.py:190-193
+                if np.sum(d) == 0.:
+                    d += 1e-30
+                return d
+        problem = Problem()
+        problem.cost, problem.grad = cost, grad
+        problem.hess = types.MethodType(get_hessianfd, problem)   # manifold_optimize.py:199-200 (sets _hess there)
+        x0 = osph.rand(rng_tr, nstart, dim)
+        xs, fs, its = [], [], []
+        for i in range(nstart):
+            solver = TrustRegions()
+            x = solver.solve(problem, x=x0[i].copy())
+            xs.append(x)
+            fs.append(cost(x))
+            its.append(solver._last_iter)
+        out[name + '_xtrain'], out[name + '_y'] = xt, np.asarray(y)
+        out[name + '_hyper'] = np.array([beta, noise])
+        out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
+        out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
+
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %d arrays, %.1f KiB' % (path, len(out), os.path.getsize(path) / 1024))

@@ -208,3 +208,71 @@ def test_argmax_records_is_exact_and_sharding_invariant():
         assert np.array(recs_g)[order][int(w)] == 17
     allnan = np.full(7, np.nan)
     assert int(ops.argmax_records(allnan)[0]) == 0
+
+
+# ---- trust-region solver: pinned on the reference's own TrustRegions class -----------------------
+
+def _gp_from_golden(golden, name):
+    beta, noise = golden[name + '_hyper']
+    return ogp.make_gp('sphere', golden[name + '_xtrain'], golden[name + '_y'], beta=float(beta), noise=float(noise))
+
+
+@pytest.mark.parametrize('name', ['rtr_s2', 'rtr_s5', 'rtr_s5_noisy'])
+def test_rtr_f64_reproduces_the_reference_solver(golden, name):
+    # tests/golden/make_golden.py ran robust_trust_regions.TrustRegions + approximate_hessian.get_hessianfd (the
+    # reference's own code) from these starts: same iteration counts, same candidates, same costs
+    gp = _gp_from_golden(golden, name)
+    x, val, iters, reason = ops.acq_rtr(device_gp(gp, _lib.GABO_F64), golden[name + '_x0'])
+    np.testing.assert_array_equal(iters.cpu().numpy(), golden[name + '_iters'])
+    np.testing.assert_allclose(x.cpu().numpy(), golden[name + '_x'], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(-val.cpu().numpy(), golden[name + '_cost'], rtol=1e-8, atol=1e-12)
+    assert (reason.cpu().numpy() == 2).all()                       # every solve ended on the gradient norm
+
+
+@pytest.mark.parametrize('D,n,R', [(3, 5, 33), (6, 32, 256), (4, 40, 50), (8, 100, 40), (12, 64, 30)])
+def test_rtr_vs_oracle_and_f32_reaches_the_same_optima(D, n, R):
+    from oracle import rtr as ortr
+    rng, gp = sphere_problem(D, n, beta=1.0 + math.log(2.0), noise=1e-2, seed=100 + D)
+    x0 = osph.rand(rng, R, D)
+    opts = ortr.TROptions(maxiter=60)
+    ref_x, ref_v, ref_it = ortr.gen_candidates(gp, x0[:12], opts)
+    x64, v64, it64, _ = ops.acq_rtr(device_gp(gp, _lib.GABO_F64), x0, maxiter=60)
+    same = it64.cpu().numpy()[:12] == ref_it
+    assert same.sum() >= 10                                        # a flipped accept/reject test changes the path
+    np.testing.assert_allclose(x64.cpu().numpy()[:12][same], ref_x[same], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(v64.cpu().numpy()[:12], ref_v, rtol=1e-6, atol=1e-10)
+    ei0 = np.array([ogp.ei_and_grad(gp, xi, want_grad=False)[0] for xi in x0])
+    x32, v32, it32, _ = ops.acq_rtr(device_gp(gp, _lib.GABO_F32), x0, maxiter=60)
+    for xs, vs in ((x64, v64), (x32, v32)):
+        xs, vs = xs.cpu().numpy(), vs.cpu().numpy()
+        np.testing.assert_allclose(np.linalg.norm(xs, axis=-1), 1.0, atol=1e-12)
+        assert (vs >= ei0 - 1e-6 * max(1.0, ei0.max())).all()      # trust regions never accept an increase of the cost
+        check = np.array([ogp.ei_and_grad(gp, xi, want_grad=False)[0] for xi in xs[:16]])
+        np.testing.assert_allclose(vs[:16], check, rtol=2e-4, atol=1e-6 * max(check.max(), 1e-30))
+    # fp32 and fp64 solves end in the same local optima for (almost) every start
+    close = np.abs(v32.cpu().numpy() - v64.cpu().numpy()) <= 1e-3 * np.abs(v64.cpu().numpy()).max()
+    assert close.mean() >= 0.9
+
+
+def test_rtr_through_the_reference_api_and_argument_errors():
+    import gabotorch_b200 as g
+    rng = np.random.default_rng(3)
+    xt = osph.rand(rng, 20, 3)
+    y = osph.ackley(xt)
+    model = g.ManifoldGP(xt, y, g.ScaleKernel(g.SphereGaussianKernel(beta_min=6.5)), noise=1e-2)
+    ei = g.ExpectedImprovement(model, best_f=float(np.min(y)), maximize=False, compute='f64')
+    x0 = torch.from_numpy(osph.rand(rng, 9, 3))[:, None, :]
+    cand, vals = g.gen_candidates_manifold(x0, ei, g.Sphere(3), g.TrustRegions(), approx_hessian=True)
+    assert tuple(cand.shape) == (9, 1, 3) and tuple(vals.shape) == (9,)
+    np.testing.assert_allclose(ei(cand).numpy(), vals.numpy(), rtol=1e-9, atol=1e-14)
+    assert (vals >= ei(x0) - 1e-12).all()
+    best = g.joint_optimize_manifold(ei, g.Sphere(3), g.TrustRegions(maxiter=50), q=1, num_restarts=8, raw_samples=64,
+                                     approx_hessian=True)
+    assert tuple(best.shape) == (1, 3) and abs(float(best.norm()) - 1.0) < 1e-12
+    with pytest.raises(NotImplementedError):
+        g.TrustRegions(use_rand=True)
+    with pytest.raises(NotImplementedError):
+        g.gen_candidates_manifold(x0, ei, g.PositiveDefinite(2), g.TrustRegions())
+    rng2, gp = sphere_problem(20, 16, beta=1.0, noise=1e-2, seed=1)
+    with pytest.raises(_lib.GaboError):
+        ops.acq_rtr(device_gp(gp, _lib.GABO_F64), osph.rand(rng2, 4, 20))      # dimension beyond the register kernel

@@ -211,3 +211,16 @@ def test_nested_spd_reconstruction_matches_reference(golden, name):
     back = onest.projection_from_spd_to_nested_spd(x, w).numpy()
     np.testing.assert_allclose(back, golden[name + '_y'], rtol=0, atol=1e-11)
     assert np.linalg.eigvalsh(0.5 * (x + np.swapaxes(x, -1, -2))).min() > 0
+
+
+@pytest.mark.parametrize('name', ['rtr_s2', 'rtr_s5', 'rtr_s5_noisy'])
+def test_trust_region_oracle_matches_reference_solver(golden, name):
+    # robust_trust_regions.py (the reference's own TrustRegions class) + approximate_hessian.py, run by make_golden.py
+    from oracle import gp as ogp
+    from oracle import rtr as ortr
+    beta, noise = golden[name + '_hyper']
+    gp = ogp.make_gp('sphere', golden[name + '_xtrain'], golden[name + '_y'], beta=float(beta), noise=float(noise))
+    xs, vals, its = ortr.gen_candidates(gp, golden[name + '_x0'])
+    np.testing.assert_array_equal(its, golden[name + '_iters'])
+    np.testing.assert_allclose(xs, golden[name + '_x'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(-vals, golden[name + '_cost'], rtol=1e-12, atol=1e-15)
