@@ -552,6 +552,91 @@ class Bench:
                 'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': self.hbm_peak, 'unit': 'GB/s',
                              'frac': gbs / self.hbm_peak, 'algorithmic_bytes_per_launch': nbytes}}
 
+    # -- SURVEY 8(f) "next" rows -----------------------------------------------------------------------------------
+    def extra_acq_rtr(self, R=1024, D=6, n_train=32, noise=1e-2, steps=5):
+        """The reference's default acquisition solver: TrustRegions (robust_trust_regions.py) with the finite-difference
+        Hessian, its own stopping rules (mingradnorm 1e-6, maxiter 1000); R restarts per GPU on S^5."""
+        import gabotorch_b200 as g
+        torch, ops = self.torch, self.ops
+        rng = np.random.default_rng(2024)
+        xt = sphere_sample(rng, n_train, D)
+        y = ackley_sphere(xt)
+        model = g.ManifoldGP(torch.from_numpy(xt), torch.from_numpy(y),
+                             g.ScaleKernel(g.SphereGaussianKernel(beta_min=1.0)), noise=noise)
+        model.covar_module.outputscale = 1.0
+        gp = g.ExpectedImprovement(model, best_f=float(y.min())).device_gp()
+        x0 = torch.from_numpy(sphere_sample(np.random.default_rng(777 + self.rank), R, D)).to(self.dev)
+        res = {}
+
+        def step():
+            res['out'] = ops.acq_rtr(gp, x0)
+        ms = self.time_steps(step, steps, 3, flush=False) / steps
+        iters = res['out'][2].double().mean().item()
+        return {'workload': 'acq trust regions (tCG, FD Hessian) on EI, S^%d, %d restarts/GPU, TrustRegions() defaults, '
+                            'n_train=%d, noise=%g' % (D - 1, R, n_train, noise),
+                'solves_per_s': self.world * R / (ms * 1e-3), 'ms_per_step': ms, 'mean_outer_iters': iters}
+
+    def extra_gp_fit(self, n_train=32, D=3, batch=4096, steps=5):
+        """GP hyper-parameter fit (gabo_gp_mll): marginal-likelihood + gradient evaluations per second for a batch of
+        hyper-parameter sets, and the wall time of one fit_gpytorch_model (scipy L-BFGS-B driving one launch + one
+        48-byte read-back per objective evaluation) on the model of gabo_sphere.py:131-147."""
+        import gabotorch_b200 as g
+        from gabotorch_b200 import gp_fit
+        torch, ops = self.torch, self.ops
+        rng = np.random.default_rng(11)
+        xt = sphere_sample(rng, n_train, D)
+        y = ackley_sphere(xt)
+        base = g.SphereGaussianKernel(beta_min=6.5)
+        dmat, _ = gp_fit.kernel_distance_matrix(base, torch.from_numpy(xt))
+        yd = torch.from_numpy(y).to(self.dev)
+        th = np.column_stack([6.5 + rng.random(batch) * 3, 0.1 + rng.random(batch) * 5, 1e-3 + rng.random(batch),
+                              rng.standard_normal(batch)])
+        th = torch.from_numpy(th).to(self.dev)
+        ms = self.time_steps(lambda: ops.gp_mll(dmat, yd, th), steps, 3, flush=False) / steps
+        t_fit = []
+        for _ in range(3):
+            cov = g.ScaleKernel(g.SphereGaussianKernel(beta_min=6.5), outputscale_prior=g.GammaPrior(2.0, 0.15))
+            model = g.ManifoldGP(xt, y, cov, noise=2.0, mean=0.0, noise_prior=g.GammaPrior(1.1, 0.05))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g.fit_gpytorch_model(model)
+            t_fit.append((time.perf_counter() - t0) * 1e3)
+        return {'workload': 'GP marginal likelihood + gradient, n_train=%d on S^%d, %d hyper-parameter sets per launch; '
+                            'fit_gpytorch_model (L-BFGS-B) on the gabo_sphere.py model' % (n_train, D - 1, batch),
+                'mll_evaluations_per_s': batch / (ms * 1e-3), 'ms_per_step': ms,
+                'fit_ms': min(t_fit), 'fit_objective_evaluations': model.fit_result['evaluations'],
+                'fit_iterations': model.fit_result['iterations']}
+
+    def extra_reconstruct(self, n=1 << 16, D=20, d=5, steps=5):
+        """projection_from_nested_spd_to_spd (nested_spd_utils.py:51-118): batched sqrtm + reconstruction, fp64."""
+        from gabotorch_b200 import nested_mappings as nm
+        torch, ops = self.torch, self.ops
+        rng = np.random.default_rng(9)
+        q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        a = rng.standard_normal((D - d, D - d))
+        c = a @ a.T + np.eye(D - d)
+        k = rng.standard_normal((d, D - d))
+        k = 0.7 * k / np.linalg.norm(k, 2)
+        rec = nm.NestedSpdReconstruction(torch.from_numpy(q[:, :d].copy()), torch.from_numpy(q[:, d:].copy()),
+                                         torch.from_numpy(c), torch.from_numpy(k))
+        b = torch.randn(n, d, d, dtype=torch.float64, device=self.dev)
+        ylow = b @ b.transpose(-1, -2) + torch.eye(d, dtype=torch.float64, device=self.dev)
+        ms = self.time_steps(lambda: rec(ylow), steps, 3) / steps
+        nbytes = n * 8 * (2 * 2 * d * d + D * D)        # y read twice + sqrt written and read + x written
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {'workload': 'nested SPD reconstruction SPD(%d)->SPD(%d), N=%d, fp64 (sqrtm + rotation, 2 launches)'
+                            % (d, D, n),
+                'matrices_per_s': self.world * n / (ms * 1e-3), 'ms_per_step': ms,
+                'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': self.hbm_peak, 'unit': 'GB/s',
+                             'frac': gbs / self.hbm_peak, 'algorithmic_bytes_per_launch': nbytes}}
+
+    def guarded(self, fn, *a, **kw):
+        """Extras of the 'next' rows must never take the headline line down with them."""
+        try:
+            return fn(*a, **kw)
+        except Exception as e:   # noqa: BLE001
+            return {'workload': fn.__name__, 'error': '%s: %s' % (type(e).__name__, e)}
+
     def cpu_baseline(self):
         torch = self.torch
         cores = os.cpu_count() or 1
@@ -597,6 +682,9 @@ class Bench:
                 extras.append(self.extra_sphere(32768, 9, 0.6 + math.log(2.0), torch.float32, steps=5))
                 extras.append(self.extra_sphere(32768, 9, 0.6 + math.log(2.0), torch.float64, steps=5))
                 extras.append(self.extra_projection(1 << 20))
+                extras.append(self.guarded(self.extra_acq_rtr))
+                extras.append(self.guarded(self.extra_gp_fit))
+                extras.append(self.guarded(self.extra_reconstruct))
         cpu = None
         if self.rank == 0 and self.world == 1 and not args.no_cpu_baseline:
             cpu = self.cpu_baseline()
