@@ -664,6 +664,12 @@ class Bench:
             if self.rank == 0:
                 emit(e)
             return 0
+        if args.only == 'next':                   # developer switch: the SURVEY 8(f) extras only
+            out = [self.guarded(f) for f in (self.extra_acq_rtr, self.extra_gp_fit, self.extra_reconstruct)]
+            self.clocks.stop()
+            if self.rank == 0:
+                emit({'extra': out})
+            return 0
         head = self.headline()
         extras = []
         if not args.no_extras:

@@ -77,6 +77,7 @@ SIGNATURES = {
     'gabo_nested_spd_reconstruct_setup': (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     'gabo_nested_spd_reconstruct': (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     'gabo_gp_mll': (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'gabo_gp_factor': (c_i32, [c_ptr, c_i64, c_ptr, c_f64, c_f64, c_f64, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
 

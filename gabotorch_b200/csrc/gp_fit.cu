@@ -29,10 +29,13 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+// FROM_GRAM: dmat already holds the base-kernel matrix exp(-beta Dm) (as written by the fused Gram kernels) and the
+// hyper-parameters come by value -- the factorisation-only form behind gabo_gp_factor.
+template <bool FROM_GRAM>
 __global__ void __launch_bounds__(kGpThreads)
 gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__ y, const double* __restrict__ theta,
-              double* __restrict__ out_ll, double* __restrict__ out_grad, double* __restrict__ out_alpha,
-              double* __restrict__ out_kinv, int* __restrict__ flags) {
+              double4 theta_val, double* __restrict__ out_ll, double* __restrict__ out_grad,
+              double* __restrict__ out_alpha, double* __restrict__ out_kinv, int* __restrict__ flags) {
     extern __shared__ double sm[];
     const int ld = n + 1;                                   // odd row stride in 8-byte words: conflict-free columns
     double* A = sm;                                         // n x ld
@@ -42,11 +45,12 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
     __shared__ int bad;
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
-    const double beta = theta[b * 4 + 0], s = theta[b * 4 + 1], noise = theta[b * 4 + 2], mean = theta[b * 4 + 3];
+    const double beta = FROM_GRAM ? theta_val.x : theta[b * 4 + 0], s = FROM_GRAM ? theta_val.y : theta[b * 4 + 1];
+    const double noise = FROM_GRAM ? theta_val.z : theta[b * 4 + 2], mean = FROM_GRAM ? theta_val.w : theta[b * 4 + 3];
     if (tid == 0) bad = 0;
     for (int e = tid; e < n * n; e += kGpThreads) {
         const int i = e / n, j = e % n;
-        if (j <= i) A[i * ld + j] = fma(s, exp(-beta * dmat[e]), (i == j) ? noise : 0.0);
+        if (j <= i) A[i * ld + j] = fma(s, FROM_GRAM ? dmat[e] : exp(-beta * dmat[e]), (i == j) ? noise : 0.0);
     }
     for (int i = tid; i < n; i += kGpThreads) vec[i] = y[i] - mean;
     __syncthreads();
@@ -79,7 +83,7 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
     if (bad) {                                              // not positive definite: NaN outputs + flag
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
         if (tid == 0) {
-            out_ll[b] = nanv;
+            if (out_ll) out_ll[b] = nanv;
             flags[b] = 1;
         }
         if (out_grad && tid < 4) out_grad[b * 4 + tid] = nanv;
@@ -108,7 +112,7 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
     }
     const double ll = -0.5 * (quad + logdet + n * 1.8378770664093453);   // log(2 pi)
     if (tid == 0) {
-        out_ll[b] = ll;
+        if (out_ll) out_ll[b] = ll;
         flags[b] = 0;
     }
     if (out_alpha) for (int i = tid; i < n; i += kGpThreads) out_alpha[b * n + i] = vec[i];
@@ -140,7 +144,7 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
         }
         const double w = fma(vec[i], vec[j], -kin);
         const double dm = dmat[i * n + j];
-        const double base = exp(-beta * dm);
+        const double base = FROM_GRAM ? dm : exp(-beta * dm);
         const double mult = (i == j) ? 0.5 : 1.0;           // 1/2 tr(.) over both triangles
         gs = fma(mult * w, base, gs);
         gb = fma(mult * w, -s * dm * base, gb);
@@ -166,6 +170,15 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
 
 using namespace gabo;
 
+static void configure_smem() {
+    static bool configured = false;
+    if (configured) return;
+    const int bytes = static_cast<int>(sizeof(double) * (kMaxGpTrain * (kMaxGpTrain + 1) + 2 * kMaxGpTrain + 8));
+    cudaFuncSetAttribute(gp_mll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(gp_mll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    configured = true;
+}
+
 extern "C" int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const double* theta, int64_t batch,
                            double* out_ll, double* out_grad, double* out_alpha, double* out_kinv, int* flags,
                            void* stream) {
@@ -175,13 +188,21 @@ extern "C" int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const
     if (batch == 0) return GABO_OK;
     GABO_REQUIRE(dmat && y && theta && out_ll && flags, GABO_E_ARG, "gabo_gp_mll: null pointer");
     const size_t smem = sizeof(double) * (static_cast<size_t>(n) * (n + 1) + 2 * n + kGpThreads / 32);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(gp_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(sizeof(double) * (kMaxGpTrain * (kMaxGpTrain + 1) + 2 * kMaxGpTrain + 8)));
-        configured = true;
-    }
-    gp_mll_kernel<<<static_cast<unsigned>(batch), kGpThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        dmat, static_cast<int>(n), y, theta, out_ll, out_grad, out_alpha, out_kinv, flags);
+    configure_smem();
+    gp_mll_kernel<false><<<static_cast<unsigned>(batch), kGpThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        dmat, static_cast<int>(n), y, theta, make_double4(0, 0, 0, 0), out_ll, out_grad, out_alpha, out_kinv, flags);
+    return check_launch("gp_mll_kernel");
+}
+
+extern "C" int gabo_gp_factor(const double* kmat, int64_t n, const double* y, double outputscale, double noise,
+                              double mean, double* out_alpha, double* out_kinv, int* flag, void* stream) {
+    GABO_REQUIRE(n >= 1 && n <= kMaxGpTrain, GABO_E_ARG, "gabo_gp_factor: n=%lld outside [1, %d]",
+                 static_cast<long long>(n), kMaxGpTrain);
+    GABO_REQUIRE(kmat && y && out_alpha && out_kinv && flag, GABO_E_ARG, "gabo_gp_factor: null pointer");
+    const size_t smem = sizeof(double) * (static_cast<size_t>(n) * (n + 1) + 2 * n + kGpThreads / 32);
+    configure_smem();
+    gp_mll_kernel<true><<<1, kGpThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        kmat, static_cast<int>(n), y, nullptr, make_double4(0.0, outputscale, noise, mean), nullptr, nullptr, out_alpha,
+        out_kinv, flag);
     return check_launch("gp_mll_kernel");
 }

@@ -214,12 +214,8 @@ def build_device_gp(model, best_f, maximize=False, compute='f32'):
     else:
         raise NotImplementedError('acquisition kernels support SphereGaussianKernel and '
                                   'SpdAffineInvariantGaussianKernel, got %s' % type(base).__name__)
-    n = k.shape[0]
-    kn = scale * k + noise * torch.eye(n, dtype=torch.float64, device=k.device)
-    kn = 0.5 * (kn + kn.T)
-    minv = torch.linalg.inv(kn)
-    minv = 0.5 * (minv + minv.T)
-    alpha = torch.linalg.solve(kn, sign * (y - mean))
+    # Cholesky factorisation, alpha and the inverse in one launch of the GP kernel (no cuSOLVER on the path)
+    alpha, minv = ops.gp_factor(k, sign * y, scale, noise, sign * mean)
     return ops.DeviceGP(manifold, dim, x_dev, alpha, minv, sign * mean, scale, beta, sign * best_f, kxx, comp)
 
 

@@ -542,6 +542,24 @@ def gp_mll(dmat, y, theta, want_grad=True, want_factors=False):
     return ll, grad, alpha, kinv, flags
 
 
+def gp_factor(kmat, y, outputscale, noise, mean):
+    """alpha = (s K + noise I)^-1 (y - m) and (s K + noise I)^-1 from a base-kernel matrix (``gabo_gp_factor``)."""
+    lib = _lib.load()
+    kmat = to_dev64(kmat)
+    y = to_dev64(y).reshape(-1)
+    n = y.shape[0]
+    if tuple(kmat.shape) != (n, n):
+        raise ValueError('kmat must be (n, n) with n = len(y)')
+    alpha = torch.empty(n, dtype=torch.float64, device=kmat.device)
+    kinv = torch.empty(n, n, dtype=torch.float64, device=kmat.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=kmat.device)
+    _lib.check(lib.gabo_gp_factor(_p(kmat), n, _p(y), float(outputscale), float(noise), float(mean), _p(alpha),
+                                  _p(kinv), _p(flag), _lib.stream_ptr()), 'gabo_gp_factor')
+    if int(flag.item()) != 0:
+        raise NotPositiveDefiniteError('the GP covariance s K + noise I is not positive definite')
+    return alpha, kinv
+
+
 def argmax_records(values, gidx=None):
     """(slot, value) of the best record: highest value, lowest global index on ties, NaN = -inf."""
     lib = _lib.load()

@@ -276,6 +276,11 @@ int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt, int64_t n
  * ------------------------------------------------------------------------------------------------------------------ */
 int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const double* theta, int64_t batch, double* out_ll,
                 double* out_grad, double* out_alpha, double* out_kinv, int* flags, void* stream);
+/* Factorisation only, from a base-kernel matrix the Gram kernels already produced (what gabo_gp_desc needs once the
+ * hyper-parameters are known): alpha = (s kmat + noise I)^-1 (y - m), kinv = (s kmat + noise I)^-1; *flag = 1 when the
+ * matrix is not positive definite.  Same kernel, same limits. */
+int gabo_gp_factor(const double* kmat, int64_t n, const double* y, double outputscale, double noise, double mean,
+                   double* out_alpha, double* out_kinv, int* flag, void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,15 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.gabo_gp_mll(fake, 129, fake, fake, 1, fake, null, null, null, fake, null) == -1   # n > 128
     assert lib.gabo_gp_mll(null, 8, null, null, 1, null, null, null, null, null, null) == -1
     assert lib.gabo_gp_mll(fake, 8, fake, fake, 0, fake, null, null, null, fake, null) == 0      # empty batch
+    assert lib.gabo_gp_factor(fake, 200, fake, 1.0, 1.0, 0.0, fake, fake, fake, null) == -1     # n > 128
+    assert lib.gabo_gp_factor(fake, 8, fake, 1.0, 1.0, 0.0, null, fake, fake, null) == -1
+    opts = _lib.RtrOpts(10, 1, 0, 0, 1e-6, 0.1, 1.0, 0.1, 1e3, 0.0, 0.0)
+    desc.manifold, desc.dim, desc.n_train = 1, 3, 4                                             # SPD: sphere only
+    assert lib.gabo_acq_rtr(ctypes.byref(desc), fake, 4, ctypes.byref(opts), fake, null, null, null) == -4
+    desc.manifold, desc.dim = 0, 20                                                              # beyond the register kernel
+    assert lib.gabo_acq_rtr(ctypes.byref(desc), fake, 4, ctypes.byref(opts), fake, null, null, null) == -4
+    opts.rho_prime = 0.5
+    assert lib.gabo_acq_rtr(ctypes.byref(desc), fake, 4, ctypes.byref(opts), fake, null, null, null) == -1
 
 
 def test_product_path_has_no_cpu_fallback():

@@ -116,7 +116,8 @@ def test_fit_matches_scipy_on_the_oracle_objective(raw_samples):
     res = model.fit_result
     beta, s, noise, mean = res['theta']
     assert res['objective'] < start and beta >= beta_min and s > 0 and noise > 1e-8
-    assert abs(float(cov.base_kernel.beta) - beta) <= 1e-6 * beta and abs(float(cov.outputscale) - s) <= 1e-6 * s
+    assert abs(float(cov.base_kernel.beta.detach()) - beta) <= 1e-6 * beta
+    assert abs(float(cov.outputscale.detach()) - s) <= 1e-6 * s
     assert model.noise == noise and model.mean == mean
     # the device objective at the fitted point equals the oracle's, and no L-BFGS run on the oracle objective from the
     # same start finds a lower value (same optimiser as botorch's fit_gpytorch_scipy)
@@ -140,3 +141,19 @@ def test_fit_unscaled_kernel_and_unsupported_kernel():
     assert model.fit_result['theta'][1] == 1.0 and model.fit_result['evaluations'] >= 2
     with pytest.raises(NotImplementedError):
         g.fit_gpytorch_model(g.ManifoldGP(x, y, g.SphereLaplaceKernel(), noise=0.5))
+
+
+@pytest.mark.parametrize('n', [1, 7, 32, 100, 128])
+def test_gp_factor_vs_numpy(n):
+    # the factors build_device_gp hands to the acquisition kernels: alpha and (s K + noise I)^-1 from a Gram matrix
+    x, y = _sphere_problem(n, 5, 40 + n)
+    k = ops.sphere_gram(torch.from_numpy(x), torch.from_numpy(x), 1.2 + math.log(2), kind=0)
+    kn = 0.7 * k.cpu().numpy() + 1e-2 * np.eye(n)
+    kn = np.tril(kn) + np.tril(kn, -1).T
+    alpha, kinv = ops.gp_factor(k, torch.from_numpy(y), 0.7, 1e-2, 0.3)
+    ref = np.linalg.inv(kn)
+    np.testing.assert_allclose(kinv.cpu().numpy(), ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+    np.testing.assert_allclose(alpha.cpu().numpy(), ref @ (y - 0.3), rtol=0, atol=1e-9 * np.abs(ref @ (y - 0.3)).max())
+    np.testing.assert_array_equal(kinv.cpu().numpy(), kinv.cpu().numpy().T)
+    with pytest.raises(ops.NotPositiveDefiniteError):
+        ops.gp_factor(k, torch.from_numpy(y), 0.7, -5.0, 0.3)
