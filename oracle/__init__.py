@@ -13,24 +13,31 @@ It restates, in plain numpy / torch-CPU fp64, the arithmetic of the reference
   ``Riemannian_utils/sphere_utils.py:14-123``.
 * ``oracle.spd``     – ``Riemannian_utils/spd_utils_torch.py:13-226``,
   ``kernel_utils/kernels_spd.py:72-100,160-187,217-313`` and ``Riemannian_utils/spd_utils.py:57-306``.
-* ``oracle.nested``  – ``nested_mappings/nested_spd_utils.py:13-48`` and ``kernel_utils/kernels_nested_spd.py``.
-* ``oracle.nested_sphere`` – ``nested_mappings/nested_spheres_utils.py:13-147``,
+* ``oracle.nested``  – ``nested_mappings/nested_spd_utils.py:13-118`` (projection and its approximate inverse) and
+  ``kernel_utils/kernels_nested_spd.py``.
+* ``oracle.nested_sphere`` – ``nested_mappings/nested_spheres_utils.py:13-213`` (both directions),
   ``Riemannian_utils/sphere_utils_torch.py:58-93``, ``kernel_utils/kernels_nested_sphere.py:129-152``.
 * ``oracle.gp``      – the GP posterior / analytic Expected Improvement that the reference
-  obtains from botorch/gpytorch (call sites ``examples/bo_sphere/benchmark_examples/gabo_sphere.py:131-165``).
+  obtains from botorch/gpytorch (call sites ``examples/bo_sphere/benchmark_examples/gabo_sphere.py:131-165``), and the
+  exact marginal log-likelihood ``fit_gpytorch_model`` optimises (``gabo_sphere.py:147,162``).
 * ``oracle.rcg``     – the multi-start driver ``manifold_optimization/manifold_optimize.py:36-321``
   with the pymanopt 0.2.x ``ConjugateGradient`` + ``LineSearchAdaptive`` it calls.
+* ``oracle.rtr``     – the reference's own trust-region solver ``manifold_optimization/robust_trust_regions.py:116-520``
+  with the finite-difference Hessian ``manifold_optimization/approximate_hessian.py:11-62``.
 
 Parity pinning
 --------------
 PINNED (against the reference's own code imported from ``/root/reference`` with a
 ``torch.symeig`` shim, see ``tests/golden/make_golden.py`` and the committed fixtures):
 sphere distance / kernel, Mandel pack/unpack, SPD affine-invariant distance / kernel,
-Frobenius and log-Euclidean distance, nested SPD projection, nested-sphere projection chain.
+Frobenius and log-Euclidean distance, nested SPD projection and reconstruction, ``sqrtm_torch``, nested-sphere
+projection chain in both directions, and the trust-region solver (the reference's ``TrustRegions`` class itself is run
+by ``make_golden.py``; only its third-party base class ``pymanopt.solvers.solver.Solver`` -- the stopping rule -- is a
+stand-in restated from pymanopt 0.2.x).
 
 PARITY UNPINNED: everything whose arithmetic lives in pymanopt / botorch / gpytorch
 (third-party, unpinned versions, absent from ``/root/reference`` and from this image):
-manifold exp/log/retr/transp, conjugate gradient, line search, GP posterior, EI.
+manifold exp/log/retr/transp, conjugate gradient, line search, GP posterior, EI, marginal likelihood + priors.
 Those are restated from the published algorithms (pymanopt 0.2.x, botorch 0.1-0.3,
 gpytorch 1.x) and pinned only by mathematical identities and by the in-repo numpy
 formulas (``sphere_utils.py``, ``spd_utils.py``) where they exist.

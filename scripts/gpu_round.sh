@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=cs
 ( timeout 600 python bench.py 2> gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_n1.json
 ( timeout 300 python bench.py --impl reference --steps 5 --warmup 1 2>> gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_ref.json
 timeout 300 python scripts/dev_e2e.py > gpurun_out/dev_e2e.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:spd_ai_gram_kernel -s 3 -c 1 \
     -o gpurun_out/prof_spd_gram -f python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/prof_spd.log 2>&1
