@@ -622,11 +622,12 @@ class Bench:
         b = torch.randn(n, d, d, dtype=torch.float64, device=self.dev)
         ylow = b @ b.transpose(-1, -2) + torch.eye(d, dtype=torch.float64, device=self.dev)
         ms = self.time_steps(lambda: rec(ylow), steps, 3) / steps
+        ms_sqrt = self.time_steps(lambda: ops.spd_sqrtm(ylow), steps, 3) / steps
         nbytes = n * 8 * (2 * 2 * d * d + D * D)        # y read twice + sqrt written and read + x written
         gbs = nbytes / (ms * 1e-3) / 1e9
         return {'workload': 'nested SPD reconstruction SPD(%d)->SPD(%d), N=%d, fp64 (sqrtm + rotation, 2 launches)'
                             % (d, D, n),
-                'matrices_per_s': self.world * n / (ms * 1e-3), 'ms_per_step': ms,
+                'matrices_per_s': self.world * n / (ms * 1e-3), 'ms_per_step': ms, 'sqrtm_ms': ms_sqrt,
                 'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': self.hbm_peak, 'unit': 'GB/s',
                              'frac': gbs / self.hbm_peak, 'algorithmic_bytes_per_launch': nbytes}}
 

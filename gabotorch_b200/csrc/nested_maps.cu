@@ -180,7 +180,7 @@ __global__ void spd_sqrtm_kernel(const double* __restrict__ mat, int64_t n, doub
 //     X = W Y W^T + E + E^T + Z,   E = W Y^(1/2) N,   N = K C^(1/2) V^T (d x D),   Z = V C V^T (D x D).
 // N and Z do not depend on the point: the setup kernel computes them once (C^(1/2) by a warp-cooperative two-sided
 // Jacobi in shared memory, any size up to 32), the batch kernel streams the points.
-// pack = [W (D x d) | N (d x D) | Z (D x D)] doubles.
+// pack = [W (D x d) | N (d x D) | Z (D x D) | P (K x D^2)] doubles (P: see the batch kernel).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxReconDim = 32;
 
@@ -282,50 +282,87 @@ nested_spd_reconstruct_setup_kernel(const double* __restrict__ w, const double* 
         for (int k = 0; k < m; ++k) acc = fma(Q[r * m + k], v[c * m + k], acc);
         pz[e] = acc;
     }
+    __syncwarp();
+    // P (K x D^2): coefficients of vec(Y) and of the upper triangle of S = Y^(1/2) in vec(X)
+    double* pp = pz + D * D;
+    const int dd = d * d, DD = D * D, K = dd + d * (d + 1) / 2;
+    for (int e = lane; e < K * DD; e += 32) {
+        const int k = e / DD, rc = e % DD, r = rc / D, c = rc % D;
+        double val;
+        if (k < dd) {
+            val = pw[r * d + k / d] * pw[c * d + k % d];                       // W Y W^T
+        } else {
+            int rem = k - dd, a = 0;
+            while (rem >= d - a) {
+                rem -= d - a;
+                ++a;
+            }
+            const int q = a + rem;                                              // S_aq, a <= q
+            val = pw[r * d + a] * pn[q * D + c] + pw[c * d + a] * pn[q * D + r];    // W S N + (W S N)^T
+            if (q != a) val += pw[r * d + q] * pn[a * D + c] + pw[c * d + q] * pn[a * D + r];
+        }
+        pp[e] = val;
+    }
 }
 
-// One CTA of 128 threads per point (grid-stride).  Output rows are written contiguously (coalesced).
-__global__ void __launch_bounds__(128)
+// The reconstruction is LINEAR in (Y, S = Y^(1/2)):  vec(X) = P^T u + vec(Z),  u = [vec(Y) (d^2) | S_aq, a <= q],
+// so a batch is one (n x K) x (K x D^2) contraction, K = d^2 + d(d+1)/2 (40 for SPD(5) -> SPD(20)).  P is built once by
+// the setup kernel and stays in L1/L2; a CTA takes 16 points at a time, stages their u in shared memory and every
+// thread owns output columns (coalesced P loads and X stores) with one fp64 accumulator per point: per k one P load,
+// 8 broadcast 128-bit shared loads and 16 DFMA -- bound by the fp64 pipe, not by load/store slots.
+constexpr int kReconPts = 16;
+constexpr int kReconThreads = 256;
+
+__global__ void __launch_bounds__(kReconThreads)
 nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __restrict__ sq, int64_t n, int D, int d,
                               const double* __restrict__ pack, double* __restrict__ x) {
-    extern __shared__ double sm[];
-    double* W = sm;                  // D x d
-    double* N = W + D * d;           // d x D
-    double* Z = N + d * D;           // D x D
-    double* T1 = Z + D * D;          // W Y      (D x d)
-    double* T2 = T1 + D * d;         // W Y^1/2  (D x d)
-    double* Yi = T2 + D * d;         // d x d
-    double* Si = Yi + d * d;         // d x d
+    extern __shared__ __align__(16) double u[];      // K x kReconPts
+    const int dd = d * d, DD = D * D, K = dd + d * (d + 1) / 2;
+    const double* __restrict__ Z = pack + 2 * D * d;
+    const double* __restrict__ P = Z + DD;
     const int tid = threadIdx.x;
-    for (int e = tid; e < 2 * D * d + D * D; e += 128) sm[e] = pack[e];
-    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const int64_t tiles = (n + kReconPts - 1) / kReconPts;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t i0 = t * kReconPts;
         __syncthreads();
-        for (int e = tid; e < d * d; e += 128) {
-            Yi[e] = y[i * d * d + e];
-            Si[e] = sq[i * d * d + e];
+        for (int e = tid; e < K * kReconPts; e += kReconThreads) {
+            const int pt = e / K, k = e % K;         // consecutive threads read consecutive entries of one point
+            const int64_t i = i0 + pt;
+            double v = 0.0;
+            if (i < n) {
+                if (k < dd) {
+                    v = y[i * dd + k];
+                } else {                              // k - dd enumerates (a, q), a <= q, row-major
+                    int rem = k - dd, a = 0;
+                    while (rem >= d - a) {
+                        rem -= d - a;
+                        ++a;
+                    }
+                    v = sq[i * dd + a * d + a + rem];
+                }
+            }
+            u[k * kReconPts + pt] = v;
         }
         __syncthreads();
-        for (int e = tid; e < D * d; e += 128) {
-            const int r = e / d, c = e % d;
-            double a1 = 0.0, a2 = 0.0;
-            for (int k = 0; k < d; ++k) {
-                a1 = fma(W[r * d + k], Yi[k * d + c], a1);
-                a2 = fma(W[r * d + k], Si[k * d + c], a2);
+        for (int c = tid; c < DD; c += kReconThreads) {
+            double acc[kReconPts];
+            const double z = Z[c];
+#pragma unroll
+            for (int pt = 0; pt < kReconPts; ++pt) acc[pt] = z;
+#pragma unroll 2
+            for (int k = 0; k < K; ++k) {
+                const double pk = P[k * DD + c];
+                const double2* uk = reinterpret_cast<const double2*>(u + k * kReconPts);
+#pragma unroll
+                for (int h = 0; h < kReconPts / 2; ++h) {
+                    const double2 uv = uk[h];
+                    acc[2 * h] = fma(uv.x, pk, acc[2 * h]);
+                    acc[2 * h + 1] = fma(uv.y, pk, acc[2 * h + 1]);
+                }
             }
-            T1[e] = a1;
-            T2[e] = a2;
-        }
-        __syncthreads();
-        double* xo = x + i * D * D;
-        for (int e = tid; e < D * D; e += 128) {
-            const int r = e / D, c = e % D;
-            double acc = Z[e];
-            for (int k = 0; k < d; ++k) {
-                acc = fma(T1[r * d + k], W[c * d + k], acc);
-                acc = fma(T2[r * d + k], N[k * D + c], acc);
-                acc = fma(T2[c * d + k], N[k * D + r], acc);
-            }
-            xo[e] = acc;
+#pragma unroll
+            for (int pt = 0; pt < kReconPts; ++pt)
+                if (i0 + pt < n) x[(i0 + pt) * DD + c] = acc[pt];
         }
     }
 }
@@ -408,7 +445,8 @@ static int check_recon_dims(const char* who, int D, int d) {
 
 extern "C" int64_t gabo_nested_spd_reconstruct_pack_size(int D, int d) {
     if (d < 1 || D <= d) return 0;
-    return static_cast<int64_t>(2) * D * d + static_cast<int64_t>(D) * D;
+    const int64_t K = static_cast<int64_t>(d) * d + static_cast<int64_t>(d) * (d + 1) / 2;
+    return static_cast<int64_t>(2) * D * d + static_cast<int64_t>(D) * D + K * D * D;
 }
 
 extern "C" int gabo_nested_spd_reconstruct_setup(const double* w, const double* v, const double* c, const double* k,
@@ -425,8 +463,11 @@ extern "C" int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt
     if (int rc = check_recon_dims("gabo_nested_spd_reconstruct", D, d)) return rc;
     if (n == 0) return GABO_OK;
     GABO_REQUIRE(y && y_sqrt && pack && x, GABO_E_ARG, "gabo_nested_spd_reconstruct: null pointer");
-    const size_t smem = sizeof(double) * (static_cast<size_t>(4) * D * d + static_cast<size_t>(D) * D + 2 * d * d);
-    const unsigned grid = static_cast<unsigned>(imin(n, static_cast<int64_t>(sm_count()) * 8));
-    nested_spd_reconstruct_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(y, y_sqrt, n, D, d, pack, x);
+    const int K = d * d + d * (d + 1) / 2;
+    const size_t smem = sizeof(double) * static_cast<size_t>(K) * kReconPts;
+    const int64_t tiles = (n + kReconPts - 1) / kReconPts;
+    const unsigned grid = static_cast<unsigned>(imin(tiles, static_cast<int64_t>(sm_count()) * 4));
+    nested_spd_reconstruct_kernel<<<grid, kReconThreads, smem, static_cast<cudaStream_t>(stream)>>>(y, y_sqrt, n, D, d,
+                                                                                                    pack, x);
     return check_launch("nested_spd_reconstruct_kernel");
 }

@@ -69,7 +69,7 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.gabo_nested_sphere_reconstruct(fake, 4, 6, 5, fake, fake, fake, null) == -1    # d_latent > D
     assert lib.gabo_nested_sphere_to_nested(fake, 4, 1, fake, 1.0, fake, null) == -1
     assert lib.gabo_spd_sqrtm(fake, 3, 9, fake, null) == -1
-    assert lib.gabo_nested_spd_reconstruct_pack_size(20, 5) == 2 * 20 * 5 + 400
+    assert lib.gabo_nested_spd_reconstruct_pack_size(20, 5) == 2 * 20 * 5 + 400 + (25 + 15) * 400
     assert lib.gabo_nested_spd_reconstruct_pack_size(5, 5) == 0
     assert lib.gabo_nested_spd_reconstruct(fake, fake, 4, 40, 5, fake, fake, null) == -1      # D > 32
     assert lib.gabo_nested_spd_reconstruct_setup(fake, fake, fake, fake, 5, 5, fake, fake, null) == -1
