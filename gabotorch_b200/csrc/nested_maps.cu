@@ -307,10 +307,10 @@ nested_spd_reconstruct_setup_kernel(const double* __restrict__ w, const double* 
 
 // The reconstruction is LINEAR in (Y, S = Y^(1/2)):  vec(X) = P^T u + vec(Z),  u = [vec(Y) (d^2) | S_aq, a <= q],
 // so a batch is one (n x K) x (K x D^2) contraction, K = d^2 + d(d+1)/2 (40 for SPD(5) -> SPD(20)).  P is built once by
-// the setup kernel and stays in L1/L2; a CTA takes 16 points at a time, stages their u in shared memory and every
+// the setup kernel and stays in L1/L2; a CTA takes 32 points at a time, stages their u in shared memory and every
 // thread owns output columns (coalesced P loads and X stores) with one fp64 accumulator per point: per k one P load,
-// 8 broadcast 128-bit shared loads and 16 DFMA -- bound by the fp64 pipe, not by load/store slots.
-constexpr int kReconPts = 16;
+// 16 broadcast 128-bit shared loads and 32 DFMA -- bound by the fp64 pipe, not by load/store slots.
+constexpr int kReconPts = 32;
 constexpr int kReconThreads = 256;
 
 __global__ void __launch_bounds__(kReconThreads)

@@ -87,7 +87,7 @@ if os.path.exists(lc):
         agg.setdefault((d['Kernel Name'], d['Grid Size'], d['Block Size']), []).append(v)
     tot = sum(sum(v) for v in agg.values())
     with open(os.path.join(out_dir, '%s_launches_summary.md' % tag), 'w') as f:
-        f.write('# launch list, round %s\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline`\n'
+        f.write('# launch list, round %s\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline`\n'
                 '(cold-cache, serialised; shares only).  `FillFunctor<unsigned char>` is the 256 MB L2 flush between timed steps.\n\n'
                 '| kernel | grid | block | launches | mean us | total us | share |\n|---|---|---|---|---|---|---|\n' % tag)
         for (k, g, b), v in agg.items():
