@@ -170,3 +170,24 @@ def test_gp_fit_transforms_priors_and_oracle_likelihood():
     base = np.exp(-th[0] * dm)
     np.testing.assert_allclose(grad, [0.5 * np.sum(w * (-th[1] * dm * base)), 0.5 * np.sum(w * base),
                                       0.5 * np.trace(w), alpha.sum()], rtol=1e-8, atol=1e-10)
+
+
+def test_trust_region_solver_surface_and_option_mapping():
+    # constructor surface of the reference's TrustRegions (robust_trust_regions.py:91-108) and what reaches the kernel
+    from gabotorch_b200 import manifold_optimization as mo
+    s = mo.TrustRegions()
+    assert (s.miniter, s.kappa, s.theta, s.rho_prime, s.use_rand, s.rho_regularization) == (3, 0.1, 1.0, 0.1, False, 1e3)
+    assert (s._maxiter, s._mingradnorm, s._maxtime) == (1000, 1e-6, 1000)          # pymanopt Solver defaults
+    o = mo._trust_region_options(mo.TrustRegions(kappa=0.2, maxiter=77, mingradnorm=1e-4, maxinner=3, Delta_bar=1.5))
+    assert o == dict(maxiter=77, mingradnorm=1e-4, kappa=0.2, theta=1.0, rho_prime=0.1, rho_regularization=1e3,
+                     mininner=1, maxinner=3, delta_bar=1.5, delta0=None)
+    with pytest.raises(NotImplementedError):
+        mo.TrustRegions(use_rand=True)
+
+    class Foreign:            # a pymanopt-style solver object of another class with the same name and use_rand set
+        use_rand = True
+    Foreign.__name__ = 'TrustRegions'
+    with pytest.raises(NotImplementedError):
+        mo._trust_region_options(Foreign())
+    with pytest.raises(NotImplementedError):
+        mo._solver_options(type('SteepestDescent', (), {})())
