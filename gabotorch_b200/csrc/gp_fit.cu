@@ -15,8 +15,8 @@
 namespace gabo {
 namespace {
 
-constexpr int kGpThreads = 256;
-constexpr int kMaxGpTrain = 128;
+constexpr int kGpThreads = 256;      // upper bound; the launch uses 64 / 128 / 256 threads for n <= 32 / 64 / 128 so that
+constexpr int kMaxGpTrain = 128;     // the per-column barriers of small problems synchronise 2 warps instead of 8
 
 __device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);
@@ -25,7 +25,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     if (lane == 0) red[w] = v;
     __syncthreads();
     double t = 0.0;
-    for (int i = 0; i < kGpThreads / 32; ++i) t += red[i];
+    for (int i = 0; i < static_cast<int>(blockDim.x) / 32; ++i) t += red[i];
     return t;
 }
 
@@ -43,16 +43,16 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
     double* dinv = vec + n;                                 // n : 1 / L_kk
     double* red = dinv + n;                                 // kGpThreads / 32
     __shared__ int bad;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t b = blockIdx.x;
     const double beta = FROM_GRAM ? theta_val.x : theta[b * 4 + 0], s = FROM_GRAM ? theta_val.y : theta[b * 4 + 1];
     const double noise = FROM_GRAM ? theta_val.z : theta[b * 4 + 2], mean = FROM_GRAM ? theta_val.w : theta[b * 4 + 3];
     if (tid == 0) bad = 0;
-    for (int e = tid; e < n * n; e += kGpThreads) {
+    for (int e = tid; e < n * n; e += nthr) {
         const int i = e / n, j = e % n;
         if (j <= i) A[i * ld + j] = fma(s, FROM_GRAM ? dmat[e] : exp(-beta * dmat[e]), (i == j) ? noise : 0.0);
     }
-    for (int i = tid; i < n; i += kGpThreads) vec[i] = y[i] - mean;
+    for (int i = tid; i < n; i += nthr) vec[i] = y[i] - mean;
     __syncthreads();
     // --- Cholesky, right-looking, in place (lower triangle) ---
     double logdet = 0.0;
@@ -69,11 +69,11 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
             A[k * ld + k] = lkk;
             dinv[k] = inv;
         }
-        for (int i = k + 1 + tid; i < n; i += kGpThreads) A[i * ld + k] *= inv;
+        for (int i = k + 1 + tid; i < n; i += nthr) A[i * ld + k] *= inv;
         __syncthreads();
         // trailing update of the lower triangle: rows i > k, columns k < j <= i
         const int m = n - k - 1;
-        for (int e = tid; e < m * m; e += kGpThreads) {
+        for (int e = tid; e < m * m; e += nthr) {
             const int i = k + 1 + e / m, j = k + 1 + e % m;
             if (j <= i) A[i * ld + j] = fma(-A[i * ld + k], A[j * ld + k], A[i * ld + j]);
         }
@@ -87,8 +87,8 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
             flags[b] = 1;
         }
         if (out_grad && tid < 4) out_grad[b * 4 + tid] = nanv;
-        if (out_alpha) for (int i = tid; i < n; i += kGpThreads) out_alpha[b * n + i] = nanv;
-        if (out_kinv) for (int e = tid; e < n * n; e += kGpThreads) out_kinv[b * n * n + e] = nanv;
+        if (out_alpha) for (int i = tid; i < n; i += nthr) out_alpha[b * n + i] = nanv;
+        if (out_kinv) for (int e = tid; e < n * n; e += nthr) out_kinv[b * n * n + e] = nanv;
         return;
     }
     // --- L z = r (column-oriented forward substitution), quad = z^T z ---
@@ -96,18 +96,18 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
         const double zk = vec[k] * dinv[k];
         __syncthreads();
         if (tid == 0) vec[k] = zk;
-        for (int i = k + 1 + tid; i < n; i += kGpThreads) vec[i] = fma(-A[i * ld + k], zk, vec[i]);
+        for (int i = k + 1 + tid; i < n; i += nthr) vec[i] = fma(-A[i * ld + k], zk, vec[i]);
         __syncthreads();
     }
     double quad = 0.0;
-    for (int i = tid; i < n; i += kGpThreads) quad = fma(vec[i], vec[i], quad);
+    for (int i = tid; i < n; i += nthr) quad = fma(vec[i], vec[i], quad);
     quad = block_sum(quad, red);
     // --- L^T alpha = z (backward substitution) ---
     for (int k = n - 1; k >= 0; --k) {
         const double ak = vec[k] * dinv[k];
         __syncthreads();
         if (tid == 0) vec[k] = ak;
-        for (int i = tid; i < k; i += kGpThreads) vec[i] = fma(-A[k * ld + i], ak, vec[i]);
+        for (int i = tid; i < k; i += nthr) vec[i] = fma(-A[k * ld + i], ak, vec[i]);
         __syncthreads();
     }
     const double ll = -0.5 * (quad + logdet + n * 1.8378770664093453);   // log(2 pi)
@@ -115,10 +115,10 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
         if (out_ll) out_ll[b] = ll;
         flags[b] = 0;
     }
-    if (out_alpha) for (int i = tid; i < n; i += kGpThreads) out_alpha[b * n + i] = vec[i];
+    if (out_alpha) for (int i = tid; i < n; i += nthr) out_alpha[b * n + i] = vec[i];
     if (!out_grad && !out_kinv) return;
     // --- X = L^-1, one column per thread, stored transposed in the strict upper triangle: A[j][i] = X_ij, i > j ---
-    for (int j = tid; j < n; j += kGpThreads) {
+    for (int j = tid; j < n; j += nthr) {
         for (int i = j + 1; i < n; ++i) {
             double acc = A[i * ld + j] * dinv[j];           // L_ij X_jj
             for (int k = j + 1; k < i; ++k) acc = fma(A[i * ld + k], A[j * ld + k], acc);
@@ -129,7 +129,7 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
     // --- K^-1 = X^T X entry by entry; gradient sums over the lower triangle ---
     double gb = 0.0, gs = 0.0, gn = 0.0, gm = 0.0;
     const int tri = n * (n + 1) / 2;
-    for (int e = tid; e < tri; e += kGpThreads) {
+    for (int e = tid; e < tri; e += nthr) {
         // e -> (i, j), j <= i
         int i = static_cast<int>((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
         while ((i + 1) * (i + 2) / 2 <= e) ++i;
@@ -150,7 +150,7 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
         gb = fma(mult * w, -s * dm * base, gb);
         if (i == j) gn = fma(0.5, w, gn);
     }
-    for (int i = tid; i < n; i += kGpThreads) gm += vec[i];
+    for (int i = tid; i < n; i += nthr) gm += vec[i];
     if (out_grad) {
         gb = block_sum(gb, red);
         gs = block_sum(gs, red);
@@ -169,6 +169,8 @@ gp_mll_kernel(const double* __restrict__ dmat, int n, const double* __restrict__
 }  // namespace gabo
 
 using namespace gabo;
+
+static unsigned gp_threads(int64_t n) { return n <= 32 ? 64u : (n <= 64 ? 128u : static_cast<unsigned>(kGpThreads)); }
 
 static void configure_smem() {
     static bool configured = false;
@@ -189,7 +191,7 @@ extern "C" int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const
     GABO_REQUIRE(dmat && y && theta && out_ll && flags, GABO_E_ARG, "gabo_gp_mll: null pointer");
     const size_t smem = sizeof(double) * (static_cast<size_t>(n) * (n + 1) + 2 * n + kGpThreads / 32);
     configure_smem();
-    gp_mll_kernel<false><<<static_cast<unsigned>(batch), kGpThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    gp_mll_kernel<false><<<static_cast<unsigned>(batch), gp_threads(n), smem, static_cast<cudaStream_t>(stream)>>>(
         dmat, static_cast<int>(n), y, theta, make_double4(0, 0, 0, 0), out_ll, out_grad, out_alpha, out_kinv, flags);
     return check_launch("gp_mll_kernel");
 }
@@ -201,7 +203,7 @@ extern "C" int gabo_gp_factor(const double* kmat, int64_t n, const double* y, do
     GABO_REQUIRE(kmat && y && out_alpha && out_kinv && flag, GABO_E_ARG, "gabo_gp_factor: null pointer");
     const size_t smem = sizeof(double) * (static_cast<size_t>(n) * (n + 1) + 2 * n + kGpThreads / 32);
     configure_smem();
-    gp_mll_kernel<true><<<1, kGpThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    gp_mll_kernel<true><<<1, gp_threads(n), smem, static_cast<cudaStream_t>(stream)>>>(
         kmat, static_cast<int>(n), y, nullptr, make_double4(0.0, outputscale, noise, mean), nullptr, nullptr, out_alpha,
         out_kinv, flag);
     return check_launch("gp_mll_kernel");

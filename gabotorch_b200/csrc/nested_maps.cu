@@ -313,19 +313,19 @@ nested_spd_reconstruct_setup_kernel(const double* __restrict__ w, const double* 
 constexpr int kReconPts = 32;
 constexpr int kReconThreads = 256;
 
-__global__ void __launch_bounds__(kReconThreads)
+__global__ void __launch_bounds__(kReconThreads, 2)
 nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __restrict__ sq, int64_t n, int D, int d,
                               const double* __restrict__ pack, double* __restrict__ x) {
     extern __shared__ __align__(16) double u[];      // K x kReconPts
     const int dd = d * d, DD = D * D, K = dd + d * (d + 1) / 2;
     const double* __restrict__ Z = pack + 2 * D * d;
     const double* __restrict__ P = Z + DD;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t tiles = (n + kReconPts - 1) / kReconPts;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int64_t i0 = t * kReconPts;
         __syncthreads();
-        for (int e = tid; e < K * kReconPts; e += kReconThreads) {
+        for (int e = tid; e < K * kReconPts; e += nthr) {
             const int pt = e / K, k = e % K;         // consecutive threads read consecutive entries of one point
             const int64_t i = i0 + pt;
             double v = 0.0;
@@ -344,12 +344,12 @@ nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __rest
             u[k * kReconPts + pt] = v;
         }
         __syncthreads();
-        for (int c = tid; c < DD; c += kReconThreads) {
+        for (int c = tid; c < DD; c += nthr) {
             double acc[kReconPts];
             const double z = Z[c];
 #pragma unroll
             for (int pt = 0; pt < kReconPts; ++pt) acc[pt] = z;
-#pragma unroll 2
+#pragma unroll 4
             for (int k = 0; k < K; ++k) {
                 const double pk = P[k * DD + c];
                 const double2* uk = reinterpret_cast<const double2*>(u + k * kReconPts);
@@ -467,7 +467,9 @@ extern "C" int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt
     const size_t smem = sizeof(double) * static_cast<size_t>(K) * kReconPts;
     const int64_t tiles = (n + kReconPts - 1) / kReconPts;
     const unsigned grid = static_cast<unsigned>(imin(tiles, static_cast<int64_t>(sm_count()) * 4));
-    nested_spd_reconstruct_kernel<<<grid, kReconThreads, smem, static_cast<cudaStream_t>(stream)>>>(y, y_sqrt, n, D, d,
-                                                                                                    pack, x);
+    // block size: the D^2 output columns split evenly over the passes of the column loop (D = 20: 2 passes of 224 threads)
+    const int passes = (D * D + kReconThreads - 1) / kReconThreads;
+    const unsigned threads = static_cast<unsigned>(32 * (((D * D + passes - 1) / passes + 31) / 32));
+    nested_spd_reconstruct_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(y, y_sqrt, n, D, d, pack, x);
     return check_launch("nested_spd_reconstruct_kernel");
 }
