@@ -307,13 +307,15 @@ nested_spd_reconstruct_setup_kernel(const double* __restrict__ w, const double* 
 
 // The reconstruction is LINEAR in (Y, S = Y^(1/2)):  vec(X) = P^T u + vec(Z),  u = [vec(Y) (d^2) | S_aq, a <= q],
 // so a batch is one (n x K) x (K x D^2) contraction, K = d^2 + d(d+1)/2 (40 for SPD(5) -> SPD(20)).  P is built once by
-// the setup kernel and stays in L1/L2; a CTA takes 32 points at a time, stages their u in shared memory and every
-// thread owns output columns (coalesced P loads and X stores) with one fp64 accumulator per point: per k one P load,
-// 16 broadcast 128-bit shared loads and 32 DFMA -- bound by the fp64 pipe, not by load/store slots.
+// the setup kernel and stays in L1/L2; a CTA takes 32 points at a time and stages their u in shared memory.  A work
+// item is 2 output columns x 8 points (16 fp64 accumulators, <= 85 registers so that three CTAs share an SM): per k
+// one 128-bit P load, 4 broadcast 128-bit shared loads and 16 DFMA.  (ncu on the earlier versions: 1 column x 32 points
+// was bound by the shared-memory pipe, 2 columns x 16 points by occupancy -- 144 registers, one CTA per SM.)
 constexpr int kReconPts = 32;
+constexpr int kReconHalf = 8;      // points per work item
 constexpr int kReconThreads = 256;
 
-__global__ void __launch_bounds__(kReconThreads, 2)
+__global__ void __launch_bounds__(kReconThreads, 3)
 nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __restrict__ sq, int64_t n, int D, int d,
                               const double* __restrict__ pack, double* __restrict__ x) {
     extern __shared__ __align__(16) double u[];      // K x kReconPts
@@ -321,6 +323,8 @@ nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __rest
     const double* __restrict__ Z = pack + 2 * D * d;
     const double* __restrict__ P = Z + DD;
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const int ncp = (DD + 1) / 2, items = ncp * (kReconPts / kReconHalf);
+    const bool even = (DD & 1) == 0 && ((reinterpret_cast<uintptr_t>(pack) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
     const int64_t tiles = (n + kReconPts - 1) / kReconPts;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int64_t i0 = t * kReconPts;
@@ -344,25 +348,49 @@ nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __rest
             u[k * kReconPts + pt] = v;
         }
         __syncthreads();
-        for (int c = tid; c < DD; c += nthr) {
-            double acc[kReconPts];
-            const double z = Z[c];
+        for (int it = tid; it < items; it += nthr) {
+            const int cp = it % ncp, h = it / ncp;
+            const int c0 = 2 * cp, c1 = (c0 + 1 < DD) ? c0 + 1 : c0;
+            double a0[kReconHalf], a1[kReconHalf];
+            const double z0 = Z[c0], z1 = Z[c1];
 #pragma unroll
-            for (int pt = 0; pt < kReconPts; ++pt) acc[pt] = z;
-#pragma unroll 4
+            for (int pt = 0; pt < kReconHalf; ++pt) {
+                a0[pt] = z0;
+                a1[pt] = z1;
+            }
+#pragma unroll 2
             for (int k = 0; k < K; ++k) {
-                const double pk = P[k * DD + c];
-                const double2* uk = reinterpret_cast<const double2*>(u + k * kReconPts);
+                double p0, p1;
+                if (even) {                                       // 16-byte aligned pair (pack offsets are even)
+                    const double2 pv = *reinterpret_cast<const double2*>(P + k * DD + c0);
+                    p0 = pv.x;
+                    p1 = pv.y;
+                } else {
+                    p0 = P[k * DD + c0];
+                    p1 = P[k * DD + c1];
+                }
+                const double2* uk = reinterpret_cast<const double2*>(u + k * kReconPts + h * kReconHalf);
 #pragma unroll
-                for (int h = 0; h < kReconPts / 2; ++h) {
-                    const double2 uv = uk[h];
-                    acc[2 * h] = fma(uv.x, pk, acc[2 * h]);
-                    acc[2 * h + 1] = fma(uv.y, pk, acc[2 * h + 1]);
+                for (int q = 0; q < kReconHalf / 2; ++q) {
+                    const double2 uv = uk[q];
+                    a0[2 * q] = fma(uv.x, p0, a0[2 * q]);
+                    a0[2 * q + 1] = fma(uv.y, p0, a0[2 * q + 1]);
+                    a1[2 * q] = fma(uv.x, p1, a1[2 * q]);
+                    a1[2 * q + 1] = fma(uv.y, p1, a1[2 * q + 1]);
                 }
             }
+            const int64_t ib = i0 + h * kReconHalf;
 #pragma unroll
-            for (int pt = 0; pt < kReconPts; ++pt)
-                if (i0 + pt < n) x[(i0 + pt) * DD + c] = acc[pt];
+            for (int pt = 0; pt < kReconHalf; ++pt) {
+                if (ib + pt < n) {
+                    if (even) {
+                        *reinterpret_cast<double2*>(x + (ib + pt) * DD + c0) = make_double2(a0[pt], a1[pt]);
+                    } else {
+                        x[(ib + pt) * DD + c0] = a0[pt];
+                        if (c1 != c0) x[(ib + pt) * DD + c1] = a1[pt];
+                    }
+                }
+            }
         }
     }
 }
@@ -466,10 +494,13 @@ extern "C" int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt
     const int K = d * d + d * (d + 1) / 2;
     const size_t smem = sizeof(double) * static_cast<size_t>(K) * kReconPts;
     const int64_t tiles = (n + kReconPts - 1) / kReconPts;
-    const unsigned grid = static_cast<unsigned>(imin(tiles, static_cast<int64_t>(sm_count()) * 4));
-    // block size: the D^2 output columns split evenly over the passes of the column loop (D = 20: 2 passes of 224 threads)
-    const int passes = (D * D + kReconThreads - 1) / kReconThreads;
-    const unsigned threads = static_cast<unsigned>(32 * (((D * D + passes - 1) / passes + 31) / 32));
+    const unsigned grid = static_cast<unsigned>(imin(tiles, static_cast<int64_t>(sm_count()) * 6));
+    // block size: the work items (column pairs x point halves) split evenly over the passes of the item loop
+    const int items = ((D * D + 1) / 2) * (kReconPts / kReconHalf);
+    const int passes = (items + kReconThreads - 1) / kReconThreads;
+    const unsigned threads = static_cast<unsigned>(32 * (((items + passes - 1) / passes + 31) / 32));
+    // a quarter of the unified L1 as shared memory (three 10 KB tiles per SM), the rest caches the operator P
+    cudaFuncSetAttribute(nested_spd_reconstruct_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
     nested_spd_reconstruct_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(y, y_sqrt, n, D, d, pack, x);
     return check_launch("nested_spd_reconstruct_kernel");
 }
