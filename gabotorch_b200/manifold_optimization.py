@@ -93,6 +93,169 @@ def _trust_region_options(solver):
     )
 
 
+def _rtr_kernel_covers(gp):
+    """The register-resident trust-region kernel (gabo_acq_rtr): sphere, ambient dimension <= 8, or <= 16 with at most
+    64 training points."""
+    return gp.manifold == _lib.SPHERE and (gp.dim <= 8 or (gp.dim <= 16 and gp.n_train <= 64))
+
+
+def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1,
+                          rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None):
+    """The reference's ``TrustRegions.solve`` (robust_trust_regions.py:116-352, tCG :410-520, finite-difference Hessian
+    approximate_hessian.py:11-62) for ALL restarts in lock-step, for the cases the single-launch kernel does not cover:
+    SPD(d) and spheres of large ambient dimension.  Every cost / gradient evaluation is one launch of ``gabo_ei_eval``
+    over the whole batch, every retraction / inner product one launch of ``gabo_spd_op`` / ``gabo_spd_scalar``
+    (pymanopt ``PositiveDefinite``: exp-map retraction, identity transport, affine-invariant inner product); the
+    per-restart scalars of the recurrences live in (R,) device tensors and finished restarts are masked out, so each
+    restart follows exactly the serial algorithm.  Returns (candidates, values, iters, reasons) like ``ops.acq_rtr``.
+    Launch-bound by construction (about 8 launches per inner iteration); fusing it into the CTA-per-restart SPD kernel
+    is the next step."""
+    X = ops.to_dev64(x0).clone()
+    R = X.shape[0]
+    dev = X.device
+    lead = (R,) + (1,) * (X.dim() - 1)
+
+    def bc(v):
+        return v.reshape(lead)
+
+    if gp.manifold == _lib.SPD:
+        d = X.shape[-1]
+        dim, typical = d * (d + 1) // 2, math.sqrt(d * (d + 1) // 2)      # pymanopt PositiveDefinite.dim / typicaldist
+
+        def inner(P, U, V):
+            return ops.spd_scalar(2, P, U, V)
+
+        def norm(P, U):
+            return ops.spd_scalar(1, P, U)
+
+        def retr(P, U):
+            return ops.spd_op(_lib.OP_RETR, P, U)
+
+        def transp(P1, P, G):                                             # pymanopt 0.2.x: identity
+            return G
+    else:
+        dim, typical = X.shape[-1] - 1, math.pi                           # pymanopt Sphere.dim / typicaldist
+
+        def inner(P, U, V):
+            return (U * V).sum(-1)
+
+        def norm(P, U):
+            return (U * U).sum(-1).sqrt()
+
+        def retr(P, U):
+            Y = P + U
+            return Y / Y.norm(dim=-1, keepdim=True)
+
+        def transp(P1, P, G):                                             # projection onto the tangent space at P
+            return G - (P * G).sum(-1, keepdim=True) * P
+
+    inf = torch.full((R,), float('inf'), dtype=torch.float64, device=dev)
+
+    def cost(P):
+        c = -ops.ei_eval(gp, P)
+        return torch.where(torch.isfinite(c), c, inf)
+
+    def cost_grad(P):
+        ei, g = ops.ei_eval(gp, P, want_grad=True)
+        c = -ei
+        return torch.where(torch.isfinite(c), c, inf), -g
+
+    maxinner = int(dim if maxinner is None else maxinner)
+    delta_bar = float(typical if delta_bar is None else delta_bar)
+    delta0 = float(delta_bar / 8 if delta0 is None else delta0)
+    fd_eps = 2.0 ** -14                                                   # approximate_hessian.py:43
+    eps = 2.220446049250313e-16                                           # np.spacing(1)
+    NEG, EXC, LIN, SUP, MAXI, INC = range(6)
+
+    def hess(P, G, A):
+        na = norm(P, A)
+        small = na < 1e-15
+        c = bc(fd_eps / torch.where(small, torch.ones_like(na), na))
+        P1 = retr(P, c * A)
+        _, G1 = cost_grad(P1)
+        H = transp(P1, P, G1) / c - G / c
+        return torch.where(bc(small), torch.zeros_like(H), H)
+
+    fx, G = cost_grad(X)
+    ng = norm(X, G)
+    radius = torch.full((R,), delta0, dtype=torch.float64, device=dev)
+    k = torch.zeros(R, dtype=torch.int32, device=dev)
+    reason = torch.zeros(R, dtype=torch.int32, device=dev)
+    active = torch.ones(R, dtype=torch.bool, device=dev)
+    zero = torch.zeros(R, dtype=torch.float64, device=dev)
+    while bool(active.any()):
+        # ---- truncated CG (use_rand=False, identity preconditioner) ----
+        eta, heta, r = torch.zeros_like(X), torch.zeros_like(X), G.clone()
+        e_pe, e_pd, model_value = zero.clone(), zero.clone(), zero.clone()
+        r_r = inner(X, r, r)
+        norm_r0 = r_r.sqrt()
+        z_r, d_pd, delta = r_r.clone(), r_r.clone(), -r
+        stop = torch.full((R,), MAXI, dtype=torch.int32, device=dev)
+        live = active.clone()
+        r2 = radius * radius
+        pw = norm_r0 ** theta
+        for j in range(maxinner):
+            if not bool(live.any()):
+                break
+            hdelta = hess(X, G, delta)
+            d_hd = inner(X, delta, hdelta)
+            nz = d_hd != 0
+            alpha = torch.where(nz, z_r / torch.where(nz, d_hd, torch.ones_like(d_hd)), zero)
+            e_pe_new = torch.where(nz, e_pe + 2 * alpha * e_pd + alpha * alpha * d_pd, e_pe)
+            out1 = live & ((d_hd <= 0) | (e_pe_new >= r2))
+            tau = (-e_pd + (e_pd * e_pd + d_pd * (r2 - e_pe)).sqrt()) / d_pd
+            eta = torch.where(bc(out1), eta + bc(tau) * delta, eta)
+            heta = torch.where(bc(out1), heta + bc(tau) * hdelta, heta)
+            stop = torch.where(out1, torch.where(d_hd <= 0, NEG, EXC).to(torch.int32), stop)
+            live = live & ~out1
+            new_eta = eta + bc(alpha) * delta
+            new_heta = heta + bc(alpha) * hdelta
+            new_mv = inner(X, new_eta, G) + 0.5 * inner(X, new_eta, new_heta)
+            out2 = live & (new_mv >= model_value)
+            stop = torch.where(out2, torch.full_like(stop, INC), stop)
+            live = live & ~out2
+            eta = torch.where(bc(live), new_eta, eta)
+            heta = torch.where(bc(live), new_heta, heta)
+            model_value = torch.where(live, new_mv, model_value)
+            e_pe = torch.where(live, e_pe_new, e_pe)
+            r = torch.where(bc(live), r + bc(alpha) * hdelta, r)
+            r_r = inner(X, r, r)
+            out3 = live & (r_r.sqrt() <= norm_r0 * torch.minimum(pw, torch.full_like(pw, kappa)))
+            if j < mininner:
+                out3 = out3 & False
+            stop = torch.where(out3, torch.where(kappa < pw, LIN, SUP).to(torch.int32), stop)
+            live = live & ~out3
+            beta = r_r / z_r
+            delta = torch.where(bc(live), -r + bc(beta) * delta, delta)
+            e_pd = torch.where(live, beta * (e_pd + alpha * d_pd), e_pd)
+            d_pd = torch.where(live, r_r + beta * beta * d_pd, d_pd)
+            z_r = torch.where(live, r_r, z_r)
+        # ---- proposal, rho, radius update, acceptance (robust_trust_regions.py:225-311) ----
+        x_prop = retr(X, eta)
+        fx_prop = cost(x_prop)
+        rho_reg = torch.clamp(fx.abs(), min=1.0) * eps * rho_regularization
+        rhonum = fx - fx_prop + rho_reg
+        rhoden = -inner(X, G, eta) - 0.5 * inner(X, eta, heta) + rho_reg
+        model_decreased = rhoden >= 0
+        rho = rhonum / rhoden
+        shrink = (rho < 0.25) | ~model_decreased | torch.isnan(rho)
+        grow = ~shrink & (rho > 0.75) & ((stop == NEG) | (stop == EXC))
+        radius = torch.where(active & shrink, radius / 4,
+                             torch.where(active & grow, torch.clamp(2 * radius, max=delta_bar), radius))
+        accept = active & model_decreased & (rho > rho_prime)
+        X = torch.where(bc(accept), x_prop, X)
+        fx = torch.where(accept, fx_prop, fx)
+        _, g_new = cost_grad(X)
+        G = torch.where(bc(accept), g_new, G)
+        ng = torch.where(accept, norm(X, G), ng)
+        k = k + active.to(torch.int32)
+        hit_iter = active & (k >= maxiter)
+        hit_grad = active & ~hit_iter & (ng < mingradnorm)
+        reason = torch.where(hit_iter, torch.ones_like(reason), torch.where(hit_grad, 2 * torch.ones_like(reason), reason))
+        active = active & ~(hit_iter | hit_grad)
+    return X, ops.ei_eval(gp, X), k, reason
+
+
 def _solver_options(solver):
     name = type(solver).__name__
     if name != 'ConjugateGradient':
@@ -311,8 +474,6 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
         raise NotImplementedError('solver-side initialisation (population methods) is not supported')
     kind = _manifold_kind(manifold)
     trust_region = type(solver).__name__ == 'TrustRegions'
-    if trust_region and kind != _lib.SPHERE:
-        raise NotImplementedError('the batched trust-region solver covers the sphere; use ConjugateGradient on SPD')
     sopts = _trust_region_options(solver) if trust_region else _solver_options(solver)
     if not isinstance(acquisition_function, ExpectedImprovement):
         raise NotImplementedError('the B200 optimiser evaluates ExpectedImprovement in closed form; got %s'
@@ -328,7 +489,13 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     if x0.dim() < 3 or x0.shape[1] != 1:
         raise NotImplementedError('initial_conditions must be R x 1 x ... (q = 1, manifold_optimize.py:206)')
     pts = x0[:, 0]
-    cand, val, iters, reason = (ops.acq_rtr if trust_region else ops.acq_rcg)(gp, pts, **sopts)
+    if not trust_region:
+        solve = ops.acq_rcg
+    elif _rtr_kernel_covers(gp):
+        solve = ops.acq_rtr                      # one launch, one warp per restart
+    else:
+        solve = batched_trust_regions            # SPD / large spheres: lock-step over the batched kernels
+    cand, val, iters, reason = solve(gp, pts, **sopts)
     candidates = cand[:, None]
     if post_processing_manifold is not None:
         candidates = post_processing_manifold(candidates)

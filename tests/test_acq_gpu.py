@@ -271,8 +271,44 @@ def test_rtr_through_the_reference_api_and_argument_errors():
     assert tuple(best.shape) == (1, 3) and abs(float(best.norm()) - 1.0) < 1e-12
     with pytest.raises(NotImplementedError):
         g.TrustRegions(use_rand=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                                            # GP on the sphere, solver manifold SPD
         g.gen_candidates_manifold(x0, ei, g.PositiveDefinite(2), g.TrustRegions())
     rng2, gp = sphere_problem(20, 16, beta=1.0, noise=1e-2, seed=1)
     with pytest.raises(_lib.GaboError):
         ops.acq_rtr(device_gp(gp, _lib.GABO_F64), osph.rand(rng2, 4, 20))      # dimension beyond the register kernel
+
+
+@pytest.mark.parametrize('manifold,dim,n,R', [('spd', 3, 16, 24), ('sphere', 20, 32, 16)])
+def test_lockstep_trust_regions_on_device_vs_oracle(manifold, dim, n, R):
+    # SPD(d) and large spheres: the reference's TrustRegions for all restarts in lock-step over the batched kernels
+    # (gabo_ei_eval, gabo_spd_op, gabo_spd_scalar); the host logic alone is checked on CPU in tests/test_host_logic.py
+    from gabotorch_b200 import manifold_optimization as mo
+    from oracle import rtr as ortr
+    if manifold == 'spd':
+        rng, gp = spd_problem(dim, n, beta=0.5 + math.log(2.0), noise=1e-2, seed=21)
+        x0 = ospd.spd_sample(rng, R, dim, max_cond=50.0)
+    else:
+        rng, gp = sphere_problem(dim, n, beta=0.35 + math.log(2.0), noise=1e-2, seed=22)
+        x0 = osph.rand(rng, R, dim)
+    dgp = device_gp(gp, _lib.GABO_F64)
+    assert not mo._rtr_kernel_covers(dgp)
+    X, val, iters, reason = mo.batched_trust_regions(dgp, x0, maxiter=15)
+    X, val, iters = X.cpu().numpy(), val.cpu().numpy(), iters.cpu().numpy()
+    ei0 = np.array([ogp.ei_and_grad(gp, xi, want_grad=False)[0] for xi in x0])
+    assert (val >= ei0 - 1e-9 * max(1.0, ei0.max())).all()                     # no accepted step increases the cost
+    assert set(np.unique(reason.cpu().numpy())) <= {1, 2} and (iters >= 1).all() and (iters <= 15).all()
+    opts = ortr.TROptions(maxiter=15)
+    same = 0
+    for i in range(6):
+        xi, ci, ki = ortr.solve_tr(gp, x0[i], opts)
+        check = ogp.ei_and_grad(gp, X[i], want_grad=False)[0]
+        assert abs(val[i] - check) <= 1e-6 * max(abs(check), 1e-12)
+        if ki == iters[i]:
+            same += 1
+            np.testing.assert_allclose(X[i], xi, rtol=0, atol=1e-5)
+            assert abs(val[i] + ci) <= 1e-6 * max(abs(ci), 1e-12)
+    assert same >= 4
+    if manifold == 'spd':
+        assert np.linalg.eigvalsh(0.5 * (X + np.swapaxes(X, -1, -2))).min() > 0
+    else:
+        np.testing.assert_allclose(np.linalg.norm(X, axis=-1), 1.0, atol=1e-12)

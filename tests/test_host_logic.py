@@ -191,3 +191,74 @@ def test_trust_region_solver_surface_and_option_mapping():
         mo._trust_region_options(Foreign())
     with pytest.raises(NotImplementedError):
         mo._solver_options(type('SteepestDescent', (), {})())
+
+
+class _OracleOps:
+    """CPU stand-ins for the batched CUDA entry points the lock-step trust-region driver calls (same signatures as
+    gabotorch_b200.ops), backed by the oracle: lets the masking / recurrence logic be checked without a GPU."""
+
+    def __init__(self, gp):
+        self.gp = gp
+
+    def to_dev64(self, x):
+        return torch.as_tensor(x, dtype=torch.float64)
+
+    def ei_eval(self, gp, x, want_grad=False):
+        from oracle import gp as ogp
+        x = torch.as_tensor(x, dtype=torch.float64).numpy()
+        ei, gr = [], []
+        for p in x:
+            try:
+                e, g = ogp.ei_and_grad(self.gp, p, want_grad=True)
+            except np.linalg.LinAlgError:
+                e, g = np.nan, np.full(p.shape, np.nan)
+            ei.append(e)
+            gr.append(g)
+        ei, gr = torch.tensor(np.array(ei)), torch.tensor(np.array(gr))
+        return (ei, gr) if want_grad else ei
+
+    def spd_scalar(self, what, x, b, c=None):
+        from oracle import spd as ospd
+        x, b = x.numpy(), b.numpy()
+        if what == 1:
+            return torch.tensor(np.array([ospd.norm(p, u) for p, u in zip(x, b)]))
+        return torch.tensor(np.array([ospd.inner(p, u, v) for p, u, v in zip(x, b, c.numpy())]))
+
+    def spd_op(self, op, a, b, c=None):
+        from oracle import spd as ospd
+        return torch.tensor(np.array([ospd.retr(p, u) for p, u in zip(a.numpy(), b.numpy())]))
+
+
+@pytest.mark.parametrize('manifold,dim,n,R', [('spd', 2, 10, 6), ('spd', 3, 12, 5), ('sphere', 20, 16, 6)])
+def test_lockstep_trust_regions_follow_the_serial_solver(monkeypatch, manifold, dim, n, R):
+    # batched_trust_regions advances all restarts together with masks; each restart must follow the serial algorithm
+    # of the reference's TrustRegions (oracle/rtr.py, pinned on the reference's own class) iteration for iteration
+    from gabotorch_b200 import _lib, manifold_optimization as mo, ops
+    from oracle import gp as ogp, rtr as ortr, sphere as osph, spd as ospd
+    rng = np.random.default_rng(dim + n)
+    if manifold == 'spd':
+        xt = ospd.spd_sample(rng, n, dim, max_cond=50.0)
+        y = ospd.ackley(ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(xt)))
+        x0 = ospd.spd_sample(rng, R, dim, max_cond=50.0)
+        beta = 0.5 + math.log(2.0)
+    else:
+        xt = osph.rand(rng, n, dim)
+        y = osph.ackley(xt)
+        x0 = osph.rand(rng, R, dim)
+        beta = 0.35 + math.log(2.0)
+    gp = ogp.make_gp(manifold, xt, y, beta=beta, noise=1e-2)
+    fake = _OracleOps(gp)
+    for name in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op'):
+        monkeypatch.setattr(ops, name, getattr(fake, name))
+    handle = type('GP', (), {'manifold': _lib.SPD if manifold == 'spd' else _lib.SPHERE, 'dim': dim, 'n_train': n})()
+    assert not mo._rtr_kernel_covers(handle)
+    X, val, iters, reason = mo.batched_trust_regions(handle, x0, maxiter=12)
+    opts = ortr.TROptions(maxiter=12)
+    for i in range(R):
+        xi, ci, ki = ortr.solve_tr(gp, x0[i], opts)
+        assert int(iters[i]) == ki
+        np.testing.assert_allclose(X[i].numpy(), xi, rtol=0, atol=1e-9)
+        assert abs(float(val[i]) + ci) <= 1e-10 * max(1.0, abs(ci))
+        assert int(reason[i]) == (1 if ki >= 12 else 2)
+    small = type('GP', (), {'manifold': _lib.SPHERE, 'dim': 6, 'n_train': 32})()
+    assert mo._rtr_kernel_covers(small)
