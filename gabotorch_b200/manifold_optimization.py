@@ -494,7 +494,11 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     elif _rtr_kernel_covers(gp):
         solve = ops.acq_rtr                      # one launch, one warp per restart
     else:
-        solve = batched_trust_regions            # SPD / large spheres: lock-step over the batched kernels
+        # SPD / large spheres: lock-step over the batched kernels, evaluated in fp64 -- the solver's stopping rule
+        # (|grad| < 1e-6) lies below the fp32 noise floor of the SPD gradient (measured: fp32 solves run to maxiter),
+        # and this path is launch-bound, so the arithmetic type does not set its speed
+        solve = batched_trust_regions
+        gp = gp.with_compute(_lib.GABO_F64)
     cand, val, iters, reason = solve(gp, pts, **sopts)
     candidates = cand[:, None]
     if post_processing_manifold is not None:

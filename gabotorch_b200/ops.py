@@ -474,6 +474,14 @@ class DeviceGP:
     def point_shape(self):
         return (self.dim,) if self.manifold == _lib.SPHERE else (self.dim, self.dim)
 
+    def with_compute(self, compute):
+        """The same GP (shared device arrays) evaluated in another arithmetic type (GABO_F32 | GABO_F64)."""
+        if int(self.desc.compute) == int(compute):
+            return self
+        d = self.desc
+        return DeviceGP(self.manifold, self.dim, self.x_train, self.alpha, self.minv, d.mean, d.outputscale, d.beta,
+                        d.best_f, d.kxx, compute)
+
 
 def ei_eval(gp, x, want_grad=False):
     """EI (and its Riemannian gradient) at r points; x: (r, D) or (r, d, d)."""

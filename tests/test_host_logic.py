@@ -262,3 +262,43 @@ def test_lockstep_trust_regions_follow_the_serial_solver(monkeypatch, manifold, 
         assert int(reason[i]) == (1 if ki >= 12 else 2)
     small = type('GP', (), {'manifold': _lib.SPHERE, 'dim': 6, 'n_train': 32})()
     assert mo._rtr_kernel_covers(small)
+
+
+def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
+    # gen_candidates_manifold: sphere of small dimension -> gabo_acq_rtr (one launch); SPD -> lock-step driver on an
+    # fp64 evaluator (no device needed: the three solve entry points are replaced by recorders)
+    from gabotorch_b200 import _lib, manifold_optimization as mo, ops
+    calls = []
+
+    class FakeGP:
+        def __init__(self, manifold, dim, n, compute=_lib.GABO_F32):
+            self.manifold, self.dim, self.n_train, self.compute = manifold, dim, n, compute
+
+        def with_compute(self, compute):
+            return FakeGP(self.manifold, self.dim, self.n_train, compute)
+
+    def recorder(name):
+        def solve(gp, pts, **kw):
+            calls.append((name, gp.compute, sorted(kw)))
+            r = pts.shape[0]
+            return pts, torch.zeros(r, dtype=torch.float64), torch.zeros(r, dtype=torch.int32), torch.zeros(r)
+        return solve
+    monkeypatch.setattr(ops, 'acq_rcg', recorder('rcg'))
+    monkeypatch.setattr(ops, 'acq_rtr', recorder('rtr'))
+    monkeypatch.setattr(mo, 'batched_trust_regions', recorder('lockstep'))
+    monkeypatch.setattr(ops, 'to_dev64', lambda x: torch.as_tensor(x, dtype=torch.float64))
+
+    def acq_for(gp):
+        a = mo.ExpectedImprovement.__new__(mo.ExpectedImprovement)
+        a._gp = gp
+        return a
+    sphere_x0 = torch.nn.functional.normalize(torch.randn(5, 1, 6, dtype=torch.float64), dim=-1)
+    spd_x0 = torch.eye(3, dtype=torch.float64).expand(4, 1, 3, 3).clone()
+    mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6), mo.TrustRegions())
+    mo.gen_candidates_manifold(spd_x0, acq_for(FakeGP(_lib.SPD, 3, 32)), g.PositiveDefinite(3), mo.TrustRegions())
+    mo.gen_candidates_manifold(spd_x0, acq_for(FakeGP(_lib.SPD, 3, 32)), g.PositiveDefinite(3), mo.ConjugateGradient())
+    big = torch.nn.functional.normalize(torch.randn(3, 1, 40, dtype=torch.float64), dim=-1)
+    mo.gen_candidates_manifold(big, acq_for(FakeGP(_lib.SPHERE, 40, 16)), g.Sphere(40), mo.TrustRegions())
+    assert [(c[0], c[1]) for c in calls] == [('rtr', _lib.GABO_F32), ('lockstep', _lib.GABO_F64),
+                                             ('rcg', _lib.GABO_F32), ('lockstep', _lib.GABO_F64)]
+    assert 'kappa' in calls[0][2] and 'kappa' in calls[1][2] and 'contraction' in calls[2][2]
