@@ -418,6 +418,29 @@ def _rand_points(manifold, n, generator):
     return ops.to_dev64(np.stack([manifold.rand() for _ in range(n)]))
 
 
+def sharded_acq_values(acq_function, X, group=None):
+    """Raw-sample screening sharded over the ranks: rank g evaluates the acquisition on its contiguous
+    block of the samples, ONE all-gather of the values (a few KB) gives every rank the whole vector.  ``X`` must be
+    identical on every rank (same seed); shards are padded to equal length for the collective."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = X.shape[0]
+    lo, hi = shard_range(n, rank, world)
+    width = -(-n // world) + 1                                   # >= the longest shard
+    with torch.no_grad():
+        vals = ops.to_dev64(acq_function(X[lo:hi])).reshape(-1) if hi > lo else X.new_zeros(0, dtype=torch.float64)
+    buf = torch.zeros(width, dtype=torch.float64, device=vals.device)
+    buf[:hi - lo] = vals
+    out = torch.empty(world, width, dtype=torch.float64, device=vals.device)
+    dist.all_gather_into_tensor(out, buf, group=group) if buf.is_cuda else \
+        dist.all_gather(list(out.unbind(0)), buf, group=group)
+    parts = []
+    for g_ in range(world):
+        a_, b_ = shard_range(n, g_, world)
+        parts.append(out[g_, :b_ - a_])
+    return torch.cat(parts)
+
+
 def gen_batch_initial_conditions_manifold(acq_function, manifold, bounds, q, num_restarts, raw_samples,
                                           sample_type=torch.float64, options=None, post_processing_manifold=None):
     """``num_restarts x q x dvec`` starting points (manifold_optimize.py:232-321).  Only q = 1 (as the reference)."""
@@ -427,6 +450,13 @@ def gen_batch_initial_conditions_manifold(acq_function, manifold, bounds, q, num
     if q != 1:
         raise NotImplementedError('q != 1 is not handled (neither by the reference, manifold_optimize.py:206)')
     seed = options.get('seed')
+    distributed = bool(options.get('distributed', False))
+    if distributed and seed is None:
+        # the ranks must draw the same raw samples: rank 0 picks the seed
+        import torch.distributed as dist
+        box = [int(torch.seed() % (2 ** 31)) if dist.get_rank() == 0 else 0]
+        dist.broadcast_object_list(box, src=0)
+        seed = box[0]
     gen = None
     if seed is not None:
         gen = torch.Generator(device=ops.device())
@@ -445,8 +475,11 @@ def gen_batch_initial_conditions_manifold(acq_function, manifold, bounds, q, num
             X_rnd = pts[:, None].to(sample_type)
             if post_processing_manifold is not None:
                 X_rnd = post_processing_manifold(X_rnd)
-            with torch.no_grad():
-                Y_rnd = ops.to_dev64(acq_function(X_rnd)).reshape(-1)
+            if distributed:
+                Y_rnd = sharded_acq_values(acq_function, X_rnd)
+            else:
+                with torch.no_grad():
+                    Y_rnd = ops.to_dev64(acq_function(X_rnd)).reshape(-1)
             batch_initial_conditions = initialize_q_batch_nonneg(X_rnd, Y_rnd, num_restarts, generator=gen,
                                                                  **init_kwargs)
             if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):

@@ -302,3 +302,36 @@ def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
     assert [(c[0], c[1]) for c in calls] == [('rtr', _lib.GABO_F32), ('lockstep', _lib.GABO_F64),
                                              ('rcg', _lib.GABO_F32), ('lockstep', _lib.GABO_F64)]
     assert 'kappa' in calls[0][2] and 'kappa' in calls[1][2] and 'contraction' in calls[2][2]
+
+
+def _screen_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from gabotorch_b200 import ops
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        ops.to_dev64 = lambda x: torch.as_tensor(x, dtype=torch.float64)       # CPU plumbing test: no device
+        X = torch.linspace(-1.0, 2.0, 11 * 3, dtype=torch.float64).reshape(11, 1, 3)   # identical on every rank
+        seen = []
+
+        def acq(x):
+            seen.append(x.shape[0])
+            return (x.reshape(x.shape[0], -1) ** 2).sum(-1)
+        vals = mo.sharded_acq_values(acq, X)
+        ret[rank] = (vals.tolist(), seen)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_raw_sample_screening_world_size_2_gloo():
+    # SURVEY 8e, raw-sample screening: every rank evaluates only its block, one all-gather returns the whole vector
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_screen_worker, args=(world, port, ret), nprocs=world, join=True)
+    X = torch.linspace(-1.0, 2.0, 11 * 3, dtype=torch.float64).reshape(11, 3)
+    full = (X ** 2).sum(-1).tolist()
+    assert ret[0][0] == full and ret[1][0] == full
+    assert ret[0][1] == [5] and ret[1][1] == [6]                # 11 samples: blocks [0, 5) and [5, 11)
