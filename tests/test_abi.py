@@ -107,3 +107,31 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    # include/gabo_b200.h is the drop-in boundary: it must compile as C (no C++ / CUDA types in the signatures) and
+    # the structs a binding passes by pointer must have exactly the layout gabotorch_b200/_lib.py mirrors
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not available')
+    fields = {'gabo_gp_desc': _lib.GpDesc, 'gabo_rcg_opts': _lib.RcgOpts, 'gabo_rtr_opts': _lib.RtrOpts}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gabo_b200.h"', 'int main(void) {']
+    for cname, mirror in fields.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in mirror._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), str(src),
+                    '-o', str(exe)], check=True, capture_output=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, mirror in fields.items():
+        assert int(out[cname]) == ctypes.sizeof(mirror), cname
+        for fname, _ in mirror._fields_:
+            assert int(out['%s.%s' % (cname, fname)]) == getattr(mirror, fname).offset, '%s.%s' % (cname, fname)
+    assert ctypes.sizeof(_lib.RtrOpts) == 16 + 7 * 8
