@@ -24,6 +24,10 @@ It restates, in plain numpy / torch-CPU fp64, the arithmetic of the reference
   with the pymanopt 0.2.x ``ConjugateGradient`` + ``LineSearchAdaptive`` it calls.
 * ``oracle.rtr``     – the reference's own trust-region solver ``manifold_optimization/robust_trust_regions.py:116-520``
   with the finite-difference Hessian ``manifold_optimization/approximate_hessian.py:11-62``.
+* ``oracle.ctr``     – the reference's own constrained trust-region solver
+  ``manifold_optimization/constrained_trust_regions.py:75-735`` with the eigenvalue constraints of
+  ``Riemannian_utils/spd_constraints_utils_torch.py:17-50`` (the configuration of ``gabo_spd.py``).  Laid down ahead of
+  the product code: nothing under ``gabotorch_b200/`` implements the constrained solver yet.
 
 Parity pinning
 --------------
@@ -31,7 +35,8 @@ PINNED (against the reference's own code imported from ``/root/reference`` with 
 ``torch.symeig`` shim, see ``tests/golden/make_golden.py`` and the committed fixtures):
 sphere distance / kernel, Mandel pack/unpack, SPD affine-invariant distance / kernel,
 Frobenius and log-Euclidean distance, nested SPD projection and reconstruction, ``sqrtm_torch``, nested-sphere
-projection chain in both directions, and the trust-region solver (the reference's ``TrustRegions`` class itself is run
+projection chain in both directions, and the trust-region solvers (the reference's ``TrustRegions`` and
+``ConstrainedTrustRegions`` classes themselves are run
 by ``make_golden.py``; only its third-party base class ``pymanopt.solvers.solver.Solver`` -- the stopping rule -- is a
 stand-in restated from pymanopt 0.2.x).
 

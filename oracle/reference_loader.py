@@ -100,3 +100,17 @@ def load_trust_regions():
     rtr = importlib.import_module('BoManifolds.manifold_optimization.robust_trust_regions')
     fd = importlib.import_module('BoManifolds.manifold_optimization.approximate_hessian')
     return rtr.TrustRegions, fd.get_hessianfd
+
+
+def load_constrained_trust_regions():
+    """The reference's own ``ConstrainedTrustRegions`` (manifold_optimization/constrained_trust_regions.py), its
+    ``Problem`` with the PyTorch autodiff backend (pymanopt_addons, in-repo) and the eigenvalue constraints
+    (Riemannian_utils/spd_constraints_utils_torch.py).  Needs the ``Solver`` stand-in of ``load_trust_regions`` and the
+    ``symeig`` shim of ``load``."""
+    load()
+    load_trust_regions()
+    import importlib
+    ctr = importlib.import_module('BoManifolds.manifold_optimization.constrained_trust_regions')
+    cons = importlib.import_module('BoManifolds.Riemannian_utils.spd_constraints_utils_torch')
+    fd = importlib.import_module('BoManifolds.manifold_optimization.approximate_hessian')
+    return ctr.ConstrainedTrustRegions, fd.get_hessianfd, cons

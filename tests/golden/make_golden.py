@@ -241,6 +241,47 @@ def main():
         out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
         out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
 
+    # ---- constrained trust regions: the reference's own ConstrainedTrustRegions class with its own Problem / PyTorch
+    # autodiff backend for the constraint, in the configuration of gabo_spd.py (mingradnorm 1e-4, maxiter 100,
+    # approx_hessian, one max-eigenvalue inequality constraint); own generator again -------------------------------
+    import functools
+    CTR, get_hessianfd_c, cons = reference_loader.load_constrained_trust_regions()
+    rng_c = np.random.default_rng(SEED + 2)
+    for name, d, n, max_eig, nstart in (('ctr_spd2', 2, 10, 3.0, 8), ('ctr_spd3', 3, 16, 4.0, 6),
+                                            ('ctr_spd2_active', 2, 10, 2.0, 8)):
+        xt = ospd.spd_sample(rng_c, n, d, max_cond=50.0)
+        y = ospd.ackley(ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(xt)))
+        beta = 0.5 + LN2
+        gp = ogp.make_gp('spd', xt, y, beta=beta, noise=1e-2)
+        man = ortr._Man('spd', xt[0])
+        man.egrad2rgrad = ospd.egrad2rgrad          # used by the reference's Problem.grad for the constraint
+        cost, grad = ortr.ei_problem(gp)
+
+        class ProblemC(object):
+            manifold = man
+            verbosity = 0
+
+            def precon(self, x, dd):
+                if np.sum(dd) == 0.:
+                    dd += 1e-30
+                return dd
+        problem = ProblemC()
+        problem.cost, problem.grad = cost, grad
+        problem.hess = types.MethodType(get_hessianfd_c, problem)
+        constraint = functools.partial(cons.max_eigenvalue_constraint_torch, maximum_eigenvalue=max_eig)
+        x0 = ospd.spd_sample(rng_c, nstart, d, min_eig=0.5, max_eig=0.9 * max_eig)      # feasible starts
+        xs, fs, its = [], [], []
+        for i in range(nstart):
+            solver = CTR(mingradnorm=1e-4, maxiter=100)
+            x = solver.solve(problem, x=x0[i].copy(), ineq_constraints=[constraint])
+            xs.append(x)
+            fs.append(cost(x))
+            its.append(solver._last_iter)
+        out[name + '_xtrain'], out[name + '_y'] = xt, np.asarray(y)
+        out[name + '_hyper'] = np.array([beta, 1e-2, max_eig])
+        out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
+        out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
+
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %d arrays, %.1f KiB' % (path, len(out), os.path.getsize(path) / 1024))

@@ -224,3 +224,21 @@ def test_trust_region_oracle_matches_reference_solver(golden, name):
     np.testing.assert_array_equal(its, golden[name + '_iters'])
     np.testing.assert_allclose(xs, golden[name + '_x'], rtol=0, atol=1e-12)
     np.testing.assert_allclose(-vals, golden[name + '_cost'], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize('name', ['ctr_spd2', 'ctr_spd3', 'ctr_spd2_active'])
+def test_constrained_trust_region_oracle_matches_reference_solver(golden, name):
+    # constrained_trust_regions.py (the reference's own ConstrainedTrustRegions class, its Problem + PyTorch autodiff
+    # for the max-eigenvalue constraint) in the configuration of gabo_spd.py, run by make_golden.py
+    from oracle import ctr as octr
+    from oracle import gp as ogp
+    from oracle import rtr as ortr
+    beta, noise, max_eig = golden[name + '_hyper']
+    gp = ogp.make_gp('spd', golden[name + '_xtrain'], golden[name + '_y'], beta=float(beta), noise=float(noise))
+    opts = ortr.TROptions(mingradnorm=1e-4, maxiter=100)
+    cons = [octr.max_eigenvalue_constraint(float(max_eig))]
+    for i, x0 in enumerate(golden[name + '_x0']):
+        x, c, k = octr.solve_ctr(gp, x0, ineq_constraints=cons, opts=opts)
+        assert k == int(golden[name + '_iters'][i])
+        np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
+        assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
