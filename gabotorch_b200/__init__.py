@@ -22,7 +22,8 @@ from .kernel_utils import (SphereGaussianKernel, SphereLaplaceKernel, SpdAffineI
                            NestedSpdLogEuclideanGaussianKernel, NestedSphereGaussianKernel)
 from ._compat import ScaleKernel  # noqa: F401
 from .manifolds import Sphere, PositiveDefinite  # noqa: F401
-from .manifold_optimization import (ConjugateGradient, TrustRegions, ExpectedImprovement, ManifoldGP,  # noqa: F401
+from .manifold_optimization import (ConjugateGradient, TrustRegions, ConstrainedTrustRegions,  # noqa: F401
+                                    ExpectedImprovement, ManifoldGP,
                                     gen_batch_initial_conditions_manifold, gen_candidates_manifold,
                                     get_best_candidates, joint_optimize_manifold)
 from .nested_mappings import (NestedSpdProjection, NestedSpdReconstruction,  # noqa: F401

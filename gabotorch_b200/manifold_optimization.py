@@ -93,6 +93,68 @@ def _trust_region_options(solver):
     )
 
 
+class ConstrainedTrustRegions(TrustRegions):
+    """Constructor surface of the reference's ``ConstrainedTrustRegions`` (constrained_trust_regions.py:102-118;
+    ``Delta_cons`` is an argument of its ``solve``, :120-121)."""
+
+    def __init__(self, *args, Delta_cons=1e-6, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.Delta_cons = Delta_cons
+
+
+def batched_constraints(constraints, manifold_kind):
+    """Turn the reference's list of inequality constraints (callables of ONE point returning a zero-dim tensor,
+    positive when satisfied; examples/bo_spd/benchmark_examples/gabo_spd.py:136-138) into one callable of the whole
+    batch: ``X (R, ...) -> (values (R, C), [C Riemannian gradients shaped like X])``.
+
+    ``functools.partial(max_eigenvalue_constraint_torch | min_eigenvalue_constraint_torch, ...)`` from
+    ``gabotorch_b200.riemannian_utils`` is evaluated in closed form for the batch (extreme eigenpair: value
+    ``+-(bound - lambda)``, Euclidean gradient ``-+ v v^T``).  Any other callable is differentiated with torch.autograd
+    one restart at a time, which is what the reference's ``Problem`` does (pymanopt_addons/problem.py:118-137)."""
+    from . import riemannian_utils as ru
+    constraints = list(constraints)
+
+    def rgrad(X, E):
+        if manifold_kind == _lib.SPD:
+            return ops.spd_op(_lib.OP_EGRAD2RGRAD, X, E)                   # X sym(E) X
+        return E - (X * E).sum(-1, keepdim=True) * X                      # projection onto the tangent space
+
+    def closed_form(c):
+        f = getattr(c, 'func', None)
+        kw = getattr(c, 'keywords', None) or {}
+        args = getattr(c, 'args', ())
+        if f is ru.max_eigenvalue_constraint_torch:
+            return 'max', float(kw.get('maximum_eigenvalue', args[0] if args else float('nan')))
+        if f is ru.min_eigenvalue_constraint_torch:
+            return 'min', float(kw.get('minimum_eigenvalue', args[0] if args else float('nan')))
+        return None
+
+    kinds = [closed_form(c) for c in constraints]
+
+    def evaluate(X):
+        vals, grads = [], []
+        eig = None
+        for c, k in zip(constraints, kinds):
+            if k is not None:
+                if eig is None:
+                    eig = torch.linalg.eigh(X)
+                lam, vec = eig
+                i = -1 if k[0] == 'max' else 0
+                v = vec[..., i]
+                outer = v.unsqueeze(-1) * v.unsqueeze(-2)
+                vals.append(k[1] - lam[..., i] if k[0] == 'max' else lam[..., i] - k[1])
+                grads.append(rgrad(X, -outer if k[0] == 'max' else outer))
+            else:
+                xs = X.detach().clone().requires_grad_(True)
+                with torch.enable_grad():
+                    f = torch.stack([c(xs[i]) for i in range(xs.shape[0])])
+                    e, = torch.autograd.grad(f.sum(), xs)
+                vals.append(f.detach())
+                grads.append(rgrad(X, e))
+        return torch.stack(vals, dim=-1), grads
+    return evaluate
+
+
 def _rtr_kernel_covers(gp):
     """The register-resident trust-region kernel (gabo_acq_rtr): sphere, ambient dimension <= 8, or <= 16 with at most
     64 training points."""
@@ -100,7 +162,8 @@ def _rtr_kernel_covers(gp):
 
 
 def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1,
-                          rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None):
+                          rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None,
+                          ineq_constraints=None, delta_cons=1e-6):
     """The reference's ``TrustRegions.solve`` (robust_trust_regions.py:116-352, tCG :410-520, finite-difference Hessian
     approximate_hessian.py:11-62) for ALL restarts in lock-step, for the cases the single-launch kernel does not cover:
     SPD(d) and spheres of large ambient dimension.  Every cost / gradient evaluation is one launch of ``gabo_ei_eval``
@@ -109,7 +172,14 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
     per-restart scalars of the recurrences live in (R,) device tensors and finished restarts are masked out, so each
     restart follows exactly the serial algorithm.  Returns (candidates, values, iters, reasons) like ``ops.acq_rtr``.
     Launch-bound by construction (about 8 launches per inner iteration); fusing it into the CTA-per-restart SPD kernel
-    is the next step."""
+    is the next step.
+
+    ``ineq_constraints`` (a callable ``X -> (values (R, C), [C Riemannian gradients shaped like X])``, see
+    ``batched_constraints``) switches to the reference's ``ConstrainedTrustRegions``
+    (constrained_trust_regions.py:120-439, constrained tCG :441-735): the linearised constraints
+    ``c(x) + <grad c, eta>`` are kept within ``delta_cons`` of feasibility along the tCG path (only negative inequality
+    terms count), the step is cut by the root of the corresponding quadratic, and the radius also grows after a step
+    that stopped on the constraints."""
     X = ops.to_dev64(x0).clone()
     R = X.shape[0]
     dev = X.device
@@ -165,7 +235,22 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
     delta0 = float(delta_bar / 8 if delta0 is None else delta0)
     fd_eps = 2.0 ** -14                                                   # approximate_hessian.py:43
     eps = 2.220446049250313e-16                                           # np.spacing(1)
-    NEG, EXC, LIN, SUP, MAXI, INC = range(6)
+    NEG, EXC, LIN, SUP, MAXI, INC, CONS = range(7)
+    dc2 = float(delta_cons) ** 2
+
+    def step_to_constraints(fc, pe, pd, step):
+        """(violated (R,), tau (R,)): does the linearised constraint term leave the delta_cons ball at ``step``, and the
+        step that brings it back onto it (constrained_trust_regions.py:565-592 / :622-650; inequality constraints only,
+        where the reference's index set is exactly the negative terms)."""
+        term = torch.clamp(fc + pe + step.unsqueeze(-1) * pd, max=0.0)
+        bad = (term * term).sum(-1) > dc2
+        m = (term < 0).to(fc.dtype)
+        qa = (m * pd * pd).sum(-1)
+        qb = 2.0 * ((m * fc * pd).sum(-1) + (m * pe * pd).sum(-1))
+        qc = (m * fc * fc).sum(-1) + 2.0 * (m * fc * pe).sum(-1) + (m * pe * pe).sum(-1) - dc2
+        disc = qb * qb - 4.0 * qa * qc
+        tau = torch.where(disc >= 0, (-qb + disc.clamp(min=0).sqrt()) / (2.0 * qa), torch.zeros_like(disc))
+        return bad, tau
 
     def hess(P, G, A):
         na = norm(P, A)
@@ -194,6 +279,9 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         live = active.clone()
         r2 = radius * radius
         pw = norm_r0 ** theta
+        if ineq_constraints is not None:
+            fc, gcs = ineq_constraints(X)                       # (R, C) values, C Riemannian gradients
+            pe = torch.zeros_like(fc)                           # <grad c, eta>, eta = 0
         for j in range(maxinner):
             if not bool(live.any()):
                 break
@@ -204,10 +292,24 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
             e_pe_new = torch.where(nz, e_pe + 2 * alpha * e_pd + alpha * alpha * d_pd, e_pe)
             out1 = live & ((d_hd <= 0) | (e_pe_new >= r2))
             tau = (-e_pd + (e_pd * e_pd + d_pd * (r2 - e_pe)).sqrt()) / d_pd
+            code1 = torch.where(d_hd <= 0, NEG, EXC).to(torch.int32)
+            if ineq_constraints is not None:
+                pd = torch.stack([inner(X, gc, delta) for gc in gcs], dim=-1)
+                tau = torch.where(torch.isnan(tau), torch.zeros_like(tau), tau)          # :562-563
+                bad, tau_c = step_to_constraints(fc, pe, pd, tau)
+                tau = torch.where(bad, tau_c, tau)
+                code1 = torch.where((d_hd > 0) & bad, torch.full_like(code1, CONS), code1)
             eta = torch.where(bc(out1), eta + bc(tau) * delta, eta)
             heta = torch.where(bc(out1), heta + bc(tau) * hdelta, heta)
-            stop = torch.where(out1, torch.where(d_hd <= 0, NEG, EXC).to(torch.int32), stop)
+            stop = torch.where(out1, code1, stop)
             live = live & ~out1
+            if ineq_constraints is not None:                    # the full CG step would violate the constraints
+                bad, tau_c = step_to_constraints(fc, pe, pd, alpha)
+                outc = live & bad
+                eta = torch.where(bc(outc), eta + bc(tau_c) * delta, eta)
+                heta = torch.where(bc(outc), heta + bc(tau_c) * hdelta, heta)
+                stop = torch.where(outc, torch.full_like(stop, CONS), stop)
+                live = live & ~outc
             new_eta = eta + bc(alpha) * delta
             new_heta = heta + bc(alpha) * hdelta
             new_mv = inner(X, new_eta, G) + 0.5 * inner(X, new_eta, new_heta)
@@ -230,6 +332,8 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
             e_pd = torch.where(live, beta * (e_pd + alpha * d_pd), e_pd)
             d_pd = torch.where(live, r_r + beta * beta * d_pd, d_pd)
             z_r = torch.where(live, r_r, z_r)
+            if ineq_constraints is not None:
+                pe = torch.where(live.unsqueeze(-1), pe + alpha.unsqueeze(-1) * pd, pe)
         # ---- proposal, rho, radius update, acceptance (robust_trust_regions.py:225-311) ----
         x_prop = retr(X, eta)
         fx_prop = cost(x_prop)
@@ -239,7 +343,7 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         model_decreased = rhoden >= 0
         rho = rhonum / rhoden
         shrink = (rho < 0.25) | ~model_decreased | torch.isnan(rho)
-        grow = ~shrink & (rho > 0.75) & ((stop == NEG) | (stop == EXC))
+        grow = ~shrink & (rho > 0.75) & ((stop == NEG) | (stop == EXC) | (stop == CONS))
         radius = torch.where(active & shrink, radius / 4,
                              torch.where(active & grow, torch.clamp(2 * radius, max=delta_bar), radius))
         accept = active & model_decreased & (rho > rho_prime)
@@ -260,8 +364,8 @@ def _solver_options(solver):
     name = type(solver).__name__
     if name != 'ConjugateGradient':
         raise NotImplementedError(
-            'solver %s: the B200 path batches ConjugateGradient and TrustRegions (constrained trust regions / ALM are '
-            'SURVEY 8f "next"); there is no CPU fallback' % name)
+            'solver %s: the B200 path batches ConjugateGradient, TrustRegions and ConstrainedTrustRegions (strict '
+            'constrained trust regions / ALM are SURVEY 8f "next"); there is no CPU fallback' % name)
     ls = getattr(solver, '_linesearch', None) or getattr(solver, 'linesearch', None)
     return dict(
         maxiter=int(getattr(solver, '_maxiter', 1000)),
@@ -501,12 +605,16 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     """All restarts solved in one launch (manifold_optimize.py:124-228).  Returns ``(candidates, acquisition values)``
     with the shapes of the reference: ``R x 1 x dvec`` and ``R``.  Bounds are accepted and ignored, as in the
     reference (:131-132 are never used by its body)."""
-    if inequality_constraints is not None or equality_constraints is not None:
-        raise NotImplementedError('constrained solvers are SURVEY 8f "next"; there is no CPU fallback')
+    if equality_constraints is not None:
+        raise NotImplementedError('equality constraints are SURVEY 8f "next"; there is no CPU fallback')
+    if inequality_constraints is not None and type(solver).__name__ != 'ConstrainedTrustRegions':
+        raise NotImplementedError('inequality constraints need ConstrainedTrustRegions (strict / ALM variants are '
+                                  'SURVEY 8f "next"); there is no CPU fallback')
     if solver_init_conds:
         raise NotImplementedError('solver-side initialisation (population methods) is not supported')
     kind = _manifold_kind(manifold)
-    trust_region = type(solver).__name__ == 'TrustRegions'
+    trust_region = type(solver).__name__ in ('TrustRegions', 'ConstrainedTrustRegions')
+    constrained = type(solver).__name__ == 'ConstrainedTrustRegions' and inequality_constraints is not None
     sopts = _trust_region_options(solver) if trust_region else _solver_options(solver)
     if not isinstance(acquisition_function, ExpectedImprovement):
         raise NotImplementedError('the B200 optimiser evaluates ExpectedImprovement in closed form; got %s'
@@ -524,6 +632,13 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     pts = x0[:, 0]
     if not trust_region:
         solve = ops.acq_rcg
+    elif constrained:
+        # the reference's ConstrainedTrustRegions: lock-step driver with the constrained tCG, fp64 evaluator
+        solve = batched_trust_regions
+        gp = gp.with_compute(_lib.GABO_F64)
+        cons = inequality_constraints if isinstance(inequality_constraints, (list, tuple)) else [inequality_constraints]
+        sopts = dict(sopts, ineq_constraints=batched_constraints(cons, kind),
+                     delta_cons=float(getattr(solver, 'Delta_cons', 1e-6)))
     elif _rtr_kernel_covers(gp):
         solve = ops.acq_rtr                      # one launch, one warp per restart
     else:

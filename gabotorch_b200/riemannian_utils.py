@@ -7,6 +7,8 @@ meaning, results on the caller's device in float64 -- computed by the fused CUDA
     logm_torch                                 spd_utils_torch.py:13-30   (also accepts a batch)
     vector_to_symmetric_matrix_mandel_torch    spd_utils_torch.py:159-194
     symmetric_matrix_to_vector_mandel_torch    spd_utils_torch.py:197-226
+    max_/min_eigenvalue_constraint_torch       spd_constraints_utils_torch.py:17-50 (plain torch, as in the reference;
+                                               recognised and batched in closed form by the constrained solver)
 """
 import torch
 
@@ -47,3 +49,13 @@ def vector_to_symmetric_matrix_mandel_torch(vectors):
 
 def symmetric_matrix_to_vector_mandel_torch(matrices):
     return _back(ops.mandel_pack(matrices), matrices)
+
+
+def max_eigenvalue_constraint_torch(x, maximum_eigenvalue):
+    """``maximum_eigenvalue - lambda_max(x)``: positive when satisfied (spd_constraints_utils_torch.py:17-32)."""
+    return maximum_eigenvalue - torch.linalg.eigvalsh(x).max()
+
+
+def min_eigenvalue_constraint_torch(x, minimum_eigenvalue):
+    """``lambda_min(x) - minimum_eigenvalue``: positive when satisfied (spd_constraints_utils_torch.py:35-50)."""
+    return torch.linalg.eigvalsh(x).min() - minimum_eigenvalue

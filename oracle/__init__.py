@@ -26,8 +26,7 @@ It restates, in plain numpy / torch-CPU fp64, the arithmetic of the reference
   with the finite-difference Hessian ``manifold_optimization/approximate_hessian.py:11-62``.
 * ``oracle.ctr``     – the reference's own constrained trust-region solver
   ``manifold_optimization/constrained_trust_regions.py:75-735`` with the eigenvalue constraints of
-  ``Riemannian_utils/spd_constraints_utils_torch.py:17-50`` (the configuration of ``gabo_spd.py``).  Laid down ahead of
-  the product code: nothing under ``gabotorch_b200/`` implements the constrained solver yet.
+  ``Riemannian_utils/spd_constraints_utils_torch.py:17-50`` (the configuration of ``gabo_spd.py``).
 
 Parity pinning
 --------------

@@ -12,7 +12,7 @@ maxiter=100)``, ``approx_hessian=True``, one inequality constraint ``max_eigenva
 PINNED on the reference's code: ``tests/golden/make_golden.py`` runs the reference's class itself, with the
 reference's own ``pymanopt_addons.problem.Problem`` + PyTorch autodiff backend for the constraint (value and gradient
 through ``torch.symeig``), on the oracle's EI problem (``ctr_*`` arrays); ``tests/test_oracle_golden.py`` compares.
-No product code implements this solver yet (remaining part): the oracle is laid down first.
+The product side is ``gabotorch_b200.manifold_optimization.batched_trust_regions(..., ineq_constraints=...)``.
 """
 import numpy as np
 

@@ -312,3 +312,23 @@ def test_lockstep_trust_regions_on_device_vs_oracle(manifold, dim, n, R):
         assert np.linalg.eigvalsh(0.5 * (X + np.swapaxes(X, -1, -2))).min() > 0
     else:
         np.testing.assert_allclose(np.linalg.norm(X, axis=-1), 1.0, atol=1e-12)
+
+
+@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: its first device run is the '
+                                        'round-end suite; the host logic is pinned on CPU (tests/test_host_logic.py)')
+@pytest.mark.parametrize('name', ['ctr_spd2_active', 'ctr_spd3'])
+def test_lockstep_constrained_trust_regions_on_device_vs_reference_solver(golden, name):
+    # gabo_spd.py's configuration: ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100), approx_hessian, one
+    # max-eigenvalue constraint; golden arrays from the reference's own class (tests/golden/make_golden.py)
+    import functools
+    from gabotorch_b200 import manifold_optimization as mo, riemannian_utils as ru
+    beta, noise, max_eig = (float(v) for v in golden[name + '_hyper'])
+    gp = ogp.make_gp('spd', golden[name + '_xtrain'], golden[name + '_y'], beta=beta, noise=noise)
+    cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=max_eig)]
+    X, val, iters, _ = mo.batched_trust_regions(device_gp(gp, _lib.GABO_F64), golden[name + '_x0'], maxiter=100,
+                                                mingradnorm=1e-4,
+                                                ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
+    same = iters.cpu().numpy() == golden[name + '_iters']
+    assert same.mean() >= 0.7
+    np.testing.assert_allclose(X.cpu().numpy()[same], golden[name + '_x'][same], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(-val.cpu().numpy()[same], golden[name + '_cost'][same], rtol=1e-5, atol=1e-9)

@@ -225,8 +225,10 @@ class _OracleOps:
         return torch.tensor(np.array([ospd.inner(p, u, v) for p, u, v in zip(x, b, c.numpy())]))
 
     def spd_op(self, op, a, b, c=None):
+        from gabotorch_b200 import _lib
         from oracle import spd as ospd
-        return torch.tensor(np.array([ospd.retr(p, u) for p, u in zip(a.numpy(), b.numpy())]))
+        fn = {_lib.OP_RETR: ospd.retr, _lib.OP_EGRAD2RGRAD: ospd.egrad2rgrad}[op]
+        return torch.tensor(np.array([fn(p, u) for p, u in zip(a.numpy(), b.numpy())]))
 
 
 @pytest.mark.parametrize('manifold,dim,n,R', [('spd', 2, 10, 6), ('spd', 3, 12, 5), ('sphere', 20, 16, 6)])
@@ -302,6 +304,27 @@ def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
     assert [(c[0], c[1]) for c in calls] == [('rtr', _lib.GABO_F32), ('lockstep', _lib.GABO_F64),
                                              ('rcg', _lib.GABO_F32), ('lockstep', _lib.GABO_F64)]
     assert 'kappa' in calls[0][2] and 'kappa' in calls[1][2] and 'contraction' in calls[2][2]
+    # constraints: ConstrainedTrustRegions + inequality constraints -> lock-step driver with the constrained tCG (fp64),
+    # also on a small sphere; without constraints it is the plain solver; everything else is refused
+    import functools
+    from gabotorch_b200 import riemannian_utils as ru
+    cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.0)]
+    calls.clear()
+    mo.gen_candidates_manifold(spd_x0, acq_for(FakeGP(_lib.SPD, 3, 32)), g.PositiveDefinite(3),
+                               mo.ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100), approx_hessian=True,
+                               inequality_constraints=cons)
+    mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6),
+                               mo.ConstrainedTrustRegions(), inequality_constraints=[lambda x: x[0]])
+    mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6), mo.ConstrainedTrustRegions())
+    assert [(c[0], c[1]) for c in calls] == [('lockstep', _lib.GABO_F64), ('lockstep', _lib.GABO_F64),
+                                             ('rtr', _lib.GABO_F32)]
+    assert 'ineq_constraints' in calls[0][2] and 'delta_cons' in calls[0][2] and 'ineq_constraints' not in calls[2][2]
+    with pytest.raises(NotImplementedError):
+        mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6), mo.TrustRegions(),
+                                   inequality_constraints=cons)
+    with pytest.raises(NotImplementedError):
+        mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6),
+                                   mo.ConstrainedTrustRegions(), equality_constraints=[lambda x: x[0]])
 
 
 def _screen_worker(rank, world, port, ret):
@@ -335,3 +358,30 @@ def test_sharded_raw_sample_screening_world_size_2_gloo():
     full = (X ** 2).sum(-1).tolist()
     assert ret[0][0] == full and ret[1][0] == full
     assert ret[0][1] == [5] and ret[1][1] == [6]                # 11 samples: blocks [0, 5) and [5, 11)
+
+
+@pytest.mark.parametrize('name', ['ctr_spd2_active', 'ctr_spd2', 'ctr_spd3'])
+@pytest.mark.parametrize('closed_form', [True, False])
+def test_lockstep_constrained_trust_regions_reproduce_the_reference_solver(monkeypatch, golden, name, closed_form):
+    # the golden arrays come from the reference's OWN ConstrainedTrustRegions class in gabo_spd.py's configuration
+    # (tests/golden/make_golden.py); the lock-step driver must reproduce its iteration counts and candidates, with the
+    # constraint batched in closed form and through the generic autograd route
+    import functools
+    from gabotorch_b200 import _lib, manifold_optimization as mo, ops, riemannian_utils as ru
+    from oracle import gp as ogp
+    beta, noise, max_eig = (float(v) for v in golden[name + '_hyper'])
+    xt = golden[name + '_xtrain']
+    gp = ogp.make_gp('spd', xt, golden[name + '_y'], beta=beta, noise=noise)
+    fake = _OracleOps(gp)
+    for attr in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op'):
+        monkeypatch.setattr(ops, attr, getattr(fake, attr))
+    if closed_form:
+        cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=max_eig)]
+    else:
+        cons = [lambda x: max_eig - torch.linalg.eigvalsh(x)[-1]]
+    handle = type('GP', (), {'manifold': _lib.SPD, 'dim': xt.shape[-1], 'n_train': xt.shape[0]})()
+    X, val, iters, reason = mo.batched_trust_regions(handle, golden[name + '_x0'], maxiter=100, mingradnorm=1e-4,
+                                                     ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
+    np.testing.assert_array_equal(iters.numpy(), golden[name + '_iters'])
+    np.testing.assert_allclose(X.numpy(), golden[name + '_x'], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(-val.numpy(), golden[name + '_cost'], rtol=1e-9, atol=1e-13)
