@@ -102,6 +102,11 @@ class ConstrainedTrustRegions(TrustRegions):
         self.Delta_cons = Delta_cons
 
 
+class StrictConstrainedTrustRegions(ConstrainedTrustRegions):
+    """The reference's ``StrictConstrainedTrustRegions`` (constrained_trust_regions.py:737-1415): proposals that violate
+    a constraint are rejected outright (``hd_gabo_spd.py``'s acquisition solver)."""
+
+
 def batched_constraints(constraints, manifold_kind):
     """Turn the reference's list of inequality constraints (callables of ONE point returning a zero-dim tensor,
     positive when satisfied; examples/bo_spd/benchmark_examples/gabo_spd.py:136-138) into one callable of the whole
@@ -155,6 +160,9 @@ def batched_constraints(constraints, manifold_kind):
     return evaluate
 
 
+_CONSTRAINED_SOLVERS = ('ConstrainedTrustRegions', 'StrictConstrainedTrustRegions')
+
+
 def _rtr_kernel_covers(gp):
     """The register-resident trust-region kernel (gabo_acq_rtr): sphere, ambient dimension <= 8, or <= 16 with at most
     64 training points."""
@@ -163,7 +171,7 @@ def _rtr_kernel_covers(gp):
 
 def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1,
                           rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None,
-                          ineq_constraints=None, delta_cons=1e-6):
+                          ineq_constraints=None, delta_cons=1e-6, strict=False):
     """The reference's ``TrustRegions.solve`` (robust_trust_regions.py:116-352, tCG :410-520, finite-difference Hessian
     approximate_hessian.py:11-62) for ALL restarts in lock-step, for the cases the single-launch kernel does not cover:
     SPD(d) and spheres of large ambient dimension.  Every cost / gradient evaluation is one launch of ``gabo_ei_eval``
@@ -179,7 +187,8 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
     (constrained_trust_regions.py:120-439, constrained tCG :441-735): the linearised constraints
     ``c(x) + <grad c, eta>`` are kept within ``delta_cons`` of feasibility along the tCG path (only negative inequality
     terms count), the step is cut by the root of the corresponding quadratic, and the radius also grows after a step
-    that stopped on the constraints."""
+    that stopped on the constraints.  ``strict=True`` is ``StrictConstrainedTrustRegions`` (:737-1415): a proposal that
+    violates a constraint gets an infinite cost, is rejected and shrinks the radius (:936-952, :972)."""
     X = ops.to_dev64(x0).clone()
     R = X.shape[0]
     dev = X.device
@@ -337,12 +346,16 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         # ---- proposal, rho, radius update, acceptance (robust_trust_regions.py:225-311) ----
         x_prop = retr(X, eta)
         fx_prop = cost(x_prop)
+        invalid = torch.zeros_like(active)
+        if strict and ineq_constraints is not None:
+            invalid = torch.clamp(ineq_constraints(x_prop)[0], max=0.0).abs().sum(-1) != 0
+            fx_prop = torch.where(invalid, inf, fx_prop)
         rho_reg = torch.clamp(fx.abs(), min=1.0) * eps * rho_regularization
         rhonum = fx - fx_prop + rho_reg
         rhoden = -inner(X, G, eta) - 0.5 * inner(X, eta, heta) + rho_reg
         model_decreased = rhoden >= 0
         rho = rhonum / rhoden
-        shrink = (rho < 0.25) | ~model_decreased | torch.isnan(rho)
+        shrink = (rho < 0.25) | ~model_decreased | torch.isnan(rho) | invalid
         grow = ~shrink & (rho > 0.75) & ((stop == NEG) | (stop == EXC) | (stop == CONS))
         radius = torch.where(active & shrink, radius / 4,
                              torch.where(active & grow, torch.clamp(2 * radius, max=delta_bar), radius))
@@ -364,8 +377,8 @@ def _solver_options(solver):
     name = type(solver).__name__
     if name != 'ConjugateGradient':
         raise NotImplementedError(
-            'solver %s: the B200 path batches ConjugateGradient, TrustRegions and ConstrainedTrustRegions (strict '
-            'constrained trust regions / ALM are SURVEY 8f "next"); there is no CPU fallback' % name)
+            'solver %s: the B200 path batches ConjugateGradient, TrustRegions and [Strict]ConstrainedTrustRegions (the '
+            'ALM solver is SURVEY 8f "next"); there is no CPU fallback' % name)
     ls = getattr(solver, '_linesearch', None) or getattr(solver, 'linesearch', None)
     return dict(
         maxiter=int(getattr(solver, '_maxiter', 1000)),
@@ -607,14 +620,14 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     reference (:131-132 are never used by its body)."""
     if equality_constraints is not None:
         raise NotImplementedError('equality constraints are SURVEY 8f "next"; there is no CPU fallback')
-    if inequality_constraints is not None and type(solver).__name__ != 'ConstrainedTrustRegions':
-        raise NotImplementedError('inequality constraints need ConstrainedTrustRegions (strict / ALM variants are '
+    if inequality_constraints is not None and type(solver).__name__ not in _CONSTRAINED_SOLVERS:
+        raise NotImplementedError('inequality constraints need [Strict]ConstrainedTrustRegions (the ALM solver is '
                                   'SURVEY 8f "next"); there is no CPU fallback')
     if solver_init_conds:
         raise NotImplementedError('solver-side initialisation (population methods) is not supported')
     kind = _manifold_kind(manifold)
-    trust_region = type(solver).__name__ in ('TrustRegions', 'ConstrainedTrustRegions')
-    constrained = type(solver).__name__ == 'ConstrainedTrustRegions' and inequality_constraints is not None
+    trust_region = type(solver).__name__ in ('TrustRegions',) + _CONSTRAINED_SOLVERS
+    constrained = type(solver).__name__ in _CONSTRAINED_SOLVERS and inequality_constraints is not None
     sopts = _trust_region_options(solver) if trust_region else _solver_options(solver)
     if not isinstance(acquisition_function, ExpectedImprovement):
         raise NotImplementedError('the B200 optimiser evaluates ExpectedImprovement in closed form; got %s'
@@ -638,7 +651,8 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
         gp = gp.with_compute(_lib.GABO_F64)
         cons = inequality_constraints if isinstance(inequality_constraints, (list, tuple)) else [inequality_constraints]
         sopts = dict(sopts, ineq_constraints=batched_constraints(cons, kind),
-                     delta_cons=float(getattr(solver, 'Delta_cons', 1e-6)))
+                     delta_cons=float(getattr(solver, 'Delta_cons', 1e-6)),
+                     strict=type(solver).__name__ == 'StrictConstrainedTrustRegions')
     elif _rtr_kernel_covers(gp):
         solve = ops.acq_rtr                      # one launch, one warp per restart
     else:

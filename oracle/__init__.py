@@ -24,8 +24,8 @@ It restates, in plain numpy / torch-CPU fp64, the arithmetic of the reference
   with the pymanopt 0.2.x ``ConjugateGradient`` + ``LineSearchAdaptive`` it calls.
 * ``oracle.rtr``     – the reference's own trust-region solver ``manifold_optimization/robust_trust_regions.py:116-520``
   with the finite-difference Hessian ``manifold_optimization/approximate_hessian.py:11-62``.
-* ``oracle.ctr``     – the reference's own constrained trust-region solver
-  ``manifold_optimization/constrained_trust_regions.py:75-735`` with the eigenvalue constraints of
+* ``oracle.ctr``     – the reference's own constrained trust-region solvers (plain and strict)
+  ``manifold_optimization/constrained_trust_regions.py:75-1415`` with the eigenvalue constraints of
   ``Riemannian_utils/spd_constraints_utils_torch.py:17-50`` (the configuration of ``gabo_spd.py``).
 
 Parity pinning

@@ -1,6 +1,7 @@
 """Oracle (CPU, fp64) for the constrained trust-region acquisition solver.  Test infrastructure only.
 
-Restates the reference's OWN ``ConstrainedTrustRegions`` (``BoManifolds/manifold_optimization/constrained_trust_regions.py``:
+Restates the reference's OWN ``ConstrainedTrustRegions`` and ``StrictConstrainedTrustRegions``
+(``BoManifolds/manifold_optimization/constrained_trust_regions.py``:
 ``solve`` ``:120-439`` -- the radius update additionally grows on ``REACHED_CONSTRAINTS`` ``:321-323``;
 ``_constrained_truncated_conjugate_gradient`` ``:441-735`` -- the linearised constraints
 ``c(x) + <grad c, eta>`` are kept within ``Delta_cons`` (1e-6) of feasibility along the tCG path, inequality terms
@@ -144,9 +145,10 @@ def constrained_truncated_cg(man, hess, x, fgradx, radius, theta, kappa, mininne
     return eta, heta, j, stop
 
 
-def solve_ctr(gp, x0, eq_constraints=(), ineq_constraints=(), opts=None, delta_cons=1e-6, trace=None):
+def solve_ctr(gp, x0, eq_constraints=(), ineq_constraints=(), opts=None, delta_cons=1e-6, trace=None, strict=False):
     """One ``ConstrainedTrustRegions.solve`` on cost = -EI.  Constraints are (value, Riemannian gradient) pairs.
-    Returns (x, cost, iters)."""
+    ``strict=True`` is ``StrictConstrainedTrustRegions`` (:737-1415): the only difference is that a proposal violating
+    a constraint gets an infinite cost and shrinks the radius (:936-952, :972).  Returns (x, cost, iters)."""
     opts = opts or _rtr.TROptions()
     x = np.array(x0, dtype=np.float64)
     man = _rtr._Man(gp.manifold, x)
@@ -173,14 +175,18 @@ def solve_ctr(gp, x0, eq_constraints=(), ineq_constraints=(), opts=None, delta_c
         eta, heta, _, stop_inner = constrained_truncated_cg(man, hess, x, fgradx, radius, opts.theta, opts.kappa,
                                                             opts.mininner, maxinner, f_eq, g_eq, f_in, g_in, delta_cons)
         x_prop = man.retr(x, eta)
-        fx_prop = cost(x_prop)
+        invalid_prop = False
+        if strict:
+            fcp = [c[0](x_prop) for c in eq_constraints] + [min(c[0](x_prop), 0.0) for c in ineq_constraints]
+            invalid_prop = float(np.sum(np.abs(np.array(fcp, dtype=np.float64)))) != 0.0
+        fx_prop = np.inf if invalid_prop else cost(x_prop)
         rho_reg = max(1, abs(fx)) * np.spacing(1) * opts.rho_regularization
         rhonum = fx - fx_prop + rho_reg
         rhoden = -man.inner(x, fgradx, eta) - 0.5 * man.inner(x, eta, heta) + rho_reg
         model_decreased = rhoden >= 0
         with np.errstate(divide='ignore', invalid='ignore'):
             rho = np.float64(rhonum) / np.float64(rhoden)
-        if rho < 0.25 or not model_decreased or np.isnan(rho):
+        if rho < 0.25 or not model_decreased or np.isnan(rho) or invalid_prop:
             radius = radius / 4
         elif rho > 0.75 and stop_inner in (NEGATIVE_CURVATURE, EXCEEDED_TR, REACHED_CONSTRAINTS):
             radius = min(2 * radius, delta_bar)

@@ -113,4 +113,5 @@ def load_constrained_trust_regions():
     ctr = importlib.import_module('BoManifolds.manifold_optimization.constrained_trust_regions')
     cons = importlib.import_module('BoManifolds.Riemannian_utils.spd_constraints_utils_torch')
     fd = importlib.import_module('BoManifolds.manifold_optimization.approximate_hessian')
+    ctr.ConstrainedTrustRegions.Strict = ctr.StrictConstrainedTrustRegions      # handed out together
     return ctr.ConstrainedTrustRegions, fd.get_hessianfd, cons

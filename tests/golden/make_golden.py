@@ -282,6 +282,43 @@ def main():
         out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
         out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
 
+    # ---- strict variant: the reference's StrictConstrainedTrustRegions with the settings of hd_gabo_spd.py
+    # (mingradnorm 2e-4, maxiter 100); own generator again ----------------------------------------------------------
+    rng_s = np.random.default_rng(SEED + 3)
+    for name, d, n, max_eig, nstart in (('sctr_spd2_active', 2, 10, 2.0, 8), ('sctr_spd3', 3, 16, 2.5, 6)):
+        xt = ospd.spd_sample(rng_s, n, d, max_cond=50.0)
+        y = ospd.ackley(ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(xt)))
+        beta = 0.5 + LN2
+        gp = ogp.make_gp('spd', xt, y, beta=beta, noise=1e-2)
+        man = ortr._Man('spd', xt[0])
+        man.egrad2rgrad = ospd.egrad2rgrad
+        cost, grad = ortr.ei_problem(gp)
+
+        class ProblemS(object):
+            manifold = man
+            verbosity = 0
+
+            def precon(self, x, dd):
+                if np.sum(dd) == 0.:
+                    dd += 1e-30
+                return dd
+        problem = ProblemS()
+        problem.cost, problem.grad = cost, grad
+        problem.hess = types.MethodType(get_hessianfd_c, problem)
+        constraint = functools.partial(cons.max_eigenvalue_constraint_torch, maximum_eigenvalue=max_eig)
+        x0 = ospd.spd_sample(rng_s, nstart, d, min_eig=0.5, max_eig=0.9 * max_eig)
+        xs, fs, its = [], [], []
+        for i in range(nstart):
+            solver = CTR.Strict(mingradnorm=2e-4, maxiter=100, minstepsize=1e-4)
+            x = solver.solve(problem, x=x0[i].copy(), ineq_constraints=[constraint])
+            xs.append(x)
+            fs.append(cost(x))
+            its.append(solver._last_iter)
+        out[name + '_xtrain'], out[name + '_y'] = xt, np.asarray(y)
+        out[name + '_hyper'] = np.array([beta, 1e-2, max_eig])
+        out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
+        out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
+
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %d arrays, %.1f KiB' % (path, len(out), os.path.getsize(path) / 1024))

@@ -319,6 +319,11 @@ def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
     assert [(c[0], c[1]) for c in calls] == [('lockstep', _lib.GABO_F64), ('lockstep', _lib.GABO_F64),
                                              ('rtr', _lib.GABO_F32)]
     assert 'ineq_constraints' in calls[0][2] and 'delta_cons' in calls[0][2] and 'ineq_constraints' not in calls[2][2]
+    calls.clear()
+    mo.gen_candidates_manifold(spd_x0, acq_for(FakeGP(_lib.SPD, 3, 32)), g.PositiveDefinite(3),
+                               mo.StrictConstrainedTrustRegions(mingradnorm=2e-4, maxiter=100, minstepsize=1e-4),
+                               approx_hessian=True, inequality_constraints=cons)
+    assert calls[0][:2] == ('lockstep', _lib.GABO_F64) and 'strict' in calls[0][2]
     with pytest.raises(NotImplementedError):
         mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6), mo.TrustRegions(),
                                    inequality_constraints=cons)
@@ -360,7 +365,7 @@ def test_sharded_raw_sample_screening_world_size_2_gloo():
     assert ret[0][1] == [5] and ret[1][1] == [6]                # 11 samples: blocks [0, 5) and [5, 11)
 
 
-@pytest.mark.parametrize('name', ['ctr_spd2_active', 'ctr_spd2', 'ctr_spd3'])
+@pytest.mark.parametrize('name', ['ctr_spd2_active', 'ctr_spd2', 'ctr_spd3', 'sctr_spd2_active', 'sctr_spd3'])
 @pytest.mark.parametrize('closed_form', [True, False])
 def test_lockstep_constrained_trust_regions_reproduce_the_reference_solver(monkeypatch, golden, name, closed_form):
     # the golden arrays come from the reference's OWN ConstrainedTrustRegions class in gabo_spd.py's configuration
@@ -380,7 +385,9 @@ def test_lockstep_constrained_trust_regions_reproduce_the_reference_solver(monke
     else:
         cons = [lambda x: max_eig - torch.linalg.eigvalsh(x)[-1]]
     handle = type('GP', (), {'manifold': _lib.SPD, 'dim': xt.shape[-1], 'n_train': xt.shape[0]})()
-    X, val, iters, reason = mo.batched_trust_regions(handle, golden[name + '_x0'], maxiter=100, mingradnorm=1e-4,
+    strict = name.startswith('sctr')          # StrictConstrainedTrustRegions with hd_gabo_spd.py's mingradnorm
+    X, val, iters, reason = mo.batched_trust_regions(handle, golden[name + '_x0'], maxiter=100,
+                                                     mingradnorm=2e-4 if strict else 1e-4, strict=strict,
                                                      ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
     np.testing.assert_array_equal(iters.numpy(), golden[name + '_iters'])
     np.testing.assert_allclose(X.numpy(), golden[name + '_x'], rtol=0, atol=1e-8)

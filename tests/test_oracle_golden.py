@@ -242,3 +242,21 @@ def test_constrained_trust_region_oracle_matches_reference_solver(golden, name):
         assert k == int(golden[name + '_iters'][i])
         np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
         assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
+
+
+@pytest.mark.parametrize('name', ['sctr_spd2_active', 'sctr_spd3'])
+def test_strict_constrained_trust_region_oracle_matches_reference_solver(golden, name):
+    # StrictConstrainedTrustRegions (constrained_trust_regions.py:737-1415) with hd_gabo_spd.py's settings
+    from oracle import ctr as octr
+    from oracle import gp as ogp
+    from oracle import rtr as ortr
+    beta, noise, max_eig = golden[name + '_hyper']
+    gp = ogp.make_gp('spd', golden[name + '_xtrain'], golden[name + '_y'], beta=float(beta), noise=float(noise))
+    opts = ortr.TROptions(mingradnorm=2e-4, maxiter=100)
+    cons = [octr.max_eigenvalue_constraint(float(max_eig))]
+    for i, x0 in enumerate(golden[name + '_x0']):
+        x, c, k = octr.solve_ctr(gp, x0, ineq_constraints=cons, opts=opts, strict=True)
+        assert k == int(golden[name + '_iters'][i])
+        np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
+        assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
+        assert np.linalg.eigvalsh(x)[-1] <= float(max_eig) + 1e-12            # strict: never leaves the feasible set
