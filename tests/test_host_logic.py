@@ -392,3 +392,62 @@ def test_lockstep_constrained_trust_regions_reproduce_the_reference_solver(monke
     np.testing.assert_array_equal(iters.numpy(), golden[name + '_iters'])
     np.testing.assert_allclose(X.numpy(), golden[name + '_x'], rtol=0, atol=1e-8)
     np.testing.assert_allclose(-val.numpy(), golden[name + '_cost'], rtol=1e-9, atol=1e-13)
+
+
+def test_gabo_spd_iteration_through_the_public_api_with_emulated_kernels(monkeypatch):
+    # The acquisition step of examples/bo_spd/benchmark_examples/gabo_spd.py:136-203 through the drop-in surface:
+    # joint_optimize_manifold(EI, PositiveDefinite, ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100), Mandel
+    # pre / post processing, approx_hessian=True, one max-eigenvalue inequality constraint).  The CUDA entry points
+    # are replaced by oracle-backed stand-ins, so this pins the HOST wiring (shapes through pre / post processing,
+    # solver dispatch, candidate selection) without a device; the kernels themselves are covered by the -m gpu tests.
+    import functools
+    from gabotorch_b200 import _lib, manifold_optimization as mo, ops, riemannian_utils as ru
+    from oracle import ctr as octr, gp as ogp, rtr as ortr, spd as ospd
+    d, n, max_eig = 2, 10, 2.0
+    rng = np.random.default_rng(17)
+    xt = ospd.spd_sample(rng, n, d, max_cond=50.0)
+    y = ospd.ackley(ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(xt)))
+    gp = ogp.make_gp('spd', xt, y, beta=0.5 + math.log(2.0), noise=1e-2)
+    fake = _OracleOps(gp)
+    for attr in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op'):
+        monkeypatch.setattr(ops, attr, getattr(fake, attr))
+    monkeypatch.setattr(ops, 'device', lambda: torch.device('cpu'))
+    monkeypatch.setattr(ops, 'mandel_unpack', lambda v: ospd.vector_to_symmetric_matrix_mandel(torch.as_tensor(v)))
+    monkeypatch.setattr(ops, 'mandel_pack', lambda m: ospd.symmetric_matrix_to_vector_mandel(torch.as_tensor(m)))
+
+    def argmax_records(values, gidx=None):
+        v = torch.nan_to_num(torch.as_tensor(values, dtype=torch.float64).reshape(-1), nan=-float('inf'))
+        slot = torch.argmax(v).reshape(1)
+        return slot, v[slot]
+    monkeypatch.setattr(ops, 'argmax_records', argmax_records)
+
+    class Handle:                                   # what ExpectedImprovement.device_gp() hands to the solvers
+        manifold, dim, n_train = _lib.SPD, d, n
+
+        def with_compute(self, compute):
+            return self
+    acq = mo.ExpectedImprovement.__new__(mo.ExpectedImprovement)
+    acq._gp = Handle()
+    man = g.PositiveDefinite(d)
+    man.min_eig, man.max_eig = 0.5, 0.9 * max_eig                      # feasible raw samples (spd_sample law)
+    cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=max_eig)]
+    solver = mo.ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=30)
+    kw = dict(pre_processing_manifold=ru.vector_to_symmetric_matrix_mandel_torch,
+              post_processing_manifold=ru.symmetric_matrix_to_vector_mandel_torch, approx_hessian=True,
+              inequality_constraints=cons)
+    ics = mo.gen_batch_initial_conditions_manifold(acq, man, None, 1, 4, 24, options={'seed': 5},
+                                                   post_processing_manifold=ru.symmetric_matrix_to_vector_mandel_torch)
+    assert tuple(ics.shape) == (4, 1, 3)
+    cand, vals = mo.gen_candidates_manifold(ics, acq, man, solver, **kw)
+    assert tuple(cand.shape) == (4, 1, 3) and tuple(vals.shape) == (4,)
+    opts = ortr.TROptions(mingradnorm=1e-4, maxiter=30)
+    mats0 = ospd.vector_to_symmetric_matrix_mandel(ics[:, 0]).numpy()
+    for i in range(4):                              # every restart equals the serial oracle solve from the same start
+        xi, ci, _ = octr.solve_ctr(gp, mats0[i], ineq_constraints=[octr.max_eigenvalue_constraint(max_eig)], opts=opts)
+        np.testing.assert_allclose(ospd.vector_to_symmetric_matrix_mandel(cand[i]).numpy()[0], xi, rtol=0, atol=1e-8)
+        assert abs(float(vals[i]) + ci) <= 1e-9 * max(1.0, abs(ci))
+    best = mo.joint_optimize_manifold(acq, man, solver, q=1, num_restarts=4, raw_samples=24, options={'seed': 5}, **kw)
+    assert tuple(best.shape) == (1, 3)
+    np.testing.assert_allclose(best.numpy(), cand[int(torch.argmax(vals))].numpy(), rtol=0, atol=1e-12)
+    # (feasibility of the result is NOT asserted: the non-strict solver only keeps the LINEARISED constraints, and the
+    # reference's own class leaves the feasible set in the same way -- golden set ctr_spd2_active)
