@@ -631,6 +631,40 @@ class Bench:
                 'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': self.hbm_peak, 'unit': 'GB/s',
                              'frac': gbs / self.hbm_peak, 'algorithmic_bytes_per_launch': nbytes}}
 
+    def extra_acq_tr_spd(self, constrained, R=256, d=3, n_train=32, noise=1e-2, steps=3):
+        """The solver configurations of gabo_spd.py on SPD(3) through the lock-step driver (fp64 evaluator): plain
+        TrustRegions(maxiter=100) or ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100) with one max-eigenvalue
+        inequality constraint.  Host-driven (about 8 launches per inner iteration): the time is launch latency."""
+        import functools
+        from gabotorch_b200 import manifold_optimization as mo, riemannian_utils as ru
+        torch, ops, _lib = self.torch, self.ops, self._lib
+        rng = np.random.default_rng(31)
+        xv = spd_sample_mandel(rng, n_train, d)
+        y = np.array([float(np.sum(v * v)) for v in xv])
+        y = (y - y.mean()) / (y.std() + 1e-12)
+        import gabotorch_b200 as g
+        model = g.ManifoldGP(torch.from_numpy(xv), torch.from_numpy(y),
+                             g.ScaleKernel(g.SpdAffineInvariantGaussianKernel(beta_min=0.5)), noise=noise)
+        model.covar_module.outputscale = 1.0
+        gp = g.ExpectedImprovement(model, best_f=float(y.min()), compute='f64').device_gp()
+        x0 = ops.mandel_unpack(torch.from_numpy(spd_sample_mandel(np.random.default_rng(32 + self.rank), R, d,
+                                                                  min_eig=0.5, max_eig=2.5)))
+        kw = dict(maxiter=100)
+        if constrained:
+            cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.0)]
+            kw.update(mingradnorm=1e-4, ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
+        res = {}
+
+        def step():
+            res['out'] = mo.batched_trust_regions(gp, x0, **kw)
+        ms = self.time_steps(step, steps, 1, flush=False) / steps
+        it = res['out'][2].double()
+        return {'workload': 'acq %s on EI, SPD(%d), %d restarts/GPU, lock-step driver, fp64 evaluator, n_train=%d'
+                            % ('ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100) + max-eigenvalue constraint'
+                               if constrained else 'TrustRegions(maxiter=100)', d, R, n_train),
+                'solves_per_s': self.world * R / (ms * 1e-3), 'ms_per_step': ms, 'mean_outer_iters': it.mean().item(),
+                'max_outer_iters': int(it.max().item())}
+
     def guarded(self, fn, *a, **kw):
         """Extras of the 'next' rows must never take the headline line down with them."""
         try:
@@ -692,6 +726,8 @@ class Bench:
                 extras.append(self.guarded(self.extra_acq_rtr))
                 extras.append(self.guarded(self.extra_gp_fit))
                 extras.append(self.guarded(self.extra_reconstruct))
+                extras.append(self.guarded(self.extra_acq_tr_spd, False))
+                extras.append(self.guarded(self.extra_acq_tr_spd, True))
         cpu = None
         if self.rank == 0 and self.world == 1 and not args.no_cpu_baseline:
             cpu = self.cpu_baseline()
