@@ -52,6 +52,22 @@ def min_eigenvalue_constraint(minimum_eigenvalue):
     return value, grad
 
 
+def sphere_domain_constraint(centre, angle):
+    """``angle - acos(clamp(<x, centre>))`` on the sphere
+    (examples/bo_sphere/constrained_benchmark_examples/gabo_sphere_inequality_constraints.py:113-120); Riemannian
+    gradient = projection of the Euclidean one, ``centre / sqrt(1 - <x, centre>^2)`` (zero where the clamp is active)."""
+    centre = np.asarray(centre, dtype=np.float64)
+
+    def value(x):
+        return angle - np.arccos(np.clip(x @ centre, -1.0, 1.0))
+
+    def grad(x):
+        u = x @ centre
+        e = centre / np.sqrt(1.0 - u * u) if -1.0 < u < 1.0 else np.zeros_like(centre)
+        return e - (x @ e) * x
+    return value, grad
+
+
 def _tau_constraints(fc, pe, pd, idx, delta_cons):
     """Largest step along delta keeping |fc + pe + tau pd|_idx <= delta_cons (the quadratic of :578-592, :636-650)."""
     qa = np.inner(pd[idx], pd[idx])

@@ -319,6 +319,56 @@ def main():
         out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
         out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
 
+    # ---- ConstrainedTrustRegions on the sphere with the domain constraint of
+    # examples/bo_sphere/constrained_benchmark_examples/gabo_sphere_inequality_constraints.py:109-122 (points within
+    # pi/4 of a centre; solver ConstrainedTrustRegions(maxiter=200), :249) -------------------------------------------
+    rng_d = np.random.default_rng(SEED + 4)
+    dim = 3
+    centre = np.zeros(dim)
+    centre[0] = 1.0
+    for name, angle in (('ctr_s2_domain', np.pi / 4.), ('ctr_s2_domain_active', 0.12)):   # pi/4: the example's value
+        def domain_constraint(x, angle=angle):
+            c = torch.Tensor(centre).type(x.dtype)
+            in_prod = torch.mm(x[None], c[:, None])
+            in_prod = torch.max(torch.min(in_prod, torch.ones(1, dtype=x.dtype)), -torch.ones(1, dtype=x.dtype))
+            return angle - torch.acos(in_prod)[0, 0]
+        xt = osph.rand(rng_d, 14, dim)
+        y = osph.ackley(xt)
+        beta = 6.5 + LN2
+        gp = ogp.make_gp('sphere', xt, y, beta=beta, noise=1e-2)
+        man = ortr._Man('sphere', xt[0])
+        man.egrad2rgrad = osph.proj
+        cost, grad = ortr.ei_problem(gp)
+
+        class ProblemD(object):
+            manifold = man
+            verbosity = 0
+
+            def precon(self, x, dd):
+                if np.sum(dd) == 0.:
+                    dd += 1e-30
+                return dd
+        problem = ProblemD()
+        problem.cost, problem.grad = cost, grad
+        problem.hess = types.MethodType(get_hessianfd_c, problem)
+        x0 = []
+        while len(x0) < 10:                               # starts inside the domain (sample_sphere_constrained, :125)
+            p = osph.rand(rng_d, 1, dim)[0]
+            if np.arccos(np.clip(p @ centre, -1, 1)) < 0.9 * angle:
+                x0.append(p)
+        x0 = np.array(x0)
+        xs, fs, its = [], [], []
+        for i in range(len(x0)):
+            solver = CTR(maxiter=200)
+            x = solver.solve(problem, x=x0[i].copy(), ineq_constraints=[domain_constraint])
+            xs.append(x)
+            fs.append(cost(x))
+            its.append(solver._last_iter)
+        out[name + '_xtrain'], out[name + '_y'] = xt, np.asarray(y)
+        out[name + '_hyper'] = np.array([beta, 1e-2, angle])
+        out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
+        out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
+
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %d arrays, %.1f KiB' % (path, len(out), os.path.getsize(path) / 1024))

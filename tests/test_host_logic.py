@@ -451,3 +451,30 @@ def test_gabo_spd_iteration_through_the_public_api_with_emulated_kernels(monkeyp
     np.testing.assert_allclose(best.numpy(), cand[int(torch.argmax(vals))].numpy(), rtol=0, atol=1e-12)
     # (feasibility of the result is NOT asserted: the non-strict solver only keeps the LINEARISED constraints, and the
     # reference's own class leaves the feasible set in the same way -- golden set ctr_spd2_active)
+
+
+@pytest.mark.parametrize('name', ['ctr_s2_domain', 'ctr_s2_domain_active'])
+def test_lockstep_constrained_trust_regions_on_the_sphere_reproduce_the_reference_solver(monkeypatch, golden, name):
+    # sphere + a user-supplied torch callable (the domain constraint of gabo_sphere_inequality_constraints.py:113-120):
+    # the generic route of batched_constraints (torch.autograd per restart + tangent projection) in the lock-step driver
+    from gabotorch_b200 import _lib, manifold_optimization as mo, ops
+    from oracle import gp as ogp
+    beta, noise, angle = (float(v) for v in golden[name + '_hyper'])
+    xt = golden[name + '_xtrain']
+    gp = ogp.make_gp('sphere', xt, golden[name + '_y'], beta=beta, noise=noise)
+    fake = _OracleOps(gp)
+    for attr in ('to_dev64', 'ei_eval'):
+        monkeypatch.setattr(ops, attr, getattr(fake, attr))
+
+    def domain_constraint(x):
+        centre = torch.zeros(3, dtype=x.dtype)
+        centre[0] = 1
+        in_prod = torch.mm(x[None], centre[:, None])
+        in_prod = torch.max(torch.min(in_prod, torch.ones(1, dtype=x.dtype)), -torch.ones(1, dtype=x.dtype))
+        return angle - torch.acos(in_prod)[0, 0]
+    handle = type('GP', (), {'manifold': _lib.SPHERE, 'dim': 3, 'n_train': xt.shape[0]})()
+    X, val, iters, _ = mo.batched_trust_regions(handle, golden[name + '_x0'][:5], maxiter=200,
+                                                ineq_constraints=mo.batched_constraints([domain_constraint], _lib.SPHERE))
+    np.testing.assert_array_equal(iters.numpy(), golden[name + '_iters'][:5])
+    np.testing.assert_allclose(X.numpy(), golden[name + '_x'][:5], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(-val.numpy(), golden[name + '_cost'][:5], rtol=1e-9, atol=1e-13)

@@ -260,3 +260,20 @@ def test_strict_constrained_trust_region_oracle_matches_reference_solver(golden,
         np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
         assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
         assert np.linalg.eigvalsh(x)[-1] <= float(max_eig) + 1e-12            # strict: never leaves the feasible set
+
+
+@pytest.mark.parametrize('name', ['ctr_s2_domain', 'ctr_s2_domain_active'])
+def test_constrained_trust_region_oracle_on_the_sphere_matches_reference_solver(golden, name):
+    # ConstrainedTrustRegions(maxiter=200) with the domain constraint of gabo_sphere_inequality_constraints.py
+    from oracle import ctr as octr
+    from oracle import gp as ogp
+    from oracle import rtr as ortr
+    beta, noise, angle = golden[name + '_hyper']
+    gp = ogp.make_gp('sphere', golden[name + '_xtrain'], golden[name + '_y'], beta=float(beta), noise=float(noise))
+    cons = [octr.sphere_domain_constraint([1.0, 0.0, 0.0], float(angle))]
+    opts = ortr.TROptions(maxiter=200)
+    for i, x0 in enumerate(golden[name + '_x0'][:5]):
+        x, c, k = octr.solve_ctr(gp, x0, ineq_constraints=cons, opts=opts)
+        assert k == int(golden[name + '_iters'][i])
+        np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
+        assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
