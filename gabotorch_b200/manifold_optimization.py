@@ -171,7 +171,7 @@ def _rtr_kernel_covers(gp):
 
 def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1,
                           rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None,
-                          ineq_constraints=None, delta_cons=1e-6, strict=False):
+                          ineq_constraints=None, delta_cons=1e-6, strict=False, eq_constraints=None):
     """The reference's ``TrustRegions.solve`` (robust_trust_regions.py:116-352, tCG :410-520, finite-difference Hessian
     approximate_hessian.py:11-62) for ALL restarts in lock-step, for the cases the single-launch kernel does not cover:
     SPD(d) and spheres of large ambient dimension.  Every cost / gradient evaluation is one launch of ``gabo_ei_eval``
@@ -188,7 +188,11 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
     ``c(x) + <grad c, eta>`` are kept within ``delta_cons`` of feasibility along the tCG path (only negative inequality
     terms count), the step is cut by the root of the corresponding quadratic, and the radius also grows after a step
     that stopped on the constraints.  ``strict=True`` is ``StrictConstrainedTrustRegions`` (:737-1415): a proposal that
-    violates a constraint gets an infinite cost, is rejected and shrinks the radius (:936-952, :972)."""
+    violates a constraint gets an infinite cost, is rejected and shrinks the radius (:936-952, :972).
+    ``eq_constraints`` (same callable form, satisfied when zero) are held in the same way with every term counting
+    (``gabo_sphere_equality_constraints.py``).  Equality and inequality constraints together are refused: the reference
+    builds its active set for that case with ``np.where(term < 0)[0] + n_eq`` over the whole vector (:573-577), which
+    indexes past the inequality block."""
     X = ops.to_dev64(x0).clone()
     R = X.shape[0]
     dev = X.device
@@ -247,13 +251,20 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
     NEG, EXC, LIN, SUP, MAXI, INC, CONS = range(7)
     dc2 = float(delta_cons) ** 2
 
+    if eq_constraints is not None and ineq_constraints is not None:
+        raise NotImplementedError('equality and inequality constraints together are not supported (see the docstring)')
+    constraints = eq_constraints if eq_constraints is not None else ineq_constraints
+    is_eq = eq_constraints is not None
+
     def step_to_constraints(fc, pe, pd, step):
         """(violated (R,), tau (R,)): does the linearised constraint term leave the delta_cons ball at ``step``, and the
         step that brings it back onto it (constrained_trust_regions.py:565-592 / :622-650; inequality constraints only,
         where the reference's index set is exactly the negative terms)."""
-        term = torch.clamp(fc + pe + step.unsqueeze(-1) * pd, max=0.0)
+        term = fc + pe + step.unsqueeze(-1) * pd
+        if not is_eq:
+            term = torch.clamp(term, max=0.0)
         bad = (term * term).sum(-1) > dc2
-        m = (term < 0).to(fc.dtype)
+        m = torch.ones_like(term) if is_eq else (term < 0).to(fc.dtype)
         qa = (m * pd * pd).sum(-1)
         qb = 2.0 * ((m * fc * pd).sum(-1) + (m * pe * pd).sum(-1))
         qc = (m * fc * fc).sum(-1) + 2.0 * (m * fc * pe).sum(-1) + (m * pe * pe).sum(-1) - dc2
@@ -288,8 +299,8 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         live = active.clone()
         r2 = radius * radius
         pw = norm_r0 ** theta
-        if ineq_constraints is not None:
-            fc, gcs = ineq_constraints(X)                       # (R, C) values, C Riemannian gradients
+        if constraints is not None:
+            fc, gcs = constraints(X)                            # (R, C) values, C Riemannian gradients
             pe = torch.zeros_like(fc)                           # <grad c, eta>, eta = 0
         for j in range(maxinner):
             if not bool(live.any()):
@@ -302,7 +313,7 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
             out1 = live & ((d_hd <= 0) | (e_pe_new >= r2))
             tau = (-e_pd + (e_pd * e_pd + d_pd * (r2 - e_pe)).sqrt()) / d_pd
             code1 = torch.where(d_hd <= 0, NEG, EXC).to(torch.int32)
-            if ineq_constraints is not None:
+            if constraints is not None:
                 pd = torch.stack([inner(X, gc, delta) for gc in gcs], dim=-1)
                 tau = torch.where(torch.isnan(tau), torch.zeros_like(tau), tau)          # :562-563
                 bad, tau_c = step_to_constraints(fc, pe, pd, tau)
@@ -312,7 +323,7 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
             heta = torch.where(bc(out1), heta + bc(tau) * hdelta, heta)
             stop = torch.where(out1, code1, stop)
             live = live & ~out1
-            if ineq_constraints is not None:                    # the full CG step would violate the constraints
+            if constraints is not None:                         # the full CG step would violate the constraints
                 bad, tau_c = step_to_constraints(fc, pe, pd, alpha)
                 outc = live & bad
                 eta = torch.where(bc(outc), eta + bc(tau_c) * delta, eta)
@@ -341,14 +352,15 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
             e_pd = torch.where(live, beta * (e_pd + alpha * d_pd), e_pd)
             d_pd = torch.where(live, r_r + beta * beta * d_pd, d_pd)
             z_r = torch.where(live, r_r, z_r)
-            if ineq_constraints is not None:
+            if constraints is not None:
                 pe = torch.where(live.unsqueeze(-1), pe + alpha.unsqueeze(-1) * pd, pe)
         # ---- proposal, rho, radius update, acceptance (robust_trust_regions.py:225-311) ----
         x_prop = retr(X, eta)
         fx_prop = cost(x_prop)
         invalid = torch.zeros_like(active)
-        if strict and ineq_constraints is not None:
-            invalid = torch.clamp(ineq_constraints(x_prop)[0], max=0.0).abs().sum(-1) != 0
+        if strict and constraints is not None:
+            fcp = constraints(x_prop)[0]
+            invalid = (fcp if is_eq else torch.clamp(fcp, max=0.0)).abs().sum(-1) != 0
             fx_prop = torch.where(invalid, inf, fx_prop)
         rho_reg = torch.clamp(fx.abs(), min=1.0) * eps * rho_regularization
         rhonum = fx - fx_prop + rho_reg
@@ -618,10 +630,14 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     """All restarts solved in one launch (manifold_optimize.py:124-228).  Returns ``(candidates, acquisition values)``
     with the shapes of the reference: ``R x 1 x dvec`` and ``R``.  Bounds are accepted and ignored, as in the
     reference (:131-132 are never used by its body)."""
+    if equality_constraints is not None and inequality_constraints is not None:
+        raise NotImplementedError('equality and inequality constraints together are not supported')
     if equality_constraints is not None:
-        raise NotImplementedError('equality constraints are SURVEY 8f "next"; there is no CPU fallback')
+        inequality_constraints, eq_mode = equality_constraints, True
+    else:
+        eq_mode = False
     if inequality_constraints is not None and type(solver).__name__ not in _CONSTRAINED_SOLVERS:
-        raise NotImplementedError('inequality constraints need [Strict]ConstrainedTrustRegions (the ALM solver is '
+        raise NotImplementedError('constraints need [Strict]ConstrainedTrustRegions (the ALM solver is '
                                   'SURVEY 8f "next"); there is no CPU fallback')
     if solver_init_conds:
         raise NotImplementedError('solver-side initialisation (population methods) is not supported')
@@ -650,7 +666,7 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
         solve = batched_trust_regions
         gp = gp.with_compute(_lib.GABO_F64)
         cons = inequality_constraints if isinstance(inequality_constraints, (list, tuple)) else [inequality_constraints]
-        sopts = dict(sopts, ineq_constraints=batched_constraints(cons, kind),
+        sopts = dict(sopts, **{'eq_constraints' if eq_mode else 'ineq_constraints': batched_constraints(cons, kind)},
                      delta_cons=float(getattr(solver, 'Delta_cons', 1e-6)),
                      strict=type(solver).__name__ == 'StrictConstrainedTrustRegions')
     elif _rtr_kernel_covers(gp):

@@ -369,6 +369,46 @@ def main():
         out[name + '_x0'], out[name + '_x'] = x0, np.array(xs)
         out[name + '_cost'], out[name + '_iters'] = np.array(fs), np.array(its)
 
+    # ---- equality constraint: the great circle x[1] = 0 of gabo_sphere_equality_constraints.py:104-109 with
+    # ConstrainedTrustRegions(maxiter=200) (:197), starts on the circle (sample_sphere_constrained, :112-118) ----------
+    rng_e = np.random.default_rng(SEED + 5)
+
+    def y_great_circle(x):
+        return x[1] - 0.
+    xt = osph.rand(rng_e, 14, 3)
+    y = osph.ackley(xt)
+    beta = 6.5 + LN2
+    gp = ogp.make_gp('sphere', xt, y, beta=beta, noise=1e-2)
+    man = ortr._Man('sphere', xt[0])
+    man.egrad2rgrad = osph.proj
+    cost, grad = ortr.ei_problem(gp)
+
+    class ProblemE(object):
+        manifold = man
+        verbosity = 0
+
+        def precon(self, x, dd):
+            if np.sum(dd) == 0.:
+                dd += 1e-30
+            return dd
+    problem = ProblemE()
+    problem.cost, problem.grad = cost, grad
+    problem.hess = types.MethodType(get_hessianfd_c, problem)
+    x0 = rng_e.standard_normal((8, 3))
+    x0[:, 1] = 0.
+    x0 /= np.linalg.norm(x0, axis=-1, keepdims=True)
+    xs, fs, its = [], [], []
+    for i in range(len(x0)):
+        solver = CTR(maxiter=200)
+        x = solver.solve(problem, x=x0[i].copy(), eq_constraints=[y_great_circle])
+        xs.append(x)
+        fs.append(cost(x))
+        its.append(solver._last_iter)
+    out['ctr_s2_circle_xtrain'], out['ctr_s2_circle_y'] = xt, np.asarray(y)
+    out['ctr_s2_circle_hyper'] = np.array([beta, 1e-2])
+    out['ctr_s2_circle_x0'], out['ctr_s2_circle_x'] = x0, np.array(xs)
+    out['ctr_s2_circle_cost'], out['ctr_s2_circle_iters'] = np.array(fs), np.array(its)
+
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %d arrays, %.1f KiB' % (path, len(out), os.path.getsize(path) / 1024))

@@ -327,9 +327,14 @@ def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
     with pytest.raises(NotImplementedError):
         mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6), mo.TrustRegions(),
                                    inequality_constraints=cons)
+    calls.clear()
+    mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6),
+                               mo.ConstrainedTrustRegions(), equality_constraints=[lambda x: x[1]])
+    assert calls[0][:2] == ('lockstep', _lib.GABO_F64) and 'eq_constraints' in calls[0][2]
     with pytest.raises(NotImplementedError):
         mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6),
-                                   mo.ConstrainedTrustRegions(), equality_constraints=[lambda x: x[0]])
+                                   mo.ConstrainedTrustRegions(), equality_constraints=[lambda x: x[1]],
+                                   inequality_constraints=cons)
 
 
 def _screen_worker(rank, world, port, ret):
@@ -478,3 +483,24 @@ def test_lockstep_constrained_trust_regions_on_the_sphere_reproduce_the_referenc
     np.testing.assert_array_equal(iters.numpy(), golden[name + '_iters'][:5])
     np.testing.assert_allclose(X.numpy(), golden[name + '_x'][:5], rtol=0, atol=1e-8)
     np.testing.assert_allclose(-val.numpy(), golden[name + '_cost'][:5], rtol=1e-9, atol=1e-13)
+
+
+def test_lockstep_equality_constrained_trust_regions_reproduce_the_reference_solver(monkeypatch, golden):
+    # the great-circle equality constraint of gabo_sphere_equality_constraints.py:104-109 as a plain torch callable
+    from gabotorch_b200 import _lib, manifold_optimization as mo, ops
+    from oracle import gp as ogp
+    name = 'ctr_s2_circle'
+    beta, noise = (float(v) for v in golden[name + '_hyper'])
+    xt = golden[name + '_xtrain']
+    gp = ogp.make_gp('sphere', xt, golden[name + '_y'], beta=beta, noise=noise)
+    fake = _OracleOps(gp)
+    for attr in ('to_dev64', 'ei_eval'):
+        monkeypatch.setattr(ops, attr, getattr(fake, attr))
+    handle = type('GP', (), {'manifold': _lib.SPHERE, 'dim': 3, 'n_train': xt.shape[0]})()
+    cons = mo.batched_constraints([lambda x: x[1] - 0.], _lib.SPHERE)
+    X, val, iters, _ = mo.batched_trust_regions(handle, golden[name + '_x0'], maxiter=200, eq_constraints=cons)
+    np.testing.assert_array_equal(iters.numpy(), golden[name + '_iters'])
+    np.testing.assert_allclose(X.numpy(), golden[name + '_x'], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(-val.numpy(), golden[name + '_cost'], rtol=1e-9, atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        mo.batched_trust_regions(handle, golden[name + '_x0'], eq_constraints=cons, ineq_constraints=cons)

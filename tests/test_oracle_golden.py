@@ -277,3 +277,21 @@ def test_constrained_trust_region_oracle_on_the_sphere_matches_reference_solver(
         assert k == int(golden[name + '_iters'][i])
         np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
         assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
+
+
+def test_equality_constrained_trust_region_oracle_matches_reference_solver(golden):
+    # the great-circle constraint x[1] = 0 of gabo_sphere_equality_constraints.py with ConstrainedTrustRegions(maxiter=200)
+    from oracle import ctr as octr
+    from oracle import gp as ogp
+    from oracle import rtr as ortr
+    from oracle import sphere as osph
+    name = 'ctr_s2_circle'
+    beta, noise = golden[name + '_hyper']
+    gp = ogp.make_gp('sphere', golden[name + '_xtrain'], golden[name + '_y'], beta=float(beta), noise=float(noise))
+    e1 = np.array([0.0, 1.0, 0.0])
+    cons = [(lambda x: x[1], lambda x: osph.proj(x, e1))]
+    for i, x0 in enumerate(golden[name + '_x0']):
+        x, c, k = octr.solve_ctr(gp, x0, eq_constraints=cons, opts=ortr.TROptions(maxiter=200))
+        assert k == int(golden[name + '_iters'][i])
+        np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
+        assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
