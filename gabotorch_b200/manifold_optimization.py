@@ -627,9 +627,16 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
                             post_processing_manifold=None, lower_bounds=None, upper_bounds=None,
                             inequality_constraints=None, equality_constraints=None, approx_hessian=False,
                             solver_init_conds=False, options=None, return_info=False):
-    """All restarts solved in one launch (manifold_optimize.py:124-228).  Returns ``(candidates, acquisition values)``
+    """All restarts solved together (manifold_optimize.py:124-228).  Returns ``(candidates, acquisition values)``
     with the shapes of the reference: ``R x 1 x dvec`` and ``R``.  Bounds are accepted and ignored, as in the
-    reference (:131-132 are never used by its body)."""
+    reference (:131-132 are never used by its body).
+
+    Recognised solvers: ``ConjugateGradient`` (one launch, ``gabo_acq_rcg``), ``TrustRegions`` (one launch on spheres
+    the register kernel covers, ``gabo_acq_rtr``; lock-step over the batched kernels otherwise) and
+    ``ConstrainedTrustRegions`` / ``StrictConstrainedTrustRegions`` with inequality OR equality constraints (lock-step).
+    Hessian-vector products are always the finite differences of approximate_hessian.py (the reference's
+    ``approx_hessian=True``); with ``approx_hessian=False`` the reference differentiates the gradient with autograd
+    instead.  Anything else raises ``NotImplementedError``: there is no CPU fallback."""
     if equality_constraints is not None and inequality_constraints is not None:
         raise NotImplementedError('equality and inequality constraints together are not supported')
     if equality_constraints is not None:
