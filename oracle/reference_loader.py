@@ -115,3 +115,17 @@ def load_constrained_trust_regions():
     fd = importlib.import_module('BoManifolds.manifold_optimization.approximate_hessian')
     ctr.ConstrainedTrustRegions.Strict = ctr.StrictConstrainedTrustRegions      # handed out together
     return ctr.ConstrainedTrustRegions, fd.get_hessianfd, cons
+
+
+def load_alm():
+    """The reference's own ``AugmentedLagrangeMethod`` (manifold_optimization/augmented_Lagrange_method.py).  It does
+    ``import pymanopt`` and tests ``isinstance(inner_solver, pymanopt.solvers.NelderMead)``: the stand-in package of
+    ``load_trust_regions`` gets an empty ``NelderMead`` class for that test."""
+    load()
+    load_trust_regions()
+    import importlib
+    solvers = sys.modules['pymanopt.solvers']
+    if not hasattr(solvers, 'NelderMead'):
+        solvers.NelderMead = type('NelderMead', (), {})
+    alm = importlib.import_module('BoManifolds.manifold_optimization.augmented_Lagrange_method')
+    return alm.AugmentedLagrangeMethod

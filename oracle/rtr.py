@@ -43,6 +43,7 @@ class _Man:
         m = _sph if name == 'sphere' else _spd
         self.inner, self.norm, self.retr, self.transp = m.inner, m.norm, m.retr, m.transp
         self.zerovec = lambda x: np.zeros(np.shape(x))
+        self.dist = m.dist
         if name == 'sphere':
             self.dim = x0.shape[-1] - 1            # pymanopt Sphere.dim
             self.typicaldist = np.pi               # pymanopt Sphere.typicaldist
@@ -129,18 +130,24 @@ def truncated_cg(man, hess, x, fgradx, delta_radius, theta, kappa, mininner, max
     return eta, heta, j, stop
 
 
-def solve_tr(gp, x0, opts=None, trace=None):
-    """One ``TrustRegions.solve`` on cost = -EI with the finite-difference Hessian.  Returns (x, cost, iters)."""
+def solve_tr(gp, x0, opts=None, trace=None, cost=None, grad=None, hess_grad=None):
+    """One ``TrustRegions.solve`` on cost = -EI with the finite-difference Hessian.  Returns (x, cost, iters).
+    ``cost`` / ``grad`` replace the EI problem (the augmented Lagrangian of oracle/alm.py); ``hess_grad`` is the gradient
+    the finite-difference Hessian differentiates (the ALM subproblem binds ``get_hessianfd`` to the ORIGINAL problem,
+    augmented_Lagrange_method.py:322)."""
     opts = opts or TROptions()
     x = np.array(x0, dtype=np.float64)
     man = _Man(gp.manifold, x)
-    cost, grad = ei_problem(gp)
+    ei_cost, ei_grad = ei_problem(gp)
+    cost = cost or ei_cost
+    grad = grad or ei_grad
+    hess_grad = hess_grad or grad
     maxinner = man.dim if opts.maxinner is None else opts.maxinner
     delta_bar = man.typicaldist if opts.delta_bar is None else opts.delta_bar
     delta0 = delta_bar / 8 if opts.delta0 is None else opts.delta0
 
     def hess(p, a):
-        return hessian_fd(man, grad, p, a, opts.fd_epsilon)
+        return hessian_fd(man, hess_grad, p, a, opts.fd_epsilon)
 
     k = 0
     fx = cost(x)

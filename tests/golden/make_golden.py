@@ -409,6 +409,65 @@ def main():
     out['ctr_s2_circle_x0'], out['ctr_s2_circle_x'] = x0, np.array(xs)
     out['ctr_s2_circle_cost'], out['ctr_s2_circle_iters'] = np.array(fs), np.array(its)
 
+    # ---- augmented Lagrangian: the reference's own AugmentedLagrangeMethod around its own TrustRegions, as in
+    # gabo_sphere_inequality_constraints.py:251-256 / gabo_sphere_equality_constraints.py:199-203 (gammas_fact=0.05);
+    # iteration limits reduced (30 outer, 50 inner) to keep the fixture generation short ---------------------------
+    from oracle import alm as oalm  # noqa: F401
+    ALM = reference_loader.load_alm()
+    rng_a = np.random.default_rng(SEED + 6)
+    for name, kind in (('alm_s2_domain', 'ineq'), ('alm_s2_circle', 'eq')):
+        angle = 0.12
+
+        def domain_constraint(x, angle=angle):
+            c = torch.Tensor(centre).type(x.dtype)
+            in_prod = torch.mm(x[None], c[:, None])
+            in_prod = torch.max(torch.min(in_prod, torch.ones(1, dtype=x.dtype)), -torch.ones(1, dtype=x.dtype))
+            return angle - torch.acos(in_prod)[0, 0]
+
+        def great_circle(x):
+            return x[1] - 0.
+        xt = osph.rand(rng_a, 14, 3)
+        y = osph.ackley(xt)
+        beta = 6.5 + LN2
+        gp = ogp.make_gp('sphere', xt, y, beta=beta, noise=1e-2)
+        man = ortr._Man('sphere', xt[0])
+        man.egrad2rgrad = osph.proj
+        cost, grad = ortr.ei_problem(gp)
+
+        class ProblemA(object):
+            manifold = man
+            verbosity = 0
+
+            def precon(self, x, dd):
+                if np.sum(dd) == 0.:
+                    dd += 1e-30
+                return dd
+        problem = ProblemA()
+        problem.cost, problem.grad = cost, grad
+        if kind == 'ineq':
+            x0 = []
+            while len(x0) < 6:
+                p = osph.rand(rng_a, 1, 3)[0]
+                if np.arccos(np.clip(p @ centre, -1, 1)) < 0.9 * angle:
+                    x0.append(p)
+            x0 = np.array(x0)
+        else:
+            x0 = rng_a.standard_normal((6, 3))
+            x0[:, 1] = 0.
+            x0 /= np.linalg.norm(x0, axis=-1, keepdims=True)
+        xs, its = [], []
+        for i in range(len(x0)):
+            solver = ALM(inner_solver=TrustRegions(maxiter=50), maxiter=30, gammas_fact=0.05)
+            if kind == 'ineq':
+                x = solver.solve(problem, x=x0[i].copy(), ineq_constraints=[domain_constraint])
+            else:
+                x = solver.solve(problem, x=x0[i].copy(), eq_constraints=[great_circle])
+            xs.append(x)
+            its.append(solver._last_iter)
+        out[name + '_xtrain'], out[name + '_y'] = xt, np.asarray(y)
+        out[name + '_hyper'] = np.array([beta, 1e-2, angle])
+        out[name + '_x0'], out[name + '_x'], out[name + '_iters'] = x0, np.array(xs), np.array(its)
+
     path = os.path.join(HERE, 'reference_vectors.npz')
     np.savez_compressed(path, **out)
     print('wrote %s: %d arrays, %.1f KiB' % (path, len(out), os.path.getsize(path) / 1024))

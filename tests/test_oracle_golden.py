@@ -295,3 +295,22 @@ def test_equality_constrained_trust_region_oracle_matches_reference_solver(golde
         assert k == int(golden[name + '_iters'][i])
         np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
         assert abs(c - golden[name + '_cost'][i]) <= 1e-10 * max(1.0, abs(c))
+
+
+@pytest.mark.parametrize('name,kind', [('alm_s2_domain', 'ineq'), ('alm_s2_circle', 'eq')])
+def test_augmented_lagrangian_oracle_matches_reference_solver(golden, name, kind):
+    # the reference's own AugmentedLagrangeMethod around its own TrustRegions (make_golden.py), constraints of the
+    # constrained sphere examples
+    from oracle import alm as oalm
+    from oracle import ctr as octr
+    from oracle import gp as ogp
+    from oracle import sphere as osph
+    beta, noise, angle = golden[name + '_hyper']
+    gp = ogp.make_gp('sphere', golden[name + '_xtrain'], golden[name + '_y'], beta=float(beta), noise=float(noise))
+    e1 = np.array([0.0, 1.0, 0.0])
+    kw = ({'ineq_constraints': [octr.sphere_domain_constraint([1.0, 0.0, 0.0], float(angle))]} if kind == 'ineq'
+          else {'eq_constraints': [(lambda x: x[1], lambda x: osph.proj(x, e1))]})
+    for i, x0 in enumerate(golden[name + '_x0']):
+        x, k = oalm.solve_alm(gp, x0, maxiter=30, inner_opts={'maxiter': 50}, gammas_fact=0.05, **kw)
+        assert k == int(golden[name + '_iters'][i])
+        np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
