@@ -23,7 +23,7 @@ from .kernel_utils import (SphereGaussianKernel, SphereLaplaceKernel, SpdAffineI
 from ._compat import ScaleKernel  # noqa: F401
 from .manifolds import Sphere, PositiveDefinite  # noqa: F401
 from .manifold_optimization import (ConjugateGradient, TrustRegions, ConstrainedTrustRegions,  # noqa: F401
-                                    StrictConstrainedTrustRegions,
+                                    StrictConstrainedTrustRegions, AugmentedLagrangeMethod,
                                     ExpectedImprovement, ManifoldGP,
                                     gen_batch_initial_conditions_manifold, gen_candidates_manifold,
                                     get_best_candidates, joint_optimize_manifold)

@@ -107,6 +107,23 @@ class StrictConstrainedTrustRegions(ConstrainedTrustRegions):
     a constraint are rejected outright (``hd_gabo_spd.py``'s acquisition solver)."""
 
 
+class AugmentedLagrangeMethod:
+    """Constructor surface of the reference's ``AugmentedLagrangeMethod`` (augmented_Lagrange_method.py:30-62; pymanopt
+    ``Solver`` keywords behind it).  ``inner_solver`` must be a ``TrustRegions``."""
+
+    def __init__(self, inner_solver, bound=20, rho_init=1, thetarho=0.3, tau=0.8, starting_tolgradnorm=1e-3,
+                 ending_tolgradnorm=1e-6, lambdas_fact=1., gammas_fact=1., maxtime=1000, maxiter=1000, mingradnorm=1e-6,
+                 minstepsize=1e-10, maxcostevals=5000, logverbosity=0):
+        if type(inner_solver).__name__ != 'TrustRegions':
+            raise NotImplementedError('AugmentedLagrangeMethod: the batched path drives TrustRegions as inner solver')
+        self.inner_solver = inner_solver
+        self._bound, self._rho_init, self._thetarho, self._tau = bound, rho_init, thetarho, tau
+        self._starting_tolgradnorm, self._ending_tolgradnorm = starting_tolgradnorm, ending_tolgradnorm
+        self._lambdas_fact, self._gammas_fact = lambdas_fact, gammas_fact
+        self._maxtime, self._maxiter, self._mingradnorm = maxtime, maxiter, mingradnorm
+        self._minstepsize, self._maxcostevals, self._logverbosity = minstepsize, maxcostevals, logverbosity
+
+
 def batched_constraints(constraints, manifold_kind):
     """Turn the reference's list of inequality constraints (callables of ONE point returning a zero-dim tensor,
     positive when satisfied; examples/bo_spd/benchmark_examples/gabo_spd.py:136-138) into one callable of the whole
@@ -171,7 +188,7 @@ def _rtr_kernel_covers(gp):
 
 def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1,
                           rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None,
-                          ineq_constraints=None, delta_cons=1e-6, strict=False, eq_constraints=None):
+                          ineq_constraints=None, delta_cons=1e-6, strict=False, eq_constraints=None, penalty=None):
     """The reference's ``TrustRegions.solve`` (robust_trust_regions.py:116-352, tCG :410-520, finite-difference Hessian
     approximate_hessian.py:11-62) for ALL restarts in lock-step, for the cases the single-launch kernel does not cover:
     SPD(d) and spheres of large ambient dimension.  Every cost / gradient evaluation is one launch of ``gabo_ei_eval``
@@ -192,7 +209,10 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
     ``eq_constraints`` (same callable form, satisfied when zero) are held in the same way with every term counting
     (``gabo_sphere_equality_constraints.py``).  Equality and inequality constraints together are refused: the reference
     builds its active set for that case with ``np.where(term < 0)[0] + n_eq`` over the whole vector (:573-577), which
-    indexes past the inequality block."""
+    indexes past the inequality block.
+    ``penalty`` (``X -> (values (R,), Riemannian gradients)``) is added to the cost and to its gradient but NOT to the
+    gradient the finite-difference Hessian differentiates: the augmented Lagrangian subproblem of ``batched_alm``
+    (augmented_Lagrange_method.py:322 binds the Hessian to the original problem)."""
     X = ops.to_dev64(x0).clone()
     R = X.shape[0]
     dev = X.device
@@ -234,14 +254,23 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
 
     inf = torch.full((R,), float('inf'), dtype=torch.float64, device=dev)
 
-    def cost(P):
-        c = -ops.ei_eval(gp, P)
-        return torch.where(torch.isfinite(c), c, inf)
-
-    def cost_grad(P):
+    def plain_cost_grad(P):
         ei, g = ops.ei_eval(gp, P, want_grad=True)
         c = -ei
         return torch.where(torch.isfinite(c), c, inf), -g
+
+    def cost(P):
+        c = -ops.ei_eval(gp, P)
+        if penalty is not None:
+            c = c + penalty(P)[0]
+        return torch.where(torch.isfinite(c), c, inf)
+
+    def cost_grad(P):
+        c, g = plain_cost_grad(P)
+        if penalty is not None:
+            pc, pg = penalty(P)
+            c, g = c + pc, g + pg
+        return torch.where(torch.isfinite(c), c, inf), g
 
     maxinner = int(dim if maxinner is None else maxinner)
     delta_bar = float(typical if delta_bar is None else delta_bar)
@@ -277,11 +306,12 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         small = na < 1e-15
         c = bc(fd_eps / torch.where(small, torch.ones_like(na), na))
         P1 = retr(P, c * A)
-        _, G1 = cost_grad(P1)
+        _, G1 = plain_cost_grad(P1)
         H = transp(P1, P, G1) / c - G / c
         return torch.where(bc(small), torch.zeros_like(H), H)
 
     fx, G = cost_grad(X)
+    Gh = G if penalty is None else plain_cost_grad(X)[1]      # what the finite-difference Hessian differentiates
     ng = norm(X, G)
     radius = torch.full((R,), delta0, dtype=torch.float64, device=dev)
     k = torch.zeros(R, dtype=torch.int32, device=dev)
@@ -305,7 +335,7 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         for j in range(maxinner):
             if not bool(live.any()):
                 break
-            hdelta = hess(X, G, delta)
+            hdelta = hess(X, Gh, delta)
             d_hd = inner(X, delta, hdelta)
             nz = d_hd != 0
             alpha = torch.where(nz, z_r / torch.where(nz, d_hd, torch.ones_like(d_hd)), zero)
@@ -376,6 +406,10 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         fx = torch.where(accept, fx_prop, fx)
         _, g_new = cost_grad(X)
         G = torch.where(bc(accept), g_new, G)
+        if penalty is not None:
+            Gh = torch.where(bc(accept), plain_cost_grad(X)[1], Gh)
+        else:
+            Gh = G
         ng = torch.where(accept, norm(X, G), ng)
         k = k + active.to(torch.int32)
         hit_iter = active & (k >= maxiter)
@@ -383,6 +417,84 @@ def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, the
         reason = torch.where(hit_iter, torch.ones_like(reason), torch.where(hit_grad, 2 * torch.ones_like(reason), reason))
         active = active & ~(hit_iter | hit_grad)
     return X, ops.ei_eval(gp, X), k, reason
+
+
+def batched_alm(gp, x0, inner_opts, ineq_constraints=None, eq_constraints=None, maxiter=1000, minstepsize=1e-10, bound=20.0,
+                rho_init=1.0, thetarho=0.3, tau=0.8, starting_tolgradnorm=1e-3, ending_tolgradnorm=1e-6,
+                lambdas_fact=1.0, gammas_fact=1.0):
+    """The reference's ``AugmentedLagrangeMethod`` (augmented_Lagrange_method.py:66-203, subproblem :205-328) around the
+    lock-step trust-region driver, all restarts together: multipliers, penalty parameters and the stopping test live in
+    per-restart device tensors; the inner tolerance follows the reference's schedule.  ``ineq_constraints`` /
+    ``eq_constraints`` are ``batched_constraints`` callables.  Returns (candidates, values, outer iterations, reasons)."""
+    X = ops.to_dev64(x0).clone()
+    R, dev = X.shape[0], X.device
+    lead = (R,) + (1,) * (X.dim() - 1)
+
+    def both(P):
+        fi, gi = ineq_constraints(P) if ineq_constraints is not None else (P.new_zeros(R, 0), [])
+        fe, ge = eq_constraints(P) if eq_constraints is not None else (P.new_zeros(R, 0), [])
+        return fi, gi, fe, ge
+    fi0, _, fe0, _ = both(X)
+    lambdas = torch.full_like(fi0, lambdas_fact)
+    gammas = torch.full_like(fe0, gammas_fact)
+    rho = torch.full((R,), float(rho_init), dtype=torch.float64, device=dev)
+    oldacc = torch.full((R,), float('inf'), dtype=torch.float64, device=dev)
+    tol = float(starting_tolgradnorm)
+    theta_tol = (ending_tolgradnorm / starting_tolgradnorm) ** (1.0 / maxiter)
+    active = torch.ones(R, dtype=torch.bool, device=dev)
+    iters = torch.zeros(R, dtype=torch.int32, device=dev)
+    reason = torch.zeros(R, dtype=torch.int32, device=dev)
+    if gp.manifold == _lib.SPD:
+        def dist(A, B):
+            return ops.spd_scalar(0, A, B)
+    else:
+        def dist(A, B):
+            return torch.acos(torch.clamp((A * B).sum(-1), -1.0, 1.0))       # pymanopt Sphere.dist
+    k = 0
+    while bool(active.any()):
+        lam, gam, r = lambdas.clone(), gammas.clone(), rho.clone()
+
+        def penalty(P):
+            fi, gi, fe, ge = both(P)
+            slack = lam / r.unsqueeze(-1) - fi
+            on = slack > 0
+            val = (r.unsqueeze(-1) / 2.0 * torch.clamp(slack, min=0.0) ** 2).sum(-1) \
+                + (r.unsqueeze(-1) / 2.0 * (gam / r.unsqueeze(-1) + fe) ** 2).sum(-1)
+            grad = torch.zeros_like(P)
+            for c, g_ in enumerate(gi):
+                coef = torch.where(on[:, c], fi[:, c] * r - lam[:, c], torch.zeros_like(r))
+                grad = grad + coef.reshape(lead) * g_
+            for c, g_ in enumerate(ge):
+                grad = grad + (fe[:, c] * r + gam[:, c]).reshape(lead) * g_
+            return val, grad
+        xbest = batched_trust_regions(gp, X, **dict(inner_opts, mingradnorm=tol), penalty=penalty)[0]
+        xbest = torch.where(active.reshape(lead), xbest, X)                 # finished restarts keep their result
+        fi, _, fe, _ = both(xbest)
+        newacc = torch.zeros(R, dtype=torch.float64, device=dev)
+        if fi.shape[1]:
+            newacc = torch.maximum(newacc, torch.maximum(-lambdas / rho.unsqueeze(-1), fi).abs().amax(-1))
+            new_l = torch.clamp(lambdas + rho.unsqueeze(-1) * fi, min=0.0, max=bound)
+            lambdas = torch.where(active.unsqueeze(-1), new_l, lambdas)
+        if fe.shape[1]:
+            newacc = torch.maximum(newacc, fe.abs().amax(-1))
+            new_g = torch.clamp(gammas + rho.unsqueeze(-1) * fe, min=-bound, max=bound)
+            gammas = torch.where(active.unsqueeze(-1), new_g, gammas)
+        grow = active & ((newacc > tau * oldacc) if k > 0 else torch.ones_like(active))
+        rho = torch.where(grow, rho / thetarho, rho)
+        oldacc = torch.where(active, newacc, oldacc)
+        tol = max(ending_tolgradnorm, tol * theta_tol)
+        k += 1
+        iters = iters + active.to(torch.int32)
+        step = dist(xbest, X)
+        hit_iter = active & torch.full_like(active, k >= maxiter)
+        hit_step = active & ~hit_iter & (step < minstepsize)
+        hit_tol = active & ~hit_iter & ~hit_step & torch.full_like(active, tol <= ending_tolgradnorm)
+        reason = torch.where(hit_iter, torch.ones_like(reason),
+                             torch.where(hit_step, 3 * torch.ones_like(reason),
+                                         torch.where(hit_tol, 2 * torch.ones_like(reason), reason)))
+        X = xbest
+        active = active & ~(hit_iter | hit_step | hit_tol)
+    return X, ops.ei_eval(gp, X), iters, reason
 
 
 def _solver_options(solver):
@@ -633,10 +745,14 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
 
     Recognised solvers: ``ConjugateGradient`` (one launch, ``gabo_acq_rcg``), ``TrustRegions`` (one launch on spheres
     the register kernel covers, ``gabo_acq_rtr``; lock-step over the batched kernels otherwise) and
-    ``ConstrainedTrustRegions`` / ``StrictConstrainedTrustRegions`` with inequality OR equality constraints (lock-step).
+    ``ConstrainedTrustRegions`` / ``StrictConstrainedTrustRegions`` with inequality OR equality constraints and
+    ``AugmentedLagrangeMethod(inner_solver=TrustRegions(...))`` (lock-step).
     Hessian-vector products are always the finite differences of approximate_hessian.py (the reference's
     ``approx_hessian=True``); with ``approx_hessian=False`` the reference differentiates the gradient with autograd
     instead.  Anything else raises ``NotImplementedError``: there is no CPU fallback."""
+    if type(solver).__name__ == 'AugmentedLagrangeMethod':
+        return _gen_candidates_alm(initial_conditions, acquisition_function, manifold, solver, pre_processing_manifold,
+                                   post_processing_manifold, inequality_constraints, equality_constraints, return_info)
     if equality_constraints is not None and inequality_constraints is not None:
         raise NotImplementedError('equality and inequality constraints together are not supported')
     if equality_constraints is not None:
@@ -688,6 +804,45 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     candidates = cand[:, None]
     if post_processing_manifold is not None:
         candidates = post_processing_manifold(candidates)
+    if not like.is_cuda:
+        candidates, val = candidates.to(like.device), val.to(like.device)
+    if return_info:
+        return candidates, val, dict(iters=iters, reason=reason)
+    return candidates, val
+
+
+def _gen_candidates_alm(initial_conditions, acquisition_function, manifold, solver, pre, post, ineq, eq, return_info):
+    """``gen_candidates_manifold`` for ``AugmentedLagrangeMethod`` (equality and inequality constraints, also together)."""
+    if not isinstance(acquisition_function, ExpectedImprovement):
+        raise NotImplementedError('the B200 optimiser evaluates ExpectedImprovement in closed form; got %s'
+                                  % type(acquisition_function).__name__)
+    kind = _manifold_kind(manifold)
+    gp = acquisition_function.device_gp()
+    if gp.manifold != kind:
+        raise ValueError('the manifold and the GP kernel live on different manifolds')
+    gp = gp.with_compute(_lib.GABO_F64)
+    x0 = torch.as_tensor(initial_conditions).detach()
+    like = x0
+    if pre is not None:
+        x0 = pre(x0)
+    x0 = ops.to_dev64(x0)
+    if x0.dim() < 3 or x0.shape[1] != 1:
+        raise NotImplementedError('initial_conditions must be R x 1 x ... (q = 1, manifold_optimize.py:206)')
+
+    def as_batched(c):
+        if c is None:
+            return None
+        return batched_constraints(c if isinstance(c, (list, tuple)) else [c], kind)
+    inner = _trust_region_options(solver.inner_solver)
+    cand, val, iters, reason = batched_alm(
+        gp, x0[:, 0], inner, ineq_constraints=as_batched(ineq), eq_constraints=as_batched(eq),
+        maxiter=int(solver._maxiter), minstepsize=float(solver._minstepsize), bound=float(solver._bound),
+        rho_init=float(solver._rho_init), thetarho=float(solver._thetarho), tau=float(solver._tau),
+        starting_tolgradnorm=float(solver._starting_tolgradnorm), ending_tolgradnorm=float(solver._ending_tolgradnorm),
+        lambdas_fact=float(solver._lambdas_fact), gammas_fact=float(solver._gammas_fact))
+    candidates = cand[:, None]
+    if post is not None:
+        candidates = post(candidates)
     if not like.is_cuda:
         candidates, val = candidates.to(like.device), val.to(like.device)
     if return_info:

@@ -24,6 +24,8 @@ It restates, in plain numpy / torch-CPU fp64, the arithmetic of the reference
   with the pymanopt 0.2.x ``ConjugateGradient`` + ``LineSearchAdaptive`` it calls.
 * ``oracle.rtr``     – the reference's own trust-region solver ``manifold_optimization/robust_trust_regions.py:116-520``
   with the finite-difference Hessian ``manifold_optimization/approximate_hessian.py:11-62``.
+* ``oracle.alm``     – the reference's own augmented Lagrangian solver
+  ``manifold_optimization/augmented_Lagrange_method.py:66-328`` around its ``TrustRegions``.
 * ``oracle.ctr``     – the reference's own constrained trust-region solvers (plain and strict)
   ``manifold_optimization/constrained_trust_regions.py:75-1415`` with the eigenvalue constraints of
   ``Riemannian_utils/spd_constraints_utils_torch.py:17-50`` (the configuration of ``gabo_spd.py``).
@@ -35,7 +37,7 @@ PINNED (against the reference's own code imported from ``/root/reference`` with 
 sphere distance / kernel, Mandel pack/unpack, SPD affine-invariant distance / kernel,
 Frobenius and log-Euclidean distance, nested SPD projection and reconstruction, ``sqrtm_torch``, nested-sphere
 projection chain in both directions, and the trust-region solvers (the reference's ``TrustRegions`` and
-``ConstrainedTrustRegions`` classes themselves are run
+``ConstrainedTrustRegions`` / ``StrictConstrainedTrustRegions`` / ``AugmentedLagrangeMethod`` classes themselves are run
 by ``make_golden.py``; only its third-party base class ``pymanopt.solvers.solver.Solver`` -- the stopping rule -- is a
 stand-in restated from pymanopt 0.2.x).
 
