@@ -313,73 +313,3 @@ def test_lockstep_trust_regions_on_device_vs_oracle(manifold, dim, n, R):
     else:
         np.testing.assert_allclose(np.linalg.norm(X, axis=-1), 1.0, atol=1e-12)
 
-
-@pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: its first device run is the '
-                                        'round-end suite; the host logic is pinned on CPU (tests/test_host_logic.py)')
-@pytest.mark.parametrize('name', ['ctr_spd2_active', 'ctr_spd3'])
-def test_lockstep_constrained_trust_regions_on_device_vs_reference_solver(golden, name):
-    # gabo_spd.py's configuration: ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100), approx_hessian, one
-    # max-eigenvalue constraint; golden arrays from the reference's own class (tests/golden/make_golden.py)
-    import functools
-    from gabotorch_b200 import manifold_optimization as mo, riemannian_utils as ru
-    beta, noise, max_eig = (float(v) for v in golden[name + '_hyper'])
-    gp = ogp.make_gp('spd', golden[name + '_xtrain'], golden[name + '_y'], beta=beta, noise=noise)
-    cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=max_eig)]
-    X, val, iters, _ = mo.batched_trust_regions(device_gp(gp, _lib.GABO_F64), golden[name + '_x0'], maxiter=100,
-                                                mingradnorm=1e-4,
-                                                ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
-    same = iters.cpu().numpy() == golden[name + '_iters']
-    assert same.mean() >= 0.7
-    np.testing.assert_allclose(X.cpu().numpy()[same], golden[name + '_x'][same], rtol=0, atol=1e-5)
-    np.testing.assert_allclose(-val.cpu().numpy()[same], golden[name + '_cost'][same], rtol=1e-5, atol=1e-9)
-
-
-_PENDING = pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: its first device '
-                                                  'run is the round-end suite; the host logic is pinned on CPU '
-                                                  '(tests/test_host_logic.py)')
-
-
-def _domain_constraint(angle):
-    def constraint(x):
-        centre = torch.zeros(3, dtype=x.dtype, device=x.device)
-        centre[0] = 1
-        in_prod = torch.mm(x[None], centre[:, None])
-        one = torch.ones(1, dtype=x.dtype, device=x.device)
-        in_prod = torch.max(torch.min(in_prod, one), -one)
-        return angle - torch.acos(in_prod)[0, 0]
-    return constraint
-
-
-@_PENDING
-def test_lockstep_constrained_trust_regions_on_the_sphere_on_device(golden):
-    # ConstrainedTrustRegions(maxiter=200) with the domain constraint of gabo_sphere_inequality_constraints.py as a
-    # user-supplied torch callable (autograd per restart on the device); golden: the reference's own class
-    from gabotorch_b200 import manifold_optimization as mo
-    name = 'ctr_s2_domain'
-    beta, noise, angle = (float(v) for v in golden[name + '_hyper'])
-    gp = ogp.make_gp('sphere', golden[name + '_xtrain'], golden[name + '_y'], beta=beta, noise=noise)
-    cons = mo.batched_constraints([_domain_constraint(angle)], _lib.SPHERE)
-    X, val, iters, _ = mo.batched_trust_regions(device_gp(gp, _lib.GABO_F64), golden[name + '_x0'], maxiter=200,
-                                                ineq_constraints=cons)
-    same = iters.cpu().numpy() == golden[name + '_iters']
-    assert same.mean() >= 0.7
-    np.testing.assert_allclose(X.cpu().numpy()[same], golden[name + '_x'][same], rtol=0, atol=1e-5)
-
-
-@_PENDING
-def test_lockstep_augmented_lagrangian_on_device(golden):
-    # AugmentedLagrangeMethod(inner_solver=TrustRegions(maxiter=50), maxiter=12) against the oracle restatement of the
-    # reference's class (oracle/alm.py, itself pinned on the class through the alm_* golden arrays)
-    from gabotorch_b200 import manifold_optimization as mo
-    from oracle import alm as oalm, ctr as octr
-    name = 'alm_s2_domain'
-    beta, noise, angle = (float(v) for v in golden[name + '_hyper'])
-    gp = ogp.make_gp('sphere', golden[name + '_xtrain'], golden[name + '_y'], beta=beta, noise=noise)
-    cons = mo.batched_constraints([_domain_constraint(angle)], _lib.SPHERE)
-    X, _, iters, _ = mo.batched_alm(device_gp(gp, _lib.GABO_F64), golden[name + '_x0'], dict(maxiter=50),
-                                    ineq_constraints=cons, maxiter=12)
-    for i, x0 in enumerate(golden[name + '_x0']):
-        xo, ko = oalm.solve_alm(gp, x0, ineq_constraints=[octr.sphere_domain_constraint([1.0, 0.0, 0.0], angle)],
-                                maxiter=12, inner_opts={'maxiter': 50})
-        assert int(iters[i]) == ko
-        np.testing.assert_allclose(X[i].cpu().numpy(), xo, rtol=0, atol=1e-5)
