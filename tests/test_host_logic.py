@@ -566,3 +566,28 @@ def test_lockstep_augmented_lagrangian_reproduces_the_reference_solver(monkeypat
             assert kind == 'eq' and abs(float(cand12[i, 0, 1])) <= 1e-4
     with pytest.raises(NotImplementedError):
         mo.AugmentedLagrangeMethod(inner_solver=mo.ConjugateGradient())
+
+
+def test_batched_constraints_closed_form_equals_autograd(monkeypatch):
+    # max / min eigenvalue constraints: the closed-form batch evaluation (extreme eigenpair) must equal what
+    # torch.autograd gives one point at a time (the reference's route, pymanopt_addons/problem.py:118-137), values and
+    # Riemannian gradients X sym(G) X
+    import functools
+    from gabotorch_b200 import _lib, manifold_optimization as mo, ops, riemannian_utils as ru
+    from oracle import spd as ospd
+    monkeypatch.setattr(ops, 'spd_op', _OracleOps(None).spd_op)
+    X = torch.from_numpy(ospd.spd_sample(np.random.default_rng(1), 9, 4, max_cond=50.0))
+    closed = mo.batched_constraints([functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.5),
+                                     functools.partial(ru.min_eigenvalue_constraint_torch, minimum_eigenvalue=0.2)],
+                                    _lib.SPD)
+    generic = mo.batched_constraints([lambda x: 3.5 - torch.linalg.eigvalsh(x)[-1],
+                                      lambda x: torch.linalg.eigvalsh(x)[0] - 0.2], _lib.SPD)
+    fc, gc = closed(X)
+    fg, gg = generic(X)
+    assert tuple(fc.shape) == (9, 2) and len(gc) == 2
+    np.testing.assert_allclose(fc.numpy(), fg.numpy(), rtol=0, atol=1e-13)
+    for a, b in zip(gc, gg):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=0, atol=1e-11)
+        np.testing.assert_allclose(a.numpy(), np.swapaxes(a.numpy(), -1, -2), rtol=0, atol=1e-12)
+    lam = np.linalg.eigvalsh(X.numpy())
+    np.testing.assert_allclose(fc.numpy(), np.stack([3.5 - lam[:, -1], lam[:, 0] - 0.2], -1), rtol=0, atol=1e-13)
