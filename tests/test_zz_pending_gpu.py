@@ -80,3 +80,37 @@ def test_lockstep_augmented_lagrangian_on_device(golden):
                                 maxiter=12, inner_opts={'maxiter': 50})
         assert int(iters[i]) == ko
         np.testing.assert_allclose(X[i].cpu().numpy(), xo, rtol=0, atol=1e-5)
+
+
+def _load_example(name):
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(name, os.path.join(root, 'examples', name + '.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@_PENDING
+def test_gabo_sphere_example_runs_on_device():
+    # examples/gabo_sphere.py: GP fit + EI + TrustRegions (gabo_acq_rtr) per iteration; host wiring pinned on CPU by
+    # tests/test_example_emulated.py
+    from oracle import sphere as osph
+    x, y, best = _load_example('gabo_sphere').run(dim=3, n_iters=3, num_restarts=5, raw_samples=100, seed=11,
+                                                  verbose=False)
+    assert tuple(x.shape) == (8, 3) and len(best) == 4
+    np.testing.assert_allclose(x.norm(dim=-1).numpy(), 1.0, atol=1e-12)
+    np.testing.assert_allclose(y.numpy(), osph.ackley(x.numpy()), rtol=1e-9)
+    assert all(b1 <= b0 for b0, b1 in zip(best, best[1:]))
+
+
+@_PENDING
+def test_gabo_spd_example_runs_on_device():
+    # examples/gabo_spd.py: ConstrainedTrustRegions + max-eigenvalue constraint through the lock-step driver
+    from oracle import spd as ospd
+    x, y, best = _load_example('gabo_spd').run(dim=2, n_iters=2, num_restarts=5, raw_samples=50, seed=11, verbose=False)
+    assert tuple(x.shape) == (7, 3) and len(best) == 3
+    assert np.linalg.eigvalsh(ospd.vector_to_symmetric_matrix_mandel(x).numpy()).min() > 0
+    np.testing.assert_allclose(y.numpy(), ospd.ackley(x), rtol=1e-8)
+    assert all(b1 <= b0 for b0, b1 in zip(best, best[1:]))
