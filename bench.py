@@ -16,8 +16,13 @@ One "step" = one full Gram build = per-point factorisation of both operands (gab
   extra        the other BASELINE configs measured the same way (sphere Gram, SPD(8) Gram, acquisition optimiser
                candidates/s with the NCCL all-gather of the argmax records, nested projection)
 
-Multi-GPU (torchrun, one rank per GPU): independent Gram builds / independent restarts per rank, no data-path collective
-for the Gram (weak scaling); the acquisition extra ends with ONE all-gather of (value, index, candidate) records.
+Multi-GPU (torchrun, one rank per GPU): ONE Gram K(X1, X2) with X1 = 2048 G points and X2 = 2048 points is
+built in ROW BLOCKS -- rank g owns rows [2048 g, 2048 (g+1)) of X1, X2 is replicated (48 KB), no data-path collective;
+per-GPU work is fixed (weak scaling) and equals configs[1].  The extras carry the other sharded paths: a fixed
+8192 x 8192 SPD(3) Gram and a fixed 32768 x 32768 sphere Gram split in row blocks (strong scaling, with and without the
+all-gather of the blocks), BASELINE configs[3] exactly (SPD(8), 4096 restarts in total sharded by `shard_range`, ONE
+all-gather of (value, global index, candidate) records, winner ASSERTED bit-identical to the single-GPU winner of the
+same starts) and configs[4] (projection, N sharded).
 
 `--impl reference` times the reference's CPU algorithm (oracle port; the reference is pure Python whose kernel classes
 need gpytorch, absent from this image, so it cannot be pip-installed -- DESIGN.md) on the host cores, rank 0 only.
@@ -180,6 +185,71 @@ def cpu_vectorised_step(x1_mandel, x2_mandel, beta):
     return time.perf_counter() - t0
 
 
+def spd_parity_report(x_mandel, beta, compute=0, rows_per_chunk=256):
+    """Checker (oracle used as the CHECKER, never as the thing measured): the GPU Gram of ALL pairs of `x_mandel` against
+    the vectorised oracle restatement of spd_utils_torch.py:87-120 + kernels_spd.py:96-98.  Returns the achieved
+      max_rel_err_d            max |d - d_ref| / d_ref over pairs with d_ref >= 1e-3
+      max_dist_margin          max (|d - d_ref| - (1e-5 d_ref + 1e-6))  -- <= 0 means the SURVEY 8(d) distance bound holds
+      max_rel_err_K            max |K - K_ref| / K_ref over entries with K_ref >= 1e-6   (the flat north_star figure)
+      max_rel_err_K_amplified  max of the same error divided by 1e-5 max(1, 2 beta d^2)  (<= 1: the bound the distance
+                               tolerance implies through exp; the reference's own float32 eigenvalues have this
+                               amplification too).
+    `compute` may be a list of arithmetic types: one report per type, the oracle evaluated once."""
+    import torch
+    from gabotorch_b200 import _lib, ops
+    from oracle import spd as ospd
+    v = torch.as_tensor(x_mandel)
+    n = v.shape[0]
+    modes = list(compute) if isinstance(compute, (list, tuple)) else [compute]
+    got = [(ops.spd_ai_gram(v, v.clone(), kind=_lib.KIND_DIST, compute=c).cpu(),
+            ops.spd_ai_gram(v, v.clone(), beta, _lib.KIND_GAUSS, compute=c).cpu()) for c in modes]
+    mats = ospd.vector_to_symmetric_matrix_mandel(v)
+    reps = [{'pairs_checked': 0, 'max_rel_err_d': 0.0, 'max_dist_margin': -1.0, 'max_rel_err_K': 0.0,
+             'max_rel_err_K_amplified': 0.0} for _ in modes]
+    for lo in range(0, n, rows_per_chunk):
+        dref = ospd.affine_invariant_distance(mats[lo:lo + rows_per_chunk], mats)
+        kref = torch.exp(-dref * dref * beta)
+        big, m = dref >= 1e-3, kref >= 1e-6
+        for rep, (dg, kg) in zip(reps, got):
+            d, k = dg[lo:lo + rows_per_chunk], kg[lo:lo + rows_per_chunk]
+            ed = (d - dref).abs()
+            rep['max_dist_margin'] = max(rep['max_dist_margin'], float((ed - (1e-5 * dref + 1e-6)).max()))
+            if bool(big.any()):
+                rep['max_rel_err_d'] = max(rep['max_rel_err_d'], float((ed[big] / dref[big]).max()))
+            if bool(m.any()):
+                rel = (k - kref).abs()[m] / kref[m]
+                rep['max_rel_err_K'] = max(rep['max_rel_err_K'], float(rel.max()))
+                amp = 1e-5 * torch.clamp(2.0 * beta * dref[m] ** 2, min=1.0)
+                rep['max_rel_err_K_amplified'] = max(rep['max_rel_err_K_amplified'], float((rel / amp).max()))
+            rep['pairs_checked'] += int(dref.numel())
+    return reps if isinstance(compute, (list, tuple)) else reps[0]
+
+
+def cpu_acq_baseline(kind, gp_inputs, x0, T, budget_s=8.0, max_restarts=256):
+    """CPU baseline of the acquisition optimiser: the oracle's per-restart Riemannian CG
+    (pymanopt 0.2.x ConjugateGradient restated, parity UNPINNED) run SERIALLY over a subset of the restarts as the
+    reference does (manifold_optimize.py:207-221), exactly T iterations each; the rate is extrapolated linearly.
+    The cost here is the oracle's closed-form numpy EI -- the reference additionally pays a gpytorch posterior and a
+    torch.autograd graph per cost call, so this number is GENEROUS to the reference."""
+    from oracle import gp as ogp, rcg as orcg
+    xt, y, beta, noise = gp_inputs
+    gp = ogp.make_gp(kind, xt, y, beta=beta, outputscale=1.0, noise=noise)
+    opts = orcg.CGOptions(maxiter=T + 1, mingradnorm=0.0, minstepsize=-1.0)
+    done, iters, t0 = 0, 0, time.perf_counter()
+    with np.errstate(all='ignore'):
+        for x in x0[:max_restarts]:
+            _, _, it, _ = orcg.solve_cg(gp, x, opts)
+            done += 1
+            iters += it
+            if time.perf_counter() - t0 > budget_s:
+                break
+    dt = time.perf_counter() - t0
+    return {'value': iters / dt, 'unit': 'restart-iterations/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d of the restarts x %d CG iterations solved serially by oracle.rcg.solve_cg in %.1f s, '
+                      'extrapolated linearly; closed-form numpy EI (no autograd / gpytorch posterior): generous to '
+                      'the reference; pymanopt semantics restated, unpinned' % (done, T, dt)}
+
+
 def run_reference_arm(args):
     """--impl reference: rank 0 times the reference CPU algorithm on a bounded sample of the headline workload."""
     rank = int(os.environ.get('RANK', '0'))
@@ -309,14 +379,22 @@ class Bench:
         return ctypes.c_void_p(t.data_ptr())
 
     # -- headline: SPD(3) Gram ------------------------------------------------------------------------------
-    def spd_gram_setup(self, n, d, seed):
+    def spd_gram_setup(self, n, d, seed, sharded=False):
+        """Operands of one Gram build.  `sharded`: the GLOBAL point set has n * world points (same seed on every rank);
+        this rank owns rows [n rank, n (rank+1)) as x1, x2 = the first n points, replicated (SURVEY 8e row-block
+        partition; on one GPU x1 and x2 hold the same n points, which is BASELINE configs[1])."""
         torch = self.torch
-        rng = np.random.default_rng(seed + 7919 * self.rank)
-        xm = spd_sample_mandel(rng, n, d)
+        rng = np.random.default_rng(seed)
+        if sharded:
+            allx = spd_sample_mandel(rng, n * self.world, d)
+            xm, x2m = np.ascontiguousarray(allx[n * self.rank:n * (self.rank + 1)]), np.ascontiguousarray(allx[:n])
+        else:
+            xm = spd_sample_mandel(rng, n, d)
+            x2m = xm.copy()
         fs = self.lib.gabo_spd_factor_stride(d)
         st = {
-            'n': n, 'd': d, 'x_host': xm,
-            'x1': torch.from_numpy(xm).to(self.dev), 'x2': torch.from_numpy(xm.copy()).to(self.dev),
+            'n': n, 'd': d, 'x_host': xm, 'x2_host': x2m,
+            'x1': torch.from_numpy(xm).to(self.dev), 'x2': torch.from_numpy(x2m).to(self.dev),
             'fac1': torch.empty(n, fs, dtype=torch.float64, device=self.dev),
             'fac2': torch.empty(n, fs, dtype=torch.float64, device=self.dev),
             'flags': torch.zeros(1, dtype=torch.int32, device=self.dev),
@@ -345,7 +423,7 @@ class Bench:
 
     def headline(self):
         torch, args = self.torch, self.args
-        st = self.spd_gram_setup(N_POINTS, SPD_D, 1234)
+        st = self.spd_gram_setup(N_POINTS, SPD_D, 1234, sharded=True)
         pairs = N_POINTS * N_POINTS
         total_ms = self.time_steps(lambda: self.spd_gram_step(st, BETA_SPD3), args.steps, args.warmup)
         launches = 2 * args.steps                              # spd_factor_kernel (both operands) + spd_ai_gram_kernel per step
@@ -376,7 +454,7 @@ class Bench:
         import gabotorch_b200 as g
         kern = g.SpdAffineInvariantGaussianKernel(beta_min=0.5)
         x1h = torch.from_numpy(st['x_host']).pin_memory()
-        x2h = torch.from_numpy(st['x_host'].copy()).pin_memory()
+        x2h = torch.from_numpy(st['x2_host'].copy()).pin_memory()
         e2e_steps = max(3, min(args.steps, 50))
         with torch.no_grad():
             for _ in range(3):
@@ -437,7 +515,7 @@ class Bench:
         base = g.SphereGaussianKernel(beta_min=1.0)            # D = 6: beta_min 1.0 (hd_gabo_sphere.py:122-123)
         model = g.ManifoldGP(torch.from_numpy(xt), torch.from_numpy(y), g.ScaleKernel(base), noise=noise)
         model.covar_module.outputscale = 1.0
-        acq = g.ExpectedImprovement(model, best_f=float(y.min()))
+        acq = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False)
         gp = acq.device_gp()
         rs = np.random.default_rng(777)
         x0_all = sphere_sample(rs, R * self.world, D)          # starts keyed by GLOBAL restart index
@@ -467,10 +545,13 @@ class Bench:
                                 'stopping rules, n_train=%d, noise=%g' % (D - 1, R, T, n_train, noise),
                     'solves_per_s': self.world * R / (ms * 1e-3), 'executed_iterations_per_s': self.world * R * iters / (ms * 1e-3),
                     'ms_per_step': ms, 'mean_iters': iters}
-        return {'workload': 'acq RCG on EI, S^%d, %d restarts/GPU x %d CG steps, n_train=%d, noise=%g'
-                            % (D - 1, R, T, n_train, noise),
-                'candidates_per_s': self.world * R * T / (ms * 1e-3), 'ms_per_step': ms, 'mean_iters': iters,
-                'collective': 'one all_gather of (value, gidx, candidate) per solve' if self.world > 1 else 'none (1 GPU)'}
+        out = {'workload': 'acq RCG on EI, S^%d, %d restarts/GPU x %d CG steps, n_train=%d, noise=%g'
+                           % (D - 1, R, T, n_train, noise),
+               'candidates_per_s': self.world * R * T / (ms * 1e-3), 'ms_per_step': ms, 'mean_iters': iters,
+               'collective': 'one all_gather of (value, gidx, candidate) per solve' if self.world > 1 else 'none (1 GPU)'}
+        if self.rank == 0 and self.world == 1 and not self.args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_acq_baseline('sphere', (xt, y, float(base.beta.detach()), noise), x0_all, T)
+        return out
 
     def extra_ei_screen(self, R=1 << 20, D=6, n_train=32, noise=1e-2, steps=5):
         """A2 / A4: raw-sample screening -- EI at R random points of S^5 in one launch (manifold_optimize.py:297-309)."""
@@ -482,7 +563,7 @@ class Bench:
         base = g.SphereGaussianKernel(beta_min=1.0)
         model = g.ManifoldGP(torch.from_numpy(xt), torch.from_numpy(y), g.ScaleKernel(base), noise=noise)
         model.covar_module.outputscale = 1.0
-        gp = g.ExpectedImprovement(model, best_f=float(y.min())).device_gp()
+        gp = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False).device_gp()
         gen = torch.Generator(device=self.dev)
         gen.manual_seed(17 + self.rank)
         x = torch.randn(R, D, dtype=torch.float64, device=self.dev, generator=gen)
@@ -491,8 +572,11 @@ class Bench:
         return {'workload': 'EI screening of %d raw samples on S^%d, n_train=%d (one launch)' % (R, D - 1, n_train),
                 'ei_evals_per_s': self.world * R / (ms * 1e-3), 'ms_per_step': ms}
 
-    def extra_acq_spd(self, R, T, d=8, n_train=32, noise=1e-2, steps=3):
-        """BASELINE configs[3] per-GPU shard: Ackley on SPD(8), R restarts x T CG steps per rank + the record all-gather."""
+    def extra_acq_spd(self, R_total, T, d=8, n_train=32, noise=1e-2, steps=3, check=True):
+        """BASELINE configs[3]: Ackley on SPD(8), R_total restarts IN TOTAL sharded over the ranks by `shard_range`
+        (global restart index), T CG steps each, ONE all-gather of (value, global index, candidate) records and the
+        same deterministic argmax on every rank.  `check`: rank 0 also solves ALL R_total starts alone (outside the
+        timed region) and the gathered winner must be bit-identical."""
         import gabotorch_b200 as g
         from gabotorch_b200 import manifold_optimization as mo
         torch, ops = self.torch, self.ops
@@ -508,13 +592,13 @@ class Bench:
         base = g.SpdAffineInvariantGaussianKernel(beta_min=0.22)   # d = 8: nearest tabulated beta_min (gabo_spd.py:151-162)
         model = g.ManifoldGP(torch.from_numpy(xm), torch.from_numpy(y), g.ScaleKernel(base), noise=noise)
         model.covar_module.outputscale = 1.0
-        acq = g.ExpectedImprovement(model, best_f=float(y.min()))
+        acq = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False)
         gp = acq.device_gp()
         rs = np.random.default_rng(778)
-        x0_all = spd_sample_mandel(rs, R * self.world, d)      # starts keyed by GLOBAL restart index
-        lo = self.rank * R
-        x0 = ops.mandel_unpack(torch.from_numpy(x0_all[lo:lo + R]).to(self.dev))
-        gidx = torch.arange(lo, lo + R, device=self.dev)
+        x0_all = spd_sample_mandel(rs, R_total, d)             # starts keyed by GLOBAL restart index
+        lo, hi = mo.shard_range(R_total, self.rank, self.world)
+        x0 = ops.mandel_unpack(torch.from_numpy(x0_all[lo:hi]).to(self.dev))
+        gidx = torch.arange(lo, hi, device=self.dev)
         res = {}
 
         def step():
@@ -522,14 +606,96 @@ class Bench:
             slot, best = ops.argmax_records(val, gidx)
             if self.world > 1:
                 v_, gi, c = mo.allgather_records(best.reshape(()), gidx[slot].reshape(()), cand[slot].reshape(-1))
-                ops.argmax_records(v_, gi)
+                win, bv = ops.argmax_records(v_, gi)
+                res['winner'] = (gi[win].reshape(()), bv.reshape(()), c[win].reshape(-1))
+            else:
+                res['winner'] = (gidx[slot].reshape(()), best.reshape(()), cand[slot].reshape(-1))
             res['iters'] = iters
-        ms = self.time_steps(step, steps, 1, flush=False) / steps
-        return {'workload': 'acq RCG on EI, SPD(%d), %d restarts/GPU x %d CG steps, n_train=%d, noise=%g'
-                            % (d, R, T, n_train, noise),
-                'candidates_per_s': self.world * R * T / (ms * 1e-3), 'ms_per_step': ms,
-                'mean_iters': res['iters'].double().mean().item(),
-                'collective': 'one all_gather of (value, gidx, candidate) per solve' if self.world > 1 else 'none (1 GPU)'}
+        ms = self.time_steps(step, steps, 3, flush=False) / steps
+        out = {'workload': 'acq RCG on EI, SPD(%d), %d restarts in total (%d per GPU, shard_range) x %d CG steps, '
+                           'n_train=%d, noise=%g' % (d, R_total, hi - lo, T, n_train, noise),
+               'candidates_per_s': R_total * T / (ms * 1e-3), 'ms_per_step': ms,
+               'mean_iters': res['iters'].double().mean().item(),
+               'collective': 'one all_gather of (value, gidx, candidate) per solve' if self.world > 1 else 'none (1 GPU)'}
+        wg, wv, wc = (t.cpu() for t in res['winner'])
+        out['winner_gidx'], out['winner_value'] = int(wg), float(wv)
+        if check and self.world > 1:
+            # every rank must hold the same winner; rank 0 re-solves all the starts alone and compares bit for bit
+            box = torch.stack([wg.double().reshape(()), wv.reshape(())]).to(self.dev)
+            gathered = [torch.empty_like(box) for _ in range(self.world)]
+            self.dist.all_gather(gathered, box)
+            same_everywhere = all(torch.equal(t, gathered[0]) for t in gathered)
+            ok = None
+            if self.rank == 0:
+                xa = ops.mandel_unpack(torch.from_numpy(x0_all).to(self.dev))
+                ca, va, _, _ = ops.acq_rcg(gp, xa, maxiter=T + 1, mingradnorm=0.0, minstepsize=-1.0)
+                s1, b1 = ops.argmax_records(va, torch.arange(R_total, device=self.dev))
+                ok = bool(int(s1) == int(wg) and float(b1) == float(wv)
+                          and torch.equal(ca[int(s1)].reshape(-1).cpu(), wc))
+                out['single_gpu_winner_gidx'], out['single_gpu_winner_value'] = int(s1), float(b1)
+            out['winner_identical_on_every_rank'] = bool(same_everywhere)
+            out['winner_matches_single_gpu'] = ok
+            if self.rank == 0:
+                assert same_everywhere and ok, 'sharded argmax differs from the single-GPU argmax: %r' % (out,)
+        if self.rank == 0 and self.world == 1 and not self.args.no_cpu_baseline:
+            x0m = ops.mandel_unpack(torch.from_numpy(x0_all[:64])).cpu().numpy()
+            out['cpu_baseline'] = cpu_acq_baseline('spd', (mats, y, float(base.beta.detach()), noise), x0m, T,
+                                                   max_restarts=64)
+        return out
+
+    def extra_spd_strong(self, n=8192, d=3, steps=5):
+        """ONE fixed n x n SPD(d) Gram split in row blocks over the ranks (strong scaling, no collective)."""
+        torch, lb, p = self.torch, self._lib, self.p
+        from gabotorch_b200 import manifold_optimization as mo
+        xm = spd_sample_mandel(np.random.default_rng(4321 + d), n, d)
+        lo, hi = mo.shard_range(n, self.rank, self.world)
+        rows = hi - lo
+        fs = self.lib.gabo_spd_factor_stride(d)
+        x1 = torch.from_numpy(np.ascontiguousarray(xm[lo:hi])).to(self.dev)
+        x2 = torch.from_numpy(xm).to(self.dev)
+        f1 = torch.empty(rows, fs, dtype=torch.float64, device=self.dev)
+        f2 = torch.empty(n, fs, dtype=torch.float64, device=self.dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        out = torch.empty(rows, n, dtype=torch.float64, device=self.dev)
+        beta = BETA_SPD3
+
+        def step():
+            s = lb.stream_ptr()
+            lb.check(self.lib.gabo_spd_factor2(p(x1), rows, p(x2), n, d, 1, p(f1), p(f2), p(flags), s), 'gabo_spd_factor2')
+            lb.check(self.lib.gabo_spd_ai_gram(p(f1), rows, p(f2), n, d, beta, lb.KIND_GAUSS, lb.GABO_F32, 0, p(out),
+                                               lb.GABO_F64, n, s), 'gabo_spd_ai_gram')
+        ms = self.time_steps(step, steps, 3) / steps
+        return {'workload': 'ONE SPD(%d) Gram N=%d fp64 out, row blocks of %d rows per GPU (strong scaling, no collective)'
+                            % (d, n, rows), 'pairs_per_s': n * n / (ms * 1e-3), 'ms_per_step': ms, 'scaling': 'strong'}
+
+    def extra_sphere_strong(self, n=32768, D=3, steps=5, gather=False):
+        """ONE fixed n x n sphere Gram (fp64 out, the API's dtype) split in row blocks; `gather`: followed by the
+        all-gather of the blocks so that every rank holds the whole matrix (report with and without)."""
+        torch, lb, p = self.torch, self._lib, self.p
+        from gabotorch_b200 import manifold_optimization as mo
+        x = sphere_sample(np.random.default_rng(99 + D), n, D)
+        lo, hi = mo.shard_range(n, self.rank, self.world)
+        if gather and n % self.world:
+            return {'workload': 'sphere Gram all-gather', 'skipped': 'n not divisible by the world size'}
+        rows = hi - lo
+        x1 = torch.from_numpy(np.ascontiguousarray(x[lo:hi])).to(self.dev)
+        x2 = torch.from_numpy(x).to(self.dev)
+        beta = 6.5 + math.log(2.0)
+        full = torch.empty(n, n, dtype=torch.float64, device=self.dev) if gather and self.world > 1 else None
+        out = full[lo:hi] if full is not None else torch.empty(rows, n, dtype=torch.float64, device=self.dev)
+
+        def step():
+            lb.check(self.lib.gabo_sphere_gram(p(x1), rows, p(x2), n, D, beta, lb.KIND_GAUSS, p(out), lb.GABO_F64, n,
+                                               lb.stream_ptr()), 'gabo_sphere_gram')
+            if full is not None:
+                self.dist.all_gather_into_tensor(full, out)
+        ms = self.time_steps(step, steps, 3) / steps
+        nbytes = n * n * 8 + 2 * n * D * 8
+        return {'workload': 'ONE sphere Gram S^%d N=%d fp64 out, row blocks of %d rows per GPU (strong scaling)%s'
+                            % (D - 1, n, rows, ' + all_gather of the blocks (every rank ends with the full matrix)'
+                               if full is not None else ', no collective'),
+                'pairs_per_s': n * n / (ms * 1e-3), 'ms_per_step': ms, 'scaling': 'strong',
+                'aggregate_write_GBps': nbytes / (ms * 1e-3) / 1e9}
 
     def extra_projection(self, n, D=20, d=5, steps=10):
         torch, ops = self.torch, self.ops
@@ -564,7 +730,7 @@ class Bench:
         model = g.ManifoldGP(torch.from_numpy(xt), torch.from_numpy(y),
                              g.ScaleKernel(g.SphereGaussianKernel(beta_min=1.0)), noise=noise)
         model.covar_module.outputscale = 1.0
-        gp = g.ExpectedImprovement(model, best_f=float(y.min())).device_gp()
+        gp = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False).device_gp()
         x0 = torch.from_numpy(sphere_sample(np.random.default_rng(777 + self.rank), R, D)).to(self.dev)
         res = {}
 
@@ -646,7 +812,7 @@ class Bench:
         model = g.ManifoldGP(torch.from_numpy(xv), torch.from_numpy(y),
                              g.ScaleKernel(g.SpdAffineInvariantGaussianKernel(beta_min=0.5)), noise=noise)
         model.covar_module.outputscale = 1.0
-        gp = g.ExpectedImprovement(model, best_f=float(y.min()), compute='f64').device_gp()
+        gp = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False, compute='f64').device_gp()
         x0 = ops.mandel_unpack(torch.from_numpy(spd_sample_mandel(np.random.default_rng(32 + self.rank), R, d,
                                                                   min_eig=0.5, max_eig=2.5)))
         kw = dict(maxiter=100)
@@ -701,7 +867,7 @@ class Bench:
         args = self.args
         if args.only in ('acq', 'acq_spd'):      # developer switch: just one acquisition extra
             e = (self.extra_acq_sphere(R=args.acq_restarts, T=200) if args.only == 'acq'
-                 else self.extra_acq_spd(R=args.acq_restarts, T=args.acq_steps, d=args.acq_dim))
+                 else self.extra_acq_spd(args.acq_restarts, T=args.acq_steps, d=args.acq_dim))
             self.clocks.stop()
             if self.rank == 0:
                 emit(e)
@@ -712,32 +878,47 @@ class Bench:
             if self.rank == 0:
                 emit({'extra': out})
             return 0
+        if args.only == 'scale':                  # developer switch: the sharded (multi-GPU) extras only
+            out = [self.guarded(self.extra_acq_spd, 4096, 200), self.guarded(self.extra_spd_strong),
+                   self.guarded(self.extra_sphere_strong), self.guarded(self.extra_sphere_strong, gather=True),
+                   self.guarded(self.extra_projection, 1 << 20)]
+            self.clocks.stop()
+            if self.rank == 0:
+                emit({'n_gpus': self.world, 'extra': out})
+            return 0
         head = self.headline()
         extras = []
         if not args.no_extras:
             torch = self.torch
-            extras.append(self.extra_acq_sphere(R=1024, T=200))
-            extras.append(self.extra_acq_sphere(R=1024, T=200, forced=False))
-            extras.append(self.extra_acq_spd(R=512, T=200))
-            extras.append(self.extra_ei_screen())
+            # the sharded paths of SURVEY 8(e), at every N (so that the 1/2/4/8 runs line up):
+            extras.append(self.extra_acq_spd(4096, 200))                      # BASELINE configs[3], winner asserted
+            extras.append(self.extra_acq_sphere(R=1024, T=200))              # configs[2] per GPU + the record all-gather
+            extras.append(self.guarded(self.extra_spd_strong))
+            extras.append(self.guarded(self.extra_sphere_strong))
+            if self.world > 1:
+                extras.append(self.guarded(self.extra_sphere_strong, gather=True))
+            extras.append(self.extra_projection(1 << 20))                     # configs[4]: N sharded, 2^20 per GPU
             if self.world == 1:
+                extras.append(self.extra_acq_sphere(R=1024, T=200, forced=False))
+                extras.append(self.extra_ei_screen())
                 extras.append(self.extra_spd(N_POINTS, SPD_D, BETA_SPD3, symmetric=True))
-                extras.append(self.extra_spd(8192, 3, BETA_SPD3, symmetric=False, steps=5))
                 extras.append(self.extra_spd(2048, 8, 0.22 + math.log(2.0), symmetric=False, steps=5))
                 extras.append(self.extra_sphere(256, 3, 6.5 + math.log(2.0), torch.float64, steps=20))
                 extras.append(self.extra_sphere(32768, 3, 6.5 + math.log(2.0), torch.float32, steps=5))
                 extras.append(self.extra_sphere(32768, 3, 6.5 + math.log(2.0), torch.float64, steps=5))   # the API's dtype
                 extras.append(self.extra_sphere(32768, 9, 0.6 + math.log(2.0), torch.float32, steps=5))
                 extras.append(self.extra_sphere(32768, 9, 0.6 + math.log(2.0), torch.float64, steps=5))
-                extras.append(self.extra_projection(1 << 20))
                 extras.append(self.guarded(self.extra_acq_rtr))
                 extras.append(self.guarded(self.extra_gp_fit))
                 extras.append(self.guarded(self.extra_reconstruct))
                 extras.append(self.guarded(self.extra_acq_tr_spd, False))
                 extras.append(self.guarded(self.extra_acq_tr_spd, True))
-        cpu = None
+        cpu, parity = None, None
         if self.rank == 0 and self.world == 1 and not args.no_cpu_baseline:
             cpu = self.cpu_baseline()
+            # achieved accuracy of the timed configuration, every pair against the oracle (checker, not timed)
+            xh = spd_sample_mandel(np.random.default_rng(1234), N_POINTS, SPD_D)
+            parity = self.guarded(spd_parity_report, xh, BETA_SPD3, self._lib.GABO_F32)
         self.clocks.stop()
         clocks = self.clocks.summary()
         if self.rank == 0:
@@ -749,8 +930,11 @@ class Bench:
                            'output': 'float64 N x N', 'pairs_per_step_per_gpu': N_POINTS * N_POINTS,
                            'timing': 'CUDA events per step on the launching stream; L2 flushed (256 MB write) between '
                                      'steps; max over ranks',
-                           'sharding': 'independent Gram builds per rank, no collective',
-                           'arithmetic': 'fp64 per-point Cholesky, fp32 per-pair Jacobi, fp64 exp argument'},
+                           'sharding': 'row blocks of ONE (%d x %d) Gram: rank g builds rows [%d g, %d (g+1)) of x1 against '
+                                       'the replicated x2, no data-path collective (weak scaling: %d x %d pairs per GPU)'
+                                       % (N_POINTS * self.world, N_POINTS, N_POINTS, N_POINTS, N_POINTS, N_POINTS),
+                           'arithmetic': 'fp64 per-point Cholesky, fp32 per-pair Jacobi, fp64 exp argument',
+                           'parity_vs_oracle_all_pairs': parity},
                 'roofline': head['roofline'], 'compute_roofline': head['compute'], 'cpu_baseline': cpu,
                 'e2e': head['e2e'], 'gpu_launches': head['launches'], 'clocks': clocks, 'extra': extras,
             }
@@ -796,7 +980,7 @@ def main():
     ap.add_argument('--cpu-rows', type=int, default=640, help='rows of the N=2048 Gram in the cpu_baseline sample')
     ap.add_argument('--ref-rows', type=int, default=16, help='rows per step of the reference arm')
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
+    args.warmup = max(args.warmup, 3)          # both arms: at least 3 warm-up steps
     if args.impl == 'reference':
         return run_reference_arm(args)
     world = int(os.environ.get('WORLD_SIZE', '1'))

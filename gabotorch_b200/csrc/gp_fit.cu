@@ -172,13 +172,18 @@ using namespace gabo;
 
 static unsigned gp_threads(int64_t n) { return n <= 32 ? 64u : (n <= 64 ? 128u : static_cast<unsigned>(kGpThreads)); }
 
-static void configure_smem() {
-    static bool configured = false;
-    if (configured) return;
-    const int bytes = static_cast<int>(sizeof(double) * (kMaxGpTrain * (kMaxGpTrain + 1) + 2 * kMaxGpTrain + 8));
-    cudaFuncSetAttribute(gp_mll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(gp_mll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    configured = true;
+// Function attributes are per device / context: set on every launch that needs more than the 48 KB default (as the
+// acquisition launchers do); returns false (error recorded) when the driver refuses.
+template <bool FACTOR_ONLY>
+static bool configure_smem(size_t smem) {
+    if (smem <= 48u * 1024u) return true;
+    const cudaError_t e = cudaFuncSetAttribute(gp_mll_kernel<FACTOR_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem));
+    if (e != cudaSuccess) {
+        set_error("gp_mll_kernel: cudaFuncSetAttribute(%zu bytes of shared memory): %s", smem, cudaGetErrorString(e));
+        return false;
+    }
+    return true;
 }
 
 extern "C" int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const double* theta, int64_t batch,
@@ -190,7 +195,7 @@ extern "C" int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const
     if (batch == 0) return GABO_OK;
     GABO_REQUIRE(dmat && y && theta && out_ll && flags, GABO_E_ARG, "gabo_gp_mll: null pointer");
     const size_t smem = sizeof(double) * (static_cast<size_t>(n) * (n + 1) + 2 * n + kGpThreads / 32);
-    configure_smem();
+    if (!configure_smem<false>(smem)) return GABO_E_CUDA;
     gp_mll_kernel<false><<<static_cast<unsigned>(batch), gp_threads(n), smem, static_cast<cudaStream_t>(stream)>>>(
         dmat, static_cast<int>(n), y, theta, make_double4(0, 0, 0, 0), out_ll, out_grad, out_alpha, out_kinv, flags);
     return check_launch("gp_mll_kernel");
@@ -202,7 +207,7 @@ extern "C" int gabo_gp_factor(const double* kmat, int64_t n, const double* y, do
                  static_cast<long long>(n), kMaxGpTrain);
     GABO_REQUIRE(kmat && y && out_alpha && out_kinv && flag, GABO_E_ARG, "gabo_gp_factor: null pointer");
     const size_t smem = sizeof(double) * (static_cast<size_t>(n) * (n + 1) + 2 * n + kGpThreads / 32);
-    configure_smem();
+    if (!configure_smem<true>(smem)) return GABO_E_CUDA;
     gp_mll_kernel<true><<<1, gp_threads(n), smem, static_cast<cudaStream_t>(stream)>>>(
         kmat, static_cast<int>(n), y, nullptr, make_double4(0.0, outputscale, noise, mean), nullptr, nullptr, out_alpha,
         out_kinv, flag);

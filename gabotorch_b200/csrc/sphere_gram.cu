@@ -448,7 +448,10 @@ extern "C" int gabo_sphere_gram(const double* x1, int64_t n1, const double* x2, 
     GABO_REQUIRE(kind >= GABO_KIND_GAUSS && kind <= GABO_KIND_DIST, GABO_E_ARG, "gabo_sphere_gram: bad kind %d", kind);
     GABO_REQUIRE(out_dtype == GABO_F32 || out_dtype == GABO_F64, GABO_E_ARG, "gabo_sphere_gram: bad out_dtype");
     GABO_REQUIRE(ld_out >= n2, GABO_E_ARG, "gabo_sphere_gram: ld_out < n2");
-    GABO_REQUIRE(aligned16(x1) && aligned16(x2), GABO_E_ALIGN, "gabo_sphere_gram: inputs must be 16-byte aligned");
+    // 8-byte (element) alignment is enough: the TMA bulk copy of an x1 tile is used only when the tile is 16-byte aligned
+    // (cooperative loads otherwise) and x2 is read with scalar loads, so batch slices b*N*D with odd N*D are accepted
+    GABO_REQUIRE(((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 7u) == 0, GABO_E_ALIGN,
+                 "gabo_sphere_gram: inputs must be 8-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dim == 1) dim = 1;  // handled by the generic kernel
     if (out_dtype == GABO_F32) return launch_kind<float>(x1, n1, x2, n2, dim, param, kind, out, ld_out, s);

@@ -570,7 +570,11 @@ class ExpectedImprovement:
     device by ``gabo_ei_eval``.  ``__call__`` takes ``b x 1 x dvec`` (or ``b x dvec``) points in the GP's input
     representation (unit vectors; Mandel vectors for SPD) and returns ``b`` values."""
 
-    def __init__(self, model, best_f, maximize=False, compute='f32'):
+    nonnegative = True
+
+    def __init__(self, model, best_f, maximize=True, compute='f32'):
+        # botorch's default is maximize=True; every reference call site passes maximize=False explicitly
+        # (gabo_sphere.py:165, gabo_spd.py:197, hd_gabo_spd.py:259)
         self.model = model
         self.best_f = float(best_f)
         self.maximize = bool(maximize)
@@ -652,6 +656,40 @@ def initialize_q_batch_nonneg(X, Y, n, eta=1.0, alpha=1e-4, generator=None):
     return X[idcs]
 
 
+def initialize_q_batch(X, Y, n, eta=1.0, generator=None):
+    """botorch.optim.initializers.initialize_q_batch (the branch manifold_optimize.py:277-281 takes for acquisition
+    functions that are not known to be non-negative): keep the best point, sample the others with weights
+    exp(eta Z), Z the standardised acquisition values (eta halved until the weights are finite)."""
+    n_samples = X.shape[0]
+    if n > n_samples:
+        raise RuntimeError('n (%d) cannot be larger than the number of provided samples (%d)' % (n, n_samples))
+    if n == n_samples:
+        return X
+    Ystd = Y.std()
+    if bool(Ystd == 0):
+        warnings.warn('All acquisition values for raw samples points are the same. Choosing initial conditions at '
+                      'random.', BadInitialCandidatesWarning)
+        return X[torch.randperm(n_samples, device=X.device, generator=generator)][:n]
+    max_val, max_idx = torch.max(Y, dim=0)
+    etaZ = eta * (Y - Y.mean()) / Ystd
+    weights = torch.exp(etaZ)
+    while bool(torch.isinf(weights).any()):
+        etaZ = etaZ * 0.5
+        weights = torch.exp(etaZ)
+    idcs = torch.multinomial(weights, n, generator=generator)
+    if not bool((idcs == max_idx).any()):
+        idcs[-1] = max_idx
+    return X[idcs]
+
+
+def is_nonnegative(acq_function):
+    """botorch.acquisition.utils.is_nonnegative: True for the acquisition classes known to be non-negative (of the ones
+    this package evaluates: ExpectedImprovement); anything else is treated as signed."""
+    return bool(getattr(acq_function, 'nonnegative', False)) or type(acq_function).__name__ in (
+        'ExpectedImprovement', 'NoisyExpectedImprovement', 'ProbabilityOfImprovement', 'qExpectedImprovement',
+        'qNoisyExpectedImprovement', 'qProbabilityOfImprovement')
+
+
 def _rand_points(manifold, n, generator):
     if hasattr(manifold, 'rand_batch'):
         return manifold.rand_batch(n, generator=generator)
@@ -702,11 +740,22 @@ def gen_batch_initial_conditions_manifold(acq_function, manifold, bounds, q, num
     if seed is not None:
         gen = torch.Generator(device=ops.device())
         gen.manual_seed(int(seed))
+    batch_limit = options.get('batch_limit')
     init_kwargs = {}
     if 'eta' in options:
         init_kwargs['eta'] = options.get('eta')
-    if 'alpha' in options:
-        init_kwargs['alpha'] = options.get('alpha')
+    if options.get('nonnegative') or is_nonnegative(acq_function):       # manifold_optimize.py:277-281
+        init_func = initialize_q_batch_nonneg
+        if 'alpha' in options:
+            init_kwargs['alpha'] = options.get('alpha')
+    else:
+        init_func = initialize_q_batch
+
+    def acq_chunked(X):                                                   # manifold_optimize.py:297-307
+        step = X.shape[0] if batch_limit is None else max(1, int(batch_limit))
+        with torch.no_grad():
+            parts = [ops.to_dev64(acq_function(X[lo:lo + step])).reshape(-1) for lo in range(0, X.shape[0], step)]
+        return parts[0] if len(parts) == 1 else torch.cat(parts)
     factor, max_factor = 1, 5
     batch_initial_conditions = None
     while factor < max_factor:
@@ -717,12 +766,10 @@ def gen_batch_initial_conditions_manifold(acq_function, manifold, bounds, q, num
             if post_processing_manifold is not None:
                 X_rnd = post_processing_manifold(X_rnd)
             if distributed:
-                Y_rnd = sharded_acq_values(acq_function, X_rnd)
+                Y_rnd = sharded_acq_values(acq_chunked, X_rnd)
             else:
-                with torch.no_grad():
-                    Y_rnd = ops.to_dev64(acq_function(X_rnd)).reshape(-1)
-            batch_initial_conditions = initialize_q_batch_nonneg(X_rnd, Y_rnd, num_restarts, generator=gen,
-                                                                 **init_kwargs)
+                Y_rnd = acq_chunked(X_rnd)
+            batch_initial_conditions = init_func(X_rnd, Y_rnd, num_restarts, generator=gen, **init_kwargs)
             if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):
                 return batch_initial_conditions
             factor += 1
@@ -892,15 +939,23 @@ def joint_optimize_manifold(acq_function, manifold, solver, q, num_restarts, raw
         dist.broadcast(ics, src=0)
         lo, hi = shard_range(num_restarts, dist.get_rank(), dist.get_world_size())
     sub = {k: v for k, v in options.items() if k not in ('batch_limit', 'nonnegative', 'distributed', 'seed')}
-    cands, vals = gen_candidates_manifold(initial_conditions=ics[lo:hi], acquisition_function=acq_function,
-                                          manifold=manifold, solver=solver,
-                                          pre_processing_manifold=pre_processing_manifold,
-                                          post_processing_manifold=post_processing_manifold,
-                                          lower_bounds=None if bounds is None else bounds[0],
-                                          upper_bounds=None if bounds is None else bounds[1], options=sub,
-                                          inequality_constraints=inequality_constraints,
-                                          equality_constraints=equality_constraints, approx_hessian=approx_hessian,
-                                          solver_init_conds=solver_init_conds)
+    # manifold_optimize.py:95-116: restarts are handed to gen_candidates_manifold in chunks of `batch_limit` (default: all
+    # of them -- one launch); the chunks are independent, so the result does not depend on the chunking
+    batch_limit = max(1, int(options.get('batch_limit', num_restarts) or num_restarts))
+    cl, vl = [], []
+    for start in range(lo, hi, batch_limit):
+        c_, v_ = gen_candidates_manifold(initial_conditions=ics[start:min(start + batch_limit, hi)],
+                                         acquisition_function=acq_function, manifold=manifold, solver=solver,
+                                         pre_processing_manifold=pre_processing_manifold,
+                                         post_processing_manifold=post_processing_manifold,
+                                         lower_bounds=None if bounds is None else bounds[0],
+                                         upper_bounds=None if bounds is None else bounds[1], options=sub,
+                                         inequality_constraints=inequality_constraints,
+                                         equality_constraints=equality_constraints, approx_hessian=approx_hessian,
+                                         solver_init_conds=solver_init_conds)
+        cl.append(c_)
+        vl.append(v_)
+    cands, vals = (cl[0], vl[0]) if len(cl) == 1 else (torch.cat(cl), torch.cat(vl))
     if not distributed:
         return get_best_candidates(cands, vals)
     gidx = torch.arange(lo, hi, device=vals.device)

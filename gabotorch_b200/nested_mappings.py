@@ -33,16 +33,25 @@ def projection_mandel(x_mandel, projection_matrix):
     return NestedSpdProjection(projection_matrix).mandel(x_mandel)
 
 
-def projection_from_spd_to_nested_spd(x_spd, projection_matrix):
-    """Y = W^T X W for (..., D, D) matrices -> (..., d, d), dtype / device of ``x_spd`` (nested_spd_utils.py:13-48)."""
+def projection_from_spd_to_nested_spd(x_spd, projection_matrix, tensor_cores=None):
+    """Y = W^T X W for (..., D, D) matrices -> (..., d, d), dtype / device of ``x_spd`` (nested_spd_utils.py:13-48).
+
+    float64 inputs (the reference's dtype) take the fp64 contraction ``gabo_nested_spd_project_f64`` -- the reference
+    computes an exact fp64 ``bmm`` (:44), and the nested kernel classes use the same entry, so the function and the
+    kernels agree to rounding.  float32 inputs (or ``tensor_cores=True``) take the 3xTF32 tensor-core contraction
+    ``gabo_nested_spd_project`` (about 1e-6 relative): that is the path for screening millions of raw samples."""
     x = torch.as_tensor(x_spd)
-    proj = NestedSpdProjection(projection_matrix)
     single = x.dim() == 2
     if single:
         x = x[None]
+    if tensor_cores is None:
+        tensor_cores = x.dtype == torch.float32
     xm = ops.mandel_pack(x)                      # fp64 Mandel vectors on the device
-    ym = proj.mandel(xm.to(torch.float32))       # tensor-core contraction, fp32
-    y = ops.mandel_unpack(ym.to(torch.float64))
+    if tensor_cores:
+        ym = NestedSpdProjection(projection_matrix).mandel(xm.to(torch.float32)).to(torch.float64)
+    else:
+        ym = ops.nested_spd_project_f64(xm, projection_matrix)
+    y = ops.mandel_unpack(ym)
     if single:
         y = y[0]
     y = y.to(x.dtype)

@@ -139,7 +139,7 @@ def test_joint_optimize_manifold_spd_with_mandel_processing():
     base = g.SpdAffineInvariantGaussianKernel(beta_min=0.5)
     model = g.ManifoldGP(xv, torch.from_numpy(y), g.ScaleKernel(base), noise=1e-2)
     model.covar_module.outputscale = 1.0
-    acq = g.ExpectedImprovement(model, best_f=float(y.min()))
+    acq = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False)
     man = g.PositiveDefinite(d)
     man.min_eig, man.max_eig = 0.001, 5.0
     new_x = g.joint_optimize_manifold(acq, man, g.ConjugateGradient(maxiter=50), q=1, num_restarts=16,

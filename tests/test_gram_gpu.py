@@ -84,6 +84,34 @@ def test_sphere_gram_golden_rect_and_edge_sizes(golden):
     check_dist(ops.sphere_gram(xt, b, kind=_lib.KIND_DIST).cpu(), golden['s3_rect_d'])
 
 
+def test_sphere_gram_batched_odd_sizes_and_offset_views():
+    # the reference accepts b1 x ... x N x D (sphere_utils_torch.py:12-55): batch slices of a contiguous buffer sit at
+    # b*N*D*8 bytes, which is only 8-byte aligned when N*D is odd; so is a row-offset view x[1:] with odd D
+    rng = np.random.default_rng(17)
+    xb = osph.rand(rng, 10, 3).reshape(2, 5, 3)                  # N*D = 15
+    yb = osph.rand(rng, 14, 3).reshape(2, 7, 3)                  # N*D = 21
+    got = ops.sphere_gram(xb, yb, kind=_lib.KIND_DIST).cpu()
+    assert tuple(got.shape) == (2, 5, 7)
+    for b in range(2):
+        check_dist(got[b], osph.sphere_distance(xb[b], yb[b]))
+    # gpytorch's posterior shape: b x 1 x D test points against N x D training points
+    xt, tr = osph.rand(rng, 6, 3).reshape(6, 1, 3), osph.rand(rng, 9, 3)
+    kb = ops.sphere_gram(xt, tr, 2.0, _lib.KIND_GAUSS).cpu()
+    assert tuple(kb.shape) == (6, 1, 9)
+    check_kernel(kb[:, 0], osph.sphere_gaussian_kernel(xt[:, 0], tr, 2.0))
+    # contiguous device views that start 8 (not 16) bytes into the allocation, both operands, both output dtypes
+    x = torch.from_numpy(osph.rand(rng, 301, 3)).cuda()
+    y = torch.from_numpy(osph.rand(rng, 1031, 5)[:, :3].copy())
+    y = (y / y.norm(dim=-1, keepdim=True)).cuda()
+    for od in (torch.float32, torch.float64):
+        full = ops.sphere_gram(x, y, 1.3, _lib.KIND_GAUSS, out_dtype=od)
+        view = ops.sphere_gram(x[1:], y[1:], 1.3, _lib.KIND_GAUSS, out_dtype=od)
+        assert x[1:].data_ptr() % 16 == 8
+        assert torch.equal(view, full[1:, 1:])
+    dd = ops.sphere_gram(xb, xb.copy(), kind=_lib.KIND_DIST, diag=True).cpu()
+    assert tuple(dd.shape) == (2, 5, 1) and float(dd.max()) < 1e-6
+
+
 def test_sphere_gram_non_unit_inputs_follow_the_reference_formula():
     # the reference never normalises: it clamps the raw inner product (sphere_utils_torch.py:53)
     rng = np.random.default_rng(9)
@@ -176,6 +204,24 @@ def test_spd_gram_full_size_properties():
     check_dist(d_full[:96, 1000:1100].cpu(), ospd.affine_invariant_distance(X[:96], X[1000:1100]))
     lam_min = torch.linalg.eigvalsh(k[:512, :512].double()).min()
     assert float(lam_min) > -5e-7                              # PD at beta >= beta_min (spd_gaussian_kernel_parameters.py:50-53)
+
+
+@pytest.mark.parametrize('d,beta_min', [(3, 0.5), (8, 0.22)])
+def test_spd_gram_full_matrix_parity_at_the_benchmarked_size(d, beta_min):
+    # BASELINE configs[1] (SPD(3), N = 2048: the configuration bench.py times) and the SPD(8) extra: EVERY one of the
+    # 4.2 M pairs against the vectorised oracle (faithful to spd_utils_torch.py:87-120 incl. the float32 eigenvalues).
+    # The achieved errors are printed (pytest -s) and returned to bench.py / smoke() through the same helper.
+    import bench
+    N, beta = 2048, beta_min + math.log(2.0)
+    v = bench.spd_sample_mandel(np.random.default_rng(1234), N, d)       # bench.py's input law and seed
+    rep, rep64 = bench.spd_parity_report(v, beta, compute=[_lib.GABO_F32, _lib.GABO_F64])
+    print('SPD(%d) N=%d fp32 Jacobi: %s' % (d, N, rep))
+    print('SPD(%d) N=%d fp64 Jacobi: %s' % (d, N, rep64))
+    assert rep['pairs_checked'] == N * N
+    assert rep['max_dist_margin'] <= 0.0                       # |d - d_ref| <= 1e-5 d_ref + 1e-6 on all pairs
+    assert rep['max_rel_err_K_amplified'] <= 1.0               # rel err <= 1e-5 max(1, 2 beta d^2) on K >= 1e-6
+    assert rep64['max_dist_margin'] <= 0.0
+    assert rep64['max_rel_err_K'] <= 1e-5                      # flat north_star bound with the fp64 eigen-solve
 
 
 @pytest.mark.parametrize('name', ['spd3_n128', 'spd8_n64', 'spd5_n48'])

@@ -1,6 +1,6 @@
-"""Device tests written after the GPU budget of round 1 was spent: their first run on a B200 is the round-end suite, so
-they are xfail(strict=False) for now and live in the file pytest collects LAST.  The host logic they exercise is pinned
-on CPU against the reference's own solver classes (tests/test_host_logic.py, tests/test_oracle_golden.py)."""
+"""Device tests of the constrained trust-region / ALM solvers and of the two example BO loops (green on the B200 since
+the round-1 suite; no xfail marks: a regression must fail).  The host logic they exercise is also pinned on CPU against
+the reference's own solver classes (tests/test_host_logic.py, tests/test_oracle_golden.py)."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +12,6 @@ from test_acq_gpu import device_gp
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason='first device run pending (see the module docstring)')
 @pytest.mark.parametrize('name', ['ctr_spd2_active', 'ctr_spd3'])
 def test_lockstep_constrained_trust_regions_on_device_vs_reference_solver(golden, name):
     # gabo_spd.py's configuration: ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100), approx_hessian, one
@@ -31,11 +30,6 @@ def test_lockstep_constrained_trust_regions_on_device_vs_reference_solver(golden
     np.testing.assert_allclose(-val.cpu().numpy()[same], golden[name + '_cost'][same], rtol=1e-5, atol=1e-9)
 
 
-_PENDING = pytest.mark.xfail(strict=False, reason='written after the GPU budget of round 1 was spent: its first device '
-                                                  'run is the round-end suite; the host logic is pinned on CPU '
-                                                  '(tests/test_host_logic.py)')
-
-
 def _domain_constraint(angle):
     def constraint(x):
         centre = torch.zeros(3, dtype=x.dtype, device=x.device)
@@ -47,7 +41,6 @@ def _domain_constraint(angle):
     return constraint
 
 
-@_PENDING
 def test_lockstep_constrained_trust_regions_on_the_sphere_on_device(golden):
     # ConstrainedTrustRegions(maxiter=200) with the domain constraint of gabo_sphere_inequality_constraints.py as a
     # user-supplied torch callable (autograd per restart on the device); golden: the reference's own class
@@ -63,7 +56,6 @@ def test_lockstep_constrained_trust_regions_on_the_sphere_on_device(golden):
     np.testing.assert_allclose(X.cpu().numpy()[same], golden[name + '_x'][same], rtol=0, atol=1e-5)
 
 
-@_PENDING
 def test_lockstep_augmented_lagrangian_on_device(golden):
     # AugmentedLagrangeMethod(inner_solver=TrustRegions(maxiter=50), maxiter=12) against the oracle restatement of the
     # reference's class (oracle/alm.py, itself pinned on the class through the alm_* golden arrays)
@@ -92,7 +84,6 @@ def _load_example(name):
     return mod
 
 
-@_PENDING
 def test_gabo_sphere_example_runs_on_device():
     # examples/gabo_sphere.py: GP fit + EI + TrustRegions (gabo_acq_rtr) per iteration; host wiring pinned on CPU by
     # tests/test_example_emulated.py
@@ -105,7 +96,6 @@ def test_gabo_sphere_example_runs_on_device():
     assert all(b1 <= b0 for b0, b1 in zip(best, best[1:]))
 
 
-@_PENDING
 def test_gabo_spd_example_runs_on_device():
     # examples/gabo_spd.py: ConstrainedTrustRegions + max-eigenvalue constraint through the lock-step driver
     from oracle import spd as ospd
