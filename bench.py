@@ -797,10 +797,12 @@ class Bench:
                 'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': self.hbm_peak, 'unit': 'GB/s',
                              'frac': gbs / self.hbm_peak, 'algorithmic_bytes_per_launch': nbytes}}
 
-    def extra_acq_tr_spd(self, constrained, R=256, d=3, n_train=32, noise=1e-2, steps=3):
-        """The solver configurations of gabo_spd.py on SPD(3) through the lock-step driver (fp64 evaluator): plain
-        TrustRegions(maxiter=100) or ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100) with one max-eigenvalue
-        inequality constraint.  Host-driven (about 8 launches per inner iteration): the time is launch latency."""
+    def extra_acq_tr_spd(self, constrained, R=256, d=3, n_train=32, noise=1e-2, steps=5, lockstep=True):
+        """The solver configurations of gabo_spd.py on SPD(d): plain TrustRegions(maxiter=100) or
+        ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100) with one max-eigenvalue inequality constraint, R restarts
+        solved by ONE launch (gabo_acq_rtr / gabo_acq_ctr: one warp per restart, fp64, finite-difference Hessian).
+        `lockstep`: the same solves through the host-driven lock-step driver of round 1 (still the route for generic
+        constraint callables), wall clock, for comparison."""
         import functools
         from gabotorch_b200 import manifold_optimization as mo, riemannian_utils as ru
         torch, ops, _lib = self.torch, self.ops, self._lib
@@ -815,27 +817,35 @@ class Bench:
         gp = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False, compute='f64').device_gp()
         x0 = ops.mandel_unpack(torch.from_numpy(spd_sample_mandel(np.random.default_rng(32 + self.rank), R, d,
                                                                   min_eig=0.5, max_eig=2.5)))
-        kw = dict(maxiter=100)
-        if constrained:
-            cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.0)]
-            kw.update(mingradnorm=1e-4, ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
         res = {}
-
-        def step():
-            res['out'] = mo.batched_trust_regions(gp, x0, **kw)
-        step()                                  # warm-up
-        torch.cuda.synchronize()                # host-driven solver: wall clock between synchronisations, and NOT part
-        t0 = time.perf_counter()                # of the clock-sampled timed regions (the GPU idles between launches)
-        for _ in range(steps):
-            step()
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3 / steps
+        if constrained:
+            def step():
+                res['out'] = ops.acq_ctr(gp, x0, [('max', 3.0)], maxiter=100, mingradnorm=1e-4)
+        else:
+            def step():
+                res['out'] = ops.acq_rtr(gp, x0, maxiter=100)
+        ms = self.time_steps(step, steps, 3, flush=False) / steps
         it = res['out'][2].double()
-        return {'workload': 'acq %s on EI, SPD(%d), %d restarts/GPU, lock-step driver, fp64 evaluator, n_train=%d'
-                            % ('ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100) + max-eigenvalue constraint'
-                               if constrained else 'TrustRegions(maxiter=100)', d, R, n_train),
-                'solves_per_s': self.world * R / (ms * 1e-3), 'ms_per_step': ms, 'mean_outer_iters': it.mean().item(),
-                'max_outer_iters': int(it.max().item())}
+        out = {'workload': 'acq %s on EI, SPD(%d), %d restarts/GPU, ONE launch (one warp per restart, fp64), n_train=%d'
+                           % ('ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100) + max-eigenvalue constraint'
+                              if constrained else 'TrustRegions(maxiter=100)', d, R, n_train),
+               'solves_per_s': self.world * R / (ms * 1e-3), 'ms_per_step': ms, 'mean_outer_iters': it.mean().item(),
+               'max_outer_iters': int(it.max().item())}
+        if lockstep:
+            kw = dict(maxiter=100)
+            if constrained:
+                cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.0)]
+                kw.update(mingradnorm=1e-4, ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
+            mo.batched_trust_regions(gp, x0, **kw)          # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref = mo.batched_trust_regions(gp, x0, **kw)
+            torch.cuda.synchronize()
+            lms = (time.perf_counter() - t0) * 1e3
+            out['lockstep_driver_ms'] = lms
+            out['lockstep_driver_solves_per_s'] = self.world * R / (lms * 1e-3)
+            out['same_iteration_counts_as_lockstep'] = float((ref[2] == res['out'][2]).double().mean().item())
+        return out
 
     def guarded(self, fn, *a, **kw):
         """Extras of the 'next' rows must never take the headline line down with them."""
@@ -874,6 +884,9 @@ class Bench:
             return 0
         if args.only == 'next':                   # developer switch: the SURVEY 8(f) extras only
             out = [self.guarded(f) for f in (self.extra_acq_rtr, self.extra_gp_fit, self.extra_reconstruct)]
+            out += [self.guarded(self.extra_acq_tr_spd, False), self.guarded(self.extra_acq_tr_spd, True),
+                    self.guarded(self.extra_acq_tr_spd, True, R=4096, lockstep=False),
+                    self.guarded(self.extra_acq_tr_spd, True, R=1024, d=8, lockstep=False)]
             self.clocks.stop()
             if self.rank == 0:
                 emit({'extra': out})
@@ -913,6 +926,8 @@ class Bench:
                 extras.append(self.guarded(self.extra_reconstruct))
                 extras.append(self.guarded(self.extra_acq_tr_spd, False))
                 extras.append(self.guarded(self.extra_acq_tr_spd, True))
+                extras.append(self.guarded(self.extra_acq_tr_spd, True, R=4096, lockstep=False))
+                extras.append(self.guarded(self.extra_acq_tr_spd, True, R=1024, d=8, lockstep=False))
         cpu, parity = None, None
         if self.rank == 0 and self.world == 1 and not args.no_cpu_baseline:
             cpu = self.cpu_baseline()

@@ -38,6 +38,14 @@ class RtrOpts(ctypes.Structure):
                 ('rho_prime', c_f64), ('rho_regularization', c_f64), ('delta_bar', c_f64), ('delta0', c_f64)]
 
 
+CONS_MAX_EIG, CONS_MIN_EIG = 0, 1
+
+
+class CtrOpts(ctypes.Structure):
+    _fields_ = [('tr', RtrOpts), ('n_constraints', ctypes.c_int32), ('strict', ctypes.c_int32),
+                ('kind', ctypes.c_int32 * 2), ('bound', c_f64 * 2), ('delta_cons', c_f64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/gabo_b200.h declares (tests/test_abi.py checks it)
 SIGNATURES = {
     'gabo_version': (c_i32, []),
@@ -63,6 +71,8 @@ SIGNATURES = {
     'gabo_acq_rcg': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, ctypes.POINTER(RcgOpts), c_ptr, c_ptr, c_ptr,
                              c_ptr]),
     'gabo_acq_rtr': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, ctypes.POINTER(RtrOpts), c_ptr, c_ptr, c_ptr,
+                             c_ptr]),
+    'gabo_acq_ctr': (c_i32, [ctypes.POINTER(GpDesc), c_ptr, c_i64, ctypes.POINTER(CtrOpts), c_ptr, c_ptr, c_ptr,
                              c_ptr]),
     'gabo_argmax_records': (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     'gabo_nested_spd_project_f64': (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),

@@ -42,6 +42,45 @@ int dispatch(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* 
     return GABO_E_ARG;
 }
 
+int dispatch_ctr(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_ctr_opts* o, double* value, int32_t* iters,
+                 int32_t* reason, cudaStream_t s) {
+    const int d = gp->dim;
+    CtrParams p{};
+    p.tr.maxiter = o->tr.maxiter;
+    p.tr.mininner = o->tr.mininner;
+    p.tr.maxinner = o->tr.maxinner > 0 ? o->tr.maxinner : d * (d + 1) / 2;               // pymanopt PositiveDefinite.dim
+    p.tr.mingradnorm = o->tr.mingradnorm;
+    p.tr.kappa = o->tr.kappa;
+    p.tr.theta = o->tr.theta;
+    p.tr.rho_prime = o->tr.rho_prime;
+    p.tr.rho_regularization = o->tr.rho_regularization;
+    p.tr.delta_bar = o->tr.delta_bar > 0.0 ? o->tr.delta_bar : sqrt(0.5 * d * (d + 1));   // PositiveDefinite.typicaldist
+    p.tr.delta0 = o->tr.delta0 > 0.0 ? o->tr.delta0 : p.tr.delta_bar / 8.0;
+    p.tr.fd_eps = 1.0 / 16384.0;                                                         // approximate_hessian.py:43
+    p.n_cons = o->n_constraints;
+    p.strict = o->strict;
+    for (int c = 0; c < 2; ++c) {
+        p.kind[c] = o->kind[c];
+        p.bound[c] = o->bound[c];
+    }
+    p.delta_cons = o->delta_cons;
+    switch (d) {
+#define GABO_CASE(DD) \
+    case DD:          \
+        return launch_rtr_spd<DD>(gp, x, r, p, value, iters, reason, s);
+        GABO_CASE(1)
+        GABO_CASE(2)
+        GABO_CASE(3)
+        GABO_CASE(4)
+        GABO_CASE(5)
+        GABO_CASE(6)
+        GABO_CASE(7)
+        GABO_CASE(8)
+#undef GABO_CASE
+    }
+    return GABO_E_ARG;
+}
+
 // Lexicographic (value desc, global index asc), NaN = -inf.  One CTA; n is the number of restarts (small).
 __global__ void argmax_records_kernel(const double* __restrict__ values, const int64_t* __restrict__ gidx, int64_t n,
                                       int64_t* __restrict__ out_slot, double* __restrict__ out_value) {
@@ -142,9 +181,35 @@ extern "C" int gabo_acq_rtr(const gabo_gp_desc* gp, double* x, int64_t r, const 
     GABO_REQUIRE(opts->maxiter >= 1 && opts->mininner >= 0, GABO_E_ARG, "gabo_acq_rtr: bad iteration limits");
     GABO_REQUIRE(opts->kappa > 0.0 && opts->rho_prime >= 0.0 && opts->rho_prime < 0.25, GABO_E_ARG,
                  "gabo_acq_rtr: need kappa > 0 and 0 <= rho_prime < 1/4");
-    GABO_REQUIRE(gp->manifold == GABO_SPHERE, GABO_E_UNSUPPORTED,
-                 "gabo_acq_rtr: the trust-region solver is implemented for the sphere (use gabo_acq_rcg on SPD)");
+    if (gp->manifold == GABO_SPD) {
+        gabo_ctr_opts c{};
+        c.tr = *opts;
+        c.delta_cons = 1e-6;
+        return dispatch_ctr(gp, x, r, &c, value, iters, reason, static_cast<cudaStream_t>(stream));
+    }
     return launch_rtr_sphere(gp, x, r, opts, value, iters, reason, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gabo_acq_ctr(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_ctr_opts* opts, double* value,
+                            int32_t* iters, int32_t* reason, void* stream) {
+    using namespace gabo;
+    const int rc = validate_gp(gp, "gabo_acq_ctr");
+    if (rc != GABO_OK) return rc;
+    GABO_REQUIRE(r >= 0, GABO_E_ARG, "gabo_acq_ctr: negative size");
+    if (r == 0) return GABO_OK;
+    GABO_REQUIRE(x && value && opts, GABO_E_ARG, "gabo_acq_ctr: null pointer");
+    GABO_REQUIRE(gp->manifold == GABO_SPD, GABO_E_UNSUPPORTED,
+                 "gabo_acq_ctr: the constrained trust-region kernel is implemented for SPD(d)");
+    GABO_REQUIRE(opts->tr.maxiter >= 1 && opts->tr.mininner >= 0, GABO_E_ARG, "gabo_acq_ctr: bad iteration limits");
+    GABO_REQUIRE(opts->tr.kappa > 0.0 && opts->tr.rho_prime >= 0.0 && opts->tr.rho_prime < 0.25, GABO_E_ARG,
+                 "gabo_acq_ctr: need kappa > 0 and 0 <= rho_prime < 1/4");
+    GABO_REQUIRE(opts->n_constraints >= 0 && opts->n_constraints <= 2, GABO_E_ARG,
+                 "gabo_acq_ctr: n_constraints=%d outside [0, 2]", opts->n_constraints);
+    for (int c = 0; c < opts->n_constraints; ++c)
+        GABO_REQUIRE(opts->kind[c] == GABO_CONS_MAX_EIG || opts->kind[c] == GABO_CONS_MIN_EIG, GABO_E_ARG,
+                     "gabo_acq_ctr: unknown constraint kind %d", opts->kind[c]);
+    GABO_REQUIRE(opts->delta_cons > 0.0, GABO_E_ARG, "gabo_acq_ctr: delta_cons must be positive");
+    return dispatch_ctr(gp, x, r, opts, value, iters, reason, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gabo_argmax_records(const double* values, const int64_t* gidx, int64_t n, int64_t* out_slot,

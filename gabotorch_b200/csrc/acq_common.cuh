@@ -33,6 +33,15 @@ struct RtrParams {
     double mingradnorm, kappa, theta, rho_prime, rho_regularization, delta_bar, delta0, fd_eps;
 };
 
+struct CtrParams {
+    RtrParams tr;
+    int n_cons;        // 0 (plain TrustRegions), 1 or 2 eigenvalue constraints
+    int strict;        // StrictConstrainedTrustRegions
+    int kind[2];       // GABO_CONS_MAX_EIG | GABO_CONS_MIN_EIG
+    double bound[2];
+    double delta_cons; // Delta_cons of ConstrainedTrustRegions.solve (1e-6)
+};
+
 template <typename T>
 struct M;
 template <>
@@ -126,5 +135,9 @@ int launch_rtr_sphere(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_r
 template <int d>
 int launch_acq_spd(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_opts* opts, double* value,
                    double* grad, int32_t* iters, int32_t* reason, cudaStream_t stream);
+
+template <int d>
+int launch_rtr_spd(const gabo_gp_desc* gp, double* x, int64_t r, const CtrParams& opt, double* value, int32_t* iters,
+                   int32_t* reason, cudaStream_t stream);
 
 }  // namespace gabo

@@ -205,6 +205,7 @@ class SpdAffineInvariantGaussianKernel(_BetaKernel):
     def __init__(self, beta_min, beta_prior=None, compute='f32', **kwargs):
         super().__init__(beta_min, beta_prior=beta_prior, **kwargs)
         self.compute = compute
+        self._host_ws = ops.HostGramWorkspace()
 
     def _compute(self):
         return _lib.GABO_F64 if self.compute == 'f64' else _lib.GABO_F32
@@ -223,12 +224,10 @@ class SpdAffineInvariantGaussianKernel(_BetaKernel):
         else:
             # host inputs: the per-pair kernel stores straight into a pinned host tensor (the PCIe transfer of the
             # Gram matrix overlaps its computation); the mirrored x1-is-x2 form stays on the device path
-            host = _host_result(x1, x2)
-            out = ops.spd_ai_gram(x1, x2, float(beta.detach()), _lib.KIND_GAUSS, compute=self._compute(),
-                                  host_out=host)
-            if host:
-                torch.cuda.current_stream().synchronize()
-                return out
+            if _host_result(x1, x2) and x1.dtype == torch.float64 and x2.dtype == torch.float64:
+                return ops.spd_ai_gram_host(self._host_ws, x1, x2, float(beta.detach()), _lib.KIND_GAUSS,
+                                            compute=self._compute())
+            out = ops.spd_ai_gram(x1, x2, float(beta.detach()), _lib.KIND_GAUSS, compute=self._compute())
         return _finish(out, x1)
 
 

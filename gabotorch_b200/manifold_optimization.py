@@ -181,9 +181,30 @@ _CONSTRAINED_SOLVERS = ('ConstrainedTrustRegions', 'StrictConstrainedTrustRegion
 
 
 def _rtr_kernel_covers(gp):
-    """The register-resident trust-region kernel (gabo_acq_rtr): sphere, ambient dimension <= 8, or <= 16 with at most
-    64 training points."""
-    return gp.manifold == _lib.SPHERE and (gp.dim <= 8 or (gp.dim <= 16 and gp.n_train <= 64))
+    """The one-launch trust-region kernels (gabo_acq_rtr): spheres of ambient dimension <= 8 (or <= 16 with at most 64
+    training points, register-resident iterate) and SPD(d) (one warp per restart, whitened coordinates)."""
+    if gp.manifold == _lib.SPD:
+        return True
+    return gp.dim <= 8 or (gp.dim <= 16 and gp.n_train <= 64)
+
+
+def eigenvalue_constraint_specs(constraints):
+    """``[('max' | 'min', bound), ...]`` when EVERY constraint is a ``functools.partial`` of
+    ``max_eigenvalue_constraint_torch`` / ``min_eigenvalue_constraint_torch`` (the constraints of gabo_spd.py:136-138) and
+    there are at most two of them -- the set ``gabo_acq_ctr`` evaluates inside the solver kernel; None otherwise."""
+    from . import riemannian_utils as ru
+    specs = []
+    for c in constraints:
+        f = getattr(c, 'func', None)
+        kw = getattr(c, 'keywords', None) or {}
+        args = getattr(c, 'args', ())
+        if f is ru.max_eigenvalue_constraint_torch and ('maximum_eigenvalue' in kw or args):
+            specs.append(('max', float(kw.get('maximum_eigenvalue', args[0] if args else 0.0))))
+        elif f is ru.min_eigenvalue_constraint_torch and ('minimum_eigenvalue' in kw or args):
+            specs.append(('min', float(kw.get('minimum_eigenvalue', args[0] if args else 0.0))))
+        else:
+            return None
+    return specs if 0 < len(specs) <= 2 else None
 
 
 def batched_trust_regions(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1,
@@ -832,19 +853,25 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     if not trust_region:
         solve = ops.acq_rcg
     elif constrained:
-        # the reference's ConstrainedTrustRegions: lock-step driver with the constrained tCG, fp64 evaluator
-        solve = batched_trust_regions
-        gp = gp.with_compute(_lib.GABO_F64)
         cons = inequality_constraints if isinstance(inequality_constraints, (list, tuple)) else [inequality_constraints]
-        sopts = dict(sopts, **{'eq_constraints' if eq_mode else 'ineq_constraints': batched_constraints(cons, kind)},
-                     delta_cons=float(getattr(solver, 'Delta_cons', 1e-6)),
-                     strict=type(solver).__name__ == 'StrictConstrainedTrustRegions')
+        strict = type(solver).__name__ == 'StrictConstrainedTrustRegions'
+        delta_cons = float(getattr(solver, 'Delta_cons', 1e-6))
+        specs = None if (eq_mode or kind != _lib.SPD) else eigenvalue_constraint_specs(cons)
+        if specs is not None:
+            # gabo_spd.py's configuration: eigenvalue constraints on SPD(d) -> the whole constrained solve in one launch
+            solve = ops.acq_ctr
+            sopts = dict(sopts, constraints=specs, strict=strict, delta_cons=delta_cons)
+        else:
+            # any other constraint callable (differentiated with torch.autograd per restart, as the reference's Problem
+            # does) or equality constraints: lock-step driver with the constrained tCG, fp64 evaluator
+            solve = batched_trust_regions
+            gp = gp.with_compute(_lib.GABO_F64)
+            sopts = dict(sopts, **{'eq_constraints' if eq_mode else 'ineq_constraints': batched_constraints(cons, kind)},
+                         delta_cons=delta_cons, strict=strict)
     elif _rtr_kernel_covers(gp):
-        solve = ops.acq_rtr                      # one launch, one warp per restart
+        solve = ops.acq_rtr                      # one launch, one warp per restart (SPD: fp64 whatever gp.compute says)
     else:
-        # SPD / large spheres: lock-step over the batched kernels, evaluated in fp64 -- the solver's stopping rule
-        # (|grad| < 1e-6) lies below the fp32 noise floor of the SPD gradient (measured: fp32 solves run to maxiter),
-        # and this path is launch-bound, so the arithmetic type does not set its speed
+        # spheres beyond the register kernel: lock-step over the batched kernels, evaluated in fp64
         solve = batched_trust_regions
         gp = gp.with_compute(_lib.GABO_F64)
     cand, val, iters, reason = solve(gp, pts, **sopts)

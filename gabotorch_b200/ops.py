@@ -216,6 +216,59 @@ def spd_ai_gram(x1, x2, param=0.0, kind=_lib.KIND_GAUSS, is_mandel=True, compute
     return out.reshape(lead + (n1, n2))
 
 
+class HostGramWorkspace:
+    """Device-side staging of ``spd_ai_gram_host`` for one (n1, n2, dv) problem shape: the input copies, the factor
+    records and the not-positive-definite flag (device + its pinned host mirror) are allocated once per kernel object and
+    reused, so a host-to-host Gram build costs two asynchronous H2D copies, three launches and ONE synchronisation."""
+
+    def __init__(self):
+        self.key = None
+
+    def get(self, dev, n1, n2, dv, d, fs):
+        key = (dev, n1, n2, dv)
+        if self.key != key:
+            self.key = key
+            self.x1 = torch.empty(n1, dv, dtype=torch.float64, device=dev)
+            self.x2 = torch.empty(n2, dv, dtype=torch.float64, device=dev)
+            self.f1 = torch.empty(n1, fs, dtype=torch.float64, device=dev)
+            self.f2 = torch.empty(n2, fs, dtype=torch.float64, device=dev)
+            self.flags = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        return self
+
+
+def spd_ai_gram_host(ws, x1, x2, param=0.0, kind=_lib.KIND_GAUSS, compute=_lib.GABO_F32, out_dtype=torch.float64):
+    """f(d_AI(X1_i, X2_j)) for HOST Mandel vectors (n1, dv), (n2, dv) -> HOST (n1, n2) tensor in pinned memory.  The
+    per-pair kernel stores straight into the pinned (device-mapped) result, so the PCIe transfer of the Gram matrix
+    overlaps its computation (measured on the B200 box: 52 GB/s for the zero-copy stores vs 57 GB/s for a copy-engine
+    transfer that could only start after the kernel).  One stream synchronisation at the end; the not-positive-definite
+    flag travels in a pinned mirror and is read from host memory after that synchronisation."""
+    lib = _lib.load()
+    dev = device()
+    n1, n2, dv = x1.shape[0], x2.shape[0], x1.shape[1]
+    if x2.shape[1] != dv:
+        raise ValueError('spd_ai_gram: x1 and x2 live on different SPD manifolds')
+    d = mandel_dim(dv)
+    fs = lib.gabo_spd_factor_stride(d)
+    if fs < 0:
+        raise ValueError('SPD(%d): matrix size outside [1, %d]' % (d, _lib.MAX_SPD_DIM))
+    w = ws.get(dev, n1, n2, dv, d, fs)
+    w.x1.copy_(x1, non_blocking=True)
+    w.x2.copy_(x2, non_blocking=True)
+    w.flags.zero_()
+    s = _lib.stream_ptr()
+    _lib.check(lib.gabo_spd_factor2(_p(w.x1), n1, _p(w.x2), n2, d, 1, _p(w.f1), _p(w.f2), _p(w.flags), s),
+               'gabo_spd_factor2')
+    w.flag_host.copy_(w.flags, non_blocking=True)
+    out = torch.empty(n1, n2, dtype=out_dtype, pin_memory=True)
+    _lib.check(lib.gabo_spd_ai_gram(_p(w.f1), n1, _p(w.f2), n2, d, float(param), kind, compute, 0, _p(out),
+                                    _DT[out_dtype], n2, s), 'gabo_spd_ai_gram')
+    torch.cuda.current_stream().synchronize()
+    if int(w.flag_host[0]) != 0:
+        raise NotPositiveDefiniteError('input contains a matrix that is not positive definite')
+    return out
+
+
 def spd_ai_gram_backward(fac1, fac2, d, w, transpose_w=False, compute=_lib.GABO_F32):
     """sum_j w_ij grad_{X1_i} d_AI^2(X1_i, X2_j) as (n1, d, d) fp64 matrices (gabo_spd_ai_gram_backward)."""
     lib = _lib.load()
@@ -513,8 +566,8 @@ def acq_rcg(gp, x0, maxiter=1000, mingradnorm=1e-6, minstepsize=1e-10, ls_maxite
 
 def acq_rtr(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_prime=0.1, rho_regularization=1e3,
             mininner=1, maxinner=None, delta_bar=None, delta0=None):
-    """Multi-start Riemannian trust regions (tCG, finite-difference Hessian) on -EI, sphere.  Returns (candidates,
-    values, iters, reasons)."""
+    """Multi-start Riemannian trust regions (tCG, finite-difference Hessian) on -EI: spheres the register kernel covers
+    and SPD(d) (fp64, one warp per restart).  Returns (candidates, values, iters, reasons)."""
     lib = _lib.load()
     x = to_dev64(x0).clone()
     r = x.shape[0]
@@ -526,6 +579,33 @@ def acq_rtr(gp, x0, maxiter=1000, mingradnorm=1e-6, kappa=0.1, theta=1.0, rho_pr
                         float(delta0 or 0.0))
     _lib.check(lib.gabo_acq_rtr(ctypes.byref(gp.desc), _p(x), r, ctypes.byref(opts), _p(val), _p(iters), _p(reason),
                                 _lib.stream_ptr()), 'gabo_acq_rtr')
+    return x, val, iters, reason
+
+
+def acq_ctr(gp, x0, constraints=(), strict=False, delta_cons=1e-6, maxiter=1000, mingradnorm=1e-6, kappa=0.1,
+            theta=1.0, rho_prime=0.1, rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None):
+    """Multi-start [Strict]ConstrainedTrustRegions on SPD(d) in one launch (``gabo_acq_ctr``).  ``constraints``: up to
+    two ``('max' | 'min', bound)`` eigenvalue inequality constraints; none = plain TrustRegions.  Returns (candidates,
+    values, iters, reasons)."""
+    lib = _lib.load()
+    x = to_dev64(x0).clone()
+    r = x.shape[0]
+    val = torch.empty(r, dtype=torch.float64, device=x.device)
+    iters = torch.empty(r, dtype=torch.int32, device=x.device)
+    reason = torch.empty(r, dtype=torch.int32, device=x.device)
+    constraints = list(constraints)
+    if len(constraints) > 2:
+        raise ValueError('gabo_acq_ctr takes at most two eigenvalue constraints')
+    opts = _lib.CtrOpts()
+    opts.tr = _lib.RtrOpts(int(maxiter), int(mininner), int(maxinner or 0), 0, float(mingradnorm), float(kappa),
+                           float(theta), float(rho_prime), float(rho_regularization), float(delta_bar or 0.0),
+                           float(delta0 or 0.0))
+    opts.n_constraints, opts.strict, opts.delta_cons = len(constraints), int(bool(strict)), float(delta_cons)
+    for i, (kind, bound) in enumerate(constraints):
+        opts.kind[i] = _lib.CONS_MAX_EIG if kind == 'max' else _lib.CONS_MIN_EIG
+        opts.bound[i] = float(bound)
+    _lib.check(lib.gabo_acq_ctr(ctypes.byref(gp.desc), _p(x), r, ctypes.byref(opts), _p(val), _p(iters), _p(reason),
+                                _lib.stream_ptr()), 'gabo_acq_ctr')
     return x, val, iters, reason
 
 

@@ -203,8 +203,9 @@ int gabo_acq_rcg(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rcg_op
 
 /* Trust-region variant: the reference's own TrustRegions solver
  * (manifold_optimization/robust_trust_regions.py:116-352 with _truncated_conjugate_gradient :410-520) over the
- * finite-difference Hessian of manifold_optimization/approximate_hessian.py:11-62, one warp per restart, sphere only
- * (ambient dimension <= 8, or <= 16 with n_train <= 64).  reason 1 = maxiter, 2 = gradnorm. */
+ * finite-difference Hessian of manifold_optimization/approximate_hessian.py:11-62, one warp per restart: spheres of
+ * ambient dimension <= 8 (or <= 16 with n_train <= 64) and SPD(d), d <= 8 (fp64; see gabo_acq_ctr).
+ * reason 1 = maxiter, 2 = gradnorm. */
 typedef struct gabo_rtr_opts {
     int32_t maxiter;            /* pymanopt Solver maxiter (1000)                                   */
     int32_t mininner;           /* TrustRegions.solve mininner (1)                                  */
@@ -219,6 +220,28 @@ typedef struct gabo_rtr_opts {
     double delta0;              /* <= 0: delta_bar / 8                                              */
 } gabo_rtr_opts;
 int gabo_acq_rtr(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_rtr_opts* opts, double* value,
+                 int32_t* iters, int32_t* reason, void* stream);
+
+/* Constrained variant on SPD(d) (what examples/bo_spd/benchmark_examples/gabo_spd.py:183,200-203 runs): the reference's
+ * ConstrainedTrustRegions (manifold_optimization/constrained_trust_regions.py:120-439, constrained tCG :441-735) and
+ * StrictConstrainedTrustRegions (:737-1415; infeasible proposals rejected, :932-952, :1036) with up to two eigenvalue
+ * inequality constraints (Riemannian_utils/spd_constraints_utils_torch.py:17-50):
+ *   GABO_CONS_MAX_EIG: bound - lambda_max(X) >= 0,   GABO_CONS_MIN_EIG: lambda_min(X) - bound >= 0.
+ * One warp per restart, the whole solve inside one launch, fp64 (gp->compute is ignored: the stopping rule of the
+ * solver lies below the fp32 noise floor of the SPD gradient).  n_constraints = 0 is plain TrustRegions on SPD(d), which
+ * is also what gabo_acq_rtr runs for gp->manifold == GABO_SPD.  x: r x d x d (in/out).  reason 1 = maxiter,
+ * 2 = gradnorm, -1 = start not positive definite (value NaN). */
+#define GABO_CONS_MAX_EIG 0
+#define GABO_CONS_MIN_EIG 1
+typedef struct gabo_ctr_opts {
+    gabo_rtr_opts tr;          /* delta_bar <= 0: sqrt(d(d+1)/2) (pymanopt PositiveDefinite.typicaldist); maxinner <= 0: d(d+1)/2 */
+    int32_t n_constraints;     /* 0, 1 or 2                                                       */
+    int32_t strict;            /* != 0: StrictConstrainedTrustRegions                             */
+    int32_t kind[2];           /* GABO_CONS_*                                                     */
+    double bound[2];
+    double delta_cons;         /* Delta_cons of ConstrainedTrustRegions.solve (1e-6)              */
+} gabo_ctr_opts;
+int gabo_acq_ctr(const gabo_gp_desc* gp, double* x, int64_t r, const gabo_ctr_opts* opts, double* value,
                  int32_t* iters, int32_t* reason, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------

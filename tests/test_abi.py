@@ -79,8 +79,18 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.gabo_gp_factor(fake, 200, fake, 1.0, 1.0, 0.0, fake, fake, fake, null) == -1     # n > 128
     assert lib.gabo_gp_factor(fake, 8, fake, 1.0, 1.0, 0.0, null, fake, fake, null) == -1
     opts = _lib.RtrOpts(10, 1, 0, 0, 1e-6, 0.1, 1.0, 0.1, 1e3, 0.0, 0.0)
-    desc.manifold, desc.dim, desc.n_train = 1, 3, 4                                             # SPD: sphere only
-    assert lib.gabo_acq_rtr(ctypes.byref(desc), fake, 4, ctypes.byref(opts), fake, null, null, null) == -4
+    desc.manifold, desc.dim, desc.n_train = 1, 3, 4                                             # SPD(3)
+    copts = _lib.CtrOpts()
+    copts.tr, copts.delta_cons, copts.n_constraints = opts, 1e-6, 3
+    assert lib.gabo_acq_ctr(ctypes.byref(desc), fake, 4, ctypes.byref(copts), fake, null, null, null) == -1   # > 2 constraints
+    copts.n_constraints, copts.kind[0] = 1, 7
+    assert lib.gabo_acq_ctr(ctypes.byref(desc), fake, 4, ctypes.byref(copts), fake, null, null, null) == -1   # unknown kind
+    copts.kind[0], copts.delta_cons = 0, 0.0
+    assert lib.gabo_acq_ctr(ctypes.byref(desc), fake, 4, ctypes.byref(copts), fake, null, null, null) == -1
+    copts.delta_cons = 1e-6
+    assert lib.gabo_acq_ctr(ctypes.byref(desc), fake, 0, ctypes.byref(copts), fake, null, null, null) == 0    # no restart
+    desc.manifold = 0
+    assert lib.gabo_acq_ctr(ctypes.byref(desc), fake, 4, ctypes.byref(copts), fake, null, null, null) == -4   # sphere
     desc.manifold, desc.dim = 0, 20                                                              # beyond the register kernel
     assert lib.gabo_acq_rtr(ctypes.byref(desc), fake, 4, ctypes.byref(opts), fake, null, null, null) == -4
     opts.rho_prime = 0.5
@@ -117,7 +127,8 @@ def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirrors(tmp_path)
     gcc = shutil.which('gcc')
     if gcc is None:
         pytest.skip('gcc not available')
-    fields = {'gabo_gp_desc': _lib.GpDesc, 'gabo_rcg_opts': _lib.RcgOpts, 'gabo_rtr_opts': _lib.RtrOpts}
+    fields = {'gabo_gp_desc': _lib.GpDesc, 'gabo_rcg_opts': _lib.RcgOpts, 'gabo_rtr_opts': _lib.RtrOpts,
+              'gabo_ctr_opts': _lib.CtrOpts}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gabo_b200.h"', 'int main(void) {']
     for cname, mirror in fields.items():
         lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

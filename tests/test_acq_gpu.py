@@ -313,3 +313,125 @@ def test_lockstep_trust_regions_on_device_vs_oracle(manifold, dim, n, R):
     else:
         np.testing.assert_allclose(np.linalg.norm(X, axis=-1), 1.0, atol=1e-12)
 
+
+
+# ---- trust regions on SPD(d) in one launch (gabo_acq_rtr / gabo_acq_ctr): pinned on the reference's own classes ------
+
+def _spd_gp_from_golden(golden, name):
+    beta, noise, bound = (float(v) for v in golden[name + '_hyper'])
+    return ogp.make_gp('spd', golden[name + '_xtrain'], golden[name + '_y'], beta=beta, noise=noise), bound
+
+
+@pytest.mark.parametrize('name', ['ctr_spd2_active', 'ctr_spd2', 'ctr_spd3', 'sctr_spd2_active', 'sctr_spd3'])
+def test_spd_constrained_trust_region_kernel_reproduces_the_reference_solver(golden, name):
+    # tests/golden/make_golden.py ran the reference's OWN ConstrainedTrustRegions / StrictConstrainedTrustRegions classes
+    # (constrained_trust_regions.py) in gabo_spd.py's configuration -- mingradnorm 1e-4 (2e-4 strict, hd_gabo_spd.py:194),
+    # maxiter 100, finite-difference Hessian, one max-eigenvalue inequality constraint -- from these starts
+    from oracle import ctr as octr
+    gp, max_eig = _spd_gp_from_golden(golden, name)
+    strict = name.startswith('sctr')
+    x, val, iters, reason = ops.acq_ctr(device_gp(gp, _lib.GABO_F64), golden[name + '_x0'], [('max', max_eig)],
+                                        strict=strict, maxiter=100, mingradnorm=2e-4 if strict else 1e-4)
+    x, val, iters = x.cpu().numpy(), val.cpu().numpy(), iters.cpu().numpy()
+    same = iters == golden[name + '_iters']
+    assert same.mean() >= 0.8, (iters, golden[name + '_iters'])
+    np.testing.assert_allclose(x[same], golden[name + '_x'][same], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(-val[same], golden[name + '_cost'][same], rtol=1e-6, atol=1e-10)
+    # restarts whose path forked on a rounding-level accept / reject decision: still a valid solve -- SPD, value equal to
+    # the oracle's EI at the returned point, and no worse than the start
+    cons = octr.max_eigenvalue_constraint(max_eig)[0]
+    for i in range(len(iters)):
+        assert np.linalg.eigvalsh(x[i]).min() > 0
+        e_here = ogp.ei_and_grad(gp, x[i], want_grad=False)[0]
+        e_start = ogp.ei_and_grad(gp, golden[name + '_x0'][i], want_grad=False)[0]
+        assert abs(val[i] - e_here) <= 1e-7 * max(1.0, abs(e_here)) and val[i] >= e_start - 1e-12
+        if strict:      # the strict solver never accepts an infeasible point
+            assert cons(x[i]) >= -1e-9 or cons(golden[name + '_x0'][i]) < 0
+    assert set(reason.cpu().numpy().tolist()) <= {1, 2}
+
+
+@pytest.mark.parametrize('d,n,R', [(1, 6, 9), (2, 10, 33), (3, 12, 64), (4, 20, 16), (5, 33, 20), (8, 24, 10)])
+def test_spd_trust_region_kernel_follows_the_serial_solver(d, n, R):
+    # plain TrustRegions on SPD(d): the oracle (oracle/rtr.py, pinned on the reference's own class on the sphere) solved
+    # serially from the same starts; pymanopt PositiveDefinite operations (exp retraction, identity transport)
+    from oracle import rtr as ortr
+    rng, gp = spd_problem(d, n, beta=0.5 + math.log(2.0), noise=1e-2, seed=300 + d)
+    x0 = ospd.spd_sample(rng, R, d, max_cond=50.0)
+    x, val, iters, _ = ops.acq_rtr(device_gp(gp, _lib.GABO_F32), x0, maxiter=15)     # fp64 whatever the descriptor says
+    x, val, iters = x.cpu().numpy(), val.cpu().numpy(), iters.cpu().numpy()
+    nref = min(R, 10)
+    opts = ortr.TROptions(maxiter=15)
+    same = 0
+    for i in range(nref):
+        xi, ci, ki = ortr.solve_tr(gp, x0[i], opts)
+        if int(iters[i]) == ki:
+            same += 1
+            np.testing.assert_allclose(x[i], xi, rtol=0, atol=1e-6 * max(1.0, np.abs(xi).max()))
+            assert abs(-val[i] - ci) <= 1e-7 * max(1.0, abs(ci))
+    assert same >= nref - 2
+    ei0 = np.array([ogp.ei_and_grad(gp, xi, want_grad=False)[0] for xi in x0])
+    assert (val >= ei0 - 1e-12).all()                                  # trust regions never accept a worse point
+    np.testing.assert_allclose(x, np.swapaxes(x, -1, -2), rtol=0, atol=1e-12)
+    assert np.linalg.eigvalsh(x).min() > 0
+
+
+def test_spd_constrained_kernel_agrees_with_the_lockstep_driver_and_handles_two_constraints():
+    # two independent implementations of the reference's constrained solver on the device: the one-launch kernel and the
+    # lock-step driver (host logic pinned on CPU against the reference's class, tests/test_host_logic.py)
+    import functools
+    from gabotorch_b200 import manifold_optimization as mo, riemannian_utils as ru
+    rng, gp = spd_problem(3, 16, beta=0.5 + math.log(2.0), noise=1e-2, seed=77)
+    x0 = ospd.spd_sample(rng, 48, 3, min_eig=0.3, max_eig=2.5, max_cond=50.0)
+    dgp = device_gp(gp, _lib.GABO_F64)
+    cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.0),
+            functools.partial(ru.min_eigenvalue_constraint_torch, minimum_eigenvalue=0.2)]
+    for strict in (False, True):
+        xk, vk, ik, _ = ops.acq_ctr(dgp, x0, [('max', 3.0), ('min', 0.2)], strict=strict, maxiter=40, mingradnorm=1e-4)
+        xl, vl, il, _ = mo.batched_trust_regions(dgp, x0, maxiter=40, mingradnorm=1e-4, strict=strict,
+                                                 ineq_constraints=mo.batched_constraints(cons, _lib.SPD))
+        same = (ik == il).cpu().numpy()
+        assert same.mean() >= 0.85, (ik, il)
+        np.testing.assert_allclose(xk.cpu().numpy()[same], xl.cpu().numpy()[same], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(vk.cpu().numpy()[same], vl.cpu().numpy()[same], rtol=1e-6, atol=1e-10)
+        if strict:
+            lam = np.linalg.eigvalsh(xk.cpu().numpy())
+            assert lam.max() <= 3.0 + 1e-9 and lam.min() >= 0.2 - 1e-9
+    # a start that is not positive definite is reported, not solved
+    bad = x0[:3].copy()
+    bad[1] = -bad[1]
+    xb, vb, ib, rb = ops.acq_ctr(dgp, bad, [('max', 3.0)])
+    assert np.isnan(float(vb[1])) and int(rb[1]) == -1 and np.isfinite(vb.cpu().numpy()[[0, 2]]).all()
+
+
+def test_spd_trust_regions_through_the_reference_api():
+    # gabo_spd.py:183,200-203 through the drop-in surface: the constrained solve is ONE launch of gabo_acq_ctr
+    import functools
+    import gabotorch_b200 as g
+    from gabotorch_b200 import riemannian_utils as ru
+    rng = np.random.default_rng(5)
+    xt = ospd.spd_sample(rng, 12, 2, max_cond=50.0)
+    xv = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(xt))
+    y = ospd.ackley(xv)
+    model = g.ManifoldGP(xv, torch.from_numpy(y), g.ScaleKernel(g.SpdAffineInvariantGaussianKernel(beta_min=0.6)),
+                         noise=1e-2)
+    model.covar_module.outputscale = 1.0
+    acq = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False)
+    man = g.PositiveDefinite(2)
+    man.min_eig, man.max_eig = 0.5, 1.8
+    cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=2.0)]
+    kw = dict(pre_processing_manifold=ru.vector_to_symmetric_matrix_mandel_torch,
+              post_processing_manifold=ru.symmetric_matrix_to_vector_mandel_torch, approx_hessian=True)
+    ics = g.gen_batch_initial_conditions_manifold(acq, man, None, 1, 8, 64, options={'seed': 3},
+                                                  post_processing_manifold=ru.symmetric_matrix_to_vector_mandel_torch)
+    for solver, extra in ((g.TrustRegions(maxiter=50), {}),
+                          (g.ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100), dict(inequality_constraints=cons)),
+                          (g.StrictConstrainedTrustRegions(mingradnorm=2e-4, maxiter=100, minstepsize=1e-4),
+                           dict(inequality_constraints=cons))):
+        cand, vals, info = g.gen_candidates_manifold(ics, acq, man, solver, return_info=True, **kw, **extra)
+        assert tuple(cand.shape) == (8, 1, 3) and tuple(vals.shape) == (8,)
+        start_vals = acq(ics)
+        assert bool((vals.cpu() >= start_vals.cpu() - 1e-12).all())
+        mats = ospd.vector_to_symmetric_matrix_mandel(cand[:, 0].cpu()).numpy()
+        assert np.linalg.eigvalsh(mats).min() > 0
+        if type(solver).__name__ == 'StrictConstrainedTrustRegions':
+            assert np.linalg.eigvalsh(mats).max() <= 2.0 + 1e-9

@@ -149,9 +149,30 @@ def _install_spd(monkeypatch):
     monkeypatch.setattr(ops, 'spd_op', spd_op)
 
 
+    def acq_ctr(gp, x0, constraints=(), strict=False, delta_cons=1e-6, maxiter=1000, mingradnorm=1e-6, kappa=0.1,
+                theta=1.0, rho_prime=0.1, rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None, delta0=None):
+        # stand-in of gabo_acq_ctr: the oracle restatement of the reference's [Strict]ConstrainedTrustRegions
+        from oracle import ctr as octr
+        og = _oracle_gp(gp)
+        opts = ortr.TROptions(maxiter=maxiter, mingradnorm=mingradnorm, kappa=kappa, theta=theta, rho_prime=rho_prime,
+                              rho_regularization=rho_regularization, mininner=mininner, maxinner=maxinner,
+                              delta_bar=delta_bar, delta0=delta0)
+        cons = [octr.max_eigenvalue_constraint(b) if k == 'max' else octr.min_eigenvalue_constraint(b)
+                for k, b in constraints]
+        xs, vals, its = [], [], []
+        for p in t64(x0).numpy():
+            x, c, k = octr.solve_ctr(og, p, ineq_constraints=cons, opts=opts, delta_cons=delta_cons, strict=strict)
+            xs.append(x)
+            vals.append(-c)
+            its.append(k)
+        return (torch.from_numpy(np.array(xs)), torch.tensor(vals, dtype=torch.float64),
+                torch.tensor(its, dtype=torch.int32), torch.full((len(its),), 2, dtype=torch.int32))
+    monkeypatch.setattr(ops, 'acq_ctr', acq_ctr)
+
+
 def test_gabo_spd_example_loop_with_emulated_kernels(monkeypatch):
-    # gabo_spd.py's loop: Mandel inputs, ConstrainedTrustRegions with the max-eigenvalue constraint through the
-    # lock-step driver, GP fit on the affine-invariant squared distances
+    # gabo_spd.py's loop: Mandel inputs, ConstrainedTrustRegions with the max-eigenvalue constraint (routed to the
+    # one-launch kernel entry gabo_acq_ctr, emulated here by the oracle), GP fit on the affine-invariant squared distances
     _install(monkeypatch)
     _install_spd(monkeypatch)
     spec = importlib.util.spec_from_file_location('gabo_spd_example', os.path.join(ROOT, 'examples', 'gabo_spd.py'))

@@ -230,6 +230,21 @@ class _OracleOps:
         fn = {_lib.OP_RETR: ospd.retr, _lib.OP_EGRAD2RGRAD: ospd.egrad2rgrad}[op]
         return torch.tensor(np.array([fn(p, u) for p, u in zip(a.numpy(), b.numpy())]))
 
+    def acq_ctr(self, gp, x0, constraints=(), strict=False, delta_cons=1e-6, maxiter=1000, mingradnorm=1e-6, kappa=0.1,
+                theta=1.0, rho_prime=0.1, rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None,
+                delta0=None):
+        # stand-in of the one-launch constrained kernel (gabo_acq_ctr): the oracle's serial solve per restart
+        from oracle import ctr as octr, rtr as ortr
+        opts = ortr.TROptions(maxiter=maxiter, mingradnorm=mingradnorm, kappa=kappa, theta=theta, rho_prime=rho_prime,
+                              rho_regularization=rho_regularization, mininner=mininner, maxinner=maxinner,
+                              delta_bar=delta_bar, delta0=delta0)
+        cons = [octr.max_eigenvalue_constraint(b) if k == 'max' else octr.min_eigenvalue_constraint(b)
+                for k, b in constraints]
+        res = [octr.solve_ctr(self.gp, p, ineq_constraints=cons, opts=opts, delta_cons=delta_cons, strict=strict)
+               for p in torch.as_tensor(x0, dtype=torch.float64).numpy()]
+        return (torch.from_numpy(np.array([r[0] for r in res])), torch.tensor([-r[1] for r in res], dtype=torch.float64),
+                torch.tensor([r[2] for r in res], dtype=torch.int32), torch.full((len(res),), 2, dtype=torch.int32))
+
 
 @pytest.mark.parametrize('manifold,dim,n,R', [('spd', 2, 10, 6), ('spd', 3, 12, 5), ('sphere', 20, 16, 6)])
 def test_lockstep_trust_regions_follow_the_serial_solver(monkeypatch, manifold, dim, n, R):
@@ -253,7 +268,7 @@ def test_lockstep_trust_regions_follow_the_serial_solver(monkeypatch, manifold, 
     for name in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op'):
         monkeypatch.setattr(ops, name, getattr(fake, name))
     handle = type('GP', (), {'manifold': _lib.SPD if manifold == 'spd' else _lib.SPHERE, 'dim': dim, 'n_train': n})()
-    assert not mo._rtr_kernel_covers(handle)
+    assert mo._rtr_kernel_covers(handle) == (manifold == 'spd')       # SPD(d) has its own one-launch kernel now
     X, val, iters, reason = mo.batched_trust_regions(handle, x0, maxiter=12)
     opts = ortr.TROptions(maxiter=12)
     for i in range(R):
@@ -267,8 +282,9 @@ def test_lockstep_trust_regions_follow_the_serial_solver(monkeypatch, manifold, 
 
 
 def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
-    # gen_candidates_manifold: sphere of small dimension -> gabo_acq_rtr (one launch); SPD -> lock-step driver on an
-    # fp64 evaluator (no device needed: the three solve entry points are replaced by recorders)
+    # gen_candidates_manifold: small spheres and SPD(d) -> gabo_acq_rtr (one launch); eigenvalue-constrained SPD solves
+    # -> gabo_acq_ctr (one launch); large spheres and generic constraint callables -> lock-step driver on an fp64
+    # evaluator (no device needed: the solve entry points are replaced by recorders)
     from gabotorch_b200 import _lib, manifold_optimization as mo, ops
     calls = []
 
@@ -287,6 +303,7 @@ def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
         return solve
     monkeypatch.setattr(ops, 'acq_rcg', recorder('rcg'))
     monkeypatch.setattr(ops, 'acq_rtr', recorder('rtr'))
+    monkeypatch.setattr(ops, 'acq_ctr', recorder('ctr'))
     monkeypatch.setattr(mo, 'batched_trust_regions', recorder('lockstep'))
     monkeypatch.setattr(ops, 'to_dev64', lambda x: torch.as_tensor(x, dtype=torch.float64))
 
@@ -301,11 +318,12 @@ def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
     mo.gen_candidates_manifold(spd_x0, acq_for(FakeGP(_lib.SPD, 3, 32)), g.PositiveDefinite(3), mo.ConjugateGradient())
     big = torch.nn.functional.normalize(torch.randn(3, 1, 40, dtype=torch.float64), dim=-1)
     mo.gen_candidates_manifold(big, acq_for(FakeGP(_lib.SPHERE, 40, 16)), g.Sphere(40), mo.TrustRegions())
-    assert [(c[0], c[1]) for c in calls] == [('rtr', _lib.GABO_F32), ('lockstep', _lib.GABO_F64),
+    assert [(c[0], c[1]) for c in calls] == [('rtr', _lib.GABO_F32), ('rtr', _lib.GABO_F32),
                                              ('rcg', _lib.GABO_F32), ('lockstep', _lib.GABO_F64)]
     assert 'kappa' in calls[0][2] and 'kappa' in calls[1][2] and 'contraction' in calls[2][2]
-    # constraints: ConstrainedTrustRegions + inequality constraints -> lock-step driver with the constrained tCG (fp64),
-    # also on a small sphere; without constraints it is the plain solver; everything else is refused
+    # constraints: ConstrainedTrustRegions + eigenvalue constraints on SPD -> the constrained kernel; any other callable
+    # (here on a small sphere, and a lambda on SPD) -> lock-step driver with the constrained tCG (fp64); without
+    # constraints it is the plain solver; everything else is refused
     import functools
     from gabotorch_b200 import riemannian_utils as ru
     cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.0)]
@@ -316,14 +334,21 @@ def test_trust_region_dispatch_chooses_kernel_or_lockstep_in_fp64(monkeypatch):
     mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6),
                                mo.ConstrainedTrustRegions(), inequality_constraints=[lambda x: x[0]])
     mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6), mo.ConstrainedTrustRegions())
-    assert [(c[0], c[1]) for c in calls] == [('lockstep', _lib.GABO_F64), ('lockstep', _lib.GABO_F64),
-                                             ('rtr', _lib.GABO_F32)]
-    assert 'ineq_constraints' in calls[0][2] and 'delta_cons' in calls[0][2] and 'ineq_constraints' not in calls[2][2]
+    mo.gen_candidates_manifold(spd_x0, acq_for(FakeGP(_lib.SPD, 3, 32)), g.PositiveDefinite(3),
+                               mo.ConstrainedTrustRegions(), inequality_constraints=[lambda x: 3.0 - x[0, 0]])
+    assert [(c[0], c[1]) for c in calls] == [('ctr', _lib.GABO_F32), ('lockstep', _lib.GABO_F64),
+                                             ('rtr', _lib.GABO_F32), ('lockstep', _lib.GABO_F64)]
+    assert 'constraints' in calls[0][2] and 'delta_cons' in calls[0][2] and 'strict' in calls[0][2]
+    assert 'ineq_constraints' in calls[1][2] and 'ineq_constraints' not in calls[2][2]
+    assert mo.eigenvalue_constraint_specs(cons) == [('max', 3.0)]
+    assert mo.eigenvalue_constraint_specs(cons + [functools.partial(ru.min_eigenvalue_constraint_torch, 0.01)]) == \
+        [('max', 3.0), ('min', 0.01)]
+    assert mo.eigenvalue_constraint_specs(cons * 3) is None and mo.eigenvalue_constraint_specs([len]) is None
     calls.clear()
     mo.gen_candidates_manifold(spd_x0, acq_for(FakeGP(_lib.SPD, 3, 32)), g.PositiveDefinite(3),
                                mo.StrictConstrainedTrustRegions(mingradnorm=2e-4, maxiter=100, minstepsize=1e-4),
                                approx_hessian=True, inequality_constraints=cons)
-    assert calls[0][:2] == ('lockstep', _lib.GABO_F64) and 'strict' in calls[0][2]
+    assert calls[0][0] == 'ctr' and 'strict' in calls[0][2]
     with pytest.raises(NotImplementedError):
         mo.gen_candidates_manifold(sphere_x0, acq_for(FakeGP(_lib.SPHERE, 6, 32)), g.Sphere(6), mo.TrustRegions(),
                                    inequality_constraints=cons)
@@ -414,7 +439,7 @@ def test_gabo_spd_iteration_through_the_public_api_with_emulated_kernels(monkeyp
     y = ospd.ackley(ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(xt)))
     gp = ogp.make_gp('spd', xt, y, beta=0.5 + math.log(2.0), noise=1e-2)
     fake = _OracleOps(gp)
-    for attr in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op'):
+    for attr in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op', 'acq_ctr'):
         monkeypatch.setattr(ops, attr, getattr(fake, attr))
     monkeypatch.setattr(ops, 'device', lambda: torch.device('cpu'))
     monkeypatch.setattr(ops, 'mandel_unpack', lambda v: ospd.vector_to_symmetric_matrix_mandel(torch.as_tensor(v)))
