@@ -291,7 +291,7 @@ def test_lockstep_trust_regions_on_device_vs_oracle(manifold, dim, n, R):
         rng, gp = sphere_problem(dim, n, beta=0.35 + math.log(2.0), noise=1e-2, seed=22)
         x0 = osph.rand(rng, R, dim)
     dgp = device_gp(gp, _lib.GABO_F64)
-    assert not mo._rtr_kernel_covers(dgp)
+    assert mo._rtr_kernel_covers(dgp) == (manifold == 'spd')      # SPD(d) also has the one-launch kernel (tested below)
     X, val, iters, reason = mo.batched_trust_regions(dgp, x0, maxiter=15)
     X, val, iters = X.cpu().numpy(), val.cpu().numpy(), iters.cpu().numpy()
     ei0 = np.array([ogp.ei_and_grad(gp, xi, want_grad=False)[0] for xi in x0])
