@@ -891,6 +891,12 @@ class Bench:
             if self.rank == 0:
                 emit({'extra': out})
             return 0
+        if args.only == 'trspd':                  # developer switch: the one-launch constrained trust regions on SPD(3)
+            out = [self.guarded(self.extra_acq_tr_spd, True, R=4096, lockstep=False)]
+            self.clocks.stop()
+            if self.rank == 0:
+                emit({'extra': out})
+            return 0
         if args.only == 'scale':                  # developer switch: the sharded (multi-GPU) extras only
             out = [self.guarded(self.extra_acq_spd, 4096, 200), self.guarded(self.extra_spd_strong),
                    self.guarded(self.extra_sphere_strong), self.guarded(self.extra_sphere_strong, gather=True),
