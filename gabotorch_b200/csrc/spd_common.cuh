@@ -474,6 +474,100 @@ __device__ __forceinline__ float2 sum_log2_sq_x2(const float2 (&lam)[d]) {
     return s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Closed-form eigenvalues for d = 2, 3 with the RELATIVE accuracy the log-distance needs ("bilateral" form).
+// The trigonometric formula gives the eigenvalues of a symmetric 3 x 3 matrix M with an ABSOLUTE error of a few
+// eps |M| -- fine for the largest eigenvalue, useless for the smallest one of an ill-conditioned W = G G^T (the
+// tolerance on d needs ~1e-5 relative on every eigenvalue).  So only LARGEST eigenvalues are taken from it:
+//     lambda_max(W)        from M1 = G G^T,
+//     1 / lambda_min(W)    = lambda_max(W^-1) from M2 = H^T H,  H = G^-1 = L_j^-1 L_i  (the factor records hold L and
+//                            L^-1 of both points, so H is a second triangular product, not an inversion),
+//     lambda_mid(W)        = det W / (lambda_max lambda_min),  det W = (g00 g11 g22)^2 exactly (G is triangular).
+// When the two largest (or two smallest) eigenvalues nearly coincide the angle of the trigonometric formula is
+// ill-conditioned (error ~ sqrt(eps)), but the determinant identity moves the middle eigenvalue by the opposite
+// relative amount, and sum log^2 is stationary under such a split: the error enters d^2 only as p^2 * eps-ish
+// (scripts/dev_closed3.py checks the bound of SURVEY 8(d) in float32 emulation on the benchmark law, near-identical
+// pairs, double / triple eigenvalues, cond up to 5000 per matrix).  ~95 issue slots per pair against ~520 for the
+// Jacobi sweeps (ncu, N = 2048).  Two problems per thread on the packed fp32x2 pipe (.x / .y).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float2 log2_2(float2 v) { return make_float2(__log2f(v.x), __log2f(v.y)); }
+
+// Largest eigenvalue of the symmetric matrix [[m00 m01 m02], [m01 m11 m12], [m02 m12 m22]]:
+//   q = tr/3, p^2 = |M - qI|_F^2 / 6, r = det((M - qI)/p)/2 = cos(3 phi), lambda_max = q + 2 p cos(phi),
+//   cos(phi) = g(s) with s = sqrt((1 + r)/2) = cos(3 phi / 2):  g(s) = cos(2/3 acos s) is analytic on [0, 1]
+//   (degree-8 polynomial, |error| < 1.2e-7 in fp32), so no acos / cos evaluation is needed.
+__device__ __forceinline__ float2 sym3_lam_max_x2(float2 m00, float2 m11, float2 m22, float2 m01, float2 m02,
+                                                  float2 m12) {
+    const float2 q = mul2(add2(add2(m00, m11), m22), splat2(0.333333343267440796f));
+    const float2 b00 = sub2(m00, q), b11 = sub2(m11, q), b22 = sub2(m22, q);
+    float2 off = mul2(m01, m01);
+    off = fma2(m02, m02, off);
+    off = fma2(m12, m12, off);
+    float2 dg = mul2(b00, b00);
+    dg = fma2(b11, b11, dg);
+    dg = fma2(b22, b22, dg);
+    float2 p2 = fma2(off, splat2(0.333333343267440796f), mul2(dg, splat2(0.166666671633720398f)));
+    p2 = make_float2(fmaxf(p2.x, 1e-37f), fmaxf(p2.y, 1e-37f));
+    const float2 ip = rsqrt2(p2);
+    const float2 c00 = mul2(b00, ip), c11 = mul2(b11, ip), c22 = mul2(b22, ip);
+    const float2 c01 = mul2(m01, ip), c02 = mul2(m02, ip), c12 = mul2(m12, ip);
+    const float2 t0 = fma2(c11, c22, neg2(mul2(c12, c12)));
+    const float2 t1 = fma2(c12, c02, neg2(mul2(c01, c22)));
+    const float2 t2 = fma2(c01, c12, neg2(mul2(c11, c02)));
+    const float2 det = fma2(c02, t2, fma2(c01, t1, mul2(c00, t0)));
+    float2 s2 = fma2(det, splat2(0.25f), splat2(0.5f));                    // (1 + r) / 2
+    s2 = make_float2(fminf(fmaxf(s2.x, 0.0f), 1.0f), fminf(fmaxf(s2.y, 0.0f), 1.0f));
+    const float2 sv = make_float2(sqrt_approx(s2.x), sqrt_approx(s2.y));
+    float2 g = splat2(-6.393143697e-04f);
+    g = fma2(g, sv, splat2(3.707686486e-03f));
+    g = fma2(g, sv, splat2(-1.032549309e-02f));
+    g = fma2(g, sv, splat2(1.967571822e-02f));
+    g = fma2(g, sv, splat2(-3.196129547e-02f));
+    g = fma2(g, sv, splat2(5.328865600e-02f));
+    g = fma2(g, sv, splat2(-1.110956833e-01f));
+    g = fma2(g, sv, splat2(5.773497198e-01f));
+    g = fma2(g, sv, splat2(5.000000033e-01f));
+    const float2 p = mul2(p2, ip);                                         // sqrt(p2)
+    return fma2(add2(p, p), g, q);
+}
+
+// sum_k log2(lambda_k(G G^T))^2 for lower-triangular G (packed row-major: g00 | g10 g11 | g20 g21 g22) and H = G^-1.
+template <int d>
+__device__ __forceinline__ float2 closed_form_log2_sq_x2(const float2 (&G)[tri_size(d)], const float2 (&H)[tri_size(d)]) {
+    static_assert(d == 2 || d == 3, "closed forms exist for d = 2, 3");
+    if constexpr (d == 2) {
+        const float2 a = mul2(G[0], G[0]), b = fma2(G[1], G[1], mul2(G[2], G[2])), c = mul2(G[0], G[1]);
+        const float2 h = sub2(a, b), c2 = add2(c, c);
+        const float2 disc = fma2(h, h, mul2(c2, c2));
+        const float2 root = make_float2(sqrt_approx(disc.x), sqrt_approx(disc.y));
+        const float2 l1 = log2_2(mul2(add2(add2(a, b), root), splat2(0.5f)));       // larger eigenvalue: no cancellation
+        const float2 ld = log2_2(mul2(G[0], G[2]));
+        const float2 l2 = sub2(add2(ld, ld), l1);                                  // log2(det / lambda_1)
+        return fma2(l1, l1, mul2(l2, l2));
+    } else {
+        // M1 = G G^T
+        const float2 m00 = mul2(G[0], G[0]);
+        const float2 m11 = fma2(G[1], G[1], mul2(G[2], G[2]));
+        const float2 m22 = fma2(G[3], G[3], fma2(G[4], G[4], mul2(G[5], G[5])));
+        const float2 m01 = mul2(G[0], G[1]), m02 = mul2(G[0], G[3]);
+        const float2 m12 = fma2(G[1], G[3], mul2(G[2], G[4]));
+        const float2 l1 = sym3_lam_max_x2(m00, m11, m22, m01, m02, m12);
+        // M2 = H^T H
+        const float2 n00 = fma2(H[0], H[0], fma2(H[1], H[1], mul2(H[3], H[3])));
+        const float2 n11 = fma2(H[2], H[2], mul2(H[4], H[4]));
+        const float2 n22 = mul2(H[5], H[5]);
+        const float2 n01 = fma2(H[1], H[2], mul2(H[3], H[4]));
+        const float2 n02 = mul2(H[3], H[5]), n12 = mul2(H[4], H[5]);
+        const float2 mu = sym3_lam_max_x2(n00, n11, n22, n01, n02, n12);
+        const float2 a = log2_2(l1);
+        const float2 c = neg2(log2_2(mu));
+        const float2 ld = log2_2(mul2(mul2(G[0], G[2]), G[5]));
+        const float2 b = sub2(sub2(add2(ld, ld), a), c);
+        return fma2(a, a, fma2(b, b, mul2(c, c)));
+    }
+}
+
 // G = A * L for packed lower-triangular A (rows) and L, accumulated in fp64, returned in T.
 template <int d, typename T, typename AccA, typename AccL>
 __device__ __forceinline__ void tri_product(AccA A, AccL L, T (&G)[d][d]) {

@@ -156,6 +156,9 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int FS = factor_stride(d);
     constexpr bool kLInRegs = (d <= 5);
     constexpr bool kX2 = PairCfg<d>::kPacked && sizeof(T) == 4;   // two pairs per thread on the fp32x2 pipe
+    // d = 2, 3 in fp32: closed-form eigenvalues (spd_common.cuh, closed_form_log2_sq_x2) instead of Jacobi sweeps
+    constexpr bool kClosed = kX2 && (d == 2 || d == 3);
+    constexpr bool kNeedH = kClosed && d == 3;                    // H = G^-1 = A_j L_i
     constexpr int kMaxTileM = PairCfg<d>::kMaxTileM;
     __shared__ __align__(16) double fs[2][kMaxTileM * FS];              // staged x1 records (we read the A halves)
     __shared__ double ls[kLInRegs ? 1 : TRI * kThreads];                // L_j, entry-major (conflict-free), d >= 6 only
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     int64_t jb_loaded = -1;
     double Lreg[kLInRegs ? TRI : 1];
+    double Areg[kNeedH ? TRI : 1];                                  // A_j = L_j^-1 (closed form, d = 3)
     int64_t j = 0;
     bool jvalid = false;
 
@@ -240,6 +244,10 @@ __global__ void __launch_bounds__(kThreads)
             if (kLInRegs) {
 #pragma unroll
                 for (int e = 0; e < (kLInRegs ? TRI : 1); ++e) Lreg[e] = __ldg(src + e);
+                if (kNeedH) {
+#pragma unroll
+                    for (int e = 0; e < (kNeedH ? TRI : 1); ++e) Areg[e] = __ldg(src + TRI + e);
+                }
             } else {
 #pragma unroll
                 for (int e = 0; e < TRI; ++e) ls[e * kThreads + threadIdx.x] = __ldg(src + e);
@@ -260,7 +268,50 @@ __global__ void __launch_bounds__(kThreads)
         };
         auto Lj = [&](int e) { return kLInRegs ? Lreg[kLInRegs ? e : 0] : ls[e * kThreads + threadIdx.x]; };
 
-        if (kX2) {
+        if constexpr (kClosed) {
+            // two rows of the tile per step, same column; triangular products in fp64, everything else packed fp32x2
+            for (int i = 0; i < rows; i += 2) {
+                const int i1 = min(i + 1, rows - 1);            // odd tail: the partner repeats row i (not stored)
+                const double* R0 = &fs[buf][i * FS];            // record of row i: [L_i | A_i]
+                const double* R1 = &fs[buf][i1 * FS];
+                float2 G[TRI], H[TRI];
+#pragma unroll
+                for (int r = 0; r < d; ++r) {
+#pragma unroll
+                    for (int c = 0; c <= r; ++c) {
+                        double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
+#pragma unroll
+                        for (int k = c; k <= r; ++k) {
+                            const double l = Lj(tri_idx(k, c));
+                            s0 = fma(R0[TRI + tri_idx(r, k)], l, s0);           // G = A_i L_j
+                            s1 = fma(R1[TRI + tri_idx(r, k)], l, s1);
+                            if (kNeedH) {
+                                const double a = Areg[kNeedH ? tri_idx(r, k) : 0];
+                                h0 = fma(a, R0[tri_idx(k, c)], h0);              // H = A_j L_i
+                                h1 = fma(a, R1[tri_idx(k, c)], h1);
+                            }
+                        }
+                        G[tri_idx(r, c)] = make_float2(static_cast<float>(s0), static_cast<float>(s1));
+                        H[tri_idx(r, c)] = make_float2(static_cast<float>(h0), static_cast<float>(h1));
+                    }
+                }
+                // spd_utils_torch.py:117-120 in fp32: d^2 = sum log(lambda)^2 + 1e-15, log = ln2 * log2 (MUFU)
+                const float2 d2 = fma2(closed_form_log2_sq_x2<d>(G, H), splat2(0.48045301391820142f), splat2(1e-15f));
+                float2 v;
+                if (KIND == GABO_KIND_GAUSS) {
+                    const float2 t = fma2(d2, splat2(kp.k_hi), mul2(d2, splat2(kp.k_lo)));   // kernels_spd.py:96-98
+                    v = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                } else {
+                    v = make_float2(sqrt_approx(d2.x), sqrt_approx(d2.y));
+                    if (KIND == GABO_KIND_LAPLACE) {
+                        const float2 t = fma2(v, splat2(kp.k_hi), mul2(v, splat2(kp.k_lo)));  // kernels_spd.py:185
+                        v = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+                    }
+                }
+                store(i0 + i, v.x);
+                if (i1 != i) store(i0 + i1, v.y);
+            }
+        } else if constexpr (kX2) {
             // two rows of the tile per step, same column: (A_i, A_i+1) x L_j on the packed fp32x2 pipe
             for (int i = 0; i < rows; i += 2) {
                 const int i1 = min(i + 1, rows - 1);            // odd tail: the partner repeats row i (not stored)

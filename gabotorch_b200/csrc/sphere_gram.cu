@@ -87,13 +87,36 @@ __device__ __forceinline__ float far_side(float r2) {   // (pi - sqrt(r2)), the 
     return (3.14159274101257324f - r) + (-8.74227765734758577e-8f);
 }
 
-// Same arithmetic as tail<KIND>() for the two inner products (c0, c1).
-template <int KIND>
+// fp64 -> fp32 of w2 = 1 - |c| WITHOUT the conversion unit.  ncu on the N = 32768 launch: the XU pipe (MUFU and
+// F2F.F32.F64, 16 lanes per SM) was the busiest unit of the fp32-output kernel -- 3 XU operations per pair (conversion,
+// far-side root, 2^t) cap the kernel at 5.3 pairs per clock per SM, below what HBM takes (5.6).  The conversion is done
+// on the ALU pipe instead: clamp the high word (signed compare: negative, zero and tiny values all land on the
+// reference's clamp 1 - (1 - 1e-15) = 0x3CD20000'00000000), then the float pattern is the double's exponent re-biased
+// (E - 896; for E in [897, 1023] that is "clear the two top bits of the 9 low exponent bits") in front of the top 23
+// mantissa bits: one funnel shift and one add.  Truncation instead of rounding: relative error < 1.2e-7 on w2.
+// Only for FINITE inputs: a NaN would come out as 1.5, so the callers take this path only for tiles whose points they
+// have checked (warp-uniform), everything else runs the converting form above.
+__device__ __forceinline__ float w2_bits(double c) {
+    const double w = 1.0 - fabs(c);
+    const int hi = max(__double2hiint(w), 0x3CD20000);
+    return __uint_as_float(__funnelshift_l(static_cast<unsigned>(__double2loint(w)), static_cast<unsigned>(hi), 3) +
+                           0x40000000u);
+}
+
+// Same arithmetic as tail<KIND>() for the two inner products (c0, c1).  kFast: see w2_bits.
+template <int KIND, bool kFast = false>
 __device__ __forceinline__ float2 tail2(double c0, double c1, const TailParams& tp) {
     constexpr float kClampW = 9.992007221626409e-16f;
-    float w0 = static_cast<float>(1.0 - fabs(c0)), w1 = static_cast<float>(1.0 - fabs(c1));
-    w0 = (w0 < kClampW) ? kClampW : w0;
-    w1 = (w1 < kClampW) ? kClampW : w1;
+    float w0, w1;
+    if (kFast) {
+        w0 = w2_bits(c0);
+        w1 = w2_bits(c1);
+    } else {
+        w0 = static_cast<float>(1.0 - fabs(c0));
+        w1 = static_cast<float>(1.0 - fabs(c1));
+        w0 = (w0 < kClampW) ? kClampW : w0;
+        w1 = (w1 < kClampW) ? kClampW : w1;
+    }
     if (KIND == GABO_KIND_GAUSS) {   // fused exponent (see TailParams): 10 packed FMAs + the far-side fix-up
         const float2 w = make_float2(w0, w1);
         float2 p = splat2(tp.pc[0]);
@@ -221,6 +244,7 @@ __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __r
     constexpr bool kPairLayout = sizeof(OutT) == 8;
     int valid = 0, valid_hi = 0;
     int64_t j_first = 0;
+    bool b_finite = true;   // the x2 columns of this thread are finite (fast row loop, see below)
 
     for (int64_t t = t_begin; t < t_end; ++t) {
         const int buf = static_cast<int>((t - t_begin) & 1);
@@ -250,6 +274,12 @@ __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __r
 #pragma unroll
                 for (int k = 0; k < D; ++k) b[q][k] = __ldg(x2 + j * D + k);
             }
+            b_finite = true;
+#pragma unroll
+            for (int q = 0; q < kVec; ++q)
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    b_finite = b_finite && ((__double2hiint(b[q][k]) & 0x7ff00000) != 0x7ff00000);
         }
 
         if (bulk_cur) {
@@ -259,9 +289,41 @@ __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __r
             __syncthreads();
         }
 
-        if (valid > 0) {
-            OutT* orow = out + i0 * ld_out + j_first;
+        // Warp-uniform choice of the row loop.  Fast form: every lane of the warp owns only valid columns, vector stores
+        // are possible and neither the x2 columns of this warp nor the rows of this tile hold a NaN / Inf (checked here:
+        // each lane looks at rows * D / 32 staged values) -- it converts on the ALU pipe (w2_bits) and has no per-row
+        // edge branches.  Everything else (ragged edges, unaligned output, non-finite points) takes the general form.
+        bool fast = vec_ok && b_finite && (kPairLayout ? (valid == 2 && valid_hi == 2) : (valid == kVec));
+        {
+            bool row_ok = true;
+            for (int e = threadIdx.x & 31; e < rows * D; e += 32)
+                row_ok = row_ok && ((__double2hiint(xs[buf][e]) & 0x7ff00000) != 0x7ff00000);
+            fast = __all_sync(0xffffffffu, fast && row_ok);
+        }
+        OutT* orow = out + i0 * ld_out + j_first;
+        if (fast) {
 #pragma unroll 2
+            for (int i = 0; i < rows; ++i, orow += ld_out) {
+                double a[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) a[k] = xs[buf][i * D + k];
+                double c[kVec];
+#pragma unroll
+                for (int q = 0; q < kVec; ++q) {
+                    c[q] = a[0] * b[q][0];
+#pragma unroll
+                    for (int k = 1; k < D; ++k) c[q] = fma(a[k], b[q][k], c[q]);
+                }
+                const float2 v01 = tail2<KIND, true>(c[0], c[1], tp), v23 = tail2<KIND, true>(c[2], c[3], tp);
+                if (kPairLayout) {
+                    st_cs2(reinterpret_cast<double*>(orow), static_cast<double>(v01.x), static_cast<double>(v01.y));
+                    st_cs2(reinterpret_cast<double*>(orow) + 64, static_cast<double>(v23.x), static_cast<double>(v23.y));
+                } else {
+                    st_cs4(reinterpret_cast<float*>(orow), v01.x, v01.y, v23.x, v23.y);
+                }
+            }
+        } else if (valid > 0) {
+#pragma unroll 1
             for (int i = 0; i < rows; ++i, orow += ld_out) {
                 double a[D];
 #pragma unroll

@@ -206,6 +206,41 @@ def test_spd_gram_full_size_properties():
     assert float(lam_min) > -5e-7                              # PD at beta >= beta_min (spd_gaussian_kernel_parameters.py:50-53)
 
 
+@pytest.mark.parametrize('d', [2, 3])
+def test_spd_gram_closed_form_hard_cases(d):
+    # d = 2, 3 in fp32 take closed-form eigenvalues (largest of W and of W^-1, the middle one from det W): the cases
+    # where a trigonometric / quadratic formula is fragile, all pairs against the oracle
+    rng = np.random.default_rng(77 + d)
+    sets = {}
+    base = ospd.spd_sample(rng, 1, d, max_cond=100.0)[0]
+    near = [base]
+    for eps in (1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-9, 1e-12):
+        for _ in range(12):
+            e = rng.standard_normal((d, d))
+            near.append(base + 0.5 * (e + e.T) * eps)
+    sets['near-identical'] = np.stack(near)
+    q, _ = np.linalg.qr(rng.standard_normal((96, d, d)))
+    lam = []
+    for a in (0.01, 0.1, 1.0, 3.0):
+        for b in (0.011, 0.5, 1.0001, 1.0 + 1e-7, 5.0):
+            lam += [[a] * (d - 1) + [b], [b] + [a] * (d - 1), [a] * d]
+    lam = np.array(lam)[:96]
+    sets['double / triple eigenvalues'] = (q[:len(lam)] * lam[:, None, :]) @ np.swapaxes(q[:len(lam)], -1, -2)
+    sets['cond up to 5000'] = ospd.spd_sample(rng, 160, d, max_cond=1e9)
+    sets['diagonal (commuting)'] = np.stack([np.diag(rng.uniform(0.001, 5, d)) for _ in range(64)])
+    sets['scaled identities'] = np.stack([np.eye(d) * s for s in (1e-3, 0.5, 1.0, 2.0, 1e3)])
+    beta = 0.5 + math.log(2.0)
+    for name, X in sets.items():
+        X = 0.5 * (X + np.swapaxes(X, -1, -2))
+        dref = ospd.affine_invariant_distance(X, X).numpy()
+        dg = ops.spd_ai_gram(X, X.copy(), kind=_lib.KIND_DIST, is_mandel=False).cpu().numpy()
+        err = np.abs(dg - dref) - (1e-5 * dref + 1e-6)
+        assert err.max() <= 0, '%s: distance bound violated by %.3e' % (name, err.max())
+        kg = ops.spd_ai_gram(X, X.copy(), beta, _lib.KIND_GAUSS, is_mandel=False).cpu().numpy()
+        check_kernel(kg, np.exp(-beta * dref * dref), amplification=2.0 * beta * dref * dref)
+        assert np.abs(np.diag(dg) - math.sqrt(1e-15)).max() < 1e-6
+
+
 @pytest.mark.parametrize('d,beta_min', [(3, 0.5), (8, 0.22)])
 def test_spd_gram_full_matrix_parity_at_the_benchmarked_size(d, beta_min):
     # BASELINE configs[1] (SPD(3), N = 2048: the configuration bench.py times) and the SPD(8) extra: EVERY one of the
