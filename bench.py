@@ -441,13 +441,21 @@ class Bench:
                     'peak': self.hbm_peak, 'unit': 'GB/s', 'frac': achieved / self.hbm_peak,
                     'traffic': self.ncu_traffic('spd_ai_gram_kernel<3, float, double, 0>'),
                     'peak_source': self.peak_src, 'ms_per_launch': roof_ms, 'algorithmic_bytes_per_launch': alg_bytes,
-                    'note': 'the per-pair Jacobi solve is FP32-pipe bound (about 0.6 kFLOP per 8 output bytes): '
+                    'note': 'the per-pair eigenvalue solve is instruction-bound (about 115 FLOP per 8 output bytes): '
                             'see compute_roofline; the HBM fraction is reported because the contract asks for it'}
-        flop_per_pair = 620.0       # sandwich + one-sided Jacobi sweeps + logs at d = 3
+        # Executed arithmetic of the closed-form SPD(3) solve (ncu opcode mix of the N = 8192 launch, profiles/r02*):
+        # per pair 28 FFMA + 21 FMUL + 5 FADD (packed two pairs per instruction) + 11 DFMA/DMUL + 8 MUFU = ~115 FLOP.
+        # Round 1's Jacobi sweeps needed ~620 algorithmic (~1200 executed) FLOP per pair for the same result.
+        flop_per_pair = 115.0
         sm_mhz = self.peaks.get('sm_max_mhz', 1965.0)
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         compute = {'bound': 'fp32', 'achieved': pairs * flop_per_pair / (roof_ms * 1e-3) / 1e12, 'peak': fp32_peak,
-                   'unit': 'TFLOP/s', 'flop_per_pair': flop_per_pair}
+                   'unit': 'TFLOP/s', 'flop_per_pair': flop_per_pair,
+                   'jacobi_equivalent_tflops': pairs * 620.0 / (roof_ms * 1e-3) / 1e12,
+                   'note': 'closed-form eigenvalues (largest of W and of adj W by the trigonometric formula, middle one '
+                           'from det W): 5x fewer FLOP per pair than the Jacobi sweeps of round 1, so the FP32 fraction '
+                           'falls while the time per Gram drops 3x; ncu: issue slots 57 %, FMA pipe 55 %, XU pipe 58 % '
+                           '-- no single pipe binds, the mix does'}
         compute['frac'] = compute['achieved'] / fp32_peak
 
         # e2e through the reference-facing API: pinned host tensors in, host float64 Gram out
@@ -954,7 +962,7 @@ class Bench:
                            'sharding': 'row blocks of ONE (%d x %d) Gram: rank g builds rows [%d g, %d (g+1)) of x1 against '
                                        'the replicated x2, no data-path collective (weak scaling: %d x %d pairs per GPU)'
                                        % (N_POINTS * self.world, N_POINTS, N_POINTS, N_POINTS, N_POINTS, N_POINTS),
-                           'arithmetic': 'fp64 per-point Cholesky, fp32 per-pair Jacobi, fp64 exp argument',
+                           'arithmetic': 'fp64 per-point Cholesky, fp64 triangular product per pair, fp32 closed-form eigenvalues (d = 3), 2^t on the MUFU',
                            'parity_vs_oracle_all_pairs': parity},
                 'roofline': head['roofline'], 'compute_roofline': head['compute'], 'cpu_baseline': cpu,
                 'e2e': head['e2e'], 'gpu_launches': head['launches'], 'clocks': clocks, 'extra': extras,

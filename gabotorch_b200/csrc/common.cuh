@@ -125,6 +125,21 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// log2 on the MUFU without the denormal pre-scaling of __log2f (3 extra instructions per call); inputs here are
+// eigenvalue-sized (never denormal); a flushed zero gives -inf like the slow path would for 0.
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Exact float -> double widening of a NON-NEGATIVE finite float on the ALU pipe (the converting instruction F2F.F64.F32
+// runs on the 16-lane XU pipe, which the per-pair kernels saturate first): exponent re-biased by +896 in front of the
+// mantissa shifted down by 3.  A float zero (a kernel value below 1.2e-38 that the MUFU flushed) widens to 2^-127 instead
+// of 0 -- the mathematical value exp(-beta d^2) is positive anyway, and the branch-free form saves a compare + select.
+__device__ __forceinline__ double widen_nonneg(float v) {
+    const unsigned b = __float_as_uint(v);
+    return __hiloint2double(static_cast<int>((b >> 3) + 0x38000000u), static_cast<int>(b << 29));
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

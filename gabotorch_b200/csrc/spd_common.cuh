@@ -479,27 +479,30 @@ __device__ __forceinline__ float2 sum_log2_sq_x2(const float2 (&lam)[d]) {
 // The trigonometric formula gives the eigenvalues of a symmetric 3 x 3 matrix M with an ABSOLUTE error of a few
 // eps |M| -- fine for the largest eigenvalue, useless for the smallest one of an ill-conditioned W = G G^T (the
 // tolerance on d needs ~1e-5 relative on every eigenvalue).  So only LARGEST eigenvalues are taken from it:
-//     lambda_max(W)        from M1 = G G^T,
-//     1 / lambda_min(W)    = lambda_max(W^-1) from M2 = H^T H,  H = G^-1 = L_j^-1 L_i  (the factor records hold L and
-//                            L^-1 of both points, so H is a second triangular product, not an inversion),
-//     lambda_mid(W)        = det W / (lambda_max lambda_min),  det W = (g00 g11 g22)^2 exactly (G is triangular).
+//     lambda_max(W)              from M1 = G G^T,
+//     det W / lambda_min(W)      = lambda_max(adj(G)^T adj(G)) from M2: adj(G) = det(G) G^-1 of the lower-triangular G is
+//                                  five plain products of its entries plus ONE entry with a cancellation,
+//                                  x = g10 g21 - g20 g11, which the caller forms in fp64 before rounding,
+//     lambda_mid(W)              = det W / (lambda_max lambda_min),  det W = (g00 g11 g22)^2 exactly (G is triangular).
 // When the two largest (or two smallest) eigenvalues nearly coincide the angle of the trigonometric formula is
 // ill-conditioned (error ~ sqrt(eps)), but the determinant identity moves the middle eigenvalue by the opposite
 // relative amount, and sum log^2 is stationary under such a split: the error enters d^2 only as p^2 * eps-ish
 // (scripts/dev_closed3.py checks the bound of SURVEY 8(d) in float32 emulation on the benchmark law, near-identical
-// pairs, double / triple eigenvalues, cond up to 5000 per matrix).  ~95 issue slots per pair against ~520 for the
-// Jacobi sweeps (ncu, N = 2048).  Two problems per thread on the packed fp32x2 pipe (.x / .y).
+// pairs, double / triple eigenvalues, cond up to 5000 per matrix; tests/test_gram_gpu.py does it on the device).
+// Two problems per thread on the packed fp32x2 pipe (.x / .y).  Intermediate quantities reach |G|^8: the caller
+// checks closed_form_in_range() and sends anything else through the Jacobi sweeps.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
-__device__ __forceinline__ float2 log2_2(float2 v) { return make_float2(__log2f(v.x), __log2f(v.y)); }
+__device__ __forceinline__ float2 log2_2(float2 v) { return make_float2(lg2_approx(v.x), lg2_approx(v.y)); }
 
 // Largest eigenvalue of the symmetric matrix [[m00 m01 m02], [m01 m11 m12], [m02 m12 m22]]:
 //   q = tr/3, p^2 = |M - qI|_F^2 / 6, r = det((M - qI)/p)/2 = cos(3 phi), lambda_max = q + 2 p cos(phi),
 //   cos(phi) = g(s) with s = sqrt((1 + r)/2) = cos(3 phi / 2):  g(s) = cos(2/3 acos s) is analytic on [0, 1]
-//   (degree-8 polynomial, |error| < 1.2e-7 in fp32), so no acos / cos evaluation is needed.
+//   (degree-8 polynomial, |error| < 1.2e-7 in fp32), so no acos / cos evaluation is needed.  q is returned as well
+//   (range check of the caller).
 __device__ __forceinline__ float2 sym3_lam_max_x2(float2 m00, float2 m11, float2 m22, float2 m01, float2 m02,
-                                                  float2 m12) {
-    const float2 q = mul2(add2(add2(m00, m11), m22), splat2(0.333333343267440796f));
+                                                  float2 m12, float2& q) {
+    q = mul2(add2(add2(m00, m11), m22), splat2(0.333333343267440796f));
     const float2 b00 = sub2(m00, q), b11 = sub2(m11, q), b22 = sub2(m22, q);
     float2 off = mul2(m01, m01);
     off = fma2(m02, m02, off);
@@ -510,40 +513,54 @@ __device__ __forceinline__ float2 sym3_lam_max_x2(float2 m00, float2 m11, float2
     float2 p2 = fma2(off, splat2(0.333333343267440796f), mul2(dg, splat2(0.166666671633720398f)));
     p2 = make_float2(fmaxf(p2.x, 1e-37f), fmaxf(p2.y, 1e-37f));
     const float2 ip = rsqrt2(p2);
-    const float2 c00 = mul2(b00, ip), c11 = mul2(b11, ip), c22 = mul2(b22, ip);
-    const float2 c01 = mul2(m01, ip), c02 = mul2(m02, ip), c12 = mul2(m12, ip);
-    const float2 t0 = fma2(c11, c22, neg2(mul2(c12, c12)));
-    const float2 t1 = fma2(c12, c02, neg2(mul2(c01, c22)));
-    const float2 t2 = fma2(c01, c12, neg2(mul2(c11, c02)));
-    const float2 det = fma2(c02, t2, fma2(c01, t1, mul2(c00, t0)));
-    float2 s2 = fma2(det, splat2(0.25f), splat2(0.5f));                    // (1 + r) / 2
-    s2 = make_float2(fminf(fmaxf(s2.x, 0.0f), 1.0f), fminf(fmaxf(s2.y, 0.0f), 1.0f));
-    const float2 sv = make_float2(sqrt_approx(s2.x), sqrt_approx(s2.y));
-    float2 g = splat2(-6.393143697e-04f);
-    g = fma2(g, sv, splat2(3.707686486e-03f));
-    g = fma2(g, sv, splat2(-1.032549309e-02f));
-    g = fma2(g, sv, splat2(1.967571822e-02f));
-    g = fma2(g, sv, splat2(-3.196129547e-02f));
-    g = fma2(g, sv, splat2(5.328865600e-02f));
-    g = fma2(g, sv, splat2(-1.110956833e-01f));
-    g = fma2(g, sv, splat2(5.773497198e-01f));
-    g = fma2(g, sv, splat2(5.000000033e-01f));
+    // r = det(B) / (2 p^3) with the UNSCALED B = M - qI (three multiplies instead of six; |det B| <= 2 p^3 stays inside
+    // the fp32 range because the caller keeps q in [1e-6, 1e9], and a det that underflows belongs to a p below 2e-13,
+    // i.e. to a correction of lambda below 2e-7 q)
+    const float2 t0 = fma2(b11, b22, neg2(mul2(m12, m12)));
+    const float2 t1 = fma2(m12, m02, neg2(mul2(m01, b22)));
+    const float2 t2 = fma2(m01, m12, neg2(mul2(b11, m02)));
+    const float2 det = fma2(m02, t2, fma2(m01, t1, mul2(b00, t0)));
+    // scaled one factor at a time: ip^3 alone overflows when p^2 sits at its floor (M = qI: det = 0, ip = 3e18)
+    const float2 s2 = fma2(mul2(mul2(det, ip), ip), mul2(ip, splat2(0.25f)), splat2(0.5f));   // (1 + r) / 2
+    const float2 sv = make_float2(sqrt_approx(__saturatef(s2.x)), sqrt_approx(__saturatef(s2.y)));
+    float2 g = splat2(2.0f * -6.393143697e-04f);                           // 2 g(s): lambda = q + p (2 cos phi)
+    g = fma2(g, sv, splat2(2.0f * 3.707686486e-03f));
+    g = fma2(g, sv, splat2(2.0f * -1.032549309e-02f));
+    g = fma2(g, sv, splat2(2.0f * 1.967571822e-02f));
+    g = fma2(g, sv, splat2(2.0f * -3.196129547e-02f));
+    g = fma2(g, sv, splat2(2.0f * 5.328865600e-02f));
+    g = fma2(g, sv, splat2(2.0f * -1.110956833e-01f));
+    g = fma2(g, sv, splat2(2.0f * 5.773497198e-01f));
+    g = fma2(g, sv, splat2(2.0f * 5.000000033e-01f));
     const float2 p = mul2(p2, ip);                                         // sqrt(p2)
-    return fma2(add2(p, p), g, q);
+    return fma2(p, g, q);
 }
 
-// sum_k log2(lambda_k(G G^T))^2 for lower-triangular G (packed row-major: g00 | g10 g11 | g20 g21 g22) and H = G^-1.
+// Both means q1 = tr(M1)/3, q2 = tr(M2)/3 of a lane inside [1e-6, 1e9]: then nothing overflows on the way
+// (|det B| <= 2 p^3 <= 1e28) and whatever underflows is below 2e-7 of q (see sym3_lam_max_x2).  NaN fails the test.
+// M2's eigenvalues are products of two eigenvalues of W, so the window covers eigenvalues of W in about [1e-3, 3e4];
+// pairs outside it take the Jacobi sweeps.
+__device__ __forceinline__ bool closed_form_in_range(float q1, float q2) {
+    return fminf(q1, q2) >= 1e-6f && fmaxf(q1, q2) <= 1e9f;
+}
+
+// sum_k log2(lambda_k(G G^T))^2 for lower-triangular G (packed row-major: g00 | g10 g11 | g20 g21 g22);
+// d = 3 also takes x = g10 g21 - g20 g11 (formed in fp64 by the caller).  `ok` = closed_form_in_range per problem.
 template <int d>
-__device__ __forceinline__ float2 closed_form_log2_sq_x2(const float2 (&G)[tri_size(d)], const float2 (&H)[tri_size(d)]) {
+__device__ __forceinline__ float2 closed_form_log2_sq_x2(const float2 (&G)[tri_size(d)], float2 x, bool& ok0, bool& ok1) {
     static_assert(d == 2 || d == 3, "closed forms exist for d = 2, 3");
     if constexpr (d == 2) {
         const float2 a = mul2(G[0], G[0]), b = fma2(G[1], G[1], mul2(G[2], G[2])), c = mul2(G[0], G[1]);
         const float2 h = sub2(a, b), c2 = add2(c, c);
         const float2 disc = fma2(h, h, mul2(c2, c2));
         const float2 root = make_float2(sqrt_approx(disc.x), sqrt_approx(disc.y));
-        const float2 l1 = log2_2(mul2(add2(add2(a, b), root), splat2(0.5f)));       // larger eigenvalue: no cancellation
-        const float2 ld = log2_2(mul2(G[0], G[2]));
+        const float2 tr = add2(a, b);
+        const float2 l1 = log2_2(mul2(add2(tr, root), splat2(0.5f)));              // larger eigenvalue: no cancellation
+        const float2 dt = mul2(G[0], G[2]);
+        const float2 ld = log2_2(dt);
         const float2 l2 = sub2(add2(ld, ld), l1);                                  // log2(det / lambda_1)
+        ok0 = closed_form_in_range(tr.x, dt.x);      // trace and determinant of G inside [1e-9, 1e9]
+        ok1 = closed_form_in_range(tr.y, dt.y);
         return fma2(l1, l1, mul2(l2, l2));
     } else {
         // M1 = G G^T
@@ -552,18 +569,25 @@ __device__ __forceinline__ float2 closed_form_log2_sq_x2(const float2 (&G)[tri_s
         const float2 m22 = fma2(G[3], G[3], fma2(G[4], G[4], mul2(G[5], G[5])));
         const float2 m01 = mul2(G[0], G[1]), m02 = mul2(G[0], G[3]);
         const float2 m12 = fma2(G[1], G[3], mul2(G[2], G[4]));
-        const float2 l1 = sym3_lam_max_x2(m00, m11, m22, m01, m02, m12);
-        // M2 = H^T H
-        const float2 n00 = fma2(H[0], H[0], fma2(H[1], H[1], mul2(H[3], H[3])));
-        const float2 n11 = fma2(H[2], H[2], mul2(H[4], H[4]));
-        const float2 n22 = mul2(H[5], H[5]);
-        const float2 n01 = fma2(H[1], H[2], mul2(H[3], H[4]));
-        const float2 n02 = mul2(H[3], H[5]), n12 = mul2(H[4], H[5]);
-        const float2 mu = sym3_lam_max_x2(n00, n11, n22, n01, n02, n12);
-        const float2 a = log2_2(l1);
-        const float2 c = neg2(log2_2(mu));
-        const float2 ld = log2_2(mul2(mul2(G[0], G[2]), G[5]));
-        const float2 b = sub2(sub2(add2(ld, ld), a), c);
+        float2 q1, q2;
+        const float2 l1 = sym3_lam_max_x2(m00, m11, m22, m01, m02, m12, q1);
+        // H = D adj(G) D with D = diag(1, -1, 1) (same singular values, no sign flips):
+        //   h00 = g11 g22, h11 = g00 g22, h22 = g00 g11, h10 = g10 g22, h21 = g21 g00, h20 = x;   M2 = H^T H
+        const float2 h00 = mul2(G[2], G[5]), h11 = mul2(G[0], G[5]), h22 = mul2(G[0], G[2]);
+        const float2 h10 = mul2(G[1], G[5]), h21 = mul2(G[4], G[0]);
+        const float2 n00 = fma2(h00, h00, fma2(h10, h10, mul2(x, x)));
+        const float2 n11 = fma2(h11, h11, mul2(h21, h21));
+        const float2 n22 = mul2(h22, h22);
+        const float2 n01 = fma2(h10, h11, mul2(x, h21));
+        const float2 n02 = mul2(x, h22), n12 = mul2(h21, h22);
+        const float2 mu = sym3_lam_max_x2(n00, n11, n22, n01, n02, n12, q2);       // det W / lambda_min
+        ok0 = closed_form_in_range(q1.x, q2.x);
+        ok1 = closed_form_in_range(q1.y, q2.y);
+        const float2 ld = log2_2(mul2(h22, G[5]));                                 // log2 det G
+        const float2 ld2 = add2(ld, ld);                                           // log2 det W
+        const float2 a = log2_2(l1);                                               // log2 lambda_max
+        const float2 c = sub2(ld2, log2_2(mu));                                    // log2 lambda_min
+        const float2 b = sub2(sub2(ld2, a), c);                                    // log2 lambda_mid
         return fma2(a, a, fma2(b, b, mul2(c, c)));
     }
 }

@@ -141,6 +141,28 @@ struct TileCursor {
     }
 };
 
+// Jacobi route for the (rare) pairs whose scales fall outside closed_form_in_range: kept out of line so that the hot
+// loop of the closed-form kernels does not carry its registers.
+template <int d>
+__device__ __noinline__ float2 jacobi_log2_sq_x2_slow(float2 g00, float2 g10, float2 g11, float2 g20, float2 g21,
+                                                      float2 g22) {   // by value: G stays in registers at the call site
+    const float2 z = make_float2(0.0f, 0.0f);
+    float2 G[d][d], lam[d];
+    G[0][0] = g00;
+    G[0][1] = z;
+    G[1][0] = g10;
+    G[1][1] = g11;
+    if constexpr (d == 3) {
+        G[0][2] = z;
+        G[1][2] = z;
+        G[2][0] = g20;
+        G[2][1] = g21;
+        G[2][2] = g22;
+    }
+    jacobi_onesided_x2<d>(G, lam);
+    return sum_log2_sq_x2<d>(lam);
+}
+
 template <int d>
 struct PairCfg {
     static constexpr int kMaxTileM = (d <= 5) ? 32 : 8;  // keeps static shared memory under 48 KB for d = 8
@@ -158,7 +180,6 @@ __global__ void __launch_bounds__(kThreads)
     constexpr bool kX2 = PairCfg<d>::kPacked && sizeof(T) == 4;   // two pairs per thread on the fp32x2 pipe
     // d = 2, 3 in fp32: closed-form eigenvalues (spd_common.cuh, closed_form_log2_sq_x2) instead of Jacobi sweeps
     constexpr bool kClosed = kX2 && (d == 2 || d == 3);
-    constexpr bool kNeedH = kClosed && d == 3;                    // H = G^-1 = A_j L_i
     constexpr int kMaxTileM = PairCfg<d>::kMaxTileM;
     __shared__ __align__(16) double fs[2][kMaxTileM * FS];              // staged x1 records (we read the A halves)
     __shared__ double ls[kLInRegs ? 1 : TRI * kThreads];                // L_j, entry-major (conflict-free), d >= 6 only
@@ -206,7 +227,6 @@ __global__ void __launch_bounds__(kThreads)
     }
     int64_t jb_loaded = -1;
     double Lreg[kLInRegs ? TRI : 1];
-    double Areg[kNeedH ? TRI : 1];                                  // A_j = L_j^-1 (closed form, d = 3)
     int64_t j = 0;
     bool jvalid = false;
 
@@ -244,10 +264,6 @@ __global__ void __launch_bounds__(kThreads)
             if (kLInRegs) {
 #pragma unroll
                 for (int e = 0; e < (kLInRegs ? TRI : 1); ++e) Lreg[e] = __ldg(src + e);
-                if (kNeedH) {
-#pragma unroll
-                    for (int e = 0; e < (kNeedH ? TRI : 1); ++e) Areg[e] = __ldg(src + TRI + e);
-                }
             } else {
 #pragma unroll
                 for (int e = 0; e < TRI; ++e) ls[e * kThreads + threadIdx.x] = __ldg(src + e);
@@ -269,34 +285,51 @@ __global__ void __launch_bounds__(kThreads)
         auto Lj = [&](int e) { return kLInRegs ? Lreg[kLInRegs ? e : 0] : ls[e * kThreads + threadIdx.x]; };
 
         if constexpr (kClosed) {
-            // two rows of the tile per step, same column; triangular products in fp64, everything else packed fp32x2
-            for (int i = 0; i < rows; i += 2) {
+            // two rows of the tile per step, same column; the triangular product G = A_i L_j (and, for d = 3, the one
+            // adjugate entry with a cancellation) in fp64, everything else packed fp32x2 (closed_form_log2_sq_x2)
+            const bool sym = map.symmetric != 0;
+            OutT* o1 = out + i0 * ld_out + j;
+            OutT* o2 = out + j * ld_out + i0;               // mirrored entry (symmetric builds only)
+            auto widen = [](float v) -> OutT {
+                if constexpr (sizeof(OutT) == 8) return widen_nonneg(v);   // K, d >= 0: ALU-pipe widening
+                else return v;
+            };
+            for (int i = 0; i < rows; i += 2, o1 += 2 * ld_out, o2 += 2) {
                 const int i1 = min(i + 1, rows - 1);            // odd tail: the partner repeats row i (not stored)
-                const double* R0 = &fs[buf][i * FS];            // record of row i: [L_i | A_i]
-                const double* R1 = &fs[buf][i1 * FS];
-                float2 G[TRI], H[TRI];
+                const double* A0 = &fs[buf][i * FS + TRI];
+                const double* A1 = &fs[buf][i1 * FS + TRI];
+                double g0[TRI], g1[TRI];
 #pragma unroll
                 for (int r = 0; r < d; ++r) {
 #pragma unroll
                     for (int c = 0; c <= r; ++c) {
-                        double s0 = 0.0, s1 = 0.0, h0 = 0.0, h1 = 0.0;
+                        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                         for (int k = c; k <= r; ++k) {
                             const double l = Lj(tri_idx(k, c));
-                            s0 = fma(R0[TRI + tri_idx(r, k)], l, s0);           // G = A_i L_j
-                            s1 = fma(R1[TRI + tri_idx(r, k)], l, s1);
-                            if (kNeedH) {
-                                const double a = Areg[kNeedH ? tri_idx(r, k) : 0];
-                                h0 = fma(a, R0[tri_idx(k, c)], h0);              // H = A_j L_i
-                                h1 = fma(a, R1[tri_idx(k, c)], h1);
-                            }
+                            s0 = fma(A0[tri_idx(r, k)], l, s0);
+                            s1 = fma(A1[tri_idx(r, k)], l, s1);
                         }
-                        G[tri_idx(r, c)] = make_float2(static_cast<float>(s0), static_cast<float>(s1));
-                        H[tri_idx(r, c)] = make_float2(static_cast<float>(h0), static_cast<float>(h1));
+                        g0[tri_idx(r, c)] = s0;
+                        g1[tri_idx(r, c)] = s1;
                     }
                 }
+                float2 G[TRI];
+#pragma unroll
+                for (int e = 0; e < TRI; ++e) G[e] = make_float2(static_cast<float>(g0[e]), static_cast<float>(g1[e]));
+                float2 x = make_float2(0.0f, 0.0f);
+                if constexpr (d == 3) {
+                    x = make_float2(static_cast<float>(fma(g0[1], g0[4], -(g0[3] * g0[2]))),
+                                    static_cast<float>(fma(g1[1], g1[4], -(g1[3] * g1[2]))));
+                }
+                bool ok0, ok1;
+                float2 ls = closed_form_log2_sq_x2<d>(G, x, ok0, ok1);
+                if (!(ok0 && ok1)) {                                        // out-of-range scales: rare
+                    if constexpr (d == 3) ls = jacobi_log2_sq_x2_slow<d>(G[0], G[1], G[2], G[3], G[4], G[5]);
+                    else ls = jacobi_log2_sq_x2_slow<d>(G[0], G[1], G[2], G[0], G[0], G[0]);
+                }
                 // spd_utils_torch.py:117-120 in fp32: d^2 = sum log(lambda)^2 + 1e-15, log = ln2 * log2 (MUFU)
-                const float2 d2 = fma2(closed_form_log2_sq_x2<d>(G, H), splat2(0.48045301391820142f), splat2(1e-15f));
+                const float2 d2 = fma2(ls, splat2(0.48045301391820142f), splat2(1e-15f));
                 float2 v;
                 if (KIND == GABO_KIND_GAUSS) {
                     const float2 t = fma2(d2, splat2(kp.k_hi), mul2(d2, splat2(kp.k_lo)));   // kernels_spd.py:96-98
@@ -308,8 +341,22 @@ __global__ void __launch_bounds__(kThreads)
                         v = make_float2(ex2_approx(t.x), ex2_approx(t.y));
                     }
                 }
-                store(i0 + i, v.x);
-                if (i1 != i) store(i0 + i1, v.y);
+                if (jvalid) {
+                    if (!sym) {
+                        st_cs(o1, widen(v.x));
+                        if (i1 != i) st_cs(o1 + ld_out, widen(v.y));
+                    } else {
+                        const int64_t gi = i0 + i;
+                        if (j >= gi) {
+                            o1[0] = widen(v.x);
+                            if (j > gi) o2[0] = widen(v.x);
+                        }
+                        if (i1 != i && j > gi) {
+                            o1[ld_out] = widen(v.y);
+                            if (j > gi + 1) o2[1] = widen(v.y);
+                        }
+                    }
+                }
             }
         } else if constexpr (kX2) {
             // two rows of the tile per step, same column: (A_i, A_i+1) x L_j on the packed fp32x2 pipe

@@ -23,10 +23,25 @@ namespace gabo {
 
 namespace {
 
+// Tuning knobs (defaults = the measured best on B200; scripts/micro/sphere_variants.cu rebuilds this file with others)
+#ifndef GABO_SG_TILEM
+#define GABO_SG_TILEM 32
+#endif
+// measured at N = 32768, D = 3 (profiles/r02_sphere_variants.log): 4 rows in flight at <= 102 registers (5 CTAs per SM)
+// gives 4494 / 6348 GB/s (fp32 / fp64 out) against 4396 / 5991 for 2 rows at 56 registers; Estrin's scheme is slower
+// (the kernel is bound by instruction issue, not by the latency of the Horner chain)
+#ifndef GABO_SG_UNROLL
+#define GABO_SG_UNROLL 4
+#endif
+#ifndef GABO_SG_MINBLOCKS
+#define GABO_SG_MINBLOCKS 5
+#endif
+#define GABO_SG_BOUNDS __launch_bounds__(kThreads, GABO_SG_MINBLOCKS)
 constexpr int kThreads = 128;
 constexpr int kVec = 4;                    // columns per thread
 constexpr int kTileN = kThreads * kVec;    // 512 columns per tile
-constexpr int kTileM = 32;                 // rows per tile
+constexpr int kTileM = GABO_SG_TILEM;      // rows per tile
+constexpr int kUnroll = GABO_SG_UNROLL;    // rows in flight per thread (fast row loop)
 
 struct TailParams {
     float k_hi, k_lo;  // k = -param * log2(e) split in two floats (Gauss / Laplace)
@@ -119,9 +134,19 @@ __device__ __forceinline__ float2 tail2(double c0, double c1, const TailParams& 
     }
     if (KIND == GABO_KIND_GAUSS) {   // fused exponent (see TailParams): 10 packed FMAs + the far-side fix-up
         const float2 w = make_float2(w0, w1);
+#ifdef GABO_SG_ESTRIN
+        // Estrin's scheme: 9 FMA + 4 MUL at depth 6 instead of 9 FMA + 1 MUL at depth 10 (coefficient of w^j = pc[9-j])
+        const float2 wa = mul2(w, w), wb = mul2(wa, wa), wc = mul2(wb, wb);
+        const float2 e0 = fma2(splat2(tp.pc[8]), w, splat2(tp.pc[9])), e1 = fma2(splat2(tp.pc[6]), w, splat2(tp.pc[7]));
+        const float2 e2 = fma2(splat2(tp.pc[4]), w, splat2(tp.pc[5])), e3 = fma2(splat2(tp.pc[2]), w, splat2(tp.pc[3]));
+        const float2 e4 = fma2(splat2(tp.pc[0]), w, splat2(tp.pc[1]));
+        const float2 f0 = fma2(e1, wa, e0), f1 = fma2(e3, wa, e2);
+        const float2 p = fma2(e4, wc, fma2(f1, wb, f0));
+#else
         float2 p = splat2(tp.pc[0]);
 #pragma unroll
         for (int j = 1; j <= 9; ++j) p = fma2(p, w, splat2(tp.pc[j]));
+#endif
         const float2 tn = mul2(w, p);                                         // k d^2 on the near side (<= 0)
         const float2 s = make_float2(sqrt_approx(-tn.x), sqrt_approx(-tn.y));
         const float2 u = add2(sub2(splat2(tp.skpi_hi), s), splat2(tp.skpi_lo));  // sqrt|k| (pi - r)
@@ -198,7 +223,7 @@ __device__ __forceinline__ void store2<double>(double* p, float v0, float v1, in
 }
 
 template <int D, typename OutT, int KIND>
-__global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __restrict__ x1, int64_t n1,
+__global__ void GABO_SG_BOUNDS sphere_gram_kernel(const double* __restrict__ x1, int64_t n1,
                                                                const double* __restrict__ x2, int64_t n2,
                                                                TailParams tp, OutT* __restrict__ out, int64_t ld_out,
                                                                int64_t tiles_i, int64_t tiles_total, bool vec_ok) {
@@ -302,7 +327,7 @@ __global__ void __launch_bounds__(kThreads) sphere_gram_kernel(const double* __r
         }
         OutT* orow = out + i0 * ld_out + j_first;
         if (fast) {
-#pragma unroll 2
+#pragma unroll kUnroll
             for (int i = 0; i < rows; ++i, orow += ld_out) {
                 double a[D];
 #pragma unroll

@@ -1,6 +1,6 @@
 """CPU prototype (numpy float32 emulation) of the 'bilateral closed form' for the SPD(3) / SPD(2) affine-invariant
 distance: largest eigenvalue of W = G G^T and of W^-1 = H^T H (H = G^-1 = A_j L_i, both from the factor records) by the
-trigonometric formula, the middle one from det W = (g00 g11 g22)^2.  Checks the distance bound of SURVEY 8(d) against the
+trigonometric formula (the inverse through the adjugate of the triangular G), the middle one from det W = (g00 g11 g22)^2.  Checks the distance bound of SURVEY 8(d) against the
 fp64 oracle on the benchmark law and on hard cases.  Development aid, not part of the product."""
 import sys
 import numpy as np, torch
@@ -35,10 +35,10 @@ def lam_max_sym3(m00, m11, m22, m01, m02, m12, g=cos_third_acos):
     q = (m00 + m11 + m22) * third
     b00, b11, b22 = m00 - q, m11 - q, m22 - q
     p2 = (b00 * b00 + b11 * b11 + b22 * b22 + f32(2) * (m01 * m01 + m02 * m02 + m12 * m12)) * f32(1.0 / 6.0)
-    ip = f32(1) / np.sqrt(np.maximum(p2, f32(1e-37)))
-    c00, c11, c22, c01, c02, c12 = b00 * ip, b11 * ip, b22 * ip, m01 * ip, m02 * ip, m12 * ip
-    det = c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02)
-    r = np.clip(det * f32(0.5), f32(-1), f32(1))
+    p2 = np.maximum(p2, f32(1e-37))
+    ip = (f32(1) / np.sqrt(p2)).astype(f32)
+    det = b00 * (b11 * b22 - m12 * m12) + m01 * (m12 * m02 - m01 * b22) + m02 * (m01 * m12 - b11 * m02)   # unscaled B
+    r = np.clip(((det * ip) * ip) * (ip * f32(0.5)), f32(-1), f32(1))
     p = p2 * ip
     return q + f32(2) * p * g(r)
 
@@ -46,7 +46,11 @@ def lam_max_sym3(m00, m11, m22, m01, m02, m12, g=cos_third_acos):
 def dist3(fac_L, fac_A, i_idx, j_idx):
     """fac_L, fac_A: (N,3,3) fp64 lower-triangular.  Returns d for the pairs (i_idx, j_idx)."""
     G = (fac_A[i_idx] @ fac_L[j_idx]).astype(f32)          # lower triangular, rounded to fp32 as on the device
-    H = (fac_A[j_idx] @ fac_L[i_idx]).astype(f32)          # G^-1
+    G64 = fac_A[i_idx] @ fac_L[j_idx]
+    x = (G64[:, 1, 0] * G64[:, 2, 1] - G64[:, 2, 0] * G64[:, 1, 1]).astype(f32)   # the one cancelling adjugate entry, fp64
+    H = np.zeros_like(G)                                   # D adj(G) D, D = diag(1,-1,1): five products + x
+    H[:, 0, 0] = G[:, 1, 1] * G[:, 2, 2]; H[:, 1, 1] = G[:, 0, 0] * G[:, 2, 2]; H[:, 2, 2] = G[:, 0, 0] * G[:, 1, 1]
+    H[:, 1, 0] = G[:, 1, 0] * G[:, 2, 2]; H[:, 2, 1] = G[:, 2, 1] * G[:, 0, 0]; H[:, 2, 0] = x
     def gram_rows(G):   # M = G G^T for lower-triangular G
         g00, g10, g11, g20, g21, g22 = G[:, 0, 0], G[:, 1, 0], G[:, 1, 1], G[:, 2, 0], G[:, 2, 1], G[:, 2, 2]
         return (g00 * g00, g10 * g10 + g11 * g11, g20 * g20 + g21 * g21 + g22 * g22,
@@ -59,7 +63,7 @@ def dist3(fac_L, fac_A, i_idx, j_idx):
     m1 = lam_max_sym3(*gram_cols(H))
     ldet = f32(2) * np.log2(G[:, 0, 0] * G[:, 1, 1] * G[:, 2, 2])
     a = np.log2(l1)
-    c = -np.log2(m1)
+    c = ldet - np.log2(m1)                                 # m1 = det W / lambda_min
     b = ldet - a - c
     s = (a * a + b * b + c * c) * f32(0.48045301391820142) + f32(1e-15)
     return np.sqrt(s).astype(np.float64)

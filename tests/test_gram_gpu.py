@@ -229,6 +229,9 @@ def test_spd_gram_closed_form_hard_cases(d):
     sets['cond up to 5000'] = ospd.spd_sample(rng, 160, d, max_cond=1e9)
     sets['diagonal (commuting)'] = np.stack([np.diag(rng.uniform(0.001, 5, d)) for _ in range(64)])
     sets['scaled identities'] = np.stack([np.eye(d) * s for s in (1e-3, 0.5, 1.0, 2.0, 1e3)])
+    # scales far apart: intermediate quantities leave the window of the closed form -> the Jacobi route takes over
+    far = ospd.spd_sample(rng, 40, d, max_cond=100.0)
+    sets['scales far apart'] = far * np.repeat([1e-7, 1e-3, 1.0, 1e3, 1e7], 8)[:, None, None]
     beta = 0.5 + math.log(2.0)
     for name, X in sets.items():
         X = 0.5 * (X + np.swapaxes(X, -1, -2))
@@ -250,8 +253,8 @@ def test_spd_gram_full_matrix_parity_at_the_benchmarked_size(d, beta_min):
     N, beta = 2048, beta_min + math.log(2.0)
     v = bench.spd_sample_mandel(np.random.default_rng(1234), N, d)       # bench.py's input law and seed
     rep, rep64 = bench.spd_parity_report(v, beta, compute=[_lib.GABO_F32, _lib.GABO_F64])
-    print('SPD(%d) N=%d fp32 Jacobi: %s' % (d, N, rep))
-    print('SPD(%d) N=%d fp64 Jacobi: %s' % (d, N, rep64))
+    print('SPD(%d) N=%d fp32 compute: %s' % (d, N, rep))
+    print('SPD(%d) N=%d fp64 compute: %s' % (d, N, rep64))
     assert rep['pairs_checked'] == N * N
     assert rep['max_dist_margin'] <= 0.0                       # |d - d_ref| <= 1e-5 d_ref + 1e-6 on all pairs
     assert rep['max_rel_err_K_amplified'] <= 1.0               # rel err <= 1e-5 max(1, 2 beta d^2) on K >= 1e-6
