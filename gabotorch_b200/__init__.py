@@ -10,6 +10,7 @@ Module map (reference module -> here):
     BoManifolds/kernel_utils/kernels_{sphere,spd,nested_spd,nested_sphere}.py -> gabotorch_b200.kernel_utils
     BoManifolds/Riemannian_utils/{sphere,spd}_utils_torch.py   -> gabotorch_b200.riemannian_utils
     BoManifolds/manifold_optimization/manifold_optimize.py     -> gabotorch_b200.manifold_optimization
+    BoManifolds/manifold_optimization/manifold_gp_fit.py       -> gabotorch_b200.manifold_gp_fit
     BoManifolds/nested_mappings/nested_spd_utils.py            -> gabotorch_b200.nested_mappings
     pymanopt.manifolds.{Sphere,PositiveDefinite}               -> gabotorch_b200.manifolds
 """
@@ -30,4 +31,5 @@ from .manifold_optimization import (ConjugateGradient, TrustRegions, Constrained
 from .nested_mappings import (NestedSpdProjection, NestedSpdReconstruction,  # noqa: F401
                               projection_from_spd_to_nested_spd, projection_from_nested_spd_to_spd)
 from .gp_fit import fit_gpytorch_model, ExactMarginalLogLikelihood  # noqa: F401
+from .manifold_gp_fit import fit_gpytorch_manifold  # noqa: F401
 from ._compat import GammaPrior  # noqa: F401

@@ -85,8 +85,8 @@ class _BetaKernel(Kernel):
 class _SphereDistance(torch.autograd.Function):
     """d_ij = acos(clamp(<x1_i, x2_j>)) from the fused kernel, differentiable with respect to the inputs the way the
     reference's op sequence is (sphere_utils_torch.py:29-55 under autograd): dd/dc = -1 / sqrt(1 - c^2) = -1 / sin d,
-    zero where the clamp is active.  Forward is one launch of ``gabo_sphere_gram(KIND_DIST)``; the backward is two
-    device matrix products on the (N1, N2) weight matrix  -g_ij / sin d_ij."""
+    zero where the clamp is active.  Forward is one launch of ``gabo_sphere_gram(KIND_DIST)``; the backward is one launch
+    of ``gabo_weighted_points_sum`` per operand (weights -g_ij / sin d_ij formed inside the reduction)."""
 
     @staticmethod
     def forward(ctx, x1, x2):
@@ -99,11 +99,9 @@ class _SphereDistance(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         a, b, d = ctx.saved_tensors
-        lo = math.acos(1.0 - 1e-15)                       # clamp active: d == acos(1 - 1e-15) or pi - that
-        live = (d > lo * (1 + 1e-9)) & (d < math.pi - lo * (1 + 1e-9))
-        w = torch.where(live, -g.to(d) / torch.sin(d), torch.zeros_like(d))
-        ga = torch.matmul(w, b) if ctx.needs_input_grad[0] else None
-        gb = torch.matmul(w.transpose(-1, -2), a) if ctx.needs_input_grad[1] else None
+        g = ops.to_dev64(g).contiguous()
+        ga = ops.weighted_points_sum(g, b, transpose=False, dist=d) if ctx.needs_input_grad[0] else None
+        gb = ops.weighted_points_sum(g, a, transpose=True, dist=d) if ctx.needs_input_grad[1] else None
         d1, d2, t1, t2 = ctx.devs
         return (None if ga is None else ga.to(device=d1, dtype=t1)), (None if gb is None else gb.to(device=d2, dtype=t2))
 
@@ -149,6 +147,135 @@ class _SpdAiDistance2(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g2 = ops.mandel_pack(ops.spd_ai_gram_backward(f2, f1, d, g, True, compute)).to(device=dev2, dtype=t2)
         return g1, g2, None
+
+
+class _MandelUnpack(torch.autograd.Function):
+    """Mandel vectors (n, dv) -> symmetric matrices (n, d, d); backward = Mandel pack of the symmetrised gradient."""
+
+    @staticmethod
+    def forward(ctx, v):
+        ctx.meta = (v.device, v.dtype)
+        return ops.mandel_unpack(ops.to_dev64(v))
+
+    @staticmethod
+    def backward(ctx, g):
+        g = ops.to_dev64(g)
+        dev, dt = ctx.meta
+        return ops.mandel_pack(0.5 * (g + g.transpose(-1, -2))).to(device=dev, dtype=dt)
+
+
+class _SpdLogm(torch.autograd.Function):
+    """logm of SPD matrices (``gabo_spd_logm``) with the adjoint of its Frechet derivative (``gabo_spd_logm_backward``):
+    what autograd gives the reference through ``logm_torch`` (symeig with eigenvectors, spd_utils_torch.py:13-30)."""
+
+    @staticmethod
+    def forward(ctx, m):
+        m = ops.to_dev64(m)
+        ctx.save_for_backward(m)
+        return ops.spd_logm(m)
+
+    @staticmethod
+    def backward(ctx, g):
+        (m,) = ctx.saved_tensors
+        return ops.spd_logm_backward(m, ops.to_dev64(g).contiguous())
+
+
+class _FrobeniusDistance2(torch.autograd.Function):
+    """||M1_i - M2_j + 1e-15||_F^2 (spd_utils_torch.py:156) for (n1, d, d), (n2, d, d); the backward
+    2 sum_j g_ij (M1_i - M2_j + 1e-15) is a row sum and one ``gabo_weighted_points_sum`` per operand."""
+
+    @staticmethod
+    def forward(ctx, m1, m2):
+        m1, m2 = ops.to_dev64(m1), ops.to_dev64(m2)
+        ctx.save_for_backward(m1, m2)
+        d = ops.frobenius_gram(m1, m2, kind=_lib.KIND_DIST)
+        return d * d
+
+    @staticmethod
+    def backward(ctx, g):
+        m1, m2 = ctx.saved_tensors
+        g = ops.to_dev64(g).contiguous()
+        n1, n2, dd = m1.shape[0], m2.shape[0], m1.shape[-1] * m1.shape[-2]
+        f1, f2 = m1.reshape(n1, dd), m2.reshape(n2, dd)
+        g1 = g2 = None
+        if ctx.needs_input_grad[0]:
+            g1 = 2.0 * (g.sum(1, keepdim=True) * (f1 + 1e-15) - ops.weighted_points_sum(g, f2, transpose=False))
+            g1 = g1.reshape(m1.shape)
+        if ctx.needs_input_grad[1]:
+            g2 = 2.0 * (g.sum(0).unsqueeze(1) * (f2 - 1e-15) - ops.weighted_points_sum(g, f1, transpose=True))
+            g2 = g2.reshape(m2.shape)
+        return g1, g2
+
+
+class _NestedSpdProject(torch.autograd.Function):
+    """Mandel(W^T X W) (``gabo_nested_spd_project_f64``) with gradients for the inputs AND the projection matrix
+    (``gabo_nested_spd_project_backward``): dX_n = W G_n W^T, dW = 2 sum_n X_n W G_n (nested_spd_utils.py:13-48 under
+    autograd).  The gradient with respect to W is the EUCLIDEAN one; ``fit_gpytorch_manifold`` projects it onto the
+    Grassmann tangent space as pymanopt's ``egrad2rgrad`` does."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        xd, wd = ops.to_dev64(x), ops.to_dev64(w)
+        ctx.save_for_backward(xd, wd)
+        ctx.meta = (x.device, x.dtype, w.device, w.dtype, tuple(x.shape))
+        return ops.nested_spd_project_f64(xd, wd)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xd, wd = ctx.saved_tensors
+        xdev, xdt, wdev, wdt, xshape = ctx.meta
+        gmat = ops.mandel_unpack(ops.to_dev64(gy).reshape(-1, gy.shape[-1]))
+        want_x, want_w = ctx.needs_input_grad
+        xm = ops.mandel_unpack(xd.reshape(-1, xd.shape[-1])) if want_w else None
+        gx, gw = ops.nested_spd_project_backward(xm, wd, gmat, want_x=want_x, want_w=want_w)
+        if gx is not None:
+            gx = ops.mandel_pack(gx).reshape(xshape).to(device=xdev, dtype=xdt)
+        if gw is not None:
+            gw = gw.to(device=wdev, dtype=wdt)
+        return gx, gw
+
+
+def _dev64_keep_grad(x):
+    """fp64 on the compute device WITHOUT leaving the autograd graph (``ops.to_dev64`` detaches)."""
+    x = torch.as_tensor(x)
+    return x.to(device=x.device if x.is_cuda else ops.device(), dtype=torch.float64)
+
+
+def _rotate_to_north(x, axis):
+    """R x for the rotation R that moves the unit vector ``axis`` to the north pole e_last along their geodesic
+    (rotation_from_sphere_points_torch, sphere_utils_torch.py:58-93), applied in O(k) without forming R:
+    R = I + sin(t) (y c^T - c y^T) + (cos(t) - 1) (y y^T + c c^T), y = e_last, cos t = <axis, y>, c = unit(axis - y cos t).
+    Differentiable torch code on the device: used only when the axes are being fitted (requires_grad)."""
+    ct = axis[-1].clamp(-1.0 + 1e-15, 1.0 - 1e-15)
+    y = torch.zeros_like(axis)
+    y[-1] = 1.0
+    c = axis - y * ct
+    c = c / c.norm()
+    st = torch.sin(torch.acos(ct))
+    xc, xy = x @ c, x[:, -1]
+    return x + st * (xc[:, None] * y - xy[:, None] * c) + (ct - 1.0) * (xy[:, None] * y + xc[:, None] * c)
+
+
+def _nested_sphere_project_autograd(x, axes, dists):
+    """The nested-sphere projection chain S^{D-1} -> S^{d-1} (nested_spheres_utils.py:13-147) in differentiable device
+    code, one level per axis: rotate the axis to the north pole, project onto the small circle at ``dist`` from it,
+    drop the last coordinate and renormalise (with the reference's 1e-6 guards).  The forward values equal
+    ``gabo_nested_sphere_project`` (tested); this form exists for the gradients with respect to the axes."""
+    x = _dev64_keep_grad(x)
+    lead = x.shape[:-1]
+    x = x.reshape(-1, x.shape[-1])
+    for axis, r in zip(axes, dists):
+        a = _dev64_keep_grad(axis).reshape(-1).to(x.device)
+        r = _dev64_keep_grad(r).reshape(()).to(x.device)
+        xr = _rotate_to_north(x, a)
+        dist = torch.acos(xr[:, -1].clamp(-1.0 + 1e-15, 1.0 - 1e-15))[:, None]
+        north = torch.zeros_like(xr)
+        north[:, -1] = 1.0
+        # on the small circle, still in the rotated frame (the reference rotates back and forth: R^T then R[:-1] = identity)
+        xn = (torch.sin(r) * xr + torch.sin(dist - r) * north) / (torch.sin(dist) + 1e-6)
+        xs = xn[:, :-1] / (torch.sin(r) + 1e-6)
+        x = xs / (xs.norm(dim=-1, keepdim=True) + 1e-6)
+    return x.reshape(lead + (x.shape[-1],))
 
 
 def _param_gram(dist_fn, param, power):
@@ -235,11 +362,15 @@ class SpdAffineInvariantLaplaceKernel(SpdAffineInvariantGaussianKernel):
     """exp(-beta d_AI(X1,X2)) (kernels_spd.py:103-187)."""
 
     def forward(self, x1, x2, diagonal_distance=False, **params):
-        _reject_input_grad(x1, x2)
         if diagonal_distance is True:
             return _spd_diag_ones(x2)
         beta = self._beta_scalar()
-        if _needs_param_grad(self.raw_beta):
+        if _wants_input_grad(x1, x2):      # d = sqrt(d^2): the reference's 1e-15 under the root keeps d'(0) finite
+            if x1.dim() != 2 or x2.dim() != 2:
+                raise NotImplementedError('input gradients are provided for (N, dv) Mandel inputs')
+            d2 = _SpdAiDistance2.apply(x1, x2, self._compute())
+            out = torch.exp(-torch.sqrt(d2) * beta.double().to(d2.device).reshape(()))
+        elif _needs_param_grad(self.raw_beta):
             out = _param_gram(lambda: ops.spd_ai_gram(x1, x2, kind=_lib.KIND_DIST, compute=self._compute()), beta, 1)
         else:
             out = ops.spd_ai_gram(x1, x2, float(beta.detach()), _lib.KIND_LAPLACE, compute=self._compute())
@@ -256,12 +387,19 @@ class SpdFrobeniusGaussianKernel(Kernel):
     def _matrices(self, x):
         return ops.mandel_unpack(x)
 
+    def _matrices_autograd(self, x):
+        return _MandelUnpack.apply(x)
+
     def forward(self, x1, x2, diagonal_distance=False, **params):
-        _reject_input_grad(x1, x2)
         if diagonal_distance is True:
             return _spd_diag_ones(x2)
         ls = self.lengthscale.reshape(()).double()
         inv = 1.0 / (ls * ls)
+        if _wants_input_grad(x1, x2):
+            if x1.dim() != 2 or x2.dim() != 2:
+                raise NotImplementedError('input gradients are provided for (N, dv) Mandel inputs')
+            d2 = _FrobeniusDistance2.apply(self._matrices_autograd(x1), self._matrices_autograd(x2))
+            return _finish(torch.exp(-d2 * inv.to(d2.device)), x1)
         m1 = self._matrices(x1)
         m2 = m1 if x2 is x1 else self._matrices(x2)
         if _needs_param_grad(self.raw_lengthscale):
@@ -277,11 +415,25 @@ class SpdLogEuclideanGaussianKernel(SpdFrobeniusGaussianKernel):
     def _matrices(self, x):
         return ops.spd_logm(ops.mandel_unpack(x))
 
+    def _matrices_autograd(self, x):
+        return _SpdLogm.apply(_MandelUnpack.apply(x))
+
 
 def _grassmann_rand(D, d):
     """pymanopt ``Grassmann(D, d).rand()``: the Q factor of a Gaussian matrix (kernels_nested_spd.py:75-78)."""
     q, _ = torch.linalg.qr(torch.randn(D, d, dtype=torch.float64))
     return q
+
+
+class _SphereStub:
+    """What the reference stores as ``raw_axis_S<k>_manifold`` (pymanopt ``Sphere(k)``)."""
+
+    def __init__(self, n):
+        self._n = n
+
+    def rand(self):
+        v = torch.randn(1, self._n, dtype=torch.float64)
+        return (v / v.norm()).numpy()
 
 
 class _GrassmannStub:
@@ -295,18 +447,17 @@ class _GrassmannStub:
 
 
 class _NestedSpdMixin:
-    """Projection parameter shared by the nested SPD kernels (kernels_nested_spd.py:74-100, :176-191).
-
-    Deviation: ``raw_projection_matrix`` is created with ``requires_grad=False`` -- in the reference it is fitted on the
-    Grassmann manifold by ``fit_gpytorch_manifold`` (GP fitting is outside this package's scope); asking for
-    its gradient raises instead of silently returning none."""
+    """Projection parameter shared by the nested SPD kernels (kernels_nested_spd.py:74-100, :176-191):
+    ``raw_projection_matrix`` lives on the Grassmann manifold G(dim, latent_dim) (``raw_projection_matrix_manifold``) and
+    is fitted there by ``manifold_gp_fit.fit_gpytorch_manifold``; the projection back-propagates to it and to the inputs
+    (``_NestedSpdProject``)."""
 
     def _init_projection(self, dim, latent_dim):
         self.dim = dim
         self.latent_dim = latent_dim
         self.raw_projection_matrix_manifold = _GrassmannStub(dim, latent_dim)
         w = _grassmann_rand(dim, latent_dim).to(torch.float32).repeat(*self.batch_shape, 1, 1)
-        self.register_parameter(name='raw_projection_matrix', parameter=torch.nn.Parameter(w, requires_grad=False))
+        self.register_parameter(name='raw_projection_matrix', parameter=torch.nn.Parameter(w))
 
     @property
     def projection_matrix(self):
@@ -317,16 +468,22 @@ class _NestedSpdMixin:
         self._set_projection_matrix(value)
 
     def _set_projection_matrix(self, value):
-        self.initialize(raw_projection_matrix=value)
+        if not torch.is_tensor(value):
+            value = torch.as_tensor(value)
+        self.initialize(raw_projection_matrix=value.to(self.raw_projection_matrix))
 
-    def _project(self, x):
+    def _wants_autograd(self, *xs):
+        return _wants_input_grad(*xs) or _needs_param_grad(self.raw_projection_matrix)
+
+    def _project(self, x, autograd=False):
         """Mandel vectors of SPD(dim) -> Mandel vectors of SPD(latent_dim): G3 -> P1 -> G3 of SURVEY section 8."""
         w = self.raw_projection_matrix
-        if torch.is_grad_enabled() and w.requires_grad:
-            raise NotImplementedError('gradients with respect to the projection matrix are not provided '
-                                      '(fit_gpytorch_manifold is outside the scope of gabotorch_b200)')
         if w.dim() != 2:
             raise NotImplementedError('batched projection matrices (batch_shape != []) are not supported')
+        if autograd:
+            if x.dim() != 2:
+                raise NotImplementedError('gradients are provided for (N, dv) Mandel inputs')
+            return _NestedSpdProject.apply(x, w)
         return ops.nested_spd_project_f64(x, w.detach().double())
 
 
@@ -339,11 +496,15 @@ class NestedSpdAffineInvariantGaussianKernel(_NestedSpdMixin, _BetaKernel):
         self._init_projection(dim, latent_dim)
 
     def forward(self, x1, x2, diagonal_distance=False, **params):
-        _reject_input_grad(x1, x2)
         if diagonal_distance is True:
             return _spd_diag_ones(x2)
         beta = self._beta_scalar()
         comp = _lib.GABO_F64 if self.compute == 'f64' else _lib.GABO_F32
+        if self._wants_autograd(x1, x2):   # gradients for the inputs and / or the Grassmann parameter
+            y1 = self._project(x1, autograd=True)
+            y2 = y1 if x2 is x1 else self._project(x2, autograd=True)
+            d2 = _SpdAiDistance2.apply(y1, y2, comp)
+            return _finish(torch.exp(-d2 * beta.double().to(d2.device).reshape(())), x1)
         y1 = self._project(x1)
         y2 = y1 if x2 is x1 else self._project(x2)
         if _needs_param_grad(self.raw_beta):
@@ -362,11 +523,15 @@ class NestedSpdLogEuclideanGaussianKernel(_NestedSpdMixin, Kernel):
         self._init_projection(dim, latent_dim)
 
     def forward(self, x1, x2, diagonal_distance=False, **params):
-        _reject_input_grad(x1, x2)
         if diagonal_distance is True:
             return _spd_diag_ones(x2)
         ls = self.lengthscale.reshape(()).double()
         inv = 1.0 / (ls * ls)
+        if self._wants_autograd(x1, x2):
+            a1 = _SpdLogm.apply(_MandelUnpack.apply(self._project(x1, autograd=True)))
+            a2 = a1 if x2 is x1 else _SpdLogm.apply(_MandelUnpack.apply(self._project(x2, autograd=True)))
+            d2 = _FrobeniusDistance2.apply(a1, a2)
+            return _finish(torch.exp(-d2 * inv.to(d2.device)), x1)
         m1 = ops.spd_logm(ops.mandel_unpack(self._project(x1)))
         m2 = m1 if x2 is x1 else ops.spd_logm(ops.mandel_unpack(self._project(x2)))
         if _needs_param_grad(self.raw_lengthscale):
@@ -378,9 +543,9 @@ class NestedSpdLogEuclideanGaussianKernel(_NestedSpdMixin, Kernel):
 
 class NestedSphereGaussianKernel(_BetaKernel):
     """exp(-beta d(p(x1), p(x2))^2) with p the nested-sphere projection S^{dim-1} -> S^{latent_dim-1}
-    (kernels_nested_sphere.py:19-152).  One axis parameter ``raw_axis_S<k>`` per level k = dim .. latent_dim+1 and the
-    distances to the axes fixed at pi/2, as in the reference; the axes are created with ``requires_grad=False`` (they
-    are fitted on sphere manifolds by ``fit_gpytorch_manifold`` in the reference, which is outside this package)."""
+    (kernels_nested_sphere.py:19-152).  One axis parameter ``raw_axis_S<k>`` per level k = dim .. latent_dim+1 (each on
+    its own sphere manifold ``raw_axis_S<k>_manifold``, fitted by ``manifold_gp_fit.fit_gpytorch_manifold``) and the
+    distances to the axes fixed at pi/2, as in the reference."""
 
     def __init__(self, dim, latent_dim, beta_min, beta_prior=None, **kwargs):
         super().__init__(beta_min, beta_prior=beta_prior, **kwargs)
@@ -389,7 +554,8 @@ class NestedSphereGaussianKernel(_BetaKernel):
         for k in range(dim, latent_dim, -1):
             axis = torch.randn(1, k)
             axis = (axis / torch.norm(axis)).repeat(*self.batch_shape, 1, 1)
-            self.register_parameter(name='raw_axis_S%d' % k, parameter=torch.nn.Parameter(axis, requires_grad=False))
+            self.register_parameter(name='raw_axis_S%d' % k, parameter=torch.nn.Parameter(axis))
+            setattr(self, 'raw_axis_S%d_manifold' % k, _SphereStub(k))
         self.distances_to_axis = [math.pi / 2 * torch.ones(1, 1) for _ in range(dim, latent_dim, -1)]
 
     @property
@@ -409,14 +575,16 @@ class NestedSphereGaussianKernel(_BetaKernel):
             self.initialize(**{name: value.to(self._parameters[name]).reshape(self._parameters[name].shape)})
 
     def _project(self, x):
-        if torch.is_grad_enabled() and any(a.requires_grad for a in self.axes):
-            raise NotImplementedError('gradients with respect to the nested-sphere axes are not provided '
-                                      '(fit_gpytorch_manifold is outside the scope of gabotorch_b200)')
         return ops.nested_sphere_project(x, [a.detach().double() for a in self.axes], self.distances_to_axis)
 
     def forward(self, x1, x2, diag=False, **params):
-        _reject_input_grad(x1, x2)
         beta = self._beta_scalar()
+        if _wants_input_grad(x1, x2) or (torch.is_grad_enabled() and any(a.requires_grad for a in self.axes)):
+            # gradients for the inputs and / or the axes: the projection chain in differentiable device code
+            q1 = _nested_sphere_project_autograd(x1, self.axes, self.distances_to_axis)
+            q2 = q1 if x2 is x1 else _nested_sphere_project_autograd(x2, self.axes, self.distances_to_axis)
+            out = _param_gram(lambda: _sphere_distance_with_grad(q1, q2, diag), beta, 2)
+            return _finish(out, x1)
         p1 = self._project(x1)
         p2 = p1 if x2 is x1 else self._project(x2)
         if _needs_param_grad(self.raw_beta):

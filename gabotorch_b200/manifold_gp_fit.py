@@ -1,0 +1,481 @@
+"""GP fit with manifold-valued kernel parameters: ``fit_gpytorch_manifold``.
+
+Mirrors ``BoManifolds/manifold_optimization/manifold_gp_fit.py:54-222`` of the reference: the negative marginal
+log-likelihood is minimised over the PRODUCT of the parameter manifolds -- Euclidean for the raw noise, the constant
+mean, the raw outputscale and the raw beta / lengthscale; ``Grassmann(D, d)`` for the projection matrix of the nested
+SPD kernels and one ``Sphere(k)`` per axis of the nested-sphere kernel (the ``<name>_manifold`` attributes the reference
+looks up with ``attrgetter``, :158-166) -- with a pymanopt solver (default ``ConjugateGradient(maxiter=500)``) started
+from the best of ``nb_init_candidates`` random parameter sets, three quarters of which keep the current values of the
+first four (Euclidean) parameters (:186-196).
+
+What runs where.  The parameter manifolds are tiny (a 20 x 5 matrix, a few unit vectors, four scalars): their
+retractions / projections are host numpy, exactly like pymanopt's.  Every objective evaluation is device work through the
+package's kernels: projection -> factorisation -> geodesic distance matrix (``kernel_utils``), then ONE launch of
+``gabo_gp_mll`` (Cholesky, solves, log-determinant, closed-form gradient of the four Euclidean parameters, ``alpha`` and
+``K^-1``); the gradient of the manifold-valued parameters goes back through the distance matrix with the backward kernels
+(``gabo_spd_ai_gram_backward``, ``gabo_nested_spd_project_backward``, ``gabo_weighted_points_sum``).  The reference gets
+both from torch.autograd through its per-pair Python loops.
+
+pymanopt (``Product``, ``Grassmann``, ``Sphere``, ``Euclidean``, ``ConjugateGradient``, ``LineSearchAdaptive``) is
+third-party and absent from the image: PARITY UNPINNED for the trajectory (restated from pymanopt 0.2.x); the objective and
+its gradients are checked against finite differences and the oracle.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from . import kernel_utils as ku
+from .gp_fit import MarginalLogLikelihood, NOISE_MIN, _prior_of, _model_parts
+from .manifold_optimization import ConjugateGradient, ManifoldGP
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host-side parameter manifolds (pymanopt 0.2.x formulas; points are small numpy arrays)
+# ----------------------------------------------------------------------------------------------------------------
+
+class EuclideanParam:
+    """pymanopt ``Euclidean(n)``."""
+
+    def __init__(self, *shape):
+        self._shape = tuple(shape)
+
+    def rand(self):
+        return np.random.randn(*self._shape)
+
+    def inner(self, x, u, v):
+        return float(np.tensordot(u, v, axes=u.ndim))
+
+    def norm(self, x, u):
+        return float(np.linalg.norm(u))
+
+    def proj(self, x, u):
+        return u
+
+    egrad2rgrad = proj
+
+    def retr(self, x, u):
+        return x + u
+
+    def transp(self, x, y, u):
+        return u
+
+
+class SphereParam:
+    """pymanopt ``Sphere(n)`` (vectors): projection retraction, projection transport."""
+
+    def __init__(self, n):
+        self._n = int(n)
+
+    def rand(self):
+        v = np.random.randn(self._n)
+        return v / np.linalg.norm(v)
+
+    def inner(self, x, u, v):
+        return float(np.dot(u.ravel(), v.ravel()))
+
+    def norm(self, x, u):
+        return float(np.linalg.norm(u))
+
+    def proj(self, x, u):
+        return u - np.dot(x.ravel(), u.ravel()) * x
+
+    egrad2rgrad = proj
+
+    def retr(self, x, u):
+        y = x + u
+        return y / np.linalg.norm(y)
+
+    def transp(self, x, y, u):
+        return self.proj(y, u)
+
+
+class GrassmannParam:
+    """pymanopt ``Grassmann(n, p)`` (one subspace): orthonormal n x p representatives, horizontal projection
+    U - X X^T U, polar retraction (SVD of X + U), projection transport."""
+
+    def __init__(self, n, p):
+        self._n, self._p = int(n), int(p)
+
+    def rand(self):
+        q, _ = np.linalg.qr(np.random.randn(self._n, self._p))
+        return q
+
+    def inner(self, x, u, v):
+        return float(np.tensordot(u, v, axes=2))
+
+    def norm(self, x, u):
+        return float(np.linalg.norm(u))
+
+    def proj(self, x, u):
+        return u - x @ (x.T @ u)
+
+    egrad2rgrad = proj
+
+    def retr(self, x, u):
+        a, _, bt = np.linalg.svd(x + u, full_matrices=False)
+        return a @ bt
+
+    def transp(self, x, y, u):
+        return self.proj(y, u)
+
+
+class ProductParam:
+    """pymanopt ``Product``: points and tangent vectors are lists, one entry per factor."""
+
+    def __init__(self, manifolds):
+        self.manifolds = list(manifolds)
+
+    def rand(self):
+        return [m.rand() for m in self.manifolds]
+
+    def inner(self, x, u, v):
+        return float(sum(m.inner(a, b, c) for m, a, b, c in zip(self.manifolds, x, u, v)))
+
+    def norm(self, x, u):
+        return math.sqrt(max(self.inner(x, u, u), 0.0))
+
+    def proj(self, x, u):
+        return [m.proj(a, b) for m, a, b in zip(self.manifolds, x, u)]
+
+    def egrad2rgrad(self, x, u):
+        return [m.egrad2rgrad(a, b) for m, a, b in zip(self.manifolds, x, u)]
+
+    def retr(self, x, u):
+        return [m.retr(a, b) for m, a, b in zip(self.manifolds, x, u)]
+
+    def transp(self, x, y, u):
+        return [m.transp(a, b, c) for m, a, b, c in zip(self.manifolds, x, y, u)]
+
+
+def _lin(a, x, b=None, y=None):
+    """a x (+ b y) on lists of arrays."""
+    if y is None:
+        return [a * xi for xi in x]
+    return [a * xi + b * yi for xi, yi in zip(x, y)]
+
+
+def host_manifold(obj):
+    """Host parameter manifold for what a kernel stores as ``<parameter>_manifold`` (the package's stubs, or a pymanopt
+    ``Grassmann`` / ``Sphere`` / ``Euclidean`` object, recognised by class name and its ``_n`` / ``_p`` attributes)."""
+    name = type(obj).__name__
+    if isinstance(obj, (EuclideanParam, SphereParam, GrassmannParam)):
+        return obj
+    if 'Grassmann' in name:
+        return GrassmannParam(obj._n, obj._p)
+    if 'Sphere' in name:
+        return SphereParam(getattr(obj, '_n', None) or obj._shape[0])
+    if 'Euclidean' in name:
+        return EuclideanParam(*obj._shape)
+    raise NotImplementedError('parameter manifold %s is not supported (Grassmann, Sphere, Euclidean)' % name)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pymanopt ConjugateGradient + LineSearchAdaptive on a (product) manifold, host loop over device evaluations
+# ----------------------------------------------------------------------------------------------------------------
+
+def riemannian_cg(manifold, cost, cost_grad, x0, solver=None, callback=None):
+    """pymanopt 0.2.x ``ConjugateGradient.solve`` (Hestenes-Stiefel, ``orth_value = inf``, ``LineSearchAdaptive``) for a
+    problem given by ``cost(x) -> float`` and ``cost_grad(x) -> (float, euclidean gradient)``.
+    Returns (x, log) with log = {'iterations', 'stop', 'cost', 'gradnorm', 'costevals'}."""
+    s = solver or ConjugateGradient()
+    maxiter, mingradnorm = int(s._maxiter), float(s._mingradnorm)
+    minstepsize, maxcostevals, maxtime = float(s._minstepsize), int(s._maxcostevals), float(s._maxtime)
+    contraction, suff_decr = float(s.contraction_factor), float(s.suff_decr)
+    ls_maxiter, init_step = int(s.ls_maxiter), float(s.initial_stepsize)
+    t0 = time.time()
+    x = x0
+    f, eg = cost_grad(x)
+    costevals = 1
+    grad = manifold.egrad2rgrad(x, eg)
+    gradnorm = manifold.norm(x, grad)
+    gPg = manifold.inner(x, grad, grad)
+    desc = _lin(-1.0, grad)
+    it, stepsize, oldalpha, stop = 0, float('nan'), None, ''
+    while True:
+        if callback is not None:
+            callback(it, f, gradnorm)
+        # Solver._check_stopping_criterion(time0, iter = it + 1, gradnorm, stepsize, costevals)
+        if time.time() - t0 >= maxtime:
+            stop = 'maxtime'
+        elif it + 1 >= maxiter:
+            stop = 'maxiter'
+        elif gradnorm < mingradnorm:
+            stop = 'mingradnorm'
+        elif stepsize < minstepsize:
+            stop = 'minstepsize'
+        elif costevals >= maxcostevals:
+            stop = 'maxcostevals'
+        if stop:
+            break
+        df0 = manifold.inner(x, grad, desc)
+        if df0 >= 0:                                   # not a descent direction: restart from steepest descent
+            desc = _lin(-1.0, grad)
+            df0 = -gPg
+        # LineSearchAdaptive.search
+        norm_d = manifold.norm(x, desc)
+        alpha = oldalpha if oldalpha is not None else init_step / norm_d
+        newx = manifold.retr(x, _lin(alpha, desc))
+        newf = cost(newx)
+        evals = 1
+        while newf > f + suff_decr * alpha * df0 and evals <= ls_maxiter:
+            alpha *= contraction
+            newx = manifold.retr(x, _lin(alpha, desc))
+            newf = cost(newx)
+            evals += 1
+        if newf > f:
+            alpha, newx = 0.0, x
+        costevals += evals
+        stepsize = alpha * norm_d
+        oldalpha = alpha if evals == 2 else 2.0 * alpha
+        newf, neweg = cost_grad(newx)
+        costevals += 1
+        newgrad = manifold.egrad2rgrad(newx, neweg)
+        newgradnorm = manifold.norm(newx, newgrad)
+        newgPg = manifold.inner(newx, newgrad, newgrad)
+        oldgrad = manifold.transp(x, newx, grad)
+        desc = manifold.transp(x, newx, desc)
+        diff = _lin(1.0, newgrad, -1.0, oldgrad)
+        ip_diff = manifold.inner(newx, newgrad, diff)
+        den = manifold.inner(newx, diff, desc)
+        try:
+            beta = max(0.0, ip_diff / den)             # Hestenes-Stiefel; NaN -> 0 as Python's max(0, nan)
+        except ZeroDivisionError:
+            beta = 1.0
+        desc = _lin(-1.0, newgrad, beta, desc)
+        x, f, grad, gradnorm, gPg = newx, newf, newgrad, newgradnorm, newgPg
+        it += 1
+    return x, {'iterations': it, 'stop': stop, 'cost': f, 'gradnorm': gradnorm, 'costevals': costevals,
+               'time': time.time() - t0}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the objective
+# ----------------------------------------------------------------------------------------------------------------
+
+def _manifold_parameters(base):
+    """[(name, parameter, host manifold)] for the parameters of the base kernel that carry a ``<name>_manifold``
+    attribute, in registration order (manifold_gp_fit.py:158-166 walks ``named_parameters`` the same way)."""
+    out = []
+    for name, p in base.named_parameters():
+        if not p.requires_grad:
+            continue
+        man = getattr(base, name + '_manifold', None)
+        if man is not None:
+            out.append((name, p, host_manifold(man)))
+    return out
+
+
+def _distance_matrix(base, x):
+    """Dm with base kernel = exp(-theta Dm), through the differentiable operator chain of ``kernel_utils`` (under
+    ``torch.no_grad()`` the same chain simply runs forward, so objective-only and gradient evaluations see bit-identical
+    distances -- the fp32 tail of the affine-invariant distance differs by one rounding between the mirrored and the
+    general tile path of the Gram kernel, which would otherwise show up in the line search)."""
+    comp = _lib.GABO_F64
+    if isinstance(base, ku.NestedSpdAffineInvariantGaussianKernel):
+        y = base._project(x, autograd=True)
+        return ku._SpdAiDistance2.apply(y, y, comp)
+    if isinstance(base, ku.NestedSpdLogEuclideanGaussianKernel):
+        a = ku._SpdLogm.apply(ku._MandelUnpack.apply(base._project(x, autograd=True)))
+        return ku._FrobeniusDistance2.apply(a, a)
+    if isinstance(base, ku.NestedSphereGaussianKernel):
+        q = ku._nested_sphere_project_autograd(x, base.axes, base.distances_to_axis)
+        d = ku._SphereDistance.apply(q, q)
+        return d * d
+    from .gp_fit import kernel_distance_matrix
+    return kernel_distance_matrix(base, x)[0]
+
+
+def _kernel_parameter(base):
+    """(lower bound, prior, getter, setter) of the scalar the base kernel multiplies its distance matrix with:
+    ``beta >= beta_min`` for the beta kernels, ``1 / lengthscale^2`` for the lengthscale kernels (fitted through
+    ``raw_lengthscale`` there)."""
+    if hasattr(base, 'raw_beta'):
+        return 'beta'
+    return 'lengthscale'
+
+
+class ManifoldObjective:
+    """-(log-likelihood + log-priors) / n of a ``ManifoldGP`` as a function of the parameter LIST
+    [raw_noise, mean, raw_outputscale, raw_beta | raw_lengthscale, *manifold-valued kernel parameters]
+    (the order of ``mll.named_parameters()`` in the reference's model) together with its Euclidean gradient."""
+
+    def __init__(self, model):
+        if not isinstance(model, ManifoldGP):
+            raise NotImplementedError('fit_gpytorch_manifold expects a gabotorch_b200.ManifoldGP (or an mll holding one)')
+        self.model = model
+        self.cov, self.base, self.scaled = _model_parts(model)
+        self.kind = _kernel_parameter(self.base)
+        x = model.train_inputs[0]
+        self.x = ops.to_dev64(x.reshape(-1, x.shape[-1]))
+        self.mparams = _manifold_parameters(self.base)
+        if self.kind == 'beta':
+            lower, prior = float(self.base.beta_min), _prior_of(self.base, 'beta_prior')
+        else:
+            lower, prior = 0.0, _prior_of(self.base, 'lengthscale_prior')
+        self.inner = MarginalLogLikelihood(
+            torch.zeros(1, 1, dtype=torch.float64), model.train_targets, lower, getattr(model, 'noise_min', NOISE_MIN),
+            outputscale_prior=_prior_of(self.cov, 'outputscale_prior') if self.scaled else None,
+            noise_prior=getattr(model, 'noise_prior', None), beta_prior=prior)
+        self.n = self.inner.n
+        self.evaluations = 0
+        self.manifold = ProductParam([EuclideanParam(1)] * 4 + [m for _, _, m in self.mparams])
+
+    # -- parameter list <-> model ---------------------------------------------------------------------------
+    def current(self):
+        """The model's parameters as the list the solver works on."""
+        if self.kind == 'beta':
+            kp = float(self.base.beta.detach().reshape(-1)[0])
+        else:
+            ls = float(self.base.lengthscale.detach().reshape(-1)[0])
+            kp = 1.0 / (ls * ls)
+        s = float(self.cov.outputscale.detach()) if self.scaled else 1.0
+        noise = max(self.model.noise, self.inner.noise_min * (1 + 1e-6) + 1e-300)
+        raw = self.inner.inverse_transform((self._kp_to_internal(kp), s, noise, self.model.mean))
+        # order: raw_noise, mean, raw_outputscale, raw kernel parameter
+        out = [np.array([raw[2]]), np.array([raw[3]]), np.array([raw[1]]), np.array([raw[0]])]
+        for _, p, _ in self.mparams:
+            a = p.detach().cpu().double().numpy()
+            out.append(a.copy() if (a.ndim > 1 and a.shape[0] > 1) else a.reshape(-1).copy())
+        return out
+
+    def _kp_to_internal(self, kp):
+        # the inner objective's first slot is "lower + softplus(raw)"; for lengthscale kernels it holds the lengthscale
+        return kp if self.kind == 'beta' else 1.0 / math.sqrt(kp)
+
+    def _raw4(self, x):
+        return np.array([float(x[3][0]), float(x[2][0]), float(x[0][0]), float(x[1][0])])   # inner order: kp, s, noise, mean
+
+    def _theta(self, raw4):
+        kp, s, noise, mean = self.inner.transform(raw4)
+        if self.kind != 'beta':
+            kp = 1.0 / (kp * kp)                              # lengthscale -> 1 / lengthscale^2
+        return kp, s, noise, mean
+
+    def _set_manifold_params(self, x):
+        with torch.no_grad():
+            for (name, p, _), val in zip(self.mparams, x[4:]):
+                p.copy_(torch.as_tensor(np.asarray(val), dtype=p.dtype).reshape(p.shape))
+
+    def apply(self, x):
+        """Write the parameter list into the model (what ``set_params_with_list_of_array`` does in the reference)."""
+        self._set_manifold_params(x)
+        raw4 = self._raw4(x)
+        kp, s, noise, mean = self.inner.transform(raw4)
+        if self.kind == 'beta':
+            self.base.beta = kp
+        else:
+            self.base.lengthscale = kp
+        if self.scaled:
+            self.cov.outputscale = s
+        self.model.noise, self.model.mean = noise, mean
+
+    # -- evaluations ----------------------------------------------------------------------------------------
+    def _prior(self, raw4):
+        kp, s, noise, mean = self.inner.transform(raw4)
+        return self.inner._prior_terms((kp, s, noise, mean))
+
+    def cost_device(self, x):
+        """Objective as a 0-d DEVICE tensor without synchronising (candidate screening reads all values back at once)."""
+        self._set_manifold_params(x)
+        raw4 = self._raw4(x)
+        with torch.no_grad():
+            dm = _distance_matrix(self.base, self.x)
+        theta = torch.tensor([self._theta(raw4)], dtype=torch.float64)
+        ll, _, _, _, flags = ops.gp_mll(dm, self.inner.y, theta, want_grad=False)
+        self.evaluations += 1
+        lp = self._prior(raw4)[0]
+        val = -(ll[0] + lp) / self.n
+        return torch.where((flags[0] != 0) | ~torch.isfinite(val), torch.full_like(val, float('inf')), val)
+
+    def cost(self, x):
+        return float(self.cost_device(x))
+
+    def cost_grad(self, x):
+        """(objective, Euclidean gradient list): one forward through the kernels, one ``gabo_gp_mll`` launch, one
+        backward through the distance matrix."""
+        self._set_manifold_params(x)
+        raw4 = self._raw4(x)
+        kp, s, noise, mean = self._theta(raw4)
+        with torch.enable_grad():
+            dm = _distance_matrix(self.base, self.x)
+        theta = torch.tensor([[kp, s, noise, mean]], dtype=torch.float64)
+        ll, g4, alpha, kinv, flags = ops.gp_mll(dm.detach(), self.inner.y, theta, want_grad=True, want_factors=True)
+        self.evaluations += 1
+        head = torch.cat([ll, g4.reshape(-1), flags.double()]).cpu().numpy()
+        zero = [np.zeros(1)] * 4 + [np.zeros_like(np.asarray(v, dtype=np.float64)) for v in x[4:]]
+        if head[5] != 0 or not np.isfinite(head[0]):
+            return 1e10, zero
+        t_in = self.inner.transform(raw4)
+        lp, dlp = self.inner._prior_terms(t_in)
+        g = head[1:5].copy()                                   # d ll / d (kp, s, noise, mean)
+        if self.kind != 'beta':
+            g[0] = g[0] * (-2.0 / t_in[0] ** 3)                # d (1 / l^2) / d l
+        from .gp_fit import _sigmoid
+        for i in range(3):
+            g[i] = (g[i] + dlp[i]) * _sigmoid(raw4[i])
+        g = -g / self.n
+        grads = [np.array([g[2]]), np.array([g[3]]), np.array([g[1] if self.scaled else 0.0]), np.array([g[0]])]
+        if self.mparams and dm.requires_grad:
+            # d ll / d Dm_ij = 1/2 (alpha alpha^T - Ktilde^-1)_ij * (-kp s exp(-kp Dm_ij))
+            a = alpha[0]
+            gd = 0.5 * (torch.outer(a, a) - kinv[0]) * (-kp * s) * torch.exp(-kp * dm.detach())
+            for _, p, _ in self.mparams:
+                p.grad = None
+            dm.backward(-gd / self.n)
+            for (name, p, _), val in zip(self.mparams, x[4:]):
+                gp = p.grad.detach().cpu().double().numpy() if p.grad is not None else np.zeros(tuple(p.shape))
+                grads.append(gp.reshape(np.asarray(val).shape))
+                p.grad = None
+        return -(head[0] + lp) / self.n, grads
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the entry point
+# ----------------------------------------------------------------------------------------------------------------
+
+def fit_gpytorch_manifold(mll, bounds=None, solver=None, nb_init_candidates=200, last_x_as_candidate_prob=0.9,
+                          options=None, track_iterations=True, approx_mll=False, **kwargs):
+    """Drop-in for the reference's ``fit_gpytorch_manifold`` (manifold_gp_fit.py:54-222) on a ``ManifoldGP`` (or an
+    object with ``.model``): fits noise, mean, outputscale, beta / lengthscale AND the manifold-valued kernel parameters
+    in place.  Returns ``(mll, info_dict)`` with ``fopt``, ``wall_time``, ``opt_log`` (and ``iterations`` when
+    ``track_iterations``)."""
+    if bounds is not None:
+        import warnings
+        warnings.warn('Bounds handling not supported yet in fit_gpytorch_manifold')      # as in the reference (:108-110)
+    if approx_mll:
+        raise NotImplementedError('approx_mll=True (gpytorch stochastic log-determinant) is not provided: the exact '
+                                  'marginal likelihood is one kernel launch')
+    solver = solver or ConjugateGradient(maxiter=500)
+    if type(solver).__name__ != 'ConjugateGradient':
+        raise NotImplementedError('fit_gpytorch_manifold drives ConjugateGradient (the reference default), got %s'
+                                  % type(solver).__name__)
+    model = getattr(mll, 'model', mll)
+    t1 = time.time()
+    obj = ManifoldObjective(model)
+    x0 = obj.current()
+    man = obj.manifold
+    nb = int(nb_init_candidates)
+    # initial candidates (:186-196): x0 with probability last_x_as_candidate_prob, random draws otherwise; the first
+    # three quarters keep the current Euclidean hyper-parameters x0[0:4]
+    if np.random.rand() < last_x_as_candidate_prob:
+        cands = [x0] + [man.rand() for _ in range(nb - 1)]
+    else:
+        cands = [man.rand() for _ in range(nb)]
+    for i in range(int(3 * nb / 4)):
+        cands[i][0:4] = [v.copy() for v in x0[0:4]]
+    vals = torch.stack([obj.cost_device(c) for c in cands]).cpu().numpy()   # ONE read-back for all candidates
+    x_init = cands[int(np.argmin(vals))]
+    iterations = []
+    cb = (lambda it, f, gn: iterations.append((it, float(f), time.time() - t1))) if track_iterations else None
+    opt_x, log = riemannian_cg(man, obj.cost, obj.cost_grad, x_init, solver, callback=cb)
+    fopt = obj.cost(opt_x)
+    obj.apply(opt_x)
+    model.fit_result = {'objective': fopt, 'iterations': log['iterations'], 'evaluations': obj.evaluations,
+                        'stop': log['stop'], 'gradnorm': log['gradnorm']}
+    info = {'fopt': fopt, 'wall_time': time.time() - t1, 'opt_log': log}
+    if track_iterations:
+        info['iterations'] = iterations
+    return mll, info

@@ -295,6 +295,53 @@ def spd_logm(mat):
     return out.reshape(m.shape)
 
 
+def spd_logm_backward(mat, grad_out):
+    """Adjoint of the Frechet derivative of logm at the SPD matrices ``mat`` applied to ``grad_out`` ((n, d, d) each)."""
+    lib = _lib.load()
+    m, g = to_dev64(mat), to_dev64(grad_out)
+    d = m.shape[-1]
+    fm, fg = m.reshape(-1, d, d), g.reshape(-1, d, d)
+    out = torch.empty_like(fm)
+    _lib.check(lib.gabo_spd_logm_backward(_p(fm), _p(fg), fm.shape[0], d, _p(out), _lib.stream_ptr()),
+               'gabo_spd_logm_backward')
+    return out.reshape(m.shape)
+
+
+def weighted_points_sum(g, b, transpose=False, dist=None):
+    """out_i = sum_j W_ij b_j for the (n1, n2) weights ``g`` (``transpose``: W = g^T, the gradient of the second
+    operand) and the points ``b`` (cols, k).  With ``dist`` (same shape as g) the weights are the sphere-distance
+    backward ``-g / sin(dist)``, zero where the reference's clamp is active."""
+    lib = _lib.load()
+    g, b = to_dev64(g), to_dev64(b)
+    n1, n2 = int(g.shape[0]), int(g.shape[1])
+    rows = n2 if transpose else n1
+    k = int(b.shape[1])
+    if int(b.shape[0]) != (n1 if transpose else n2):
+        raise ValueError('weighted_points_sum: %d points for %d weights' % (b.shape[0], n1 if transpose else n2))
+    out = torch.empty(rows, k, dtype=torch.float64, device=g.device)
+    dd = None if dist is None else to_dev64(dist)
+    _lib.check(lib.gabo_weighted_points_sum(_p(g), None if dd is None else _p(dd), n1, n2, n2, 1 if transpose else 0,
+                                            0 if dd is None else 1, _p(b), k, _p(out), _lib.stream_ptr()),
+               'gabo_weighted_points_sum')
+    return out
+
+
+def nested_spd_project_backward(x_mat, w, grad_y, want_x=True, want_w=True):
+    """Backward of Y_n = W^T X_n W: (grad_x (n, D, D) or None, grad_w (D, d) or None) from grad_y (n, d, d)."""
+    lib = _lib.load()
+    w = to_dev64(w)
+    gy = to_dev64(grad_y)
+    D, d = int(w.shape[0]), int(w.shape[1])
+    n = int(gy.shape[0])
+    x = None if x_mat is None else to_dev64(x_mat)
+    gx = torch.empty(n, D, D, dtype=torch.float64, device=w.device) if want_x else None
+    gw = torch.empty(D, d, dtype=torch.float64, device=w.device) if want_w else None
+    _lib.check(lib.gabo_nested_spd_project_backward(None if x is None else _p(x), _p(w), _p(gy), n, D, d,
+                                                    None if gx is None else _p(gx), None if gw is None else _p(gw),
+                                                    _lib.stream_ptr()), 'gabo_nested_spd_project_backward')
+    return gx, gw
+
+
 def spd_sqrtm(mat):
     """Batched sqrtm_torch (spd_utils_torch.py:33-50): (..., d, d) -> (..., d, d)."""
     lib = _lib.load()

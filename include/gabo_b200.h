@@ -102,6 +102,23 @@ int gabo_spd_ai_gram(const double* fac1, int64_t n1, const double* fac2, int64_t
 int gabo_spd_ai_gram_backward(const double* fac1, int64_t n1, const double* fac2, int64_t n2, int d, const double* w,
                               int64_t ld_w, int transpose_w, int compute, double* out, void* stream);
 
+/* Backward building blocks of the other kernels (every reference kernel is differentiable under torch.autograd with
+ * respect to its inputs and its manifold-valued parameters: kernels_sphere.py:71-134, kernels_spd.py:190-313,
+ * kernels_nested_spd.py:104-246).
+ *   gabo_weighted_points_sum: out_i = sum_j W_ij b_j (out: rows x k, b: cols x k, k <= 128), the reduction a pairwise
+ *     distance backward ends in.  g (and dist) are n1 x n2 with row stride ld; transpose != 0 reads them transposed
+ *     (rows = n2: the gradient of the SECOND operand).  mode 0: W = g.  mode 1: W = -g / sin(dist), 0 where the
+ *     reference's clamp of the inner product is active (d/dx_i acos(clamp(<x_i, y_j>)), sphere_utils_torch.py:49-55).
+ *   gabo_spd_logm_backward: grad_in_n = adjoint of the Frechet derivative of logm at mat_n applied to grad_out_n
+ *     (n x d x d each; what autograd gives through logm_torch, spd_utils_torch.py:13-30).
+ *   gabo_nested_spd_project_backward: Y_n = W^T X_n W (nested_spd_utils.py:13-48):
+ *     grad_x_n = W sym(G_n) W^T (n x D x D, nullable), grad_w = 2 sum_n sym(X_n) W sym(G_n) (D x d, nullable). */
+int gabo_weighted_points_sum(const double* g, const double* dist, int64_t n1, int64_t n2, int64_t ld, int transpose,
+                             int mode, const double* b, int k, double* out, void* stream);
+int gabo_spd_logm_backward(const double* mat, const double* grad_out, int64_t n, int d, double* grad_in, void* stream);
+int gabo_nested_spd_project_backward(const double* x, const double* w, const double* grad_y, int64_t n, int D, int d,
+                                     double* grad_x, double* grad_w, void* stream);
+
 /* Frobenius / log-Euclidean Gram (spd_utils_torch.py:124-156, kernels_spd.py:230-241, 283-313):
  *   out[i,j] = f(|| M1_i - M2_j + 1e-15 ||_F), m: n x d x d fp64 (apply gabo_spd_logm first for log-Euclidean);
  *   kind GAUSS uses exp(-param d^2) with param = 1/lengthscale^2. */

@@ -73,8 +73,9 @@ def test_spd_kernel_classes(golden):
         le.lengthscale = 1.3
         np.testing.assert_allclose(le.forward(v, v).numpy(),
                                    ospd.spd_log_euclidean_gaussian_kernel(v, v, ls).numpy(), rtol=1e-8, atol=1e-12)
-    with pytest.raises(NotImplementedError):                       # no input gradients for the Laplace / Frobenius kernels
-        lap.forward(v.clone().requires_grad_(True), v)
+    vg = v.clone().requires_grad_(True)                            # every kernel back-propagates to its inputs
+    lap.forward(vg, v.clone()).sum().backward()                    # (values checked in tests/test_grad_gpu.py)
+    assert vg.grad is not None and torch.isfinite(vg.grad).all()
 
 
 def test_riemannian_utils_functions(golden):

@@ -616,3 +616,35 @@ def test_batched_constraints_closed_form_equals_autograd(monkeypatch):
         np.testing.assert_allclose(a.numpy(), np.swapaxes(a.numpy(), -1, -2), rtol=0, atol=1e-12)
     lam = np.linalg.eigvalsh(X.numpy())
     np.testing.assert_allclose(fc.numpy(), np.stack([3.5 - lam[:, -1], lam[:, 0] - 0.2], -1), rtol=0, atol=1e-13)
+
+
+def test_riemannian_cg_on_a_product_manifold_finds_the_known_minimiser():
+    """Host logic of fit_gpytorch_manifold (manifold_gp_fit.py:54-222): pymanopt-style CG on Product(Euclidean, Grassmann,
+    Sphere) with numpy points.  Problem with a closed-form answer: minimise (t - 2)^2 - tr(X^T A X) - v^T B v, whose
+    minimum is -(sum of the two largest eigenvalues of A) - (largest eigenvalue of B) at t = 2."""
+    from gabotorch_b200 import manifold_gp_fit as mgf
+    rng = np.random.default_rng(0)
+    np.random.seed(0)
+    A = rng.standard_normal((6, 6)); A = A @ A.T
+    B = rng.standard_normal((4, 4)); B = B @ B.T
+    man = mgf.ProductParam([mgf.EuclideanParam(1), mgf.GrassmannParam(6, 2), mgf.SphereParam(4)])
+
+    def cost(x):
+        t, X, v = x
+        return float((t[0] - 2.0) ** 2 - np.trace(X.T @ A @ X) - v @ B @ v)
+
+    def cost_grad(x):
+        t, X, v = x
+        return cost(x), [np.array([2.0 * (t[0] - 2.0)]), -2.0 * A @ X, -2.0 * B @ v]
+
+    x0 = man.rand()
+    x, log = mgf.riemannian_cg(man, cost, cost_grad, x0, g.ConjugateGradient(maxiter=400, mingradnorm=1e-8))
+    want = -np.sort(np.linalg.eigvalsh(A))[-2:].sum() - np.linalg.eigvalsh(B)[-1]
+    assert abs(log['cost'] - want) <= 1e-8 * abs(want), (log, want)
+    assert abs(x[0][0] - 2.0) < 1e-6
+    assert np.abs(x[1].T @ x[1] - np.eye(2)).max() < 1e-12 and abs(np.linalg.norm(x[2]) - 1.0) < 1e-12
+    assert log['stop'] in ('mingradnorm', 'minstepsize') and log['iterations'] < 400
+    # the retraction / projection pairs satisfy the manifold identities the solver relies on
+    u = man.proj(x, man.rand())
+    assert abs(np.trace(x[1].T @ u[1])) < 1e-12 and abs(x[2] @ u[2]) < 1e-12
+    assert mgf.host_manifold(mgf.GrassmannParam(5, 2))._n == 5

@@ -96,13 +96,12 @@ def test_nested_spd_kernels_vs_oracle(D, d, n1, n2):
         got_le = le.forward(x1, x2)
     ref_le = onest.nested_spd_log_euclidean_gaussian_kernel(x1, x2, torch.from_numpy(w32), ls).numpy()
     np.testing.assert_allclose(got_le.numpy(), ref_le, rtol=1e-7, atol=1e-12)
-    # beta / lengthscale stay differentiable (GP hyper-parameter fitting), the projection matrix does not
+    # beta / lengthscale AND the Grassmann parameter are differentiable (fit_gpytorch_manifold); values checked in
+    # tests/test_grad_gpu.py
     out = k.forward(x1, x2)
     out.sum().backward()
     assert k.raw_beta.grad is not None and torch.isfinite(k.raw_beta.grad).all()
-    k.raw_projection_matrix.requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        k.forward(x1, x2)
+    assert k.raw_projection_matrix.grad is not None and torch.isfinite(k.raw_projection_matrix.grad).all()
 
 
 @pytest.mark.parametrize('name,D,dl', [('nsph_5_3', 5, 3), ('nsph_6_2', 6, 2)])
