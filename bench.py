@@ -767,19 +767,37 @@ class Bench:
                               rng.standard_normal(batch)])
         th = torch.from_numpy(th).to(self.dev)
         ms = self.time_steps(lambda: ops.gp_mll(dmat, yd, th), steps, 3, flush=False) / steps
-        t_fit = []
-        for _ in range(3):
-            cov = g.ScaleKernel(g.SphereGaussianKernel(beta_min=6.5), outputscale_prior=g.GammaPrior(2.0, 0.15))
-            model = g.ManifoldGP(xt, y, cov, noise=2.0, mean=0.0, noise_prior=g.GammaPrior(1.1, 0.05))
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            g.fit_gpytorch_model(model)
-            t_fit.append((time.perf_counter() - t0) * 1e3)
+        res = {}
+        for opt in ('device', 'scipy'):
+            t_fit = []
+            for _ in range(3):
+                cov = g.ScaleKernel(g.SphereGaussianKernel(beta_min=6.5), outputscale_prior=g.GammaPrior(2.0, 0.15))
+                model = g.ManifoldGP(xt, y, cov, noise=2.0, mean=0.0, noise_prior=g.GammaPrior(1.1, 0.05))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                g.fit_gpytorch_model(model, optimizer=opt)
+                t_fit.append((time.perf_counter() - t0) * 1e3)
+            res[opt] = (min(t_fit), model.fit_result)
+        # the fit kernel alone (device time, 1 start and 64 starts side by side)
+        obj = gp_fit.MarginalLogLikelihood(dmat, y, 6.5, outputscale_prior=(2.0, 0.15), noise_prior=(1.1, 0.05))
+        raw0 = obj.inverse_transform((6.5 + math.log(2.0), math.log(2.0), 2.0, 0.0))
+        pri = [0.0, 0.0, 2.0, 0.15, 1.1, 0.05]
+        kern_ms = {}
+        for nb in (1, 64):
+            st = torch.from_numpy(np.repeat(raw0[None], nb, 0) + (np.random.default_rng(1).standard_normal((nb, 4))
+                                                                 * np.array([1.0, 1.0, 2.0, 0.0]) if nb > 1 else 0.0))
+            kern_ms[nb] = self.time_steps(lambda: ops.gp_fit(dmat, yd, st, 6.5, 1e-8, pri, [0, 0, 0, 0]), steps, 2,
+                                          flush=False) / steps
         return {'workload': 'GP marginal likelihood + gradient, n_train=%d on S^%d, %d hyper-parameter sets per launch; '
-                            'fit_gpytorch_model (L-BFGS-B) on the gabo_sphere.py model' % (n_train, D - 1, batch),
+                            'fit_gpytorch_model on the gabo_sphere.py model: one-launch device BFGS (gabo_gp_fit) and '
+                            'scipy L-BFGS-B over one launch + read-back per evaluation' % (n_train, D - 1, batch),
                 'mll_evaluations_per_s': batch / (ms * 1e-3), 'ms_per_step': ms,
-                'fit_ms': min(t_fit), 'fit_objective_evaluations': model.fit_result['evaluations'],
-                'fit_iterations': model.fit_result['iterations']}
+                'fit_ms': res['device'][0], 'fit_objective': res['device'][1]['objective'],
+                'fit_objective_evaluations': res['device'][1]['evaluations'],
+                'fit_iterations': res['device'][1]['iterations'],
+                'fit_kernel_ms_1_start': kern_ms[1], 'fit_kernel_ms_64_starts': kern_ms[64],
+                'scipy_fit_ms': res['scipy'][0], 'scipy_fit_objective': res['scipy'][1]['objective'],
+                'scipy_fit_objective_evaluations': res['scipy'][1]['evaluations']}
 
     def extra_reconstruct(self, n=1 << 16, D=20, d=5, steps=5):
         """projection_from_nested_spd_to_spd (nested_spd_utils.py:51-118): batched sqrtm + reconstruction, fp64."""

@@ -91,6 +91,8 @@ SIGNATURES = {
     'gabo_nested_spd_reconstruct': (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     'gabo_gp_mll': (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'gabo_gp_factor': (c_i32, [c_ptr, c_i64, c_ptr, c_f64, c_f64, c_f64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'gabo_gp_fit': (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_f64, c_f64, c_ptr, c_ptr, c_i32, c_f64, c_f64, c_ptr,
+                            c_ptr, c_ptr, c_ptr]),
 }
 
 

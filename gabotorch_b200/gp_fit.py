@@ -131,11 +131,14 @@ def _model_parts(model):
     return cov, base, scaled
 
 
-def fit_gpytorch_model(mll, options=None, raw_samples=0, generator=None, **kwargs):
+def fit_gpytorch_model(mll, options=None, raw_samples=0, generator=None, optimizer='device', num_restarts=1, **kwargs):
     """Drop-in for ``botorch.fit_gpytorch_model(mll=...)`` on a ``ManifoldGP`` (or an object with ``.model``): fits
-    (beta, outputscale, noise, constant mean) in place and returns its argument.  ``options`` are passed to scipy's
-    L-BFGS-B (botorch's ``fit_gpytorch_scipy`` default: maxiter 15000)."""
-    from scipy.optimize import minimize
+    (beta, outputscale, noise, constant mean) in place and returns its argument.
+
+    ``optimizer='device'`` (default): the whole quasi-Newton fit is ONE launch of ``gabo_gp_fit`` (one CTA per start,
+    ``num_restarts`` starts side by side, best objective kept) and one read-back.  ``optimizer='scipy'``: scipy's
+    L-BFGS-B on the host as in botorch, one ``gabo_gp_mll`` launch + read-back per evaluation (``options`` are passed to
+    it; botorch's ``fit_gpytorch_scipy`` default: maxiter 15000)."""
     model = getattr(mll, 'model', mll)
     if not isinstance(model, ManifoldGP):
         raise NotImplementedError('fit_gpytorch_model expects a gabotorch_b200.ManifoldGP (or an mll holding one)')
@@ -149,25 +152,52 @@ def fit_gpytorch_model(mll, options=None, raw_samples=0, generator=None, **kwarg
     theta0 = (float(base.beta.detach().reshape(-1)[0]), float(cov.outputscale.detach()) if scaled else 1.0,
               max(model.noise, objective.noise_min * (1 + 1e-6) + 1e-300), model.mean)
     raw0 = objective.inverse_transform(theta0)
+    rng = np.random.default_rng(None if generator is None else generator)
+    starts = raw0[None]
     if raw_samples and raw_samples > 0:
         # batched screening of random raw parameter sets around the start (one launch), keep the best
-        rng = np.random.default_rng(None if generator is None else generator)
         cand = raw0[None] + rng.standard_normal((int(raw_samples), 4)) * np.array([2.0, 2.0, 3.0, 0.0])
         cand[:, 3] = raw0[3]
         cand = np.vstack([raw0[None], cand])
-        raw0 = cand[int(np.argmin(objective.batch_values(cand)))]
+        order = np.argsort(objective.batch_values(cand), kind='stable')
+        starts = cand[order[:max(1, int(num_restarts))]]
+    elif num_restarts > 1:
+        extra = raw0[None] + rng.standard_normal((int(num_restarts) - 1, 4)) * np.array([2.0, 2.0, 3.0, 0.0])
+        starts = np.vstack([raw0[None], extra])
     opts = {'maxiter': 15000}
     opts.update(options or {})
-    lower = np.array([-np.inf, -np.inf if scaled else raw0[1], -np.inf, -np.inf])
-    upper = np.array([np.inf, np.inf if scaled else raw0[1], np.inf, np.inf])
-    res = minimize(objective, raw0, jac=True, method='L-BFGS-B', bounds=list(zip(lower, upper)), options=opts)
-    beta, s, noise, mean = objective.transform(res.x)
+    if optimizer == 'device':
+        pri = []
+        for p in objective.priors:
+            pri += [p[0], p[1]] if p is not None else [0.0, 0.0]
+        if not scaled:
+            starts = starts.copy()
+            starts[:, 1] = raw0[1]
+        raws, fs, info = ops.gp_fit(objective.dmat, objective.y, torch.from_numpy(np.ascontiguousarray(starts)),
+                                    objective.beta_min, objective.noise_min, pri, [0, 0 if scaled else 1, 0, 0],
+                                    maxiter=int(opts['maxiter']), pgtol=float(opts.get('gtol', 1e-5)),
+                                    ftol=float(opts.get('ftol', 2.220446049250313e-09)))
+        fs = np.where(np.isfinite(fs), fs, np.inf)
+        best = int(np.argmin(fs))
+        if not np.isfinite(fs[best]):
+            raise _lib.GaboError('fit_gpytorch_model: the covariance is not positive definite at any start')
+        xbest, fbest = raws[best], float(fs[best])
+        nit, nev, success = int(info[best, 1]), int(info[:, 2].sum()), bool(info[best, 0] in (0, 1))
+    elif optimizer == 'scipy':
+        from scipy.optimize import minimize
+        lower = np.array([-np.inf, -np.inf if scaled else raw0[1], -np.inf, -np.inf])
+        upper = np.array([np.inf, np.inf if scaled else raw0[1], np.inf, np.inf])
+        res = minimize(objective, starts[0], jac=True, method='L-BFGS-B', bounds=list(zip(lower, upper)), options=opts)
+        xbest, fbest, nit, nev, success = res.x, float(res.fun), int(res.nit), objective.evaluations, bool(res.success)
+    else:
+        raise ValueError("optimizer must be 'device' or 'scipy'")
+    beta, s, noise, mean = objective.transform(xbest)
     base.beta = beta
     if scaled:
         cov.outputscale = s
     model.noise, model.mean = noise, mean
-    model.fit_result = {'objective': float(res.fun), 'iterations': int(res.nit), 'evaluations': objective.evaluations,
-                        'converged': bool(res.success), 'theta': (beta, s, noise, mean)}
+    model.fit_result = {'objective': fbest, 'iterations': nit, 'evaluations': nev, 'converged': success,
+                        'theta': (beta, s, noise, mean), 'optimizer': optimizer}
     return mll
 
 

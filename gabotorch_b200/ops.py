@@ -677,6 +677,32 @@ def gp_mll(dmat, y, theta, want_grad=True, want_factors=False):
     return ll, grad, alpha, kinv, flags
 
 
+def gp_fit(dmat, y, raw0, beta_min, noise_min, priors, fixed, maxiter=15000, pgtol=1e-5, ftol=2.220446049250313e-09):
+    """``gabo_gp_fit``: BFGS fits of (raw_beta, raw_outputscale, raw_noise, mean) from the starts ``raw0`` (B, 4), all in
+    one launch.  ``priors``: 6 floats (Gamma concentration, rate for beta, outputscale, noise; concentration <= 0: none);
+    ``fixed``: 4 ints.  Returns host numpy (raw (B, 4), f (B,), info (B, 3) = status, iterations, evaluations) after ONE
+    read-back."""
+    lib = _lib.load()
+    dmat = to_dev64(dmat)
+    y = to_dev64(y).reshape(-1)
+    raw0 = to_dev64(raw0).reshape(-1, 4)
+    n, B = y.shape[0], raw0.shape[0]
+    if tuple(dmat.shape) != (n, n):
+        raise ValueError('dmat must be (n, n) with n = len(y)')
+    dev = dmat.device
+    pri = torch.tensor([float(v) for v in priors], dtype=torch.float64)
+    fix = torch.tensor([int(v) for v in fixed], dtype=torch.int32)
+    # one packed result buffer: raw (4), f (1), info as doubles (3) per start -> a single device-to-host copy
+    out_raw = torch.empty(B, 4, dtype=torch.float64, device=dev)
+    out_f = torch.empty(B, dtype=torch.float64, device=dev)
+    out_info = torch.empty(B, 3, dtype=torch.int32, device=dev)
+    _lib.check(lib.gabo_gp_fit(_p(dmat), n, _p(y), _p(raw0), B, float(beta_min), float(noise_min), _p(pri), _p(fix),
+                               int(maxiter), float(pgtol), float(ftol), _p(out_raw), _p(out_f), _p(out_info),
+                               _lib.stream_ptr()), 'gabo_gp_fit')
+    packed = torch.cat([out_raw, out_f[:, None], out_info.double()], dim=1).cpu().numpy()
+    return packed[:, :4], packed[:, 4], packed[:, 5:].astype(int)
+
+
 def gp_factor(kmat, y, outputscale, noise, mean):
     """alpha = (s K + noise I)^-1 (y - m) and (s K + noise I)^-1 from a base-kernel matrix (``gabo_gp_factor``)."""
     lib = _lib.load()

@@ -316,6 +316,19 @@ int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt, int64_t n
  * ------------------------------------------------------------------------------------------------------------------ */
 int gabo_gp_mll(const double* dmat, int64_t n, const double* y, const double* theta, int64_t batch, double* out_ll,
                 double* out_grad, double* out_alpha, double* out_kinv, int* flags, void* stream);
+/* The whole fit in ONE launch (what botorch.fit_gpytorch_model does with scipy's L-BFGS-B, one objective evaluation =
+ * one Gram rebuild + Cholesky + autograd per call, gabo_sphere.py:162): `batch` independent starts, one CTA each, run BFGS
+ * (dense 4 x 4 inverse Hessian = full-memory L-BFGS, Armijo backtracking) on
+ *   f(raw) = -(ll(theta) + log-priors(theta)) / n,
+ *   theta = (beta_min + softplus(raw[0]), softplus(raw[1]), noise_min + softplus(raw[2]), raw[3])
+ * i.e. gpytorch's constraints and botorch's objective.  raw0 / out_raw: batch x 4; priors: 6 doubles = Gamma
+ * (concentration, rate) for beta, outputscale, noise (concentration <= 0: no prior); fixed: 4 ints, != 0 holds that raw
+ * parameter at its start value; stop: max|g| <= pgtol, relative decrease <= ftol, or maxiter.
+ * out_f: batch (inf when the start is not positive definite); out_info: batch x 3 ints = {status (0 pgtol, 1 ftol,
+ * 2 maxiter, 3 line search failed, 4 not PD), iterations, objective evaluations}. */
+int gabo_gp_fit(const double* dmat, int64_t n, const double* y, const double* raw0, int64_t batch, double beta_min,
+                double noise_min, const double* priors, const int* fixed, int maxiter, double pgtol, double ftol,
+                double* out_raw, double* out_f, int* out_info, void* stream);
 /* Factorisation only, from a base-kernel matrix the Gram kernels already produced (what gabo_gp_desc needs once the
  * hyper-parameters are known): alpha = (s kmat + noise I)^-1 (y - m), kinv = (s kmat + noise I)^-1; *flag = 1 when the
  * matrix is not positive definite.  Same kernel, same limits. */

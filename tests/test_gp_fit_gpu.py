@@ -91,8 +91,9 @@ def test_objective_in_raw_parameters_vs_oracle_spd():
         assert abs(vals[1] - ref) <= 1e-9 * max(1.0, abs(ref))
 
 
+@pytest.mark.parametrize('optimizer', ['device', 'scipy'])
 @pytest.mark.parametrize('raw_samples', [0, 64])
-def test_fit_matches_scipy_on_the_oracle_objective(raw_samples):
+def test_fit_matches_scipy_on_the_oracle_objective(raw_samples, optimizer):
     # the model of gabo_sphere.py:131-147: ScaleKernel(SphereGaussianKernel) with Gamma(2, 0.15) on the outputscale,
     # Gamma(1.1, 0.05) on the noise starting at its mode, constant mean
     from scipy.optimize import minimize
@@ -111,7 +112,8 @@ def test_fit_matches_scipy_on_the_oracle_objective(raw_samples):
 
     raw0 = np.array([0.0, 0.0, gp_fit._inv_softplus(mode - 1e-8), 0.0])
     start = f(raw0)
-    out = g.fit_gpytorch_model(mll=mll, raw_samples=raw_samples, generator=3)
+    out = g.fit_gpytorch_model(mll=mll, raw_samples=raw_samples, generator=3, optimizer=optimizer)
+    assert model.fit_result['optimizer'] == optimizer
     assert out is mll
     res = model.fit_result
     beta, s, noise, mean = res['theta']
@@ -132,6 +134,32 @@ def test_fit_matches_scipy_on_the_oracle_objective(raw_samples):
     ei = g.ExpectedImprovement(model, best_f=float(y.min()), maximize=False)
     vals = ei(torch.from_numpy(osph.rand(np.random.default_rng(0), 50, 3))[:, None, :])
     assert vals.shape == (50,) and torch.isfinite(vals).all() and (vals >= 0).all()
+
+
+def test_device_fit_many_starts_in_one_launch():
+    # gabo_gp_fit: one CTA per start; every start ends at a stationary point of the oracle objective, the best is kept
+    x, y = _sphere_problem(32, 3, 21)
+    d = osph.sphere_distance(torch.from_numpy(x), torch.from_numpy(x)).numpy()
+    dm = d * d
+    rng = np.random.default_rng(0)
+    starts = np.vstack([[0.0, 0.0, 3.0, 0.0], rng.standard_normal((15, 4)) * np.array([2.0, 2.0, 3.0, 0.5])])
+    pri = [0.0, 0.0, 2.0, 0.15, 1.1, 0.05]
+    raws, fs, info = ops.gp_fit(torch.from_numpy(dm), torch.from_numpy(y), torch.from_numpy(starts), 6.5, 1e-8, pri,
+                                [0, 0, 0, 0])
+    assert raws.shape == (16, 4) and np.isfinite(fs).all() and (info[:, 0] <= 1).all() and (info[:, 1] >= 1).all()
+    for raw, f in zip(raws, fs):
+        ref = ogp.mll_objective(dm, y, raw, 6.5, outputscale_prior=(2.0, 0.15), noise_prior=(1.1, 0.05))
+        assert abs(ref - f) <= 1e-9 * max(1.0, abs(ref))
+        num = np.array([(ogp.mll_objective(dm, y, raw + e, 6.5, outputscale_prior=(2.0, 0.15), noise_prior=(1.1, 0.05))
+                         - ogp.mll_objective(dm, y, raw - e, 6.5, outputscale_prior=(2.0, 0.15), noise_prior=(1.1, 0.05)))
+                        / 2e-5 for e in 1e-5 * np.eye(4)])
+        assert np.abs(num).max() <= 5e-4                      # stationary (pgtol 1e-5 or flat to ftol)
+    f0 = [ogp.mll_objective(dm, y, s0, 6.5, outputscale_prior=(2.0, 0.15), noise_prior=(1.1, 0.05)) for s0 in starts]
+    assert (fs <= np.array(f0) + 1e-12).all()
+    # a fixed parameter stays where it started
+    raws2, _, _ = ops.gp_fit(torch.from_numpy(dm), torch.from_numpy(y), torch.from_numpy(starts[:3]), 6.5, 1e-8, pri,
+                             [0, 1, 0, 0])
+    np.testing.assert_array_equal(raws2[:, 1], starts[:3, 1])
 
 
 def test_fit_unscaled_kernel_and_unsupported_kernel():
