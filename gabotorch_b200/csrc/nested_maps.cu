@@ -395,6 +395,141 @@ nested_spd_reconstruct_kernel(const double* __restrict__ y, const double* __rest
     }
 }
 
+// Symmetric form with the operator resident in shared memory (used whenever it fits).  ncu on the kernel above (round 1):
+// 20 % of HBM, fp64 pipe 36 % busy, long_scoreboard on the P loads -- the 128 KB operator does not fit L1 next to the
+// shared-memory tiles and is re-read from L2 for every 32-point tile; and the contraction itself (2 D^2 K FLOP per point,
+// fp64) needs 58 TFLOP/s to keep up with HBM, more than the chip has.  X is symmetric, so only the column pairs of the
+// UPPER triangle are contracted (D (D+1)/2 entries instead of D^2: half the FLOP) and mirrored on the store, and that half
+// of P (K x ~D(D+1)/2 doubles: 70 KB for SPD(5) -> SPD(20)) is staged ONCE per persistent CTA in shared memory.
+// Work item = one pair of row-adjacent upper-triangle entries x 8 points; per k: one 16-byte P load and four 16-byte
+// broadcast u loads from shared memory feed 16 DFMA.
+constexpr int kReconSymThreads = 224;
+constexpr int kReconLd = kReconPts + 2;   // padded row stride of the tile inputs (even: 16-byte aligned rows)
+constexpr int kReconFill = 8;             // tile entries per thread held in registers (K * 32 <= 8 * 224)
+
+__global__ void __launch_bounds__(kReconSymThreads, 2)
+nested_spd_reconstruct_sym_kernel(const double* __restrict__ y, const double* __restrict__ sq, int64_t n, int D, int d,
+                                  const double* __restrict__ pack, double* __restrict__ x, int npairs) {
+    extern __shared__ __align__(16) double smem_sym[];
+    const int dd = d * d, DD = D * D, K = dd + d * (d + 1) / 2;
+    double* Ps = smem_sym;                            // K x (2 npairs): pair p holds entries (r, c0), (r, c0 + 1)
+    double* Zs = Ps + static_cast<size_t>(K) * 2 * npairs;   // 2 npairs
+    double* u = Zs + 2 * npairs;                      // K x kReconLd
+    int* tab = reinterpret_cast<int*>(u + K * kReconLd);     // npairs: r << 8 | c0 ; bit 16: second entry valid
+    const double* __restrict__ Z = pack + 2 * D * d;
+    const double* __restrict__ P = Z + DD;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    // pair table: row r contributes the pairs (r, r), (r, r+2), ... ; an odd run ends with a single
+    if (tid == 0) {
+        int p = 0;
+        for (int r = 0; r < D; ++r)
+            for (int c = r; c < D; c += 2) tab[p++] = (r << 8) | c | ((c + 1 < D) ? (1 << 16) : 0);
+    }
+    __syncthreads();
+    for (int e = tid; e < (K + 1) * npairs; e += nthr) {
+        const int k = e / npairs, p = e % npairs;
+        const int t = tab[p], r = (t >> 8) & 0xff, c0 = t & 0xff;
+        const bool two = (t >> 16) & 1;
+        const double* src = (k < K) ? P + static_cast<size_t>(k) * DD : Z;
+        double* dst = (k < K) ? Ps + static_cast<size_t>(k) * 2 * npairs : Zs;
+        dst[2 * p] = src[r * D + c0];
+        dst[2 * p + 1] = two ? src[r * D + c0 + 1] : 0.0;
+    }
+    const int items = npairs * (kReconPts / kReconHalf);
+    const int64_t tiles = (n + kReconPts - 1) / kReconPts;
+    // Tile inputs u[k][pt] (k-major, row stride kReconLd: the padding spreads the transposing stores over the banks).
+    // Entry e = tid + j nthr of a tile is (pt, k) = (e / K, e % K) for EVERY tile, so its source offset and its slot are
+    // computed once; the values of the NEXT tile are loaded into registers before the contraction of the current one
+    // (ncu on the first version of this kernel: long_scoreboard on these loads + 19 % IMAD for the index arithmetic).
+    int src[kReconFill], dst[kReconFill];
+#pragma unroll
+    for (int j = 0; j < kReconFill; ++j) {
+        const int e = tid + j * nthr;
+        src[j] = -1;
+        dst[j] = 0;
+        if (e < K * kReconPts) {
+            const int pt = e / K, k = e % K;
+            int off;
+            if (k < dd) {
+                off = k;
+            } else {                                  // k - dd enumerates (a, q), a <= q, row-major
+                int rem = k - dd, a = 0;
+                while (rem >= d - a) {
+                    rem -= d - a;
+                    ++a;
+                }
+                off = a * d + a + rem;
+            }
+            src[j] = (pt * dd + off) * 2 + (k < dd ? 0 : 1);   // low bit: 0 = y, 1 = sq
+            dst[j] = (k * kReconLd + pt) | (pt << 20);
+        }
+    }
+    double val[kReconFill];
+    auto prefetch = [&](int64_t i0) {
+#pragma unroll
+        for (int j = 0; j < kReconFill; ++j) {
+            double v = 0.0;
+            if (src[j] >= 0 && i0 + (dst[j] >> 20) < n) {
+                const double* base = (src[j] & 1) ? sq : y;
+                v = __ldg(base + i0 * dd + (src[j] >> 1));
+            }
+            val[j] = v;
+        }
+    };
+    if (static_cast<int64_t>(blockIdx.x) < tiles) prefetch(static_cast<int64_t>(blockIdx.x) * kReconPts);
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t i0 = t * kReconPts;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kReconFill; ++j)
+            if (src[j] >= 0) u[dst[j] & 0xfffff] = val[j];
+        __syncthreads();
+        if (t + gridDim.x < tiles) prefetch((t + gridDim.x) * kReconPts);
+        for (int it = tid; it < items; it += nthr) {
+            const int p = it % npairs, h = it / npairs;
+            double a0[kReconHalf], a1[kReconHalf];
+            const double2 zv = *reinterpret_cast<const double2*>(Zs + 2 * p);
+#pragma unroll
+            for (int pt = 0; pt < kReconHalf; ++pt) {
+                a0[pt] = zv.x;
+                a1[pt] = zv.y;
+            }
+            // (a hand-pipelined form of this loop -- operands of step k + 1 loaded during the DFMAs of step k -- measured
+            // slower: 0.149 ms against 0.125 ms at N = 65536; the compiler's own schedule of the 4x unrolled loop is kept)
+            const double* pp = Ps + 2 * p;
+            const double* up = u + h * kReconHalf;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k, pp += 2 * npairs, up += kReconLd) {
+                const double2 pv = *reinterpret_cast<const double2*>(pp);
+                const double2* uk = reinterpret_cast<const double2*>(up);
+#pragma unroll
+                for (int q = 0; q < kReconHalf / 2; ++q) {
+                    const double2 uv = uk[q];
+                    a0[2 * q] = fma(uv.x, pv.x, a0[2 * q]);
+                    a0[2 * q + 1] = fma(uv.y, pv.x, a0[2 * q + 1]);
+                    a1[2 * q] = fma(uv.x, pv.y, a1[2 * q]);
+                    a1[2 * q + 1] = fma(uv.y, pv.y, a1[2 * q + 1]);
+                }
+            }
+            const int tb = tab[p], r = (tb >> 8) & 0xff, c0 = tb & 0xff;
+            const bool two = (tb >> 16) & 1;
+            const int64_t ib = i0 + h * kReconHalf;
+#pragma unroll
+            for (int pt = 0; pt < kReconHalf; ++pt) {
+                if (ib + pt < n) {
+                    double* xo = x + (ib + pt) * DD;
+                    xo[r * D + c0] = a0[pt];
+                    if (c0 != r) xo[c0 * D + r] = a0[pt];                 // mirrored entry
+                    if (two) {
+                        xo[r * D + c0 + 1] = a1[pt];
+                        xo[(c0 + 1) * D + r] = a1[pt];
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 }  // namespace gabo
 
@@ -492,8 +627,25 @@ extern "C" int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt
     if (n == 0) return GABO_OK;
     GABO_REQUIRE(y && y_sqrt && pack && x, GABO_E_ARG, "gabo_nested_spd_reconstruct: null pointer");
     const int K = d * d + d * (d + 1) / 2;
-    const size_t smem = sizeof(double) * static_cast<size_t>(K) * kReconPts;
     const int64_t tiles = (n + kReconPts - 1) / kReconPts;
+    {   // symmetric form with the operator in shared memory, when it fits twice per SM
+        int npairs = 0;
+        for (int r = 0; r < D; ++r) npairs += (D - r + 1) / 2;
+        const size_t smem_sym = sizeof(double) * (static_cast<size_t>(K + 1) * 2 * npairs + static_cast<size_t>(K) * kReconLd) +
+                                sizeof(int) * npairs + 16;
+        if (smem_sym <= 100u * 1024u && tiles >= 4 && K * kReconPts <= kReconFill * kReconSymThreads) {
+            const cudaError_t e = cudaFuncSetAttribute(nested_spd_reconstruct_sym_kernel,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       static_cast<int>(smem_sym));
+            GABO_REQUIRE(e == cudaSuccess, GABO_E_CUDA, "nested_spd_reconstruct_sym_kernel: cudaFuncSetAttribute: %s",
+                         cudaGetErrorString(e));
+            const unsigned grid_sym = static_cast<unsigned>(imin(tiles, static_cast<int64_t>(sm_count()) * 2));
+            nested_spd_reconstruct_sym_kernel<<<grid_sym, kReconSymThreads, smem_sym, static_cast<cudaStream_t>(stream)>>>(
+                y, y_sqrt, n, D, d, pack, x, npairs);
+            return check_launch("nested_spd_reconstruct_sym_kernel");
+        }
+    }
+    const size_t smem = sizeof(double) * static_cast<size_t>(K) * kReconPts;
     const unsigned grid = static_cast<unsigned>(imin(tiles, static_cast<int64_t>(sm_count()) * 6));
     // block size: the work items (column pairs x point halves) split evenly over the passes of the item loop
     const int items = ((D * D + 1) / 2) * (kReconPts / kReconHalf);

@@ -18,6 +18,7 @@ namespace {
 
 constexpr int kTileRows = 64;
 constexpr int kStages = 3;
+constexpr int kMaxStages = 6;                 // ring depth limit (shared memory decides: 4 stages for SPD(20))
 constexpr int kSplitK = 4;                    // warps sharing a row group, each with a quarter of the k range
 constexpr int kThreadsP = 4 * kSplitK * 32;   // 16 warps
 
@@ -94,8 +95,12 @@ __global__ void __launch_bounds__(kThreadsP, 1)
     const int stage_floats = kTileRows * dvh;  // 64 * dvh * 4 bytes: a multiple of 256
     const int os_floats = (kTileRows * dvl + 3) & ~3;
     float* As = reinterpret_cast<float*>(smem_raw);
-    float* Bp = As + nstages * stage_floats;
-    float* Os = Bp + ksteps * 32 * NT * 4;          // kSplitK partial output tiles; part 0 becomes the total
+    // KH > 0: the operator fragments live in registers, so their shared-memory image is only needed while they are
+    // loaded -- it borrows the LAST ring stage, whose first TMA copy is issued after that.  The space this frees buys a
+    // fourth ring stage (SPD(20): 4 x 53.8 KB): with three stages only ~107 KB per SM were in flight while a tile was
+    // being processed, short of the ~90-130 KB Little's law asks for at 44 GB/s per SM and 2-3 us loaded HBM latency.
+    float* Bp = (KH > 0) ? As + (nstages - 1) * stage_floats : As + nstages * stage_floats;
+    float* Os = (KH > 0) ? As + nstages * stage_floats : Bp + ksteps * 32 * NT * 4;   // kSplitK partial output tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(Os + kSplitK * os_floats);
 
     const int64_t tiles = (n + kTileRows - 1) / kTileRows;
@@ -114,10 +119,10 @@ __global__ void __launch_bounds__(kThreadsP, 1)
             tma_load_1d(As + stage * stage_floats, x + tile * kTileRows * dvh, full_bytes, &bars[stage]);
         }
     };
+    const int early = (KH > 0) ? nstages - 1 : nstages;   // stages whose first copy can start right away
     if (threadIdx.x == 0) {
-        for (int s = 0; s < nstages; ++s) issue(static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x, s);
+        for (int s = 0; s < early; ++s) issue(static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(s) * gridDim.x, s);
     }
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rowgrp = warp & 3, khalf = warp >> 2;   // khalf: which part of the k range (0 .. kSplitK-1)
     const int g = lane >> 2, t = lane & 3;
@@ -141,6 +146,11 @@ __global__ void __launch_bounds__(kThreadsP, 1)
                 breg[i][j] = (s_begin + i < s_end)
                                  ? reinterpret_cast<const float4*>(Bp)[(s_begin + i) * 32 * NT + lane * NT + j]
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();                                   // everyone has its fragments: the borrowed stage is free
+        if (threadIdx.x == 0) {
+            fence_proxy_async();                           // generic-proxy reads of Bp before the async-proxy write
+            issue(static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(nstages - 1) * gridDim.x, nstages - 1);
+        }
     }
     uint32_t phase_bits = 0u;
     int it = 0;
@@ -257,15 +267,22 @@ template <int NT>
 int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, float* y, cudaStream_t s) {
     const int ksteps = ksteps_for(dvh);
     // ring depth: kStages when it fits the 227 KB of shared memory, otherwise 2 (long Mandel vectors)
+    constexpr int kRegSteps = (NT <= 2) ? 7 : 0;
+    const bool in_regs = kRegSteps > 0 && (ksteps + kSplitK - 1) / kSplitK <= kRegSteps;
+    // operator in registers: no resident shared-memory image (it borrows the last stage at start-up), ring as deep as fits
+    // up to kMaxStages; otherwise the image stays and the ring is kStages deep when that fits, 2 for long Mandel vectors
     auto smem_for = [&](int stages) {
-        return sizeof(float) * (static_cast<size_t>(stages) * kTileRows * dvh + static_cast<size_t>(ksteps) * 32 * NT * 4 +
-                                kSplitK * ((kTileRows * dvl + 3) & ~3)) + 8 * kStages + 16;
+        const size_t op = in_regs ? 0 : static_cast<size_t>(ksteps) * 32 * NT * 4;
+        return sizeof(float) * (static_cast<size_t>(stages) * kTileRows * dvh + op + kSplitK * ((kTileRows * dvl + 3) & ~3)) +
+               8 * kMaxStages + 16;
     };
-    int nstages = kStages;
+    int nstages = in_regs ? kMaxStages : kStages;
     while (nstages > 2 && smem_for(nstages) > 227 * 1024) --nstages;
     const size_t smem = smem_for(nstages);
     GABO_REQUIRE(smem <= 227 * 1024, GABO_E_UNSUPPORTED,
                  "gabo_nested_spd_project: Mandel length %d needs %zu bytes of shared memory (> 227 KB)", dvh, smem);
+    GABO_REQUIRE(!in_regs || static_cast<size_t>(ksteps) * 32 * NT * 4 <= static_cast<size_t>(kTileRows) * dvh, GABO_E_UNSUPPORTED,
+                 "gabo_nested_spd_project: operator image does not fit a ring stage");
     const int64_t tiles = (n + kTileRows - 1) / kTileRows;
     const unsigned grid = static_cast<unsigned>(imin(tiles, sm_count()));
     const bool even = (dvh % 2) == 0;
@@ -275,8 +292,7 @@ int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, fl
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         kern<<<grid, kThreadsP, smem, s>>>(x, n, dvh, dvl, ksteps, nstages, pack, y);
     };
-    constexpr int kRegSteps = (NT <= 2) ? 7 : 0;
-    if (kRegSteps > 0 && (ksteps + kSplitK - 1) / kSplitK <= kRegSteps) {
+    if (in_regs) {
         if (even) go(nested_project_kernel<NT, true, kRegSteps>);
         else go(nested_project_kernel<NT, false, kRegSteps>);
     } else {

@@ -475,8 +475,17 @@ class _NestedSpdMixin:
     def _wants_autograd(self, *xs):
         return _wants_input_grad(*xs) or _needs_param_grad(self.raw_projection_matrix)
 
+    #: rows from which ``projection='auto'`` streams the inputs through the tensor-core projection
+    TENSOR_CORE_ROWS = 16384
+
     def _project(self, x, autograd=False):
-        """Mandel vectors of SPD(dim) -> Mandel vectors of SPD(latent_dim): G3 -> P1 -> G3 of SURVEY section 8."""
+        """Mandel vectors of SPD(dim) -> Mandel vectors of SPD(latent_dim): G3 -> P1 -> G3 of SURVEY section 8.
+
+        Two device paths.  ``gabo_nested_spd_project_f64`` (fp64 in / out) for training-set-sized inputs: the projected
+        matrices feed an affine-invariant distance whose error grows with their condition number.  The tensor-core GEMM
+        ``gabo_nested_spd_project`` (3xTF32, fp32 in / out, ~1e-6 relative, HBM-bound) for the raw-sample screening of
+        hd_gabo_spd.py:239-256 -- hundreds of thousands to millions of Mandel vectors whose kernel values are only ranked.
+        ``self.projection``: 'auto' (tensor cores from ``TENSOR_CORE_ROWS`` rows when ``compute == 'f32'``), 'f64', 'tf32'."""
         w = self.raw_projection_matrix
         if w.dim() != 2:
             raise NotImplementedError('batched projection matrices (batch_shape != []) are not supported')
@@ -484,15 +493,29 @@ class _NestedSpdMixin:
             if x.dim() != 2:
                 raise NotImplementedError('gradients are provided for (N, dv) Mandel inputs')
             return _NestedSpdProject.apply(x, w)
+        mode = getattr(self, 'projection', 'auto')
+        rows = int(x.numel() // x.shape[-1]) if x.shape[-1] else 0
+        tensor = mode == 'tf32' or (mode == 'auto' and getattr(self, 'compute', 'f64') == 'f32'
+                                    and rows >= self.TENSOR_CORE_ROWS)
+        if tensor and self.latent_dim <= _lib.MAX_SPD_DIM:
+            wd = w.detach().double()
+            key = (wd.data_ptr(), w._version, str(wd.device))
+            if getattr(self, '_pack_key', None) != key:              # operator packed once per value of W
+                self._pack = ops.nested_projection_matrix(wd)
+                self._pack_key = key
+            flat = torch.as_tensor(x).reshape(-1, x.shape[-1])
+            y = ops.nested_spd_project(flat, self.dim, self.latent_dim, self._pack)
+            return y.double().reshape(tuple(x.shape[:-1]) + (y.shape[-1],))
         return ops.nested_spd_project_f64(x, w.detach().double())
 
 
 class NestedSpdAffineInvariantGaussianKernel(_NestedSpdMixin, _BetaKernel):
     """exp(-beta d_AI(W^T X1 W, W^T X2 W)^2) for Mandel-vectorised SPD(dim) inputs (kernels_nested_spd.py:19-136)."""
 
-    def __init__(self, dim, latent_dim, beta_min, beta_prior=None, compute='f32', **kwargs):
+    def __init__(self, dim, latent_dim, beta_min, beta_prior=None, compute='f32', projection='auto', **kwargs):
         _BetaKernel.__init__(self, beta_min, beta_prior=beta_prior, **kwargs)
         self.compute = compute
+        self.projection = projection
         self._init_projection(dim, latent_dim)
 
     def forward(self, x1, x2, diagonal_distance=False, **params):

@@ -241,3 +241,29 @@ def test_nested_spd_reconstruction_right_inverse(D, d, n):
     assert np.linalg.eigvalsh(0.5 * (x + np.swapaxes(x, -1, -2))).min() > 0
     with pytest.raises(ops.NotPositiveDefiniteError):
         nm.NestedSpdReconstruction(torch.from_numpy(w), torch.from_numpy(v), torch.from_numpy(-c), torch.from_numpy(k))
+
+
+def test_nested_kernel_streams_raw_samples_through_the_tensor_core_projection():
+    # hd_gabo_spd.py:239-256: the acquisition screens raw samples of SPD(20) against the training set through the nested
+    # kernel; from TENSOR_CORE_ROWS rows the projection runs on the tensor cores (3xTF32, fp32) instead of the fp64 kernel
+    import gabotorch_b200 as g
+    from oracle import spd as ospd
+    rng = np.random.default_rng(3)
+    D, d, n_raw, n_train = 20, 5, 20000, 24
+    raw = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(ospd.spd_sample(rng, n_raw, D, max_cond=50.0)))
+    train = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(ospd.spd_sample(rng, n_train, D, max_cond=50.0)))
+    k = g.NestedSpdAffineInvariantGaussianKernel(D, d, beta_min=0.25)
+    k.projection_matrix = torch.from_numpy(onest.grassmann_rand(rng, D, d))
+    assert n_raw >= k.TENSOR_CORE_ROWS
+    with torch.no_grad():
+        auto = k.forward(raw.cuda(), train.cuda())
+        k.projection = 'f64'
+        exact = k.forward(raw.cuda(), train.cuda())
+        k.projection = 'tf32'
+        forced = k.forward(raw[:100].cuda(), train.cuda())
+    assert float((forced - auto[:100]).abs().max()) <= 5e-6          # same path; fp32 pair kernel, different tile shapes
+    m = exact >= 1e-6
+    rel = ((auto - exact).abs()[m] / exact[m]).max()
+    assert float(rel) <= 2e-4, float(rel)          # fp32 projection: ~1e-6 on the entries, amplified by cond(Y) and beta d^2
+    assert torch.equal(torch.argsort(auto.sum(1))[-50:].sort().values, torch.argsort(exact.sum(1))[-50:].sort().values) or \
+        float((auto.sum(1) - exact.sum(1)).abs().max()) <= 1e-3
