@@ -15,7 +15,10 @@
 // 3xTF32 split) feed three MMAs with no register shuffling.  The round-1 form had the streamed rows as the A fragment:
 // its four values per lane come from two rows, and interleaving them cost 62 IMAD.MOV per loop body -- 21 % of all
 // instructions (ncu), which is what kept the kernel at 70 % of HBM (6.7 k warp-instructions per tile at 2 per clock).
+#include <cstdlib>
+
 #include "spd_common.cuh"
+#include "nested_project_tc.cuh"
 
 namespace gabo {
 namespace {
@@ -284,8 +287,36 @@ __global__ void __launch_bounds__(kThreadsP, kCtasPerSm)
     }
 }
 
+// Canonical (K-major, no-swizzle UMMA core-matrix) image of the operator for the tcgen05 kernel: [hi | lo], 16 x kp floats each,
+// float index of (n, k) = ((k / 4) * 2 + n / 8) * 32 + (n % 8) * 4 + k % 4; rows n >= dvl and columns k >= dvh are zero.
+__global__ void projection_pack_canonical_kernel(const double* __restrict__ w, int D, int d, int kp, float* __restrict__ out) {
+    const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
+    const int total = tc::kN * kp;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int o = e / kp, i = e % kp;
+        double v = 0.0;
+        if (o < dvl && i < dvh) {
+            int a, b, p, q;
+            mandel_rc_dev(d, o, a, b);
+            mandel_rc_dev(D, i, p, q);
+            const double mab = (a == b) ? 1.0 : 1.4142135623730951;
+            if (p == q) v = mab * w[p * d + a] * w[p * d + b];
+            else v = mab * (w[p * d + a] * w[q * d + b] + w[q * d + a] * w[p * d + b]) / 1.4142135623730951;
+        }
+        const float hi = to_tf32(static_cast<float>(v));
+        const float lo = to_tf32(static_cast<float>(v - static_cast<double>(hi)));
+        const int idx = ((i / 4) * 2 + o / 8) * 32 + (o % 8) * 4 + i % 4;
+        out[idx] = hi;
+        out[total + idx] = lo;
+    }
+}
+
 int ksteps_for(int dvh) { return (dvh + 7) / 8; }
+// tcgen05 path: at most 16 output Mandel entries (d <= 5) and a tile ring + chunk buffers + operator inside 227 KB
+bool tc_eligible(int dvh, int dvl) { return dvl <= tc::kN && tc::Smem(dvh).total <= 227u * 1024u; }
+int64_t fragment_pack_floats(int dvh, int dvl);
 int ntiles_for(int dvl) { return (dvl + 15) / 16; }   // m16 tiles of output Mandel entries
+int64_t fragment_pack_floats(int dvh, int dvl) { return static_cast<int64_t>(ksteps_for(dvh)) * 32 * ntiles_for(dvl) * 8; }
 
 template <int MT>
 int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, float* y, cudaStream_t s) {
@@ -378,7 +409,9 @@ extern "C" int gabo_nested_spd_project_f64(const double* x_mandel, int64_t n, in
 
 extern "C" int64_t gabo_nested_projection_pack_size(int D, int d) {
     if (D < 1 || d < 1 || d > D || d > GABO_MAX_SPD_DIM) return -1;
-    return static_cast<int64_t>(gabo::ksteps_for(D * (D + 1) / 2)) * 32 * gabo::ntiles_for(d * (d + 1) / 2) * 8;
+    const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
+    // [mma.sync fragment image | canonical UMMA image (hi, lo) when the tcgen05 kernel can take the shape]
+    return gabo::fragment_pack_floats(dvh, dvl) + (gabo::tc_eligible(dvh, dvl) ? 2 * gabo::tc::kN * gabo::tc::Smem(dvh).kp : 0);
 }
 
 extern "C" int gabo_nested_projection_matrix(const double* w, int D, int d, float* p_pack, void* stream) {
@@ -391,6 +424,12 @@ extern "C" int gabo_nested_projection_matrix(const double* w, int D, int d, floa
     const int total = ksteps * 32 * nt * 4;
     projection_pack_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, D, d, ksteps, nt,
                                                                                               p_pack);
+    const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
+    if (tc_eligible(dvh, dvl)) {
+        const int kp = tc::Smem(dvh).kp;
+        projection_pack_canonical_kernel<<<(tc::kN * kp + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            w, D, d, kp, p_pack + fragment_pack_floats(dvh, dvl));
+    }
     return check_launch("projection_pack_kernel");
 }
 
@@ -406,6 +445,26 @@ extern "C" int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, 
                  "gabo_nested_spd_project: x and pack must be 16-byte aligned");
     const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // The tcgen05 / TMEM kernel (nested_project_tc.cuh) is parity-green but SLOWER than the mma.sync kernel on this shape
+    // (N = 2^20: 0.597 ms against 0.196 ms): with 16 output columns every tcgen05.mma is a 64 x 16 x 8 product, and the 81
+    // dependent products of a 64-row tile run at ~110 cycles each (fixed issue / operand-fetch latency, far above the
+    // 8-cycle throughput floor), i.e. ~9 k cycles per tile where HBM needs 2.4 k.  It is therefore opt-in
+    // (GABO_PROJECT_KERNEL=tc) and kept as the measured answer to "would tcgen05 help this GEMM?".
+    static const bool want_tc = [] {
+        const char* e = std::getenv("GABO_PROJECT_KERNEL");
+        return e != nullptr && e[0] == 't';
+    }();
+    if (tc_eligible(dvh, dvl) && want_tc && n >= tc::kRows) {
+        const tc::Smem L(dvh);
+        const cudaError_t e = cudaFuncSetAttribute(tc::nested_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(L.total));
+        GABO_REQUIRE(e == cudaSuccess, GABO_E_CUDA, "nested_project_tc_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        const int64_t tiles = (n + tc::kRows - 1) / tc::kRows;
+        const unsigned grid = static_cast<unsigned>(imin(tiles, sm_count()));
+        tc::nested_project_tc_kernel<<<grid, tc::kThreads, L.total, s>>>(x_mandel, n, dvh, dvl,
+                                                                         p_pack + fragment_pack_floats(dvh, dvl), y_mandel);
+        return check_launch("nested_project_tc_kernel");
+    }
     switch (ntiles_for(dvl)) {
         case 1: return launch_nt<1>(x_mandel, n, dvh, dvl, p_pack, y_mandel, s);
         case 2: return launch_nt<2>(x_mandel, n, dvh, dvl, p_pack, y_mandel, s);

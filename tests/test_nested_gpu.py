@@ -267,3 +267,13 @@ def test_nested_kernel_streams_raw_samples_through_the_tensor_core_projection():
     assert float(rel) <= 2e-4, float(rel)          # fp32 projection: ~1e-6 on the entries, amplified by cond(Y) and beta d^2
     assert torch.equal(torch.argsort(auto.sum(1))[-50:].sort().values, torch.argsort(exact.sum(1))[-50:].sort().values) or \
         float((auto.sum(1) - exact.sum(1)).abs().max()) <= 1e-3
+
+
+def test_projection_tcgen05_kernel_parity():
+    # the opt-in tcgen05 / TMEM kernel (GABO_PROJECT_KERNEL=tc, read once per process): same results as the default kernel
+    import os, subprocess, sys
+    env = dict(os.environ, GABO_PROJECT_KERNEL='tc')
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), '..', 'scripts', 'dev_tc.py'), '--parity-only'],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'kernel: tc' in out.stdout and 'FAIL' not in out.stdout and out.stdout.count(' OK') >= 7, out.stdout
