@@ -445,11 +445,9 @@ extern "C" int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, 
                  "gabo_nested_spd_project: x and pack must be 16-byte aligned");
     const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // The tcgen05 / TMEM kernel (nested_project_tc.cuh) is parity-green but SLOWER than the mma.sync kernel on this shape
-    // (N = 2^20: 0.597 ms against 0.196 ms): with 16 output columns every tcgen05.mma is a 64 x 16 x 8 product, and the 81
-    // dependent products of a 64-row tile run at ~110 cycles each (fixed issue / operand-fetch latency, far above the
-    // 8-cycle throughput floor), i.e. ~9 k cycles per tile where HBM needs 2.4 k.  It is therefore opt-in
-    // (GABO_PROJECT_KERNEL=tc) and kept as the measured answer to "would tcgen05 help this GEMM?".
+    // The tcgen05 / TMEM kernel (nested_project_tc.cuh) is parity-green but slower than the mma.sync kernel on this skinny
+    // shape (N = 2^20: 0.64 ms against 0.196 ms; ~110 cycles per 64 x 16 x 8 tcgen05.mma, see its header): opt-in with
+    // GABO_PROJECT_KERNEL=tc, kept as the measured answer to "would tcgen05 help this GEMM as it stands?".
     static const bool want_tc = [] {
         const char* e = std::getenv("GABO_PROJECT_KERNEL");
         return e != nullptr && e[0] == 't';

@@ -1,11 +1,16 @@
 // Nested SPD projection on the 5th-generation tensor cores: tcgen05.mma.kind::tf32 with the accumulators in TMEM.
 // Included by nested_project.cu (same pack buffer, same entry point).
 //
-// STATUS: parity-green (tests/test_nested_gpu.py with GABO_PROJECT_KERNEL=tc) and opt-in: measured 0.597 ms at N = 2^20 against
-// 0.196 ms for the mma.sync kernel.  With only 16 output columns each tcgen05.mma is a 64 x 16 x 8 product; the 81 dependent
-// products of a tile run at ~110 cycles each (issue / operand-fetch latency, not the 8-cycle throughput floor).  Making the
-// products fat enough to hide that latency means the streamed rows must be the N operand (N = 128..256) with the operator
-// as a 64-row A operand -- which does not fit next to the TMA ring in 227 KB of shared memory without moving A into TMEM.
+// STATUS: parity-green on the B200 (tests/test_nested_gpu.py::test_projection_tcgen05_kernel_parity) and OPT-IN
+// (GABO_PROJECT_KERNEL=tc): it is slower than the mma.sync kernel on this shape.  Measured at N = 2^20 (scripts/micro/
+// project_variants.cu, profiles/r02_*): 0.643 ms against 0.196 ms.  Ablations: without the MMAs (split / pack pass, barriers,
+// commits, epilogue) 0.314 ms; without the pack pass (MMAs on stale buffers) 0.554 ms.  With 16 output columns each tcgen05.mma
+// is a 64 x 16 x 8 product and costs ~110 cycles in SS mode whether or not consecutive products share an accumulator (one
+// accumulator pair: 0.597 ms; 12 independent TMEM accumulators used round-robin, the current form: 0.643 ms) -- the
+// shared-memory operand fetch of each instruction is not hidden at this size, far above the 8-cycle dispatch floor.  A form that
+// would win needs fat products: the streamed rows as the N operand (N = 256: 128 rows x {hi, lo}) and the operator as the A
+// operand held in TMEM; the tile ring, the packed chunks and a 64-row operator image do not fit in 227 KB of shared memory
+// together.  Left for the next round; the mma.sync kernel (0.74 of HBM) stays the default.
 //
 // Why it was built: the ablation of the mma.sync kernel (scripts/micro/project_variants.cu, profiles/r02_*) shows that kernel is bound by
 // the LEGACY tensor pipe -- with one HMMA.1688.TF32 per k-step instead of the three of 3xTF32 it streams at 0.98 of HBM, with
@@ -35,7 +40,10 @@ constexpr int kChunkCols = 72;       // columns per packed chunk (9 k-steps of 8
 constexpr int kChunkKc = kChunkCols / 4;   // 16-byte k-chunks per packed chunk
 constexpr int kThreads = 256;
 constexpr int kN = 16;               // output Mandel entries per MMA (dvl <= 16)
-constexpr int kAccCols = 64;         // TMEM columns: 2 tiles in flight x (main, small) x 16
+constexpr int kPhases = 4;            // independent accumulators per product: k-step s accumulates into phase s % kPhases
+constexpr int kAccPerTile = 3 * kPhases;   // (hi*hi, lo*hi, hi*lo) x phases, 16 TMEM columns each
+constexpr int kTileCols = 256;       // TMEM columns reserved per tile in flight (12 x 16 = 192 used)
+constexpr int kAccCols = 512;        // TMEM columns allocated: 2 tiles in flight
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // cute::UMMA::SmemDescriptor: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version 1 [46,48), layout NONE
@@ -142,13 +150,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     auto epilogue = [&](int64_t tile, int par) {         // warps 0-3: rows 16 warp .. 16 warp + 15 on TMEM lanes 32 warp + 0..15
         if (warp < 4) {
             float a[16], b[16];
-            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + static_cast<uint32_t>(par * 32);
-            tmem_ld16(t0, a);
-            tmem_ld16(t0 + 16, b);
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(32 * warp) << 16) + static_cast<uint32_t>(par * kTileCols);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a[c] = 0.0f;
+            // small products first (accumulators kPhases .. 3 kPhases - 1), then the hi * hi partial tiles
+#pragma unroll 1
+            for (int q = kAccPerTile - 1; q >= 0; --q) {
+                tmem_ld16(t0 + static_cast<uint32_t>(q * 16), b);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) a[c] += b[c];
+            }
             const int64_t row = tile * kRows + 16 * warp + lane;
             if (lane < 16 && row < n) {
                 float* dst = y + row * dvl;
-                for (int c = 0; c < dvl; ++c) __stcs(dst + c, a[c] + b[c]);
+                for (int c = 0; c < dvl; ++c) __stcs(dst + c, a[c]);
             }
         }
         tc_fence_before();
@@ -177,7 +192,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int j = 0; j < (kChunkKc + 3) / 4; ++j) {
                 const int kc = kc0 + 4 * j;
+#if defined(GABO_TC_ABLATE) && GABO_TC_ABLATE == 2      // ablation 2: no split / pack pass (MMAs on stale buffers)
+                if (kc < 0) {
+#else
                 if (kc < kChunkKc) {
+#endif
                     const int col = c * kChunkCols + 4 * kc;
                     float v[4];
                     if (even && col + 3 < dvh) {     // 8-byte aligned pairs only when the row pitch is even
@@ -205,7 +224,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(hi), a_lo = smem_u32(lo);
-                const uint32_t d_main = tmem_base + static_cast<uint32_t>(par * 32), d_small = d_main + 16;
+                // A chain of dependent tcgen05.mma into ONE accumulator runs at the pipeline latency (~110 cycles per 64 x 16 x 8
+                // product, measured), not at the 8-cycle dispatch floor.  So every product type gets kPhases independent
+                // accumulators, used round-robin over the k-steps: consecutive MMAs never touch the same TMEM columns and
+                // the 12 chains overlap; the epilogue adds the 12 partial tiles.
+                const uint32_t d_tile = tmem_base + static_cast<uint32_t>(par * kTileCols);
 #pragma unroll 1
                 for (int s = 0; s < kChunkCols / 8; ++s) {
                     const int ks = c * (kChunkCols / 8) + s;                       // global k-step
@@ -213,10 +236,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const uint64_t dal = umma_desc(a_lo + 2048u * s, 1024u, 128u);
                     const uint64_t dbh = umma_desc(op_hi + 512u * ks, 256u, 128u);
                     const uint64_t dbl = umma_desc(op_lo + 512u * ks, 256u, 128u);
-                    const uint32_t acc = (ks > 0) ? 1u : 0u;
-                    umma_tf32(d_main, dah, dbh, acc);
-                    umma_tf32(d_small, dal, dbh, acc);
-                    umma_tf32(d_small, dah, dbl, 1u);
+                    const uint32_t acc = (ks >= kPhases) ? 1u : 0u;
+                    const uint32_t col = d_tile + static_cast<uint32_t>((ks % kPhases) * 16);
+#if !defined(GABO_TC_ABLATE) || GABO_TC_ABLATE != 1   // ablation 1 (scripts/micro/project_variants.cu): no MMAs
+                    umma_tf32(col, dah, dbh, acc);                                 // hi * hi
+                    umma_tf32(col + kPhases * 16, dal, dbh, acc);                  // lo(x) * hi(P)
+                    umma_tf32(col + 2 * kPhases * 16, dah, dbl, acc);              // hi(x) * lo(P)
+#endif
                 }
                 umma_commit(&bars[2 + buf]);
                 if (c == L.nchunks - 1) umma_commit(&bars[4 + par]);
