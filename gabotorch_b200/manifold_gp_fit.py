@@ -42,6 +42,14 @@ class EuclideanParam:
     def __init__(self, *shape):
         self._shape = tuple(shape)
 
+    @property
+    def typicaldist(self):
+        return math.sqrt(float(np.prod(self._shape)))
+
+    @property
+    def dim(self):
+        return int(np.prod(self._shape))
+
     def rand(self):
         return np.random.randn(*self._shape)
 
@@ -68,6 +76,12 @@ class SphereParam:
 
     def __init__(self, n):
         self._n = int(n)
+
+    typicaldist = math.pi
+
+    @property
+    def dim(self):
+        return self._n - 1
 
     def rand(self):
         v = np.random.randn(self._n)
@@ -99,6 +113,14 @@ class GrassmannParam:
     def __init__(self, n, p):
         self._n, self._p = int(n), int(p)
 
+    @property
+    def typicaldist(self):
+        return math.sqrt(self._p)
+
+    @property
+    def dim(self):
+        return self._p * (self._n - self._p)
+
     def rand(self):
         q, _ = np.linalg.qr(np.random.randn(self._n, self._p))
         return q
@@ -127,6 +149,14 @@ class ProductParam:
 
     def __init__(self, manifolds):
         self.manifolds = list(manifolds)
+
+    @property
+    def typicaldist(self):
+        return math.sqrt(sum(m.typicaldist ** 2 for m in self.manifolds))
+
+    @property
+    def dim(self):
+        return sum(m.dim for m in self.manifolds)
 
     def rand(self):
         return [m.rand() for m in self.manifolds]
@@ -249,6 +279,118 @@ def riemannian_cg(manifold, cost, cost_grad, x0, solver=None, callback=None):
         it += 1
     return x, {'iterations': it, 'stop': stop, 'cost': f, 'gradnorm': gradnorm, 'costevals': costevals,
                'time': time.time() - t0}
+
+
+def riemannian_trust_regions(manifold, cost, cost_grad, x0, solver=None):
+    """pymanopt 0.2.x ``TrustRegions.solve`` (Steihaug-Toint truncated CG, no preconditioner, ``use_rand=False``) on a
+    (product) manifold with numpy points, the Hessian-vector product being the finite difference of the gradient that the
+    reference installs everywhere (``get_hessianfd``, approximate_hessian.py:11-62: step 2^-14 / |a|, transport back).
+    ``solver``: a ``manifold_optimization.TrustRegions`` options holder.  Returns (x, log)."""
+    from .manifold_optimization import TrustRegions
+    s = solver or TrustRegions()
+    maxiter, mingradnorm, maxtime = int(s._maxiter), float(s._mingradnorm), float(s._maxtime)
+    kappa, theta, rho_prime, rho_reg_fact = float(s.kappa), float(s.theta), float(s.rho_prime), float(s.rho_regularization)
+    mininner = int(getattr(s, 'mininner', 1))
+    maxinner = int(manifold.dim if getattr(s, 'maxinner', None) is None else s.maxinner)
+    delta_bar = float(manifold.typicaldist if getattr(s, 'Delta_bar', None) is None else s.Delta_bar)
+    delta = float(delta_bar / 8 if getattr(s, 'Delta0', None) is None else s.Delta0)
+    eps = float(np.spacing(1))
+    t0 = time.time()
+
+    def grad_at(x):
+        f, eg = cost_grad(x)
+        return f, manifold.egrad2rgrad(x, eg)
+
+    def hess(x, gx, a):
+        na = manifold.norm(x, a)
+        if na < 1e-15:
+            return _lin(0.0, a)
+        c = 2.0 ** -14 / na
+        x1 = manifold.retr(x, _lin(c, a))
+        g1 = grad_at(x1)[1]
+        return _lin(1.0 / c, manifold.transp(x1, x, g1), -1.0 / c, gx)
+
+    x = x0
+    fx, gx = grad_at(x)
+    ng = manifold.norm(x, gx)
+    k, stop = 0, ''
+    while True:
+        if time.time() - t0 >= maxtime:
+            stop = 'maxtime'
+        elif k >= maxiter:
+            stop = 'maxiter'
+        elif ng < mingradnorm:
+            stop = 'mingradnorm'
+        if stop:
+            break
+        # ---- truncated CG from eta = 0 ----
+        eta, heta = _lin(0.0, gx), _lin(0.0, gx)
+        r = gx
+        e_pe, r_r = 0.0, manifold.inner(x, gx, gx)
+        norm_r0 = math.sqrt(r_r)
+        z_r, d_pd, e_pd = r_r, r_r, 0.0
+        dlt = _lin(-1.0, r)
+        model_value, inner_stop = 0.0, 'maxinner'
+        for j in range(maxinner):
+            hd = hess(x, gx, dlt)
+            d_hd = manifold.inner(x, dlt, hd)
+            alpha = z_r / d_hd if d_hd != 0 else float('inf')
+            e_pe_new = e_pe + 2.0 * alpha * e_pd + alpha * alpha * d_pd
+            if d_hd <= 0 or e_pe_new >= delta * delta:
+                tau = (-e_pd + math.sqrt(e_pd * e_pd + d_pd * (delta * delta - e_pe))) / d_pd
+                eta = _lin(1.0, eta, tau, dlt)
+                heta = _lin(1.0, heta, tau, hd)
+                inner_stop = 'negative curvature' if d_hd <= 0 else 'exceeded'
+                break
+            e_pe = e_pe_new
+            new_eta = _lin(1.0, eta, alpha, dlt)
+            new_heta = _lin(1.0, heta, alpha, hd)
+            new_model = manifold.inner(x, new_eta, gx) + 0.5 * manifold.inner(x, new_eta, new_heta)
+            if new_model >= model_value:
+                inner_stop = 'model increased'
+                break
+            eta, heta, model_value = new_eta, new_heta, new_model
+            r = _lin(1.0, r, alpha, hd)
+            r_r = manifold.inner(x, r, r)
+            norm_r = math.sqrt(r_r)
+            if j + 1 >= mininner and norm_r <= norm_r0 * min(norm_r0 ** theta, kappa):
+                inner_stop = 'target'
+                break
+            zold = z_r
+            z_r = r_r
+            beta = z_r / zold
+            dlt = manifold.proj(x, _lin(-1.0, r, beta, dlt))
+            e_pd = beta * (e_pd + alpha * d_pd)
+            d_pd = z_r + beta * beta * d_pd
+        # ---- accept / reject, radius update ----
+        x_prop = manifold.retr(x, eta)
+        f_prop = cost(x_prop)
+        rhonum = fx - f_prop
+        rhoden = -manifold.inner(x, gx, eta) - 0.5 * manifold.inner(x, heta, eta)
+        reg = max(1.0, abs(fx)) * eps * rho_reg_fact
+        rhonum, rhoden = rhonum + reg, rhoden + reg
+        model_decreased = rhoden >= 0
+        rho = rhonum / rhoden if rhoden != 0 else float('nan')
+        if rho < 0.25 or not model_decreased or math.isnan(rho):
+            delta /= 4.0
+        elif rho > 0.75 and inner_stop in ('negative curvature', 'exceeded'):
+            delta = min(2.0 * delta, delta_bar)
+        if model_decreased and rho > rho_prime:
+            x, fx = x_prop, f_prop
+            fx, gx = grad_at(x)
+            ng = manifold.norm(x, gx)
+        k += 1
+    return x, {'iterations': k, 'stop': stop, 'cost': fx, 'gradnorm': ng, 'time': time.time() - t0}
+
+
+def solve_on_manifold(manifold, cost, cost_grad, x0, solver):
+    """Dispatch on the solver options object (``ConjugateGradient`` or ``TrustRegions``), as ``solver.solve(problem, x=x0)``."""
+    name = type(solver).__name__
+    if name == 'ConjugateGradient':
+        return riemannian_cg(manifold, cost, cost_grad, x0, solver)
+    if name == 'TrustRegions':
+        return riemannian_trust_regions(manifold, cost, cost_grad, x0, solver)
+    raise NotImplementedError('solver %s is not supported here (ConjugateGradient, TrustRegions)' % name)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -66,6 +66,8 @@ for rep in sorted(f for f in os.listdir(go) if f.endswith('.ncu-rep')):
     for r in rows:
         d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
         name = re.sub(r'^void |unnamed>::|<unnamed>::|gabo::', '', d.get('Kernel Name', '?')).split('(')[0]
+        if name in traffic:      # first capture of a kernel wins (prof_spd_gram = the headline launch sorts before _n8192)
+            continue
         traffic[name] = {'dram_bytes_read': _bytes(d['dram__bytes_read.sum'], u['dram__bytes_read.sum']),
                          'dram_bytes_write': _bytes(d['dram__bytes_write.sum'], u['dram__bytes_write.sum']),
                          'gpu_time_us_under_ncu': float(d['gpu__time_duration.sum'].replace(',', '')) * {'us': 1, 'ms': 1e3, 'ns': 1e-3}[u['gpu__time_duration.sum']],

@@ -648,3 +648,67 @@ def test_riemannian_cg_on_a_product_manifold_finds_the_known_minimiser():
     u = man.proj(x, man.rand())
     assert abs(np.trace(x[1].T @ u[1])) < 1e-12 and abs(x[2] @ u[2]) < 1e-12
     assert mgf.host_manifold(mgf.GrassmannParam(5, 2))._n == 5
+
+
+def test_riemannian_trust_regions_on_a_product_manifold():
+    """Host trust-region solver behind optimize_reconstruction_parameters_nested_sphere (pymanopt TrustRegions semantics,
+    finite-difference Hessian): same closed-form problem as the CG test."""
+    from gabotorch_b200 import manifold_gp_fit as mgf
+    rng = np.random.default_rng(1)
+    np.random.seed(1)
+    A = rng.standard_normal((6, 6)); A = A @ A.T
+    B = rng.standard_normal((4, 4)); B = B @ B.T
+    man = mgf.ProductParam([mgf.EuclideanParam(1), mgf.GrassmannParam(6, 2), mgf.SphereParam(4)])
+    assert man.dim == 1 + 8 + 3
+
+    def cost(x):
+        t, X, v = x
+        return float((t[0] - 2.0) ** 2 - np.trace(X.T @ A @ X) - v @ B @ v)
+
+    def cost_grad(x):
+        t, X, v = x
+        return cost(x), [np.array([2.0 * (t[0] - 2.0)]), -2.0 * A @ X, -2.0 * B @ v]
+
+    x, log = mgf.solve_on_manifold(man, cost, cost_grad, man.rand(), g.TrustRegions(maxiter=200, mingradnorm=1e-7))
+    want = -np.sort(np.linalg.eigvalsh(A))[-2:].sum() - np.linalg.eigvalsh(B)[-1]
+    assert log['stop'] == 'mingradnorm' and log['iterations'] < 200, log
+    assert abs(log['cost'] - want) <= 1e-9 * abs(want), (log, want)
+    assert np.abs(x[1].T @ x[1] - np.eye(2)).max() < 1e-12 and abs(np.linalg.norm(x[2]) - 1.0) < 1e-12
+    with pytest.raises(NotImplementedError):
+        mgf.solve_on_manifold(man, cost, cost_grad, man.rand(), object())
+
+
+def test_nested_sphere_reconstruction_cost_and_fit_host_logic(monkeypatch):
+    """nested_spheres_optimization.py:20-98: the differentiable inverse chain equals the oracle's (pinned on the reference's
+    own functions), its gradient matches finite differences, and the fit recovers the distances that generated the data.
+    The tensor code is device-agnostic; here it runs on CPU tensors (ops.to_dev64 replaced), the device run is in
+    tests/test_nested_gpu.py."""
+    from gabotorch_b200 import nested_optimization as nopt
+    from oracle import nested_sphere as onsph, sphere as osph
+    monkeypatch.setattr(nopt.ops, 'to_dev64', lambda x: torch.as_tensor(x, dtype=torch.float64))
+    monkeypatch.setattr(nopt, '_dev64_keep_grad', lambda x: torch.as_tensor(x, dtype=torch.float64))
+    rng = np.random.default_rng(5)
+    np.random.seed(5)
+    D, d, n = 6, 3, 40
+    axes = [torch.from_numpy(osph.rand(rng, 1, k)) for k in range(D, d, -1)]
+    true_r = [1.1, 0.7, 1.9]
+    xs = torch.from_numpy(osph.rand(rng, n, d))
+    dists = [torch.tensor([[r]], dtype=torch.float64) for r in true_r]
+    xd = onsph.projection_from_subsphere_to_sphere(xs, axes, dists)[-1]
+    ours = nopt._reconstruct(xs, [a.reshape(-1) for a in axes], torch.tensor(true_r, dtype=torch.float64))
+    assert float((ours - xd).abs().max()) < 1e-13
+    assert float(nopt.min_error_reconstruction_cost(xd, xs, axes, dists)) < 1e-12
+    # gradient of the cost with respect to the distances vs central differences
+    p = torch.tensor([0.9, 1.0, 1.5], dtype=torch.float64, requires_grad=True)
+    f = nopt._cost_from_distances(xd, xs, [a.reshape(-1) for a in axes], p)
+    f.backward()
+    for i in range(3):
+        e = torch.zeros(3, dtype=torch.float64); e[i] = 1e-6
+        fd = (nopt._cost_from_distances(xd, xs, [a.reshape(-1) for a in axes], p.detach() + e)
+              - nopt._cost_from_distances(xd, xs, [a.reshape(-1) for a in axes], p.detach() - e)) / 2e-6
+        assert abs(float(fd) - float(p.grad[i])) <= 1e-5 * max(1.0, abs(float(fd)))
+    for solver in (g.TrustRegions(), g.ConjugateGradient(maxiter=300)):
+        out = g.optimize_reconstruction_parameters_nested_sphere(xd, xs, axes, solver, nb_init_candidates=50)
+        assert len(out) == 3 and all(tuple(o.shape) == (1,) and o.dtype == torch.float32 for o in out)
+        got = np.array([float(o) for o in out])
+        assert np.abs(got - np.array(true_r)).max() < 2e-3, (got, true_r)

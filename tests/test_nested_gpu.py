@@ -277,3 +277,27 @@ def test_projection_tcgen05_kernel_parity():
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'kernel: tc' in out.stdout and 'FAIL' not in out.stdout and out.stdout.count(' OK') >= 7, out.stdout
+
+
+def test_optimize_reconstruction_parameters_nested_sphere_on_device():
+    # nested_spheres_optimization.py:41-98 (hd_gabo_sphere.py:196-199): data generated with known distances-to-axis are
+    # recovered; the cost equals the oracle's composition of the reference-pinned inverse chain and sphere distance
+    import gabotorch_b200 as g
+    from oracle import nested_sphere as onsph, sphere as osph
+    rng = np.random.default_rng(12)
+    np.random.seed(12)
+    D, d, n = 7, 3, 64
+    axes = [torch.from_numpy(osph.rand(rng, 1, k)) for k in range(D, d, -1)]
+    true_r = [1.3, 0.8, 2.0, 1.1]
+    xs = torch.from_numpy(osph.rand(rng, n, d))
+    dists = [torch.tensor([[r]], dtype=torch.float64) for r in true_r]
+    xd = onsph.projection_from_subsphere_to_sphere(xs, axes, dists)[-1]
+    wrong = [torch.tensor([[r + 0.2]], dtype=torch.float64) for r in true_r]
+    c_dev = float(g.min_error_reconstruction_cost(xd, xs, axes, wrong))
+    xr = onsph.projection_from_subsphere_to_sphere(xs, axes, wrong)[-1]
+    c_ref = float((osph.sphere_distance(xd, xr, diag=True) ** 2).sum())
+    assert abs(c_dev - c_ref) <= 1e-10 * max(1.0, c_ref)
+    out = g.optimize_reconstruction_parameters_nested_sphere(xd, xs, axes, g.TrustRegions(), nb_init_candidates=100)
+    got = np.array([float(o) for o in out])
+    assert np.abs(got - np.array(true_r)).max() < 2e-3, (got, true_r)
+    assert g.optimize_reconstruction_parameters_nested_sphere.last_log['cost'] < 1e-6
