@@ -12,7 +12,7 @@ Module map (reference module -> here):
     BoManifolds/manifold_optimization/manifold_optimize.py     -> gabotorch_b200.manifold_optimization
     BoManifolds/manifold_optimization/manifold_gp_fit.py       -> gabotorch_b200.manifold_gp_fit
     BoManifolds/nested_mappings/nested_spd_utils.py            -> gabotorch_b200.nested_mappings
-    BoManifolds/nested_mappings/nested_spheres_optimization.py -> gabotorch_b200.nested_optimization
+    BoManifolds/nested_mappings/nested_{spheres,spd}_optimization.py -> gabotorch_b200.nested_optimization
     pymanopt.manifolds.{Sphere,PositiveDefinite}               -> gabotorch_b200.manifolds
 """
 __version__ = '0.1.0'
@@ -34,5 +34,8 @@ from .nested_mappings import (NestedSpdProjection, NestedSpdReconstruction,  # n
 from .gp_fit import fit_gpytorch_model, ExactMarginalLogLikelihood  # noqa: F401
 from .manifold_gp_fit import fit_gpytorch_manifold  # noqa: F401
 from .nested_optimization import (min_error_reconstruction_cost,  # noqa: F401
-                                  optimize_reconstruction_parameters_nested_sphere)
+                                  optimize_reconstruction_parameters_nested_sphere,
+                                  min_affine_invariant_distance_reconstruction_cost,
+                                  min_log_euclidean_distance_reconstruction_cost,
+                                  optimize_reconstruction_parameters_nested_spd)
 from ._compat import GammaPrior  # noqa: F401

@@ -62,6 +62,7 @@ SIGNATURES = {
     'gabo_spd_ai_gram_backward': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     'gabo_frobenius_gram': (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_i32, c_f64, c_i32, c_ptr, c_i32, c_i64, c_ptr]),
     'gabo_spd_logm': (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
+    'gabo_sym_eig': (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'gabo_weighted_points_sum': (c_i32, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i32, c_i32, c_ptr, c_i32, c_ptr, c_ptr]),
     'gabo_spd_logm_backward': (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     'gabo_nested_spd_project_backward': (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),

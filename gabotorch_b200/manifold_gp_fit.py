@@ -70,6 +70,9 @@ class EuclideanParam:
     def transp(self, x, y, u):
         return u
 
+    def dist(self, x, y):
+        return float(np.linalg.norm(x - y))
+
 
 class SphereParam:
     """pymanopt ``Sphere(n)`` (vectors): projection retraction, projection transport."""
@@ -104,6 +107,9 @@ class SphereParam:
 
     def transp(self, x, y, u):
         return self.proj(y, u)
+
+    def dist(self, x, y):
+        return float(np.arccos(np.clip(np.dot(x.ravel(), y.ravel()), -1.0, 1.0)))
 
 
 class GrassmannParam:
@@ -143,6 +149,65 @@ class GrassmannParam:
     def transp(self, x, y, u):
         return self.proj(y, u)
 
+    def dist(self, x, y):
+        s = np.linalg.svd(x.T @ y, compute_uv=False)
+        return float(np.linalg.norm(np.arccos(np.clip(s, None, 1.0))))
+
+
+def _sym(a):
+    return 0.5 * (a + a.T)
+
+
+class SpdParam:
+    """pymanopt 0.2.x ``PositiveDefinite(n)`` (k = 1): affine-invariant metric tr(X^-1 U X^-1 V), Riemannian gradient
+    X sym(G) X, exponential map as the retraction, identity transport, random points U diag(1 + rand) U^T."""
+
+    def __init__(self, n):
+        self._n = int(n)
+
+    @property
+    def typicaldist(self):
+        return math.sqrt(self._n * (self._n + 1) / 2.0)
+
+    @property
+    def dim(self):
+        return self._n * (self._n + 1) // 2
+
+    def rand(self):
+        d = 1.0 + np.random.rand(self._n)
+        u, _ = np.linalg.qr(np.random.randn(self._n, self._n))
+        return (u * d) @ u.T
+
+    def inner(self, x, u, v):
+        return float(np.tensordot(np.linalg.solve(x, u), np.linalg.solve(x, v).T, axes=2))
+
+    def norm(self, x, u):
+        c = np.linalg.cholesky(x)
+        w = np.linalg.solve(c, np.linalg.solve(c, u).T)       # L^-1 U L^-T
+        return float(np.linalg.norm(w))
+
+    def proj(self, x, u):
+        return _sym(u)
+
+    def egrad2rgrad(self, x, u):
+        return x @ _sym(u) @ x
+
+    def retr(self, x, u):
+        c = np.linalg.cholesky(x)
+        w = _sym(np.linalg.solve(c, np.linalg.solve(c, _sym(u)).T))
+        lam, q = np.linalg.eigh(w)
+        cq = c @ q
+        return _sym((cq * np.exp(lam)) @ cq.T)
+
+    def transp(self, x, y, u):
+        return u
+
+    def dist(self, x, y):
+        c = np.linalg.cholesky(x)
+        w = _sym(np.linalg.solve(c, np.linalg.solve(c, y).T))
+        lam = np.linalg.eigvalsh(w)
+        return float(np.linalg.norm(np.log(lam)))
+
 
 class ProductParam:
     """pymanopt ``Product``: points and tangent vectors are lists, one entry per factor."""
@@ -179,6 +244,9 @@ class ProductParam:
     def transp(self, x, y, u):
         return [m.transp(a, b, c) for m, a, b, c in zip(self.manifolds, x, y, u)]
 
+    def dist(self, x, y):
+        return math.sqrt(sum(m.dist(a, b) ** 2 for m, a, b in zip(self.manifolds, x, y)))
+
 
 def _lin(a, x, b=None, y=None):
     """a x (+ b y) on lists of arrays."""
@@ -191,15 +259,17 @@ def host_manifold(obj):
     """Host parameter manifold for what a kernel stores as ``<parameter>_manifold`` (the package's stubs, or a pymanopt
     ``Grassmann`` / ``Sphere`` / ``Euclidean`` object, recognised by class name and its ``_n`` / ``_p`` attributes)."""
     name = type(obj).__name__
-    if isinstance(obj, (EuclideanParam, SphereParam, GrassmannParam)):
+    if isinstance(obj, (EuclideanParam, SphereParam, GrassmannParam, SpdParam, ProductParam)):
         return obj
+    if 'PositiveDefinite' in name:
+        return SpdParam(obj._n)
     if 'Grassmann' in name:
         return GrassmannParam(obj._n, obj._p)
     if 'Sphere' in name:
         return SphereParam(getattr(obj, '_n', None) or obj._shape[0])
     if 'Euclidean' in name:
         return EuclideanParam(*obj._shape)
-    raise NotImplementedError('parameter manifold %s is not supported (Grassmann, Sphere, Euclidean)' % name)
+    raise NotImplementedError('parameter manifold %s is not supported (Grassmann, Sphere, PositiveDefinite, Euclidean)' % name)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -391,6 +461,93 @@ def solve_on_manifold(manifold, cost, cost_grad, x0, solver):
     if name == 'TrustRegions':
         return riemannian_trust_regions(manifold, cost, cost_grad, x0, solver)
     raise NotImplementedError('solver %s is not supported here (ConjugateGradient, TrustRegions)' % name)
+
+
+def riemannian_alm(manifold, cost, cost_grad, x0, solver, eq_constraints=None, ineq_constraints=None, lambdas=None,
+                   gammas=None, rho=None):
+    """The reference's ``AugmentedLagrangeMethod.solve`` (augmented_Lagrange_method.py:66-229, sub-problem :231-328; Liu &
+    Boumal 2019) for ONE start on a (product) manifold with numpy points: the host loop of the reconstruction fit.
+
+    ``cost(x) -> float`` and ``cost_grad(x) -> (float, Euclidean gradient)`` as for ``solve_on_manifold``; every
+    constraint is a callable ``x -> (value, Euclidean gradient)`` (equalities hold at 0, inequalities at >= 0).  ``solver``
+    is a ``manifold_optimization.AugmentedLagrangeMethod`` options holder whose inner solver (``TrustRegions`` or
+    ``ConjugateGradient``) is run by ``solve_on_manifold`` with the tolerance schedule of the reference
+    (``starting_tolgradnorm`` shrinking geometrically to ``ending_tolgradnorm`` over ``maxiter`` outer iterations).
+    Returns (x, log)."""
+    import copy
+    eqs = [] if eq_constraints is None else (list(eq_constraints) if isinstance(eq_constraints, (list, tuple))
+                                             else [eq_constraints])
+    ineqs = [] if ineq_constraints is None else (list(ineq_constraints) if isinstance(ineq_constraints, (list, tuple))
+                                                 else [ineq_constraints])
+    bound, thetarho, tau = float(solver._bound), float(solver._thetarho), float(solver._tau)
+    start_tol, end_tol = float(solver._starting_tolgradnorm), float(solver._ending_tolgradnorm)
+    maxiter, minstepsize, maxtime = int(solver._maxiter), float(solver._minstepsize), float(solver._maxtime)
+    lambdas = (float(solver._lambdas_fact) * np.ones(len(ineqs))) if lambdas is None else np.array(lambdas, dtype=float)
+    gammas = (float(solver._gammas_fact) * np.ones(len(eqs))) if gammas is None else np.array(gammas, dtype=float)
+    rho = float(solver._rho_init if rho is None else rho)
+    inner = copy.copy(solver.inner_solver)
+    tolgradnorm = start_tol
+    theta_tol = (end_tol / start_tol) ** (1.0 / maxiter)
+    oldacc = float('inf')
+    t0 = time.time()
+    x = x0
+    k, stop, inner_logs = 0, '', []
+    while True:
+        lam_k, gam_k, rho_k = lambdas.copy(), gammas.copy(), rho
+
+        def sub_cost(p):
+            f = cost(p)
+            for c, l in zip(ineqs, lam_k):
+                f += 0.5 * rho_k * max(0.0, l / rho_k - c(p)[0]) ** 2
+            for c, g in zip(eqs, gam_k):
+                f += 0.5 * rho_k * (g / rho_k + c(p)[0]) ** 2
+            return f
+
+        def sub_cost_grad(p):
+            f, grad = cost_grad(p)
+            grad = [np.array(g, dtype=float) for g in grad]
+            for c, l in zip(ineqs, lam_k):
+                v, gc = c(p)
+                if l / rho_k - v > 0:
+                    f += 0.5 * rho_k * (l / rho_k - v) ** 2
+                    grad = [g + (v * rho_k - l) * np.asarray(h) for g, h in zip(grad, gc)]
+            for c, g_mult in zip(eqs, gam_k):
+                v, gc = c(p)
+                f += 0.5 * rho_k * (g_mult / rho_k + v) ** 2
+                grad = [g + (v * rho_k + g_mult) * np.asarray(h) for g, h in zip(grad, gc)]
+            return f, grad
+
+        inner._mingradnorm = tolgradnorm
+        x_new, ilog = solve_on_manifold(manifold, sub_cost, sub_cost_grad, x, inner)
+        inner_logs.append((ilog['iterations'], ilog['stop']))
+        newacc = 0.0
+        for i, c in enumerate(ineqs):
+            v = c(x_new)[0]
+            newacc = max(newacc, abs(max(-lambdas[i] / rho, v)))
+            lambdas[i] = min(bound, max(lambdas[i] + rho * v, 0.0))
+        for i, c in enumerate(eqs):
+            v = c(x_new)[0]
+            newacc = max(newacc, abs(v))
+            gammas[i] = min(bound, max(-bound, gammas[i] + rho * v))
+        if k == 0 or newacc > tau * oldacc:
+            rho = rho / thetarho
+        oldacc = newacc
+        tolgradnorm = max(end_tol, tolgradnorm * theta_tol)
+        k += 1
+        stepsize = manifold.dist(x_new, x)
+        x = x_new
+        if time.time() - t0 >= maxtime:
+            stop = 'maxtime'
+        elif k >= maxiter:
+            stop = 'maxiter'
+        elif stepsize < minstepsize:
+            stop = 'minstepsize'
+        if tolgradnorm <= end_tol:
+            stop = 'mingradnorm'
+        if stop:
+            break
+    return x, {'iterations': k, 'stop': stop, 'cost': cost(x), 'violation': oldacc, 'rho': rho,
+               'lambdas': lambdas, 'gammas': gammas, 'inner': inner_logs, 'time': time.time() - t0}
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -109,13 +109,15 @@ class StrictConstrainedTrustRegions(ConstrainedTrustRegions):
 
 class AugmentedLagrangeMethod:
     """Constructor surface of the reference's ``AugmentedLagrangeMethod`` (augmented_Lagrange_method.py:30-62; pymanopt
-    ``Solver`` keywords behind it).  ``inner_solver`` must be a ``TrustRegions``."""
+    ``Solver`` keywords behind it).  The batched acquisition path (``gen_candidates_manifold``) drives ``TrustRegions`` as
+    inner solver; the host path of the reconstruction fit (``manifold_gp_fit.riemannian_alm``) also takes
+    ``ConjugateGradient`` (the inner solver of hd_gabo_spd.py:192)."""
 
     def __init__(self, inner_solver, bound=20, rho_init=1, thetarho=0.3, tau=0.8, starting_tolgradnorm=1e-3,
                  ending_tolgradnorm=1e-6, lambdas_fact=1., gammas_fact=1., maxtime=1000, maxiter=1000, mingradnorm=1e-6,
                  minstepsize=1e-10, maxcostevals=5000, logverbosity=0):
-        if type(inner_solver).__name__ != 'TrustRegions':
-            raise NotImplementedError('AugmentedLagrangeMethod: the batched path drives TrustRegions as inner solver')
+        if type(inner_solver).__name__ not in ('TrustRegions', 'ConjugateGradient'):
+            raise NotImplementedError('AugmentedLagrangeMethod: inner_solver must be TrustRegions or ConjugateGradient')
         self.inner_solver = inner_solver
         self._bound, self._rho_init, self._thetarho, self._tau = bound, rho_init, thetarho, tau
         self._starting_tolgradnorm, self._ending_tolgradnorm = starting_tolgradnorm, ending_tolgradnorm
@@ -907,6 +909,8 @@ def _gen_candidates_alm(initial_conditions, acquisition_function, manifold, solv
         if c is None:
             return None
         return batched_constraints(c if isinstance(c, (list, tuple)) else [c], kind)
+    if type(solver.inner_solver).__name__ != 'TrustRegions':
+        raise NotImplementedError('AugmentedLagrangeMethod: the batched path drives TrustRegions as inner solver')
     inner = _trust_region_options(solver.inner_solver)
     cand, val, iters, reason = batched_alm(
         gp, x0[:, 0], inner, ineq_constraints=as_batched(ineq), eq_constraints=as_batched(eq),

@@ -12,9 +12,18 @@ Here the cost and its gradient are device work: the inverse chain (rotation of t
 nested_spheres_utils.py:149-213) and the row-wise geodesic distance run as fp64 tensor code on the B200 for ALL candidates at
 once (one pass, one read-back), and for the solver's evaluations with torch.autograd over the same code; the solver itself is
 the host loop of ``manifold_gp_fit`` (pymanopt ``TrustRegions`` / ``ConjugateGradient`` semantics, finite-difference
-Hessian), a handful of scalars.  The SPD counterpart (``nested_spd_optimization.py:95-186``: augmented Lagrangian over
-Grassmann x SPD(D - d) x Sphere x R with affine-invariant distances on SPD(20)) is NOT provided: its cost lives on matrices
-beyond the d <= 8 register kernels of this package.
+Hessian), a handful of scalars.
+
+The SPD counterpart mirrors ``BoManifolds/nested_mappings/nested_spd_optimization.py``:
+``min_affine_invariant_distance_reconstruction_cost`` (:22-55), ``min_log_euclidean_distance_reconstruction_cost`` (:58-92)
+and ``optimize_reconstruction_parameters_nested_spd`` (:95-186, the step of hd_gabo_spd.py:230-233): the complement V of the
+projection, the bottom block C and the contraction K = sigmoid(s) * k (|k| = 1) are fitted on
+Grassmann(D, D - d) x SPD(D - d) x Sphere(d (D - d)) x R by the augmented Lagrangian method under W^T V = 0.  The data
+matrices are D x D (10 .. 20 in the reference's examples), beyond the d <= 8 register kernels: every cost evaluation is ONE
+launch of ``gabo_sym_eig`` (a warp per matrix, Jacobi in shared memory) over all N reconstructed matrices -- the reference
+runs N ``torch.symeig`` calls in a Python loop -- wrapped in autograd Functions whose backward is the Daleckii-Krein formula
+on the saved eigenpairs; the small products around it are batched fp64 device matmuls.  All ``nb_init_candidates`` random
+starts are screened in one batched pass.
 """
 import math
 
@@ -23,7 +32,8 @@ import torch
 
 from . import ops
 from .kernel_utils import _dev64_keep_grad
-from .manifold_gp_fit import EuclideanParam, ProductParam, solve_on_manifold
+from .manifold_gp_fit import (EuclideanParam, GrassmannParam, ProductParam, SphereParam, SpdParam, riemannian_alm,
+                              solve_on_manifold)
 
 
 def _rotate(v, p_from, p_to):
@@ -109,3 +119,195 @@ def optimize_reconstruction_parameters_nested_sphere(x_data, x_subsphere, sphere
     out = [transform(torch.tensor(np.asarray(v), dtype=torch.float32).reshape(1)) for v in opt]
     optimize_reconstruction_parameters_nested_sphere.last_log = dict(log, start_cost=float(vals.min()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# nested SPD mapping
+# ----------------------------------------------------------------------------------------------------------------
+
+class _SpectralFn(torch.autograd.Function):
+    """U f(lambda) U^T for a batch of symmetric D x D matrices (D <= 32) from ONE ``gabo_sym_eig`` launch; ``kind`` 0: f = log
+    (logm_torch, spd_utils_torch.py:13-30), 1: f = sqrt (sqrtm_torch, :33-50).  Backward: Daleckii-Krein,
+    U [(U^T sym(G) U) o F] U^T with F_ij the divided differences of f (log: log1p form, sqrt: 1 / (f_i + f_j) -- no
+    cancellation for close eigenvalues)."""
+
+    @staticmethod
+    def forward(ctx, mat, kind):
+        lam, vec, _ = ops.sym_eig(mat)
+        f = torch.log(lam) if kind == 0 else torch.sqrt(lam)
+        ctx.save_for_backward(lam, vec, f)
+        ctx.kind = kind
+        return (vec * f.unsqueeze(-2)) @ vec.transpose(-1, -2)
+
+    @staticmethod
+    def backward(ctx, g):
+        lam, vec, f = ctx.saved_tensors
+        gs = 0.5 * (g + g.transpose(-1, -2))
+        inner = vec.transpose(-1, -2) @ gs @ vec
+        if ctx.kind == 0:
+            lj = lam.unsqueeze(-2)
+            x = (lam.unsqueeze(-1) - lj) / lj
+            small = x.abs() < 1e-9
+            dd = torch.where(small, 1.0 - 0.5 * x, torch.log1p(x) / torch.where(small, torch.ones_like(x), x)) / lj
+        else:
+            dd = 1.0 / (f.unsqueeze(-1) + f.unsqueeze(-2))
+        return vec @ (inner * dd) @ vec.transpose(-1, -2), None
+
+
+class _LogEigSumSq(torch.autograd.Function):
+    """sum_k log^2 lambda_k(M) for a batch of symmetric positive definite matrices (the squared affine-invariant distance
+    when M = L^-1 X L^-T, spd_utils_torch.py:100-120); backward U diag(2 log(lambda) / lambda) U^T."""
+
+    @staticmethod
+    def forward(ctx, mat):
+        lam, vec, _ = ops.sym_eig(mat)
+        ll = torch.log(lam)
+        ctx.save_for_backward(lam, vec, ll)
+        return (ll * ll).sum(-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        lam, vec, ll = ctx.saved_tensors
+        w = (2.0 * ll / lam) * g.unsqueeze(-1)
+        return (vec * w.unsqueeze(-2)) @ vec.transpose(-1, -2)
+
+
+def _reconstruct_spd(y, y_sqrt, w, v, c, k):
+    """projection_from_nested_spd_to_spd (nested_spd_utils.py:51-118) as differentiable device code: y, y_sqrt (N, d, d);
+    w (D, d); v (..., D, m), c (..., m, m), k (..., d, m) with optional leading candidate dimensions -> (..., N, D, D)."""
+    lead = v.shape[:-2]
+    n = y.shape[0]
+    c_sqrt = _SpectralFn.apply(c, 1)
+    side = y_sqrt @ (k @ c_sqrt).unsqueeze(-3)                               # (..., N, d, m)
+    top = torch.cat([y.expand(lead + tuple(y.shape)), side], dim=-1)
+    bottom = torch.cat([side.transpose(-1, -2), c.unsqueeze(-3).expand(lead + (n,) + tuple(c.shape[-2:]))], dim=-1)
+    xr = torch.cat([top, bottom], dim=-2)
+    r = torch.cat([w.expand(lead + tuple(w.shape)), v], dim=-1).unsqueeze(-3)
+    return r @ xr @ r.transpose(-1, -2)
+
+
+class _SpdReconstructionCost:
+    """The two reconstruction costs with the data-only terms (sqrt of the latent matrices; inverse Cholesky factors or
+    logarithms of the data) computed once.  ``kind``: 'affine_invariant' or 'log_euclidean'."""
+
+    def __init__(self, x_data, x_data_projected, projection_matrix, kind):
+        self.kind = kind
+        self.x = ops.to_dev64(x_data)
+        self.y = ops.to_dev64(x_data_projected).to(self.x.device)
+        self.w = ops.to_dev64(projection_matrix).to(self.x.device)
+        if self.x.dim() != 3 or self.y.dim() != 3 or self.x.shape[0] != self.y.shape[0]:
+            raise ValueError('expected x_data (N, D, D) and x_data_projected (N, d, d)')
+        self.D, self.d = int(self.x.shape[-1]), int(self.y.shape[-1])
+        if tuple(self.w.shape) != (self.D, self.d):
+            raise ValueError('projection_matrix must be (D, d) = (%d, %d)' % (self.D, self.d))
+        with torch.no_grad():
+            self.y_sqrt = _SpectralFn.apply(self.y, 1)
+            if kind == 'affine_invariant':
+                # X = L L^T from the eigenpairs: L^-1 may be ANY factor with L^-1 X L^-T = I (the eigenvalues of
+                # L^-1 Xrec L^-T do not depend on the choice); X^(-1/2) = U diag(lambda^-1/2) U^T
+                lam, vec, _ = ops.sym_eig(self.x)
+                self.linv = (vec * lam.rsqrt().unsqueeze(-2)) @ vec.transpose(-1, -2)
+            elif kind == 'log_euclidean':
+                self.logx = _SpectralFn.apply(self.x, 0)
+            else:
+                raise ValueError('kind must be affine_invariant or log_euclidean')
+
+    def __call__(self, v, c, k):
+        xrec = _reconstruct_spd(self.y, self.y_sqrt, self.w, v, c, k)
+        if self.kind == 'affine_invariant':
+            m = self.linv @ xrec @ self.linv
+            return (_LogEigSumSq.apply(m) + 1e-15).sum(-1)
+        diff = self.logx - _SpectralFn.apply(xrec, 0) + 1e-15                 # frobenius_distance_torch, :156
+        return (diff * diff).sum((-1, -2)).sum(-1)
+
+
+def _spd_cost(kind, x_data, x_data_projected, projection_matrix, projection_complement_matrix, bottom_spd_matrix,
+              contraction_matrix):
+    fn = _SpdReconstructionCost(x_data, x_data_projected, projection_matrix, kind)
+    dev = fn.x.device
+    return fn(_dev64_keep_grad(projection_complement_matrix).to(dev), _dev64_keep_grad(bottom_spd_matrix).to(dev),
+              _dev64_keep_grad(contraction_matrix).to(dev))
+
+
+def min_affine_invariant_distance_reconstruction_cost(x_data, x_data_projected, projection_matrix,
+                                                      projection_complement_matrix, bottom_spd_matrix,
+                                                      contraction_matrix):
+    """Sum of squared affine-invariant distances between the SPD data and their reconstruction from the projections
+    Y = W^T X W (nested_spd_optimization.py:22-55).  Differentiable device code, 0-d fp64 tensor."""
+    return _spd_cost('affine_invariant', x_data, x_data_projected, projection_matrix, projection_complement_matrix,
+                     bottom_spd_matrix, contraction_matrix)
+
+
+def min_log_euclidean_distance_reconstruction_cost(x_data, x_data_projected, projection_matrix,
+                                                   projection_complement_matrix, bottom_spd_matrix, contraction_matrix):
+    """Same with the log-Euclidean distance ||logm X - logm Xrec + 1e-15||_F (nested_spd_optimization.py:58-92)."""
+    return _spd_cost('log_euclidean', x_data, x_data_projected, projection_matrix, projection_complement_matrix,
+                     bottom_spd_matrix, contraction_matrix)
+
+
+def optimize_reconstruction_parameters_nested_spd(x_data, x_data_projected, projection_matrix, inner_solver,
+                                                  cost_function=min_affine_invariant_distance_reconstruction_cost,
+                                                  nb_init_candidates=100, maxiter=50):
+    """Parameters (V, C, K) of ``projection_from_nested_spd_to_spd`` that minimise the reconstruction error of the data
+    (nested_spd_optimization.py:95-186): augmented Lagrangian (``lambdas_fact=0.05``, ``maxiter`` outer iterations) around
+    ``inner_solver`` on Grassmann(D, D - d) x SPD(D - d) x Sphere(d (D - d)) x R under ||V^T W|| = 0, started from the best
+    of ``nb_init_candidates`` random points.  Returns fp64 CPU tensors (D, D - d), (D - d, D - d), (d, D - d)."""
+    from .manifold_optimization import AugmentedLagrangeMethod
+    if cost_function is min_affine_invariant_distance_reconstruction_cost:
+        kind = 'affine_invariant'
+    elif cost_function is min_log_euclidean_distance_reconstruction_cost:
+        kind = 'log_euclidean'
+    else:
+        raise NotImplementedError('cost_function must be one of the two reconstruction costs of this module')
+    fn = _SpdReconstructionCost(x_data, x_data_projected, projection_matrix, kind)
+    dev, D, d = fn.x.device, fn.D, fn.d
+    m = D - d
+    if not 1 <= m or D > 32:
+        raise ValueError('need d < D <= 32, got D=%d, d=%d' % (D, d))
+    manifold = ProductParam([GrassmannParam(D, m), SpdParam(m), SphereParam(d * m), EuclideanParam(1)])
+    w_host = fn.w.cpu().numpy()
+
+    def to_device(points, requires_grad=False):
+        """list of manifold points (or a list of such lists) -> V, C, k, s device tensors (leading candidate dimension)."""
+        batch = isinstance(points[0], (list, tuple))
+        cols = list(zip(*points)) if batch else [[p] for p in points]
+        ts = [torch.from_numpy(np.ascontiguousarray(np.array(col, dtype=np.float64))).to(dev) for col in cols]
+        if not batch:
+            ts = [t[0] for t in ts]
+        return [t.requires_grad_(requires_grad) for t in ts]
+
+    def evaluate(v, c, kvec, s):
+        kmat = torch.sigmoid(s).unsqueeze(-1) * kvec.reshape(kvec.shape[:-1] + (d, m))   # Interval(0, 1) of the norm
+        return fn(v, c, kmat)
+
+    # candidate screening: all candidates in one batched pass (the reference evaluates them one after the other)
+    cands = [manifold.rand() for _ in range(int(nb_init_candidates))]
+    with torch.no_grad():
+        vals = evaluate(*to_device(cands)).cpu().numpy()
+    x0 = cands[int(np.nanargmin(vals))]
+
+    def cost(x):
+        with torch.no_grad():
+            return float(evaluate(*to_device(x)))
+
+    def cost_grad(x):
+        ts = to_device(x, requires_grad=True)
+        with torch.enable_grad():
+            f = evaluate(*ts)
+            f.backward()
+        return float(f.detach()), [t.grad.cpu().numpy() for t in ts]
+
+    def orthogonality(x):                                   # ||V^T W||_F and its gradient (zero at the feasible point)
+        vtw = x[0].T @ w_host
+        val = float(np.linalg.norm(vtw))
+        gv = (w_host @ vtw.T) / val if val > 0 else np.zeros_like(x[0])
+        return val, [gv, np.zeros_like(x[1]), np.zeros_like(x[2]), np.zeros_like(x[3])]
+
+    solver = AugmentedLagrangeMethod(maxiter=maxiter, inner_solver=inner_solver, lambdas_fact=0.05)
+    opt, log = riemannian_alm(manifold, cost, cost_grad, x0, solver, eq_constraints=[orthogonality])
+    v = torch.from_numpy(np.array(opt[0], dtype=np.float64))
+    c = torch.from_numpy(np.array(opt[1], dtype=np.float64))
+    norm = torch.sigmoid(torch.from_numpy(np.array(opt[3], dtype=np.float64)))
+    kmat = norm * torch.from_numpy(np.array(opt[2], dtype=np.float64)).view(d, m)
+    optimize_reconstruction_parameters_nested_spd.last_log = dict(log, start_cost=float(np.nanmin(vals)))
+    return v, c, kmat

@@ -353,6 +353,25 @@ def spd_sqrtm(mat):
     return out.reshape(m.shape)
 
 
+def sym_eig(mat, vectors=True):
+    """Batched symmetric eigendecomposition, D <= 32 (gabo_sym_eig): (..., D, D) -> eigenvalues (..., D) and, with
+    ``vectors``, eigenvectors (..., D, D) (column k belongs to eigenvalue k; eigenvalues are NOT sorted).  The convergence
+    flag stays on the device and is returned as a 1-element int32 tensor (no synchronisation here)."""
+    lib = _lib.load()
+    m = to_dev64(mat)
+    D = int(m.shape[-1])
+    if m.dim() < 2 or m.shape[-2] != D:
+        raise ValueError('sym_eig: expected (..., D, D), got %s' % (tuple(m.shape),))
+    flat = m.reshape(-1, D, D)
+    lam = torch.empty(flat.shape[0], D, dtype=torch.float64, device=m.device)
+    vec = torch.empty_like(flat) if vectors else None
+    flag = torch.zeros(1, dtype=torch.int32, device=m.device)
+    _lib.check(lib.gabo_sym_eig(_p(flat), flat.shape[0], D, _p(lam), _p(vec), _p(flag), _lib.stream_ptr()),
+               'gabo_sym_eig')
+    lam = lam.reshape(tuple(m.shape[:-1]))
+    return (lam, vec.reshape(m.shape), flag) if vectors else (lam, None, flag)
+
+
 def nested_spd_reconstruct_pack(w, v, c, k):
     """Point-independent factors of projection_from_nested_spd_to_spd for fixed (W, V, C, K)."""
     lib = _lib.load()

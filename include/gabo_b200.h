@@ -126,6 +126,12 @@ int gabo_frobenius_gram(const double* m1, int64_t n1, const double* m2, int64_t 
                         void* out, int out_dtype, int64_t ld_out, void* stream);
 /* logm_torch (spd_utils_torch.py:13-30) batched: out_i = V diag(log lambda) V^T. */
 int gabo_spd_logm(const double* mat, int64_t n, int d, double* out, void* stream);
+/* Batched symmetric eigendecomposition for matrices beyond the register kernels (1 <= D <= 32), fp64: mats n x D x D
+ * (symmetrised on load), evals n x D, evecs n x D x D with column k the eigenvector of evals[k] (nullable: values only),
+ * flags (nullable) gets bit 0 when a matrix is not finite or Jacobi did not converge.  One launch replaces the per-matrix
+ * torch.symeig calls of affine_invariant_distance_torch / logm_torch / sqrtm_torch (spd_utils_torch.py:108-112, :25-30,
+ * :45-50) inside the reconstruction costs of nested_mappings/nested_spd_optimization.py:22-92. */
+int gabo_sym_eig(const double* mats, int64_t n, int D, double* evals, double* evecs, int32_t* flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * M1: batched sphere manifold operations (pymanopt Sphere; reference formulas Riemannian_utils/sphere_utils.py:14-123).

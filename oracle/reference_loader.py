@@ -129,3 +129,21 @@ def load_alm():
         solvers.NelderMead = type('NelderMead', (), {})
     alm = importlib.import_module('BoManifolds.manifold_optimization.augmented_Lagrange_method')
     return alm.AugmentedLagrangeMethod
+
+
+def load_nested_spd_optimization():
+    """The reference's reconstruction costs (nested_mappings/nested_spd_optimization.py:22-92).  The module imports
+    ``gpytorch`` and ``pymanopt.manifolds`` at the top (used only inside ``optimize_reconstruction_parameters_nested_spd``,
+    which needs the absent pymanopt ``Product`` / ``Grassmann`` manifolds and is NOT run): empty stand-in modules are
+    registered for the import; the two cost functions themselves run unmodified reference code."""
+    load_alm()
+    import importlib
+    import types
+    if 'gpytorch' not in sys.modules:
+        sys.modules['gpytorch'] = types.ModuleType('gpytorch')
+    pkg = sys.modules['pymanopt']
+    if 'pymanopt.manifolds' not in sys.modules:
+        man = types.ModuleType('pymanopt.manifolds')
+        pkg.manifolds = man
+        sys.modules['pymanopt.manifolds'] = man
+    return importlib.import_module('BoManifolds.nested_mappings.nested_spd_optimization')

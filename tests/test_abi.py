@@ -37,7 +37,8 @@ def test_version_and_struct_layout(lib):
     assert ctypes.sizeof(_lib.RcgOpts) == 8 + 5 * 8
     assert lib.gabo_spd_factor_stride(3) == 12 and lib.gabo_spd_factor_stride(8) == 72
     assert lib.gabo_spd_factor_stride(9) == -1
-    assert lib.gabo_nested_projection_pack_size(20, 5) == 27 * 32 * 2 * 4
+    # 27 k-steps x 32 lanes x one 16-row operator tile x (hi, lo) float4 + the canonical (hi, lo) image of the tcgen05 kernel
+    assert lib.gabo_nested_projection_pack_size(20, 5) == 27 * 32 * 8 + 2 * 16 * 216
     assert lib.gabo_nested_projection_pack_size(5, 9) == -1
 
 
@@ -56,6 +57,8 @@ def test_argument_errors_are_codes_not_crashes(lib):
     assert lib.gabo_spd_ai_gram(fake, 4, fake, 5, 3, 1.0, 0, 0, 1, fake, 0, 5, null) == -1  # symmetric needs same set
     assert lib.gabo_mandel_unpack(null, 3, 3, null, null) == -1
     assert lib.gabo_spd_logm(fake, 3, 12, fake, null) == -1
+    assert lib.gabo_sym_eig(fake, 3, 33, fake, null, null, null) == -1
+    assert lib.gabo_sym_eig(fake, 0, 33, fake, null, null, null) == 0
     assert lib.gabo_argmax_records(null, null, 4, null, null, null) == -1
     desc = _lib.GpDesc(0, 3, 0, 0, 4096, 4096, 4096, 0.0, 1.0, 1.0, 0.0, 1.0)
     assert lib.gabo_ei_eval(ctypes.byref(desc), fake, 4, fake, null, null) == -1           # n_train = 0

@@ -46,6 +46,22 @@ def _install(monkeypatch):
                 torch.zeros(len(theta), dtype=torch.int32))
     monkeypatch.setattr(ops, 'gp_mll', gp_mll)
 
+    def gp_fit(dmat, y, raw0, beta_min, noise_min, priors, fixed, maxiter=15000, pgtol=1e-5, ftol=2.220446049250313e-09):
+        # stand-in of the one-launch BFGS fit: L-BFGS-B over the same objective (the emulated gp_mll above), per start
+        from scipy.optimize import minimize
+        from gabotorch_b200.gp_fit import MarginalLogLikelihood
+        pri = [(priors[2 * i], priors[2 * i + 1]) if priors[2 * i] > 0 else None for i in range(3)]
+        obj = MarginalLogLikelihood(dmat, y, beta_min, noise_min, beta_prior=pri[0], outputscale_prior=pri[1],
+                                    noise_prior=pri[2])
+        raws, fs, info = [], [], []
+        for start in t64(raw0).reshape(-1, 4).numpy():
+            bounds = [(v, v) if f else (None, None) for v, f in zip(start, fixed)]
+            res = minimize(obj, start, jac=True, method='L-BFGS-B', bounds=bounds,
+                           options={'maxiter': maxiter, 'gtol': pgtol, 'ftol': ftol})
+            raws.append(res.x), fs.append(res.fun), info.append([0 if res.success else 2, res.nit, res.nfev])
+        return np.array(raws), np.array(fs), np.array(info, dtype=int)
+    monkeypatch.setattr(ops, 'gp_fit', gp_fit)
+
     def gp_factor(kmat, y, outputscale, noise, mean):
         k = outputscale * t64(kmat).numpy() + noise * np.eye(len(y))
         k = np.tril(k) + np.tril(k, -1).T

@@ -590,7 +590,7 @@ def test_lockstep_augmented_lagrangian_reproduces_the_reference_solver(monkeypat
         else:
             assert kind == 'eq' and abs(float(cand12[i, 0, 1])) <= 1e-4
     with pytest.raises(NotImplementedError):
-        mo.AugmentedLagrangeMethod(inner_solver=mo.ConjugateGradient())
+        mo.AugmentedLagrangeMethod(inner_solver=object())
 
 
 def test_batched_constraints_closed_form_equals_autograd(monkeypatch):
@@ -712,3 +712,157 @@ def test_nested_sphere_reconstruction_cost_and_fit_host_logic(monkeypatch):
         assert len(out) == 3 and all(tuple(o.shape) == (1,) and o.dtype == torch.float32 for o in out)
         got = np.array([float(o) for o in out])
         assert np.abs(got - np.array(true_r)).max() < 2e-3, (got, true_r)
+
+
+def _cpu_sym_eig(mat, vectors=True):
+    """Test stand-in of ops.sym_eig (the device kernel) for the CPU runs of the tensor code around it."""
+    lam, vec = torch.linalg.eigh(torch.as_tensor(mat, dtype=torch.float64))
+    return lam, (vec if vectors else None), torch.zeros(1, dtype=torch.int32)
+
+
+def _nested_spd_on_cpu(monkeypatch):
+    from gabotorch_b200 import nested_optimization as nopt
+    monkeypatch.setattr(nopt.ops, 'to_dev64', lambda x: torch.as_tensor(x).detach().to(torch.float64).contiguous())
+    monkeypatch.setattr(nopt, '_dev64_keep_grad', lambda x: torch.as_tensor(x, dtype=torch.float64))
+    monkeypatch.setattr(nopt.ops, 'sym_eig', _cpu_sym_eig)
+    return nopt
+
+
+def test_nested_spd_reconstruction_costs_match_reference(monkeypatch):
+    """nested_spd_optimization.py:22-92: both costs against values produced by the reference's own functions
+    (tests/golden/make_golden_recon_cost.py; the reference accumulates in float32, hence 5e-6), and their gradients with
+    respect to (V, C, K) against central differences.  Host run of the tensor code (the eigensolver kernel replaced by a
+    stand-in); the device run is tests/test_nested_gpu.py."""
+    nopt = _nested_spd_on_cpu(monkeypatch)
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'recon_cost_vectors.npz'))
+    for name in ('rc_6_2', 'rc_10_3', 'rc_20_5'):
+        args = [torch.from_numpy(gold[name + '_' + k]) for k in ('x', 'y', 'w', 'v', 'c', 'k')]
+        ai = float(nopt.min_affine_invariant_distance_reconstruction_cost(*args))
+        le = float(nopt.min_log_euclidean_distance_reconstruction_cost(*args))
+        assert abs(ai - float(gold[name + '_ai'])) <= 5e-6 * abs(ai), (name, ai, float(gold[name + '_ai']))
+        assert abs(le - float(gold[name + '_le'])) <= 5e-6 * abs(le), (name, le, float(gold[name + '_le']))
+    rng = np.random.default_rng(3)
+    name = 'rc_6_2'
+    x, y, w = (torch.from_numpy(gold[name + '_' + k]) for k in ('x', 'y', 'w'))
+    for kind in ('affine_invariant', 'log_euclidean'):
+        fn = nopt._SpdReconstructionCost(x, y, w, kind)
+        params = [torch.from_numpy(gold[name + '_' + k]).clone().requires_grad_(True) for k in ('v', 'c', 'k')]
+        fn(*params).backward()
+        for i, p in enumerate(params):
+            direction = torch.from_numpy(rng.standard_normal(tuple(p.shape)))
+            if i == 1:
+                direction = 0.5 * (direction + direction.T)           # C stays symmetric
+            h = 1e-6
+            plus = [q.detach() + (h * direction if j == i else 0.0) for j, q in enumerate(params)]
+            minus = [q.detach() - (h * direction if j == i else 0.0) for j, q in enumerate(params)]
+            fd = (float(fn(*plus)) - float(fn(*minus))) / (2 * h)
+            an = float((p.grad * direction).sum())
+            assert abs(fd - an) <= 2e-6 * max(1.0, abs(fd)), (kind, i, fd, an)
+    # candidate batches: a leading dimension gives the same values as one call per candidate
+    fn = nopt._SpdReconstructionCost(x, y, w, 'affine_invariant')
+    vs = torch.stack([torch.from_numpy(gold[name + '_v']), torch.from_numpy(np.linalg.qr(rng.standard_normal((6, 4)))[0])])
+    cs = torch.stack([torch.from_numpy(gold[name + '_c']), torch.eye(4, dtype=torch.float64) * 1.5])
+    ks = torch.stack([torch.from_numpy(gold[name + '_k']), torch.zeros(2, 4, dtype=torch.float64)])
+    both = fn(vs, cs, ks)
+    for i in range(2):
+        assert abs(float(both[i]) - float(fn(vs[i], cs[i], ks[i]))) <= 1e-12 * abs(float(both[i]))
+
+
+def test_riemannian_alm_and_spd_parameter_manifold():
+    """Host ALM (augmented_Lagrange_method.py:66-328) on product manifolds, and the PositiveDefinite parameter manifold."""
+    from gabotorch_b200 import manifold_gp_fit as mgf
+    np.random.seed(11)
+    # 1. max <a, x> on S^2 subject to x_1 = 0  ->  x = (a_0, 0, a_2) / |.|; a scalar rides along (t - 1)^2
+    a = np.array([0.3, 0.8, -0.5])
+    man = mgf.ProductParam([mgf.SphereParam(3), mgf.EuclideanParam(1)])
+
+    def cost(p):
+        return float(-a @ p[0] + (p[1][0] - 1.0) ** 2)
+
+    def cost_grad(p):
+        return cost(p), [-a, np.array([2.0 * (p[1][0] - 1.0)])]
+
+    def plane(p):
+        return float(p[0][1]), [np.array([0.0, 1.0, 0.0]), np.zeros(1)]
+
+    want = np.array([a[0], 0.0, a[2]]) / np.hypot(a[0], a[2])
+    for inner in (g.TrustRegions(maxiter=50), g.ConjugateGradient(maxiter=100)):
+        # tight inner tolerances: with the defaults (1e-3 -> 1e-6) the loop ends as soon as an inner solve starts below its
+        # tolerance and returns its start (step size 0 < minstepsize), exactly like the reference's loop
+        solver = g.AugmentedLagrangeMethod(inner_solver=inner, maxiter=40, starting_tolgradnorm=1e-6,
+                                           ending_tolgradnorm=1e-9)
+        x, log = mgf.riemannian_alm(man, cost, cost_grad, man.rand(), solver, eq_constraints=plane)
+        # pymanopt's adaptive line search restarts every inner solve from a unit-length step and gives up after 10
+        # contractions: close to the solution the CG inner solver stalls ('minstepsize'), TrustRegions does not
+        tol = 1e-4 if type(inner).__name__ == 'TrustRegions' else 5e-3
+        assert np.abs(x[0] - want).max() < tol and abs(x[1][0] - 1.0) < tol, (x, log)
+        assert log['violation'] < tol and log['iterations'] <= 40
+        loose, llog = mgf.riemannian_alm(man, cost, cost_grad, man.rand(),
+                                         g.AugmentedLagrangeMethod(inner_solver=inner, maxiter=40), eq_constraints=plane)
+        assert np.abs(loose[0] - want).max() < 5e-3 and llog['stop'] in ('minstepsize', 'mingradnorm', 'maxiter'), llog
+        assert inner._mingradnorm == 1e-6                      # the caller's solver object is not modified
+    # inequality: the same objective with x_1 <= 0.2  <=>  0.2 - x_1 >= 0 (active at the solution)
+    def cap(p):
+        return float(0.2 - p[0][1]), [np.array([0.0, -1.0, 0.0]), np.zeros(1)]
+    solver = g.AugmentedLagrangeMethod(inner_solver=g.TrustRegions(maxiter=50), maxiter=40, starting_tolgradnorm=1e-6,
+                                       ending_tolgradnorm=1e-9)
+    x, log = mgf.riemannian_alm(man, cost, cost_grad, man.rand(), solver, ineq_constraints=[cap])
+    # the reference's multiplier update for inequalities is lambda + rho * g(x) (augmented_Lagrange_method.py:156-159),
+    # which also grows on the feasible side and so keeps the iterate strictly inside: feasibility is what it guarantees
+    assert x[0][1] <= 0.2 + 1e-3 and abs(np.linalg.norm(x[0]) - 1.0) < 1e-12 and log['lambdas'][0] >= 0.0, (x, log)
+    # 2. SPD parameter manifold: retraction = exponential map, metric, gradient conversion; CG and TR find C0
+    spd = mgf.SpdParam(4)
+    c0 = spd.rand() * 3.0
+    pman = mgf.ProductParam([spd])
+
+    def cost2(p):
+        return float(((p[0] - c0) ** 2).sum())
+
+    def cost2_grad(p):
+        return cost2(p), [2.0 * (p[0] - c0)]
+    for solver in (g.TrustRegions(maxiter=200), g.ConjugateGradient(maxiter=500)):
+        x, log = mgf.solve_on_manifold(pman, cost2, cost2_grad, pman.rand(), solver)
+        assert np.abs(x[0] - c0).max() < 1e-5, log
+        assert np.linalg.eigvalsh(x[0]).min() > 0
+    xa, u = spd.rand(), spd.proj(None, np.random.randn(4, 4))
+    assert abs(spd.dist(xa, spd.retr(xa, 0.2 * u)) - 0.2 * spd.norm(xa, u)) < 1e-12
+    assert abs(spd.inner(xa, u, u) - spd.norm(xa, u) ** 2) < 1e-12
+    assert mgf.host_manifold(type('PositiveDefinite', (), {'_n': 3})()).dim == 6
+
+
+def test_nested_spd_reconstruction_fit_host_logic(monkeypatch):
+    """optimize_reconstruction_parameters_nested_spd (nested_spd_optimization.py:95-186) on data that the mapping can
+    reproduce exactly: the fit drives the cost from the best random candidate down by orders of magnitude, keeps
+    W^T V = 0, returns an SPD bottom block and a contraction."""
+    nopt = _nested_spd_on_cpu(monkeypatch)
+    rng = np.random.default_rng(8)
+    np.random.seed(8)
+    D, d, n = 5, 2, 10
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    w, v = q[:, :d], q[:, d:]
+    c = np.diag([1.0, 1.5, 2.0])
+    k = rng.standard_normal((d, D - d))
+    k = 0.5 * k / np.linalg.norm(k)
+    ys = []
+    for _ in range(n):
+        b = rng.standard_normal((d, d))
+        ys.append(b @ b.T + 0.5 * np.eye(d))
+    y = torch.from_numpy(np.array(ys))
+    x = nopt._reconstruct_spd(y, nopt._SpectralFn.apply(y, 1), torch.from_numpy(w), torch.from_numpy(v),
+                              torch.from_numpy(c), torch.from_numpy(k))
+    for cost_fn in (g.min_affine_invariant_distance_reconstruction_cost,
+                    g.min_log_euclidean_distance_reconstruction_cost):
+        assert float(cost_fn(x, y, torch.from_numpy(w), torch.from_numpy(v), torch.from_numpy(c),
+                             torch.from_numpy(k))) < 1e-10
+    vo, co, ko = g.optimize_reconstruction_parameters_nested_spd(
+        x, y, torch.from_numpy(w), g.ConjugateGradient(maxiter=100),
+        cost_function=g.min_log_euclidean_distance_reconstruction_cost, nb_init_candidates=30, maxiter=30)
+    log = g.optimize_reconstruction_parameters_nested_spd.last_log
+    assert tuple(vo.shape) == (D, D - d) and tuple(co.shape) == (D - d, D - d) and tuple(ko.shape) == (d, D - d)
+    assert vo.dtype == co.dtype == ko.dtype == torch.float64
+    assert log['cost'] < 0.05 * log['start_cost'], log
+    assert float(torch.linalg.norm(vo.T @ torch.from_numpy(w))) < 5e-3, log
+    assert float(torch.linalg.eigvalsh(co).min()) > 0 and float(torch.linalg.norm(ko)) < 1.0
+    with pytest.raises(NotImplementedError):
+        g.optimize_reconstruction_parameters_nested_spd(x, y, torch.from_numpy(w), g.ConjugateGradient(),
+                                                        cost_function=lambda *a: 0.0)

@@ -301,3 +301,105 @@ def test_optimize_reconstruction_parameters_nested_sphere_on_device():
     got = np.array([float(o) for o in out])
     assert np.abs(got - np.array(true_r)).max() < 2e-3, (got, true_r)
     assert g.optimize_reconstruction_parameters_nested_sphere.last_log['cost'] < 1e-6
+
+
+@pytest.mark.parametrize('D,n', [(1, 3), (2, 5), (5, 130), (9, 33), (10, 64), (17, 7), (20, 200), (31, 5), (32, 9)])
+def test_sym_eig_kernel(D, n):
+    # gabo_sym_eig (the batched replacement of the per-matrix torch.symeig calls, spd_utils_torch.py:25,45,110) against
+    # LAPACK: eigenvalues, orthonormal vectors, reconstruction; clustered and repeated eigenvalues; non-finite input flagged
+    rng = np.random.default_rng(100 * D + n)
+    a = rng.standard_normal((n, D, D))
+    m = a @ a.transpose(0, 2, 1) + 0.1 * np.eye(D)
+    if n > 2:
+        m[1] = np.eye(D) * 2.5                                          # all eigenvalues equal
+        q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        lam = np.concatenate([np.full(D - D // 2, 1.0), 1.0 + 1e-9 * np.arange(D // 2)])
+        m[2] = (q * lam) @ q.T                                          # cluster
+    lam_d, vec_d, flag = ops.sym_eig(torch.from_numpy(m))
+    assert int(flag.item()) == 0
+    lam_d, vec_d = lam_d.cpu().numpy(), vec_d.cpu().numpy()
+    want = np.linalg.eigvalsh(m)
+    scale = np.abs(want).max(axis=-1, keepdims=True)
+    assert np.abs(np.sort(lam_d, axis=-1) - want).max() <= 1e-13 * scale.max()
+    eye = np.eye(D)
+    assert np.abs(vec_d.transpose(0, 2, 1) @ vec_d - eye).max() < 1e-13
+    rec = (vec_d * lam_d[:, None, :]) @ vec_d.transpose(0, 2, 1)
+    assert (np.abs(rec - m).max(axis=(1, 2)) <= 1e-13 * scale[:, 0]).all()
+    only, none, _ = ops.sym_eig(torch.from_numpy(m), vectors=False)
+    assert none is None and np.array_equal(only.cpu().numpy(), lam_d)
+    bad = m.copy()
+    bad[0, 0, 0] = np.nan
+    lam_b, _, flag_b = ops.sym_eig(torch.from_numpy(bad))
+    assert int(flag_b.item()) == 1 and np.isnan(lam_b[0].cpu().numpy()).all()
+    if n > 1:
+        assert np.abs(np.sort(lam_b[1:].cpu().numpy(), axis=-1) - want[1:]).max() <= 1e-13 * scale.max()
+
+
+def test_nested_spd_reconstruction_costs_on_device():
+    # nested_spd_optimization.py:22-92 on the device: values produced by the reference's own functions
+    # (tests/golden/make_golden_recon_cost.py; float32 accumulation there), gradients against central differences
+    import os
+    import gabotorch_b200 as g
+    from gabotorch_b200 import nested_optimization as nopt
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'recon_cost_vectors.npz'))
+    for name in ('rc_6_2', 'rc_10_3', 'rc_20_5'):
+        args = [torch.from_numpy(gold[name + '_' + k]) for k in ('x', 'y', 'w', 'v', 'c', 'k')]
+        ai = g.min_affine_invariant_distance_reconstruction_cost(*args)
+        le = g.min_log_euclidean_distance_reconstruction_cost(*args)
+        assert ai.is_cuda and ai.dtype == torch.float64
+        assert abs(float(ai) - float(gold[name + '_ai'])) <= 5e-6 * float(ai)
+        assert abs(float(le) - float(gold[name + '_le'])) <= 5e-6 * float(le)
+    rng = np.random.default_rng(3)
+    name = 'rc_10_3'
+    x, y, w = (torch.from_numpy(gold[name + '_' + k]) for k in ('x', 'y', 'w'))
+    for kind in ('affine_invariant', 'log_euclidean'):
+        fn = nopt._SpdReconstructionCost(x, y, w, kind)
+        params = [torch.from_numpy(gold[name + '_' + k]).cuda().requires_grad_(True) for k in ('v', 'c', 'k')]
+        fn(*params).backward()
+        for i, p in enumerate(params):
+            direction = torch.from_numpy(rng.standard_normal(tuple(p.shape))).cuda()
+            if i == 1:
+                direction = 0.5 * (direction + direction.T)
+            h = 1e-6
+            plus = [q.detach() + (h * direction if j == i else 0.0) for j, q in enumerate(params)]
+            minus = [q.detach() - (h * direction if j == i else 0.0) for j, q in enumerate(params)]
+            fd = (float(fn(*plus)) - float(fn(*minus))) / (2 * h)
+            an = float((p.grad * direction).sum())
+            assert abs(fd - an) <= 5e-6 * max(1.0, abs(fd)), (kind, i, fd, an)
+
+
+def test_optimize_reconstruction_parameters_nested_spd_on_device():
+    # nested_spd_optimization.py:95-186 (hd_gabo_spd.py:230-233, CG inner solver, log-Euclidean cost): data the mapping can
+    # reproduce exactly; the fit ends far below the best random candidate with W^T V = 0, C SPD and |K| < 1
+    import gabotorch_b200 as g
+    from gabotorch_b200 import nested_optimization as nopt
+    rng = np.random.default_rng(21)
+    np.random.seed(21)
+    D, d, n = 10, 3, 40
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    w, v = q[:, :d].copy(), q[:, d:].copy()
+    c = np.diag(np.linspace(1.0, 2.0, D - d))
+    k = rng.standard_normal((d, D - d))
+    k = 0.5 * k / np.linalg.norm(k)
+    ys = []
+    for _ in range(n):
+        b = rng.standard_normal((d, d))
+        ys.append(b @ b.T + 0.5 * np.eye(d))
+    y = torch.from_numpy(np.array(ys)).cuda()
+    tw, tv, tc, tk = (torch.from_numpy(t).cuda() for t in (w, v, c, k))
+    x = nopt._reconstruct_spd(y, nopt._SpectralFn.apply(y, 1), tw, tv, tc, tk)
+    # the same map as the reconstruction kernel of nested_mappings (pinned on the reference, test_reconstruction_golden)
+    from gabotorch_b200 import nested_mappings as nmap
+    x_kernel = nmap.projection_from_nested_spd_to_spd(y, tw, tv, tc, tk)
+    assert float((x - x_kernel.to(x.device)).abs().max()) < 1e-11
+    for cost_fn in (g.min_affine_invariant_distance_reconstruction_cost, g.min_log_euclidean_distance_reconstruction_cost):
+        assert float(cost_fn(x, y, tw, tv, tc, tk)) < 1e-9
+        vo, co, ko = g.optimize_reconstruction_parameters_nested_spd(
+            x, y, tw, g.ConjugateGradient(maxiter=100), cost_function=cost_fn, nb_init_candidates=100, maxiter=30)
+        log = g.optimize_reconstruction_parameters_nested_spd.last_log
+        assert not vo.is_cuda and vo.dtype == torch.float64 and tuple(ko.shape) == (d, D - d)
+        assert log['cost'] < 0.05 * log['start_cost'], log
+        assert float(torch.linalg.norm(vo.T @ torch.from_numpy(w))) < 1e-2, log
+        assert float(torch.linalg.eigvalsh(co).min()) > 0 and float(torch.linalg.norm(ko)) < 1.0
+        print('nested SPD reconstruction fit (%s): start %.3f -> %.5f in %.2f s, %d outer iterations'
+              % (cost_fn.__name__, log['start_cost'], log['cost'], log['time'], log['iterations']))
