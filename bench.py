@@ -823,6 +823,60 @@ class Bench:
                 'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': self.hbm_peak, 'unit': 'GB/s',
                              'frac': gbs / self.hbm_peak, 'algorithmic_bytes_per_launch': nbytes}}
 
+    def extra_recon_fit(self, n=40, D=10, d=3, steps=5):
+        """Reconstruction-parameter fit of the nested SPD mapping (nested_spd_optimization.py:95-186 as run by
+        hd_gabo_spd.py:230-233: ALM around ConjugateGradient(maxiter=100), log-Euclidean cost) on data the mapping can
+        reproduce; one cost + gradient evaluation (ONE gabo_sym_eig launch over the n reconstructed matrices), the
+        eigensolver kernel alone on a screening-sized batch, and the reference's cost evaluation (oracle restatement: n
+        eigendecompositions in a Python loop, host, 1 core) next to it."""
+        import time
+        import gabotorch_b200 as g
+        from gabotorch_b200 import nested_optimization as nopt
+        torch, ops = self.torch, self.ops
+        rng = np.random.default_rng(21)
+        np.random.seed(21)
+        q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        w, v = q[:, :d].copy(), q[:, d:].copy()
+        c = np.diag(np.linspace(1.0, 2.0, D - d))
+        k = rng.standard_normal((d, D - d))
+        k = 0.5 * k / np.linalg.norm(k)
+        b = rng.standard_normal((n, d, d))
+        y = torch.from_numpy(b @ b.transpose(0, 2, 1) + 0.5 * np.eye(d)).to(self.dev)
+        tw, tv, tc, tk = (torch.from_numpy(t).to(self.dev) for t in (w, v, c, k))
+        x = nopt._reconstruct_spd(y, nopt._SpectralFn.apply(y, 1), tw, tv, tc, tk)
+        fn = nopt._SpdReconstructionCost(x, y, tw, 'log_euclidean')
+        params = [t.clone().requires_grad_(True) for t in (tv, tc * 1.1, tk * 0.9)]
+
+        def evaluate():
+            for t in params:
+                t.grad = None
+            fn(*params).backward()
+        ms_eval = self.time_steps(evaluate, steps, 3, flush=False) / steps
+        batch = 100 * n
+        mats = x.repeat(100, 1, 1)
+        ms_eig = self.time_steps(lambda: ops.sym_eig(mats), steps, 3, flush=False) / steps
+        t0 = time.perf_counter()
+        g.optimize_reconstruction_parameters_nested_spd(
+            x, y, tw, g.ConjugateGradient(maxiter=100), cost_function=g.min_log_euclidean_distance_reconstruction_cost,
+            nb_init_candidates=100, maxiter=30)
+        fit_s = time.perf_counter() - t0
+        log = g.optimize_reconstruction_parameters_nested_spd.last_log
+        out = {'workload': 'nested SPD reconstruction fit SPD(%d)->SPD(%d), N=%d data, ALM(30) around CG(100), log-Euclidean '
+                           'cost, 100 candidates screened in one batch' % (d, D, n),
+               'fit_s': fit_s, 'start_cost': log['start_cost'], 'final_cost': log['cost'], 'outer_iterations': log['iterations'],
+               'inner_iterations': int(sum(i for i, _ in log['inner'])), 'cost_and_grad_ms': ms_eval,
+               'sym_eig_ms': ms_eig, 'sym_eig_matrices_per_s': batch / (ms_eig * 1e-3), 'sym_eig_batch': batch}
+        if self.rank == 0 and self.world == 1:
+            from oracle import nested as onest
+            xs, ys = x.cpu().numpy(), y.cpu().numpy()
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                onest.min_log_euclidean_distance_reconstruction_cost(xs, ys, w, v, c * 1.1, k * 0.9)
+            out['cpu_cost_only_ms'] = (time.perf_counter() - t0) / reps * 1e3
+            out['cpu_kind'] = 'oracle port of the reference cost (value only, no gradient), 1 core'
+        return out
+
     def extra_acq_tr_spd(self, constrained, R=256, d=3, n_train=32, noise=1e-2, steps=5, lockstep=True):
         """The solver configurations of gabo_spd.py on SPD(d): plain TrustRegions(maxiter=100) or
         ConstrainedTrustRegions(mingradnorm=1e-4, maxiter=100) with one max-eigenvalue inequality constraint, R restarts
@@ -917,6 +971,12 @@ class Bench:
             if self.rank == 0:
                 emit({'extra': out})
             return 0
+        if args.only == 'reconfit':               # developer switch: the nested SPD reconstruction fit
+            out = [self.guarded(self.extra_recon_fit)]
+            self.clocks.stop()
+            if self.rank == 0:
+                emit({'extra': out})
+            return 0
         if args.only == 'trspd':                  # developer switch: the one-launch constrained trust regions on SPD(3)
             out = [self.guarded(self.extra_acq_tr_spd, True, R=4096, lockstep=False)]
             self.clocks.stop()
@@ -956,6 +1016,7 @@ class Bench:
                 extras.append(self.guarded(self.extra_acq_rtr))
                 extras.append(self.guarded(self.extra_gp_fit))
                 extras.append(self.guarded(self.extra_reconstruct))
+                extras.append(self.guarded(self.extra_recon_fit))
                 extras.append(self.guarded(self.extra_acq_tr_spd, False))
                 extras.append(self.guarded(self.extra_acq_tr_spd, True))
                 extras.append(self.guarded(self.extra_acq_tr_spd, True, R=4096, lockstep=False))

@@ -85,3 +85,24 @@ def projection_from_nested_spd_to_spd(y, w, v, c, k):
         out.append(torch.mm(rot, torch.mm(xr, rot.T)))
     out = torch.stack(out)
     return out[0] if single else out
+
+
+def min_affine_invariant_distance_reconstruction_cost(x_data, y, w, v, c, k):
+    """nested_spd_optimization.py:22-55: sum over the data of d_AI(X_n, Xrec_n)^2, one pair at a time, accumulated in a
+    float32 tensor like the reference (``cost = torch.zeros(n_data)``, :49)."""
+    x_data = torch.as_tensor(x_data, dtype=torch.float64)
+    xr = projection_from_nested_spd_to_spd(y, w, v, c, k)
+    cost = torch.zeros(x_data.shape[0])
+    for n in range(x_data.shape[0]):
+        cost[n] = _spd.affine_invariant_distance(x_data[n].unsqueeze(0), xr[n].unsqueeze(0))
+    return torch.sum(cost * cost)
+
+
+def min_log_euclidean_distance_reconstruction_cost(x_data, y, w, v, c, k):
+    """nested_spd_optimization.py:58-92: the same with ||logm X_n - logm Xrec_n + 1e-15||_F (spd_utils_torch.py:156)."""
+    x_data = torch.as_tensor(x_data, dtype=torch.float64)
+    xr = projection_from_nested_spd_to_spd(y, w, v, c, k)
+    cost = torch.zeros(x_data.shape[0])
+    for n in range(x_data.shape[0]):
+        cost[n] = _spd.frobenius_distance(_spd.logm(x_data[n]).unsqueeze(0), _spd.logm(xr[n]).unsqueeze(0))
+    return torch.sum(cost * cost)

@@ -314,3 +314,17 @@ def test_augmented_lagrangian_oracle_matches_reference_solver(golden, name, kind
         x, k = oalm.solve_alm(gp, x0, maxiter=30, inner_opts={'maxiter': 50}, gammas_fact=0.05, **kw)
         assert k == int(golden[name + '_iters'][i])
         np.testing.assert_allclose(x, golden[name + '_x'][i], rtol=0, atol=1e-9)
+
+
+def test_nested_spd_reconstruction_costs_oracle_vs_reference():
+    """oracle.nested.min_*_reconstruction_cost against values produced by the reference's own functions
+    (nested_spd_optimization.py:22-92; tests/golden/make_golden_recon_cost.py).  Both sides accumulate in float32."""
+    import os
+    from oracle import nested as onest
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'recon_cost_vectors.npz'))
+    for name in ('rc_6_2', 'rc_10_3', 'rc_20_5'):
+        args = [gold[name + '_' + k] for k in ('x', 'y', 'w', 'v', 'c', 'k')]
+        ai = float(onest.min_affine_invariant_distance_reconstruction_cost(*args))
+        le = float(onest.min_log_euclidean_distance_reconstruction_cost(*args))
+        assert abs(ai - float(gold[name + '_ai'])) <= 2e-6 * abs(ai), (name, ai, float(gold[name + '_ai']))
+        assert abs(le - float(gold[name + '_le'])) <= 2e-6 * abs(le), (name, le, float(gold[name + '_le']))
