@@ -2,15 +2,26 @@
 // Included by nested_project.cu (same pack buffer, same entry point).
 //
 // STATUS: parity-green on the B200 (tests/test_nested_gpu.py::test_projection_tcgen05_kernel_parity) and OPT-IN
-// (GABO_PROJECT_KERNEL=tc): it is slower than the mma.sync kernel on this shape.  Measured at N = 2^20 (scripts/micro/
-// project_variants.cu, profiles/r02_*): 0.643 ms against 0.196 ms.  Ablations: without the MMAs (split / pack pass, barriers,
-// commits, epilogue) 0.314 ms; without the pack pass (MMAs on stale buffers) 0.554 ms.  With 16 output columns each tcgen05.mma
-// is a 64 x 16 x 8 product and costs ~110 cycles in SS mode whether or not consecutive products share an accumulator (one
-// accumulator pair: 0.597 ms; 12 independent TMEM accumulators used round-robin, the current form: 0.643 ms) -- the
-// shared-memory operand fetch of each instruction is not hidden at this size, far above the 8-cycle dispatch floor.  A form that
-// would win needs fat products: the streamed rows as the N operand (N = 256: 128 rows x {hi, lo}) and the operator as the A
-// operand held in TMEM; the tile ring, the packed chunks and a 64-row operator image do not fit in 227 KB of shared memory
-// together.  Left for the next round; the mma.sync kernel (0.74 of HBM) stays the default.
+// (GABO_PROJECT_KERNEL=tc): it is slower than the mma.sync kernel on this shape.  Measured at N = 2^20 (scripts/dev_tc.py):
+// 0.413 ms (2.29 TB/s) against 0.196 ms for the mma.sync kernel.
+//
+// What the measurements say (scripts/micro/umma_rate.cu, umma_rate2.cu; profiles/r02b_umma_rate*.log):
+//  * tcgen05.mma.kind::tf32 from shared memory, issued by ONE elected lane of a warp-uniform branch with the products unrolled:
+//    M 64 x N 16 x K 8 = 23 cycles, N 64 = 32, N 128 = 64, N 256 = 128 (M = 128 costs the same from N = 128 on: 4090 FLOP/clk/SM,
+//    the dense TF32 peak; kind::f16 K = 16 takes the same cycles = 8180 FLOP/clk/SM), same whether or not consecutive products
+//    share an accumulator or the operand addresses advance.  Issued from `if (tid == 0)` inside a rolled loop -- the first form
+//    of this kernel -- ptxas wraps every product in an ELECT / BRA.U.ANY retry loop and the same product costs 110 - 210 cycles:
+//    that, not the tensor core, was the 0.643 ms of the first version.
+//  * With the products at 23 cycles (81 per 64-row tile = 1.9 k cycles, under the 2.4 k cycles HBM needs per tile) the kernel
+//    is bound by the split / pack pass: without the MMAs it takes 0.314 ms.  The rows arrive with an 840-byte pitch (no tensor
+//    map can deliver them in the canonical core-matrix layout: the pitch is not a multiple of 16 bytes), so every value is read
+//    from the raw tile, split and written twice (hi, lo) by the CUDA cores, and then read three times by the tensor core
+//    (hi twice, lo once): ~7.9 bytes of shared-memory traffic per input byte, 3.3 k cycles per tile at 128 B/clk -- already above
+//    the HBM time before any latency.  The mma.sync kernel reads every value ONCE into a register fragment (the operator
+//    lives in registers), which is why it wins here although its tensor pipe is the slow one.
+//  * A form that could win keeps the operator as the A operand in TMEM ([hi; lo] stacked to M = 64) and streams the rows as
+//    the N operand (hi and lo read once each): 4.7 bytes of shared-memory traffic per input byte, best case ~0.9 of HBM.
+//    Not built this round.
 //
 // Why it was built: the ablation of the mma.sync kernel (scripts/micro/project_variants.cu, profiles/r02_*) shows that kernel is bound by
 // the LEGACY tensor pipe -- with one HMMA.1688.TF32 per k-step instead of the three of 3xTF32 it streams at 0.98 of HBM, with
@@ -62,6 +73,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "}\n" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {          // one lane of a converged warp
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(e));
+    return e != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -221,15 +237,16 @@ __global__ void __launch_bounds__(kThreads, 1)
             fence_proxy_async();                         // packed chunk: generic-proxy writes -> tensor-core reads
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            // issue pattern matters (scripts/micro/umma_rate*.cu): from ONE elected lane of a warp-uniform branch, unrolled, a
+            // 64 x 16 x 8 product costs 23 cycles; from `if (tid == 0)` with a rolled loop ptxas wraps every tcgen05.mma in an
+            // ELECT / BRA.U.ANY retry loop and the same product costs 110 - 210 cycles
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(hi), a_lo = smem_u32(lo);
-                // A chain of dependent tcgen05.mma into ONE accumulator runs at the pipeline latency (~110 cycles per 64 x 16 x 8
-                // product, measured), not at the 8-cycle dispatch floor.  So every product type gets kPhases independent
-                // accumulators, used round-robin over the k-steps: consecutive MMAs never touch the same TMEM columns and
-                // the 12 chains overlap; the epilogue adds the 12 partial tiles.
+                // kPhases accumulators per product type, used round-robin over the k-steps (kept from the first version; the
+                // micro-benchmark shows dependent products pipeline just as well), added up by the epilogue
                 const uint32_t d_tile = tmem_base + static_cast<uint32_t>(par * kTileCols);
-#pragma unroll 1
+#pragma unroll
                 for (int s = 0; s < kChunkCols / 8; ++s) {
                     const int ks = c * (kChunkCols / 8) + s;                       // global k-step
                     const uint64_t dah = umma_desc(a_hi + 2048u * s, 1024u, 128u);
@@ -254,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
         }
         // every thread is past its reads of the raw stage (the barrier of the last chunk): refill it
+        if (warp == 0) __syncwarp();
         if (tid == 0) {
             fence_proxy_async();
             issue_tma(tile + 2 * static_cast<int64_t>(gridDim.x), st);
