@@ -48,6 +48,34 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const float4& a, float b
           "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
+// m16n8k16 bf16 product (same issue cost as the TF32 k8 product on the legacy pipe, scripts/micro/mma_rate.cu)
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const float4& a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+          "r"(__float_as_uint(a.w)), "r"(b0), "r"(b1));
+}
+// {lower half, upper half} = bf16(lo), bf16(hi), round to nearest
+__device__ __forceinline__ uint32_t pack_bf16(float lower, float upper) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(upper), "f"(lower));
+    return r;
+}
+
+// GABO_PROJECT_KERNEL: unset / "3xtf32" = three TF32 products per k-step; "bf16" = one TF32 product + ONE bf16 k16 product
+// for both correction terms; "tc" = the tcgen05 kernel.  Read once; the operator pack depends on it.
+int project_mode() {
+    static const int mode = [] {
+        const char* e = std::getenv("GABO_PROJECT_KERNEL");
+        if (e == nullptr) return 0;
+        if (e[0] == 't') return 2;
+        if (e[0] == 'b') return 1;
+        return 0;
+    }();
+    return mode;
+}
+
 __device__ __forceinline__ void mandel_rc_dev(int d, int pos, int& r, int& c) {
     int k = 0, len = d;
     while (pos >= len) {
@@ -62,33 +90,49 @@ __device__ __forceinline__ void mandel_rc_dev(int d, int pos, int& r, int& c) {
 // pack[((s * 32 + lane) * MT + j) * 8 + {0..3, 4..7}] = {hi, lo} of the A fragment (a0, a1, a2, a3) of m-tile j, k-step s:
 //   a0 = P[16j + g][8s + 2t], a1 = P[16j + g + 8][8s + 2t], a2 = P[16j + g][8s + 2t + 1], a3 = P[16j + g + 8][8s + 2t + 1]
 // (fragment k index t <-> memory column 8s + 2t and t + 4 <-> 8s + 2t + 1: a permutation of k shared with the B loads).
-__global__ void projection_pack_kernel(const double* __restrict__ w, int D, int d, int ksteps, int mt,
+__global__ void projection_pack_kernel(const double* __restrict__ w, int D, int d, int ksteps, int mt, int c16,
                                        float* __restrict__ pack) {
     const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
-    const int total = ksteps * 32 * mt * 4;
+    const int total = ksteps * 32 * mt;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int q = e & 3;                       // a0 .. a3
-        const int j = (e >> 2) % mt;
-        const int lane = ((e >> 2) / mt) & 31;
-        const int s = ((e >> 2) / mt) >> 5;
+        const int j = e % mt;
+        const int lane = (e / mt) & 31;
+        const int s = (e / mt) >> 5;
         const int g = lane >> 2, t = lane & 3;
-        const int o = 16 * j + g + ((q & 1) ? 8 : 0);   // low Mandel index (output column)
-        const int i = 8 * s + 2 * t + (q >> 1);         // high Mandel index (k)
-        double v = 0.0;
-        if (o < dvl && i < dvh) {
-            int a, b, p, qq;
-            mandel_rc_dev(d, o, a, b);
-            mandel_rc_dev(D, i, p, qq);
-            const double mab = (a == b) ? 1.0 : 1.4142135623730951;
-            if (p == qq) v = mab * w[p * d + a] * w[p * d + b];
-            else v = mab * (w[p * d + a] * w[qq * d + b] + w[qq * d + a] * w[p * d + b]) / 1.4142135623730951;
+        float hi[4], lo[4];
+        double full[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                  // a0 .. a3
+            const int o = 16 * j + g + ((q & 1) ? 8 : 0);   // low Mandel index (output column)
+            const int i = 8 * s + 2 * t + (q >> 1);         // high Mandel index (k)
+            double v = 0.0;
+            if (o < dvl && i < dvh) {
+                int a, b, p, qq;
+                mandel_rc_dev(d, o, a, b);
+                mandel_rc_dev(D, i, p, qq);
+                const double mab = (a == b) ? 1.0 : 1.4142135623730951;
+                if (p == qq) v = mab * w[p * d + a] * w[p * d + b];
+                else v = mab * (w[p * d + a] * w[qq * d + b] + w[qq * d + a] * w[p * d + b]) / 1.4142135623730951;
+            }
+            full[q] = v;
+            hi[q] = to_tf32(static_cast<float>(v));
+            lo[q] = static_cast<float>(v - static_cast<double>(hi[q]));
         }
-        const float vf = static_cast<float>(v);
-        const float hi = to_tf32(vf);
-        const float lo = to_tf32(static_cast<float>(v - static_cast<double>(hi)));
-        float* dst = pack + (static_cast<int64_t>((s * 32 + lane) * mt + j)) * 8;
-        dst[q] = hi;
-        dst[4 + q] = lo;
+        float* dst = pack + static_cast<int64_t>(e) * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = hi[q];
+        if (c16) {
+            // A fragment of the m16n8k16 correction product: k slots (2t, 2t + 1) pair with lo(x) of the lane's two columns
+            // (operator entry in bf16), slots (2t + 8, 2t + 9) with hi(x) (operator residual lo = P - tf32(P) in bf16)
+            uint32_t* c = reinterpret_cast<uint32_t*>(dst + 4);
+            c[0] = pack_bf16(static_cast<float>(full[0]), static_cast<float>(full[2]));   // row g
+            c[1] = pack_bf16(static_cast<float>(full[1]), static_cast<float>(full[3]));   // row g + 8
+            c[2] = pack_bf16(lo[0], lo[2]);
+            c[3] = pack_bf16(lo[1], lo[3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[4 + q] = to_tf32(lo[q]);
+        }
     }
 }
 
@@ -99,7 +143,7 @@ __global__ void projection_pack_kernel(const double* __restrict__ w, int D, int 
 // The operator was split (round-to-nearest) when it was packed; when a warp's part of the k range is at most KH steps
 // (and there is one m-tile) its fragments live in REGISTERS for the whole kernel (KH > 0), otherwise they are read from
 // shared memory every tile (KH = 0).
-template <int MT, bool EVEN, int KH>
+template <int MT, bool EVEN, int KH, bool C16>
 __global__ void __launch_bounds__(kThreadsP, kCtasPerSm)
     nested_project_kernel(const float* __restrict__ x, int64_t n, int dvh, int dvl, int ksteps, int nstages,
                           const float* __restrict__ pack, float* __restrict__ y) {
@@ -201,8 +245,12 @@ __global__ void __launch_bounds__(kThreadsP, kCtasPerSm)
 #pragma unroll
                 for (int j = 0; j < MT; ++j) {
 #if !defined(GABO_NP_ABLATE)
-                    mma_tf32(acc_a[q][j], p[j][0], bl0, bl1);     // hi(P) lo(x)
-                    mma_tf32(acc_b[q][j], p[j][1], bh0, bh1);     // lo(P) hi(x)
+                    if (C16) {   // both correction terms in ONE bf16 k16 product: slots 0-7 = P lo(x), slots 8-15 = lo(P) hi(x)
+                        mma_bf16(acc_a[q][j], p[j][1], pack_bf16(bl0, bl1), pack_bf16(bh0, bh1));
+                    } else {
+                        mma_tf32(acc_a[q][j], p[j][0], bl0, bl1);     // hi(P) lo(x)
+                        mma_tf32(acc_b[q][j], p[j][1], bh0, bh1);     // lo(P) hi(x)
+                    }
                     mma_tf32(acc[q][j], p[j][0], bh0, bh1);       // hi(P) hi(x)
 #elif GABO_NP_ABLATE == 1   // ablation (scripts/micro/project_variants.cu): everything but the MMAs
                     acc_a[q][j][0] += p[j][0].x * bl0; acc_b[q][j][1] += p[j][1].y * bh1; acc[q][j][2] += bl1 + bh0;
@@ -348,12 +396,13 @@ int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, fl
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         kern<<<grid, kThreadsP, smem, s>>>(x, n, dvh, dvl, ksteps, nstages, pack, y);
     };
+    const bool c16 = project_mode() == 1;
     if (in_regs) {
-        if (even) go(nested_project_kernel<MT, true, kRegSteps>);
-        else go(nested_project_kernel<MT, false, kRegSteps>);
+        if (even) { if (c16) go(nested_project_kernel<MT, true, kRegSteps, true>); else go(nested_project_kernel<MT, true, kRegSteps, false>); }
+        else { if (c16) go(nested_project_kernel<MT, false, kRegSteps, true>); else go(nested_project_kernel<MT, false, kRegSteps, false>); }
     } else {
-        if (even) go(nested_project_kernel<MT, true, 0>);
-        else go(nested_project_kernel<MT, false, 0>);
+        if (even) { if (c16) go(nested_project_kernel<MT, true, 0, true>); else go(nested_project_kernel<MT, true, 0, false>); }
+        else { if (c16) go(nested_project_kernel<MT, false, 0, true>); else go(nested_project_kernel<MT, false, 0, false>); }
     }
     return check_launch("nested_project_kernel");
 }
@@ -422,8 +471,8 @@ extern "C" int gabo_nested_projection_matrix(const double* w, int D, int d, floa
     GABO_REQUIRE(aligned16(p_pack), GABO_E_ALIGN, "gabo_nested_projection_matrix: pack must be 16-byte aligned");
     const int ksteps = ksteps_for(D * (D + 1) / 2), nt = ntiles_for(d * (d + 1) / 2);
     const int total = ksteps * 32 * nt * 4;
-    projection_pack_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, D, d, ksteps, nt,
-                                                                                              p_pack);
+    projection_pack_kernel<<<(total / 4 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, D, d, ksteps, nt, project_mode() == 1 ? 1 : 0, p_pack);
     const int dvh = D * (D + 1) / 2, dvl = d * (d + 1) / 2;
     if (tc_eligible(dvh, dvl)) {
         const int kp = tc::Smem(dvh).kp;
@@ -448,10 +497,7 @@ extern "C" int gabo_nested_spd_project(const float* x_mandel, int64_t n, int D, 
     // The tcgen05 / TMEM kernel (nested_project_tc.cuh) is parity-green but slower than the mma.sync kernel on this skinny
     // shape (N = 2^20: 0.64 ms against 0.196 ms; ~110 cycles per 64 x 16 x 8 tcgen05.mma, see its header): opt-in with
     // GABO_PROJECT_KERNEL=tc, kept as the measured answer to "would tcgen05 help this GEMM as it stands?".
-    static const bool want_tc = [] {
-        const char* e = std::getenv("GABO_PROJECT_KERNEL");
-        return e != nullptr && e[0] == 't';
-    }();
+    const bool want_tc = project_mode() == 2;
     if (tc_eligible(dvh, dvl) && want_tc && n >= tc::kRows) {
         const tc::Smem L(dvh);
         const cudaError_t e = cudaFuncSetAttribute(tc::nested_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
