@@ -38,6 +38,9 @@ __global__ void spd_factor_kernel(const double* __restrict__ x1, int64_t n1, con
                                   int32_t* __restrict__ flags) {
     constexpr int TRI = tri_size(d);
     constexpr int FS = factor_stride(d);
+    // let a dependent launch (the pair kernel, programmatic stream serialisation) start its CTAs now; it still waits for
+    // this grid to finish before it reads the records (griddepcontrol.wait)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n1 + n2) return;
     const double* x = x1;
@@ -194,9 +197,12 @@ __global__ void __launch_bounds__(kThreads)
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_mbar_init();
-        s_tile[0] = atomicAdd(&sched[0], 1u);
-    }
+        s_tile[0] = blockIdx.x;     // the first two tiles of a CTA are static (no ticket round trip on the start-up path);
+    }                               // tickets are drawn from the third tile on, offset by 2 gridDim.x
     __syncthreads();
+    // Programmatic dependent launch: this kernel may have been started while the factorisation kernel before it in the
+    // stream was still running (its launch latency and ramp-up are hidden); nothing above reads that kernel's output.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     uint32_t phase_bits = 0u;
     // stage the rows of the tile under cursor `c` (an empty edge tile stages nothing and nothing is waited for)
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(kThreads)
             cur.start32(map, t_cur);
             issue(cur, 0);
         }
-        const unsigned int t1 = atomicAdd(&sched[0], 1u);
+        const unsigned int t1 = blockIdx.x + gridDim.x;
         s_tile[1] = t1;
         if (t1 < tiles_total) {
             TileCursor nx;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(kThreads)
             __syncthreads();
             const unsigned int t_next = s_tile[buf ^ 1];
             if (threadIdx.x == 0) {
-                const unsigned int t_nn = atomicAdd(&sched[0], 1u);
+                const unsigned int t_nn = atomicAdd(&sched[0], 1u) + 2u * gridDim.x;
                 s_tile[buf] = t_nn;            // read by everyone after the NEXT barrier
                 if (t_nn < tiles_total) {
                     TileCursor nx;
@@ -470,8 +476,21 @@ int launch_pair(const double* fac1, int64_t n1, const double* fac2, int64_t n2, 
     unsigned int* sched = sched_slot();
     GABO_REQUIRE(sched != nullptr, GABO_E_CUDA, "spd_ai_gram: cannot resolve the scheduler counters");
     GABO_REQUIRE(tiles < (1ll << 31), GABO_E_UNSUPPORTED, "spd_ai_gram: %lld tiles exceed the 32-bit tile id", (long long)tiles);
-    spd_ai_gram_kernel<d, T, OutT, KIND><<<static_cast<unsigned>(grid), kThreads, 0, stream>>>(
-        fac1, n1, fac2, n2, kp, static_cast<OutT*>(out), ld_out, map, tiles, sched);
+    // launched with programmatic stream serialisation: the CTAs may start under the tail of the previous kernel in the stream
+    // (the factorisation) and wait at griddepcontrol.wait before their first read of its output
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, spd_ai_gram_kernel<d, T, OutT, KIND>, fac1, n1, fac2, n2, kp,
+                                              static_cast<OutT*>(out), ld_out, map, tiles, sched);
+    GABO_REQUIRE(le == cudaSuccess, GABO_E_CUDA, "spd_ai_gram_kernel: %s", cudaGetErrorString(le));
     return check_launch("spd_ai_gram_kernel");
 }
 
