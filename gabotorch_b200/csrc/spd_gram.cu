@@ -22,10 +22,10 @@ namespace gabo {
 namespace {
 
 constexpr int kThreads = 128;  // columns per tile
-#ifndef GABO_TILES_PER_SLOT
-#define GABO_TILES_PER_SLOT 4
+#ifndef GABO_TILE_OVERHEAD_ROWS
+#define GABO_TILE_OVERHEAD_ROWS 4
 #endif
-constexpr int kTilesPerSlot = GABO_TILES_PER_SLOT;  // dynamic scheduler: target tiles per resident CTA
+constexpr int kTileOverheadRows = GABO_TILE_OVERHEAD_ROWS;  // tile-size model of launch_pair: per-tile overhead in rows
 
 // ------------------------------------------------------------------------------------------------------------
 // per-point factorisation
@@ -459,9 +459,19 @@ int launch_pair(const double* fac1, int64_t n1, const double* fac2, int64_t n2, 
         if (!symmetric) return ((n1 + tm - 1) / tm) * tiles_j;
         return (kThreads / tm) * (tiles_j * (tiles_j + 1) / 2);
     };
-    // rows per tile: as large as possible while every resident CTA still gets >= 4 tiles (load balance at small N)
-    int tile_m = PairCfg<d>::kMaxTileM;
-    while (tile_m > 2 && count(tile_m) < kTilesPerSlot * slots) tile_m >>= 1;
+    // rows per tile from a two-term cost model: waves of tiles over the resident CTAs (quantisation) x rows per tile plus a
+    // per-tile overhead worth ~kTileOverheadRows rows (barrier, ticket, TMA turn-around).  Measured at SPD(3) with
+    // scripts/micro/spd_variants.cu: N = 2048 takes 16-row tiles (32.2 us) over 8-row (33.8) and 4-row (37.2) ones.
+    int tile_m = 2;
+    int64_t best_cost = -1;
+    for (int tm = PairCfg<d>::kMaxTileM; tm >= 2; tm >>= 1) {
+        const int64_t waves = (count(tm) + slots - 1) / slots;
+        const int64_t cost = waves * (tm + kTileOverheadRows);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            tile_m = tm;
+        }
+    }
     TileMap map;
     map.tile_m = tile_m;
     map.tiles_i = (n1 + tile_m - 1) / tile_m;

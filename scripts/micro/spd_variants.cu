@@ -1,5 +1,5 @@
 // Tuning harness for the SPD Gram kernel: rebuilds gabotorch_b200/csrc/spd_gram.cu with other knob values
-// (-DGABO_TILES_PER_SLOT=..) and times SPD(3) Gram builds through the C ABI.
+// (-DGABO_TILE_OVERHEAD_ROWS=..) and times SPD(3) Gram builds through the C ABI.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,7 +12,7 @@ static double urand() { return rand() / (double)RAND_MAX; }
 
 int main(int argc, char** argv) {
     const int d = 3;
-    for (int64_t N : {2048, 4096, 8192}) {
+    for (int64_t N : {512, 1024, 1536, 2048, 3072, 4096, 8192}) {
         std::vector<double> h(N * d * d);
         srand(1);
         for (int64_t i = 0; i < N; ++i) {   // X = R R^T + 0.05 I, R uniform in [-1, 1]
