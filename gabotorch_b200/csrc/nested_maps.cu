@@ -7,6 +7,8 @@
 //   gabo_nested_spd_reconstruct_*   : projection_from_nested_spd_to_spd (nested_mappings/nested_spd_utils.py:51-118)
 // All fp64 (the reference runs these in fp64 on a handful of points; here they are batched, one thread or one CTA
 // per point, with every rotation applied in O(k) without forming the k x k matrix).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "spd_common.cuh"
 
@@ -530,6 +532,218 @@ nested_spd_reconstruct_sym_kernel(const double* __restrict__ y, const double* __
     }
 }
 
+
+// ---- the contraction on the fp64 tensor cores --------------------------------------------------------------------------
+// x_half[n x 2 npairs] = u[n x K] * P_half[K x 2 npairs] + Z_half as mma.sync.m8n8k4.f64 products (DMMA: 256 FMA per warp
+// instruction, measured at the full fp64 rate of the SM, scripts/micro/dmma_rate.cu: 36.6 TFLOP/s against 32.6 for DFMA, with
+// one operand load per 256 FMA instead of per 3).  M = 8 points, N = 8 entries = 4 column pairs of the upper triangle, K in
+// steps of 4.  A warp OWNS kDmTilesN N-tiles for the whole kernel: their B fragments (the operator) are loaded once from
+// global memory into kDmStepsK * kDmTilesN registers and never touch shared memory; the A fragments of an M-tile (the
+// point inputs u, staged k-major in shared memory as in the kernels above, row stride = 4 mod 16 doubles: conflict-free
+// 64-bit fragment loads) are read once per M-tile and used for all N-tiles.  C fragment: lane (l / 4) = point, lanes' two
+// values = the two entries of column pair (l % 4): stored to (r, c0), (r, c0 + 1) and mirrored.
+constexpr int kDmStepsK = 10;      // K <= 40 (d <= 5)
+constexpr int kDmTilesN = 2;       // N-tiles per warp (14 warps x 2 for SPD(20): one 448-thread CTA per SM, no spills)
+constexpr int kDmPts = 32;         // points per tile (4 M-tiles)
+constexpr int kDmLd = 36;          // row stride of u (doubles)
+constexpr int kDmFill = 4;         // tile inputs per thread held in registers (K * kDmPts <= kDmFill * blockDim)
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(448, 1)
+nested_spd_reconstruct_dmma_kernel(const double* __restrict__ y, const double* __restrict__ sq, int64_t n, int D, int d,
+                                   const double* __restrict__ pack, double* __restrict__ x, int npairs, int nbuf, int xstride) {
+    extern __shared__ __align__(16) double u_dm[];    // 2 x (4 kDmStepsK) x kDmLd | nbuf output tiles (kDmPts x xstride)
+    // Output path.  Scattered 8-byte global stores of the C fragments (and their mirrored twins) cost ~4 L2 sector transactions
+    // per 32 bytes written and bound the kernel at 0.15 ms (N = 65536) -- the same bound the DFMA kernels above sit on.  So a
+    // tile is assembled in shared memory and leaves as bulk stores (cp.async.bulk shared -> global, one per point: 8 D^2
+    // contiguous bytes), two tiles in flight so that the stores of a tile overlap the products of the next one.  Roles of
+    // the product: A = operator (M = 8 entries), B = point inputs (N = 8 points), so a lane's C values are ONE entry of TWO
+    // points: with the per-point stride xstride = 2 (mod 8) doubles the fragment stores of the upper triangle are
+    // bank-conflict free; the mirrored twins are stored from the same fragments.
+    const int dd = d * d, DD = D * D, K = dd + d * (d + 1) / 2;
+    double* xs = u_dm + 2 * 4 * kDmStepsK * kDmLd;
+    const double* __restrict__ Z = pack + 2 * D * d;
+    const double* __restrict__ P = Z + DD;
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    // this lane's entries: N-tile j of the warp covers half-vector entries 8 (warp kDmTilesN + j) + g (A fragment rows and
+    // C fragment rows alike); entry e = pair e / 2, member e & 1 of the enumeration r = 0.., c0 = r, r + 2, ...
+    int e_off[kDmTilesN];         // r * D + c of the entry, -1: padding
+    int e_mir[kDmTilesN];         // c * D + r, -1 on the diagonal / padding
+    double zc[kDmTilesN];
+    double afrag[KS][kDmTilesN];
+#pragma unroll
+    for (int j = 0; j < kDmTilesN; ++j) {
+        const int col = 8 * (warp * kDmTilesN + j) + g, pb = col >> 1;
+        e_off[j] = e_mir[j] = -1;
+        zc[j] = 0.0;
+        if (pb < npairs) {
+            int r = 0, left = pb;
+            while (r < D && left >= (D - r + 1) / 2) {
+                left -= (D - r + 1) / 2;
+                ++r;
+            }
+            const int c = r + 2 * left + (col & 1);
+            if (c < D) {
+                e_off[j] = r * D + c;
+                if (c != r) e_mir[j] = c * D + r;
+                zc[j] = Z[r * D + c];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int k = 4 * s + t4;
+            afrag[s][j] = (e_off[j] >= 0 && k < K) ? P[static_cast<size_t>(k) * DD + e_off[j]] : 0.0;
+        }
+    }
+    // tile inputs, as in the kernel above: (pt, k) = (e / K, e % K) for every tile, source offsets computed once, the values
+    // of the next tile prefetched into registers
+    int src[kDmFill], dst[kDmFill];
+#pragma unroll
+    for (int j = 0; j < kDmFill; ++j) {
+        const int e = tid + j * nthr;
+        src[j] = -1;
+        dst[j] = 0;
+        if (e < K * kDmPts) {
+            const int pt = e / K, k = e % K;
+            int off;
+            if (k < dd) {
+                off = k;
+            } else {
+                int rem = k - dd, a = 0;
+                while (rem >= d - a) {
+                    rem -= d - a;
+                    ++a;
+                }
+                off = a * d + a + rem;
+            }
+            src[j] = (pt * dd + off) * 2 + (k < dd ? 0 : 1);
+            dst[j] = (k * kDmLd + pt) | (pt << 20);
+        }
+    }
+    constexpr int kUFloats = 4 * kDmStepsK * kDmLd;
+    for (int e = tid; e < 2 * kUFloats; e += nthr) u_dm[e] = 0.0;   // both input buffers; rows K .. 4 ks - 1 stay zero
+    double val[kDmFill];
+    auto prefetch = [&](int64_t i0) {
+#pragma unroll
+        for (int j = 0; j < kDmFill; ++j) {
+            double v = 0.0;
+            if (src[j] >= 0 && i0 + (dst[j] >> 20) < n) {
+                const double* base = (src[j] & 1) ? sq : y;
+                v = __ldg(base + i0 * dd + (src[j] >> 1));
+            }
+            val[j] = v;
+        }
+    };
+    auto fill = [&](double* ub) {
+#pragma unroll
+        for (int j = 0; j < kDmFill; ++j)
+            if (src[j] >= 0) ub[dst[j] & 0xfffff] = val[j];
+    };
+    // ONE barrier per tile: the inputs of tile t + 1 are written into the other input buffer and the inputs of tile t + 2
+    // requested from global memory while tile t is computed; the barrier at the end of a tile publishes the output tile (for
+    // the bulk stores), the next inputs, and the fact that the stores of two tiles ago released their buffer.
+    const int64_t tiles = (n + kDmPts - 1) / kDmPts;
+    __syncthreads();
+    if (static_cast<int64_t>(blockIdx.x) < tiles) {
+        prefetch(static_cast<int64_t>(blockIdx.x) * kDmPts);
+        fill(u_dm);
+    }
+    if (static_cast<int64_t>(blockIdx.x) + gridDim.x < tiles) prefetch((static_cast<int64_t>(blockIdx.x) + gridDim.x) * kDmPts);
+    __syncthreads();
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int64_t i0 = t * kDmPts;
+        const bool staged = nbuf > 0 && i0 + kDmPts <= n;   // the ragged last tile takes the direct stores
+        double* xt = xs + static_cast<size_t>(nbuf > 1 ? (it & 1) : 0) * kDmPts * xstride;
+        const double* ucur = u_dm + (it & 1) * kUFloats;
+        if (t + gridDim.x < tiles) {
+            fill(u_dm + ((it & 1) ^ 1) * kUFloats);
+            if (t + 2 * static_cast<int64_t>(gridDim.x) < tiles) prefetch((t + 2 * static_cast<int64_t>(gridDim.x)) * kDmPts);
+        }
+        if (nbuf == 1 && staged) {                     // single output buffer: wait for the previous tile's stores here
+            if (tid < kDmPts) tma_store_wait_read<0>();
+            __syncthreads();
+        }
+#pragma unroll 1
+        for (int m0 = 0; m0 < kDmPts; m0 += 16) {       // two M-tiles at a time: four independent DMMA chains per warp
+            if (i0 + m0 >= n) break;
+            double b[2][KS];
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                b[0][s] = ucur[(4 * s + t4) * kDmLd + m0 + g];
+                b[1][s] = ucur[(4 * s + t4) * kDmLd + m0 + 8 + g];
+            }
+            double c[2][kDmTilesN][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < kDmTilesN; ++j) c[h][j][0] = c[h][j][1] = zc[j];
+#pragma unroll
+            for (int s = 0; s < KS; ++s)
+#pragma unroll
+                for (int j = 0; j < kDmTilesN; ++j) {
+                    dmma(c[0][j], afrag[s][j], b[0][s]);
+                    dmma(c[1][j], afrag[s][j], b[1][s]);
+                }
+            // C fragment: row g = this lane's entry, columns 2 t4, 2 t4 + 1 = points m0 + 8 h + 2 t4 (+ 1)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p0 = m0 + 8 * h + 2 * t4;
+                if (staged) {
+                    double* o0 = xt + p0 * xstride;
+#pragma unroll
+                    for (int j = 0; j < kDmTilesN; ++j)
+                        if (e_off[j] >= 0) {
+                            o0[e_off[j]] = c[h][j][0];
+                            o0[xstride + e_off[j]] = c[h][j][1];
+                            if (e_mir[j] >= 0) {        // mirrored twin straight from the fragment: 4-way bank conflicts, but
+                                o0[e_mir[j]] = c[h][j][0];   // a separate conflict-free mirror pass over the tile costs a second
+                                o0[xstride + e_mir[j]] = c[h][j][1];   // barrier and measured slower (0.125 against 0.106 ms)
+                            }
+                        }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int64_t pt = i0 + p0 + q;
+                        if (pt < n) {
+                            double* xo = x + pt * DD;
+#pragma unroll
+                            for (int j = 0; j < kDmTilesN; ++j)
+                                if (e_off[j] >= 0) {
+                                    xo[e_off[j]] = c[h][j][q];
+                                    if (e_mir[j] >= 0) xo[e_mir[j]] = c[h][j][q];
+                                }
+                        }
+                    }
+                }
+            }
+        }
+        if (staged) {
+            // every earlier bulk store of this thread has finished reading shared memory (they were issued a tile ago): after
+            // the barrier the OTHER output buffer is free for the next tile
+            if (tid < kDmPts) tma_store_wait_read<0>();
+            fence_proxy_async();                        // generic-proxy writes of the tile -> async-proxy reads of the stores
+            __syncthreads();
+            if (tid < kDmPts) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(x + (i0 + tid) * DD),
+                             "r"(smem_u32(xt + tid * xstride)), "r"(static_cast<uint32_t>(DD * sizeof(double)))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            __syncthreads();                            // the next tile's inputs are in place
+        }
+    }
+    if (tid < kDmPts) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores complete before exit
+}
+
 }  // namespace
 }  // namespace gabo
 
@@ -628,9 +842,44 @@ extern "C" int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt
     GABO_REQUIRE(y && y_sqrt && pack && x, GABO_E_ARG, "gabo_nested_spd_reconstruct: null pointer");
     const int K = d * d + d * (d + 1) / 2;
     const int64_t tiles = (n + kReconPts - 1) / kReconPts;
+    int npairs = 0;
+    for (int r = 0; r < D; ++r) npairs += (D - r + 1) / 2;
+    {   // fp64 tensor cores (DMMA): the operator in registers, K <= 40 and at most 14 warps x 2 N-tiles of 4 column pairs
+        const int nt = (2 * npairs + 7) / 8;
+        const int warps = (nt + kDmTilesN - 1) / kDmTilesN;
+        static const bool no_dmma = std::getenv("GABO_RECONSTRUCT_KERNEL") != nullptr;   // developer switch: older kernels
+        if (!no_dmma && K <= 4 * kDmStepsK && warps <= 14 && K * kDmPts <= kDmFill * 32 * warps) {
+            const size_t smem_u = sizeof(double) * 2 * 4 * kDmStepsK * kDmLd;
+            int xstride = D * D;                        // per-point stride of the staged tile: = 2 (mod 8) doubles
+            while ((xstride & 7) != 2) ++xstride;
+            const size_t tile_bytes = sizeof(double) * kDmPts * xstride;
+            // staged output needs 16-byte aligned bulk copies of 8 D^2 bytes (D even)
+            int nbuf = (aligned16(x) && (D & 1) == 0) ? 2 : 0;
+            while (nbuf > 0 && smem_u + nbuf * tile_bytes > 227u * 1024u) --nbuf;
+            const size_t smem_dm = smem_u + nbuf * tile_bytes;
+            const unsigned grid_dm = static_cast<unsigned>(imin(tiles, static_cast<int64_t>(sm_count())));
+            auto go = [&](auto kern) {
+                const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           static_cast<int>(smem_dm));
+                if (e != cudaSuccess) return e;
+                kern<<<grid_dm, 32 * warps, smem_dm, static_cast<cudaStream_t>(stream)>>>(y, y_sqrt, n, D, d, pack, x, npairs,
+                                                                                          nbuf, xstride);
+                return cudaSuccess;
+            };
+            cudaError_t e = cudaSuccess;
+            switch ((K + 3) / 4) {                      // k-steps: d = 1 .. 5 -> 1, 2, 4, 7, 10
+                case 1: e = go(nested_spd_reconstruct_dmma_kernel<1>); break;
+                case 2: e = go(nested_spd_reconstruct_dmma_kernel<2>); break;
+                case 4: e = go(nested_spd_reconstruct_dmma_kernel<4>); break;
+                case 7: e = go(nested_spd_reconstruct_dmma_kernel<7>); break;
+                default: e = go(nested_spd_reconstruct_dmma_kernel<10>); break;
+            }
+            GABO_REQUIRE(e == cudaSuccess, GABO_E_CUDA, "nested_spd_reconstruct_dmma_kernel: cudaFuncSetAttribute: %s",
+                         cudaGetErrorString(e));
+            return check_launch("nested_spd_reconstruct_dmma_kernel");
+        }
+    }
     {   // symmetric form with the operator in shared memory, when it fits twice per SM
-        int npairs = 0;
-        for (int r = 0; r < D; ++r) npairs += (D - r + 1) / 2;
         const size_t smem_sym = sizeof(double) * (static_cast<size_t>(K + 1) * 2 * npairs + static_cast<size_t>(K) * kReconLd) +
                                 sizeof(int) * npairs + 16;
         if (smem_sym <= 100u * 1024u && tiles >= 4 && K * kReconPts <= kReconFill * kReconSymThreads) {
