@@ -481,7 +481,7 @@ def riemannian_alm(manifold, cost, cost_grad, x0, solver, eq_constraints=None, i
                                                  else [ineq_constraints])
     bound, thetarho, tau = float(solver._bound), float(solver._thetarho), float(solver._tau)
     start_tol, end_tol = float(solver._starting_tolgradnorm), float(solver._ending_tolgradnorm)
-    maxiter, minstepsize, maxtime = int(solver._maxiter), float(solver._minstepsize), float(solver._maxtime)
+    maxiter, minstepsize, maxtime = max(1, int(solver._maxiter)), float(solver._minstepsize), float(solver._maxtime)
     lambdas = (float(solver._lambdas_fact) * np.ones(len(ineqs))) if lambdas is None else np.array(lambdas, dtype=float)
     gammas = (float(solver._gammas_fact) * np.ones(len(eqs))) if gammas is None else np.array(gammas, dtype=float)
     rho = float(solver._rho_init if rho is None else rho)

@@ -205,7 +205,9 @@ class _SpdReconstructionCost:
             if kind == 'affine_invariant':
                 # X = L L^T from the eigenpairs: L^-1 may be ANY factor with L^-1 X L^-T = I (the eigenvalues of
                 # L^-1 Xrec L^-T do not depend on the choice); X^(-1/2) = U diag(lambda^-1/2) U^T
-                lam, vec, _ = ops.sym_eig(self.x)
+                lam, vec, flag = ops.sym_eig(self.x)
+                if int(flag.item()) != 0 or not bool((lam > 0).all()):         # one read-back, at construction only
+                    raise ops.NotPositiveDefiniteError('x_data contains a matrix that is not symmetric positive definite')
                 self.linv = (vec * lam.rsqrt().unsqueeze(-2)) @ vec.transpose(-1, -2)
             elif kind == 'log_euclidean':
                 self.logx = _SpectralFn.apply(self.x, 0)
