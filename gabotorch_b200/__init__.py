@@ -30,7 +30,9 @@ from .manifold_optimization import (ConjugateGradient, TrustRegions, Constrained
                                     gen_batch_initial_conditions_manifold, gen_candidates_manifold,
                                     get_best_candidates, joint_optimize_manifold)
 from .nested_mappings import (NestedSpdProjection, NestedSpdReconstruction,  # noqa: F401
-                              projection_from_spd_to_nested_spd, projection_from_nested_spd_to_spd)
+                              projection_from_spd_to_nested_spd, projection_from_nested_spd_to_spd,
+                              max_eigenvalue_nested_spd_constraint, min_eigenvalue_nested_spd_constraint,
+                              random_nested_spd_with_spd_eigenvalue_constraints)
 from .gp_fit import fit_gpytorch_model, ExactMarginalLogLikelihood  # noqa: F401
 from .manifold_gp_fit import fit_gpytorch_manifold  # noqa: F401
 from .nested_optimization import (min_error_reconstruction_cost,  # noqa: F401

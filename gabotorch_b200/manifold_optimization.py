@@ -133,8 +133,10 @@ def batched_constraints(constraints, manifold_kind):
 
     ``functools.partial(max_eigenvalue_constraint_torch | min_eigenvalue_constraint_torch, ...)`` from
     ``gabotorch_b200.riemannian_utils`` is evaluated in closed form for the batch (extreme eigenpair: value
-    ``+-(bound - lambda)``, Euclidean gradient ``-+ v v^T``).  Any other callable is differentiated with torch.autograd
-    one restart at a time, which is what the reference's ``Problem`` does (pymanopt_addons/problem.py:118-137)."""
+    ``+-(bound - lambda)``, Euclidean gradient ``-+ v v^T``; the eigenpairs come from one ``gabo_sym_eig`` launch).  A
+    callable that declares ``supports_batch = True`` (the nested-SPD eigenvalue constraints of ``nested_mappings``) is
+    differentiated with torch.autograd over the whole batch at once; any other callable one restart at a time, which is
+    what the reference's ``Problem`` does (pymanopt_addons/problem.py:118-137)."""
     from . import riemannian_utils as ru
     constraints = list(constraints)
 
@@ -161,13 +163,21 @@ def batched_constraints(constraints, manifold_kind):
         for c, k in zip(constraints, kinds):
             if k is not None:
                 if eig is None:
-                    eig = torch.linalg.eigh(X)
+                    eig = ops.sym_eig(X)[:2]                               # unsorted eigenpairs, one launch
                 lam, vec = eig
-                i = -1 if k[0] == 'max' else 0
-                v = vec[..., i]
+                i = lam.argmax(-1) if k[0] == 'max' else lam.argmin(-1)
+                ext = lam.gather(-1, i.unsqueeze(-1)).squeeze(-1)
+                v = vec.gather(-1, i[..., None, None].expand(vec.shape[:-1] + (1,))).squeeze(-1)
                 outer = v.unsqueeze(-1) * v.unsqueeze(-2)
-                vals.append(k[1] - lam[..., i] if k[0] == 'max' else lam[..., i] - k[1])
+                vals.append(k[1] - ext if k[0] == 'max' else ext - k[1])
                 grads.append(rgrad(X, -outer if k[0] == 'max' else outer))
+            elif getattr(getattr(c, 'func', c), 'supports_batch', False):
+                xs = X.detach().clone().requires_grad_(True)
+                with torch.enable_grad():
+                    f = c(xs)
+                    e, = torch.autograd.grad(f.sum(), xs)
+                vals.append(f.detach())
+                grads.append(rgrad(X, e))
             else:
                 xs = X.detach().clone().requires_grad_(True)
                 with torch.enable_grad():

@@ -121,3 +121,69 @@ def projection_from_subsphere_to_sphere(x_subsphere, sphere_axes, sphere_distanc
     the order of the projection and consumed last to first, as in the reference."""
     levels = ops.nested_sphere_reconstruct(x_subsphere, _as_list(sphere_axes), _as_list(sphere_distances_to_axes))
     return [x_subsphere] + [_like(v, x_subsphere) for v in levels]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# nested_spd_constraints_utils.py of the reference: eigenvalue constraints of the AMBIENT matrix for a latent optimiser
+# ----------------------------------------------------------------------------------------------------------------
+
+class _ExtremeEigenvalue(torch.autograd.Function):
+    """Largest (``sign`` > 0) or smallest eigenvalue of a batch of symmetric matrices from ONE ``gabo_sym_eig`` launch
+    (D <= 32); backward ``g u u^T`` with the eigenvector u (what autograd gives through ``torch.symeig``)."""
+
+    @staticmethod
+    def forward(ctx, mat, sign):
+        lam, vec, _ = ops.sym_eig(mat)
+        i = lam.argmax(-1) if sign > 0 else lam.argmin(-1)
+        u = vec.gather(-1, i[..., None, None].expand(vec.shape[:-1] + (1,))).squeeze(-1)
+        ctx.save_for_backward(u)
+        return lam.gather(-1, i.unsqueeze(-1)).squeeze(-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        u, = ctx.saved_tensors
+        return g[..., None, None] * u.unsqueeze(-1) * u.unsqueeze(-2), None
+
+
+def _nested_to_ambient_autograd(x_nested_spd, projection_matrix, projection_complement_matrix, bottom_spd_matrix,
+                                contraction_matrix):
+    """projection_from_nested_spd_to_spd (nested_spd_utils.py:51-118) as differentiable device code, (..., d, d) ->
+    (..., D, D): the square roots are ``_SpectralFn`` (eigenpairs from ``gabo_sym_eig``, Daleckii-Krein backward)."""
+    from .kernel_utils import _dev64_keep_grad
+    from .nested_optimization import _SpectralFn, _reconstruct_spd
+    y = _dev64_keep_grad(x_nested_spd)
+    w, v, c, k = (_dev64_keep_grad(t).to(y.device) for t in (projection_matrix, projection_complement_matrix,
+                                                             bottom_spd_matrix, contraction_matrix))
+    single = y.dim() == 2
+    yb = y[None] if single else y.reshape((-1,) + tuple(y.shape[-2:]))
+    x = _reconstruct_spd(yb, _SpectralFn.apply(yb, 1), w, v, c, k)
+    return x[0] if single else x.reshape(tuple(y.shape[:-2]) + tuple(x.shape[-2:]))
+
+
+def max_eigenvalue_nested_spd_constraint(x_nested_spd, maximum_eigenvalue, projection_matrix,
+                                         projection_complement_matrix, bottom_spd_matrix, contraction_matrix):
+    """``maximum_eigenvalue - lambda_max`` of the ambient matrix reconstructed from the nested SPD matrix
+    (nested_spd_constraints_utils.py:13-44; satisfied when >= 0).  Differentiable; accepts one matrix or a batch."""
+    x = _nested_to_ambient_autograd(x_nested_spd, projection_matrix, projection_complement_matrix, bottom_spd_matrix,
+                                    contraction_matrix)
+    return maximum_eigenvalue - _ExtremeEigenvalue.apply(x, 1)
+
+
+def min_eigenvalue_nested_spd_constraint(x_nested_spd, minimum_eigenvalue, projection_matrix,
+                                         projection_complement_matrix, bottom_spd_matrix, contraction_matrix):
+    """``lambda_min - minimum_eigenvalue`` of the reconstructed ambient matrix (nested_spd_constraints_utils.py:47-78)."""
+    x = _nested_to_ambient_autograd(x_nested_spd, projection_matrix, projection_complement_matrix, bottom_spd_matrix,
+                                    contraction_matrix)
+    return _ExtremeEigenvalue.apply(x, -1) - minimum_eigenvalue
+
+
+max_eigenvalue_nested_spd_constraint.supports_batch = True
+min_eigenvalue_nested_spd_constraint.supports_batch = True
+
+
+def random_nested_spd_with_spd_eigenvalue_constraints(self, random_spd_fct, projection_matrix):
+    """A nested SPD sample: a sample of the ambient manifold that respects the constraints there, projected
+    (nested_spd_constraints_utils.py:81-97).  Bound as the ``rand`` method of the latent manifold in hd_gabo_spd.py:236-239;
+    returns numpy like the reference (pymanopt's format)."""
+    x_spd = torch.as_tensor(random_spd_fct(), dtype=torch.as_tensor(projection_matrix).dtype)
+    return projection_from_spd_to_nested_spd(x_spd, projection_matrix).cpu().numpy()

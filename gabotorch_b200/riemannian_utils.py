@@ -52,10 +52,16 @@ def symmetric_matrix_to_vector_mandel_torch(matrices):
 
 
 def max_eigenvalue_constraint_torch(x, maximum_eigenvalue):
-    """``maximum_eigenvalue - lambda_max(x)``: positive when satisfied (spd_constraints_utils_torch.py:17-32)."""
-    return maximum_eigenvalue - torch.linalg.eigvalsh(x).max()
+    """``maximum_eigenvalue - lambda_max(x)``: positive when satisfied (spd_constraints_utils_torch.py:17-32).  One matrix
+    or a batch; differentiable (the extreme eigenpair comes from ``gabo_sym_eig``).  The solvers recognise
+    ``functools.partial`` objects of this function and evaluate them in closed form (in the kernel where there is one)."""
+    from .kernel_utils import _dev64_keep_grad
+    from .nested_mappings import _ExtremeEigenvalue
+    return maximum_eigenvalue - _ExtremeEigenvalue.apply(_dev64_keep_grad(x), 1)
 
 
 def min_eigenvalue_constraint_torch(x, minimum_eigenvalue):
     """``lambda_min(x) - minimum_eigenvalue``: positive when satisfied (spd_constraints_utils_torch.py:35-50)."""
-    return torch.linalg.eigvalsh(x).min() - minimum_eigenvalue
+    from .kernel_utils import _dev64_keep_grad
+    from .nested_mappings import _ExtremeEigenvalue
+    return _ExtremeEigenvalue.apply(_dev64_keep_grad(x), -1) - minimum_eigenvalue

@@ -230,6 +230,11 @@ class _OracleOps:
         fn = {_lib.OP_RETR: ospd.retr, _lib.OP_EGRAD2RGRAD: ospd.egrad2rgrad}[op]
         return torch.tensor(np.array([fn(p, u) for p, u in zip(a.numpy(), b.numpy())]))
 
+    def sym_eig(self, mat, vectors=True):
+        # stand-in of the batched eigensolver kernel (gabo_sym_eig)
+        lam, vec = torch.linalg.eigh(torch.as_tensor(mat, dtype=torch.float64))
+        return lam, (vec if vectors else None), torch.zeros(1, dtype=torch.int32)
+
     def acq_ctr(self, gp, x0, constraints=(), strict=False, delta_cons=1e-6, maxiter=1000, mingradnorm=1e-6, kappa=0.1,
                 theta=1.0, rho_prime=0.1, rho_regularization=1e3, mininner=1, maxinner=None, delta_bar=None,
                 delta0=None):
@@ -265,7 +270,7 @@ def test_lockstep_trust_regions_follow_the_serial_solver(monkeypatch, manifold, 
         beta = 0.35 + math.log(2.0)
     gp = ogp.make_gp(manifold, xt, y, beta=beta, noise=1e-2)
     fake = _OracleOps(gp)
-    for name in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op'):
+    for name in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op', 'sym_eig'):
         monkeypatch.setattr(ops, name, getattr(fake, name))
     handle = type('GP', (), {'manifold': _lib.SPD if manifold == 'spd' else _lib.SPHERE, 'dim': dim, 'n_train': n})()
     assert mo._rtr_kernel_covers(handle) == (manifold == 'spd')       # SPD(d) has its own one-launch kernel now
@@ -408,7 +413,7 @@ def test_lockstep_constrained_trust_regions_reproduce_the_reference_solver(monke
     xt = golden[name + '_xtrain']
     gp = ogp.make_gp('spd', xt, golden[name + '_y'], beta=beta, noise=noise)
     fake = _OracleOps(gp)
-    for attr in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op'):
+    for attr in ('to_dev64', 'ei_eval', 'spd_scalar', 'spd_op', 'sym_eig'):
         monkeypatch.setattr(ops, attr, getattr(fake, attr))
     if closed_form:
         cons = [functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=max_eig)]
@@ -601,6 +606,7 @@ def test_batched_constraints_closed_form_equals_autograd(monkeypatch):
     from gabotorch_b200 import _lib, manifold_optimization as mo, ops, riemannian_utils as ru
     from oracle import spd as ospd
     monkeypatch.setattr(ops, 'spd_op', _OracleOps(None).spd_op)
+    monkeypatch.setattr(ops, 'sym_eig', _cpu_sym_eig)            # stand-in of the batched eigensolver kernel
     X = torch.from_numpy(ospd.spd_sample(np.random.default_rng(1), 9, 4, max_cond=50.0))
     closed = mo.batched_constraints([functools.partial(ru.max_eigenvalue_constraint_torch, maximum_eigenvalue=3.5),
                                      functools.partial(ru.min_eigenvalue_constraint_torch, minimum_eigenvalue=0.2)],
@@ -866,3 +872,64 @@ def test_nested_spd_reconstruction_fit_host_logic(monkeypatch):
     with pytest.raises(NotImplementedError):
         g.optimize_reconstruction_parameters_nested_spd(x, y, torch.from_numpy(w), g.ConjugateGradient(),
                                                         cost_function=lambda *a: 0.0)
+
+
+def test_nested_spd_eigenvalue_constraints(monkeypatch):
+    """nested_spd_constraints_utils.py:13-97: eigenvalue constraints of the ambient matrix evaluated on the latent one.
+    Values against the oracle's reconstruction (pinned on the reference) + LAPACK, and against the reference's own functions
+    when the tree is mounted; gradients against central differences; the batched evaluation of
+    ``batched_constraints`` (one autograd pass over all restarts) equals the one-point-at-a-time route."""
+    import functools
+    from gabotorch_b200 import _lib, manifold_optimization as mo, nested_mappings as nmap, ops
+    from oracle import nested as onest, reference_loader, spd as ospd
+    nopt = _nested_spd_on_cpu(monkeypatch)
+    monkeypatch.setattr(nmap.ops, 'sym_eig', _cpu_sym_eig)
+    monkeypatch.setattr(ops, 'spd_op', _OracleOps(None).spd_op)
+    import gabotorch_b200.kernel_utils as ku
+    monkeypatch.setattr(ku, '_dev64_keep_grad', lambda x: torch.as_tensor(x, dtype=torch.float64))
+    rng = np.random.default_rng(17)
+    D, d, R = 7, 3, 6
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    w, v = q[:, :d].copy(), q[:, d:].copy()
+    c = ospd.spd_sample(rng, 1, D - d, max_cond=20.0)[0]
+    k = rng.standard_normal((d, D - d))
+    k = 0.6 * k / np.linalg.norm(k)
+    y = ospd.spd_sample(rng, R, d, max_cond=50.0)
+    args = tuple(torch.from_numpy(t) for t in (w, v, c, k))
+    xa = onest.projection_from_nested_spd_to_spd(y, w, v, c, k).numpy()
+    lam = np.linalg.eigvalsh(xa)
+    fmax = g.max_eigenvalue_nested_spd_constraint(torch.from_numpy(y), 4.0, *args)
+    fmin = g.min_eigenvalue_nested_spd_constraint(torch.from_numpy(y), 0.05, *args)
+    np.testing.assert_allclose(fmax.numpy(), 4.0 - lam[:, -1], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(fmin.numpy(), lam[:, 0] - 0.05, rtol=0, atol=1e-12)
+    one = g.max_eigenvalue_nested_spd_constraint(torch.from_numpy(y[2]), 4.0, *args)
+    assert one.dim() == 0 and abs(float(one) - float(fmax[2])) < 1e-13
+    if reference_loader.available():
+        reference_loader.load()
+        import importlib
+        ref = importlib.import_module('BoManifolds.nested_mappings.nested_spd_constraints_utils')
+        for i in range(R):
+            r1 = ref.max_eigenvalue_nested_spd_constraint(torch.from_numpy(y[i]), 4.0, *args)
+            r2 = ref.min_eigenvalue_nested_spd_constraint(torch.from_numpy(y[i]), 0.05, *args)
+            assert abs(float(r1) - float(fmax[i])) < 1e-10 and abs(float(r2) - float(fmin[i])) < 1e-10
+    # gradient with respect to the latent matrix
+    yt = torch.from_numpy(y[1]).clone().requires_grad_(True)
+    g.max_eigenvalue_nested_spd_constraint(yt, 4.0, *args).backward()
+    direction = rng.standard_normal((d, d)); direction = torch.from_numpy(0.5 * (direction + direction.T))
+    h = 1e-6
+    fd = (float(g.max_eigenvalue_nested_spd_constraint(torch.from_numpy(y[1]) + h * direction, 4.0, *args))
+          - float(g.max_eigenvalue_nested_spd_constraint(torch.from_numpy(y[1]) - h * direction, 4.0, *args))) / (2 * h)
+    assert abs(fd - float((yt.grad * direction).sum())) < 1e-6 * max(1.0, abs(fd))
+    # batched evaluation (supports_batch) == one point at a time
+    cons = [functools.partial(g.max_eigenvalue_nested_spd_constraint, maximum_eigenvalue=4.0, projection_matrix=args[0],
+                              projection_complement_matrix=args[1], bottom_spd_matrix=args[2], contraction_matrix=args[3])]
+    per_point = [lambda x: cons[0](x)]                       # a plain callable: the reference's one-at-a-time route
+    fb, gb = mo.batched_constraints(cons, _lib.SPD)(torch.from_numpy(y))
+    fp, gp_ = mo.batched_constraints(per_point, _lib.SPD)(torch.from_numpy(y))
+    np.testing.assert_allclose(fb.numpy(), fp.numpy(), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(gb[0].numpy(), gp_[0].numpy(), rtol=0, atol=1e-12)
+    # random latent points: a projected ambient sample, numpy like the reference
+    monkeypatch.setattr(nmap, 'projection_from_spd_to_nested_spd',
+                        lambda x, p: torch.as_tensor(p).T @ torch.as_tensor(x) @ torch.as_tensor(p))
+    sample = g.random_nested_spd_with_spd_eigenvalue_constraints(None, lambda: xa[0], args[0])
+    assert isinstance(sample, np.ndarray) and np.abs(sample - w.T @ xa[0] @ w).max() < 1e-12

@@ -104,3 +104,46 @@ def test_gabo_spd_example_runs_on_device():
     assert np.linalg.eigvalsh(ospd.vector_to_symmetric_matrix_mandel(x).numpy()).min() > 0
     np.testing.assert_allclose(y.numpy(), ospd.ackley(x), rtol=1e-8)
     assert all(b1 <= b0 for b0, b1 in zip(best, best[1:]))
+
+
+def test_strict_constrained_trust_regions_with_nested_spd_constraints_on_device(golden):
+    # the acquisition step of hd_gabo_spd.py (:242-268): StrictConstrainedTrustRegions(mingradnorm=2e-4, maxiter=100) on the
+    # LATENT manifold SPD(3) with the eigenvalue constraints of the AMBIENT matrix (nested_spd_constraints_utils.py:13-78,
+    # reconstructed with projection_from_nested_spd_to_spd).  The constraints are batch-capable callables: one
+    # reconstruction + one gabo_sym_eig launch + one autograd pass for all restarts.  The strict variant never leaves the
+    # feasible set; the iterates end feasible with an acquisition value no worse than at the feasible starts.
+    import functools
+    import gabotorch_b200 as g
+    from gabotorch_b200 import manifold_optimization as mo
+    from oracle import nested as onest, spd as ospd
+    name = 'ctr_spd3'
+    beta, noise, _ = (float(v) for v in golden[name + '_hyper'])
+    gp = ogp.make_gp('spd', golden[name + '_xtrain'], golden[name + '_y'], beta=beta, noise=noise)
+    dgp = device_gp(gp, _lib.GABO_F64)
+    rng = np.random.default_rng(4)
+    D, d = 6, 3
+    q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+    w, v = q[:, :d].copy(), q[:, d:].copy()
+    c = np.diag([0.8, 1.0, 1.2])
+    k = rng.standard_normal((d, D - d))
+    k = 0.4 * k / np.linalg.norm(k)
+    args = dict(projection_matrix=torch.from_numpy(w), projection_complement_matrix=torch.from_numpy(v),
+                bottom_spd_matrix=torch.from_numpy(c), contraction_matrix=torch.from_numpy(k))
+    x0 = golden[name + '_x0']
+    amb = np.linalg.eigvalsh(onest.projection_from_nested_spd_to_spd(x0, w, v, c, k).numpy())
+    max_eig, min_eig = float(amb[:, -1].max() * 1.05), float(amb[:, 0].min() * 0.5)      # every start strictly feasible
+    cons = [functools.partial(g.max_eigenvalue_nested_spd_constraint, maximum_eigenvalue=max_eig, **args),
+            functools.partial(g.min_eigenvalue_nested_spd_constraint, minimum_eigenvalue=min_eig, **args)]
+    batched = mo.batched_constraints(cons, _lib.SPD)
+    f0, _ = batched(torch.from_numpy(x0).cuda())
+    assert float(f0.min()) > 0
+    # the device values equal the oracle composition (reconstruction pinned on the reference + LAPACK)
+    np.testing.assert_allclose(f0.cpu().numpy(), np.stack([max_eig - amb[:, -1], amb[:, 0] - min_eig], -1), rtol=0, atol=1e-10)
+    from gabotorch_b200 import ops
+    ei0 = ops.ei_eval(dgp, torch.from_numpy(x0).cuda())
+    X, val, iters, _ = mo.batched_trust_regions(dgp, x0, maxiter=100, mingradnorm=2e-4, ineq_constraints=batched,
+                                                strict=True)
+    f1, _ = batched(X)
+    assert float(f1.min()) >= -1e-6, f1.min()
+    assert bool((val >= ei0 - 1e-9).all())
+    assert np.linalg.eigvalsh(X.cpu().numpy()).min() > 0
