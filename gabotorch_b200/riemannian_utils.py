@@ -65,3 +65,39 @@ def min_eigenvalue_constraint_torch(x, minimum_eigenvalue):
     from .kernel_utils import _dev64_keep_grad
     from .nested_mappings import _ExtremeEigenvalue
     return _ExtremeEigenvalue.apply(_dev64_keep_grad(x), -1) - minimum_eigenvalue
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# host helpers the reference's examples import from Riemannian_utils/spd_utils.py (numpy, one matrix at a time: data
+# generation and the `rand` method bound to the manifold object, gabo_spd.py:100-124).  Not device work in the reference
+# either; the batched device equivalents are PositiveDefinite.rand_batch and the *_mandel_torch functions above.
+# ----------------------------------------------------------------------------------------------------------------
+
+def symmetric_matrix_to_vector_mandel(M):
+    """Mandel vector of ONE symmetric matrix: diagonal, then the k-th super-diagonals times sqrt 2 (spd_utils.py:57-76)."""
+    import numpy as np
+    M = np.asarray(M)
+    return np.concatenate([M.diagonal()] + [2.0 ** 0.5 * M.diagonal(i) for i in range(1, M.shape[0])])
+
+
+def vector_to_symmetric_matrix_mandel(v):
+    """Inverse of ``symmetric_matrix_to_vector_mandel`` (spd_utils.py:79-101)."""
+    import numpy as np
+    v = np.asarray(v)
+    n = int((-1.0 + (1.0 + 8.0 * v.shape[0]) ** 0.5) / 2.0)
+    M = np.diag(v[:n]).astype(v.dtype, copy=True)
+    start = n
+    for i in range(1, n):
+        off = v[start:start + n - i] / 2.0 ** 0.5
+        M += np.diag(off, i) + np.diag(off, -i)
+        start += n - i
+    return M
+
+
+def spd_sample(self):
+    """A random SPD matrix with eigenvalues uniform in [self.min_eig, self.max_eig] and a Haar-like orthogonal factor
+    (spd_utils.py:290-306); bound as the ``rand`` method of a ``PositiveDefinite`` object by the examples."""
+    import numpy as np
+    d = self.min_eig + (self.max_eig - self.min_eig) * np.random.rand(self._n)
+    u, _ = np.linalg.qr(np.random.randn(self._n, self._n))
+    return u @ np.diag(d) @ u.T

@@ -933,3 +933,25 @@ def test_nested_spd_eigenvalue_constraints(monkeypatch):
                         lambda x, p: torch.as_tensor(p).T @ torch.as_tensor(x) @ torch.as_tensor(p))
     sample = g.random_nested_spd_with_spd_eigenvalue_constraints(None, lambda: xa[0], args[0])
     assert isinstance(sample, np.ndarray) and np.abs(sample - w.T @ xa[0] @ w).max() < 1e-12
+
+
+def test_numpy_host_helpers_of_spd_utils():
+    """symmetric_matrix_to_vector_mandel / vector_to_symmetric_matrix_mandel / spd_sample (spd_utils.py:57-101, 290-306): the
+    numpy helpers the examples import, against the oracle's (reference-pinned) Mandel functions and the sampling law."""
+    import types
+    from gabotorch_b200 import riemannian_utils as ru
+    from oracle import spd as ospd
+    rng = np.random.default_rng(2)
+    for d in (1, 2, 3, 5, 8):
+        a = rng.standard_normal((d, d)); m = a + a.T
+        v = ru.symmetric_matrix_to_vector_mandel(m)
+        want = ospd.symmetric_matrix_to_vector_mandel(torch.from_numpy(m[None]))[0].numpy()
+        np.testing.assert_allclose(v, want, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(ru.vector_to_symmetric_matrix_mandel(v), m, rtol=0, atol=1e-15)
+    man = types.SimpleNamespace(_n=4, min_eig=0.5, max_eig=3.0)
+    np.random.seed(3)
+    x = ru.spd_sample(man)
+    lam = np.linalg.eigvalsh(x)
+    assert x.shape == (4, 4) and np.abs(x - x.T).max() < 1e-14 and lam.min() >= 0.5 - 1e-12 and lam.max() <= 3.0 + 1e-12
+    man.rand = types.MethodType(ru.spd_sample, man)           # the binding of gabo_spd.py:102
+    assert man.rand().shape == (4, 4)
