@@ -138,7 +138,14 @@ def fit_gpytorch_model(mll, options=None, raw_samples=0, generator=None, optimiz
     ``optimizer='device'`` (default): the whole quasi-Newton fit is ONE launch of ``gabo_gp_fit`` (one CTA per start,
     ``num_restarts`` starts side by side, best objective kept) and one read-back.  ``optimizer='scipy'``: scipy's
     L-BFGS-B on the host as in botorch, one ``gabo_gp_mll`` launch + read-back per evaluation (``options`` are passed to
-    it; botorch's ``fit_gpytorch_scipy`` default: maxiter 15000)."""
+    it; botorch's ``fit_gpytorch_scipy`` default: maxiter 15000).  A CALLABLE ``optimizer`` is called as
+    ``optimizer(mll, **kwargs)`` like botorch does -- ``fit_gpytorch_model(mll, optimizer=fit_gpytorch_manifold,
+    solver=..., nb_init_candidates=...)`` is the call of hd_gabo_spd.py:205-206."""
+    if callable(optimizer):
+        if options is not None:
+            kwargs['options'] = options
+        optimizer(mll, **kwargs)
+        return mll
     model = getattr(mll, 'model', mll)
     if not isinstance(model, ManifoldGP):
         raise NotImplementedError('fit_gpytorch_model expects a gabotorch_b200.ManifoldGP (or an mll holding one)')

@@ -24,7 +24,8 @@ import warnings
 import torch
 
 from . import _lib, ops
-from .kernel_utils import SphereGaussianKernel, SpdAffineInvariantGaussianKernel
+from .kernel_utils import (SphereGaussianKernel, SpdAffineInvariantGaussianKernel, SpdLogEuclideanGaussianKernel,
+                           SpdFrobeniusGaussianKernel)
 
 
 class BadInitialCandidatesWarning(RuntimeWarning):
@@ -195,6 +196,8 @@ _CONSTRAINED_SOLVERS = ('ConstrainedTrustRegions', 'StrictConstrainedTrustRegion
 def _rtr_kernel_covers(gp):
     """The one-launch trust-region kernels (gabo_acq_rtr): spheres of ambient dimension <= 8 (or <= 16 with at most 64
     training points, register-resident iterate) and SPD(d) (one warp per restart, whitened coordinates)."""
+    if getattr(gp, 'is_tensor_gp', False):
+        return False
     if gp.manifold == _lib.SPD:
         return True
     return gp.dim <= 8 or (gp.dim <= 16 and gp.n_train <= 64)
@@ -634,7 +637,7 @@ def build_device_gp(model, best_f, maximize=False, compute='f32'):
     """Precompute alpha = (sK + noise I)^-1 (y - m) and (sK + noise I)^-1 on the device (n <= 128, fp64)."""
     x, y, base, scale, noise, mean = _unwrap_model(model)
     comp = _lib.GABO_F64 if compute == 'f64' else _lib.GABO_F32
-    beta = float(base.beta.detach())
+    beta = float(base.beta.detach()) if hasattr(base, 'raw_beta') else float('nan')
     x = ops.to_dev64(x)
     y = ops.to_dev64(y)
     sign = 1.0
@@ -652,9 +655,21 @@ def build_device_gp(model, best_f, maximize=False, compute='f32'):
         k = ops.spd_ai_gram_from_factors(x_dev, x_dev, dim, beta, _lib.KIND_GAUSS, compute=_lib.GABO_F64,
                                          symmetric=True)
         kxx = 1.0  # diagonal_distance=True returns zero distances (spd_utils_torch.py:72-75)
+    elif isinstance(base, (SpdLogEuclideanGaussianKernel, SpdFrobeniusGaussianKernel)):
+        # kernels_spd.py:190-313 (the latent model of hd_gabo_spd.py): EI as differentiable device tensor code
+        dim = ops.mandel_dim(x.shape[-1])
+        use_log = isinstance(base, SpdLogEuclideanGaussianKernel)
+        mats = ops.mandel_unpack(x)
+        s_train = ops.spd_logm(mats) if use_log else mats
+        ls = float(base.lengthscale.detach().reshape(-1)[0])
+        inv = 1.0 / (ls * ls)
+        k = ops.frobenius_gram(s_train, s_train, inv, _lib.KIND_GAUSS)
+        alpha, minv = ops.gp_factor(k, sign * y, scale, noise, sign * mean)
+        return ops.TensorGP(dim, s_train, alpha, minv, sign * mean, scale, inv, sign * best_f, use_log)
     else:
-        raise NotImplementedError('acquisition kernels support SphereGaussianKernel and '
-                                  'SpdAffineInvariantGaussianKernel, got %s' % type(base).__name__)
+        raise NotImplementedError('acquisition kernels support SphereGaussianKernel, SpdAffineInvariantGaussianKernel '
+                                  'and (through the lock-step solvers) SpdLogEuclidean / SpdFrobeniusGaussianKernel, got %s'
+                                  % type(base).__name__)
     # Cholesky factorisation, alpha and the inverse in one launch of the GP kernel (no cuSOLVER on the path)
     alpha, minv = ops.gp_factor(k, sign * y, scale, noise, sign * mean)
     return ops.DeviceGP(manifold, dim, x_dev, alpha, minv, sign * mean, scale, beta, sign * best_f, kxx, comp)
@@ -724,6 +739,11 @@ def is_nonnegative(acq_function):
 
 
 def _rand_points(manifold, n, generator):
+    if 'rand' in getattr(manifold, '__dict__', {}):
+        # ``rand`` re-bound on the manifold OBJECT, the reference's way of installing a problem-specific sampler
+        # (gabo_spd.py:102, hd_gabo_spd.py:236-239): honour it, one point per call
+        import numpy as np
+        return ops.to_dev64(np.stack([np.asarray(manifold.rand()) for _ in range(n)]))
     if hasattr(manifold, 'rand_batch'):
         return manifold.rand_batch(n, generator=generator)
     import numpy as np  # foreign (pymanopt) manifold object: its own sampler, one point per call as in the reference
@@ -862,13 +882,17 @@ def gen_candidates_manifold(initial_conditions, acquisition_function, manifold, 
     if x0.dim() < 3 or x0.shape[1] != 1:
         raise NotImplementedError('initial_conditions must be R x 1 x ... (q = 1, manifold_optimize.py:206)')
     pts = x0[:, 0]
+    tensor_gp = getattr(gp, 'is_tensor_gp', False)
     if not trust_region:
+        if tensor_gp:
+            raise NotImplementedError('log-Euclidean / Frobenius kernels: the acquisition is optimised by the trust-region '
+                                      'solvers (TrustRegions, [Strict]ConstrainedTrustRegions), as in hd_gabo_spd.py')
         solve = ops.acq_rcg
     elif constrained:
         cons = inequality_constraints if isinstance(inequality_constraints, (list, tuple)) else [inequality_constraints]
         strict = type(solver).__name__ == 'StrictConstrainedTrustRegions'
         delta_cons = float(getattr(solver, 'Delta_cons', 1e-6))
-        specs = None if (eq_mode or kind != _lib.SPD) else eigenvalue_constraint_specs(cons)
+        specs = None if (eq_mode or kind != _lib.SPD or tensor_gp) else eigenvalue_constraint_specs(cons)
         if specs is not None:
             # gabo_spd.py's configuration: eigenvalue constraints on SPD(d) -> the whole constrained solve in one launch
             solve = ops.acq_ctr

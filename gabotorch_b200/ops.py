@@ -7,6 +7,7 @@ is returned on the device (the reference-facing classes in ``kernels.py`` / ``ma
 back to the caller's device).
 """
 import ctypes
+import math
 
 import torch
 
@@ -602,8 +603,62 @@ class DeviceGP:
                         d.best_f, d.kxx, compute)
 
 
+class TensorGP:
+    """GP behind the acquisition function for the SPD kernels the solver kernels do not evaluate in closed form (the
+    log-Euclidean and Frobenius Gaussian kernels: ``hd_gabo_spd.py`` builds its latent model on
+    ``SpdLogEuclideanGaussianKernel``).  EI and its Riemannian gradient are differentiable DEVICE tensor code for all
+    restarts at once: ``logm`` of the iterates and its adjoint are the ``gabo_spd_logm`` / ``gabo_spd_logm_backward`` kernels,
+    the rest (n_train <= 128 kernel values, posterior mean / variance, EI) is a handful of small fp64 tensor operations;
+    the gradient comes from one autograd pass.  Same quantities and conventions as ``gabo_ei_eval`` (botorch analytic EI,
+    variance floor 1e-9, targets already sign-flipped for maximisation).  Used by the lock-step trust-region drivers."""
+
+    is_tensor_gp = True
+    manifold = _lib.SPD
+
+    def __init__(self, dim, s_train, alpha, minv, mean, outputscale, inv_ls2, best_f, use_log):
+        self.dim = int(dim)
+        self.s_train = to_dev64(s_train)     # (n, d, d): logm of the training matrices (or the matrices themselves)
+        self.alpha = to_dev64(alpha)
+        self.minv = to_dev64(minv)
+        self.n_train = int(self.alpha.shape[0])
+        self.mean, self.outputscale, self.inv_ls2, self.best_f = float(mean), float(outputscale), float(inv_ls2), float(best_f)
+        self.use_log = bool(use_log)
+        d2self = self.dim * self.dim * 1e-30   # ||0 + 1e-15||_F^2: the reference adds 1e-15 to every entry of the difference
+        self.kxx = math.exp(-d2self * self.inv_ls2)
+
+    @property
+    def point_shape(self):
+        return (self.dim, self.dim)
+
+    def with_compute(self, compute):
+        return self
+
+    def ei(self, x, want_grad=False):
+        from .kernel_utils import _SpdLogm
+        x = to_dev64(x)
+        xs = x.clone().requires_grad_(True) if want_grad else x
+        with torch.enable_grad() if want_grad else torch.no_grad():
+            s = _SpdLogm.apply(xs) if self.use_log else xs
+            diff = s.unsqueeze(1) - self.s_train.unsqueeze(0) + 1e-15
+            k = self.outputscale * torch.exp(-(diff * diff).sum((-1, -2)) * self.inv_ls2)       # (r, n)
+            mk = k @ self.minv
+            mu = self.mean + k @ self.alpha
+            var = (self.outputscale * self.kxx - (mk * k).sum(-1)).clamp_min(1e-9)
+            sigma = var.sqrt()
+            u = (self.best_f - mu) / sigma
+            pdf = torch.exp(-0.5 * u * u) * 0.3989422804014327
+            cdf = 0.5 * torch.erfc(-u * 0.7071067811865476)
+            ei = sigma * (pdf + u * cdf)
+            if not want_grad:
+                return ei
+            e, = torch.autograd.grad(ei.sum(), xs)
+        return ei.detach(), spd_op(_lib.OP_EGRAD2RGRAD, x, e)
+
+
 def ei_eval(gp, x, want_grad=False):
     """EI (and its Riemannian gradient) at r points; x: (r, D) or (r, d, d)."""
+    if getattr(gp, 'is_tensor_gp', False):
+        return gp.ei(x, want_grad)
     lib = _lib.load()
     x = to_dev64(x)
     r = x.shape[0]
