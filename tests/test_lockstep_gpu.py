@@ -215,3 +215,17 @@ def test_tensor_gp_expected_improvement_vs_oracle_formulas():
         xinv = np.linalg.inv(xs[i])
         an = np.trace(xinv @ grad[i].cpu().numpy() @ xinv @ xi)
         assert abs(fd - an) <= 1e-4 * abs(fd) + 1e-9, (i, fd, an)
+
+
+def test_hd_gabo_sphere_example_loop_on_device():
+    # the whole HD-GaBO iteration of hd_gabo_sphere.py on the device: manifold GP fit (sphere-valued axes), latent sphere GP,
+    # reconstruction fit of the distances to axis, multi-start trust regions on the latent sphere, lift of the candidate
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('hd_gabo_sphere_example', os.path.join(root, 'examples', 'hd_gabo_sphere.py'))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    x, y, best = ex.run(dim=5, latent_dim=3, n_iters=3, num_restarts=3, raw_samples=40, nb_data_init=5, seed=5, verbose=False)
+    assert tuple(x.shape) == (8, 5) and tuple(y.shape) == (8,) and len(best) == 4
+    np.testing.assert_allclose(x.norm(dim=-1).numpy(), 1.0, atol=1e-6)      # the fitted distances are float32, as in the reference
+    assert all(b1 <= b0 for b0, b1 in zip(best, best[1:])) and best[-1] == float(y.min())
