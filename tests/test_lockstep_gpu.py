@@ -229,3 +229,22 @@ def test_hd_gabo_sphere_example_loop_on_device():
     assert tuple(x.shape) == (8, 5) and tuple(y.shape) == (8,) and len(best) == 4
     np.testing.assert_allclose(x.norm(dim=-1).numpy(), 1.0, atol=1e-6)      # the fitted distances are float32, as in the reference
     assert all(b1 <= b0 for b0, b1 in zip(best, best[1:])) and best[-1] == float(y.min())
+
+
+@pytest.mark.parametrize('constraint,solver', [('bound', 'ctr'), ('inequality', 'ctr'), ('inequality', 'alm'),
+                                               ('equality', 'ctr'), ('equality', 'alm')])
+def test_constrained_sphere_example_loops_on_device(constraint, solver):
+    # the three constrained examples of the reference (bo_sphere/constrained_benchmark_examples/): user-supplied torch
+    # callables as constraints, the feasible sampler re-bound on the manifold object, both solver choices; the proposed
+    # candidates stay on the sphere and inside the domain (to the solvers' tolerance)
+    import importlib.util, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('gabo_sphere_constrained_example',
+                                                  os.path.join(root, 'examples', 'gabo_sphere_constrained.py'))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    x, y, best, worst = ex.run(constraint, solver, n_iters=3, num_restarts=3, raw_samples=40, seed=11, verbose=False)
+    assert tuple(x.shape) == (8, 3) and len(best) == 4
+    np.testing.assert_allclose(x.norm(dim=-1).numpy(), 1.0, atol=1e-9)
+    assert worst > -1e-3, worst
+    assert all(b1 <= b0 for b0, b1 in zip(best, best[1:]))
