@@ -545,8 +545,6 @@ nested_spd_reconstruct_sym_kernel(const double* __restrict__ y, const double* __
 constexpr int kDmStepsK = 10;      // K <= 40 (d <= 5)
 constexpr int kDmTilesN = 2;       // N-tiles per warp (14 warps x 2 for SPD(20): one 448-thread CTA per SM, no spills)
 constexpr int kDmPts = 32;         // points per tile (4 M-tiles)
-constexpr int kDmLd = 36;          // row stride of u (doubles)
-constexpr int kDmFill = 4;         // tile inputs per thread held in registers (K * kDmPts <= kDmFill * blockDim)
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -558,7 +556,7 @@ template <int KS>
 __global__ void __launch_bounds__(448, 1)
 nested_spd_reconstruct_dmma_kernel(const double* __restrict__ y, const double* __restrict__ sq, int64_t n, int D, int d,
                                    const double* __restrict__ pack, double* __restrict__ x, int npairs, int nbuf, int xstride) {
-    extern __shared__ __align__(16) double u_dm[];    // 2 x (4 kDmStepsK) x kDmLd | nbuf output tiles (kDmPts x xstride)
+    extern __shared__ __align__(16) double u_dm[];    // 2 x {y, sqrt(y)} input tiles | nbuf output tiles (kDmPts x xstride) | barriers
     // Output path.  Scattered 8-byte global stores of the C fragments (and their mirrored twins) cost ~4 L2 sector transactions
     // per 32 bytes written and bound the kernel at 0.15 ms (N = 65536) -- the same bound the DFMA kernels above sit on.  So a
     // tile is assembled in shared memory and leaves as bulk stores (cp.async.bulk shared -> global, one per point: 8 D^2
@@ -567,7 +565,13 @@ nested_spd_reconstruct_dmma_kernel(const double* __restrict__ y, const double* _
     // points: with the per-point stride xstride = 2 (mod 8) doubles the fragment stores of the upper triangle are
     // bank-conflict free; the mirrored twins are stored from the same fragments.
     const int dd = d * d, DD = D * D, K = dd + d * (d + 1) / 2;
-    double* xs = u_dm + 2 * 4 * kDmStepsK * kDmLd;
+    // tile inputs: the y and sqrt(y) rows of a tile are two contiguous blocks of kDmPts d^2 doubles in global memory: they
+    // arrive by TMA bulk loads (two tiles in flight) and the B fragments are read straight from the row-major images
+    // (8-byte `__ldg` prefetches into registers + a transposing store cost ~1 us per tile that nothing hid)
+    const int raw_tile = kDmPts * dd;                   // doubles per array per tile
+    double* raw = u_dm;                                 // [2 buffers][y | sq][kDmPts x d^2]
+    double* xs = u_dm + 4 * raw_tile;
+    uint64_t* in_bar = reinterpret_cast<uint64_t*>(xs + static_cast<size_t>(nbuf) * kDmPts * xstride);
     const double* __restrict__ Z = pack + 2 * D * d;
     const double* __restrict__ P = Z + DD;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
@@ -602,70 +606,61 @@ nested_spd_reconstruct_dmma_kernel(const double* __restrict__ y, const double* _
             afrag[s][j] = (e_off[j] >= 0 && k < K) ? P[static_cast<size_t>(k) * DD + e_off[j]] : 0.0;
         }
     }
-    // tile inputs, as in the kernel above: (pt, k) = (e / K, e % K) for every tile, source offsets computed once, the values
-    // of the next tile prefetched into registers
-    int src[kDmFill], dst[kDmFill];
+    // offset of this lane's k = 4 s + t4 inside a point's inputs: k < d^2 -> y entry k, else the (a, q >= a) entry of sqrt(y)
+    int koff[KS];
 #pragma unroll
-    for (int j = 0; j < kDmFill; ++j) {
-        const int e = tid + j * nthr;
-        src[j] = -1;
-        dst[j] = 0;
-        if (e < K * kDmPts) {
-            const int pt = e / K, k = e % K;
-            int off;
-            if (k < dd) {
-                off = k;
-            } else {
-                int rem = k - dd, a = 0;
-                while (rem >= d - a) {
-                    rem -= d - a;
-                    ++a;
-                }
-                off = a * d + a + rem;
+    for (int s = 0; s < KS; ++s) {
+        const int k = 4 * s + t4;
+        koff[s] = -1;
+        if (k < dd) {
+            koff[s] = k;
+        } else if (k < K) {
+            int rem = k - dd, a = 0;
+            while (rem >= d - a) {
+                rem -= d - a;
+                ++a;
             }
-            src[j] = (pt * dd + off) * 2 + (k < dd ? 0 : 1);
-            dst[j] = (k * kDmLd + pt) | (pt << 20);
+            koff[s] = raw_tile + a * d + a + rem;
         }
     }
-    constexpr int kUFloats = 4 * kDmStepsK * kDmLd;
-    for (int e = tid; e < 2 * kUFloats; e += nthr) u_dm[e] = 0.0;   // both input buffers; rows K .. 4 ks - 1 stay zero
-    double val[kDmFill];
-    auto prefetch = [&](int64_t i0) {
-#pragma unroll
-        for (int j = 0; j < kDmFill; ++j) {
-            double v = 0.0;
-            if (src[j] >= 0 && i0 + (dst[j] >> 20) < n) {
-                const double* base = (src[j] & 1) ? sq : y;
-                v = __ldg(base + i0 * dd + (src[j] >> 1));
-            }
-            val[j] = v;
-        }
-    };
-    auto fill = [&](double* ub) {
-#pragma unroll
-        for (int j = 0; j < kDmFill; ++j)
-            if (src[j] >= 0) ub[dst[j] & 0xfffff] = val[j];
-    };
-    // ONE barrier per tile: the inputs of tile t + 1 are written into the other input buffer and the inputs of tile t + 2
-    // requested from global memory while tile t is computed; the barrier at the end of a tile publishes the output tile (for
-    // the bulk stores), the next inputs, and the fact that the stores of two tiles ago released their buffer.
     const int64_t tiles = (n + kDmPts - 1) / kDmPts;
-    __syncthreads();
-    if (static_cast<int64_t>(blockIdx.x) < tiles) {
-        prefetch(static_cast<int64_t>(blockIdx.x) * kDmPts);
-        fill(u_dm);
+    const uint32_t tile_bytes = static_cast<uint32_t>(raw_tile * sizeof(double));
+    if (tid == 0) {
+        mbar_init(&in_bar[0], 1);
+        mbar_init(&in_bar[1], 1);
+        fence_mbar_init();
     }
-    if (static_cast<int64_t>(blockIdx.x) + gridDim.x < tiles) prefetch((static_cast<int64_t>(blockIdx.x) + gridDim.x) * kDmPts);
     __syncthreads();
+    auto issue_in = [&](int64_t t, int b) {             // thread 0; full tiles only (the ragged last tile is copied by hand)
+        if (t < tiles && (t + 1) * kDmPts <= n) {
+            mbar_expect_tx(&in_bar[b], 2 * tile_bytes);
+            tma_load_1d(raw + (2 * b) * raw_tile, y + t * raw_tile, tile_bytes, &in_bar[b]);
+            tma_load_1d(raw + (2 * b + 1) * raw_tile, sq + t * raw_tile, tile_bytes, &in_bar[b]);
+        }
+    };
+    if (tid == 0) {
+        issue_in(blockIdx.x, 0);
+        issue_in(static_cast<int64_t>(blockIdx.x) + gridDim.x, 1);
+    }
+    // ONE barrier per tile: it publishes the output tile (for the bulk stores), releases the input buffer for the load of
+    // the tile after next, and tells that the stores of two tiles ago released their output buffer.
     int it = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
         const int64_t i0 = t * kDmPts;
-        const bool staged = nbuf > 0 && i0 + kDmPts <= n;   // the ragged last tile takes the direct stores
+        const bool full = i0 + kDmPts <= n;
+        const bool staged = nbuf > 0 && full;           // the ragged last tile takes the direct stores
         double* xt = xs + static_cast<size_t>(nbuf > 1 ? (it & 1) : 0) * kDmPts * xstride;
-        const double* ucur = u_dm + (it & 1) * kUFloats;
-        if (t + gridDim.x < tiles) {
-            fill(u_dm + ((it & 1) ^ 1) * kUFloats);
-            if (t + 2 * static_cast<int64_t>(gridDim.x) < tiles) prefetch((t + 2 * static_cast<int64_t>(gridDim.x)) * kDmPts);
+        const double* ucur = raw + (2 * (it & 1)) * raw_tile;
+        if (full) {
+            mbar_wait(&in_bar[it & 1], (it >> 1) & 1);
+        } else {                                        // ragged last tile: plain cooperative copy, zero fill
+            double* dstb = raw + (2 * (it & 1)) * raw_tile;
+            const int64_t valid = (n - i0) * dd;
+            for (int e = tid; e < raw_tile; e += nthr) {
+                dstb[e] = e < valid ? y[i0 * dd + e] : 0.0;
+                dstb[raw_tile + e] = e < valid ? sq[i0 * dd + e] : 0.0;
+            }
+            __syncthreads();
         }
         if (nbuf == 1 && staged) {                     // single output buffer: wait for the previous tile's stores here
             if (tid < kDmPts) tma_store_wait_read<0>();
@@ -677,8 +672,8 @@ nested_spd_reconstruct_dmma_kernel(const double* __restrict__ y, const double* _
             double b[2][KS];
 #pragma unroll
             for (int s = 0; s < KS; ++s) {
-                b[0][s] = ucur[(4 * s + t4) * kDmLd + m0 + g];
-                b[1][s] = ucur[(4 * s + t4) * kDmLd + m0 + 8 + g];
+                b[0][s] = koff[s] >= 0 ? ucur[(m0 + g) * dd + koff[s]] : 0.0;
+                b[1][s] = koff[s] >= 0 ? ucur[(m0 + 8 + g) * dd + koff[s]] : 0.0;
             }
             double c[2][kDmTilesN][2];
 #pragma unroll
@@ -738,7 +733,11 @@ nested_spd_reconstruct_dmma_kernel(const double* __restrict__ y, const double* _
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {
-            __syncthreads();                            // the next tile's inputs are in place
+            __syncthreads();
+        }
+        if (tid == 0) {                                 // everyone is past its reads of this input buffer: refill it
+            fence_proxy_async();
+            issue_in(t + 2 * static_cast<int64_t>(gridDim.x), it & 1);
         }
     }
     if (tid < kDmPts) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores complete before exit
@@ -848,8 +847,8 @@ extern "C" int gabo_nested_spd_reconstruct(const double* y, const double* y_sqrt
         const int nt = (2 * npairs + 7) / 8;
         const int warps = (nt + kDmTilesN - 1) / kDmTilesN;
         static const bool no_dmma = std::getenv("GABO_RECONSTRUCT_KERNEL") != nullptr;   // developer switch: older kernels
-        if (!no_dmma && K <= 4 * kDmStepsK && warps <= 14 && K * kDmPts <= kDmFill * 32 * warps) {
-            const size_t smem_u = sizeof(double) * 2 * 4 * kDmStepsK * kDmLd;
+        if (!no_dmma && K <= 4 * kDmStepsK && warps <= 14 && aligned16(y) && aligned16(y_sqrt)) {
+            const size_t smem_u = sizeof(double) * 4 * kDmPts * d * d + 2 * sizeof(uint64_t);   // input tiles + their barriers
             int xstride = D * D;                        // per-point stride of the staged tile: = 2 (mod 8) doubles
             while ((xstride & 7) != 2) ++xstride;
             const size_t tile_bytes = sizeof(double) * kDmPts * xstride;
