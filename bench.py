@@ -864,7 +864,7 @@ class Bench:
         out = {'workload': 'nested SPD reconstruction fit SPD(%d)->SPD(%d), N=%d data, ALM(30) around CG(100), log-Euclidean '
                            'cost, 100 candidates screened in one batch' % (d, D, n),
                'fit_s': fit_s, 'start_cost': log['start_cost'], 'final_cost': log['cost'], 'outer_iterations': log['iterations'],
-               'inner_iterations': int(sum(i for i, _ in log['inner'])), 'cost_and_grad_ms': ms_eval,
+               'inner_iterations': int(sum(i for i, _ in log['inner'])), 'cuda_graph': bool(log.get('cuda_graph')), 'cost_and_grad_ms_eager': ms_eval,
                'sym_eig_ms': ms_eig, 'sym_eig_matrices_per_s': batch / (ms_eig * 1e-3), 'sym_eig_batch': batch}
         if self.rank == 0 and self.world == 1:
             from oracle import nested as onest

@@ -249,7 +249,7 @@ def min_log_euclidean_distance_reconstruction_cost(x_data, x_data_projected, pro
 
 def optimize_reconstruction_parameters_nested_spd(x_data, x_data_projected, projection_matrix, inner_solver,
                                                   cost_function=min_affine_invariant_distance_reconstruction_cost,
-                                                  nb_init_candidates=100, maxiter=50):
+                                                  nb_init_candidates=100, maxiter=50, use_cuda_graph=True):
     """Parameters (V, C, K) of ``projection_from_nested_spd_to_spd`` that minimise the reconstruction error of the data
     (nested_spd_optimization.py:95-186): augmented Lagrangian (``lambdas_fact=0.05``, ``maxiter`` outer iterations) around
     ``inner_solver`` on Grassmann(D, D - d) x SPD(D - d) x Sphere(d (D - d)) x R under ||V^T W|| = 0, started from the best
@@ -288,16 +288,59 @@ def optimize_reconstruction_parameters_nested_spd(x_data, x_data_projected, proj
         vals = evaluate(*to_device(cands)).cpu().numpy()
     x0 = cands[int(np.nanargmin(vals))]
 
-    def cost(x):
-        with torch.no_grad():
-            return float(evaluate(*to_device(x)))
+    # One cost + gradient evaluation is ~60 small launches (eigensolver, products, element-wise steps) on tiny operands:
+    # launch-bound.  The solver calls it hundreds of times with operands of fixed shape, so the whole forward + backward
+    # pass is captured ONCE in a CUDA graph over static input / output tensors and replayed per evaluation (one packed
+    # host-to-device copy in, one read-back out).  Any capture problem falls back to the eager evaluation.
+    sizes = [D * m, m * m, d * m, 1]
+    shapes = [(D, m), (m, m), (d * m,), (1,)]
+    graph = None
+    if dev.type == 'cuda' and use_cuda_graph:
+        try:
+            packed_in = torch.zeros(sum(sizes), dtype=torch.float64, device=dev)
+            stat = [packed_in[sum(sizes[:i]):sum(sizes[:i + 1])].view(shapes[i]).requires_grad_(True) for i in range(4)]
+            x0_dev = torch.from_numpy(np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in x0])).to(dev)
+            with torch.no_grad():
+                packed_in.copy_(x0_dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):               # warm-up outside the capture (lazy initialisations)
+                for _ in range(2):
+                    torch.autograd.grad(evaluate(*stat), stat)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                f_stat = evaluate(*stat)
+                g_stat = torch.autograd.grad(f_stat, stat)
+                packed_out = torch.cat([f_stat.detach().reshape(1)] + [gi.detach().reshape(-1) for gi in g_stat])
+        except Exception:                               # noqa: BLE001 -- e.g. capture-unsafe allocator state: eager path
+            graph = None
+
+    def pack_point(x):
+        return torch.from_numpy(np.concatenate([np.asarray(a, dtype=np.float64).ravel() for a in x]))
 
     def cost_grad(x):
+        if graph is not None:
+            with torch.no_grad():
+                packed_in.copy_(pack_point(x))
+            graph.replay()
+            out = packed_out.detach().cpu().numpy()
+            grads, at = [], 1
+            for size, shape in zip(sizes, shapes):
+                grads.append(out[at:at + size].reshape(shape).copy())
+                at += size
+            return float(out[0]), grads
         ts = to_device(x, requires_grad=True)
         with torch.enable_grad():
             f = evaluate(*ts)
             f.backward()
         return float(f.detach()), [t.grad.cpu().numpy() for t in ts]
+
+    def cost(x):
+        if graph is not None:
+            return cost_grad(x)[0]
+        with torch.no_grad():
+            return float(evaluate(*to_device(x)))
 
     def orthogonality(x):                                   # ||V^T W||_F and its gradient (zero at the feasible point)
         vtw = x[0].T @ w_host
@@ -311,5 +354,6 @@ def optimize_reconstruction_parameters_nested_spd(x_data, x_data_projected, proj
     c = torch.from_numpy(np.array(opt[1], dtype=np.float64))
     norm = torch.sigmoid(torch.from_numpy(np.array(opt[3], dtype=np.float64)))
     kmat = norm * torch.from_numpy(np.array(opt[2], dtype=np.float64)).view(d, m)
-    optimize_reconstruction_parameters_nested_spd.last_log = dict(log, start_cost=float(np.nanmin(vals)))
+    optimize_reconstruction_parameters_nested_spd.last_log = dict(log, start_cost=float(np.nanmin(vals)),
+                                                                  cuda_graph=graph is not None)
     return v, c, kmat
