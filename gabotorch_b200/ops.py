@@ -633,9 +633,42 @@ class TensorGP:
     def with_compute(self, compute):
         return self
 
+    #: evaluations of a fixed batch size are captured in a CUDA graph after this many eager calls (the lock-step solvers call
+    #: the evaluator hundreds of times with all restarts at once; one evaluation is ~30 small launches)
+    graph_after = 3
+
     def ei(self, x, want_grad=False):
-        from .kernel_utils import _SpdLogm
         x = to_dev64(x)
+        key = (int(x.shape[0]), bool(want_grad))
+        cache = self.__dict__.setdefault('_graphs', {})
+        entry = cache.get(key)
+        if entry is None:
+            entry = cache[key] = {'calls': 0, 'graph': None}
+        if entry['graph'] is None and entry['calls'] >= 0 and x.is_cuda and 2 <= key[0] <= 4096:
+            entry['calls'] += 1
+            if entry['calls'] > self.graph_after:
+                try:
+                    static_x = x.clone()
+                    side = torch.cuda.Stream(device=x.device)
+                    side.wait_stream(torch.cuda.current_stream(x.device))
+                    with torch.cuda.stream(side):
+                        self._ei_eager(static_x, want_grad)
+                    torch.cuda.current_stream(x.device).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        out = self._ei_eager(static_x, want_grad)
+                    entry.update(graph=graph, x=static_x, out=out)
+                except Exception:                       # noqa: BLE001 -- capture not possible here: stay eager
+                    entry['calls'] = -1
+        if entry['graph'] is not None:
+            entry['x'].copy_(x)
+            entry['graph'].replay()
+            out = entry['out']
+            return (out[0].clone(), out[1].clone()) if want_grad else out.clone()
+        return self._ei_eager(x, want_grad)
+
+    def _ei_eager(self, x, want_grad=False):
+        from .kernel_utils import _SpdLogm
         xs = x.clone().requires_grad_(True) if want_grad else x
         with torch.enable_grad() if want_grad else torch.no_grad():
             s = _SpdLogm.apply(xs) if self.use_log else xs
