@@ -172,8 +172,11 @@ struct PairCfg {
     static constexpr bool kPacked = (d <= 5);            // G for two problems fits the register file
 };
 
+#ifndef GABO_SPD_MINBLOCKS
+#define GABO_SPD_MINBLOCKS 1
+#endif
 template <int d, typename T, typename OutT, int KIND>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, GABO_SPD_MINBLOCKS)
     spd_ai_gram_kernel(const double* __restrict__ fac1, int64_t n1, const double* __restrict__ fac2, int64_t n2,
                        ExpParams kp, OutT* __restrict__ out, int64_t ld_out, TileMap map, int64_t tiles_total,
                        unsigned int* __restrict__ sched) {
