@@ -28,7 +28,10 @@ namespace {
 #endif
 constexpr int kRowGroups = GABO_NP_ROWGROUPS;       // 16-row groups per tile
 constexpr int kTileRows = 16 * kRowGroups;          // 32-row tiles, TWO CTAs per SM: while one CTA reduces and stores its
-constexpr int kCtasPerSm = (kRowGroups <= 2) ? 2 : 1;   // tile the other one feeds the tensor pipe (one 64-row CTA per SM
+#ifndef GABO_NP_CTAS
+#define GABO_NP_CTAS ((GABO_NP_ROWGROUPS <= 2) ? 2 : 1)
+#endif
+constexpr int kCtasPerSm = GABO_NP_CTAS;   // tile the other one feeds the tensor pipe (one 64-row CTA per SM
 constexpr int kStages = 3;                          // left the pipe idle during every epilogue: 0.73 -> see profiles/)
 constexpr int kMaxStages = 6;                 // ring depth limit (shared memory decides: 4 stages for SPD(20))
 constexpr int kSplitK = 4;                    // warps sharing a row group, each with a quarter of the k range
@@ -380,7 +383,7 @@ int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, fl
                8 * kMaxStages + 16;
     };
     int nstages = in_regs ? kMaxStages : kStages;
-    const size_t smem_cap = (kCtasPerSm == 2) ? 113 * 1024 + 512 : 227 * 1024;
+    const size_t smem_cap = (kCtasPerSm > 1) ? (227 * 1024) / kCtasPerSm - 512 + (kCtasPerSm == 2 ? 1024 : 0) : 227 * 1024;
     while (nstages > 2 && smem_for(nstages) > smem_cap) --nstages;
     const size_t smem = smem_for(nstages);
     GABO_REQUIRE(smem <= 227 * 1024, GABO_E_UNSUPPORTED,
