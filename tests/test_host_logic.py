@@ -955,3 +955,52 @@ def test_numpy_host_helpers_of_spd_utils():
     assert x.shape == (4, 4) and np.abs(x - x.T).max() < 1e-14 and lam.min() >= 0.5 - 1e-12 and lam.max() <= 3.0 + 1e-12
     man.rand = types.MethodType(ru.spd_sample, man)           # the binding of gabo_spd.py:102
     assert man.rand().shape == (4, 4)
+
+
+def test_tensor_gp_expected_improvement_host_logic(monkeypatch):
+    """ops.TensorGP (EI of the log-Euclidean latent GP of hd_gabo_spd.py as differentiable tensor code): values against a
+    plain fp64 restatement of botorch's analytic EI, Riemannian gradient against central differences.  Host run with the
+    logm kernels replaced by an eigh-based stand-in; the device run is tests/test_lockstep_gpu.py."""
+    from gabotorch_b200 import _lib, kernel_utils as ku, ops
+    from oracle import spd as ospd
+
+    class _Logm:
+        @staticmethod
+        def apply(m):
+            lam, q = torch.linalg.eigh(m)
+            return (q * torch.log(lam).unsqueeze(-2)) @ q.transpose(-1, -2)
+    monkeypatch.setattr(ku, '_SpdLogm', _Logm)
+    monkeypatch.setattr(ops, 'to_dev64', lambda x: torch.as_tensor(x, dtype=torch.float64))
+    monkeypatch.setattr(ops, 'spd_op', _OracleOps(None).spd_op)
+    rng = np.random.default_rng(6)
+    d, n, r = 3, 9, 4
+    xt = ospd.spd_sample(rng, n, d, max_cond=30.0)
+    y = rng.standard_normal(n)
+    xs = ospd.spd_sample(rng, r, d, max_cond=30.0)
+    scale, ls, noise, mean = 1.3, 1.7, 0.05, 0.1
+
+    def logm(m):
+        lam, q = np.linalg.eigh(m)
+        return (q * np.log(lam)) @ q.T
+    st = np.array([logm(m) for m in xt])
+    kk = lambda a, b: scale * math.exp(-np.sum((a - b + 1e-15) ** 2) / ls ** 2)   # noqa: E731
+    K = np.array([[kk(a, b) for b in st] for a in st]) + noise * np.eye(n)
+    kinv = np.linalg.inv(K)
+    gp = ops.TensorGP(d, torch.from_numpy(st), torch.from_numpy(kinv @ (y - mean)), torch.from_numpy(kinv), mean, scale,
+                      1.0 / ls ** 2, float(y.min()), use_log=True)
+
+    def ei_ref(x):
+        kx = np.array([kk(logm(x), b) for b in st])
+        mu = mean + kx @ kinv @ (y - mean)
+        s = math.sqrt(max(scale - kx @ kinv @ kx, 1e-9))
+        u = (y.min() - mu) / s
+        return s * (math.exp(-0.5 * u * u) / math.sqrt(2 * math.pi) + u * 0.5 * math.erfc(-u / math.sqrt(2)))
+    ei, grad = ops.ei_eval(gp, torch.from_numpy(xs), want_grad=True)
+    np.testing.assert_allclose(ei.numpy(), [ei_ref(x) for x in xs], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(ops.ei_eval(gp, torch.from_numpy(xs)).numpy(), ei.numpy(), rtol=0, atol=0)
+    xi = rng.standard_normal((d, d)); xi = 0.5 * (xi + xi.T)
+    for i in range(r):
+        fd = (ei_ref(xs[i] + 1e-6 * xi) - ei_ref(xs[i] - 1e-6 * xi)) / 2e-6
+        xinv = np.linalg.inv(xs[i])
+        assert abs(fd - np.trace(xinv @ grad[i].numpy() @ xinv @ xi)) <= 1e-5 * abs(fd) + 1e-10
+    assert gp.manifold == _lib.SPD and gp.with_compute(_lib.GABO_F64) is gp and gp.point_shape == (d, d)
