@@ -383,7 +383,8 @@ int launch_nt(const float* x, int64_t n, int dvh, int dvl, const float* pack, fl
                8 * kMaxStages + 16;
     };
     int nstages = in_regs ? kMaxStages : kStages;
-    const size_t smem_cap = (kCtasPerSm > 1) ? (227 * 1024) / kCtasPerSm - 512 + (kCtasPerSm == 2 ? 1024 : 0) : 227 * 1024;
+    // per-CTA budget that still lets kCtasPerSm CTAs share the 228 KB of an SM (1 KB per CTA is reserved by the system)
+    const size_t smem_cap = (kCtasPerSm == 2) ? 113 * 1024 + 512 : (kCtasPerSm > 2 ? (228 * 1024) / kCtasPerSm - 1024 : 227 * 1024);
     while (nstages > 2 && smem_for(nstages) > smem_cap) --nstages;
     const size_t smem = smem_for(nstages);
     GABO_REQUIRE(smem <= 227 * 1024, GABO_E_UNSUPPORTED,
